@@ -1,0 +1,16 @@
+"""Public names, following FinEtools' exports for the assembly hot path (src/FinEtools.jl:25-673, the subset on the path)."""
+from ._lib import FEGPUError, LIB_PATH  # noqa: F401
+from .assembly import (AbstractSysmatAssembler, GPUContext, SysmatAssemblerSparseGPU, assemble, expectedntriples,  # noqa: F401
+                       makematrix, setnomatrixresult, startassembly)
+from .datacache import DataCache  # noqa: F401
+from .femm import (CSys, DeforModelRed3D, FEMMBase, bilform_diffusion, bilform_dot, bilform_lin_elastic, innerproduct)  # noqa: F401
+from .fesets import (ETYPE, FESET_BY_NAME, FESetH8, FESetH20, FESetH27, FESetQ4, FESetT3, FESetT4, FESetT10)  # noqa: F401
+from .fields import (FENodeSet, NodalField, applyebc, gatherdofnums, gathersysvec, gathervalues_asmat, nalldofs, ndofs,  # noqa: F401
+                     nents, nfreedofs, numberdofs, setebc)
+from .integdomain import IntegDomain, integrationdata, otherdimensionunity  # noqa: F401
+from .integrule import GaussRule, TetRule, TriRule  # noqa: F401
+from .meshgen import (H8block, H8blockx, H8toH20, H8toH27, H20block, H27block, Q4block, Q4blockx, T3block, T3blockx,  # noqa: F401
+                      T4block, T4blockx, T4toT10, T10block, linearspace, meshboundary)
+from .partition import pointpartitioning, slab_owner  # noqa: F401
+
+__all__ = [n for n in dir() if not n.startswith("_")]

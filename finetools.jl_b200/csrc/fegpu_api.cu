@@ -1,0 +1,699 @@
+// C ABI of libfinegpu.so (include/fegpu.h): handles, uploads, the three bilinear forms, the generic assembler protocol,
+// result access.  No CPU fallback anywhere: every compute call ends in a kernel launch on the context's stream.
+#include <algorithm>
+#include <cstring>
+
+#include "fegpu_internal.h"
+
+static thread_local std::string g_last_error;
+
+int32_t fegpu_fail(fegpu_ctx *ctx, int32_t code, const std::string &msg) {
+  g_last_error = msg;
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+namespace {
+
+int nne_of(int et) {
+  switch (et) {
+    case FEGPU_T3: return 3; case FEGPU_Q4: return 4; case FEGPU_T4: return 4; case FEGPU_T10: return 10;
+    case FEGPU_H8: return 8; case FEGPU_H20: return 20; case FEGPU_H27: return 27;
+  }
+  return -1;
+}
+int mdim_of(int et) { return (et == FEGPU_T3 || et == FEGPU_Q4) ? 2 : 3; }
+
+__global__ void k_conn_convert(const int64_t *__restrict__ in, int32_t *__restrict__ out, int64_t n, int64_t nnodes, int *err) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t v = in[i];
+  if (v < 1 || v > nnodes) {
+    *err = 1;
+    v = 1;
+  }
+  out[i] = (int32_t)(v - 1);
+}
+
+// dofnums -> 0-based int32; range checks of assemble! (AssemblyModule.jl:268-273), only for nodes used by elements
+__global__ void k_dof_convert(const int64_t *__restrict__ in, int32_t *__restrict__ out, int64_t n, int64_t nnodes, int64_t row_nall,
+                              int64_t col_nall, const uint8_t *__restrict__ used, int *err, int32_t *seen) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t v = in[i];
+  const bool u = used[i % nnodes] != 0;
+  if (u) {
+    int code = 0;
+    if (v < 1) code = 1;
+    else if (v > col_nall) code = 2;
+    else if (v > row_nall) code = 4;
+    if (code) {
+      atomicCAS(err, 0, code);
+      v = 1;
+    } else if (v <= INT32_MAX) {
+      if (atomicAdd(&seen[v - 1], 1) > 0) err[1] = 1;  // two used (node, comp) slots share a dof number
+    }
+  } else if (v < 1 || v > INT32_MAX) {
+    v = 1;
+  }
+  out[i] = (int32_t)(v - 1);
+}
+
+__global__ void k_mark_used(const int32_t *__restrict__ conn, int64_t n, uint8_t *__restrict__ used) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) used[conn[i]] = 1;
+}
+
+__global__ void k_rowowned(const int32_t *__restrict__ owner, int64_t nnodes, int32_t rank, uint8_t *__restrict__ owned) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nnodes) owned[i] = (owner[i] == rank) ? 1 : 0;
+}
+
+__global__ void k_elem_active(const int32_t *__restrict__ conn, int64_t nelem, int nne, const uint8_t *__restrict__ owned,
+                              int32_t *__restrict__ flag) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nelem) return;
+  int f = 0;
+  for (int a = 0; a < nne; a++) f |= owned[conn[e * nne + a]];
+  flag[e] = f;
+}
+
+__global__ void k_compact(const int32_t *__restrict__ flag, const int64_t *__restrict__ pos, int64_t nelem, int32_t *__restrict__ list) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nelem && flag[e]) list[pos[e]] = (int32_t)e;
+}
+
+// ---- roofline micro-benchmarks
+__global__ void k_dfma_peak(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void k_copy(const double2 *__restrict__ in, double2 *__restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+int32_t finish(fegpu_ctx *ctx) {
+  if (!ctx->async) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return FEGPU_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char *fegpu_last_error(fegpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int32_t fegpu_create(fegpu_ctx **out, int32_t device) {
+  if (!out) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "ctx pointer is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fegpu_fail(nullptr, FEGPU_ERR_CUDA, std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "device index out of range");
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  CUDA_TRY(nullptr, cudaFree(0));
+  fegpu_ctx *ctx = new fegpu_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return FEGPU_OK;
+}
+
+int32_t fegpu_destroy(fegpu_ctx *ctx) {
+  if (!ctx) return FEGPU_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  delete ctx;
+  return FEGPU_OK;
+}
+
+int32_t fegpu_set_stream(fegpu_ctx *ctx, void *s) {
+  if (!ctx) return FEGPU_ERR_ARG;
+  ctx->stream = (cudaStream_t)s;
+  return FEGPU_OK;
+}
+int32_t fegpu_set_async(fegpu_ctx *ctx, int32_t on) {
+  if (!ctx) return FEGPU_ERR_ARG;
+  ctx->async = on != 0;
+  return FEGPU_OK;
+}
+int32_t fegpu_synchronize(fegpu_ctx *ctx) {
+  if (!ctx) return FEGPU_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return FEGPU_OK;
+}
+int64_t fegpu_launch_count(fegpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t fegpu_measure_peaks(fegpu_ctx *ctx, double *dfma_tflops, double *copy_gbs) {
+  if (!ctx) return FEGPU_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(ctx, cudaEventCreate(&e0));
+  CUDA_TRY(ctx, cudaEventCreate(&e1));
+  float ms = 0;
+  if (dfma_tflops) {
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 14;
+    double *d = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void **)&d, sizeof(double) * blocks * threads));
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+      CUDA_TRY(ctx, cudaEventRecord(e0, st));
+      k_dfma_peak<<<blocks, threads, 0, st>>>(d, iters);
+      ctx->launches++;
+      CUDA_TRY(ctx, cudaEventRecord(e1, st));
+      CUDA_TRY(ctx, cudaEventSynchronize(e1));
+      CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+      double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+      if (rep > 0) best = std::max(best, tf);
+    }
+    *dfma_tflops = best;
+    cudaFree(d);
+  }
+  if (copy_gbs) {
+    const int64_t n = (int64_t)1 << 26;  // double2: 1 GiB read + 1 GiB write
+    double2 *a = nullptr, *b = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void **)&a, sizeof(double2) * n));
+    CUDA_TRY(ctx, cudaMalloc((void **)&b, sizeof(double2) * n));
+    CUDA_TRY(ctx, cudaMemsetAsync(a, 0, sizeof(double2) * n, st));
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+      CUDA_TRY(ctx, cudaEventRecord(e0, st));
+      k_copy<<<ctx->sm_count * 16, 512, 0, st>>>(a, b, n);
+      ctx->launches++;
+      CUDA_TRY(ctx, cudaEventRecord(e1, st));
+      CUDA_TRY(ctx, cudaEventSynchronize(e1));
+      CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+      if (rep > 0) best = std::max(best, 2.0 * sizeof(double2) * n / (ms * 1e-3) / 1e9);
+    }
+    *copy_gbs = best;
+    cudaFree(a);
+    cudaFree(b);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return FEGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- mesh
+int32_t fegpu_mesh_upload(fegpu_ctx *ctx, int32_t etype, int64_t nelem, const int64_t *conn, int64_t nnodes, int32_t sdim,
+                          const double *xyz, fegpu_mesh **out) {
+  if (!ctx || !out) return fegpu_fail(ctx, FEGPU_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  const int nne = nne_of(etype);
+  if (nne < 0) return fegpu_fail(ctx, FEGPU_ERR_ARG, "unknown element type");
+  if (sdim < mdim_of(etype) || sdim > 3) return fegpu_fail(ctx, FEGPU_ERR_ARG, "space dimension does not fit the element manifold");
+  if (nelem < 0 || nnodes < 0 || nnodes >= INT32_MAX || nelem >= INT32_MAX) return fegpu_fail(ctx, FEGPU_ERR_ARG, "mesh too large for int32 ids");
+  if ((nelem > 0 && !conn) || (nnodes > 0 && !xyz)) return fegpu_fail(ctx, FEGPU_ERR_ARG, "NULL mesh arrays");
+  DeviceGuard g(ctx->device);
+  fegpu_mesh *m = new fegpu_mesh();
+  m->ctx = ctx; m->etype = etype; m->nne = nne; m->mdim = mdim_of(etype); m->sdim = sdim; m->nelem = nelem; m->nnodes = nnodes;
+  m->nactive = nelem;
+  cudaStream_t st = ctx->stream;
+  int64_t *d_c64 = nullptr;
+  int *d_err = nullptr;
+  auto fail = [&](int32_t code, const std::string &msg) {
+    cudaFree(d_c64); cudaFree(d_err);
+    fegpu_mesh_destroy(m);
+    return fegpu_fail(ctx, code, msg);
+  };
+  const size_t nc = (size_t)nelem * nne;
+  cudaError_t e;
+#define MT(expr) if ((e = (expr)) != cudaSuccess) return fail(FEGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e))
+  MT(cudaMalloc((void **)&m->d_conn, sizeof(int32_t) * std::max<size_t>(nc, 1)));
+  MT(cudaMalloc((void **)&m->d_xyz, sizeof(double) * std::max<size_t>((size_t)nnodes * sdim, 1)));
+  MT(cudaMalloc((void **)&d_c64, sizeof(int64_t) * std::max<size_t>(nc, 1)));
+  MT(cudaMalloc((void **)&d_err, sizeof(int)));
+  MT(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+  if (nc) MT(cudaMemcpyAsync(d_c64, conn, sizeof(int64_t) * nc, cudaMemcpyHostToDevice, st));
+  if (nnodes) MT(cudaMemcpyAsync(m->d_xyz, xyz, sizeof(double) * (size_t)nnodes * sdim, cudaMemcpyHostToDevice, st));
+  if (nc) {
+    k_conn_convert<<<grid_for((int64_t)nc, 256), 256, 0, st>>>(d_c64, m->d_conn, (int64_t)nc, nnodes, d_err);
+    ctx->launches++;
+  }
+  int h_err = 0;
+  MT(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MT(cudaStreamSynchronize(st));
+#undef MT
+  if (h_err) return fail(FEGPU_ERR_ARG, "connectivity refers to a node outside 1..nnodes");
+  cudaFree(d_c64);
+  cudaFree(d_err);
+  *out = m;
+  return FEGPU_OK;
+}
+
+int32_t fegpu_mesh_destroy(fegpu_mesh *m) {
+  if (!m) return FEGPU_OK;
+  DeviceGuard g(m->ctx->device);
+  cudaFree(m->d_conn); cudaFree(m->d_xyz); cudaFree(m->d_tab); cudaFree(m->d_w); cudaFree(m->d_elem_list); cudaFree(m->d_rowowned);
+  delete m;
+  return FEGPU_OK;
+}
+
+int32_t fegpu_geom_update(fegpu_mesh *m, const double *xyz) {
+  if (!m || !xyz) return fegpu_fail(m ? m->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  DeviceGuard g(m->ctx->device);
+  CUDA_TRY(m->ctx, cudaMemcpyAsync(m->d_xyz, xyz, sizeof(double) * (size_t)m->nnodes * m->sdim, cudaMemcpyHostToDevice, m->ctx->stream));
+  CUDA_TRY(m->ctx, cudaStreamSynchronize(m->ctx->stream));  // the host array may go away after return
+  return FEGPU_OK;
+}
+
+int32_t fegpu_rule_set(fegpu_mesh *m, int32_t npts, const double *Ns, const double *gradNpar, const double *w) {
+  if (!m || !Ns || !gradNpar || !w) return fegpu_fail(m ? m->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  fegpu_ctx *ctx = m->ctx;
+  if (npts < 1 || npts > FEGPU_MAX_NPTS || (int64_t)npts * m->nne * (1 + m->mdim) > FEGPU_TAB_DOUBLES)
+    return fegpu_fail(ctx, FEGPU_ERR_ARG, "quadrature rule too large for the on-chip tables");
+  DeviceGuard g(ctx->device);
+  const size_t nN = (size_t)npts * m->nne, nD = nN * m->mdim;
+  m->h_tab.assign(Ns, Ns + nN);
+  m->h_tab.insert(m->h_tab.end(), gradNpar, gradNpar + nD);
+  m->h_w.assign(w, w + npts);
+  cudaFree(m->d_tab);
+  cudaFree(m->d_w);
+  m->d_tab = nullptr;
+  m->d_w = nullptr;
+  CUDA_TRY(ctx, cudaMalloc((void **)&m->d_tab, sizeof(double) * (nN + nD)));
+  CUDA_TRY(ctx, cudaMalloc((void **)&m->d_w, sizeof(double) * npts));
+  CUDA_TRY(ctx, cudaMemcpyAsync(m->d_tab, m->h_tab.data(), sizeof(double) * (nN + nD), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(m->d_w, m->h_w.data(), sizeof(double) * npts, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  m->npts = npts;
+  return FEGPU_OK;
+}
+
+int32_t fegpu_partition_set(fegpu_mesh *m, const int32_t *node_owner, int32_t my_rank) {
+  if (!m) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL mesh");
+  fegpu_ctx *ctx = m->ctx;
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  m->topo_version++;
+  cudaFree(m->d_elem_list);
+  cudaFree(m->d_rowowned);
+  m->d_elem_list = nullptr;
+  m->d_rowowned = nullptr;
+  m->partitioned = false;
+  m->nactive = m->nelem;
+  if (!node_owner) return FEGPU_OK;
+  int32_t *d_owner = nullptr, *d_flag = nullptr;
+  int64_t *d_pos = nullptr;
+  auto cleanup = [&]() { cudaFree(d_owner); cudaFree(d_flag); cudaFree(d_pos); };
+  cudaError_t e;
+#define PT(expr) if ((e = (expr)) != cudaSuccess) { cleanup(); return fegpu_fail(ctx, FEGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e)); }
+  PT(cudaMalloc((void **)&d_owner, sizeof(int32_t) * std::max<int64_t>(m->nnodes, 1)));
+  PT(cudaMalloc((void **)&m->d_rowowned, std::max<int64_t>(m->nnodes, 1)));
+  PT(cudaMalloc((void **)&d_flag, sizeof(int32_t) * std::max<int64_t>(m->nelem, 1)));
+  PT(cudaMalloc((void **)&d_pos, sizeof(int64_t) * (m->nelem + 1)));
+  PT(cudaMemcpyAsync(d_owner, node_owner, sizeof(int32_t) * m->nnodes, cudaMemcpyHostToDevice, st));
+  if (m->nnodes) k_rowowned<<<grid_for(m->nnodes, 256), 256, 0, st>>>(d_owner, m->nnodes, my_rank, m->d_rowowned);
+  if (m->nelem) k_elem_active<<<grid_for(m->nelem, 256), 256, 0, st>>>(m->d_conn, m->nelem, m->nne, m->d_rowowned, d_flag);
+  ctx->launches += 2;
+  int64_t nact = 0;
+  int32_t s = fe_exclusive_scan_i32_to_i64(ctx, d_flag, d_pos, m->nelem, 0, true, &nact);
+  if (s != FEGPU_OK) { cleanup(); return s; }
+  PT(cudaMalloc((void **)&m->d_elem_list, sizeof(int32_t) * std::max<int64_t>(nact, 1)));
+  if (m->nelem) {
+    k_compact<<<grid_for(m->nelem, 256), 256, 0, st>>>(d_flag, d_pos, m->nelem, m->d_elem_list);
+    ctx->launches++;
+  }
+  PT(cudaStreamSynchronize(st));
+#undef PT
+  cleanup();
+  m->nactive = nact;
+  m->partitioned = true;
+  return FEGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- dof map
+int32_t fegpu_dofmap_upload(fegpu_ctx *ctx, fegpu_mesh *mesh, int32_t ndn, const int64_t *dofnums, int64_t row_nall, int64_t col_nall,
+                            fegpu_dofmap **out) {
+  if (!ctx || !mesh || !dofnums || !out) return fegpu_fail(ctx, FEGPU_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  if (ndn < 1 || ndn > 6) return fegpu_fail(ctx, FEGPU_ERR_ARG, "dofs per node must be in 1..6");
+  if (row_nall < 0 || col_nall < 0 || row_nall >= INT32_MAX || col_nall >= INT32_MAX)
+    return fegpu_fail(ctx, FEGPU_ERR_ARG, "matrix dimension outside int32 range");
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  fegpu_dofmap *d = new fegpu_dofmap();
+  d->ctx = ctx; d->mesh = mesh; d->ndn = ndn; d->row_nall = row_nall; d->col_nall = col_nall;
+  const int64_t n = mesh->nnodes * ndn;
+  int64_t *d64 = nullptr;
+  uint8_t *d_used = nullptr;
+  int *d_err = nullptr;
+  int32_t *d_seen = nullptr;
+  auto fail = [&](int32_t code, const std::string &msg) {
+    cudaFree(d64); cudaFree(d_used); cudaFree(d_err); cudaFree(d_seen);
+    fegpu_dofmap_destroy(d);
+    return fegpu_fail(ctx, code, msg);
+  };
+  cudaError_t e;
+#define DT(expr) if ((e = (expr)) != cudaSuccess) return fail(FEGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e))
+  const int64_t nseen = std::max<int64_t>(std::max(row_nall, col_nall), 1);
+  DT(cudaMalloc((void **)&d->d_dof, sizeof(int32_t) * std::max<int64_t>(n, 1)));
+  DT(cudaMalloc((void **)&d64, sizeof(int64_t) * std::max<int64_t>(n, 1)));
+  DT(cudaMalloc((void **)&d_used, std::max<int64_t>(mesh->nnodes, 1)));
+  DT(cudaMalloc((void **)&d_err, sizeof(int) * 2));
+  DT(cudaMalloc((void **)&d_seen, sizeof(int32_t) * nseen));
+  DT(cudaMemsetAsync(d_used, 0, std::max<int64_t>(mesh->nnodes, 1), st));
+  DT(cudaMemsetAsync(d_err, 0, sizeof(int) * 2, st));
+  DT(cudaMemsetAsync(d_seen, 0, sizeof(int32_t) * nseen, st));
+  if (n) DT(cudaMemcpyAsync(d64, dofnums, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+  const int64_t nc = mesh->nelem * mesh->nne;
+  if (nc) {
+    k_mark_used<<<grid_for(nc, 256), 256, 0, st>>>(mesh->d_conn, nc, d_used);
+    ctx->launches++;
+  }
+  if (n) {
+    k_dof_convert<<<grid_for(n, 256), 256, 0, st>>>(d64, d->d_dof, n, mesh->nnodes, row_nall, col_nall, d_used, d_err, d_seen);
+    ctx->launches++;
+  }
+  int h_err[2] = {0, 0};
+  DT(cudaMemcpyAsync(h_err, d_err, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+  DT(cudaStreamSynchronize(st));
+#undef DT
+  if (h_err[0]) {
+    static const char *msgs[] = {"", "Column degree of freedom < 1", "Column degree of freedom > size", "Row degree of freedom < 1",
+                                 "Row degree of freedom > size"};
+    return fail(FEGPU_ERR_COL_LT1 - (h_err[0] - 1), msgs[h_err[0]]);
+  }
+  d->injective = (h_err[1] == 0);
+  cudaFree(d64); cudaFree(d_used); cudaFree(d_err); cudaFree(d_seen);
+  *out = d;
+  return FEGPU_OK;
+}
+
+int32_t fegpu_dofmap_destroy(fegpu_dofmap *d) {
+  if (!d) return FEGPU_OK;
+  DeviceGuard g(d->ctx->device);
+  cudaFree(d->d_dof);
+  if (d->pat) fe_pattern_free(d->pat);
+  delete d;
+  return FEGPU_OK;
+}
+
+int32_t fegpu_pattern_invalidate(fegpu_dofmap *d) {
+  if (!d) return FEGPU_ERR_ARG;
+  DeviceGuard g(d->ctx->device);
+  if (d->pat) fe_pattern_free(d->pat);
+  d->pat = nullptr;
+  d->pat_topo_version = 0;
+  return FEGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- assembler
+int32_t fegpu_asm_create(fegpu_ctx *ctx, fegpu_asm **out) {
+  if (!ctx || !out) return fegpu_fail(ctx, FEGPU_ERR_ARG, "NULL argument");
+  DeviceGuard g(ctx->device);
+  fegpu_asm *a = new fegpu_asm();
+  a->ctx = ctx;
+  for (auto &ev : a->ev) CUDA_TRY(ctx, cudaEventCreate(&ev));
+  *out = a;
+  return FEGPU_OK;
+}
+
+int32_t fegpu_asm_destroy(fegpu_asm *a) {
+  if (!a) return FEGPU_OK;
+  DeviceGuard g(a->ctx->device);
+  cudaFree(a->d_V); cudaFree(a->d_nzval); cudaFree(a->own_colptr); cudaFree(a->own_rowval);
+  for (auto &ev : a->ev)
+    if (ev) cudaEventDestroy(ev);
+  delete a;
+  return FEGPU_OK;
+}
+
+static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &fa, fegpu_asm *as) {
+  if (!mesh || !dm || !as) return fegpu_fail(mesh ? mesh->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  fegpu_ctx *ctx = mesh->ctx;
+  if (dm->mesh != mesh || as->ctx != ctx || dm->ctx != ctx) return fegpu_fail(ctx, FEGPU_ERR_ARG, "handles belong to different meshes / contexts");
+  if (dm->ndn != fa.ndn) return fegpu_fail(ctx, FEGPU_ERR_ARG, "Wrong size of matrix: dofs per node of the field do not fit the form");
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int EM = mesh->nne * fa.ndn;
+  const int64_t ntrip = mesh->nactive * (int64_t)EM * EM;
+  FE_TRY(fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(ntrip, 1)));
+  as->V_n = ntrip;
+  as->last_EM = EM;
+  as->have_result = false;
+  as->started = false;
+  CUDA_TRY(ctx, cudaEventRecord(as->ev[0], st));
+  FE_TRY(fe_integrate(mesh, fa, as->d_V));
+  CUDA_TRY(ctx, cudaEventRecord(as->ev[1], st));
+  bool fast = fe_pattern_usable(dm);
+  as->pattern_cached = false;
+  if (fast) {
+    if (!dm->pat || dm->pat_topo_version != mesh->topo_version) {
+      FE_TRY(fe_pattern_build(dm));
+      fast = fe_pattern_usable(dm) && dm->pat;  // the build may discover a degenerate mesh
+    } else {
+      as->pattern_cached = true;
+    }
+  }
+  CUDA_TRY(ctx, cudaEventRecord(as->ev[2], st));
+  if (fast) {
+    const int64_t nnz = fe_pattern_nnz(dm->pat);
+    FE_TRY(fe_asm_reserve(as, &as->d_nzval, &as->nz_cap, (size_t)std::max<int64_t>(nnz, 1)));
+    FE_TRY(fe_gather(dm, as->d_V, as->d_nzval));
+    as->nnz = nnz;
+    as->nrows = dm->row_nall;
+    as->ncols = dm->col_nall;
+    as->d_colptr = fe_pattern_colptr(dm->pat);
+    as->d_rowval = fe_pattern_rowval(dm->pat);
+  } else {
+    if (mesh->partitioned) return fegpu_fail(ctx, FEGPU_ERR_ARG, "row-block partitioning needs an injective dof map and non-degenerate elements");
+    int64_t *dI = nullptr, *dJ = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void **)&dI, sizeof(int64_t) * std::max<int64_t>(ntrip, 1)));
+    cudaError_t e = cudaMalloc((void **)&dJ, sizeof(int64_t) * std::max<int64_t>(ntrip, 1));
+    if (e != cudaSuccess) { cudaFree(dI); return fegpu_fail(ctx, FEGPU_ERR_CUDA, cudaGetErrorString(e)); }
+    int32_t s = fe_emit_ij(dm, dI, dJ);
+    if (s == FEGPU_OK) s = fe_coo_to_csc(as, ntrip, dI, dJ, as->d_V, dm->row_nall, dm->col_nall);
+    cudaFree(dI);
+    cudaFree(dJ);
+    FE_TRY(s);
+  }
+  CUDA_TRY(ctx, cudaEventRecord(as->ev[3], st));
+  as->ev_valid = true;
+  as->have_result = true;
+  return finish(ctx);
+}
+
+int32_t fegpu_bilform_diffusion(fegpu_mesh *mesh, fegpu_dofmap *dm, int32_t kappa_kind, const double *kappa, fegpu_asm *as) {
+  if (!mesh || !kappa) return fegpu_fail(mesh ? mesh->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  if (mesh->sdim != mesh->mdim) return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "bilform_diffusion needs sdim == manifold dimension");
+  FormArgs fa;
+  std::memset(&fa, 0, sizeof(fa));
+  fa.form = (kappa_kind == 0) ? FORM_DIFF_ISO : FORM_DIFF_GEN;
+  fa.ndn = 1;
+  const int nk = (kappa_kind == 0) ? 1 : mesh->mdim * mesh->mdim;
+  for (int i = 0; i < nk; i++) fa.coef[i] = kappa[i];
+  fa.m = 3;
+  fa.otherdim = 1.0;
+  return run_bilform(mesh, dm, fa, as);
+}
+
+int32_t fegpu_bilform_lin_elastic(fegpu_mesh *mesh, fegpu_dofmap *dm, const double *C, fegpu_asm *as) {
+  if (!mesh || !C) return fegpu_fail(mesh ? mesh->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  if (mesh->mdim != 3 || mesh->sdim != 3) return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "bilform_lin_elastic (DeforModelRed3D) needs 3-manifold elements in 3-D");
+  FormArgs fa;
+  std::memset(&fa, 0, sizeof(fa));
+  fa.form = FORM_ELASTIC;
+  fa.ndn = 3;
+  for (int i = 0; i < 36; i++) fa.coef[i] = C[i];
+  fa.m = 3;
+  fa.otherdim = 1.0;
+  return run_bilform(mesh, dm, fa, as);
+}
+
+int32_t fegpu_bilform_dot(fegpu_mesh *mesh, fegpu_dofmap *dm, const double *c, int32_t m, double otherdim, fegpu_asm *as) {
+  if (!mesh || !dm || !c) return fegpu_fail(mesh ? mesh->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  if (mesh->mdim == 3 && m != 3) return fegpu_fail(mesh->ctx, FEGPU_ERR_MANIFOLD, "That is the only acceptable option here.");
+  if (mesh->mdim == 2 && (m < 2 || m > 3)) return fegpu_fail(mesh->ctx, FEGPU_ERR_MANIFOLD, "Those are the only acceptable options here.");
+  if (dm->ndn > 3) return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "bilform_dot: up to 3 dofs per node");
+  FormArgs fa;
+  std::memset(&fa, 0, sizeof(fa));
+  fa.form = FORM_DOT;
+  fa.ndn = dm->ndn;
+  for (int i = 0; i < dm->ndn * dm->ndn; i++) fa.coef[i] = c[i];
+  fa.m = m;
+  fa.otherdim = otherdim;
+  return run_bilform(mesh, dm, fa, as);
+}
+
+// ---- generic protocol
+int32_t fegpu_startassembly(fegpu_asm *as, int64_t nr, int64_t nc, int64_t nmats, int64_t row_nall, int64_t col_nall) {
+  if (!as) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL assembler");
+  if (nr < 0 || nc < 0 || nmats < 0 || row_nall < 0 || col_nall < 0) return fegpu_fail(as->ctx, FEGPU_ERR_ARG, "negative size");
+  // like the reference (AssemblyModule.jl:221-229) sizes are only taken when no assembly is in flight
+  if (!as->started) {
+    as->hI.clear(); as->hJ.clear(); as->hV.clear();
+    const size_t expect = (size_t)(nr * nc * nmats);  // expectedntriples, :54-59
+    as->hI.reserve(expect); as->hJ.reserve(expect); as->hV.reserve(expect);
+    as->g_row_nall = row_nall;
+    as->g_col_nall = col_nall;
+    as->started = true;
+  }
+  return FEGPU_OK;
+}
+
+int32_t fegpu_assemble(fegpu_asm *as, const double *mat, const int64_t *dr, int64_t nrows, const int64_t *dc, int64_t ncols) {
+  if (!as || !mat || !dr || !dc) return fegpu_fail(as ? as->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  if (!as->started) return fegpu_fail(as->ctx, FEGPU_ERR_STATE, "assemble! before startassembly!");
+  for (int64_t j = 0; j < ncols; j++) {
+    const int64_t dj = dc[j];
+    if (dj < 1) return fegpu_fail(as->ctx, FEGPU_ERR_COL_LT1, "Column degree of freedom < 1");
+    if (dj > as->g_col_nall) return fegpu_fail(as->ctx, FEGPU_ERR_COL_GT, "Column degree of freedom > size");
+    for (int64_t i = 0; i < nrows; i++) {
+      const int64_t di = dr[i];
+      if (di < 1) return fegpu_fail(as->ctx, FEGPU_ERR_ROW_LT1, "Row degree of freedom < 1");
+      if (di > as->g_row_nall) return fegpu_fail(as->ctx, FEGPU_ERR_ROW_GT, "Row degree of freedom > size");
+      as->hV.push_back(mat[i + nrows * j]);
+      as->hI.push_back(di);
+      as->hJ.push_back(dj);
+    }
+  }
+  return FEGPU_OK;
+}
+
+int32_t fegpu_triplets_append(fegpu_asm *as, int64_t n, const int64_t *I, const int64_t *J, const double *V) {
+  if (!as || (n > 0 && (!I || !J || !V))) return fegpu_fail(as ? as->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  if (!as->started) return fegpu_fail(as->ctx, FEGPU_ERR_STATE, "triplets before startassembly!");
+  as->hI.insert(as->hI.end(), I, I + n);
+  as->hJ.insert(as->hJ.end(), J, J + n);
+  as->hV.insert(as->hV.end(), V, V + n);
+  return FEGPU_OK;
+}
+
+int32_t fegpu_makematrix(fegpu_asm *as) {
+  if (!as) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL assembler");
+  fegpu_ctx *ctx = as->ctx;
+  if (!as->started) return fegpu_fail(ctx, FEGPU_ERR_STATE, "makematrix! without startassembly!");
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int64_t n = (int64_t)as->hV.size();
+  int64_t *dI = nullptr, *dJ = nullptr;
+  cudaError_t e;
+  auto cleanup = [&]() { cudaFree(dI); cudaFree(dJ); };
+#define GT(expr) if ((e = (expr)) != cudaSuccess) { cleanup(); return fegpu_fail(ctx, FEGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e)); }
+  GT(cudaMalloc((void **)&dI, sizeof(int64_t) * std::max<int64_t>(n, 1)));
+  GT(cudaMalloc((void **)&dJ, sizeof(int64_t) * std::max<int64_t>(n, 1)));
+  int32_t s = fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(n, 1));
+  if (s != FEGPU_OK) { cleanup(); return s; }
+  GT(cudaEventRecord(as->ev[0], st));
+  if (n) {
+    GT(cudaMemcpyAsync(dI, as->hI.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+    GT(cudaMemcpyAsync(dJ, as->hJ.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+    GT(cudaMemcpyAsync(as->d_V, as->hV.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  }
+  GT(cudaEventRecord(as->ev[1], st));
+  GT(cudaEventRecord(as->ev[2], st));
+  s = fe_coo_to_csc(as, n, dI, dJ, as->d_V, as->g_row_nall, as->g_col_nall);
+  cleanup();
+  FE_TRY(s);
+  CUDA_TRY(ctx, cudaEventRecord(as->ev[3], st));
+#undef GT
+  as->ev_valid = true;
+  as->have_result = true;
+  as->pattern_cached = false;
+  as->started = false;  // "_buffer_pointer = 1": ready for the next startassembly!  (AssemblyModule.jl:327)
+  as->V_n = 0;
+  return finish(ctx);
+}
+
+// ---- results
+int32_t fegpu_makematrix_sizes(fegpu_asm *as, int64_t *nrows, int64_t *ncols, int64_t *nnz) {
+  if (!as) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL assembler");
+  if (!as->have_result) return fegpu_fail(as->ctx, FEGPU_ERR_STATE, "no assembled matrix");
+  if (nrows) *nrows = as->nrows;
+  if (ncols) *ncols = as->ncols;
+  if (nnz) *nnz = as->nnz;
+  return FEGPU_OK;
+}
+
+int32_t fegpu_makematrix_copy(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *nzval) {
+  if (!as) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL assembler");
+  fegpu_ctx *ctx = as->ctx;
+  if (!as->have_result) return fegpu_fail(ctx, FEGPU_ERR_STATE, "no assembled matrix");
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  if (colptr) CUDA_TRY(ctx, cudaMemcpyAsync(colptr, as->d_colptr, sizeof(int64_t) * (as->ncols + 1), cudaMemcpyDeviceToHost, st));
+  if (rowval && as->nnz) CUDA_TRY(ctx, cudaMemcpyAsync(rowval, as->d_rowval, sizeof(int64_t) * as->nnz, cudaMemcpyDeviceToHost, st));
+  if (nzval && as->nnz) CUDA_TRY(ctx, cudaMemcpyAsync(nzval, as->d_nzval, sizeof(double) * as->nnz, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return FEGPU_OK;
+}
+
+int32_t fegpu_makematrix_copy_values(fegpu_asm *as, double *nzval) { return fegpu_makematrix_copy(as, nullptr, nullptr, nzval); }
+
+int32_t fegpu_makematrix_device(fegpu_asm *as, const int64_t **c, const int64_t **r, const double **v) {
+  if (!as) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL assembler");
+  if (!as->have_result) return fegpu_fail(as->ctx, FEGPU_ERR_STATE, "no assembled matrix");
+  if (c) *c = as->d_colptr;
+  if (r) *r = as->d_rowval;
+  if (v) *v = as->d_nzval;
+  return FEGPU_OK;
+}
+
+int32_t fegpu_coo_copy(fegpu_asm *as, fegpu_mesh *mesh, fegpu_dofmap *dm, int64_t *I, int64_t *J, double *V) {
+  if (!as || !mesh || !dm) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL argument");
+  fegpu_ctx *ctx = as->ctx;
+  const int EM = mesh->nne * dm->ndn;
+  const int64_t n = mesh->nactive * (int64_t)EM * EM;
+  if (as->V_n != n || as->last_EM != EM) return fegpu_fail(ctx, FEGPU_ERR_STATE, "assembler does not hold this mesh's element matrices");
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  if (n == 0) return FEGPU_OK;
+  if (I || J) {
+    int64_t *dI = nullptr, *dJ = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void **)&dI, sizeof(int64_t) * n));
+    cudaError_t e = cudaMalloc((void **)&dJ, sizeof(int64_t) * n);
+    if (e != cudaSuccess) { cudaFree(dI); return fegpu_fail(ctx, FEGPU_ERR_CUDA, cudaGetErrorString(e)); }
+    int32_t s = fe_emit_ij(dm, dI, dJ);
+    if (s == FEGPU_OK && I && cudaMemcpyAsync(I, dI, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st) != cudaSuccess) s = FEGPU_ERR_CUDA;
+    if (s == FEGPU_OK && J && cudaMemcpyAsync(J, dJ, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st) != cudaSuccess) s = FEGPU_ERR_CUDA;
+    cudaStreamSynchronize(st);
+    cudaFree(dI);
+    cudaFree(dJ);
+    FE_TRY(s);
+  }
+  if (V) CUDA_TRY(ctx, cudaMemcpyAsync(V, as->d_V, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return FEGPU_OK;
+}
+
+int32_t fegpu_last_timings(fegpu_asm *as, double ms[4]) {
+  if (!as || !ms) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL argument");
+  if (!as->ev_valid) return fegpu_fail(as->ctx, FEGPU_ERR_STATE, "no timed call yet");
+  DeviceGuard g(as->ctx->device);
+  CUDA_TRY(as->ctx, cudaEventSynchronize(as->ev[3]));
+  float t;
+  for (int i = 0; i < 3; i++) {
+    CUDA_TRY(as->ctx, cudaEventElapsedTime(&t, as->ev[i], as->ev[i + 1]));
+    ms[i] = t;
+  }
+  CUDA_TRY(as->ctx, cudaEventElapsedTime(&t, as->ev[0], as->ev[3]));
+  ms[3] = t;
+  return FEGPU_OK;
+}
+
+int32_t fegpu_pattern_was_cached(fegpu_asm *as) { return (as && as->pattern_cached) ? 1 : 0; }
+
+}  // extern "C"

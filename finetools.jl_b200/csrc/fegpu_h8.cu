@@ -1,0 +1,322 @@
+// Specialised H8 kernels (the benchmark configurations C1/C2/C4 of BASELINE.json).
+//
+//  k_h8_diffusion : thread per element.  Coordinates, Jacobian, gradients and the 36-entry upper triangle live in
+//                   registers; the quadrature tables sit in __constant__ memory (uniform operands of the DFMAs).
+//  k_h8_elastic   : 32 elements per CTA, 4 warps.  Phase A: thread (element, 2 quadrature points) computes Jacobian,
+//                   inverse and the 8 nodal gradients into shared memory (element index fastest => conflict free).
+//                   Phase B: warp t owns the node-column pair (t, 7-t) of the 8x8 grid of 3x3 blocks -- exactly 9 upper
+//                   blocks for every t, so no lane divergence -- and lane = element.  D*B_b (DB, add_btdb_ut_only!
+//                   MatrixUtilityModule.jl:198-206) is formed once per column node and point and reused by its blocks.
+//                   The 24x24 matrix is staged through shared memory and written with coalesced 128-bit stores in the
+//                   reference's emission order.
+// Only GaussRule(3,2) (8 points) takes these paths; other rules use the generic kernel.
+#include "fegpu_internal.h"
+
+namespace {
+
+__constant__ double c_dN[8 * 3 * 8];  // [point][dim][node]
+__constant__ double c_w[8];
+__constant__ double c_coef[36];
+
+struct H8Params {
+  const int32_t *conn;
+  const double *xyz;
+  int64_t nnodes;
+  const int32_t *elem_list;
+  int64_t nactive;
+  double *V;
+};
+
+__device__ __forceinline__ void inv3(const double *J, double *inv, double &det) {
+#define R(i, j) J[(i - 1) + 3 * (j - 1)]
+  det = R(1, 1) * (R(2, 2) * R(3, 3) - R(3, 2) * R(2, 3)) - R(1, 2) * (R(2, 1) * R(3, 3) - R(2, 3) * R(3, 1)) +
+        R(1, 3) * (R(2, 1) * R(3, 2) - R(2, 2) * R(3, 1));
+  const double invdet = 1.0 / det;
+  inv[0] = (R(2, 2) * R(3, 3) - R(3, 2) * R(2, 3)) * invdet;
+  inv[3] = -(R(1, 2) * R(3, 3) - R(1, 3) * R(3, 2)) * invdet;
+  inv[6] = (R(1, 2) * R(2, 3) - R(1, 3) * R(2, 2)) * invdet;
+  inv[1] = -(R(2, 1) * R(3, 3) - R(2, 3) * R(3, 1)) * invdet;
+  inv[4] = (R(1, 1) * R(3, 3) - R(1, 3) * R(3, 1)) * invdet;
+  inv[7] = -(R(1, 1) * R(2, 3) - R(2, 1) * R(1, 3)) * invdet;
+  inv[2] = (R(2, 1) * R(3, 2) - R(3, 1) * R(2, 2)) * invdet;
+  inv[5] = -(R(1, 1) * R(3, 2) - R(3, 1) * R(1, 2)) * invdet;
+  inv[8] = (R(1, 1) * R(2, 2) - R(2, 1) * R(1, 2)) * invdet;
+#undef R
+}
+
+template <bool GENERAL>
+__global__ void __launch_bounds__(128) k_h8_diffusion(const H8Params P) {
+  const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= P.nactive) return;
+  const int64_t e = P.elem_list ? P.elem_list[slot] : slot;
+  int nd[8];
+  {
+    const int4 *c4 = reinterpret_cast<const int4 *>(P.conn + e * 8);
+    int4 a = __ldg(c4), b = __ldg(c4 + 1);
+    nd[0] = a.x; nd[1] = a.y; nd[2] = a.z; nd[3] = a.w; nd[4] = b.x; nd[5] = b.y; nd[6] = b.z; nd[7] = b.w;
+  }
+  double X[8][3];
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int s = 0; s < 3; s++) X[a][s] = __ldg(P.xyz + (int64_t)s * P.nnodes + nd[a]);
+
+  double acc[36];
+#pragma unroll
+  for (int i = 0; i < 36; i++) acc[i] = 0.0;
+
+#pragma unroll 1
+  for (int j = 0; j < 8; j++) {
+    const double *dN = c_dN + j * 24;
+    double J[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) J[i] = 0.0;
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+      for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int s = 0; s < 3; s++) J[s + 3 * d] += X[a][s] * dN[d * 8 + a];
+    double inv[9], det;
+    inv3(J, inv, det);
+    const double Jw = det * c_w[j];
+    double G[8][3];
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) G[a][c] = dN[a] * inv[0 + 3 * c] + dN[8 + a] * inv[1 + 3 * c] + dN[16 + a] * inv[2 + 3 * c];
+    if (GENERAL) {
+      // kG[px][nx] = Jw * sum_q kappa[px,q] G[nx][q]   (add_gkgt_ut_only!, MatrixUtilityModule.jl:134-142)
+#pragma unroll
+      for (int nx = 0; nx < 8; nx++) {
+        double kg[3];
+#pragma unroll
+        for (int mx = 0; mx < 3; mx++) {
+          double a = 0.0;
+#pragma unroll
+          for (int px = 0; px < 3; px++) a += c_coef[mx + 3 * px] * G[nx][px];
+          kg[mx] = Jw * a;
+        }
+#pragma unroll
+        for (int mx = 0; mx <= nx; mx++) {
+          double a = 0.0;
+#pragma unroll
+          for (int px = 0; px < 3; px++) a += G[mx][px] * kg[px];
+          acc[nx * (nx + 1) / 2 + mx] += a;
+        }
+      }
+    } else {
+      const double mult = c_coef[0] * det * c_w[j];  // (c * Jac * w[j])  FEMMBaseModule.jl:1528
+#pragma unroll
+      for (int nx = 0; nx < 8; nx++)
+#pragma unroll
+        for (int px = 0; px < 3; px++) {
+          const double a = mult * G[nx][px];
+#pragma unroll
+          for (int mx = 0; mx <= nx; mx++) acc[nx * (nx + 1) / 2 + mx] += G[mx][px] * a;
+        }
+    }
+  }
+  // complete_lt! + emission order: V[slot][c*8 + r]
+  double2 *out = reinterpret_cast<double2 *>(P.V + slot * 64);
+#pragma unroll
+  for (int c = 0; c < 8; c++)
+#pragma unroll
+    for (int r = 0; r < 8; r += 2) {
+      const int r0 = r, r1 = r + 1;
+      const double v0 = (r0 <= c) ? acc[c * (c + 1) / 2 + r0] : acc[r0 * (r0 + 1) / 2 + c];
+      const double v1 = (r1 <= c) ? acc[c * (c + 1) / 2 + r1] : acc[r1 * (r1 + 1) / 2 + c];
+      out[(c * 8 + r) >> 1] = make_double2(v0, v1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ elasticity
+constexpr int EL_EPB = 32;                 // elements per block
+constexpr int EL_GSTRIDE = 25;             // doubles per (element, point): 24 gradients + Jw
+// shared: G [8 pts][25][32 elems] doubles = 51200 B; staging for 16 elements: 16*576*8 = 73728 B (aliases G)
+constexpr int EL_SMEM_BYTES = 16 * 578 * 8;
+
+__device__ __forceinline__ void db_col(const double *g, double Jw, double DB[18]) {
+  // DB[:, j] = Jw * D * B_b[:, j], B_b column j has 3 non-zeros (DeforModelRedModule.jl:463-468, Rm = I)
+  // comp x: rows 0(g0) 3(g1) 4(g2); comp y: rows 1(g1) 3(g0) 5(g2); comp z: rows 2(g2) 4(g0) 5(g1)
+#pragma unroll
+  for (int mx = 0; mx < 6; mx++) {
+    DB[mx] = Jw * (c_coef[mx + 6 * 0] * g[0] + c_coef[mx + 6 * 3] * g[1] + c_coef[mx + 6 * 4] * g[2]);
+    DB[6 + mx] = Jw * (c_coef[mx + 6 * 1] * g[1] + c_coef[mx + 6 * 3] * g[0] + c_coef[mx + 6 * 5] * g[2]);
+    DB[12 + mx] = Jw * (c_coef[mx + 6 * 2] * g[2] + c_coef[mx + 6 * 4] * g[0] + c_coef[mx + 6 * 5] * g[1]);
+  }
+}
+
+__device__ __forceinline__ void block_acc(double *k9, const double *ga, const double DB[18]) {
+  // k9[i + 3*j] += B_a[:, i] . DB[:, j]   (rows ascending, as add_btdb_ut_only! sums px = 1..6 skipping the zeros)
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const double *d = DB + 6 * j;
+    k9[0 + 3 * j] += ga[0] * d[0] + ga[1] * d[3] + ga[2] * d[4];
+    k9[1 + 3 * j] += ga[1] * d[1] + ga[0] * d[3] + ga[2] * d[5];
+    k9[2 + 3 * j] += ga[2] * d[2] + ga[0] * d[4] + ga[1] * d[5];
+  }
+}
+
+constexpr int EL_MSTRIDE = 578;           // staged element-matrix stride (doubles): 576 + pad against bank conflicts
+
+// Phase B + staging for the warp owning column nodes B1 = T and B2 = 7 - T.  Everything indexed by T is static.
+// Warps run different instantiations of phase B, so the CTA-wide barriers inside it are spelled as a named
+// barrier (id 1, 128 threads): arrival is counted per barrier id, not per program counter.
+__device__ __forceinline__ void block_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int T>
+__device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, const int64_t slot0, const H8Params &P) {
+  constexpr int B1 = T, B2 = 7 - T;
+  constexpr int NB2 = 8 - T;  // blocks (a = 0..7-T, B2); then blocks (a = 0..T, B1): 9 in total
+  double K[9][9];
+#pragma unroll
+  for (int s = 0; s < 9; s++)
+#pragma unroll
+    for (int i = 0; i < 9; i++) K[s][i] = 0.0;
+#pragma unroll 1
+  for (int j = 0; j < 8; j++) {
+    const double *g = sm + (size_t)j * EL_GSTRIDE * EL_EPB + lane;
+    const double Jw = g[24 * EL_EPB];
+    double gb[3], DB[18];
+    gb[0] = g[(B2 * 3 + 0) * EL_EPB]; gb[1] = g[(B2 * 3 + 1) * EL_EPB]; gb[2] = g[(B2 * 3 + 2) * EL_EPB];
+    db_col(gb, Jw, DB);
+#pragma unroll
+    for (int a = 0; a < NB2; a++) {
+      double ga[3];
+      ga[0] = g[(a * 3 + 0) * EL_EPB]; ga[1] = g[(a * 3 + 1) * EL_EPB]; ga[2] = g[(a * 3 + 2) * EL_EPB];
+      block_acc(K[a], ga, DB);
+    }
+    gb[0] = g[(B1 * 3 + 0) * EL_EPB]; gb[1] = g[(B1 * 3 + 1) * EL_EPB]; gb[2] = g[(B1 * 3 + 2) * EL_EPB];
+    db_col(gb, Jw, DB);
+#pragma unroll
+    for (int a = 0; a <= T; a++) {
+      double ga[3];
+      ga[0] = g[(a * 3 + 0) * EL_EPB]; ga[1] = g[(a * 3 + 1) * EL_EPB]; ga[2] = g[(a * 3 + 2) * EL_EPB];
+      block_acc(K[NB2 + a], ga, DB);
+    }
+  }
+  block_bar();  // everyone is done reading G: the staging buffer may overwrite it
+
+  // ---- stage + write: two halves of 16 elements, element matrix = 576 doubles, column-major
+  for (int half = 0; half < 2; half++) {
+    if ((lane >> 4) == half) {
+      double *M = sm + (size_t)(lane & 15) * EL_MSTRIDE;
+#pragma unroll
+      for (int s = 0; s < 9; s++) {
+        const int a = (s < NB2) ? s : s - NB2;
+        const int b = (s < NB2) ? B2 : B1;
+#pragma unroll
+        for (int jx = 0; jx < 3; jx++)
+#pragma unroll
+          for (int ix = 0; ix < 3; ix++) {
+            const int r = a * 3 + ix, c = b * 3 + jx;
+            if (a != b || r <= c) {  // diagonal block: only its upper triangle is the reference's value
+              const double v = K[s][ix + 3 * jx];
+              M[c * 24 + r] = v;
+              M[r * 24 + c] = v;  // complete_lt!
+            }
+          }
+      }
+    }
+    block_bar();
+    const int64_t sbase = slot0 + half * 16;
+    const int64_t nvalid = min((int64_t)16, P.nactive - sbase);
+    if (nvalid > 0) {
+      const int nvec = (int)(nvalid * 288);  // double2 count; contiguous slots are contiguous in V
+      double2 *dst = reinterpret_cast<double2 *>(P.V + sbase * 576);
+      for (int i = threadIdx.x; i < nvec; i += 128) {
+        const int el = i / 288, k = i - el * 288;
+        dst[i] = *reinterpret_cast<const double2 *>(sm + (size_t)el * EL_MSTRIDE + 2 * k);
+      }
+    }
+    block_bar();
+  }
+}
+
+__global__ void __launch_bounds__(128, 2) k_h8_elastic(const H8Params P) {
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x & 31, t = threadIdx.x >> 5;  // lane = element in block, t = column pair
+  const int64_t slot0 = (int64_t)blockIdx.x * EL_EPB;
+  const int64_t slot_raw = slot0 + lane;
+  const bool live = slot_raw < P.nactive;
+  const int64_t slot = live ? slot_raw : P.nactive - 1;
+  const int64_t e = P.elem_list ? P.elem_list[slot] : slot;
+
+  // ---- phase A: gradients for points 2t, 2t+1 of element `lane`
+  {
+    int nd[8];
+    const int4 *c4 = reinterpret_cast<const int4 *>(P.conn + e * 8);
+    int4 a = __ldg(c4), b = __ldg(c4 + 1);
+    nd[0] = a.x; nd[1] = a.y; nd[2] = a.z; nd[3] = a.w; nd[4] = b.x; nd[5] = b.y; nd[6] = b.z; nd[7] = b.w;
+    double X[8][3];
+#pragma unroll
+    for (int n = 0; n < 8; n++)
+#pragma unroll
+      for (int s = 0; s < 3; s++) X[n][s] = __ldg(P.xyz + (int64_t)s * P.nnodes + nd[n]);
+#pragma unroll 1
+    for (int jj = 0; jj < 2; jj++) {
+      const int j = 2 * t + jj;
+      const double *dN = c_dN + j * 24;
+      double J[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) J[i] = 0.0;
+#pragma unroll
+      for (int n = 0; n < 8; n++)
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+#pragma unroll
+          for (int s = 0; s < 3; s++) J[s + 3 * d] += X[n][s] * dN[d * 8 + n];
+      double inv[9], det;
+      inv3(J, inv, det);
+      double *g = sm + (size_t)j * EL_GSTRIDE * EL_EPB + lane;
+#pragma unroll
+      for (int n = 0; n < 8; n++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          g[(n * 3 + c) * EL_EPB] = dN[n] * inv[0 + 3 * c] + dN[8 + n] * inv[1 + 3 * c] + dN[16 + n] * inv[2 + 3 * c];
+      g[24 * EL_EPB] = det * c_w[j];
+    }
+  }
+  __syncthreads();
+  switch (t) {
+    case 0: elastic_phase_b<0>(sm, lane, slot0, P); break;
+    case 1: elastic_phase_b<1>(sm, lane, slot0, P); break;
+    case 2: elastic_phase_b<2>(sm, lane, slot0, P); break;
+    default: elastic_phase_b<3>(sm, lane, slot0, P); break;
+  }
+}
+
+}  // namespace
+
+int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool *handled) {
+  *handled = false;
+  fegpu_ctx *ctx = mesh->ctx;
+  if (mesh->npts != 8 || mesh->sdim != 3) return FEGPU_OK;
+  const bool diff = (fa.form == FORM_DIFF_ISO || fa.form == FORM_DIFF_GEN);
+  const bool elast = (fa.form == FORM_ELASTIC);
+  if (!diff && !elast) return FEGPU_OK;
+  if (mesh->nactive == 0) { *handled = true; return FEGPU_OK; }
+  // dN part of the host table: [npts][3][8] starting after N [npts][8]
+  CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_dN, mesh->h_tab.data() + 8 * 8, sizeof(double) * 8 * 24, 0, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_w, mesh->h_w.data(), sizeof(double) * 8, 0, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_coef, fa.coef, sizeof(double) * 36, 0, cudaMemcpyHostToDevice, ctx->stream));
+  H8Params P{mesh->d_conn, mesh->d_xyz, mesh->nnodes, mesh->d_elem_list, mesh->nactive, d_V};
+  if (diff) {
+    unsigned grid = grid_for(mesh->nactive, 128);
+    if (fa.form == FORM_DIFF_GEN) k_h8_diffusion<true><<<grid, 128, 0, ctx->stream>>>(P);
+    else k_h8_diffusion<false><<<grid, 128, 0, ctx->stream>>>(P);
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic, cudaFuncAttributeMaxDynamicSharedMemorySize, EL_SMEM_BYTES));
+      attr_set = true;
+    }
+    unsigned grid = grid_for(mesh->nactive, EL_EPB);
+    k_h8_elastic<<<grid, 128, EL_SMEM_BYTES, ctx->stream>>>(P);
+  }
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  *handled = true;
+  return FEGPU_OK;
+}

@@ -1,0 +1,336 @@
+// Element integration kernels (FP64 on the CUDA cores; no tensor cores: the contractions are 8-81 wide).
+//
+// Generic kernel k_integrate<...>: TPE cooperating threads per element (8 for the small scalar elements, 32 = one
+// warp for T10 / H8-elastic / H20-scalar, 128 = one CTA for H20/H27 vector forms).  Per quadrature point the group
+//   1. evaluates the isoparametric Jacobian from the element's coordinates (shared memory) and the caller's
+//      gradNparams table               -- locjac!  MatrixUtilityModule.jl:60, Jacobian FESetModule.jl:426-489
+//   2. forms gradN = gradNparams * inv(J) (adjugate / det)            -- gradN!  FESetModule.jl:453-544
+//   3. forms kappa*gradN' (add_gkgt_ut_only! :120) or D*B (blmat! DeforModelRedModule.jl:447, add_btdb_ut_only! :189)
+//   4. every thread accumulates its share of the upper-triangle (or full, for bilform_dot) element matrix entries
+//      in registers, in the reference's summation order.
+// At the end the triangle is mirrored (complete_lt! :164) and written in the reference's emission order
+// (AssemblyModule.jl:261-280: column-major, p = e*EM*EM + (j-1)*EM + i) as values only -- the (I,J) keys are
+// implied by conn + dofnums and never materialised on the fast path.
+#include "fegpu_internal.h"
+
+namespace {
+
+struct IntegParams {
+  const int32_t *conn;       // [nelem][NNE] 0-based
+  const double *xyz;         // [SDIM][nnodes]
+  int64_t nnodes;
+  const int32_t *elem_list;  // active element ids or nullptr
+  int64_t nactive;
+  const double *tab;         // N [npts][NNE], then dN [npts][MDIM][NNE]
+  const double *w;           // [npts]
+  int npts;
+  double *V;                 // [nactive][EM*EM]
+  double coef[36];
+  int m;
+  double otherdim;
+};
+
+template <int TPE>
+__device__ __forceinline__ void group_sync() {
+  if (TPE <= 32)
+    __syncwarp();
+  else
+    __syncthreads();
+}
+
+// Jacobian determinant / surface measure.  J is SDIM x MDIM, column-major.
+template <int SDIM, int MDIM>
+__device__ __forceinline__ double jac_measure(const double *J) {
+  if (SDIM == 3 && MDIM == 3) {
+    return J[0] * (J[4] * J[8] - J[5] * J[7]) - J[3] * (J[1] * J[8] - J[7] * J[2]) + J[6] * (J[1] * J[5] - J[4] * J[2]);
+  } else if (SDIM == 2 && MDIM == 2) {
+    return J[0] * J[3] - J[1] * J[2];
+  } else {  // SDIM == 3, MDIM == 2 : |J1 x J2|
+    double c0 = J[1] * J[5] - J[2] * J[4];
+    double c1 = J[2] * J[3] - J[0] * J[5];
+    double c2 = J[0] * J[4] - J[1] * J[3];
+    return sqrt(c0 * c0 + c1 * c1 + c2 * c2);
+  }
+}
+
+// inverse of the MDIM x MDIM Jacobian, adjugate times 1/det (FESetModule.jl:513-530)
+template <int MDIM>
+__device__ __forceinline__ void jac_inverse(const double *J, double *inv) {
+  if (MDIM == 3) {
+#define R(i, j) J[(i - 1) + 3 * (j - 1)]
+    double invdet = 1.0 / (R(1, 1) * (R(2, 2) * R(3, 3) - R(3, 2) * R(2, 3)) - R(1, 2) * (R(2, 1) * R(3, 3) - R(2, 3) * R(3, 1)) +
+                           R(1, 3) * (R(2, 1) * R(3, 2) - R(2, 2) * R(3, 1)));
+    inv[0] = (R(2, 2) * R(3, 3) - R(3, 2) * R(2, 3)) * invdet;   // 11
+    inv[3] = -(R(1, 2) * R(3, 3) - R(1, 3) * R(3, 2)) * invdet;  // 12
+    inv[6] = (R(1, 2) * R(2, 3) - R(1, 3) * R(2, 2)) * invdet;   // 13
+    inv[1] = -(R(2, 1) * R(3, 3) - R(2, 3) * R(3, 1)) * invdet;  // 21
+    inv[4] = (R(1, 1) * R(3, 3) - R(1, 3) * R(3, 1)) * invdet;   // 22
+    inv[7] = -(R(1, 1) * R(2, 3) - R(2, 1) * R(1, 3)) * invdet;  // 23
+    inv[2] = (R(2, 1) * R(3, 2) - R(3, 1) * R(2, 2)) * invdet;   // 31
+    inv[5] = -(R(1, 1) * R(3, 2) - R(3, 1) * R(1, 2)) * invdet;  // 32
+    inv[8] = (R(1, 1) * R(2, 2) - R(2, 1) * R(1, 2)) * invdet;   // 33
+#undef R
+  } else {
+    double invdet = 1.0 / (J[0] * J[3] - J[2] * J[1]);
+    inv[0] = J[3] * invdet;
+    inv[2] = -J[2] * invdet;
+    inv[1] = -J[1] * invdet;
+    inv[3] = J[0] * invdet;
+  }
+}
+
+// Nonzero rows of column (node, comp) of the 3-D strain-displacement matrix (DeforModelRedModule.jl:463-468 with Rm = I):
+// comp x: rows xx(g1) xy(g2) xz(g3); comp y: yy(g2) xy(g1) yz(g3); comp z: zz(g3) xz(g1) yz(g2).  Rows ascending.
+__device__ __forceinline__ void bcol(int comp, const double *g, int rows[3], double vals[3]) {
+  if (comp == 0) {
+    rows[0] = 0; vals[0] = g[0]; rows[1] = 3; vals[1] = g[1]; rows[2] = 4; vals[2] = g[2];
+  } else if (comp == 1) {
+    rows[0] = 1; vals[0] = g[1]; rows[1] = 3; vals[1] = g[0]; rows[2] = 5; vals[2] = g[2];
+  } else {
+    rows[0] = 2; vals[0] = g[2]; rows[1] = 4; vals[1] = g[0]; rows[2] = 5; vals[2] = g[1];
+  }
+}
+
+template <int NNE, int MDIM, int SDIM, int NDN, int FORM, int TPE>
+__global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const IntegParams P) {
+  constexpr int EM = NNE * NDN;
+  constexpr bool SYM = (FORM != FORM_DOT);
+  constexpr int NENT = SYM ? EM * (EM + 1) / 2 : EM * EM;
+  constexpr int EPT = (NENT + TPE - 1) / TPE;
+  constexpr int GPB = (TPE <= 32) ? 128 / TPE : 1;  // element groups per block
+  constexpr int NAUX = (FORM == FORM_ELASTIC) ? 6 * EM : (FORM == FORM_DIFF_GEN ? MDIM * NNE : 1);
+
+  extern __shared__ double smem[];
+  // layout: tables [npts*NNE*(1+MDIM)] | w [npts] | per group: X [NNE*SDIM], G [NNE*MDIM], AUX [NAUX]
+  double *sN = smem;
+  double *sdN = sN + P.npts * NNE;
+  double *sw = sdN + P.npts * NNE * MDIM;
+  double *sgrp = sw + P.npts;
+  const int g = threadIdx.x / TPE, t = threadIdx.x % TPE;
+  double *sX = sgrp + g * (NNE * SDIM + NNE * MDIM + NAUX);
+  double *sG = sX + NNE * SDIM;
+  double *sA = sG + NNE * MDIM;
+
+  for (int i = threadIdx.x; i < P.npts * NNE * (1 + MDIM); i += blockDim.x) sN[i] = P.tab[i];
+  for (int i = threadIdx.x; i < P.npts; i += blockDim.x) sw[i] = P.w[i];
+  __syncthreads();
+
+  // entry -> (r, c) decode, once per thread
+  int er[EPT], ec[EPT];
+#pragma unroll
+  for (int k = 0; k < EPT; k++) {
+    int idx = t + k * TPE;
+    if (idx >= NENT) idx = NENT - 1;  // clamp: duplicates recompute the last entry, stores are predicated
+    if (SYM) {
+      int c = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+      while (c * (c + 1) / 2 > idx) c--;
+      while ((c + 1) * (c + 2) / 2 <= idx) c++;
+      er[k] = idx - c * (c + 1) / 2;
+      ec[k] = c;
+    } else {
+      er[k] = idx % EM;
+      ec[k] = idx / EM;
+    }
+  }
+
+  const int64_t ngroups_total = (int64_t)gridDim.x * GPB;
+  // all groups of a block iterate the same number of times so the barriers stay aligned
+  const int64_t iters = (P.nactive + ngroups_total - 1) / ngroups_total;
+  for (int64_t it = 0; it < iters; it++) {
+    const int64_t slot_raw = (it * gridDim.x + blockIdx.x) * GPB + g;
+    const bool live = slot_raw < P.nactive;
+    const int64_t slot = live ? slot_raw : P.nactive - 1;
+    const int64_t e = P.elem_list ? P.elem_list[slot] : slot;
+    const int32_t *conn = P.conn + e * NNE;
+    group_sync<TPE>();  // previous element's smem reads are done
+    for (int i = t; i < NNE * SDIM; i += TPE) {
+      int a = i % NNE, s = i / NNE;
+      sX[a * SDIM + s] = P.xyz[(int64_t)s * P.nnodes + conn[a]];
+    }
+    group_sync<TPE>();
+
+    double acc[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; k++) acc[k] = 0.0;
+
+    for (int j = 0; j < P.npts; j++) {
+      const double *dN = sdN + j * NNE * MDIM;  // [MDIM][NNE]
+      const double *N = sN + j * NNE;
+      // J = X' * dN  (SDIM x MDIM, column-major), every thread redundantly
+      double J[SDIM * MDIM];
+#pragma unroll
+      for (int i = 0; i < SDIM * MDIM; i++) J[i] = 0.0;
+      for (int a = 0; a < NNE; a++) {
+#pragma unroll
+        for (int d = 0; d < MDIM; d++) {
+          double dn = dN[d * NNE + a];
+#pragma unroll
+          for (int s = 0; s < SDIM; s++) J[s + SDIM * d] += sX[a * SDIM + s] * dn;
+        }
+      }
+      double Jac = jac_measure<SDIM, MDIM>(J);
+      if (FORM == FORM_DOT) {
+        if (MDIM == 2 && P.m == 3) Jac = Jac * P.otherdim;
+        const double Jw = Jac * sw[j];
+#pragma unroll
+        for (int k = 0; k < EPT; k++) {
+          const int r = er[k], c = ec[k];
+          const int kn = r / NDN, pp = r % NDN, mn = c / NDN, qq = c % NDN;
+          // factor = (Ns[k]*Ns[m]*Jac*w) ; elmat += factor*c[p,q]      FEMMBaseModule.jl:1356-1359
+          const double factor = N[kn] * N[mn] * Jac * sw[j];
+          acc[k] += factor * P.coef[pp + NDN * qq];
+        }
+        (void)Jw;
+      } else {
+        // gradN rows
+        double inv[MDIM * MDIM];
+        if (SDIM == MDIM) jac_inverse<MDIM>(J, inv);
+        const double Jw = Jac * sw[j];
+        group_sync<TPE>();  // previous point's G / AUX reads are done
+        for (int a = t; a < NNE; a += TPE) {
+#pragma unroll
+          for (int c = 0; c < MDIM; c++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < MDIM; k++) s += dN[k * NNE + a] * inv[k + MDIM * c];
+            sG[a * MDIM + c] = s;
+          }
+        }
+        group_sync<TPE>();
+        if (FORM == FORM_DIFF_GEN) {
+          // kappa_bargradNT[mx, nx] = Jac_w * sum_px kappa[mx,px]*gradN[nx,px]     MatrixUtilityModule.jl:134-142
+          for (int i = t; i < MDIM * NNE; i += TPE) {
+            const int nx = i / MDIM, mx = i % MDIM;
+            double a = 0.0;
+#pragma unroll
+            for (int px = 0; px < MDIM; px++) a += P.coef[mx + MDIM * px] * sG[nx * MDIM + px];
+            sA[mx + MDIM * nx] = Jw * a;
+          }
+          group_sync<TPE>();
+        } else if (FORM == FORM_ELASTIC) {
+          // DB[:, c] = Jac_w * D * B[:, c]                                          MatrixUtilityModule.jl:198-206
+          for (int c = t; c < EM; c += TPE) {
+            int rows[3];
+            double vals[3];
+            bcol(c % 3, sG + (c / 3) * 3, rows, vals);
+#pragma unroll
+            for (int mx = 0; mx < 6; mx++) {
+              double a = 0.0;
+#pragma unroll
+              for (int q = 0; q < 3; q++) a += P.coef[mx + 6 * rows[q]] * vals[q];
+              sA[mx + 6 * c] = Jw * a;
+            }
+          }
+          group_sync<TPE>();
+        }
+#pragma unroll
+        for (int k = 0; k < EPT; k++) {
+          const int r = er[k], c = ec[k];
+          if (FORM == FORM_DIFF_ISO) {
+            // Ke[mx,nx] += gradN[mx,px] * (mult*gradN[nx,px]), px ascending          MatrixUtilityModule.jl:90-96
+            const double mult = P.coef[0] * Jac * sw[j];
+#pragma unroll
+            for (int px = 0; px < MDIM; px++) acc[k] += sG[r * MDIM + px] * (mult * sG[c * MDIM + px]);
+          } else if (FORM == FORM_DIFF_GEN) {
+            double a = 0.0;
+#pragma unroll
+            for (int px = 0; px < MDIM; px++) a += sG[r * MDIM + px] * sA[px + MDIM * c];
+            acc[k] += a;
+          } else {  // FORM_ELASTIC: accum = sum_px B[px,mx]*DB[px,nx]
+            int rows[3];
+            double vals[3];
+            bcol(r % 3, sG + (r / 3) * 3, rows, vals);
+            double a = 0.0;
+#pragma unroll
+            for (int q = 0; q < 3; q++) a += vals[q] * sA[rows[q] + 6 * c];
+            acc[k] += a;
+          }
+        }
+      }
+    }
+    // emission: V[slot][c*EM + r]; the mirrored entry is complete_lt!
+    if (live) {
+      double *Ve = P.V + slot * (int64_t)(EM * EM);
+#pragma unroll
+      for (int k = 0; k < EPT; k++) {
+        if (t + k * TPE < NENT) {
+          const int r = er[k], c = ec[k];
+          Ve[c * EM + r] = acc[k];
+          if (SYM && r != c) Ve[r * EM + c] = acc[k];
+        }
+      }
+    }
+  }
+}
+
+template <int NNE, int MDIM, int SDIM, int NDN, int FORM, int TPE>
+int32_t launch_generic(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
+  fegpu_ctx *ctx = mesh->ctx;
+  constexpr int EM = NNE * NDN;
+  constexpr int GPB = (TPE <= 32) ? 128 / TPE : 1;
+  constexpr int NAUX = (FORM == FORM_ELASTIC) ? 6 * EM : (FORM == FORM_DIFF_GEN ? MDIM * NNE : 1);
+  IntegParams P;
+  P.conn = mesh->d_conn; P.xyz = mesh->d_xyz; P.nnodes = mesh->nnodes; P.elem_list = mesh->d_elem_list;
+  P.nactive = mesh->nactive; P.tab = mesh->d_tab; P.w = mesh->d_w; P.npts = mesh->npts; P.V = d_V;
+  for (int i = 0; i < 36; i++) P.coef[i] = fa.coef[i];
+  P.m = fa.m; P.otherdim = fa.otherdim;
+  if (mesh->nactive == 0) return FEGPU_OK;
+  size_t smem = sizeof(double) * ((size_t)mesh->npts * NNE * (1 + MDIM) + mesh->npts + (size_t)GPB * (NNE * SDIM + NNE * MDIM + NAUX));
+  auto kern = k_integrate<NNE, MDIM, SDIM, NDN, FORM, TPE>;
+  if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t want = (mesh->nactive + GPB - 1) / GPB;
+  int64_t cap = (int64_t)ctx->sm_count * 16;
+  unsigned grid = (unsigned)std::min<int64_t>(want, cap);
+  kern<<<grid, (TPE <= 32 ? 128 : TPE), smem, ctx->stream>>>(P);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return FEGPU_OK;
+}
+
+template <int NNE, int MDIM, int SDIM, int TPE_S, int TPE_V>
+int32_t dispatch_form(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
+  switch (fa.form) {
+    case FORM_DIFF_ISO:
+      if (SDIM != MDIM) break;
+      return launch_generic<NNE, MDIM, (SDIM == MDIM ? SDIM : MDIM), 1, FORM_DIFF_ISO, TPE_S>(mesh, fa, d_V);
+    case FORM_DIFF_GEN:
+      if (SDIM != MDIM) break;
+      return launch_generic<NNE, MDIM, (SDIM == MDIM ? SDIM : MDIM), 1, FORM_DIFF_GEN, TPE_S>(mesh, fa, d_V);
+    case FORM_ELASTIC:
+      if (SDIM != 3 || MDIM != 3) break;
+      return launch_generic<NNE, 3, 3, 3, FORM_ELASTIC, TPE_V>(mesh, fa, d_V);
+    case FORM_DOT:
+      if (fa.ndn == 1) return launch_generic<NNE, MDIM, SDIM, 1, FORM_DOT, TPE_S>(mesh, fa, d_V);
+      if (fa.ndn == 2) return launch_generic<NNE, MDIM, SDIM, 2, FORM_DOT, TPE_V>(mesh, fa, d_V);
+      if (fa.ndn == 3) return launch_generic<NNE, MDIM, SDIM, 3, FORM_DOT, TPE_V>(mesh, fa, d_V);
+      return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "bilform_dot: 1, 2 or 3 dofs per node are supported");
+  }
+  return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "form not defined for this element manifold / space dimension");
+}
+
+}  // namespace
+
+int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool *handled);  // fegpu_h8.cu
+
+int32_t fe_integrate(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
+  if (mesh->npts <= 0) return fegpu_fail(mesh->ctx, FEGPU_ERR_STATE, "no quadrature rule set (fegpu_rule_set)");
+  if (mesh->etype == FEGPU_H8) {
+    bool handled = false;
+    FE_TRY(fe_integrate_h8(mesh, fa, d_V, &handled));
+    if (handled) return FEGPU_OK;
+  }
+  switch (mesh->etype) {
+    case FEGPU_T3:
+      if (mesh->sdim == 2) return dispatch_form<3, 2, 2, 8, 8>(mesh, fa, d_V);
+      return dispatch_form<3, 2, 3, 8, 8>(mesh, fa, d_V);
+    case FEGPU_Q4:
+      if (mesh->sdim == 2) return dispatch_form<4, 2, 2, 8, 8>(mesh, fa, d_V);
+      return dispatch_form<4, 2, 3, 8, 8>(mesh, fa, d_V);
+    case FEGPU_T4: return dispatch_form<4, 3, 3, 8, 32>(mesh, fa, d_V);
+    case FEGPU_T10: return dispatch_form<10, 3, 3, 32, 32>(mesh, fa, d_V);
+    case FEGPU_H8: return dispatch_form<8, 3, 3, 8, 32>(mesh, fa, d_V);
+    case FEGPU_H20: return dispatch_form<20, 3, 3, 32, 128>(mesh, fa, d_V);
+    case FEGPU_H27: return dispatch_form<27, 3, 3, 32, 128>(mesh, fa, d_V);
+  }
+  return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "unknown element type");
+}

@@ -1,0 +1,137 @@
+// Internal declarations shared by the translation units of libfinegpu.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fegpu.h"
+
+#define FEGPU_MAX_NNE 27
+#define FEGPU_MAX_NPTS 64
+#define FEGPU_TAB_DOUBLES 6144  // N + dN tables: npts*nne*(1+mdim) <= this
+
+struct fegpu_ctx {
+  int device = 0;
+  cudaStream_t stream = 0;
+  bool async = false;
+  int64_t launches = 0;
+  int sm_count = 148;
+  std::string err;
+};
+
+struct Pattern;  // fegpu_pattern.cu
+
+struct fegpu_mesh {
+  fegpu_ctx *ctx = nullptr;
+  int etype = 0, nne = 0, mdim = 0, sdim = 0;
+  int64_t nelem = 0, nnodes = 0;
+  int32_t *d_conn = nullptr;  // [nelem][nne] 0-based
+  double *d_xyz = nullptr;    // [sdim][nnodes]
+  // quadrature tables (device copy): N [npts][nne], dN [npts][mdim][nne], w [npts]
+  int npts = 0;
+  double *d_tab = nullptr;  // N then dN
+  double *d_w = nullptr;
+  std::vector<double> h_tab, h_w;
+  // partition (multi-GPU row blocks)
+  bool partitioned = false;
+  int64_t nactive = 0;              // == nelem when not partitioned
+  int32_t *d_elem_list = nullptr;   // active element ids ascending (nullptr = identity)
+  uint8_t *d_rowowned = nullptr;    // per node, nullptr = all owned
+  uint64_t topo_version = 1;        // bumped when the active set / ownership changes
+  bool degenerate = false;          // some element lists a node twice -> generic sort path
+};
+
+struct fegpu_dofmap {
+  fegpu_ctx *ctx = nullptr;
+  fegpu_mesh *mesh = nullptr;
+  int ndn = 0;
+  int64_t row_nall = 0, col_nall = 0;
+  int32_t *d_dof = nullptr;  // [ndn][nnodes] 0-based
+  bool injective = true;
+  Pattern *pat = nullptr;
+  uint64_t pat_topo_version = 0;
+};
+
+struct fegpu_asm {
+  fegpu_ctx *ctx = nullptr;
+  // element-matrix values of the last bilform call: [nactive][EM*EM], reference emission order
+  double *d_V = nullptr;
+  size_t V_cap = 0;  // doubles
+  int64_t V_n = 0;
+  int last_EM = 0;
+  // result
+  int64_t nrows = 0, ncols = 0, nnz = 0;
+  const int64_t *d_colptr = nullptr;  // borrowed from a Pattern or == own_colptr
+  const int64_t *d_rowval = nullptr;
+  double *d_nzval = nullptr;
+  size_t nz_cap = 0;
+  int64_t *own_colptr = nullptr, *own_rowval = nullptr;
+  size_t own_colptr_cap = 0, own_rowval_cap = 0;
+  bool have_result = false;
+  bool pattern_cached = false;
+  // generic protocol staging (host side, flushed to the device at makematrix)
+  bool started = false;
+  int64_t g_row_nall = 0, g_col_nall = 0;
+  std::vector<int64_t> hI, hJ;
+  std::vector<double> hV;
+  // timings
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid = false;
+};
+
+// ---- error helpers -----------------------------------------------------------------------------------
+int32_t fegpu_fail(fegpu_ctx *ctx, int32_t code, const std::string &msg);
+#define CUDA_TRY(ctx, expr)                                                                              \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return fegpu_fail((ctx), FEGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+  } while (0)
+#define FE_TRY(expr)                \
+  do {                              \
+    int32_t _s = (expr);            \
+    if (_s != FEGPU_OK) return _s;  \
+  } while (0)
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// ---- primitives (fegpu_prims.cu) -----------------------------------------------------------------------
+// out[i] = sum_{k<i} in[k] (+ base); out may alias in for the int64 version.  n+1 entries are written when
+// write_total is true (out[n] = total).  Returns the total through *total_host if non-null (synchronises).
+int32_t fe_exclusive_scan_i64(fegpu_ctx *ctx, const int64_t *d_in, int64_t *d_out, int64_t n, int64_t base, bool write_total,
+                              int64_t *total_host);
+int32_t fe_exclusive_scan_i32_to_i64(fegpu_ctx *ctx, const int32_t *d_in, int64_t *d_out, int64_t n, int64_t base, bool write_total,
+                                     int64_t *total_host);
+int32_t fe_max_i32(fegpu_ctx *ctx, const int32_t *d_in, int64_t n, int32_t *max_host);
+
+// ---- integration (fegpu_integrate.cu) ------------------------------------------------------------------
+enum { FORM_DIFF_ISO = 0, FORM_DIFF_GEN = 1, FORM_ELASTIC = 2, FORM_DOT = 3 };
+struct FormArgs {
+  int form;
+  int ndn;
+  double coef[36];  // kappa (mdim x mdim col-major) | C (6x6 col-major) | c (ndn x ndn col-major); coef[0] = scalar kappa
+  int m;            // bilform_dot manifold dimension
+  double otherdim;
+};
+int32_t fe_integrate(fegpu_mesh *mesh, const FormArgs &fa, double *d_V);
+
+// ---- pattern + gather (fegpu_pattern.cu) ---------------------------------------------------------------
+int32_t fe_pattern_build(fegpu_dofmap *dm);
+void fe_pattern_free(Pattern *p);
+int64_t fe_pattern_nnz(const Pattern *p);
+const int64_t *fe_pattern_colptr(const Pattern *p);
+const int64_t *fe_pattern_rowval(const Pattern *p);
+bool fe_pattern_usable(const fegpu_dofmap *dm);  // mesh-structured fast path applicable?
+int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, double *d_nzval);
+
+// ---- generic COO -> CSC by sort (fegpu_sort.cu) --------------------------------------------------------
+// d_I, d_J 1-based int64, n triplets in emission order.  Fills the assembler's own colptr/rowval/nzval.
+int32_t fe_coo_to_csc(fegpu_asm *as, int64_t n, const int64_t *d_I, const int64_t *d_J, const double *d_V, int64_t nrows,
+                      int64_t ncols);
+// emit the reference-order (I, J) of a bilform assembly (AssemblyModule.jl:266-279) from conn + dof map
+int32_t fe_emit_ij(fegpu_dofmap *dm, int64_t *d_I, int64_t *d_J);
+
+int32_t fe_asm_reserve(fegpu_asm *as, double **buf, size_t *cap, size_t need_doubles);
+int32_t fe_reserve_bytes(fegpu_ctx *ctx, void **buf, size_t *cap, size_t need_bytes);

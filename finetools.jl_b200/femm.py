@@ -1,0 +1,214 @@
+"""FEMMBase and the three bilinear forms, dispatched to the GPU when the assembler is a SysmatAssemblerSparseGPU.
+
+Mirrors src/FEMMBaseModule.jl: FEMMBase :72-84, bilform_dot :1335-1366, innerproduct :1388-1401, bilform_diffusion
+:1462-1535, bilform_lin_elastic :1774-1813.  User code keeps the reference's call shape
+    K = bilform_diffusion(femm, assembler, geom, u, DataCache(kappa))
+The eligibility checks of SURVEY.md section 8(b) raise instead of silently falling back to a CPU loop.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import VP, FEGPUError, check, fptr
+from .assembly import SysmatAssemblerSparseGPU
+from .datacache import DataCache
+from .integdomain import IntegDomain, integrationdata
+
+
+class DeforModelRed3D:
+    """Marker type (src/DeforModelRedModule.jl:30); nstressstrain = 6 (:72-76)."""
+    nstressstrain = 6
+
+
+class CSys:
+    """Material coordinate system; only the identity (the FEMMBase default, FEMMBaseModule.jl:82-84) is GPU-eligible."""
+
+    def __init__(self, sdim=3, mdim=None, isidentity=True):
+        self.isconstant = True
+        self.isidentity = bool(isidentity)
+        self.sdim, self.mdim = sdim, sdim if mdim is None else mdim
+
+
+class FEMMBase:
+    def __init__(self, integdomain, mcsys=None):
+        if not isinstance(integdomain, IntegDomain):
+            raise TypeError("FEMMBase needs an IntegDomain")
+        self.integdomain = integdomain
+        self.mcsys = mcsys if mcsys is not None else CSys(integdomain.fes.mdim)
+
+    def finite_elements(self):
+        return self.integdomain.fes
+
+
+class _DeviceMesh:
+    """Device twin of (fes, geom, rule): created once per FESet, coordinates refreshed on every form call."""
+
+    def __init__(self, ctx, fes, geom):
+        self.ctx = ctx
+        self.handle = VP()
+        xyz = _lib.colmajor_f64(geom.values)
+        self.nnodes, self.sdim = xyz.shape
+        conn = np.ascontiguousarray(fes.conn, dtype=np.int64)
+        check(_lib.lib().fegpu_mesh_upload(ctx.handle, fes.etype, conn.shape[0], fptr(conn), self.nnodes, self.sdim, fptr(xyz),
+                                           C.byref(self.handle)), ctx.handle)
+        self.conn_ref = fes.conn
+        self.rule_key = None
+        self.dofmaps = []   # [(host copy of dofnums, nalldofs, handle)]
+        self.partition_key = None
+
+    def update_geometry(self, geom):
+        xyz = _lib.colmajor_f64(geom.values)
+        if xyz.shape != (self.nnodes, self.sdim):
+            raise FEGPUError(-2, "geometry field changed shape; build a new FESet / assembler")
+        check(_lib.lib().fegpu_geom_update(self.handle, fptr(xyz)), self.ctx.handle)
+
+    def set_rule(self, integdomain):
+        rule = integdomain.integration_rule
+        key = (id(rule), rule.npts)
+        if key == self.rule_key:
+            return
+        npts, Ns, gradNparams, w, _ = integrationdata(integdomain)
+        N = np.ascontiguousarray(np.stack([n.reshape(-1) for n in Ns]))                       # [npts][nne]
+        dN = np.ascontiguousarray(np.stack([np.asfortranarray(g).T for g in gradNparams]))    # [npts][mdim][nne]
+        ww = np.ascontiguousarray(np.asarray(w, dtype=np.float64).reshape(-1))
+        check(_lib.lib().fegpu_rule_set(self.handle, npts, fptr(N), fptr(dN), fptr(ww)), self.ctx.handle)
+        self.rule_key = key
+
+    def set_partition(self, node_owner, my_rank):
+        key = None if node_owner is None else (id(node_owner), int(my_rank))
+        if key == self.partition_key:
+            return
+        if node_owner is None:
+            check(_lib.lib().fegpu_partition_set(self.handle, None, 0), self.ctx.handle)
+        else:
+            own = np.ascontiguousarray(node_owner, dtype=np.int32)
+            if own.size != self.nnodes:
+                raise FEGPUError(-2, "node_owner must have one entry per node")
+            check(_lib.lib().fegpu_partition_set(self.handle, fptr(own), int(my_rank)), self.ctx.handle)
+            self._owner_keepalive = node_owner
+        self.partition_key = key
+
+    def dofmap(self, u):
+        dn = u.dofnums
+        nall = u.nalldofs()
+        for host, n, h in self.dofmaps:
+            if n == nall and host.shape == dn.shape and np.array_equal(host, dn):
+                return h
+        if dn.shape[0] != self.nnodes:
+            raise FEGPUError(-2, "field u and geometry have different node counts")
+        d = _lib.colmajor_i64(dn)
+        h = VP()
+        check(_lib.lib().fegpu_dofmap_upload(self.ctx.handle, self.handle, dn.shape[1], fptr(d), nall, nall, C.byref(h)), self.ctx.handle)
+        self.dofmaps.append((dn.copy(), nall, h))
+        if len(self.dofmaps) > 4:
+            _, _, old = self.dofmaps.pop(0)
+            _lib.lib().fegpu_dofmap_destroy(old)
+        return h
+
+    def destroy(self):
+        for _, _, h in self.dofmaps:
+            _lib.lib().fegpu_dofmap_destroy(h)
+        self.dofmaps = []
+        if self.handle:
+            _lib.lib().fegpu_mesh_destroy(self.handle)
+            self.handle = VP()
+
+
+def _device_mesh(assembler, fes, geom):
+    cache = assembler._device_cache
+    dm = cache.get(id(fes))
+    if dm is None or dm.conn_ref is not fes.conn:
+        if dm is not None:
+            dm.destroy()
+        dm = _DeviceMesh(assembler.ctx, fes, geom)
+        cache[id(fes)] = dm
+    else:
+        dm.update_geometry(geom)
+    return dm
+
+
+def _eligible(self, assembler, geom, u, cf):
+    if not isinstance(assembler, SysmatAssemblerSparseGPU):
+        raise TypeError("this package provides the GPU assembler path only (SysmatAssemblerSparseGPU); there is no CPU loop")
+    if not isinstance(cf, DataCache):
+        raise TypeError("coefficient must be a constant DataCache")
+    if not self.mcsys.isidentity:
+        raise FEGPUError(-2, "only the identity material coordinate system is GPU-eligible")
+    if self.integdomain.axisymmetric:
+        raise FEGPUError(-2, "axisymmetric integration domains are not GPU-eligible")
+    if geom.values.dtype != np.float64 or u.dofnums.dtype != np.int64:
+        raise FEGPUError(-2, "geom must be Float64 and dofnums Int64")
+
+
+def _prepare(self, assembler, geom, u, node_owner=None, my_rank=0):
+    fes = self.integdomain.fes
+    dmesh = _device_mesh(assembler, fes, geom)
+    dmesh.set_rule(self.integdomain)
+    dmesh.set_partition(node_owner, my_rank)
+    dof = dmesh.dofmap(u)
+    return fes, dmesh, dof
+
+
+def _finish(assembler, fes, dmesh, dof, u, raw):
+    elmdim = fes.nne * u.ndofs()
+    assembler._mode = "form"
+    assembler._row_nalldofs = assembler._col_nalldofs = u.nalldofs()
+    assembler._pending_form = (dmesh.handle, dof, fes.count() * elmdim * elmdim if dmesh.partition_key is None else None)
+    return assembler.makematrix(raw=raw)
+
+
+def bilform_diffusion(self, assembler, geom, u, cf, raw=False, node_owner=None, my_rank=0):
+    """K_ij = int grad(N_i) . kappa . grad(N_j): scalar DataCache -> _iso path, matrix -> _general path."""
+    _eligible(self, assembler, geom, u, cf)
+    if u.ndofs() != 1:
+        raise FEGPUError(-15, "Wrong size of matrix")  # add_gkgt_ut_only! asserts nne == Kedim
+    fes, dmesh, dof = _prepare(self, assembler, geom, u, node_owner, my_rank)
+    if fes.mdim != geom.values.shape[1]:
+        raise FEGPUError(-2, "bilform_diffusion needs space dimension == manifold dimension")
+    kap = cf.data
+    if kap.ndim == 0:
+        kind, k = 0, np.array([float(kap)])
+    else:
+        if kap.shape != (fes.mdim, fes.mdim):
+            raise FEGPUError(-2, "conductivity matrix must be mdim x mdim")
+        kind, k = 1, np.asfortranarray(kap)
+    check(_lib.lib().fegpu_bilform_diffusion(dmesh.handle, dof, kind, fptr(k), assembler.handle), assembler.ctx.handle)
+    return _finish(assembler, fes, dmesh, dof, u, raw)
+
+
+def bilform_lin_elastic(self, assembler, geom, u, mr, cf, raw=False, node_owner=None, my_rank=0):
+    """K = int B' C B with the 3-D strain-displacement matrix (mr must be DeforModelRed3D)."""
+    _eligible(self, assembler, geom, u, cf)
+    if mr is not DeforModelRed3D and not isinstance(mr, DeforModelRed3D):
+        raise FEGPUError(-2, "only DeforModelRed3D is GPU-eligible")
+    if u.ndofs() != 3 or geom.values.shape[1] != 3:
+        raise FEGPUError(-2, "Wrong dimensions")
+    Cm = cf.data
+    if Cm.shape != (6, 6):
+        raise FEGPUError(-2, "material stiffness must be 6 x 6")
+    fes, dmesh, dof = _prepare(self, assembler, geom, u, node_owner, my_rank)
+    Cf = np.asfortranarray(Cm)
+    check(_lib.lib().fegpu_bilform_lin_elastic(dmesh.handle, dof, fptr(Cf), assembler.handle), assembler.ctx.handle)
+    return _finish(assembler, fes, dmesh, dof, u, raw)
+
+
+def bilform_dot(self, assembler, geom, u, cf, m=3, raw=False, node_owner=None, my_rank=0):
+    """M_ij = int N_i c N_j over the m-dimensional manifold Jacobian."""
+    _eligible(self, assembler, geom, u, cf)
+    ndn = u.ndofs()
+    c = cf.data
+    if c.ndim == 0:
+        c = c.reshape(1, 1)
+    if c.shape != (ndn, ndn):
+        raise FEGPUError(-2, "coefficient must be ndn x ndn")
+    fes, dmesh, dof = _prepare(self, assembler, geom, u, node_owner, my_rank)
+    cfm = np.asfortranarray(c)
+    check(_lib.lib().fegpu_bilform_dot(dmesh.handle, dof, fptr(cfm), int(m), float(self.integdomain.otherdimension), assembler.handle),
+          assembler.ctx.handle)
+    return _finish(assembler, fes, dmesh, dof, u, raw)
+
+
+def innerproduct(self, assembler, geom, afield, raw=False):
+    """bilform_dot with the identity coefficient (FEMMBaseModule.jl:1388-1401); Diagonal{Bool} densified to Float64."""
+    return bilform_dot(self, assembler, geom, afield, DataCache(np.eye(afield.ndofs())), m=3, raw=raw)

@@ -1,0 +1,141 @@
+/*
+ * fegpu.h -- C ABI of libfinegpu.so: B200 (sm_100a) element integration + sparse assembly behind
+ * FinEtools.jl's assembler protocol.
+ *
+ * FinEtools.jl is pure Julia and has no FFI on this path; the entry points below are what a
+ * `SysmatAssemblerSparseGPU <: AbstractSysmatAssembler` shim binds with `ccall` (see INTEGRATION.md and
+ * finetools.jl_b200/julia/FinEtoolsGPU.jl).  Each one names the reference interface (file:line under
+ * /root/reference/src) it replaces.
+ *
+ * Conventions
+ *  - every function returns int32 status: 0 = OK, <0 = error; fegpu_last_error() gives the message.  The
+ *    messages for dof-range violations are the reference's own strings (AssemblyModule.jl:265-273).
+ *  - all index arrays crossing the boundary are 1-based int64 (Julia Int), all reals are IEEE binary64,
+ *    matrices are column-major (Julia layout).
+ *  - the caller owns every host pointer before and after each call; the library copies in / out and keeps
+ *    no host pointers.  Device memory belongs to the handles.
+ *  - calls are blocking (stream-synchronised on return) unless fegpu_set_async(ctx, 1) was called.
+ *  - there is NO CPU fallback: without a CUDA device fegpu_create fails.
+ */
+#ifndef FEGPU_H
+#define FEGPU_H
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fegpu_ctx fegpu_ctx;       /* one GPU, one stream                                            */
+typedef struct fegpu_mesh fegpu_mesh;     /* FESet connectivity + geometry NodalField + quadrature tables   */
+typedef struct fegpu_dofmap fegpu_dofmap; /* NodalField u.dofnums + the cached sparsity pattern             */
+typedef struct fegpu_asm fegpu_asm;       /* SysmatAssemblerSparse state: triplet values, CSC result        */
+
+/* element type codes (FESetModule.jl: T3 :661, Q4 :709, T4 :1342, T10 :1393, H8 :952, H20 :1027, H27 :1215) */
+enum { FEGPU_T3 = 1, FEGPU_Q4 = 2, FEGPU_T4 = 3, FEGPU_T10 = 4, FEGPU_H8 = 5, FEGPU_H20 = 6, FEGPU_H27 = 7 };
+
+enum {
+  FEGPU_OK = 0,
+  FEGPU_ERR_CUDA = -1,         /* CUDA runtime error / no device                                              */
+  FEGPU_ERR_ARG = -2,          /* bad argument                                                                */
+  FEGPU_ERR_COL_LT1 = -11,     /* "Column degree of freedom < 1"      AssemblyModule.jl:268                   */
+  FEGPU_ERR_COL_GT = -12,      /* "Column degree of freedom > size"   AssemblyModule.jl:269                   */
+  FEGPU_ERR_ROW_LT1 = -13,     /* "Row degree of freedom < 1"         AssemblyModule.jl:272                   */
+  FEGPU_ERR_ROW_GT = -14,      /* "Row degree of freedom > size"      AssemblyModule.jl:273                   */
+  FEGPU_ERR_MATSIZE = -15,     /* "Wrong size of matrix"              AssemblyModule.jl:265                   */
+  FEGPU_ERR_MANIFOLD = -16,    /* "That is the only acceptable option here." IntegDomainModule.jl:543,600     */
+  FEGPU_ERR_STATE = -17        /* call out of order (e.g. makematrix before any assembly)                     */
+};
+
+/* -- context ------------------------------------------------------------------------------------------ */
+int32_t fegpu_create(fegpu_ctx **ctx, int32_t device);
+int32_t fegpu_destroy(fegpu_ctx *ctx);
+const char *fegpu_last_error(fegpu_ctx *ctx); /* ctx may be NULL: last error of the calling thread        */
+/* run all kernels on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); default = stream 0 */
+int32_t fegpu_set_stream(fegpu_ctx *ctx, void *cuda_stream);
+int32_t fegpu_set_async(fegpu_ctx *ctx, int32_t async_on);
+int32_t fegpu_synchronize(fegpu_ctx *ctx);
+/* number of CUDA kernels this context has launched so far (bench.py's gpu_launches)                     */
+int64_t fegpu_launch_count(fegpu_ctx *ctx);
+/* roofline denominators measured by the library itself: FP64 FMA peak (TFLOP/s) and copy bandwidth (GB/s) */
+int32_t fegpu_measure_peaks(fegpu_ctx *ctx, double *dfma_tflops, double *copy_gbs);
+
+/* -- mesh: replaces the per-element gathers of fes.conn (FESetModule.jl:61) and geom.values
+ *    (gathervalues_asmat!, FieldModule.jl:263-275): uploaded once ------------------------------------- */
+int32_t fegpu_mesh_upload(fegpu_ctx *ctx, int32_t etype, int64_t nelem, const int64_t *conn /* [nelem][nne] 1-based */,
+                          int64_t nnodes, int32_t sdim, const double *xyz /* nnodes x sdim col-major */, fegpu_mesh **mesh);
+int32_t fegpu_mesh_destroy(fegpu_mesh *mesh);
+/* new coordinates for the same connectivity (pattern cache stays valid) */
+int32_t fegpu_geom_update(fegpu_mesh *mesh, const double *xyz);
+/* quadrature tables exactly as the caller's integrationdata() produced them (IntegDomainModule.jl:631-648):
+ * Ns [npts][nne], gradNpar [npts][mdim][nne] (i.e. each point's nne x mdim matrix, column-major), w [npts] */
+int32_t fegpu_rule_set(fegpu_mesh *mesh, int32_t npts, const double *Ns, const double *gradNpar, const double *w);
+/* multi-GPU row-block ownership (pointpartitioning semantics, MeshModificationModule.jl:1029): this context
+ * integrates every element touching a node with node_owner[n] == my_rank and keeps the matrix rows of those
+ * nodes' dofs.  node_owner == NULL restores the single-GPU behaviour. */
+int32_t fegpu_partition_set(fegpu_mesh *mesh, const int32_t *node_owner /* [nnodes] */, int32_t my_rank);
+
+/* -- dof map: replaces gatherdofnums! (FieldModule.jl:304-314); validates the range checks of assemble!
+ *    (AssemblyModule.jl:268-273) once, at upload --------------------------------------------------------- */
+int32_t fegpu_dofmap_upload(fegpu_ctx *ctx, fegpu_mesh *mesh, int32_t ndn, const int64_t *dofnums /* nnodes x ndn col-major */,
+                            int64_t row_nalldofs, int64_t col_nalldofs, fegpu_dofmap **dofmap);
+int32_t fegpu_dofmap_destroy(fegpu_dofmap *dofmap);
+
+/* -- assembler ------------------------------------------------------------------------------------------ */
+int32_t fegpu_asm_create(fegpu_ctx *ctx, fegpu_asm **as);
+int32_t fegpu_asm_destroy(fegpu_asm *as);
+
+/* The three bilinear forms.  Each call = startassembly! + the whole element loop + makematrix!
+ * (the CSC stays on the device until fegpu_makematrix_copy). */
+/* bilform_diffusion, FEMMBaseModule.jl:1462-1535.  kappa_kind 0: scalar (kappa[1]) -> _iso path :1508;
+ * 1: mdim x mdim col-major -> _general path :1476 */
+int32_t fegpu_bilform_diffusion(fegpu_mesh *mesh, fegpu_dofmap *dofmap, int32_t kappa_kind, const double *kappa, fegpu_asm *as);
+/* bilform_lin_elastic with DeforModelRed3D, FEMMBaseModule.jl:1774-1813.  C: 6 x 6 col-major */
+int32_t fegpu_bilform_lin_elastic(fegpu_mesh *mesh, fegpu_dofmap *dofmap, const double *C, fegpu_asm *as);
+/* bilform_dot, FEMMBaseModule.jl:1335-1366.  c: ndn x ndn col-major; m: manifold dimension kwarg;
+ * otherdim: the constant other-dimension of the IntegDomain (IntegDomainModule.jl:150-152: 1.0) */
+int32_t fegpu_bilform_dot(fegpu_mesh *mesh, fegpu_dofmap *dofmap, const double *c, int32_t m, double otherdim, fegpu_asm *as);
+
+/* Generic assembler protocol for any other caller (AssemblyModule.jl:209-282): host triplets are staged to
+ * the device and the CSC is built there by a 64-bit key sort + segmented sum. */
+int32_t fegpu_startassembly(fegpu_asm *as, int64_t elem_mat_nrows, int64_t elem_mat_ncols, int64_t n_elem_mats,
+                            int64_t row_nalldofs, int64_t col_nalldofs);
+/* assemble!: mat is nrows x ncols col-major */
+int32_t fegpu_assemble(fegpu_asm *as, const double *mat, const int64_t *dofnums_row, int64_t nrows, const int64_t *dofnums_col,
+                       int64_t ncols);
+/* bulk form of the same: n ready triplets in emission order */
+int32_t fegpu_triplets_append(fegpu_asm *as, int64_t n, const int64_t *I, const int64_t *J, const double *V);
+/* makematrix!, AssemblyModule.jl:304-329 (= SparseArrays.sparse(I,J,V,m,n): duplicates summed left to right,
+ * explicit zeros kept, rows strictly increasing per column).  Builds the CSC on the device. */
+int32_t fegpu_makematrix(fegpu_asm *as);
+
+/* Result access.  sizes: after a bilform call or fegpu_makematrix. copy: straight into the arrays handed to
+ * SparseMatrixCSC(m, n, colptr, rowval, nzval): 1-based int64. */
+int32_t fegpu_makematrix_sizes(fegpu_asm *as, int64_t *nrows, int64_t *ncols, int64_t *nnz);
+int32_t fegpu_makematrix_copy(fegpu_asm *as, int64_t *colptr /* ncols+1 */, int64_t *rowval /* nnz */, double *nzval /* nnz */);
+/* nzval only (re-assembly on a cached pattern: colptr/rowval did not change) */
+int32_t fegpu_makematrix_copy_values(fegpu_asm *as, double *nzval);
+/* device pointers of the current result (valid until the next assembly on this assembler) */
+int32_t fegpu_makematrix_device(fegpu_asm *as, const int64_t **d_colptr, const int64_t **d_rowval, const double **d_nzval);
+/* raw COO of the last bilform assembly in the reference's emission order (setnomatrixresult(true) flows,
+ * AssemblyModule.jl:309-317): n = nelem*elmdim^2 triplets */
+int32_t fegpu_coo_copy(fegpu_asm *as, fegpu_mesh *mesh, fegpu_dofmap *dofmap, int64_t *I, int64_t *J, double *V);
+
+/* device milliseconds (CUDA events) of the phases of the last bilform / makematrix call:
+ * [0] element integration, [1] symbolic pattern build (0 when cached), [2] numeric CSC gather-sum or sort path,
+ * [3] whole call */
+int32_t fegpu_last_timings(fegpu_asm *as, double ms[4]);
+/* was the sparsity pattern of the last bilform call served from the cache (1) or built (0)? */
+int32_t fegpu_pattern_was_cached(fegpu_asm *as);
+/* forget a dofmap's cached pattern (forces the next assembly to rebuild it) */
+int32_t fegpu_pattern_invalidate(fegpu_dofmap *dofmap);
+
+#ifdef __cplusplus
+}
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#endif

@@ -1,0 +1,176 @@
+"""ctypes face of the CPU oracle (oracle/fe_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module; the product package (finetools.jl_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libfe_oracle.so")
+
+ET = {"T3": 1, "Q4": 2, "T4": 3, "T10": 4, "H8": 5, "H20": 6, "H27": 7}
+
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "fe_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libfe_oracle.so"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.orc_nne.argtypes = [C.c_int]
+        L.orc_mdim.argtypes = [C.c_int]
+        L.orc_bfun.argtypes = [C.c_int, _f64p, _f64p]
+        L.orc_bfundpar.argtypes = [C.c_int, _f64p, _f64p]
+        for f in (L.orc_gauss_rule,):
+            f.argtypes = [C.c_int, C.c_int, _f64p, _f64p]
+        L.orc_tet_rule.argtypes = [C.c_int, _f64p, _f64p]
+        L.orc_tri_rule.argtypes = [C.c_int, _f64p, _f64p]
+        L.orc_add_mggt_ut_only.argtypes = [_f64p, _f64p, C.c_double, C.c_int, C.c_int]
+        L.orc_add_mggt_ut_only.restype = None
+        L.orc_add_gkgt_ut_only.argtypes = [_f64p, _f64p, C.c_double, _f64p, _f64p, C.c_int, C.c_int]
+        L.orc_add_gkgt_ut_only.restype = None
+        L.orc_add_btdb_ut_only.argtypes = [_f64p, _f64p, C.c_double, _f64p, _f64p, C.c_int, C.c_int]
+        L.orc_add_btdb_ut_only.restype = None
+        L.orc_complete_lt.argtypes = [_f64p, C.c_int]
+        L.orc_complete_lt.restype = None
+        L.orc_assemble.argtypes = [_i64p, _i64p, _f64p, _i64p, _f64p, _i64p, C.c_int, _i64p, C.c_int, C.c_int64, C.c_int64]
+        common = [C.c_int, C.c_int64, _i64p, C.c_int64, C.c_int, _f64p]
+        L.orc_bilform_diffusion.argtypes = common + [_i64p, C.c_int64, C.c_int, _f64p, _f64p, C.c_int, _f64p, _i64p, _i64p, _f64p]
+        L.orc_bilform_lin_elastic.argtypes = common + [_i64p, C.c_int64, C.c_int, _f64p, _f64p, _f64p, _i64p, _i64p, _f64p]
+        L.orc_bilform_dot.argtypes = common + [C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double,
+                                               _i64p, _i64p, _f64p]
+        L.orc_sparse.argtypes = [C.c_int64, _i64p, _i64p, _f64p, C.c_int64, C.c_int64, _i64p, C.c_void_p, C.c_void_p]
+        L.orc_sparse.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+def _F(a):  # column-major (Julia) matrix -> flat C-contiguous buffer holding the column-major bytes
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).T).reshape(-1)
+
+
+def _I(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int64).T).reshape(-1)
+
+
+def bfun(et, pc):
+    n = lib().orc_nne(ET[et])
+    out = np.zeros(n)
+    lib().orc_bfun(ET[et], np.ascontiguousarray(pc, dtype=np.float64), out)
+    return out
+
+
+def bfundpar(et, pc):
+    n, m = lib().orc_nne(ET[et]), lib().orc_mdim(ET[et])
+    out = np.zeros(n * m)
+    lib().orc_bfundpar(ET[et], np.ascontiguousarray(pc, dtype=np.float64), out)
+    return out.reshape(m, n).T.copy()
+
+
+def gauss_rule(dim, order):
+    npts = order ** dim
+    pc, w = np.zeros(npts * dim), np.zeros(npts)
+    r = lib().orc_gauss_rule(dim, order, pc, w)
+    assert r == npts
+    return pc.reshape(dim, npts).T.copy(), w
+
+
+def tet_rule(npts):
+    pc, w = np.zeros(npts * 3), np.zeros(npts)
+    assert lib().orc_tet_rule(npts, pc, w) == npts
+    return pc.reshape(3, npts).T.copy(), w
+
+
+def tri_rule(npts):
+    pc, w = np.zeros(npts * 2), np.zeros(npts)
+    assert lib().orc_tri_rule(npts, pc, w) == npts
+    return pc.reshape(2, npts).T.copy(), w
+
+
+def _prep(et, conn, xyz, dofnums, pc, w):
+    conn = np.ascontiguousarray(conn, dtype=np.int64)
+    nelem, nne = conn.shape
+    assert nne == lib().orc_nne(ET[et])
+    xyz = np.asarray(xyz, dtype=np.float64)
+    nnodes, sdim = xyz.shape
+    dofnums = np.asarray(dofnums, dtype=np.int64).reshape(nnodes, -1)
+    ndn = dofnums.shape[1]
+    pc = np.asarray(pc, dtype=np.float64)
+    npts = pc.shape[0]
+    return conn, nelem, nne, _F(xyz), nnodes, sdim, _I(dofnums), ndn, _F(pc), np.ascontiguousarray(w, dtype=np.float64).reshape(-1), npts
+
+
+def bilform_diffusion_coo(et, conn, xyz, dofnums, nalldofs, pc, w, kappa):
+    """Reference-order COO triplets (I, J, V) of bilform_diffusion; kappa scalar -> iso path, matrix -> general."""
+    conn, nelem, nne, X, nnodes, sdim, dn, ndn, P, W, npts = _prep(et, conn, xyz, dofnums, pc, w)
+    assert ndn == 1
+    n = nelem * nne * nne
+    I, J, V = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n)
+    kind = 0 if np.ndim(kappa) == 0 else 1
+    kap = _F(np.atleast_2d(np.asarray(kappa, dtype=np.float64)))
+    rc = lib().orc_bilform_diffusion(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, dn, nalldofs, npts, P, W, kind, kap, I, J, V)
+    if rc:
+        raise RuntimeError(_ERR.get(rc, "oracle error %d" % rc))
+    return I, J, V
+
+
+def bilform_lin_elastic_coo(et, conn, xyz, dofnums, nalldofs, pc, w, Cmat):
+    conn, nelem, nne, X, nnodes, sdim, dn, ndn, P, W, npts = _prep(et, conn, xyz, dofnums, pc, w)
+    assert ndn == 3
+    n = nelem * (3 * nne) ** 2
+    I, J, V = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n)
+    rc = lib().orc_bilform_lin_elastic(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, dn, nalldofs, npts, P, W, _F(Cmat), I, J, V)
+    if rc:
+        raise RuntimeError(_ERR.get(rc, "oracle error %d" % rc))
+    return I, J, V
+
+
+def bilform_dot_coo(et, conn, xyz, dofnums, nalldofs, pc, w, c, m=3, otherdim=1.0):
+    conn, nelem, nne, X, nnodes, sdim, dn, ndn, P, W, npts = _prep(et, conn, xyz, dofnums, pc, w)
+    n = nelem * (ndn * nne) ** 2
+    I, J, V = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n)
+    cm = _F(np.asarray(c, dtype=np.float64).reshape(ndn, ndn))
+    rc = lib().orc_bilform_dot(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, ndn, dn, nalldofs, npts, P, W, cm, m, otherdim, I, J, V)
+    if rc:
+        raise RuntimeError(_ERR.get(rc, "oracle error %d" % rc))
+    return I, J, V
+
+
+_ERR = {1: "Column degree of freedom < 1", 2: "Column degree of freedom > size", 3: "Row degree of freedom < 1",
+        4: "Row degree of freedom > size", -2: "manifold/space dimension mismatch", -3: "That is the only acceptable option here."}
+
+
+def sparse(I, J, V, m, n):
+    """Julia's sparse(I,J,V,m,n): returns 1-based (colptr, rowval, nzval)."""
+    I = np.ascontiguousarray(I, dtype=np.int64)
+    J = np.ascontiguousarray(J, dtype=np.int64)
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    nt = I.size
+    colptr = np.zeros(n + 1, np.int64)
+    rowval = np.zeros(max(nt, 1), np.int64)
+    nzval = np.zeros(max(nt, 1))
+    nnz = lib().orc_sparse(nt, I, J, V, m, n, colptr, rowval.ctypes.data, nzval.ctypes.data)
+    if nnz < 0:
+        raise ValueError("row/column index out of range")
+    return colptr, rowval[:nnz].copy(), nzval[:nnz].copy()
+
+
+def to_scipy(colptr, rowval, nzval, m, n):
+    import scipy.sparse as sp
+    return sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(m, n))

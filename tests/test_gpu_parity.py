@@ -1,0 +1,340 @@
+"""GPU parity: the CUDA path through the C ABI versus the CPU oracle on the same inputs.
+colptr/rowval must be bit-exact, nzval within 1e-12 of the matrix max-abs (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import KAPPA3, isotropic_C
+from helpers import assert_parity, gpu_csc, make_field, oracle_csc
+
+pytestmark = pytest.mark.gpu
+
+
+def _mesh(fe, et, n=3):
+    dims = (1.3, 3.1, 2.7)
+    if et == "H8":
+        return fe.H8block(*dims, n, n + 1, n + 2)
+    if et == "H20":
+        return fe.H20block(*dims, n, n, n + 1)
+    if et == "H27":
+        return fe.H27block(*dims, n, n, n)
+    if et == "T4":
+        return fe.T4block(*dims, n, n + 1, n)
+    if et == "T10":
+        return fe.T10block(*dims, n, n, n + 1)
+    raise ValueError(et)
+
+
+def _distort(fens):
+    x = fens.xyz
+    h = 0.05
+    x[:, 0] += h * np.sin(3 * x[:, 1]) * np.cos(2 * x[:, 2])
+    x[:, 1] += h * np.sin(3 * x[:, 2]) * np.cos(2 * x[:, 0])
+    x[:, 2] += h * np.sin(3 * x[:, 0]) * np.cos(2 * x[:, 1])
+    return fens
+
+
+VOL_RULES = {"H8": ("gauss", 2), "H20": ("gauss", 3), "H27": ("gauss", 3), "T4": ("tet", 1), "T10": ("tet", 4)}
+
+
+def _rule(fe, et):
+    kind, k = VOL_RULES[et]
+    return fe.GaussRule(3, k) if kind == "gauss" else fe.TetRule(k)
+
+
+@pytest.mark.parametrize("et", ["H8", "H20", "H27", "T4", "T10"])
+@pytest.mark.parametrize("kappa", ["matrix", "scalar"])
+def test_diffusion_parity(fe, orc, gpu_ctx, et, kappa):
+    fens, fes = _mesh(fe, et)
+    _distort(fens)
+    u = make_field(fe, fens, 1)
+    rule = _rule(fe, et)
+    coef = KAPPA3 if kappa == "matrix" else 1.7
+    ref, _ = oracle_csc(orc, "diffusion", et, fes, fens, u, rule, coef)
+    got, _ = gpu_csc(fe, "diffusion", fes, fens, u, rule, coef)
+    assert_parity(ref, got)
+
+
+@pytest.mark.parametrize("et", ["H8", "H20", "H27", "T4", "T10"])
+def test_elastic_parity(fe, orc, gpu_ctx, et):
+    fens, fes = _mesh(fe, et, 2)
+    _distort(fens)
+    u = make_field(fe, fens, 3)
+    rule = _rule(fe, et)
+    C = isotropic_C()
+    C[0, 3] = C[3, 0] = 0.05  # a little anisotropy so every D entry matters
+    ref, _ = oracle_csc(orc, "elastic", et, fes, fens, u, rule, C)
+    got, _ = gpu_csc(fe, "elastic", fes, fens, u, rule, C)
+    assert_parity(ref, got)
+
+
+@pytest.mark.parametrize("et", ["H8", "H20", "H27", "T4", "T10"])
+@pytest.mark.parametrize("ndn", [1, 3])
+def test_dot_parity(fe, orc, gpu_ctx, et, ndn):
+    fens, fes = _mesh(fe, et, 2)
+    _distort(fens)
+    u = make_field(fe, fens, ndn)
+    rule = _rule(fe, et)
+    c = np.array([[1.0]]) if ndn == 1 else np.array([[2.0, 0.1, 0.0], [0.3, 1.0, 0.2], [0.0, 0.4, 3.0]])
+    ref, _ = oracle_csc(orc, "dot", et, fes, fens, u, rule, c)
+    got, _ = gpu_csc(fe, "dot", fes, fens, u, rule, c)
+    assert_parity(ref, got)
+
+
+@pytest.mark.parametrize("et,m", [("Q4", 2), ("T3", 2), ("Q4", 3)])
+def test_surface_dot_parity(fe, orc, gpu_ctx, et, m):
+    """Boundary mass on the Q4 / T3 skins of a volume block (config 5): sdim = 3, manifold dim = 2."""
+    if et == "Q4":
+        fens, vol = fe.H8block(1.3, 3.1, 2.7, 3, 4, 2)
+        rule = fe.GaussRule(2, 2)
+    else:
+        fens, vol = fe.T4block(1.3, 3.1, 2.7, 3, 4, 2)
+        rule = fe.TriRule(3)
+    _distort(fens)
+    bfes = fe.meshboundary(vol)
+    u = make_field(fe, fens, 1)
+    c = np.array([[1.0]])
+    ref, _ = oracle_csc(orc, "dot", et, bfes, fens, u, rule, c, m=m, otherdim=1.0)
+    got, _ = gpu_csc(fe, "dot", bfes, fens, u, rule, c, m=m)
+    assert_parity(ref, got)
+    # interior nodes have empty columns: colptr must still have ncols + 1 entries
+    assert got[0].size == u.nalldofs() + 1
+
+
+@pytest.mark.parametrize("et", ["Q4", "T3"])
+def test_planar_diffusion_parity(fe, orc, gpu_ctx, et):
+    fens, fes = (fe.Q4block(2.0, 1.0, 5, 4) if et == "Q4" else fe.T3block(2.0, 1.0, 5, 4))
+    u = make_field(fe, fens, 1)
+    rule = fe.GaussRule(2, 2) if et == "Q4" else fe.TriRule(3)
+    kap = np.array([[1.5, 0.2], [0.2, 2.5]])
+    ref, _ = oracle_csc(orc, "diffusion", et, fes, fens, u, rule, kap)
+    got, _ = gpu_csc(fe, "diffusion", fes, fens, u, rule, kap)
+    assert_parity(ref, got)
+
+
+def test_config1_h8_20cube(fe, orc, gpu_ctx):
+    """BASELINE config 1 + the fingerprints of SURVEY.md appendix B."""
+    fens, fes = fe.H8block(12.0, 1.1, 0.32, 20, 20, 20)
+    u = make_field(fe, fens, 1)
+    rule = fe.GaussRule(3, 2)
+    ref, _ = oracle_csc(orc, "diffusion", "H8", fes, fens, u, rule, KAPPA3)
+    got, a = gpu_csc(fe, "diffusion", fes, fens, u, rule, KAPPA3)
+    assert_parity(ref, got)
+    colptr, rowval, nzval = got[0], got[1], got[2]
+    assert nzval.size == 61 ** 3
+    np.testing.assert_array_equal(colptr[:5], [1, 9, 21, 33, 45])
+    np.testing.assert_array_equal(rowval[:8], [1, 2, 22, 23, 442, 443, 463, 464])
+    assert abs(nzval[0] - 0.88226262626262) < 1e-12
+
+
+def test_ebc_permuted_dofnums(fe, orc, gpu_ctx):
+    """Free-first / fixed-last numbering (FieldModule.jl:360-377) makes dofnums a non-trivial permutation."""
+    fens, fes = fe.H8block(1.3, 3.1, 2.7, 3, 3, 3)
+    u = make_field(fe, fens, 3, fixed_nodes=[1, 2, 3, 17, 40], fixed_comp=None)
+    fe.setebc(u, [5, 9], True, 2, 0.0)
+    fe.numberdofs(u)
+    rule = fe.GaussRule(3, 2)
+    C = isotropic_C()
+    ref, _ = oracle_csc(orc, "elastic", "H8", fes, fens, u, rule, C)
+    got, _ = gpu_csc(fe, "elastic", fes, fens, u, rule, C)
+    assert_parity(ref, got)
+
+
+def test_reassembly_is_bit_identical_and_cached(fe, orc, gpu_ctx):
+    """test/test_basics.jl:3039-3045: repeated assemblies with one assembler are bit-identical; the second one is
+    served from the cached pattern."""
+    fens, fes = fe.T10block(1.0, 1.0, 1.0, 3, 3, 3)
+    u = make_field(fe, fens, 1)
+    rule = fe.TetRule(4)
+    c = np.array([[1.0]])
+    a = fe.SysmatAssemblerSparseGPU(0.0)
+    femm = fe.FEMMBase(fe.IntegDomain(fes, rule))
+    geom = fe.NodalField(fens.xyz)
+    r1 = fe.bilform_dot(femm, a, geom, u, fe.DataCache(c), raw=True)
+    assert not a.pattern_was_cached()
+    r2 = fe.bilform_dot(femm, a, geom, u, fe.DataCache(c), raw=True)
+    assert a.pattern_was_cached()
+    r3 = fe.bilform_dot(femm, a, geom, u, fe.DataCache(c), raw=True)
+    for k in range(3):
+        np.testing.assert_array_equal(r1[k], r2[k])
+        np.testing.assert_array_equal(r1[k], r3[k])
+    # moved geometry, same pattern: values change, pattern arrays do not
+    geom.values[:, 0] *= 1.5
+    r4 = fe.bilform_dot(femm, a, geom, u, fe.DataCache(c), raw=True)
+    assert a.pattern_was_cached()
+    np.testing.assert_array_equal(r1[1], r4[1])
+    fens2 = fe.FENodeSet(geom.values)
+    ref, _ = oracle_csc(orc, "dot", "T10", fes, fens2, u, rule, c)
+    assert_parity(ref, r4)
+
+
+def test_raw_coo_matches_reference_emission_order(fe, orc, gpu_ctx):
+    fens, fes = fe.H8block(1.3, 3.1, 2.7, 2, 3, 2)
+    u = make_field(fe, fens, 1)
+    rule = fe.GaussRule(3, 2)
+    ref, (I, J, V) = oracle_csc(orc, "diffusion", "H8", fes, fens, u, rule, KAPPA3)
+    got, a = gpu_csc(fe, "diffusion", fes, fens, u, rule, KAPPA3)
+    gI, gJ, gV = a.coo()
+    np.testing.assert_array_equal(gI, I)
+    np.testing.assert_array_equal(gJ, J)
+    assert np.abs(gV - V).max() <= 1e-12 * np.abs(V).max()
+
+
+def test_generic_protocol_testA(fe, gpu_ctx):
+    """test/test_basics.jl:72-129: two dense blocks into a 7x7 matrix (known answer testA, tol 1e-5)."""
+    m1 = np.array([[0.24406, 0.599773, 0.833404, 0.0420141],
+                   [0.786024, 0.00206713, 0.995379, 0.780298],
+                   [0.845816, 0.198459, 0.355149, 0.224996]])
+    m1 = m1.T @ m1
+    i1 = [5, 2, 1, 4]
+    m2 = np.array([[0.146618, 0.53471, 0.614342, 0.737833],
+                   [0.479719, 0.41354, 0.00760941, 0.836455],
+                   [0.254868, 0.476189, 0.460794, 0.00919633],
+                   [0.159064, 0.261821, 0.317078, 0.77646],
+                   [0.643538, 0.429817, 0.59788, 0.958909]])
+    m2 = m2.T @ m2
+    i2 = [2, 3, 1, 5]
+    testA = np.array([[2.85928, 1.21875, 0.891063, 0.891614, 2.56958, 0.0, 0.0],
+                      [1.21875, 1.15515, 0.716396, 0.0714644, 1.56825, 0.0, 0.0],
+                      [0.891063, 0.716396, 0.936979, 0.0, 1.36026, 0.0, 0.0],
+                      [0.891614, 0.0714644, 0.0, 0.661253, 0.813892, 0.0, 0.0],
+                      [2.56958, 1.56825, 1.36026, 0.813892, 4.15934, 0.0, 0.0],
+                      [0.0] * 7, [0.0] * 7])
+    a = fe.SysmatAssemblerSparseGPU(0.0)
+    fe.startassembly(a, 5, 5, 3, 7, 7)
+    fe.assemble(a, m1, i1, i1)
+    fe.assemble(a, m2, i2, i2)
+    A = fe.makematrix(a)
+    assert np.abs(testA - A.toarray()).max() < 1.0e-5
+    # the assembler is reusable right away (AssemblyModule.jl:327)
+    fe.startassembly(a, 5, 5, 3, 7, 7)
+    fe.assemble(a, m1, i1, i1)
+    B = fe.makematrix(a)
+    M = np.zeros((7, 7))
+    M[np.ix_(np.array(i1) - 1, np.array(i1) - 1)] += m1
+    assert np.abs(M - B.toarray()).max() < 1e-14
+
+
+def test_generic_protocol_random_blocks_vs_sparse_oracle(fe, orc, gpu_ctx):
+    """test/test_basics.jl:2087-2172 pattern: many small blocks with repeated dofs, rectangular target; compared with the
+    oracle's sparse() bit for bit in colptr/rowval and to rounding in nzval (same left-to-right sum order => exact)."""
+    rng = np.random.default_rng(1234)
+    nr, nc = 137, 91
+    a = fe.SysmatAssemblerSparseGPU(0.0)
+    fe.startassembly(a, 4, 3, 10, nr, nc)  # deliberately undersized, like the reference's buffer-growth test
+    Is, Js, Vs = [], [], []
+    for _ in range(1500):
+        dr = rng.integers(1, nr + 1, size=4)
+        dc = rng.integers(1, nc + 1, size=3)
+        m = rng.standard_normal((4, 3))
+        fe.assemble(a, m, dr, dc)
+        for j in range(3):
+            for i in range(4):
+                Is.append(dr[i]); Js.append(dc[j]); Vs.append(m[i, j])
+    colptr, rowval, nzval, mm, nn = fe.makematrix(a, raw=True)
+    cp, rv, nz = orc.sparse(np.array(Is), np.array(Js), np.array(Vs), nr, nc)
+    assert (mm, nn) == (nr, nc)
+    np.testing.assert_array_equal(colptr, cp)
+    np.testing.assert_array_equal(rowval, rv)
+    np.testing.assert_array_equal(nzval, nz)  # same summation order: bit-exact
+
+
+def test_dof_range_errors_use_reference_strings(fe, gpu_ctx):
+    a = fe.SysmatAssemblerSparseGPU(0.0)
+    fe.startassembly(a, 2, 2, 1, 5, 5)
+    with pytest.raises(fe.FEGPUError, match="Row degree of freedom > size"):
+        fe.assemble(a, np.eye(2), [1, 6], [1, 2])
+    with pytest.raises(fe.FEGPUError, match="Column degree of freedom < 1"):
+        fe.assemble(a, np.eye(2), [1, 2], [0, 2])
+    with pytest.raises(fe.FEGPUError, match="Wrong size of matrix"):
+        fe.assemble(a, np.eye(3), [1, 2], [1, 2])
+    # through the form path: a dof number beyond nalldofs is caught at upload
+    fens, fes = fe.H8block(1, 1, 1, 2, 2, 2)
+    u = make_field(fe, fens, 1)
+    u.dofnums[3, 0] = u.nalldofs() + 5
+    with pytest.raises(fe.FEGPUError, match="degree of freedom > size"):
+        gpu_csc(fe, "diffusion", fes, fens, u, fe.GaussRule(3, 2), KAPPA3)
+
+
+def test_non_injective_dofmap_takes_sort_path(fe, orc, gpu_ctx):
+    """Two nodes tied to one dof (periodic-style numbering): the mesh-structured pattern does not apply; the generic
+    sort path must give the reference's sparse() result."""
+    fens, fes = fe.H8block(1.0, 1.0, 1.0, 3, 2, 2)
+    u = make_field(fe, fens, 1)
+    u.dofnums[u.dofnums == u.nalldofs()] = 1  # last node shares dof 1
+    rule = fe.GaussRule(3, 2)
+    ref, _ = oracle_csc(orc, "diffusion", "H8", fes, fens, u, rule, KAPPA3)
+    got, _ = gpu_csc(fe, "diffusion", fes, fens, u, rule, KAPPA3)
+    assert_parity(ref, got)
+
+
+def test_degenerate_element_takes_sort_path(fe, orc, gpu_ctx):
+    """A collapsed hexahedron (one node listed twice) is legal input for assemble!; duplicates inside one element
+    matrix are summed by sparse()."""
+    fens, fes = fe.H8block(1.0, 1.0, 1.0, 2, 2, 2)
+    fes.conn[0, 1] = fes.conn[0, 0]
+    u = make_field(fe, fens, 1)
+    rule = fe.GaussRule(3, 2)
+    c = np.array([[1.0]])
+    ref, _ = oracle_csc(orc, "dot", "H8", fes, fens, u, rule, c)
+    got, _ = gpu_csc(fe, "dot", fes, fens, u, rule, c)
+    assert_parity(ref, got)
+
+
+@pytest.mark.parametrize("nparts", [2, 4])
+def test_row_block_partition_reassembles_the_matrix(fe, orc, gpu_ctx, nparts):
+    """Multi-GPU semantics on one device: rank p keeps the rows of its nodes; the blocks are disjoint and their union is
+    the single-GPU matrix (same pattern, values to rounding)."""
+    fens, fes = fe.H8block(1.0, 1.0, 1.0, 4, 3, 6)
+    u = make_field(fe, fens, 3)
+    rule = fe.GaussRule(3, 2)
+    C = isotropic_C()
+    ref, _ = oracle_csc(orc, "elastic", "H8", fes, fens, u, rule, C)
+    n = u.nalldofs()
+    import scipy.sparse as sp
+    full = sp.csc_matrix((ref[2], ref[1] - 1, ref[0] - 1), shape=(n, n))
+    owner = fe.slab_owner(fens.count(), nparts)
+    total = sp.csc_matrix((n, n))
+    nnz_sum = 0
+    for p in range(nparts):
+        got, _ = gpu_csc(fe, "elastic", fes, fens, u, rule, C, node_owner=owner, my_rank=p)
+        colptr, rowval, nzval, mm, nn = got
+        blk = sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(n, n))
+        rows_owned = np.zeros(n, bool)
+        rows_owned[(u.dofnums[owner == p] - 1).reshape(-1)] = True
+        assert rows_owned[rowval - 1].all()
+        # rows strictly increasing inside every column
+        for j in range(0, n, 7):
+            seg = rowval[colptr[j] - 1: colptr[j + 1] - 1]
+            assert np.all(np.diff(seg) > 0)
+        nnz_sum += nzval.size
+        total = total + blk
+    assert nnz_sum == ref[2].size
+    diff = (total - full)
+    assert abs(diff).max() <= 1e-12 * np.abs(ref[2]).max()
+
+
+def test_full_size_config2_properties(fe, gpu_ctx):
+    """BASELINE config 2 at full size (128^3 H8 elasticity, 2.1 M elements, 1.2 G triplets): size-independent properties.
+    nnz = 9*385^3; K is exactly symmetric (the element triangle is mirrored); rigid translations are in the null space."""
+    n = 128
+    fens, fes = fe.H8block(1.0, 1.0, 1.0, n, n, n)
+    u = make_field(fe, fens, 3)
+    rule = fe.GaussRule(3, 2)
+    a = fe.SysmatAssemblerSparseGPU(0.0)
+    femm = fe.FEMMBase(fe.IntegDomain(fes, rule))
+    geom = fe.NodalField(fens.xyz)
+    K = fe.bilform_lin_elastic(femm, a, geom, u, fe.DeforModelRed3D, fe.DataCache(isotropic_C()))
+    assert K.nnz == 9 * 385 ** 3
+    assert K.shape == (3 * 129 ** 3, 3 * 129 ** 3)
+    ip = K.indptr
+    assert np.all(np.diff(ip) > 0)
+    scale = np.abs(K.data).max()
+    for comp in range(3):
+        v = np.zeros(K.shape[0])
+        v[u.dofnums[:, comp] - 1] = 1.0
+        assert np.abs(K @ v).max() <= 1e-10 * scale
+    # symmetry on a sampled set of columns (full transpose of 513 M entries is too slow for a test)
+    cols = np.arange(0, K.shape[0], 50021)
+    sub = K[:, cols].tocoo()
+    vals_t = np.asarray(K[cols[sub.col], sub.row]).reshape(-1)
+    np.testing.assert_array_equal(vals_t, sub.data)
