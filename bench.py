@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- elements/s assembled into CSC on B200 (BASELINE.json metric).
+
+Workload (N = 1): BASELINE.json configs[1] -- bilform_lin_elastic on a 128^3 H8 block (2 097 152 elements, 24x24 element
+matrices, 1 207 959 552 triplets, nnz = 9*385^3 = 513 599 625), GaussRule(3,2), isotropic C (E = 1, nu = 0.3).
+N > 1 (weak scaling): the block grows to 128 x 128 x 128N elements and is split into N node-owned row blocks (z-slabs,
+contiguous node ranges); every rank integrates the elements touching its nodes (halo recomputed) and builds the CSC of
+its rows; no collective on the data path.
+
+A "step" is one complete fresh assembly: element integration -> triplet values -> symbolic pattern -> CSC gather-sum.
+The sparsity-pattern cache is INVALIDATED before every timed step so no work is skipped; the cached re-assembly rate is
+reported separately under "cached".
+
+  value  : inputs resident in HBM, CUDA-event time over K steps (max over ranks)
+  e2e    : same step through the public Python API (the reference's call shape) with host buffers: coordinates go
+           host->device and colptr/rowval/nzval come back device->host inside the timed region
+  --impl reference : the CPU oracle (C restatement of FinEtools.jl's serial path; Julia is not available) on a bounded
+           sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "elements/s assembled into CSC (H8 lin_elastic stiffness, fresh assembly incl. pattern build)"
+UNIT = "elements/s"
+N_EDGE = 128
+FLOPS_PER_ELEM = 51936          # H8 lin_elastic as the reference executes it
+BYTES_INTEGRATE = 64 + 8 * 576 + 49      # conn + values (8 B/triplet, keys are never materialised) + amortised node data
+BYTES_GATHER_PER_ELEM = 8 * 576          # V read; nzval/rowval/index traffic is added per nnz below
+
+
+def isotropic_C(E=1.0, nu=0.3):
+    lam = E * nu / ((1 + nu) * (1 - 2 * nu))
+    mu = E / (2 * (1 + nu))
+    C = np.zeros((6, 6))
+    C[:3, :3] = lam
+    C[np.arange(3), np.arange(3)] += 2 * mu
+    C[3:, 3:] = mu * np.eye(3)
+    return C
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_run(n_edge, threads):
+    """One assembly of an n_edge^3 H8 elasticity block with the CPU oracle.  threads == 1 is the reference's own serial
+    path; threads > 1 shards the ELEMENT LOOP over threads writing disjoint slices of one COO buffer (what
+    FinEtoolsMultithreading does for the reference) and keeps the serial sparse()."""
+    import finetools_jl_b200 as fe   # host-side mesh generator only
+    from oracle import oracle as orc
+    fens, fes = fe.H8block(1.0, 1.0, 1.0, n_edge, n_edge, n_edge)
+    u = fe.NodalField(np.zeros((fens.count(), 3)))
+    fe.numberdofs(u)
+    rule = fe.GaussRule(3, 2)
+    C = isotropic_C()
+    nall = u.nalldofs()
+    nel = fes.count()
+    t0 = time.perf_counter()
+    if threads <= 1:
+        I, J, V = orc.bilform_lin_elastic_coo("H8", fes.conn, fens.xyz, u.dofnums, nall, rule.param_coords, rule.weights, C)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        nt = nel * 576
+        I, J, V = np.empty(nt, np.int64), np.empty(nt, np.int64), np.empty(nt)
+        bounds = np.linspace(0, nel, threads + 1).astype(np.int64)
+
+        def work(k):
+            lo, hi = int(bounds[k]), int(bounds[k + 1])
+            sl = slice(lo * 576, hi * 576)
+            orc.bilform_lin_elastic_coo("H8", fes.conn[lo:hi], fens.xyz, u.dofnums, nall, rule.param_coords, rule.weights, C,
+                                        out=(I[sl], J[sl], V[sl]))
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(work, range(threads)))
+    t1 = time.perf_counter()
+    colptr, rowval, nzval = orc.sparse(I, J, V, nall, nall)
+    t2 = time.perf_counter()
+    return nel, t2 - t0, t1 - t0, t2 - t1, nzval.size
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    threads = args.ref_threads if args.ref_threads > 0 else (os.cpu_count() or 1)
+    n = args.ref_edge
+    for _ in range(args.warmup):
+        cpu_reference_run(n, threads)
+    t = 0.0
+    nel = 0
+    for _ in range(args.steps):
+        ne, dt, _, _, _ = cpu_reference_run(n, threads)
+        t += dt
+        nel += ne
+    val = nel / t
+    sample = "%d^3 H8 lin_elastic block (%d elements) per step; element loop on %d process(es), serial sparse()" % (n, n ** 3, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: bilform_lin_elastic, H8 block, GaussRule(3,2) -- bounded sample", "sample_edge": n},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "C restatement of FinEtools.jl v8.2.11 (oracle/fe_oracle.c); Julia is not installed on this image"}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import finetools_jl_b200 as fe
+    from finetools_jl_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = N_EDGE
+    nz_edge = n * world
+    fens, fes = fe.H8block(1.0, 1.0, float(world), n, n, nz_edge)
+    u = fe.NodalField(np.zeros((fens.count(), 3)))
+    fe.numberdofs(u)
+    rule = fe.GaussRule(3, 2)
+    C = isotropic_C()
+    nelem_global = fes.count()
+    owner = fe.slab_owner(fens.count(), world) if world > 1 else None
+
+    ctx = fe.GPUContext(local_rank, stream=torch.cuda.current_stream().cuda_stream)
+    a = fe.SysmatAssemblerSparseGPU(0.0, ctx=ctx)
+    femm = fe.FEMMBase(fe.IntegDomain(fes, rule))
+    geom = fe.NodalField(fens.xyz)
+    cache = fe.DataCache(C)
+    L = _lib.lib()
+
+    # first call: uploads, builds everything (also the warm-up of the allocator)
+    fe.bilform_lin_elastic(femm, a, geom, u, fe.DeforModelRed3D, cache, raw=True, node_owner=owner, my_rank=rank)
+    dmesh = a._device_cache[id(fes)]
+    dof = dmesh.dofmap(u)
+    Cf = np.asfortranarray(C)
+    m_, n_, nnz_local = a.sizes()
+
+    def device_step(fresh=True):
+        if fresh:
+            _lib.check(L.fegpu_pattern_invalidate(dof), ctx.handle)
+        _lib.check(L.fegpu_bilform_lin_elastic(dmesh.handle, dof, _lib.fptr(Cf), a.handle), ctx.handle)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    ctx.set_async(True)
+    launches0 = ctx.launch_count()
+    for _ in range(args.warmup):
+        device_step(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches1 = ctx.launch_count()
+    phase = np.zeros(4)
+
+    def step_and_log():
+        device_step(True)
+
+    ms_total = timed(step_and_log, args.steps)
+    launches = ctx.launch_count() - launches1
+    # per-phase device times of ONE fresh step (library CUDA events on the launching stream)
+    phases = []
+    for _ in range(max(3, min(args.steps, 5))):
+        device_step(True)
+        ctx.synchronize()
+        phases.append(a.timings())
+    ph = {k: float(np.median([p[k] for p in phases])) for k in phases[0]}
+    # cached re-assembly (pattern reused: integration + gather-sum only)
+    for _ in range(2):
+        device_step(False)
+    ms_cached = timed(lambda: device_step(False), args.steps)
+    cached_ph = []
+    for _ in range(3):
+        device_step(False)
+        ctx.synchronize()
+        cached_ph.append(a.timings())
+    cph = {k: float(np.median([p[k] for p in cached_ph])) for k in cached_ph[0]}
+    clocks = sampler.stop() if rank == 0 else None
+    ctx.set_async(False)
+
+    # ---- e2e through the public API with host buffers (pinned result arrays, as a Julia shim would allocate once)
+    m_, n_, nnz_local = a.sizes()
+    pin = lambda cnt, dt: torch.empty(cnt, dtype=dt, pin_memory=True).numpy()
+    out = (pin(n_ + 1, torch.int64), pin(max(nnz_local, 1), torch.int64)[:nnz_local], pin(max(nnz_local, 1), torch.float64)[:nnz_local])
+
+    def e2e_step():
+        # the public call a user makes: coordinates host->device, fresh pattern, full CSC device->host
+        a.invalidate_patterns()
+        fe.bilform_lin_elastic(femm, a, geom, u, fe.DeforModelRed3D, cache, raw=True, node_owner=owner, my_rank=rank, out=out)
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = fens.xyz.size * 8
+    d2h = (n_ + 1) * 8 + nnz_local * 16
+
+    nnz_total = nnz_local
+    nactive_local = None
+    if dist is not None:
+        t = torch.tensor([nnz_local], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        nnz_total = int(t.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms_total / args.steps
+    value = nelem_global / (ms_step * 1e-3)
+    hbm_peak, peak_kind = measured_peaks()
+    nel_rank = nelem_global / world
+    # dominant kernel by device time: integration (k_h8_elastic) or the numeric gather (k_gather)
+    integ_gbs = BYTES_INTEGRATE * nel_rank / (ph["integrate_ms"] * 1e-3) / 1e9
+    gather_bytes = BYTES_GATHER_PER_ELEM * nel_rank + nnz_local * 8
+    gather_gbs = gather_bytes / (ph["numeric_ms"] * 1e-3) / 1e9
+    if ph["integrate_ms"] >= ph["numeric_ms"]:
+        dom = {"kernel": "k_h8_elastic", "achieved": integ_gbs}
+    else:
+        dom = {"kernel": "k_gather<3>", "achieved": gather_gbs}
+    peaks = ctx.measure_peaks()
+    roofline = {"bound": "hbm", "achieved": dom["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["achieved"] / hbm_peak,
+                "traffic": None, "kernel": dom["kernel"], "peak_kind": peak_kind,
+                "kernels": {"k_h8_elastic": {"ms": ph["integrate_ms"], "algorithmic_GBps": integ_gbs,
+                                             "algorithmic_TFLOPs": FLOPS_PER_ELEM * nel_rank / (ph["integrate_ms"] * 1e-3) / 1e12,
+                                             "dfma_peak_TFLOPs_measured": peaks["dfma_tflops"]},
+                            "symbolic(pattern build)": {"ms": ph["symbolic_ms"]},
+                            "k_gather<3>": {"ms": ph["numeric_ms"], "algorithmic_GBps": gather_gbs}},
+                "copy_gbs_measured_here": peaks["copy_gbs"]}
+
+    # bounded serial CPU baseline (the reference's own single-threaded path)
+    from oracle import oracle as orc
+    orc.build()
+    ne, dt, t_form, t_sparse, _ = cpu_reference_run(args.cpu_edge, 1)
+    cpu = {"value": ne / dt, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": "%d^3 H8 lin_elastic block (%d elements), one serial pass: element loop %.2f s + sparse() %.2f s; host has %d cores"
+                     % (args.cpu_edge, ne, t_form, t_sparse, os.cpu_count() or 0)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: bilform_lin_elastic, H8 block 128x128x%d (%d elements, %d nnz), GaussRule(3,2), "
+                               "isotropic C; %s" % (nz_edge, nelem_global, nnz_total,
+                                                    "single GPU" if world == 1 else "%d node-owned row blocks (z-slabs), halo recomputed" % world),
+                   "l2": "working set (9.7 GB triplet values per rank) >> 126 MB L2; no flush needed",
+                   "step": "fresh assembly: pattern cache invalidated before every step"},
+        "clocks": clocks,
+        "e2e": {"value": nelem_global / (e2e_s / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "note": "per rank: xyz H2D + full CSC (colptr,rowval,nzval) D2H into pinned host arrays"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "phases_ms": ph,
+        "cached": {"value": nelem_global / (ms_cached / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms_cached / args.steps,
+                   "phases_ms": cph, "note": "re-assembly on the cached pattern (integration + gather-sum), reported separately"},
+        "nnz_per_s_csc_construction": nnz_total / ((ph["symbolic_ms"] + ph["numeric_ms"]) * 1e-3),
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--ref-threads", type=int, default=0, help="reference arm: processes for the element loop (0 = all cores)")
+    ap.add_argument("--ref-edge", type=int, default=48, help="reference arm: block edge of the bounded sample")
+    ap.add_argument("--cpu-edge", type=int, default=40, help="cpu_baseline leg: block edge of the bounded serial sample")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -92,9 +92,10 @@ class SysmatAssemblerSparseGPU(AbstractSysmatAssembler):
         check(_lib.lib().fegpu_assemble(self.handle, fptr(m), fptr(dr), dr.size, fptr(dc), dc.size), self.ctx.handle)
         return self
 
-    def makematrix(self, raw=False):
+    def makematrix(self, raw=False, out=None):
         """Returns scipy.sparse.csc_matrix (raw=False) or the 1-based (colptr, rowval, nzval, m, n) arrays exactly as they
-        would be handed to Julia's SparseMatrixCSC(m, n, colptr, rowval, nzval) (raw=True)."""
+        would be handed to Julia's SparseMatrixCSC(m, n, colptr, rowval, nzval) (raw=True).  `out` = preallocated
+        (colptr, rowval, nzval) host arrays to fill (e.g. pinned), like a shim that reuses its result buffers."""
         L = _lib.lib()
         if self._mode == "generic":
             if self._nomatrixresult:
@@ -106,7 +107,7 @@ class SysmatAssemblerSparseGPU(AbstractSysmatAssembler):
             raise _lib.FEGPUError(-17, "makematrix! before any assembly")
         elif self._nomatrixresult:
             return self._zeros(raw)
-        return self._fetch(raw)
+        return self._fetch(raw, out)
 
     # ---- helpers ------------------------------------------------------------------------------------------
     def setnomatrixresult(self, flag):
@@ -165,6 +166,12 @@ class SysmatAssemblerSparseGPU(AbstractSysmatAssembler):
         check(_lib.lib().fegpu_last_timings(self.handle, ms), self.ctx.handle)
         return {"integrate_ms": ms[0], "symbolic_ms": ms[1], "numeric_ms": ms[2], "total_ms": ms[3]}
 
+    def invalidate_patterns(self):
+        """Drop every cached sparsity pattern held for this assembler's meshes (next assembly rebuilds it)."""
+        for dm in self._device_cache.values():
+            for _, _, h in dm.dofmaps:
+                check(_lib.lib().fegpu_pattern_invalidate(h), self.ctx.handle)
+
     def pattern_was_cached(self):
         return bool(_lib.lib().fegpu_pattern_was_cached(self.handle))
 
@@ -185,8 +192,8 @@ def assemble(a, mat, dofnums_row, dofnums_col):
     return a.assemble(mat, dofnums_row, dofnums_col)
 
 
-def makematrix(a, raw=False):
-    return a.makematrix(raw=raw)
+def makematrix(a, raw=False, out=None):
+    return a.makematrix(raw=raw, out=out)
 
 
 def setnomatrixresult(a, flag):

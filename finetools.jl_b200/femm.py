@@ -150,15 +150,15 @@ def _prepare(self, assembler, geom, u, node_owner=None, my_rank=0):
     return fes, dmesh, dof
 
 
-def _finish(assembler, fes, dmesh, dof, u, raw):
+def _finish(assembler, fes, dmesh, dof, u, raw, out=None):
     elmdim = fes.nne * u.ndofs()
     assembler._mode = "form"
     assembler._row_nalldofs = assembler._col_nalldofs = u.nalldofs()
     assembler._pending_form = (dmesh.handle, dof, fes.count() * elmdim * elmdim if dmesh.partition_key is None else None)
-    return assembler.makematrix(raw=raw)
+    return assembler.makematrix(raw=raw, out=out)
 
 
-def bilform_diffusion(self, assembler, geom, u, cf, raw=False, node_owner=None, my_rank=0):
+def bilform_diffusion(self, assembler, geom, u, cf, raw=False, node_owner=None, my_rank=0, out=None):
     """K_ij = int grad(N_i) . kappa . grad(N_j): scalar DataCache -> _iso path, matrix -> _general path."""
     _eligible(self, assembler, geom, u, cf)
     if u.ndofs() != 1:
@@ -174,10 +174,10 @@ def bilform_diffusion(self, assembler, geom, u, cf, raw=False, node_owner=None, 
             raise FEGPUError(-2, "conductivity matrix must be mdim x mdim")
         kind, k = 1, np.asfortranarray(kap)
     check(_lib.lib().fegpu_bilform_diffusion(dmesh.handle, dof, kind, fptr(k), assembler.handle), assembler.ctx.handle)
-    return _finish(assembler, fes, dmesh, dof, u, raw)
+    return _finish(assembler, fes, dmesh, dof, u, raw, out)
 
 
-def bilform_lin_elastic(self, assembler, geom, u, mr, cf, raw=False, node_owner=None, my_rank=0):
+def bilform_lin_elastic(self, assembler, geom, u, mr, cf, raw=False, node_owner=None, my_rank=0, out=None):
     """K = int B' C B with the 3-D strain-displacement matrix (mr must be DeforModelRed3D)."""
     _eligible(self, assembler, geom, u, cf)
     if mr is not DeforModelRed3D and not isinstance(mr, DeforModelRed3D):
@@ -190,10 +190,10 @@ def bilform_lin_elastic(self, assembler, geom, u, mr, cf, raw=False, node_owner=
     fes, dmesh, dof = _prepare(self, assembler, geom, u, node_owner, my_rank)
     Cf = np.asfortranarray(Cm)
     check(_lib.lib().fegpu_bilform_lin_elastic(dmesh.handle, dof, fptr(Cf), assembler.handle), assembler.ctx.handle)
-    return _finish(assembler, fes, dmesh, dof, u, raw)
+    return _finish(assembler, fes, dmesh, dof, u, raw, out)
 
 
-def bilform_dot(self, assembler, geom, u, cf, m=3, raw=False, node_owner=None, my_rank=0):
+def bilform_dot(self, assembler, geom, u, cf, m=3, raw=False, node_owner=None, my_rank=0, out=None):
     """M_ij = int N_i c N_j over the m-dimensional manifold Jacobian."""
     _eligible(self, assembler, geom, u, cf)
     ndn = u.ndofs()
@@ -206,7 +206,7 @@ def bilform_dot(self, assembler, geom, u, cf, m=3, raw=False, node_owner=None, m
     cfm = np.asfortranarray(c)
     check(_lib.lib().fegpu_bilform_dot(dmesh.handle, dof, fptr(cfm), int(m), float(self.integdomain.otherdimension), assembler.handle),
           assembler.ctx.handle)
-    return _finish(assembler, fes, dmesh, dof, u, raw)
+    return _finish(assembler, fes, dmesh, dof, u, raw, out)
 
 
 def innerproduct(self, assembler, geom, afield, raw=False):

@@ -10,7 +10,25 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libfe_oracle.so")
+
+
+def _cpu_tag():
+    """The oracle is compiled -march=native (it doubles as the timed CPU baseline), so the binary is keyed by the host's
+    CPU feature flags: a .so built in the build container is never loaded on a different CPU."""
+    import hashlib
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    flags = line
+                    break
+    except OSError:
+        pass
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
+_SO = os.path.join(_HERE, "libfe_oracle.%s.so" % _cpu_tag())
 
 ET = {"T3": 1, "Q4": 2, "T4": 3, "T10": 4, "H8": 5, "H20": 6, "H27": 7}
 
@@ -21,7 +39,7 @@ _f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 def build(force=False):
     src = os.path.join(_HERE, "fe_oracle.c")
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-B", "libfe_oracle.so"], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", _HERE, "-B", "OUT=" + os.path.basename(_SO)], stdout=subprocess.DEVNULL)
     return _SO
 
 
@@ -130,11 +148,14 @@ def bilform_diffusion_coo(et, conn, xyz, dofnums, nalldofs, pc, w, kappa):
     return I, J, V
 
 
-def bilform_lin_elastic_coo(et, conn, xyz, dofnums, nalldofs, pc, w, Cmat):
+def bilform_lin_elastic_coo(et, conn, xyz, dofnums, nalldofs, pc, w, Cmat, out=None):
+    """out = preallocated (I, J, V) contiguous slices for these elements (lets several threads fill one COO buffer;
+    ctypes drops the GIL during the call)."""
     conn, nelem, nne, X, nnodes, sdim, dn, ndn, P, W, npts = _prep(et, conn, xyz, dofnums, pc, w)
     assert ndn == 3
     n = nelem * (3 * nne) ** 2
-    I, J, V = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n)
+    I, J, V = out if out is not None else (np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n))
+    assert I.size == n
     rc = lib().orc_bilform_lin_elastic(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, dn, nalldofs, npts, P, W, _F(Cmat), I, J, V)
     if rc:
         raise RuntimeError(_ERR.get(rc, "oracle error %d" % rc))
