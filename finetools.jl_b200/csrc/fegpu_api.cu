@@ -135,6 +135,13 @@ int32_t fegpu_create(fegpu_ctx **out, int32_t device) {
   cudaDeviceProp prop;
   CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
+  {  // stream-ordered allocator: never hand freed blocks back to the OS, so re-building a pattern costs no cudaMalloc
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   *out = ctx;
   return FEGPU_OK;
 }

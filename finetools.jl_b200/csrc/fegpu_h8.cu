@@ -160,15 +160,21 @@ __device__ __forceinline__ void block_acc(double *k9, const double *ga, const do
 
 constexpr int EL_MSTRIDE = 578;           // staged element-matrix stride (doubles): 576 + pad against bank conflicts
 
-// Phase B + staging for the warp owning column nodes B1 = T and B2 = 7 - T.  Everything indexed by T is static.
-// Warps run different instantiations of phase B, so the CTA-wide barriers inside it are spelled as a named
-// barrier (id 1, 128 threads): arrival is counted per barrier id, not per program counter.
+// Phase B + staging for the warp owning column nodes B1 = t and B2 = 7 - t.  All warps run the SAME code (t is a
+// warp-uniform runtime value): slots 0..4 always belong to column B2, slot 8 always to B1, slots 5..7 to B2 iff
+// s < 8 - t.  One DB column is live at a time.  (A fully static 4-way instantiation was 61 KB of SASS and starved the
+// 32 KB instruction cache: 49 % of the stall samples were "no_instructions".)
+// CTA-wide barrier of phase B spelled as a named barrier (id 1, 128 threads).
 __device__ __forceinline__ void block_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int T>
-__device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, const int64_t slot0, const H8Params &P) {
-  constexpr int B1 = T, B2 = 7 - T;
-  constexpr int NB2 = 8 - T;  // blocks (a = 0..7-T, B2); then blocks (a = 0..T, B1): 9 in total
+__device__ __forceinline__ void load3(double *d, const double *g, int node) {
+  d[0] = g[(node * 3 + 0) * EL_EPB];
+  d[1] = g[(node * 3 + 1) * EL_EPB];
+  d[2] = g[(node * 3 + 2) * EL_EPB];
+}
+
+__device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, const int t, const int64_t slot0, const H8Params &P) {
+  const int B1 = t, B2 = 7 - t, NB2 = 8 - t;
   double K[9][9];
 #pragma unroll
   for (int s = 0; s < 9; s++)
@@ -178,23 +184,30 @@ __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, cons
   for (int j = 0; j < 8; j++) {
     const double *g = sm + (size_t)j * EL_GSTRIDE * EL_EPB + lane;
     const double Jw = g[24 * EL_EPB];
-    double gb[3], DB[18];
-    gb[0] = g[(B2 * 3 + 0) * EL_EPB]; gb[1] = g[(B2 * 3 + 1) * EL_EPB]; gb[2] = g[(B2 * 3 + 2) * EL_EPB];
+    double gb[3], ga[3], DB[18];
+    load3(gb, g, B2);
     db_col(gb, Jw, DB);
 #pragma unroll
-    for (int a = 0; a < NB2; a++) {
-      double ga[3];
-      ga[0] = g[(a * 3 + 0) * EL_EPB]; ga[1] = g[(a * 3 + 1) * EL_EPB]; ga[2] = g[(a * 3 + 2) * EL_EPB];
-      block_acc(K[a], ga, DB);
+    for (int s = 0; s < 5; s++) {
+      load3(ga, g, s);
+      block_acc(K[s], ga, DB);
     }
-    gb[0] = g[(B1 * 3 + 0) * EL_EPB]; gb[1] = g[(B1 * 3 + 1) * EL_EPB]; gb[2] = g[(B1 * 3 + 2) * EL_EPB];
+#pragma unroll
+    for (int s = 5; s < 8; s++)
+      if (s < NB2) {
+        load3(ga, g, s);
+        block_acc(K[s], ga, DB);
+      }
+    load3(gb, g, B1);
     db_col(gb, Jw, DB);
 #pragma unroll
-    for (int a = 0; a <= T; a++) {
-      double ga[3];
-      ga[0] = g[(a * 3 + 0) * EL_EPB]; ga[1] = g[(a * 3 + 1) * EL_EPB]; ga[2] = g[(a * 3 + 2) * EL_EPB];
-      block_acc(K[NB2 + a], ga, DB);
-    }
+    for (int s = 5; s < 8; s++)
+      if (s >= NB2) {
+        load3(ga, g, s - NB2);
+        block_acc(K[s], ga, DB);
+      }
+    load3(ga, g, t);  // slot 8: block (a = t, b = B1), the diagonal block of column B1
+    block_acc(K[8], ga, DB);
   }
   block_bar();  // everyone is done reading G: the staging buffer may overwrite it
 
@@ -206,17 +219,18 @@ __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, cons
       for (int s = 0; s < 9; s++) {
         const int a = (s < NB2) ? s : s - NB2;
         const int b = (s < NB2) ? B2 : B1;
+        const bool diag = (a == b);
+        double *Mu = M + (b * 3) * 24 + a * 3;  // (row a-block, column b-block)
+        double *Ml = M + (a * 3) * 24 + b * 3;  // mirrored block
 #pragma unroll
         for (int jx = 0; jx < 3; jx++)
 #pragma unroll
-          for (int ix = 0; ix < 3; ix++) {
-            const int r = a * 3 + ix, c = b * 3 + jx;
-            if (a != b || r <= c) {  // diagonal block: only its upper triangle is the reference's value
+          for (int ix = 0; ix < 3; ix++)
+            if (!diag || ix <= jx) {  // diagonal block: only its upper triangle is the reference's value
               const double v = K[s][ix + 3 * jx];
-              M[c * 24 + r] = v;
-              M[r * 24 + c] = v;  // complete_lt!
+              Mu[jx * 24 + ix] = v;
+              Ml[ix * 24 + jx] = v;  // complete_lt!
             }
-          }
       }
     }
     block_bar();
@@ -279,12 +293,7 @@ __global__ void __launch_bounds__(128, 2) k_h8_elastic(const H8Params P) {
     }
   }
   __syncthreads();
-  switch (t) {
-    case 0: elastic_phase_b<0>(sm, lane, slot0, P); break;
-    case 1: elastic_phase_b<1>(sm, lane, slot0, P); break;
-    case 2: elastic_phase_b<2>(sm, lane, slot0, P); break;
-    default: elastic_phase_b<3>(sm, lane, slot0, P); break;
-  }
+  elastic_phase_b(sm, lane, t, slot0, P);
 }
 
 }  // namespace

@@ -2,34 +2,42 @@
 // assemblies whose triplets come from element matrices scattered through one dof map.
 //
 // Symbolic phase (once per mesh + dof map + partition; cached in the dofmap):
-//   node -> element adjacency (CSR, ascending element order)            k_count_adj / k_fill_adj / k_sort_adj
-//   node -> sorted unique neighbour nodes (warp per node, bitonic sort) k_nbr<false> (count) / k_nbr<true> (fill)
-//   colptr from per-column counts (all ndn columns of a node share one row set), rowval = neighbour dofs sorted,
-//   per (node, neighbour) the list of (adjacent element, local row node) sources in ascending triplet order.
-// Numeric phase (every assembly): k_gather -- one warp per column node sums, for every stored entry, its source
-//   values in ascending element order (the reference's left-to-right duplicate sum), no atomics => bit-reproducible.
+//   node -> element adjacency (CSR, ascending element order)             k_count_adj / k_fill_adj / k_sort_adj
+//   k_nbr (one warp per node): candidate neighbour nodes of all adjacent elements -> 32-bit bitonic sort -> unique
+//     list U; every candidate (adjacent element a, local row node li) finds its neighbour slot s by binary search and
+//     sets bit a of mask[s]; popcounts of the masks give the per-slot source offsets and a deterministic, ascending
+//     (= reference triplet order) placement of the sources without a second sort.
+//   colptr from per-column counts (the ndn columns of a node share one row set)
+//   k_rows: rowval = dofs of (neighbour, component) in ascending order; when node-major order is not already
+//     ascending (free-first/fixed-last numbering, FieldModule.jl:360-377) a per-node sort produces a rank table.
+// Numeric phase (every assembly): k_gather -- one warp per column node stages its adjacency / source lists in shared
+//   memory and sums, for every stored entry, its source values in ascending element order (the reference's left-to-right
+//   duplicate sum).  No atomics => bit-reproducible (test/test_basics.jl:3039-3045).
 //
-// The pattern equals sparse()'s: one entry per (row dof, col dof) pair that shares an element, explicit zeros kept,
-// rows strictly increasing in a column, 1-based int64 colptr/rowval.
+// The pattern equals sparse()'s: one entry per (row dof, col dof) pair sharing an element, explicit zeros kept, rows
+// strictly increasing in a column, 1-based int64 colptr/rowval.
 #include "fegpu_internal.h"
 
 struct Pattern {
   int64_t nnz = 0, ncols = 0, nrows = 0;
-  int64_t *d_colptr = nullptr;  // [ncols+1] 1-based
-  int64_t *d_rowval = nullptr;  // [nnz] 1-based
-  int64_t *d_adjptr = nullptr;  // [nnodes+1]
+  int64_t *d_colptr = nullptr;    // [ncols+1] 1-based
+  int64_t *d_rowval = nullptr;    // [nnz] 1-based
+  int64_t *d_adjptr = nullptr;    // [nnodes+1]
   int32_t *d_adj_slot = nullptr;  // active-element slot
   uint8_t *d_adj_lc = nullptr;    // local node index of this node in that element
+  int32_t *d_nnbr = nullptr;      // [nnodes]
   int64_t *d_nbrptr = nullptr;    // [nnodes+1]
-  uint16_t *d_srcoff = nullptr;   // per node nnbr+1 entries at nbrptr[n] + n
+  uint16_t *d_srcoff = nullptr;   // per node nnbr+1 entries at adjptr[n]*nne + n
   uint16_t *d_src = nullptr;      // per node at adjptr[n]*nne: (adj index << 5) | local row node
-  uint16_t *d_rank = nullptr;     // per node nnbr*ndn entries at nbrptr[n]*ndn, nullptr when identity
-  int maxcand = 0;
+  uint16_t *d_rank = nullptr;     // per node nnbr*ndn entries at nbrptr[n]*ndn, nullptr when identity everywhere
+  int maxdeg = 0, maxcand = 0, maxnbr = 0;
+  cudaStream_t stream = 0;
 };
 
 namespace {
 
-constexpr int WPB = 4;  // warps per block in the per-node kernels
+constexpr int WPB = 4;  // warps per block in the per-node symbolic kernels
+constexpr int GWPB = 8; // warps per block in the gather
 
 struct SymParams {
   const int32_t *conn;
@@ -113,105 +121,127 @@ __device__ __forceinline__ int next_pow2(int v) {
   return p;
 }
 
-// One warp per node.  Shared per warp: keys[cap] (uint64; reused as the three work lists), cap = pow2 >= maxcand*max(1,ndn)
-// FILL == false: nnbr[n] only.  FILL == true: rowval, rank, srcoff, src.
-template <bool FILL>
-__global__ void __launch_bounds__(WPB * 32) k_nbr(SymParams S, const int64_t *adjptr, const int32_t *adj_slot, const uint8_t *adj_lc,
-                                                  int cap, int32_t *nnbr_out, const int64_t *nbrptr, const int64_t *colptr,
-                                                  int64_t *rowval, uint16_t *rank, uint16_t *srcoff, uint16_t *src, int *rank_nonident) {
-  extern __shared__ unsigned long long sk[];
+// One warp per node.  Shared per warp (uint32 words): el[maxdeg] | cand[capc] | work[capc] | uq[capc] | mask[capc*W]
+__global__ void __launch_bounds__(WPB * 32) k_nbr(SymParams S, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ adj_slot,
+                                                  int maxdeg, int capc, int W, int32_t *__restrict__ nnbr_out, int32_t *__restrict__ U,
+                                                  uint16_t *__restrict__ srcoff, uint16_t *__restrict__ src, uint8_t *__restrict__ sorted_flag,
+                                                  int *any_unsorted) {
+  extern __shared__ uint32_t su[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  unsigned long long *keys = sk + (size_t)w * cap * 2;  // [cap] work keys
-  unsigned long long *uniq = keys + cap;                // [cap] unique neighbour node ids (as u64) / second list
+  const int per_warp = maxdeg + 3 * capc + capc * W;
+  uint32_t *el = su + (size_t)w * per_warp;
+  uint32_t *cand = el + maxdeg;
+  uint32_t *work = cand + capc;
+  uint32_t *uq = work + capc;
+  uint32_t *mask = uq + capc;
   const int nne = S.nne, ndn = S.ndn;
   for (int64_t n = (int64_t)blockIdx.x * WPB + w; n < S.nnodes; n += (int64_t)gridDim.x * WPB) {
     const int64_t ab = adjptr[n];
     const int deg = (int)(adjptr[n + 1] - ab);
     if (deg == 0) {
-      if (!FILL && lane == 0) nnbr_out[n] = 0;
+      if (lane == 0) {
+        nnbr_out[n] = 0;
+        sorted_flag[n] = 1;
+      }
       continue;
     }
     const int ncand = deg * nne;
     const int p2 = next_pow2(ncand);
-    // candidates: key = (node << 16) | k, k = a*nne + li ; dropped (not an owned row) -> all ones
-    for (int k = lane; k < p2; k += 32) {
-      unsigned long long key = ~0ull;
-      if (k < ncand) {
-        int a = k / nne, li = k - a * nne;
-        int64_t slot = adj_slot[ab + a];
-        int64_t e = S.elem_list ? S.elem_list[slot] : slot;
-        int m = S.conn[e * nne + li];
-        if (!S.rowowned || S.rowowned[m]) key = ((unsigned long long)(unsigned)m << 16) | (unsigned)k;
-      }
-      keys[k] = key;
+    for (int a = lane; a < deg; a += 32) {
+      int64_t slot = adj_slot[ab + a];
+      el[a] = (uint32_t)(S.elem_list ? S.elem_list[slot] : slot);
     }
     __syncwarp();
-    warp_bitonic(keys, p2, lane);
-    // heads of runs of equal node id -> unique list; every candidate learns its neighbour slot
-    // pass 1: count heads (ballot prefix)
+    // candidates in triplet order k = a*nne + li; rows not owned by this rank are dropped (all ones)
+    for (int k = lane; k < p2; k += 32) {
+      uint32_t m = 0xffffffffu;
+      if (k < ncand) {
+        int a = k / nne, li = k - a * nne;
+        uint32_t mm = (uint32_t)S.conn[(int64_t)el[a] * nne + li];
+        if (!S.rowowned || S.rowowned[mm]) m = mm;
+      }
+      cand[k] = m;
+      work[k] = m;
+    }
+    __syncwarp();
+    warp_bitonic(work, p2, lane);
     int nu = 0;
     for (int base = 0; base < p2; base += 32) {
       int k = base + lane;
-      bool valid = (k < p2) && (keys[k] != ~0ull);
-      bool head = valid && (k == 0 || (keys[k - 1] >> 16) != (keys[k] >> 16));
+      uint32_t v = (k < p2) ? work[k] : 0xffffffffu;
+      bool head = (v != 0xffffffffu) && (k == 0 || work[k - 1] != v);
       unsigned bal = __ballot_sync(0xffffffffu, head);
-      if (head) uniq[nu + __popc(bal & ((1u << lane) - 1))] = keys[k] >> 16;
+      if (head) uq[nu + __popc(bal & ((1u << lane) - 1))] = v;
       nu += __popc(bal);
     }
+    for (int i = lane; i < nu * W; i += 32) mask[i] = 0;
     __syncwarp();
-    if (!FILL) {
-      if (lane == 0) nnbr_out[n] = nu;
-      continue;
+    // neighbour slot of every candidate (binary search in uq); bit a of mask[s] marks "element a holds neighbour s"
+    for (int k = lane; k < ncand; k += 32) {
+      uint32_t m = cand[k];
+      uint32_t s = 0xffffffffu;
+      if (m != 0xffffffffu) {
+        int lo = 0, hi = nu - 1;
+        while (lo < hi) {
+          int mid = (lo + hi) >> 1;
+          if (uq[mid] < m) lo = mid + 1;
+          else hi = mid;
+        }
+        s = (uint32_t)lo;
+        int a = k / nne;
+        atomicOr(&mask[s * W + (a >> 5)], 1u << (a & 31));
+      }
+      work[k] = s;
     }
-    // ---- sources: sorted keys are already grouped by neighbour (ascending node id = ascending slot s) and, inside a
-    // group, ascending k = ascending (adjacent element, local row node) = the reference's triplet order.
-    const int64_t nb = nbrptr[n];
-    uint16_t *so = srcoff + nb + n;
+    __syncwarp();
+    // source offsets: exclusive scan of the popcounts over the slots; cand[] is reused to hold them
+    uint16_t *so = srcoff + ab * nne + n;
     uint16_t *sr = src + ab * nne;
-    int s_run = 0;  // number of heads seen before this chunk
-    int nvalid = 0;
-    for (int base = 0; base < p2; base += 32) {
-      int k = base + lane;
-      bool valid = (k < p2) && (keys[k] != ~0ull);
-      bool head = valid && (k == 0 || (keys[k - 1] >> 16) != (keys[k] >> 16));
-      unsigned bal = __ballot_sync(0xffffffffu, head);
-      if (valid) {
-        unsigned kk = (unsigned)(keys[k] & 0xffffu);
-        unsigned a = kk / nne, li = kk - a * nne;
-        sr[k] = (uint16_t)((a << 5) | li);
-        if (head) so[s_run + __popc(bal & ((1u << lane) - 1))] = (uint16_t)k;
+    int run = 0;
+    for (int base = 0; base < nu; base += 32) {
+      int s = base + lane;
+      int c = 0;
+      if (s < nu)
+        for (int ww = 0; ww < W; ww++) c += __popc(mask[s * W + ww]);
+      int incl = c;
+      for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
       }
-      s_run += __popc(bal);
-      nvalid += __popc(__ballot_sync(0xffffffffu, valid));
+      if (s < nu) {
+        cand[s] = (uint32_t)(run + incl - c);
+        so[s] = (uint16_t)(run + incl - c);
+      }
+      run += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (lane == 0) so[nu] = (uint16_t)nvalid;
+    if (lane == 0) so[nu] = (uint16_t)run;
     __syncwarp();
-    // ---- rows: dofs of (neighbour s, component p), sorted ascending -> rowval of every column of this node, and rank
+    for (int k = lane; k < ncand; k += 32) {
+      uint32_t s = work[k];
+      if (s != 0xffffffffu) {
+        int a = k / nne, li = k - a * nne;
+        int r = 0;
+        for (int ww = 0; ww < (a >> 5); ww++) r += __popc(mask[s * W + ww]);
+        r += __popc(mask[s * W + (a >> 5)] & ((1u << (a & 31)) - 1));
+        sr[cand[s] + r] = (uint16_t)((a << 5) | li);
+      }
+    }
+    // unique neighbour list to global; is the node-major dof order already ascending?
+    int32_t *Un = U + ab * nne;
+    for (int s = lane; s < nu; s += 32) Un[s] = (int32_t)uq[s];
+    bool ok = true;
     const int nr = nu * ndn;
-    const int q2 = next_pow2(nr);
-    for (int i = lane; i < q2; i += 32) {
-      unsigned long long key = ~0ull;
-      if (i < nr) {
-        int s = i / ndn, p = i - s * ndn;
-        int m = (int)uniq[s];
-        key = ((unsigned long long)(unsigned)S.dof[(int64_t)p * S.nnodes + m] << 16) | (unsigned)i;
-      }
-      keys[i] = key;
+    for (int i = lane; i + 1 < nr; i += 32) {
+      int s0 = i / ndn, p0 = i - s0 * ndn, s1 = (i + 1) / ndn, p1 = (i + 1) - s1 * ndn;
+      int d0 = S.dof[(int64_t)p0 * S.nnodes + uq[s0]], d1 = S.dof[(int64_t)p1 * S.nnodes + uq[s1]];
+      if (d0 >= d1) ok = false;
     }
-    __syncwarp();
-    warp_bitonic(keys, q2, lane);
-    bool nonident = false;
-    for (int pos = lane; pos < nr; pos += 32) {
-      unsigned i = (unsigned)(keys[pos] & 0xffffu);
-      int64_t rdof = (int64_t)(keys[pos] >> 16) + 1;
-      rank[nb * ndn + i] = (uint16_t)pos;
-      if ((int)i != pos) nonident = true;
-      for (int q = 0; q < ndn; q++) {
-        int64_t J = S.dof[(int64_t)q * S.nnodes + n];
-        rowval[colptr[J] - 1 + pos] = rdof;
-      }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+      nnbr_out[n] = nu;
+      sorted_flag[n] = ok ? 1 : 0;
+      if (!ok) *any_unsorted = 1;
     }
-    if (__any_sync(0xffffffffu, nonident) && lane == 0) *rank_nonident = 1;
     __syncwarp();
   }
 }
@@ -224,6 +254,53 @@ __global__ void k_col_counts(SymParams S, const int32_t *nnbr, int64_t *colcount
   if (nnbr[n] > 0) colcount[S.dof[(int64_t)q * S.nnodes + n]] = (int64_t)nnbr[n] * S.ndn;
 }
 
+// rowval (+ rank).  One warp per node; shared per warp: cap2 uint64 keys, used only by nodes whose dof order needs a sort.
+__global__ void __launch_bounds__(WPB * 32) k_rows(SymParams S, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ nnbr,
+                                                   const int64_t *__restrict__ nbrptr, const int32_t *__restrict__ U,
+                                                   const uint8_t *__restrict__ sorted_flag, const int64_t *__restrict__ colptr, int cap2,
+                                                   int64_t *__restrict__ rowval, uint16_t *__restrict__ rank) {
+  extern __shared__ unsigned long long sk[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned long long *keys = sk + (size_t)w * cap2;
+  const int ndn = S.ndn;
+  for (int64_t n = (int64_t)blockIdx.x * WPB + w; n < S.nnodes; n += (int64_t)gridDim.x * WPB) {
+    const int nu = nnbr[n];
+    if (nu == 0) continue;
+    const int32_t *Un = U + adjptr[n] * S.nne;
+    const int64_t nb = nbrptr[n];
+    const int nr = nu * ndn;
+    int64_t cbase[6];
+    for (int q = 0; q < ndn; q++) cbase[q] = colptr[S.dof[(int64_t)q * S.nnodes + n]] - 1;
+    if (sorted_flag[n]) {
+      for (int i = lane; i < nr; i += 32) {
+        int s = i / ndn, p = i - s * ndn;
+        int64_t rdof = (int64_t)S.dof[(int64_t)p * S.nnodes + Un[s]] + 1;
+        for (int q = 0; q < ndn; q++) rowval[cbase[q] + i] = rdof;
+        if (rank) rank[nb * ndn + i] = (uint16_t)i;
+      }
+    } else {
+      const int q2 = next_pow2(nr);
+      for (int i = lane; i < q2; i += 32) {
+        unsigned long long key = ~0ull;
+        if (i < nr) {
+          int s = i / ndn, p = i - s * ndn;
+          key = ((unsigned long long)(unsigned)S.dof[(int64_t)p * S.nnodes + Un[s]] << 16) | (unsigned)i;
+        }
+        keys[i] = key;
+      }
+      __syncwarp();
+      warp_bitonic(keys, q2, lane);
+      for (int pos = lane; pos < nr; pos += 32) {
+        unsigned i = (unsigned)(keys[pos] & 0xffffu);
+        int64_t rdof = (int64_t)(keys[pos] >> 16) + 1;
+        rank[nb * ndn + i] = (uint16_t)pos;
+        for (int q = 0; q < ndn; q++) rowval[cbase[q] + pos] = rdof;
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- numeric gather
 struct GatherParams {
   int64_t nnodes;
@@ -231,6 +308,7 @@ struct GatherParams {
   const int64_t *adjptr;
   const int32_t *adj_slot;
   const uint8_t *adj_lc;
+  const int32_t *nnbr;
   const int64_t *nbrptr;
   const uint16_t *srcoff;
   const uint16_t *src;
@@ -239,38 +317,50 @@ struct GatherParams {
   const int64_t *colptr;
   const double *V;
   double *nzval;
+  int maxdeg, maxcand, maxnbr;
 };
 
+// shared per warp: base[maxdeg] (int64 element-matrix column offsets) | off[maxnbr+1] | code[maxcand] (uint16)
 template <int NDN>
-__global__ void __launch_bounds__(256) k_gather(const GatherParams G) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+__global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
+  extern __shared__ unsigned long long sg[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int u16_per_warp = ((G.maxnbr + 1 + G.maxcand + 3) / 4) * 4;
+  const size_t words_per_warp = (size_t)G.maxdeg + u16_per_warp / 4;
+  long long *base = reinterpret_cast<long long *>(sg + (size_t)w * words_per_warp);
+  uint16_t *off = reinterpret_cast<uint16_t *>(base + G.maxdeg);
+  uint16_t *code = off + (G.maxnbr + 1);
   const int ndn = (NDN > 0) ? NDN : G.ndn;
   const int EM = G.nne * ndn;
   const int64_t EM2 = (int64_t)EM * EM;
-  for (int64_t n = warp; n < G.nnodes; n += nwarps) {
-    const int64_t nb = G.nbrptr[n];
-    const int nn = (int)(G.nbrptr[n + 1] - nb);
+  for (int64_t n = (int64_t)blockIdx.x * GWPB + w; n < G.nnodes; n += (int64_t)gridDim.x * GWPB) {
+    const int nn = G.nnbr[n];
     if (nn == 0) continue;
     const int64_t ab = G.adjptr[n];
-    const uint16_t *so = G.srcoff + nb + n;
+    const int deg = (int)(G.adjptr[n + 1] - ab);
+    const uint16_t *so = G.srcoff + ab * G.nne + n;
     const uint16_t *sr = G.src + ab * G.nne;
+    __syncwarp();  // previous node's reads of the staging area are complete
+    for (int a = lane; a < deg; a += 32) base[a] = (long long)G.adj_slot[ab + a] * EM2 + (long long)(G.adj_lc[ab + a] * ndn) * EM;
+    for (int s = lane; s <= nn; s += 32) off[s] = so[s];
+    __syncwarp();
+    const int nsrc = off[nn];
+    for (int j = lane; j < nsrc; j += 32) code[j] = sr[j];
+    __syncwarp();
     const int per_col = nn * ndn;
     const int total = per_col * ndn;
+    const int64_t nb = G.rank ? G.nbrptr[n] : 0;
     for (int idx = lane; idx < total; idx += 32) {
       const int q = idx / per_col;
       const int rem = idx - q * per_col;
       const int s = rem / ndn;
       const int p = rem - s * ndn;
-      const int j0 = so[s], j1 = so[s + 1];
+      const int j0 = off[s], j1 = off[s + 1];
+      const double *Vq = G.V + (int64_t)q * EM + p;
       double v = 0.0;
       for (int j = j0; j < j1; j++) {
-        const unsigned code = sr[j];
-        const unsigned a = code >> 5, li = code & 31u;
-        const int64_t slot = G.adj_slot[ab + a];
-        const int lc = G.adj_lc[ab + a];
-        v += G.V[slot * EM2 + (int64_t)(lc * ndn + q) * EM + (li * ndn + p)];
+        const unsigned c = code[j];
+        v += Vq[base[c >> 5] + (int)(c & 31u) * ndn];
       }
       const int64_t J = G.dof[(int64_t)q * G.nnodes + n];
       const int pos = G.rank ? G.rank[nb * ndn + rem] : rem;
@@ -283,7 +373,7 @@ template <typename T>
 int32_t dalloc(fegpu_ctx *ctx, T **p, size_t n) {
   *p = nullptr;
   if (n == 0) n = 1;
-  CUDA_TRY(ctx, cudaMalloc((void **)p, sizeof(T) * n));
+  CUDA_TRY(ctx, cudaMallocAsync((void **)p, sizeof(T) * n, ctx->stream));
   return FEGPU_OK;
 }
 
@@ -291,8 +381,10 @@ int32_t dalloc(fegpu_ctx *ctx, T **p, size_t n) {
 
 void fe_pattern_free(Pattern *p) {
   if (!p) return;
-  cudaFree(p->d_colptr); cudaFree(p->d_rowval); cudaFree(p->d_adjptr); cudaFree(p->d_adj_slot); cudaFree(p->d_adj_lc);
-  cudaFree(p->d_nbrptr); cudaFree(p->d_srcoff); cudaFree(p->d_src); cudaFree(p->d_rank);
+  cudaStream_t st = p->stream;  // stream-ordered frees: blocks go back to the pool, no device synchronisation
+  void *ptrs[] = {p->d_colptr, p->d_rowval, p->d_adjptr, p->d_adj_slot, p->d_adj_lc, p->d_nnbr, p->d_nbrptr, p->d_srcoff, p->d_src, p->d_rank};
+  for (void *q : ptrs)
+    if (q) cudaFreeAsync(q, st);
   delete p;
 }
 int64_t fe_pattern_nnz(const Pattern *p) { return p->nnz; }
@@ -310,21 +402,34 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
   if (dm->pat) { fe_pattern_free(dm->pat); dm->pat = nullptr; }
   Pattern *P = new Pattern();
   dm->pat = P;  // owned by the dofmap from here on (freed with it, also on error paths)
+  P->stream = st;
   P->ncols = dm->col_nall;
   P->nrows = dm->row_nall;
   const int64_t nn = mesh->nnodes;
-  SymParams S{mesh->d_conn, mesh->d_elem_list, mesh->nactive, mesh->nne, nn, mesh->d_rowowned, dm->d_dof, dm->ndn};
-  const int64_t nadj = mesh->nactive * mesh->nne;
+  const int nne = mesh->nne, ndn = dm->ndn;
+  SymParams S{mesh->d_conn, mesh->d_elem_list, mesh->nactive, nne, nn, mesh->d_rowowned, dm->d_dof, ndn};
+  const int64_t nadj = mesh->nactive * nne;
 
-  int32_t *d_deg = nullptr, *d_cursor = nullptr, *d_nnbr = nullptr;
-  int *d_flags = nullptr;  // [0] degenerate, [1] rank non-identity
-  FE_TRY(dalloc(ctx, &d_deg, nn));
-  FE_TRY(dalloc(ctx, &d_cursor, nn));
-  FE_TRY(dalloc(ctx, &d_nnbr, nn));
-  FE_TRY(dalloc(ctx, &d_flags, 2));
-  auto cleanup = [&]() { cudaFree(d_deg); cudaFree(d_cursor); cudaFree(d_nnbr); cudaFree(d_flags); };
+  int32_t *d_deg = nullptr, *d_cursor = nullptr, *d_U = nullptr;
+  uint8_t *d_sorted = nullptr;
+  int *d_flags = nullptr;  // [0] degenerate, [1] some node needs a dof sort
+  auto cleanup = [&]() {
+    void *ptrs[] = {d_deg, d_cursor, d_U, d_sorted, d_flags};
+    for (void *q : ptrs)
+      if (q) cudaFreeAsync(q, st);
+  };
+  auto bail = [&]() {  // the mesh cannot use the structured path: free everything, the caller takes the sort path
+    mesh->degenerate = true;
+    cleanup();
+    fe_pattern_free(P);
+    dm->pat = nullptr;
+    return FEGPU_OK;
+  };
 #define PT(expr) do { int32_t _s = (expr); if (_s != FEGPU_OK) { cleanup(); return _s; } } while (0)
 #define PC(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fegpu_fail(ctx, FEGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+  PT(dalloc(ctx, &d_deg, nn));
+  PT(dalloc(ctx, &d_cursor, nn));
+  PT(dalloc(ctx, &d_flags, 2));
   PC(cudaMemsetAsync(d_deg, 0, sizeof(int32_t) * nn, st));
   PC(cudaMemsetAsync(d_cursor, 0, sizeof(int32_t) * nn, st));
   PC(cudaMemsetAsync(d_flags, 0, sizeof(int) * 2, st));
@@ -339,25 +444,17 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
   int h_flags[2] = {0, 0};
   PC(cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
   PC(cudaStreamSynchronize(st));
-  if (h_flags[0]) {
-    mesh->degenerate = true;
-    cleanup();
-    fe_pattern_free(P);
-    dm->pat = nullptr;
-    return FEGPU_OK;  // caller re-checks fe_pattern_usable and takes the sort path
-  }
-  if (maxdeg < 0) maxdeg = 0;
-  P->maxcand = maxdeg * mesh->nne;
-  int cap = 32;
-  while (cap < P->maxcand * std::max(1, dm->ndn)) cap <<= 1;
-  // limits of the packed encodings: adjacency index < 2048 (11 bits), candidate index < 65536, rows per column < 65536
-  if (maxdeg >= 2048 || P->maxcand >= 65536 || (int64_t)P->maxcand * dm->ndn >= 65536 || (size_t)cap * 2 * 8 > 200 * 1024) {
-    mesh->degenerate = true;  // valence beyond the fast path's encodings: generic sort path handles it
-    cleanup();
-    fe_pattern_free(P);
-    dm->pat = nullptr;
-    return FEGPU_OK;
-  }
+  if (h_flags[0]) return bail();
+  if (maxdeg < 1) maxdeg = 1;
+  P->maxdeg = maxdeg;
+  P->maxcand = maxdeg * nne;
+  int capc = 32;
+  while (capc < P->maxcand) capc <<= 1;
+  const int W = (maxdeg + 31) / 32;
+  // limits of the packed encodings: adjacency index < 2048 (11 bits), candidate index and rows per column < 65536
+  const size_t smem1 = (size_t)WPB * (maxdeg + 3 * (size_t)capc + (size_t)capc * W) * sizeof(uint32_t);
+  if (maxdeg >= 2048 || P->maxcand >= 65536 || (int64_t)P->maxcand * ndn >= 65536 || smem1 > 200 * 1024) return bail();
+
   PT(dalloc(ctx, &P->d_adj_slot, nadj));
   PT(dalloc(ctx, &P->d_adj_lc, nadj));
   if (nadj > 0) {
@@ -365,51 +462,50 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
     k_sort_adj<<<grid_for(nn, 128), 128, 0, st>>>(nn, P->d_adjptr, P->d_adj_slot, P->d_adj_lc);
     ctx->launches += 2;
   }
-  // neighbour counts
-  int wpb = WPB;
-  size_t smem = (size_t)wpb * cap * 2 * sizeof(unsigned long long);
-  PC(cudaFuncSetAttribute(k_nbr<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  PC(cudaFuncSetAttribute(k_nbr<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  if (smem > 220 * 1024) {
-    cleanup();
-    return fegpu_fail(ctx, FEGPU_ERR_ARG, "internal: neighbour work list exceeds shared memory");
-  }
-  unsigned gridn = (unsigned)std::min<int64_t>((nn + WPB - 1) / WPB, (int64_t)ctx->sm_count * 32);
+  PT(dalloc(ctx, &P->d_nnbr, nn));
+  PT(dalloc(ctx, &d_U, (size_t)nadj * nne));
+  PT(dalloc(ctx, &d_sorted, nn));
+  PT(dalloc(ctx, &P->d_srcoff, (size_t)nadj * nne + nn));
+  PT(dalloc(ctx, &P->d_src, (size_t)nadj * nne));
+  PC(cudaFuncSetAttribute(k_nbr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  unsigned gridn = (unsigned)std::min<int64_t>((nn + WPB - 1) / WPB, (int64_t)ctx->sm_count * 64);
   if (gridn == 0) gridn = 1;
-  k_nbr<false><<<gridn, WPB * 32, smem, st>>>(S, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, cap, d_nnbr, nullptr, nullptr, nullptr, nullptr,
-                                              nullptr, nullptr, nullptr);
+  k_nbr<<<gridn, WPB * 32, smem1, st>>>(S, P->d_adjptr, P->d_adj_slot, maxdeg, capc, W, P->d_nnbr, d_U, P->d_srcoff, P->d_src, d_sorted,
+                                        d_flags + 1);
   ctx->launches++;
   PT(dalloc(ctx, &P->d_nbrptr, nn + 1));
   int64_t total_nbr = 0;
-  PT(fe_exclusive_scan_i32_to_i64(ctx, d_nnbr, P->d_nbrptr, nn, 0, true, &total_nbr));
+  PT(fe_exclusive_scan_i32_to_i64(ctx, P->d_nnbr, P->d_nbrptr, nn, 0, true, &total_nbr));
+  int32_t maxnbr = 0;
+  PT(fe_max_i32(ctx, P->d_nnbr, nn, &maxnbr));
+  P->maxnbr = std::max(maxnbr, 1);
   // column pointers
   PT(dalloc(ctx, &P->d_colptr, P->ncols + 1));
   PC(cudaMemsetAsync(P->d_colptr, 0, sizeof(int64_t) * (P->ncols + 1), st));
-  if (nn * dm->ndn > 0) {
-    k_col_counts<<<grid_for(nn * dm->ndn, 256), 256, 0, st>>>(S, d_nnbr, P->d_colptr);
+  if (nn * ndn > 0) {
+    k_col_counts<<<grid_for(nn * ndn, 256), 256, 0, st>>>(S, P->d_nnbr, P->d_colptr);
     ctx->launches++;
   }
   int64_t tot = 0;
   PT(fe_exclusive_scan_i64(ctx, P->d_colptr, P->d_colptr, P->ncols, 1, true, &tot));
   P->nnz = tot - 1;
-  if (P->nnz != total_nbr * dm->ndn * dm->ndn) {
+  if (P->nnz != total_nbr * ndn * ndn) {
     cleanup();
     return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: pattern size mismatch");
   }
-  PT(dalloc(ctx, &P->d_rowval, (size_t)P->nnz));
-  PT(dalloc(ctx, &P->d_rank, (size_t)(total_nbr * dm->ndn)));
-  PT(dalloc(ctx, &P->d_srcoff, (size_t)(total_nbr + nn)));
-  PT(dalloc(ctx, &P->d_src, (size_t)nadj * mesh->nne));
-  k_nbr<true><<<gridn, WPB * 32, smem, st>>>(S, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, cap, nullptr, P->d_nbrptr, P->d_colptr, P->d_rowval,
-                                             P->d_rank, P->d_srcoff, P->d_src, d_flags + 1);
-  ctx->launches++;
   PC(cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
   PC(cudaStreamSynchronize(st));
+  const bool need_rank = h_flags[1] != 0;
+  PT(dalloc(ctx, &P->d_rowval, (size_t)P->nnz));
+  if (need_rank) PT(dalloc(ctx, &P->d_rank, (size_t)(total_nbr * ndn)));
+  int cap2 = 32;
+  while (cap2 < P->maxnbr * ndn) cap2 <<= 1;
+  const size_t smem2 = need_rank ? (size_t)WPB * cap2 * sizeof(unsigned long long) : 0;
+  if (smem2 > 200 * 1024) return bail();
+  if (smem2 > 48 * 1024) PC(cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  k_rows<<<gridn, WPB * 32, smem2, st>>>(S, P->d_adjptr, P->d_nnbr, P->d_nbrptr, d_U, d_sorted, P->d_colptr, cap2, P->d_rowval, P->d_rank);
+  ctx->launches++;
   PC(cudaGetLastError());
-  if (!h_flags[1]) {  // node-major row order already sorted: the gather can skip the rank table
-    cudaFree(P->d_rank);
-    P->d_rank = nullptr;
-  }
   cleanup();
 #undef PT
 #undef PC
@@ -423,17 +519,25 @@ int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, double *d_nzval) {
   fegpu_mesh *mesh = dm->mesh;
   if (!P) return fegpu_fail(ctx, FEGPU_ERR_STATE, "no pattern");
   if (P->nnz == 0) return FEGPU_OK;
-  GatherParams G{mesh->nnodes, mesh->nne, dm->ndn, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, P->d_nbrptr, P->d_srcoff,
-                 P->d_src, P->d_rank, dm->d_dof, P->d_colptr, d_V, d_nzval};
-  const int64_t warps_wanted = mesh->nnodes;
-  unsigned grid = (unsigned)std::min<int64_t>((warps_wanted + 7) / 8, (int64_t)ctx->sm_count * 64);
+  GatherParams G{mesh->nnodes, mesh->nne, dm->ndn, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, P->d_nnbr, P->d_nbrptr, P->d_srcoff,
+                 P->d_src, P->d_rank, dm->d_dof, P->d_colptr, d_V, d_nzval, P->maxdeg, P->maxcand, P->maxnbr};
+  const int u16_per_warp = ((P->maxnbr + 1 + P->maxcand + 3) / 4) * 4;
+  const size_t smem = (size_t)GWPB * ((size_t)P->maxdeg + u16_per_warp / 4) * sizeof(unsigned long long);
+  if (smem > 200 * 1024) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: gather staging exceeds shared memory");
+  unsigned grid = (unsigned)std::min<int64_t>((mesh->nnodes + GWPB - 1) / GWPB, (int64_t)ctx->sm_count * 64);
   if (grid == 0) grid = 1;
+#define LAUNCH_GATHER(N)                                                                                             \
+  do {                                                                                                               \
+    if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_gather<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_gather<N><<<grid, GWPB * 32, smem, ctx->stream>>>(G);                                                          \
+  } while (0)
   switch (dm->ndn) {
-    case 1: k_gather<1><<<grid, 256, 0, ctx->stream>>>(G); break;
-    case 2: k_gather<2><<<grid, 256, 0, ctx->stream>>>(G); break;
-    case 3: k_gather<3><<<grid, 256, 0, ctx->stream>>>(G); break;
-    default: k_gather<0><<<grid, 256, 0, ctx->stream>>>(G); break;
+    case 1: LAUNCH_GATHER(1); break;
+    case 2: LAUNCH_GATHER(2); break;
+    case 3: LAUNCH_GATHER(3); break;
+    default: LAUNCH_GATHER(0); break;
   }
+#undef LAUNCH_GATHER
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return FEGPU_OK;
