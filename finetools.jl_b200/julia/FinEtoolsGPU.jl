@@ -1,0 +1,188 @@
+# FinEtoolsGPU.jl -- drop-in GPU assembler for FinEtools.jl (v8.2.x) backed by libfinegpu.so (include/fegpu.h).
+#
+# NOT EXECUTED in the build environment (no Julia on the image).  It is the reference-side binding a maintainer adds:
+# every `ccall` below has a line-for-line twin in finetools.jl_b200/_lib.py + assembly.py + femm.py, which IS what the
+# test-suite and bench.py run.  parity.jl (next to this file) compares makematrix! outputs of the two assemblers.
+#
+#   using FinEtools, FinEtoolsGPU
+#   K = bilform_diffusion(femm, SysmatAssemblerSparseGPU(0.0), geom, u, DataCache(kappa))   # unchanged call shape
+#
+module FinEtoolsGPU
+
+using FinEtools
+using SparseArrays
+import FinEtools.AssemblyModule: AbstractSysmatAssembler, startassembly!, assemble!, makematrix!, eltype, expectedntriples
+import FinEtools.FEMMBaseModule: bilform_diffusion, bilform_lin_elastic, bilform_dot, FEMMBase, finite_elements
+using FinEtools.IntegDomainModule: integrationdata, otherdimensionunity
+using FinEtools.DeforModelRedModule: DeforModelRed3D
+
+export SysmatAssemblerSparseGPU
+
+const LIB = get(ENV, "FEGPU_LIB", joinpath(@__DIR__, "..", "libfinegpu.so"))
+
+_etype(::FESetT3) = 1; _etype(::FESetQ4) = 2; _etype(::FESetT4) = 3; _etype(::FESetT10) = 4
+_etype(::FESetH8) = 5; _etype(::FESetH20) = 6; _etype(::FESetH27) = 7
+_etype(fes) = error("Element type $(typeof(fes)) is not GPU-eligible")
+
+function _check(status::Int32, ctx::Ptr{Cvoid} = C_NULL)
+    status == 0 && return nothing
+    msg = unsafe_string(ccall((:fegpu_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx))
+    error(msg)   # same strings as AssemblyModule.jl:265-273 ("Row degree of freedom > size", ...)
+end
+
+"""
+    SysmatAssemblerSparseGPU{T} <: AbstractSysmatAssembler
+
+Same protocol as `SysmatAssemblerSparse` (AssemblyModule.jl:88-329); the element loop of the three bilinear forms and the
+COO -> CSC conversion run on the GPU.
+"""
+mutable struct SysmatAssemblerSparseGPU{T} <: AbstractSysmatAssembler
+    ctx::Ptr{Cvoid}
+    handle::Ptr{Cvoid}
+    meshes::IdDict{Any,Any}          # fes => (mesh handle, Dict(dofnums copy => dofmap handle))
+    _row_nalldofs::Int
+    _col_nalldofs::Int
+    _nomatrixresult::Bool
+    _force_init::Bool
+    _generic::Bool
+end
+
+function SysmatAssemblerSparseGPU(z::Float64 = 0.0, nomatrixresult = false; device = 0)
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    _check(ccall((:fegpu_create, LIB), Int32, (Ref{Ptr{Cvoid}}, Int32), ctx, device))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    _check(ccall((:fegpu_asm_create, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), ctx[], h), ctx[])
+    a = SysmatAssemblerSparseGPU{Float64}(ctx[], h[], IdDict(), 0, 0, nomatrixresult, false, false)
+    finalizer(a) do x
+        for (_, (m, dms)) in x.meshes
+            foreach(d -> ccall((:fegpu_dofmap_destroy, LIB), Int32, (Ptr{Cvoid},), d), values(dms))
+            ccall((:fegpu_mesh_destroy, LIB), Int32, (Ptr{Cvoid},), m)
+        end
+        ccall((:fegpu_asm_destroy, LIB), Int32, (Ptr{Cvoid},), x.handle)
+        ccall((:fegpu_destroy, LIB), Int32, (Ptr{Cvoid},), x.ctx)
+    end
+    return a
+end
+
+eltype(::SysmatAssemblerSparseGPU{T}) where {T} = T
+
+# ---- generic protocol (any caller of startassembly!/assemble!/makematrix! keeps working) ------------------------------
+function startassembly!(self::SysmatAssemblerSparseGPU, elem_mat_nrows::IT, elem_mat_ncols::IT, n_elem_mats::IT,
+    row_nalldofs::IT, col_nalldofs::IT; force_init = false) where {IT<:Integer}
+    _check(ccall((:fegpu_startassembly, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64),
+            self.handle, elem_mat_nrows, elem_mat_ncols, n_elem_mats, row_nalldofs, col_nalldofs), self.ctx)
+    self._row_nalldofs, self._col_nalldofs, self._generic = row_nalldofs, col_nalldofs, true
+    return self
+end
+
+function assemble!(self::SysmatAssemblerSparseGPU, mat::MBT, dofnums_row::CIT, dofnums_col::CIT) where {MBT,CIT}
+    nrows, ncolumns = length(dofnums_row), length(dofnums_col)
+    size(mat) == (nrows, ncolumns) || error("Wrong size of matrix")
+    m = Matrix{Float64}(mat); dr = Vector{Int64}(vec(dofnums_row)); dc = Vector{Int64}(vec(dofnums_col))
+    GC.@preserve m dr dc _check(ccall((:fegpu_assemble, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64, Ptr{Int64}, Int64), self.handle, m, dr, nrows, dc, ncolumns), self.ctx)
+    return self
+end
+
+function makematrix!(self::SysmatAssemblerSparseGPU)
+    if self._nomatrixresult
+        return spzeros(self._row_nalldofs, self._col_nalldofs)
+    end
+    if self._generic
+        _check(ccall((:fegpu_makematrix, LIB), Int32, (Ptr{Cvoid},), self.handle), self.ctx)
+        self._generic = false
+    end
+    m, n, nnz = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0)
+    _check(ccall((:fegpu_makematrix_sizes, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), self.handle, m, n, nnz), self.ctx)
+    colptr = Vector{Int64}(undef, n[] + 1); rowval = Vector{Int64}(undef, nnz[]); nzval = Vector{Float64}(undef, nnz[])
+    GC.@preserve colptr rowval nzval _check(ccall((:fegpu_makematrix_copy, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}), self.handle, colptr, rowval, nzval), self.ctx)
+    return SparseMatrixCSC(m[], n[], colptr, rowval, nzval)   # 1-based Int64 arrays, used as they are
+end
+
+# ---- device twins of (fes, geom, u) -------------------------------------------------------------------------------------
+function _eligible(self::FEMMBase, geom, u, cf)
+    self.mcsys.isidentity || error("only the identity material coordinate system is GPU-eligible")
+    self.integdomain.axisymmetric && error("axisymmetric integration domains are not GPU-eligible")
+    (self.integdomain.otherdimension === otherdimensionunity) || error("only the unit other-dimension is GPU-eligible")
+    # DataCache: only the constant constructor (DataCacheModule.jl:77-89) may cross the boundary
+    eltype(geom.values) == Float64 || error("geom must be Float64")
+    eltype(u.dofnums) == Int64 || error("dofnums must be Int64")
+    return nothing
+end
+
+function _device(self::FEMMBase, a::SysmatAssemblerSparseGPU, geom, u)
+    fes = finite_elements(self)
+    xyz = geom.values                                      # nnodes x sdim, column-major already
+    entry = get(a.meshes, fes, nothing)
+    if entry === nothing
+        conn = Matrix{Int64}(undef, nodesperelem(fes), count(fes))   # [nelem][nne] row-major == nne x nelem column-major
+        for (i, c) in enumerate(fes.conn), k in eachindex(c)
+            conn[k, i] = c[k]
+        end
+        mh = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve conn xyz _check(ccall((:fegpu_mesh_upload, LIB), Int32,
+                (Ptr{Cvoid}, Int32, Int64, Ptr{Int64}, Int64, Int32, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+                a.ctx, _etype(fes), count(fes), conn, size(xyz, 1), size(xyz, 2), xyz, mh), a.ctx)
+        npts, Ns, gradNparams, w, pc = integrationdata(self.integdomain)
+        N = reduce(hcat, [vec(Ns[j]) for j in 1:npts])                       # nne x npts  == [npts][nne]
+        dN = reduce(hcat, [vec(gradNparams[j]) for j in 1:npts])            # (nne*mdim) x npts == [npts][mdim][nne]
+        ww = Vector{Float64}(vec(w))
+        GC.@preserve N dN ww _check(ccall((:fegpu_rule_set, LIB), Int32,
+                (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), mh[], npts, N, dN, ww), a.ctx)
+        entry = (mh[], Dict{Matrix{Int64},Ptr{Cvoid}}())
+        a.meshes[fes] = entry
+    else
+        GC.@preserve xyz _check(ccall((:fegpu_geom_update, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), entry[1], xyz), a.ctx)
+    end
+    mh, dms = entry
+    dh = get(dms, u.dofnums, C_NULL)
+    if dh == C_NULL
+        d = Ref{Ptr{Cvoid}}(C_NULL)
+        dn = u.dofnums
+        GC.@preserve dn _check(ccall((:fegpu_dofmap_upload, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int64}, Int64, Int64, Ref{Ptr{Cvoid}}),
+                a.ctx, mh, ndofs(u), dn, nalldofs(u), nalldofs(u), d), a.ctx)
+        dms[copy(dn)] = d[]
+        dh = d[]
+    end
+    a._row_nalldofs = a._col_nalldofs = nalldofs(u)
+    a._generic = false
+    return mh, dh
+end
+
+# ---- the three forms: more specific methods than the generic drivers (FEMMBaseModule.jl:1335, 1462, 1774) ---------------
+function bilform_diffusion(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, geom::NodalField{FT}, u::NodalField{T},
+    cf::DC) where {FT,T,DC<:DataCache}
+    _eligible(self, geom, u, cf)
+    mh, dh = _device(self, assembler, geom, u)
+    kappa = cf._cache
+    kind = isempty(size(kappa)) ? 0 : 1
+    k = kind == 0 ? Float64[kappa] : Matrix{Float64}(kappa)
+    GC.@preserve k _check(ccall((:fegpu_bilform_diffusion, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Cvoid}),
+            mh, dh, kind, k, assembler.handle), assembler.ctx)
+    return makematrix!(assembler)
+end
+
+function bilform_lin_elastic(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, geom::NodalField{FT}, u::NodalField{T},
+    mr::Type{DeforModelRed3D}, cf::DC) where {FT,T,DC<:DataCache}
+    _eligible(self, geom, u, cf)
+    mh, dh = _device(self, assembler, geom, u)
+    C = Matrix{Float64}(cf._cache)
+    size(C) == (6, 6) || error("Wrong dimensions")
+    GC.@preserve C _check(ccall((:fegpu_bilform_lin_elastic, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}),
+            mh, dh, C, assembler.handle), assembler.ctx)
+    return makematrix!(assembler)
+end
+
+function bilform_dot(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, geom::NodalField{FT}, u::NodalField{T}, cf::DC;
+    m = 3) where {FT,T,DC<:DataCache}
+    _eligible(self, geom, u, cf)
+    mh, dh = _device(self, assembler, geom, u)
+    c = Matrix{Float64}(cf._cache)          # densifies LinearAlgebra.I(ndofs) (a Diagonal{Bool}), see innerproduct :1388-1401
+    GC.@preserve c _check(ccall((:fegpu_bilform_dot, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Ptr{Cvoid}),
+            mh, dh, c, m, 1.0, assembler.handle), assembler.ctx)
+    return makematrix!(assembler)
+end
+
+end # module

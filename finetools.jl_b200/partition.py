@@ -14,11 +14,17 @@ def slab_owner(nnodes, nparts):
 
 
 def pointpartitioning(xyz, npartitions=2):
-    """Partition labels 1..2^k (k = ceil(log2(npartitions))) by recursive inertial bisection."""
+    """Partition labels 1..2^k (k = ceil(log2(npartitions))) by recursive inertial bisection: every current part is cut
+    through its centroid, normal to the eigenvector of the SMALLEST eigenvalue of its inertia matrix (the long direction);
+    points with d < 0 get label 2p-1, d > 0 label 2p, exact zeros alternate (MeshModificationModule.jl:856-876).  The
+    reference mirrors only the (1,2) entry of the inertia matrix (:846-850); restated as is."""
     xyz = np.asarray(xyz, dtype=np.float64)
-    n = xyz.shape[0]
-    nlevels = int(np.ceil(np.log2(max(int(npartitions), 1)))) if npartitions > 1 else 0
-    part = np.ones(n, dtype=np.int64)
+    if npartitions < 2:
+        raise ValueError("Number of partitions must be >= 2")
+    if xyz.shape[1] != 3:
+        raise ValueError("Not implemented for 1D / 2D")
+    nlevels = int(round(np.ceil(np.log(npartitions) / np.log(2))))
+    part = np.ones(xyz.shape[0], dtype=np.int64)
     for level in range(nlevels):
         newpart = part.copy()
         for p in range(1, 2 ** level + 1):
@@ -26,14 +32,19 @@ def pointpartitioning(xyz, npartitions=2):
             if idx.size == 0:
                 continue
             X = xyz[idx]
-            Xc = X - X.mean(axis=0)
-            # principal direction = eigenvector of the largest eigenvalue of the covariance
-            w, v = np.linalg.eigh(Xc.T @ Xc)
-            d = Xc @ v[:, -1]
-            med = np.median(d)
-            right = d > med
-            ties = np.nonzero(d == med)[0]       # zero-distance points alternate sides (:869-872)
-            right[ties[1::2]] = True
-            newpart[idx[right]] = p + 2 ** level
+            r = X - X.sum(axis=0) / idx.size
+            x, y, z = r[:, 0], r[:, 1], r[:, 2]
+            M = np.zeros((3, 3))
+            M[0, 0] = (y * y + z * z).sum(); M[1, 1] = (x * x + z * z).sum(); M[2, 2] = (y * y + x * x).sum()
+            M[0, 1] = -(x * y).sum(); M[0, 2] = -(x * z).sum(); M[1, 2] = -(y * z).sum()
+            M[1, 0] = M[0, 1]
+            vals, vecs = np.linalg.eig(M)
+            v = np.real(vecs[:, np.argsort(np.real(vals))[0]])
+            d = r @ v
+            c = np.where(d < 0.0, 1, 0)
+            zeros = np.nonzero(d == 0.0)[0]
+            c[zeros[0::2]] = 1      # toggle starts at +1 -> c = 1, then alternates
+            c[zeros[1::2]] = 0
+            newpart[idx] = 2 * p - c
         part = newpart
     return part

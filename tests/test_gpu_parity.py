@@ -338,3 +338,19 @@ def test_full_size_config2_properties(fe, gpu_ctx):
     sub = K[:, cols].tocoo()
     vals_t = np.asarray(K[cols[sub.col], sub.row]).reshape(-1)
     np.testing.assert_array_equal(vals_t, sub.data)
+
+
+def test_golden_fixtures_on_gpu(fe, gpu_ctx):
+    """The committed golden CSC fixtures (tests/golden/, generated by make_golden.py with the oracle) against the CUDA path."""
+    import glob
+    import os
+    from golden.make_golden import CASES, build_case
+    root = os.path.dirname(os.path.abspath(__file__))
+    files = sorted(glob.glob(os.path.join(root, "golden", "*.npz")))
+    assert len(files) == len(CASES)
+    for f in files:
+        g = np.load(f)
+        name = os.path.basename(f)[:-4]
+        fens, fes, u, rule, coef, form, et, kw = build_case(fe, CASES[name])
+        got, _ = gpu_csc(fe, form, fes, fens, u, rule, coef, **kw)
+        assert_parity((g["colptr"], g["rowval"], g["nzval"]), got)
