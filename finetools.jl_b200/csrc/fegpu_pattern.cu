@@ -3,16 +3,16 @@
 //
 // Symbolic phase (once per mesh + dof map + partition; cached in the dofmap):
 //   node -> element adjacency (CSR, ascending element order)             k_count_adj / k_fill_adj / k_sort_adj
-//   k_nbr (one warp per node): candidate neighbour nodes of all adjacent elements -> 32-bit bitonic sort -> unique
-//     list U; every candidate (adjacent element a, local row node li) finds its neighbour slot s by binary search and
-//     sets bit a of mask[s]; popcounts of the masks give the per-slot source offsets and a deterministic, ascending
-//     (= reference triplet order) placement of the sources without a second sort.
+//   k_nbr (one warp per node): candidate neighbour nodes of all adjacent elements -> 32-bit bitonic sort (in registers,
+//     shuffle network) -> unique list U; every candidate (adjacent element a, local row node li) finds its neighbour
+//     slot by binary search: cslot[a*nne + li].
 //   colptr from per-column counts (the ndn columns of a node share one row set)
 //   k_rows: rowval = dofs of (neighbour, component) in ascending order; when node-major order is not already
 //     ascending (free-first/fixed-last numbering, FieldModule.jl:360-377) a per-node sort produces a rank table.
-// Numeric phase (every assembly): k_gather -- one warp per column node stages its adjacency / source lists in shared
-//   memory and sums, for every stored entry, its source values in ascending element order (the reference's left-to-right
-//   duplicate sum).  No atomics => bit-reproducible (test/test_basics.jl:3039-3045).
+// Numeric phase (every assembly): k_gather -- a group of 8/16/32 lanes per column node walks the node's adjacent elements
+//   in ascending order; for each it reads the ndn contiguous element-matrix columns of that node (coalesced) and adds
+//   every value into the node's accumulator slot (shared memory) given by cslot.  Ascending element order = the
+//   reference's left-to-right duplicate sum; no atomics => bit-reproducible (test/test_basics.jl:3039-3045).
 //
 // The pattern equals sparse()'s: one entry per (row dof, col dof) pair sharing an element, explicit zeros kept, rows
 // strictly increasing in a column, 1-based int64 colptr/rowval.
@@ -27,8 +27,7 @@ struct Pattern {
   uint8_t *d_adj_lc = nullptr;    // local node index of this node in that element
   int32_t *d_nnbr = nullptr;      // [nnodes]
   int64_t *d_nbrptr = nullptr;    // [nnodes+1]
-  uint16_t *d_srcoff = nullptr;   // per node nnbr+1 entries at adjptr[n]*nne + n
-  uint16_t *d_src = nullptr;      // per node at adjptr[n]*nne: (adj index << 5) | local row node
+  uint16_t *d_cslot = nullptr;    // per node at adjptr[n]*nne + a*nne + li: neighbour slot of that candidate (0xffff = dropped)
   uint16_t *d_rank = nullptr;     // per node nnbr*ndn entries at nbrptr[n]*ndn, nullptr when identity everywhere
   int maxdeg = 0, maxcand = 0, maxnbr = 0;
   cudaStream_t stream = 0;
@@ -121,19 +120,56 @@ __device__ __forceinline__ int next_pow2(int v) {
   return p;
 }
 
-// One warp per node.  Shared per warp (uint32 words): el[maxdeg] | cand[capc] | work[capc] | uq[capc] | mask[capc*W]
+// Bitonic sort of 32*KPL uint32 keys held KPL per lane (element index i = r*32 + lane), ascending, shuffle network.
+template <int KPL>
+__device__ __forceinline__ void reg_bitonic(uint32_t (&v)[KPL], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * KPL; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int r = 0; r < KPL; r++) {
+        const int i = r * 32 + lane;
+        const bool up = ((i & k) == 0);
+        if (j >= 32) {
+          const int rp = r ^ (j >> 5);
+          if (rp > r) {  // both live in this lane
+            uint32_t lo = min(v[r], v[rp]), hi = max(v[r], v[rp]);
+            v[r] = up ? lo : hi;
+            v[rp] = up ? hi : lo;
+          }
+        } else {
+          const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], j);
+          const bool lower = ((lane & j) == 0);
+          v[r] = (lower == up) ? min(v[r], o) : max(v[r], o);
+        }
+      }
+    }
+  }
+}
+
+template <int KPL>
+__device__ __forceinline__ void sort_via_regs(uint32_t *work, int lane) {
+  uint32_t v[KPL];
+#pragma unroll
+  for (int r = 0; r < KPL; r++) v[r] = work[r * 32 + lane];
+  reg_bitonic<KPL>(v, lane);
+#pragma unroll
+  for (int r = 0; r < KPL; r++) work[r * 32 + lane] = v[r];
+  __syncwarp();
+}
+
+// One warp per node.  Shared per warp (uint32 words): el[maxdeg] | cand[capc] | work[capc] | uq[capc]
 __global__ void __launch_bounds__(WPB * 32) k_nbr(SymParams S, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ adj_slot,
-                                                  int maxdeg, int capc, int W, int32_t *__restrict__ nnbr_out, int32_t *__restrict__ U,
-                                                  uint16_t *__restrict__ srcoff, uint16_t *__restrict__ src, uint8_t *__restrict__ sorted_flag,
-                                                  int *any_unsorted) {
+                                                  int maxdeg, int capc, int32_t *__restrict__ nnbr_out, int32_t *__restrict__ U,
+                                                  uint16_t *__restrict__ cslot, uint8_t *__restrict__ sorted_flag, int *any_unsorted) {
   extern __shared__ uint32_t su[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int per_warp = maxdeg + 3 * capc + capc * W;
+  const int per_warp = maxdeg + 3 * capc;
   uint32_t *el = su + (size_t)w * per_warp;
   uint32_t *cand = el + maxdeg;
   uint32_t *work = cand + capc;
   uint32_t *uq = work + capc;
-  uint32_t *mask = uq + capc;
   const int nne = S.nne, ndn = S.ndn;
   for (int64_t n = (int64_t)blockIdx.x * WPB + w; n < S.nnodes; n += (int64_t)gridDim.x * WPB) {
     const int64_t ab = adjptr[n];
@@ -146,7 +182,8 @@ __global__ void __launch_bounds__(WPB * 32) k_nbr(SymParams S, const int64_t *__
       continue;
     }
     const int ncand = deg * nne;
-    const int p2 = next_pow2(ncand);
+    int p2 = 32;
+    while (p2 < ncand) p2 <<= 1;
     for (int a = lane; a < deg; a += 32) {
       int64_t slot = adj_slot[ab + a];
       el[a] = (uint32_t)(S.elem_list ? S.elem_list[slot] : slot);
@@ -164,22 +201,29 @@ __global__ void __launch_bounds__(WPB * 32) k_nbr(SymParams S, const int64_t *__
       work[k] = m;
     }
     __syncwarp();
-    warp_bitonic(work, p2, lane);
+    switch (p2) {
+      case 32: sort_via_regs<1>(work, lane); break;
+      case 64: sort_via_regs<2>(work, lane); break;
+      case 128: sort_via_regs<4>(work, lane); break;
+      case 256: sort_via_regs<8>(work, lane); break;
+      case 512: sort_via_regs<16>(work, lane); break;
+      default: warp_bitonic(work, p2, lane); break;
+    }
     int nu = 0;
     for (int base = 0; base < p2; base += 32) {
       int k = base + lane;
-      uint32_t v = (k < p2) ? work[k] : 0xffffffffu;
+      uint32_t v = work[k];
       bool head = (v != 0xffffffffu) && (k == 0 || work[k - 1] != v);
       unsigned bal = __ballot_sync(0xffffffffu, head);
       if (head) uq[nu + __popc(bal & ((1u << lane) - 1))] = v;
       nu += __popc(bal);
     }
-    for (int i = lane; i < nu * W; i += 32) mask[i] = 0;
     __syncwarp();
-    // neighbour slot of every candidate (binary search in uq); bit a of mask[s] marks "element a holds neighbour s"
+    // neighbour slot of every candidate: binary search in the unique list
+    uint16_t *cs = cslot + ab * nne;
     for (int k = lane; k < ncand; k += 32) {
       uint32_t m = cand[k];
-      uint32_t s = 0xffffffffu;
+      uint16_t s = 0xffffu;
       if (m != 0xffffffffu) {
         int lo = 0, hi = nu - 1;
         while (lo < hi) {
@@ -187,44 +231,9 @@ __global__ void __launch_bounds__(WPB * 32) k_nbr(SymParams S, const int64_t *__
           if (uq[mid] < m) lo = mid + 1;
           else hi = mid;
         }
-        s = (uint32_t)lo;
-        int a = k / nne;
-        atomicOr(&mask[s * W + (a >> 5)], 1u << (a & 31));
+        s = (uint16_t)lo;
       }
-      work[k] = s;
-    }
-    __syncwarp();
-    // source offsets: exclusive scan of the popcounts over the slots; cand[] is reused to hold them
-    uint16_t *so = srcoff + ab * nne + n;
-    uint16_t *sr = src + ab * nne;
-    int run = 0;
-    for (int base = 0; base < nu; base += 32) {
-      int s = base + lane;
-      int c = 0;
-      if (s < nu)
-        for (int ww = 0; ww < W; ww++) c += __popc(mask[s * W + ww]);
-      int incl = c;
-      for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-      }
-      if (s < nu) {
-        cand[s] = (uint32_t)(run + incl - c);
-        so[s] = (uint16_t)(run + incl - c);
-      }
-      run += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) so[nu] = (uint16_t)run;
-    __syncwarp();
-    for (int k = lane; k < ncand; k += 32) {
-      uint32_t s = work[k];
-      if (s != 0xffffffffu) {
-        int a = k / nne, li = k - a * nne;
-        int r = 0;
-        for (int ww = 0; ww < (a >> 5); ww++) r += __popc(mask[s * W + ww]);
-        r += __popc(mask[s * W + (a >> 5)] & ((1u << (a & 31)) - 1));
-        sr[cand[s] + r] = (uint16_t)((a << 5) | li);
-      }
+      cs[k] = s;
     }
     // unique neighbour list to global; is the node-major dof order already ascending?
     int32_t *Un = U + ab * nne;
@@ -310,62 +319,72 @@ struct GatherParams {
   const uint8_t *adj_lc;
   const int32_t *nnbr;
   const int64_t *nbrptr;
-  const uint16_t *srcoff;
-  const uint16_t *src;
+  const uint16_t *cslot;
   const uint16_t *rank;
   const int32_t *dof;
   const int64_t *colptr;
   const double *V;
   double *nzval;
-  int maxdeg, maxcand, maxnbr;
+  int maxnbr;
 };
 
-// shared per warp: base[maxdeg] (int64 element-matrix column offsets) | off[maxnbr+1] | code[maxcand] (uint16)
-template <int NDN>
+// LPN lanes per node (32/LPN nodes per warp), NDN dofs per node (0 = runtime).  Shared per node group: maxnbr*ndn*ndn doubles.
+template <int LPN, int NDN>
 __global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
-  extern __shared__ unsigned long long sg[];
+  extern __shared__ double sacc[];
+  constexpr int NPW = 32 / LPN;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int u16_per_warp = ((G.maxnbr + 1 + G.maxcand + 3) / 4) * 4;
-  const size_t words_per_warp = (size_t)G.maxdeg + u16_per_warp / 4;
-  long long *base = reinterpret_cast<long long *>(sg + (size_t)w * words_per_warp);
-  uint16_t *off = reinterpret_cast<uint16_t *>(base + G.maxdeg);
-  uint16_t *code = off + (G.maxnbr + 1);
+  const int g = lane / LPN, gl = lane % LPN;
   const int ndn = (NDN > 0) ? NDN : G.ndn;
-  const int EM = G.nne * ndn;
+  const int nne = G.nne;
+  const int EM = nne * ndn;
   const int64_t EM2 = (int64_t)EM * EM;
-  for (int64_t n = (int64_t)blockIdx.x * GWPB + w; n < G.nnodes; n += (int64_t)gridDim.x * GWPB) {
-    const int nn = G.nnbr[n];
-    if (nn == 0) continue;
-    const int64_t ab = G.adjptr[n];
-    const int deg = (int)(G.adjptr[n + 1] - ab);
-    const uint16_t *so = G.srcoff + ab * G.nne + n;
-    const uint16_t *sr = G.src + ab * G.nne;
-    __syncwarp();  // previous node's reads of the staging area are complete
-    for (int a = lane; a < deg; a += 32) base[a] = (long long)G.adj_slot[ab + a] * EM2 + (long long)(G.adj_lc[ab + a] * ndn) * EM;
-    for (int s = lane; s <= nn; s += 32) off[s] = so[s];
-    __syncwarp();
-    const int nsrc = off[nn];
-    for (int j = lane; j < nsrc; j += 32) code[j] = sr[j];
-    __syncwarp();
+  const int acc_stride = G.maxnbr * ndn * ndn;
+  double *acc = sacc + (size_t)(w * NPW + g) * acc_stride;
+  const int64_t groups_total = (int64_t)gridDim.x * GWPB * NPW;
+  const int64_t niter = (G.nnodes + groups_total - 1) / groups_total;
+  for (int64_t it = 0; it < niter; it++) {
+    const int64_t n = (it * gridDim.x + blockIdx.x) * (GWPB * NPW) + w * NPW + g;
+    const bool live = n < G.nnodes;
+    const int nn = live ? G.nnbr[n] : 0;
+    const int64_t ab = live ? G.adjptr[n] : 0;
+    const int deg = (live && nn > 0) ? (int)(G.adjptr[n + 1] - ab) : 0;
     const int per_col = nn * ndn;
     const int total = per_col * ndn;
-    const int64_t nb = G.rank ? G.nbrptr[n] : 0;
-    for (int idx = lane; idx < total; idx += 32) {
-      const int q = idx / per_col;
-      const int rem = idx - q * per_col;
-      const int s = rem / ndn;
-      const int p = rem - s * ndn;
-      const int j0 = off[s], j1 = off[s + 1];
-      const double *Vq = G.V + (int64_t)q * EM + p;
-      double v = 0.0;
-      for (int j = j0; j < j1; j++) {
-        const unsigned c = code[j];
-        v += Vq[base[c >> 5] + (int)(c & 31u) * ndn];
+    for (int i = gl; i < total; i += LPN) acc[i] = 0.0;
+    int maxdeg = deg;
+#pragma unroll
+    for (int d = LPN; d < 32; d <<= 1) maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, d));
+    __syncwarp();
+    const uint16_t *cs = G.cslot + ab * nne;
+    for (int a = 0; a < maxdeg; a++) {
+      if (a < deg) {
+        const int64_t base = (int64_t)G.adj_slot[ab + a] * EM2 + (int64_t)(G.adj_lc[ab + a] * ndn) * EM;
+        const double *Vb = G.V + base;
+        for (int r = gl; r < EM; r += LPN) {
+          const int li = r / ndn, p = r - li * ndn;
+          const unsigned s = cs[a * nne + li];
+          if (s != 0xffffu) {
+            double *dst = acc + s * ndn + p;
+#pragma unroll
+            for (int q = 0; q < (NDN > 0 ? NDN : 6); q++)
+              if (q < ndn) dst[q * per_col] += Vb[q * EM + r];
+          }
+        }
       }
-      const int64_t J = G.dof[(int64_t)q * G.nnodes + n];
-      const int pos = G.rank ? G.rank[nb * ndn + rem] : rem;
-      G.nzval[G.colptr[J] - 1 + pos] = v;
+      __syncwarp();
     }
+    if (live && nn > 0) {
+      const int64_t nb = G.rank ? G.nbrptr[n] : 0;
+      for (int q = 0; q < ndn; q++) {
+        const int64_t cbase = G.colptr[G.dof[(int64_t)q * G.nnodes + n]] - 1;
+        for (int rem = gl; rem < per_col; rem += LPN) {
+          const int pos = G.rank ? G.rank[nb * ndn + rem] : rem;
+          G.nzval[cbase + pos] = acc[q * per_col + rem];
+        }
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -382,7 +401,7 @@ int32_t dalloc(fegpu_ctx *ctx, T **p, size_t n) {
 void fe_pattern_free(Pattern *p) {
   if (!p) return;
   cudaStream_t st = p->stream;  // stream-ordered frees: blocks go back to the pool, no device synchronisation
-  void *ptrs[] = {p->d_colptr, p->d_rowval, p->d_adjptr, p->d_adj_slot, p->d_adj_lc, p->d_nnbr, p->d_nbrptr, p->d_srcoff, p->d_src, p->d_rank};
+  void *ptrs[] = {p->d_colptr, p->d_rowval, p->d_adjptr, p->d_adj_slot, p->d_adj_lc, p->d_nnbr, p->d_nbrptr, p->d_cslot, p->d_rank};
   for (void *q : ptrs)
     if (q) cudaFreeAsync(q, st);
   delete p;
@@ -450,10 +469,9 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
   P->maxcand = maxdeg * nne;
   int capc = 32;
   while (capc < P->maxcand) capc <<= 1;
-  const int W = (maxdeg + 31) / 32;
-  // limits of the packed encodings: adjacency index < 2048 (11 bits), candidate index and rows per column < 65536
-  const size_t smem1 = (size_t)WPB * (maxdeg + 3 * (size_t)capc + (size_t)capc * W) * sizeof(uint32_t);
-  if (maxdeg >= 2048 || P->maxcand >= 65536 || (int64_t)P->maxcand * ndn >= 65536 || smem1 > 200 * 1024) return bail();
+  // limits of the packed encodings: neighbour slots and rows per column < 65535
+  const size_t smem1 = (size_t)WPB * (maxdeg + 3 * (size_t)capc) * sizeof(uint32_t);
+  if (P->maxcand >= 65535 || (int64_t)P->maxcand * ndn >= 65535 || smem1 > 200 * 1024) return bail();
 
   PT(dalloc(ctx, &P->d_adj_slot, nadj));
   PT(dalloc(ctx, &P->d_adj_lc, nadj));
@@ -465,13 +483,11 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
   PT(dalloc(ctx, &P->d_nnbr, nn));
   PT(dalloc(ctx, &d_U, (size_t)nadj * nne));
   PT(dalloc(ctx, &d_sorted, nn));
-  PT(dalloc(ctx, &P->d_srcoff, (size_t)nadj * nne + nn));
-  PT(dalloc(ctx, &P->d_src, (size_t)nadj * nne));
+  PT(dalloc(ctx, &P->d_cslot, (size_t)nadj * nne));
   PC(cudaFuncSetAttribute(k_nbr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   unsigned gridn = (unsigned)std::min<int64_t>((nn + WPB - 1) / WPB, (int64_t)ctx->sm_count * 64);
   if (gridn == 0) gridn = 1;
-  k_nbr<<<gridn, WPB * 32, smem1, st>>>(S, P->d_adjptr, P->d_adj_slot, maxdeg, capc, W, P->d_nnbr, d_U, P->d_srcoff, P->d_src, d_sorted,
-                                        d_flags + 1);
+  k_nbr<<<gridn, WPB * 32, smem1, st>>>(S, P->d_adjptr, P->d_adj_slot, maxdeg, capc, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1);
   ctx->launches++;
   PT(dalloc(ctx, &P->d_nbrptr, nn + 1));
   int64_t total_nbr = 0;
@@ -519,25 +535,35 @@ int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, double *d_nzval) {
   fegpu_mesh *mesh = dm->mesh;
   if (!P) return fegpu_fail(ctx, FEGPU_ERR_STATE, "no pattern");
   if (P->nnz == 0) return FEGPU_OK;
-  GatherParams G{mesh->nnodes, mesh->nne, dm->ndn, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, P->d_nnbr, P->d_nbrptr, P->d_srcoff,
-                 P->d_src, P->d_rank, dm->d_dof, P->d_colptr, d_V, d_nzval, P->maxdeg, P->maxcand, P->maxnbr};
-  const int u16_per_warp = ((P->maxnbr + 1 + P->maxcand + 3) / 4) * 4;
-  const size_t smem = (size_t)GWPB * ((size_t)P->maxdeg + u16_per_warp / 4) * sizeof(unsigned long long);
-  if (smem > 200 * 1024) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: gather staging exceeds shared memory");
-  unsigned grid = (unsigned)std::min<int64_t>((mesh->nnodes + GWPB - 1) / GWPB, (int64_t)ctx->sm_count * 64);
+  GatherParams G{mesh->nnodes, mesh->nne, dm->ndn, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, P->d_nnbr, P->d_nbrptr, P->d_cslot,
+                 P->d_rank, dm->d_dof, P->d_colptr, d_V, d_nzval, P->maxnbr};
+  const int EM = mesh->nne * dm->ndn;
+  const int lpn = (EM <= 8) ? 8 : (EM <= 16 ? 16 : 32);
+  const int npw = 32 / lpn;
+  const size_t smem = (size_t)GWPB * npw * P->maxnbr * dm->ndn * dm->ndn * sizeof(double);
+  if (smem > 200 * 1024) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: gather accumulators exceed shared memory");
+  const int64_t per_block = (int64_t)GWPB * npw;
+  unsigned grid = (unsigned)std::min<int64_t>((mesh->nnodes + per_block - 1) / per_block, (int64_t)ctx->sm_count * 32);
   if (grid == 0) grid = 1;
-#define LAUNCH_GATHER(N)                                                                                             \
+#define LAUNCH_GATHER(L, N)                                                                                          \
   do {                                                                                                               \
-    if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_gather<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_gather<N><<<grid, GWPB * 32, smem, ctx->stream>>>(G);                                                          \
+    if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_gather<L, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_gather<L, N><<<grid, GWPB * 32, smem, ctx->stream>>>(G);                                                       \
+  } while (0)
+#define LAUNCH_GATHER_L(N)                         \
+  do {                                             \
+    if (lpn == 8) LAUNCH_GATHER(8, N);             \
+    else if (lpn == 16) LAUNCH_GATHER(16, N);      \
+    else LAUNCH_GATHER(32, N);                     \
   } while (0)
   switch (dm->ndn) {
-    case 1: LAUNCH_GATHER(1); break;
-    case 2: LAUNCH_GATHER(2); break;
-    case 3: LAUNCH_GATHER(3); break;
-    default: LAUNCH_GATHER(0); break;
+    case 1: LAUNCH_GATHER_L(1); break;
+    case 2: LAUNCH_GATHER_L(2); break;
+    case 3: LAUNCH_GATHER_L(3); break;
+    default: LAUNCH_GATHER_L(0); break;
   }
 #undef LAUNCH_GATHER
+#undef LAUNCH_GATHER_L
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return FEGPU_OK;
