@@ -325,14 +325,16 @@ struct GatherParams {
   const int64_t *colptr;
   const double *V;
   double *nzval;
-  int maxnbr;
+  int maxnbr, maxdeg, maxcand;
 };
 
-// LPN lanes per node (32/LPN nodes per warp), NDN dofs per node (0 = runtime).  Shared per node group: maxnbr*ndn*ndn doubles.
+// LPN lanes per node (32/LPN nodes per warp), NDN dofs per node (0 = runtime).
+// Shared per node group: acc[maxnbr*ndn*ndn] doubles | base[maxdeg] int64 | cs[maxcand] uint16 (padded to 8 B)
 template <int LPN, int NDN>
 __global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
   extern __shared__ double sacc[];
   constexpr int NPW = 32 / LPN;
+  constexpr int QMAX = (NDN > 0) ? NDN : 6;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int g = lane / LPN, gl = lane % LPN;
   const int ndn = (NDN > 0) ? NDN : G.ndn;
@@ -340,7 +342,11 @@ __global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
   const int EM = nne * ndn;
   const int64_t EM2 = (int64_t)EM * EM;
   const int acc_stride = G.maxnbr * ndn * ndn;
-  double *acc = sacc + (size_t)(w * NPW + g) * acc_stride;
+  const int cs_words = (G.maxcand + 3) / 4;
+  const int grp_words = acc_stride + G.maxdeg + cs_words;
+  double *acc = sacc + (size_t)(w * NPW + g) * grp_words;
+  long long *base = reinterpret_cast<long long *>(acc + acc_stride);
+  uint16_t *cs = reinterpret_cast<uint16_t *>(base + G.maxdeg);
   const int64_t groups_total = (int64_t)gridDim.x * GWPB * NPW;
   const int64_t niter = (G.nnodes + groups_total - 1) / groups_total;
   for (int64_t it = 0; it < niter; it++) {
@@ -351,28 +357,65 @@ __global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
     const int deg = (live && nn > 0) ? (int)(G.adjptr[n + 1] - ab) : 0;
     const int per_col = nn * ndn;
     const int total = per_col * ndn;
+    // stage the node's metadata (one round trip to memory), clear the accumulators
+    for (int a = gl; a < deg; a += LPN) base[a] = (long long)G.adj_slot[ab + a] * EM2 + (long long)(G.adj_lc[ab + a] * ndn) * EM;
+    {
+      const uint16_t *csg = G.cslot + ab * nne;
+      for (int k = gl; k < deg * nne; k += LPN) cs[k] = csg[k];
+    }
     for (int i = gl; i < total; i += LPN) acc[i] = 0.0;
     int maxdeg = deg;
 #pragma unroll
     for (int d = LPN; d < 32; d <<= 1) maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, d));
     __syncwarp();
-    const uint16_t *cs = G.cslot + ab * nne;
-    for (int a = 0; a < maxdeg; a++) {
-      if (a < deg) {
-        const int64_t base = (int64_t)G.adj_slot[ab + a] * EM2 + (int64_t)(G.adj_lc[ab + a] * ndn) * EM;
-        const double *Vb = G.V + base;
-        for (int r = gl; r < EM; r += LPN) {
-          const int li = r / ndn, p = r - li * ndn;
+    if (EM <= LPN) {
+      // one value per lane and column: software-pipelined over the adjacent elements
+      const bool act = gl < EM;
+      const int li = gl / ndn, p = gl - li * ndn;
+      double cur[QMAX], nxt[QMAX];
+      if (act && deg > 0) {
+        const double *Vb = G.V + base[0] + gl;
+#pragma unroll
+        for (int q = 0; q < QMAX; q++)
+          if (q < ndn) cur[q] = Vb[q * EM];
+      }
+      for (int a = 0; a < maxdeg; a++) {
+        if (act && a + 1 < deg) {
+          const double *Vb = G.V + base[a + 1] + gl;
+#pragma unroll
+          for (int q = 0; q < QMAX; q++)
+            if (q < ndn) nxt[q] = Vb[q * EM];
+        }
+        if (act && a < deg) {
           const unsigned s = cs[a * nne + li];
           if (s != 0xffffu) {
             double *dst = acc + s * ndn + p;
 #pragma unroll
-            for (int q = 0; q < (NDN > 0 ? NDN : 6); q++)
-              if (q < ndn) dst[q * per_col] += Vb[q * EM + r];
+            for (int q = 0; q < QMAX; q++)
+              if (q < ndn) dst[q * per_col] += cur[q];
           }
         }
+#pragma unroll
+        for (int q = 0; q < QMAX; q++) cur[q] = nxt[q];
+        __syncwarp();
       }
-      __syncwarp();
+    } else {
+      for (int a = 0; a < maxdeg; a++) {
+        if (a < deg) {
+          const double *Vb = G.V + base[a];
+          for (int r = gl; r < EM; r += LPN) {
+            const int li = r / ndn, p = r - li * ndn;
+            const unsigned s = cs[a * nne + li];
+            if (s != 0xffffu) {
+              double *dst = acc + s * ndn + p;
+#pragma unroll
+              for (int q = 0; q < QMAX; q++)
+                if (q < ndn) dst[q * per_col] += Vb[q * EM + r];
+            }
+          }
+        }
+        __syncwarp();
+      }
     }
     if (live && nn > 0) {
       const int64_t nb = G.rank ? G.nbrptr[n] : 0;
@@ -536,11 +579,11 @@ int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, double *d_nzval) {
   if (!P) return fegpu_fail(ctx, FEGPU_ERR_STATE, "no pattern");
   if (P->nnz == 0) return FEGPU_OK;
   GatherParams G{mesh->nnodes, mesh->nne, dm->ndn, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, P->d_nnbr, P->d_nbrptr, P->d_cslot,
-                 P->d_rank, dm->d_dof, P->d_colptr, d_V, d_nzval, P->maxnbr};
+                 P->d_rank, dm->d_dof, P->d_colptr, d_V, d_nzval, P->maxnbr, P->maxdeg, P->maxcand};
   const int EM = mesh->nne * dm->ndn;
   const int lpn = (EM <= 8) ? 8 : (EM <= 16 ? 16 : 32);
   const int npw = 32 / lpn;
-  const size_t smem = (size_t)GWPB * npw * P->maxnbr * dm->ndn * dm->ndn * sizeof(double);
+  const size_t smem = (size_t)GWPB * npw * ((size_t)P->maxnbr * dm->ndn * dm->ndn + P->maxdeg + (P->maxcand + 3) / 4) * sizeof(double);
   if (smem > 200 * 1024) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: gather accumulators exceed shared memory");
   const int64_t per_block = (int64_t)GWPB * npw;
   unsigned grid = (unsigned)std::min<int64_t>((mesh->nnodes + per_block - 1) / per_block, (int64_t)ctx->sm_count * 32);
