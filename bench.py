@@ -27,6 +27,7 @@ import time
 
 import numpy as np
 
+_emit = None
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -166,7 +167,7 @@ def run_reference(args):
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "C restatement of FinEtools.jl v8.2.11 (oracle/fe_oracle.c); Julia is not installed on this image"}
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -357,7 +358,7 @@ def run_gpu(args):
                    "phases_ms": cph, "note": "re-assembly on the cached pattern (integration + gather-sum), reported separately"},
         "nnz_per_s_csc_construction": nnz_total / ((ph["symbolic_ms"] + ph["numeric_ms"]) * 1e-3),
     }
-    print(json.dumps(line))
+    _emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -374,6 +375,16 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    # stdout carries exactly ONE JSON line: everything else a library prints (e.g. "NCCL version ...") is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+
+    def _emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
         run_reference(args)
     else:
