@@ -313,9 +313,23 @@ def test_row_block_partition_reassembles_the_matrix(fe, orc, gpu_ctx, nparts):
     assert abs(diff).max() <= 1e-12 * np.abs(ref[2]).max()
 
 
+def _sampled_symmetry(colptr, rowval, nzval, cols):
+    """K[i,j] == K[j,i] bit for bit on the entries of the sampled columns (binary search in the partner column)."""
+    for j in cols:
+        lo, hi = colptr[j] - 1, colptr[j + 1] - 1
+        for k in range(lo, hi, max(1, (hi - lo) // 9)):
+            i = rowval[k] - 1
+            seg = rowval[colptr[i] - 1: colptr[i + 1] - 1]
+            pos = np.searchsorted(seg, j + 1)
+            assert pos < seg.size and seg[pos] == j + 1
+            assert nzval[colptr[i] - 1 + pos] == nzval[k]
+
+
 def test_full_size_config2_properties(fe, gpu_ctx):
     """BASELINE config 2 at full size (128^3 H8 elasticity, 2.1 M elements, 1.2 G triplets): size-independent properties.
-    nnz = 9*385^3; K is exactly symmetric (the element triangle is mirrored); rigid translations are in the null space."""
+    nnz = 9*385^3; rows ascending; K exactly symmetric (the element triangle is mirrored, same summation order on both
+    sides); rigid translations in the null space; a second assembly is bit-identical and served from the cached pattern."""
+    import scipy.sparse as sp
     n = 128
     fens, fes = fe.H8block(1.0, 1.0, 1.0, n, n, n)
     u = make_field(fe, fens, 3)
@@ -323,21 +337,92 @@ def test_full_size_config2_properties(fe, gpu_ctx):
     a = fe.SysmatAssemblerSparseGPU(0.0)
     femm = fe.FEMMBase(fe.IntegDomain(fes, rule))
     geom = fe.NodalField(fens.xyz)
-    K = fe.bilform_lin_elastic(femm, a, geom, u, fe.DeforModelRed3D, fe.DataCache(isotropic_C()))
-    assert K.nnz == 9 * 385 ** 3
-    assert K.shape == (3 * 129 ** 3, 3 * 129 ** 3)
-    ip = K.indptr
-    assert np.all(np.diff(ip) > 0)
-    scale = np.abs(K.data).max()
+    colptr, rowval, nzval, m_, n_ = fe.bilform_lin_elastic(femm, a, geom, u, fe.DeforModelRed3D, fe.DataCache(isotropic_C()), raw=True)
+    assert nzval.size == 9 * 385 ** 3 and m_ == n_ == 3 * 129 ** 3
+    assert colptr[0] == 1 and colptr[-1] == nzval.size + 1 and np.all(np.diff(colptr) > 0)
+    d = np.diff(rowval)
+    d[colptr[1:-1] - 2] = 1
+    assert np.all(d > 0)  # rows strictly increasing inside every column
+    del d
+    K = sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(m_, n_))
+    scale = np.abs(nzval).max()
     for comp in range(3):
-        v = np.zeros(K.shape[0])
+        v = np.zeros(m_)
         v[u.dofnums[:, comp] - 1] = 1.0
         assert np.abs(K @ v).max() <= 1e-10 * scale
-    # symmetry on a sampled set of columns (full transpose of 513 M entries is too slow for a test)
-    cols = np.arange(0, K.shape[0], 50021)
-    sub = K[:, cols].tocoo()
-    vals_t = np.asarray(K[cols[sub.col], sub.row]).reshape(-1)
-    np.testing.assert_array_equal(vals_t, sub.data)
+    del K
+    _sampled_symmetry(colptr, rowval, nzval, np.arange(0, n_, 150001))
+    nz2 = np.empty_like(nzval)
+    fe.bilform_lin_elastic(femm, a, geom, u, fe.DeforModelRed3D, fe.DataCache(isotropic_C()), raw=True, out=(colptr, rowval, nz2))
+    assert a.pattern_was_cached()
+    np.testing.assert_array_equal(nzval, nz2)
+
+
+def test_full_size_config4_properties(fe, gpu_ctx):
+    """BASELINE config 4 on one GPU (256^3 H8 diffusion, 16.8 M elements): nnz = 769^3, constants in the null space,
+    symmetry, the same matrix from two row-block halves (multi-GPU semantics on one device)."""
+    import scipy.sparse as sp
+    n = 256
+    fens, fes = fe.H8block(1.0, 1.0, 1.0, n, n, n)
+    u = make_field(fe, fens, 1)
+    rule = fe.GaussRule(3, 2)
+    a = fe.SysmatAssemblerSparseGPU(0.0)
+    femm = fe.FEMMBase(fe.IntegDomain(fes, rule))
+    geom = fe.NodalField(fens.xyz)
+    colptr, rowval, nzval, m_, n_ = fe.bilform_diffusion(femm, a, geom, u, fe.DataCache(KAPPA3), raw=True)
+    assert nzval.size == 769 ** 3 and m_ == n_ == 257 ** 3
+    K = sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(m_, n_))
+    assert np.abs(K @ np.ones(m_)).max() <= 1e-10 * np.abs(nzval).max()
+    del K
+    _sampled_symmetry(colptr, rowval, nzval, np.arange(0, n_, 400009))
+    owner = fe.slab_owner(fens.count(), 2)
+    nnz_blocks = 0
+    for p in range(2):
+        cp, rv, nz, _, _ = fe.bilform_diffusion(femm, a, geom, u, fe.DataCache(KAPPA3), raw=True, node_owner=owner, my_rank=p)
+        nnz_blocks += nz.size
+        # a column in the middle of rank p's slab lies entirely inside the block: identical to the full matrix's column
+        j = int(np.nonzero(owner == p)[0][owner[owner == p].size // 2])
+        full = slice(colptr[j] - 1, colptr[j + 1] - 1)
+        blk = slice(cp[j] - 1, cp[j + 1] - 1)
+        np.testing.assert_array_equal(rv[blk], rowval[full])
+        np.testing.assert_array_equal(nz[blk], nzval[full])
+    assert nnz_blocks == nzval.size
+
+
+def test_full_size_config3_t10_mass_cached_reassembly(fe, gpu_ctx):
+    """BASELINE config 3: consistent mass on a distorted T10 block (100^3 cells, 6 M quadratic tets), TetRule(4), then
+    re-assembly on the cached pattern after the geometry moved.  1'M1 = sum of the tet volumes (straight-edged T10)."""
+    n = 100
+    f4, s4 = fe.T4block(1.0, 1.0, 1.0, n, n, n)
+    h = 1.0 / n
+    x = f4.xyz
+    x0 = x.copy()
+    x[:, 0] += 0.2 * h * np.sin(3 * np.pi * x0[:, 1]) * np.cos(2 * np.pi * x0[:, 2])
+    x[:, 1] += 0.2 * h * np.sin(3 * np.pi * x0[:, 2]) * np.cos(2 * np.pi * x0[:, 0])
+    x[:, 2] += 0.2 * h * np.sin(3 * np.pi * x0[:, 0]) * np.cos(2 * np.pi * x0[:, 1])
+    fens, fes = fe.T4toT10(f4, s4)
+    assert fes.count() == 6 * n ** 3 and fens.count() == (2 * n + 1) ** 3
+
+    def tetvol(xyz):
+        c = fes.conn[:, :4] - 1
+        e1, e2, e3 = xyz[c[:, 1]] - xyz[c[:, 0]], xyz[c[:, 2]] - xyz[c[:, 0]], xyz[c[:, 3]] - xyz[c[:, 0]]
+        return (np.einsum("ij,ij->i", np.cross(e1, e2), e3) / 6.0).sum()
+
+    u = make_field(fe, fens, 1)
+    a = fe.SysmatAssemblerSparseGPU(0.0)
+    femm = fe.FEMMBase(fe.IntegDomain(fes, fe.TetRule(4)))
+    geom = fe.NodalField(fens.xyz)
+    colptr, rowval, nzval, m_, n_ = fe.bilform_dot(femm, a, geom, u, fe.DataCache(np.eye(1)), raw=True)
+    assert nzval.size == 230 * n ** 3 + 138 * n ** 2 + 24 * n + 1
+    vol = tetvol(fens.xyz)
+    assert abs(nzval.sum() - vol) <= 1e-9 * vol
+    # move the geometry (affine stretch keeps mid-edge nodes at the midpoints), re-assemble on the cached pattern
+    geom.values[:, 2] *= 1.25
+    nz2 = np.empty_like(nzval)
+    fe.bilform_dot(femm, a, geom, u, fe.DataCache(np.eye(1)), raw=True, out=(colptr, rowval, nz2))
+    assert a.pattern_was_cached()
+    assert abs(nz2.sum() - 1.25 * vol) <= 1e-9 * vol
+    assert np.abs(nz2 - 1.25 * nzval).max() <= 1e-12 * np.abs(nz2).max()
 
 
 def test_golden_fixtures_on_gpu(fe, gpu_ctx):
