@@ -201,6 +201,10 @@ def run_gpu(args):
     a = fe.SysmatAssemblerSparseGPU(0.0, ctx=ctx)
     femm = fe.FEMMBase(fe.IntegDomain(fes, rule))
     geom = fe.NodalField(fens.xyz)
+    # the step's input (node coordinates) lives in page-locked, column-major host memory, as the contract asks
+    pinned_xyz = torch.empty(geom.values.shape[::-1], dtype=torch.float64, pin_memory=True).numpy().T
+    pinned_xyz[:] = geom.values
+    geom.values = pinned_xyz
     cache = fe.DataCache(C)
     L = _lib.lib()
 
@@ -349,7 +353,9 @@ def run_gpu(args):
                    "step": "fresh assembly: pattern cache invalidated before every step"},
         "clocks": clocks,
         "e2e": {"value": nelem_global / (e2e_s / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "note": "per rank: xyz H2D + full CSC (colptr,rowval,nzval) D2H into pinned host arrays"},
+                "steps": e2e_steps, "note": "per rank: xyz H2D (pinned) + full CSC (colptr,rowval,nzval) into pinned host Int64/Float64 arrays; rowval crosses "
+                        "the link as int32 and is widened by 4 host threads (fegpu_transfer.cu), so link bytes = d2h_bytes - 4*nnz",
+                "link_d2h_bytes_per_step": int(d2h - 4 * nnz_local), "transfer_stats": ctx.transfer_stats()},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

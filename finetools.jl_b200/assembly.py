@@ -41,6 +41,11 @@ class GPUContext:
     def launch_count(self):
         return int(_lib.lib().fegpu_launch_count(self.handle))
 
+    def transfer_stats(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(_lib.lib().fegpu_transfer_stats(self.handle, C.byref(a), C.byref(b)), self.handle)
+        return {"staged_chunks": a.value, "bypassed_chunks": b.value}
+
     def measure_peaks(self):
         a, b = C.c_double(0), C.c_double(0)
         check(_lib.lib().fegpu_measure_peaks(self.handle, C.byref(a), C.byref(b)), self.handle)

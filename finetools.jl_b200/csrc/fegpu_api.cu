@@ -150,6 +150,7 @@ int32_t fegpu_destroy(fegpu_ctx *ctx) {
   if (!ctx) return FEGPU_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->xfer) fe_transfer_free(ctx->xfer);
   delete ctx;
   return FEGPU_OK;
 }
@@ -641,6 +642,8 @@ int32_t fegpu_makematrix_copy(fegpu_asm *as, int64_t *colptr, int64_t *rowval, d
   if (!as->have_result) return fegpu_fail(ctx, FEGPU_ERR_STATE, "no assembled matrix");
   DeviceGuard g(ctx->device);
   cudaStream_t st = ctx->stream;
+  // large results go through the transport of fegpu_transfer.cu (int32 row indices on the link, host-thread widening)
+  if (as->nnz >= ((int64_t)1 << 20) && as->nrows < INT32_MAX) return fe_copy_result(as, colptr, rowval, nzval);
   if (colptr) CUDA_TRY(ctx, cudaMemcpyAsync(colptr, as->d_colptr, sizeof(int64_t) * (as->ncols + 1), cudaMemcpyDeviceToHost, st));
   if (rowval && as->nnz) CUDA_TRY(ctx, cudaMemcpyAsync(rowval, as->d_rowval, sizeof(int64_t) * as->nnz, cudaMemcpyDeviceToHost, st));
   if (nzval && as->nnz) CUDA_TRY(ctx, cudaMemcpyAsync(nzval, as->d_nzval, sizeof(double) * as->nnz, cudaMemcpyDeviceToHost, st));

@@ -19,6 +19,7 @@ struct fegpu_ctx {
   int64_t launches = 0;
   int sm_count = 148;
   std::string err;
+  struct Transfer *xfer = nullptr;  // staging ring + host threads of the result transport (fegpu_transfer.cu), lazily built
 };
 
 struct Pattern;  // fegpu_pattern.cu
@@ -132,6 +133,11 @@ int32_t fe_coo_to_csc(fegpu_asm *as, int64_t n, const int64_t *d_I, const int64_
                       int64_t ncols);
 // emit the reference-order (I, J) of a bilform assembly (AssemblyModule.jl:266-279) from conn + dof map
 int32_t fe_emit_ij(fegpu_dofmap *dm, int64_t *d_I, int64_t *d_J);
+
+// ---- result transport (fegpu_transfer.cu) --------------------------------------------------------------
+// device CSC -> caller's host arrays; rowval crosses the link as int32 and is widened by host threads
+int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *nzval);
+void fe_transfer_free(struct Transfer *t);
 
 int32_t fe_asm_reserve(fegpu_asm *as, double **buf, size_t *cap, size_t need_doubles);
 int32_t fe_reserve_bytes(fegpu_ctx *ctx, void **buf, size_t *cap, size_t need_bytes);

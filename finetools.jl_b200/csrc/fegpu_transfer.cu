@@ -1,0 +1,331 @@
+// Result transport: the device-resident CSC -> the caller's host arrays (fegpu_makematrix_copy).
+//
+// The CSC of BASELINE config 2 is 8.27 GB (rowval 4.1 GB + nzval 4.1 GB + colptr), i.e. ~180 ms of PCIe Gen5 time against an
+// 11 ms assembly: the device->host link is the end-to-end bottleneck, so the bytes that cross it are minimised.
+//   rowval : row indices fit 32 bits (the dof map is int32 on the device), so they cross the link as int32 chunks
+//            (k_narrow -> pinned staging ring) and are widened to the caller's Int64 array by a small pool of host threads
+//            (AVX2 sign-extension + non-temporal stores) while the next chunks and nzval are in flight.  Measured on the
+//            B200 hosts (profiles/r01_xfer_sweep.jsonl): 8.27 GB plain DMA 146-155 ms; this transport 134 ms with 4 threads
+//            (more threads compete with the DMA for host memory bandwidth: 16 threads 142-149 ms).  The destination
+//            may be pageable memory (a Julia Vector{Int}): the threads write it directly, no driver bounce buffer.
+//   nzval  : DMA straight into the destination when it is page-locked; otherwise through the same staging ring with the
+//            threads doing the memcpy (faster than the driver's single-threaded pageable path).
+//   colptr : one plain copy.
+// rowval and nzval chunks are interleaved on the copy stream so widening chunk c overlaps the transfer of nzval chunk c and
+// rowval chunk c+1.  If the threads fall behind the link (the next chunk has already landed when they finish one) and the
+// destination is page-locked, the next rowval chunk bypasses them as plain int64 DMA: the split balances itself.  This is a transport codec only: every value is produced on the device.
+#include <immintrin.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+
+#include "fegpu_internal.h"
+
+namespace {
+
+constexpr int XF_NBUF = 4;                        // staging ring depth
+constexpr size_t XF_CHUNK_MAX = (size_t)32 << 20;  // bytes per staging buffer (device + pinned host)
+
+__global__ void k_narrow(const int64_t *__restrict__ in, int32_t *__restrict__ out, int64_t n) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    const longlong2 a = *reinterpret_cast<const longlong2 *>(in + i4), b = *reinterpret_cast<const longlong2 *>(in + i4 + 2);
+    *reinterpret_cast<int4 *>(out + i4) = make_int4((int)a.x, (int)a.y, (int)b.x, (int)b.y);
+  } else {
+    for (int64_t i = i4; i < n; i++) out[i] = (int32_t)in[i];
+  }
+}
+
+class HostPool {
+ public:
+  explicit HostPool(int n) : n_(n) {
+    for (int t = 0; t < n_; t++) th_.emplace_back([this, t] { loop(t); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      gen_++;
+    }
+    cv_.notify_all();
+    for (auto &t : th_) t.join();
+  }
+  int size() const { return n_; }
+  // runs fn(tid, nthreads) on every worker and returns when all are done
+  void run(const std::function<void(int, int)> &fn) {
+    std::unique_lock<std::mutex> lk(mu_);
+    fn_ = &fn;
+    pending_ = n_;
+    gen_++;
+    cv_.notify_all();
+    done_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void loop(int tid) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int, int)> *fn;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        fn = fn_;
+      }
+      (*fn)(tid, n_);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  int n_;
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int, int)> *fn_ = nullptr;
+  uint64_t gen_ = 0;
+  int pending_ = 0;
+  bool stop_ = false;
+};
+
+__attribute__((target("avx2"))) void widen_avx2(const int32_t *src, int64_t *dst, size_t n) {
+  size_t i = 0;
+  while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 31)) { dst[i] = src[i]; i++; }
+  for (; i + 8 <= n; i += 8) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 4));
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), _mm256_cvtepi32_epi64(a));
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 4), _mm256_cvtepi32_epi64(b));
+  }
+  for (; i < n; i++) dst[i] = src[i];
+  _mm_sfence();
+}
+
+__attribute__((target("avx512f"))) void widen_avx512(const int32_t *src, int64_t *dst, size_t n) {
+  size_t i = 0;
+  while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 63)) { dst[i] = src[i]; i++; }
+  for (; i + 16 <= n; i += 16) {
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+    const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 8));
+    _mm512_stream_si512(reinterpret_cast<__m512i *>(dst + i), _mm512_cvtepi32_epi64(a));
+    _mm512_stream_si512(reinterpret_cast<__m512i *>(dst + i + 8), _mm512_cvtepi32_epi64(b));
+  }
+  for (; i < n; i++) dst[i] = src[i];
+  _mm_sfence();
+}
+
+void widen_scalar(const int32_t *src, int64_t *dst, size_t n) {
+  for (size_t i = 0; i < n; i++) dst[i] = src[i];
+}
+
+}  // namespace
+
+struct Transfer {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ready = nullptr;             // results of the compute stream are complete
+  cudaEvent_t done[XF_NBUF] = {};          // staging buffer b has landed in pinned memory
+  void *d_stage[XF_NBUF] = {};
+  void *h_stage[XF_NBUF] = {};
+  HostPool *pool = nullptr;
+  int simd = 0;                            // 0 scalar, 1 AVX2, 2 AVX-512
+  size_t chunk_bytes = XF_CHUNK_MAX;       // FEGPU_XFER_CHUNK_MB (tuning knob, <= 32)
+  bool narrow = true;                      // FEGPU_XFER_NARROW=0: plain int64 DMA (A/B measurements)
+  int64_t staged = 0, bypassed = 0;        // chunk counters (diagnostics)
+  ~Transfer() {
+    delete pool;
+    for (int b = 0; b < XF_NBUF; b++) {
+      if (d_stage[b]) cudaFree(d_stage[b]);
+      if (h_stage[b]) cudaFreeHost(h_stage[b]);
+      if (done[b]) cudaEventDestroy(done[b]);
+    }
+    if (ready) cudaEventDestroy(ready);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+void fe_transfer_free(Transfer *t) { delete t; }
+
+static int32_t transfer_get(fegpu_ctx *ctx, Transfer **out) {
+  if (ctx->xfer) { *out = ctx->xfer; return FEGPU_OK; }
+  Transfer *t = new Transfer();
+  ctx->xfer = t;  // owned by the context from here on (also on error paths)
+  CUDA_TRY(ctx, cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+  CUDA_TRY(ctx, cudaEventCreateWithFlags(&t->ready, cudaEventDisableTiming));
+  for (int b = 0; b < XF_NBUF; b++) {
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&t->done[b], cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaMalloc(&t->d_stage[b], XF_CHUNK_MAX));
+    CUDA_TRY(ctx, cudaHostAlloc(&t->h_stage[b], XF_CHUNK_MAX, cudaHostAllocDefault));
+  }
+  int nt = (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  nt = std::min(nt, 4);  // measured on the B200 hosts: 4 threads keep up with the link; more only steal memory bandwidth from the DMA
+  if (const char *e = std::getenv("FEGPU_HOST_THREADS")) nt = std::max(1, std::atoi(e));
+  t->pool = new HostPool(nt);
+  __builtin_cpu_init();
+  t->simd = __builtin_cpu_supports("avx2") ? 1 : 0;  // AVX-512 (FEGPU_XFER_SIMD=2) measured no faster: the loop is memory-bound
+  if (std::getenv("FEGPU_XFER_SIMD") && std::atoi(std::getenv("FEGPU_XFER_SIMD")) >= 2 && __builtin_cpu_supports("avx512f")) t->simd = 2;
+  else if (const char *e = std::getenv("FEGPU_XFER_SIMD")) t->simd = std::min(t->simd, std::max(0, std::atoi(e)));
+  if (const char *e = std::getenv("FEGPU_XFER_CHUNK_MB")) t->chunk_bytes = std::min(XF_CHUNK_MAX, (size_t)std::max(1, std::atoi(e)) << 20);
+  if (const char *e = std::getenv("FEGPU_XFER_NARROW")) t->narrow = std::atoi(e) != 0;
+  *out = t;
+  return FEGPU_OK;
+}
+
+static bool is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// One stream of `n` items: device source -> (optional narrowing) -> pinned ring -> host threads -> destination.
+struct StagedJob {
+  const void *d_src = nullptr;  // int64 (narrow) or raw bytes
+  void *h_dst = nullptr;
+  int64_t n = 0;                // items
+  bool narrow = false;          // int64 -> int32 on the device, widened back on the host
+  bool dst_pinned = false;      // a lagging host may be bypassed by plain DMA of the 8-byte items
+  size_t item_dev = 0;          // bytes per item in the staging buffers
+  int64_t per_chunk = 0;
+  int64_t next = 0;             // first item not yet issued
+};
+
+int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *nzval) {
+  fegpu_ctx *ctx = as->ctx;
+  Transfer *T = nullptr;
+  FE_TRY(transfer_get(ctx, &T));
+  cudaStream_t cs = T->stream;
+  CUDA_TRY(ctx, cudaEventRecord(T->ready, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(cs, T->ready, 0));
+  const int64_t nnz = as->nnz;
+
+  StagedJob jobs[2];
+  int njobs = 0;
+  const double *direct_nz = nullptr;
+  const int64_t *direct_rv = nullptr;
+  if (rowval && nnz) {
+    if (!T->narrow && is_pinned(rowval)) {
+      direct_rv = as->d_rowval;
+    } else {
+      StagedJob &j = jobs[njobs++];
+      j.d_src = as->d_rowval; j.h_dst = rowval; j.n = nnz; j.narrow = true; j.item_dev = 4; j.dst_pinned = is_pinned(rowval);
+    }
+  }
+  if (nzval && nnz) {
+    if (is_pinned(nzval)) {
+      direct_nz = as->d_nzval;
+    } else {
+      StagedJob &j = jobs[njobs++];
+      j.d_src = as->d_nzval; j.h_dst = nzval; j.n = nnz; j.narrow = false; j.item_dev = 8;
+    }
+  }
+  int64_t total_chunks = 0;
+  for (int k = 0; k < njobs; k++) {
+    jobs[k].per_chunk = (int64_t)(T->chunk_bytes / jobs[k].item_dev);
+    total_chunks += (jobs[k].n + jobs[k].per_chunk - 1) / jobs[k].per_chunk;
+  }
+  if (colptr) CUDA_TRY(ctx, cudaMemcpyAsync(colptr, as->d_colptr, sizeof(int64_t) * (as->ncols + 1), cudaMemcpyDeviceToHost, cs));
+  if (direct_rv) CUDA_TRY(ctx, cudaMemcpyAsync(rowval, direct_rv, sizeof(int64_t) * nnz, cudaMemcpyDeviceToHost, cs));
+
+  // page-locked nzval goes by plain DMA, sliced in between the staged chunks so the link never idles while the threads work
+  int64_t nz_issued = 0;
+  const int64_t nz_slice = direct_nz ? (total_chunks ? (nnz + total_chunks - 1) / total_chunks : nnz) : 0;
+  auto issue_direct_nz = [&]() -> int32_t {
+    if (!direct_nz || nz_issued >= nnz) return FEGPU_OK;
+    const int64_t len = std::min(nz_slice, nnz - nz_issued);
+    CUDA_TRY(ctx, cudaMemcpyAsync(nzval + nz_issued, direct_nz + nz_issued, sizeof(double) * len, cudaMemcpyDeviceToHost, cs));
+    nz_issued += len;
+    return FEGPU_OK;
+  };
+
+  struct Pending { int buf, job; int64_t off, len; };
+  Pending ring[XF_NBUF];
+  int head = 0, npend = 0;          // FIFO of staged chunks in flight
+  int free_buf[XF_NBUF], nfree = XF_NBUF;
+  for (int b = 0; b < XF_NBUF; b++) free_buf[b] = b;
+  int rr = 0;                       // round-robin over the jobs
+  bool lagging = false;             // the next staged chunk had already landed when the threads finished the previous one
+  auto remaining = [&]() { for (int k = 0; k < njobs; k++) if (jobs[k].next < jobs[k].n) return true; return false; };
+
+  while (remaining() || npend > 0) {
+    int bypass = lagging ? 1 : 0;  // at most one bypassed chunk per consumed chunk
+    while (remaining() && (npend < XF_NBUF - 1 || bypass > 0)) {
+      while (jobs[rr].next >= jobs[rr].n) rr = (rr + 1) % njobs;
+      StagedJob &j = jobs[rr];
+      const int k = rr;
+      rr = (rr + 1) % njobs;
+      const int64_t off = j.next, len = std::min(j.per_chunk, j.n - off);
+      if (bypass > 0 && j.narrow && j.dst_pinned) {
+        // the host threads are the bottleneck right now: this chunk crosses the link as int64, straight to its destination
+        CUDA_TRY(ctx, cudaMemcpyAsync(static_cast<int64_t *>(j.h_dst) + off, static_cast<const int64_t *>(j.d_src) + off, sizeof(int64_t) * len,
+                                      cudaMemcpyDeviceToHost, cs));
+        bypass--;
+        T->bypassed++;
+      } else {
+        if (npend >= XF_NBUF - 1) break;
+        const int b = free_buf[--nfree];
+        if (j.narrow) {
+          k_narrow<<<grid_for((len + 3) / 4, 256), 256, 0, cs>>>(static_cast<const int64_t *>(j.d_src) + off, static_cast<int32_t *>(T->d_stage[b]), len);
+          ctx->launches++;
+          CUDA_TRY(ctx, cudaMemcpyAsync(T->h_stage[b], T->d_stage[b], (size_t)len * 4, cudaMemcpyDeviceToHost, cs));
+        } else {
+          CUDA_TRY(ctx, cudaMemcpyAsync(T->h_stage[b], static_cast<const char *>(j.d_src) + (size_t)off * j.item_dev, (size_t)len * j.item_dev,
+                                        cudaMemcpyDeviceToHost, cs));
+        }
+        CUDA_TRY(ctx, cudaEventRecord(T->done[b], cs));
+        ring[(head + npend) % XF_NBUF] = Pending{b, k, off, len};
+        npend++;
+        T->staged++;
+      }
+      j.next = off + len;
+      FE_TRY(issue_direct_nz());
+    }
+    if (npend == 0) continue;
+    const Pending p = ring[head];
+    head = (head + 1) % XF_NBUF;
+    npend--;
+    CUDA_TRY(ctx, cudaEventSynchronize(T->done[p.buf]));
+    const StagedJob &j = jobs[p.job];
+    const void *src = T->h_stage[p.buf];
+    const int simd = T->simd;
+    std::function<void(int, int)> fn = [&j, src, p, simd](int tid, int nth) {
+      // slices are multiples of 16 items so the vector loops stay aligned
+      const int64_t per = (((p.len + nth - 1) / nth) + 15) & ~(int64_t)15;
+      const int64_t lo = std::min<int64_t>(p.len, per * tid), hi = std::min<int64_t>(p.len, lo + per);
+      if (hi <= lo) return;
+      if (j.narrow) {
+        const int32_t *s = static_cast<const int32_t *>(src) + lo;
+        int64_t *d = static_cast<int64_t *>(j.h_dst) + p.off + lo;
+        if (simd == 2) widen_avx512(s, d, (size_t)(hi - lo));
+        else if (simd == 1) widen_avx2(s, d, (size_t)(hi - lo));
+        else widen_scalar(s, d, (size_t)(hi - lo));
+      } else {
+        std::memcpy(static_cast<char *>(j.h_dst) + (size_t)(p.off + lo) * 8, static_cast<const char *>(src) + (size_t)lo * 8, (size_t)(hi - lo) * 8);
+      }
+    };
+    T->pool->run(fn);
+    free_buf[nfree++] = p.buf;
+    lagging = npend > 0 && cudaEventQuery(T->done[ring[head].buf]) == cudaSuccess;
+  }
+  while (direct_nz && nz_issued < nnz) FE_TRY(issue_direct_nz());
+  CUDA_TRY(ctx, cudaStreamSynchronize(cs));
+  return FEGPU_OK;
+}
+
+extern "C" int32_t fegpu_transfer_stats(fegpu_ctx *ctx, int64_t *staged, int64_t *bypassed) {
+  if (!ctx) return FEGPU_ERR_ARG;
+  if (staged) *staged = ctx->xfer ? ctx->xfer->staged : 0;
+  if (bypassed) *bypassed = ctx->xfer ? ctx->xfer->bypassed : 0;
+  return FEGPU_OK;
+}

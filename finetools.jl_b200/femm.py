@@ -55,6 +55,7 @@ class _DeviceMesh:
         self.conn_ref = fes.conn
         self.rule_key = None
         self.dofmaps = []   # [(host copy of dofnums, nalldofs, handle)]
+        self._dofkeys = {}  # handle -> (id(u), numbering version, id(dofnums)) it was last matched with
         self.partition_key = None
 
     def update_geometry(self, geom):
@@ -92,17 +93,27 @@ class _DeviceMesh:
     def dofmap(self, u):
         dn = u.dofnums
         nall = u.nalldofs()
+        key = (id(u), getattr(u, "_dofver", None), id(dn))
+        step = max(1, dn.size // 4096)
         for host, n, h in self.dofmaps:
-            if n == nall and host.shape == dn.shape and np.array_equal(host, dn):
+            if n != nall or host.shape != dn.shape:
+                continue
+            # same field object and numbering version: a strided sample guards against in-place edits; otherwise compare all
+            if (key[1] is not None and self._dofkeys.get(h.value) == key and host.flags.f_contiguous == dn.flags.f_contiguous
+                    and np.array_equal(host.ravel(order="K")[::step], dn.ravel(order="K")[::step])) \
+                    or np.array_equal(host, dn):
+                self._dofkeys[h.value] = key
                 return h
         if dn.shape[0] != self.nnodes:
             raise FEGPUError(-2, "field u and geometry have different node counts")
         d = _lib.colmajor_i64(dn)
         h = VP()
         check(_lib.lib().fegpu_dofmap_upload(self.ctx.handle, self.handle, dn.shape[1], fptr(d), nall, nall, C.byref(h)), self.ctx.handle)
-        self.dofmaps.append((dn.copy(), nall, h))
+        self.dofmaps.append((dn.copy(order="K"), nall, h))
+        self._dofkeys[h.value] = key
         if len(self.dofmaps) > 4:
             _, _, old = self.dofmaps.pop(0)
+            self._dofkeys.pop(old.value, None)
             _lib.lib().fegpu_dofmap_destroy(old)
         return h
 

@@ -16,16 +16,19 @@ class FENodeSet:
 
 
 class NodalField:
-    """values (nents, ndn) float64, dofnums (nents, ndn) int64 (0 until numbered), kind (nents, ndn) int8."""
+    """values (nents, ndn) float64, dofnums (nents, ndn) int64 (0 until numbered), kind (nents, ndn) int8.
+    values and dofnums are stored column-major (order="F"), i.e. with the bytes of the Julia matrices they mirror, so they
+    cross the C ABI without a transposing copy."""
 
     def __init__(self, data):
         data = np.asarray(data, dtype=np.float64)
         if data.ndim == 1:
             data = data.reshape(-1, 1)
-        self.values = np.array(data, dtype=np.float64)
-        self.dofnums = np.zeros(self.values.shape, dtype=np.int64)
+        self.values = np.array(data, dtype=np.float64, order="F")  # copy, like the reference (NodalFieldModule.jl:34-40)
+        self.dofnums = np.zeros(self.values.shape, dtype=np.int64, order="F")
         self.kind = np.full(self.values.shape, DOF_KIND_FREE, dtype=np.int8)
         self.ranges = []
+        self._dofver = 0  # bumped whenever the numbering changes (device dof maps are cached against it)
 
     def ndofs(self):
         return self.values.shape[1]
@@ -75,6 +78,7 @@ def numberdofs(self, entperm=None, kinds=(DOF_KIND_FREE, DOF_KIND_DATA)):
         self.ranges.append((nxt, nxt + sel.size - 1))
         nxt += sel.size
     self.dofnums[perm, :] = flat.reshape(n, dim)
+    self._dofver = getattr(self, "_dofver", 0) + 1
     return self
 
 
@@ -96,6 +100,7 @@ def setebc(self, fenids=None, is_fixed=True, comp=None, val=0.0):
             self.kind[ids - 1, c - 1] = DOF_KIND_FREE
             self.values[ids - 1, c - 1] = 0.0
     self.ranges = []
+    self._dofver = getattr(self, "_dofver", 0) + 1
     return self
 
 

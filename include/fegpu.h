@@ -115,6 +115,10 @@ int32_t fegpu_makematrix(fegpu_asm *as);
  * SparseMatrixCSC(m, n, colptr, rowval, nzval): 1-based int64. */
 int32_t fegpu_makematrix_sizes(fegpu_asm *as, int64_t *nrows, int64_t *ncols, int64_t *nnz);
 int32_t fegpu_makematrix_copy(fegpu_asm *as, int64_t *colptr /* ncols+1 */, int64_t *rowval /* nnz */, double *nzval /* nnz */);
+/* Transport notes (fegpu_transfer.cu): for results above 1 M nonzeros rowval crosses the PCIe link as int32 and is widened
+ * into `rowval` by host threads (FEGPU_HOST_THREADS, default min(cores, 4)); destinations may be pageable or page-locked.
+ * fegpu_transfer_stats: staged (int32 + widen) and bypassed (plain int64 DMA) chunk counts so far. */
+int32_t fegpu_transfer_stats(fegpu_ctx *ctx, int64_t *staged_chunks, int64_t *bypassed_chunks);
 /* nzval only (re-assembly on a cached pattern: colptr/rowval did not change) */
 int32_t fegpu_makematrix_copy_values(fegpu_asm *as, double *nzval);
 /* device pointers of the current result (valid until the next assembly on this assembler) */

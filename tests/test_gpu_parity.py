@@ -439,3 +439,29 @@ def test_golden_fixtures_on_gpu(fe, gpu_ctx):
         fens, fes, u, rule, coef, form, et, kw = build_case(fe, CASES[name])
         got, _ = gpu_csc(fe, form, fes, fens, u, rule, coef, **kw)
         assert_parity((g["colptr"], g["rowval"], g["nzval"]), got)
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_result_transport_large(fe, orc, gpu_ctx, pinned):
+    """Results above 1 M nonzeros cross the link through the staged transport (int32 row indices widened by host threads,
+    fegpu_transfer.cu); the arrays that arrive must be the oracle's, for pageable and for page-locked destinations."""
+    fens, fes = fe.H8block(1.0, 2.0, 3.0, 18, 18, 18)
+    _distort(fens)
+    u = make_field(fe, fens, 3)
+    rule = fe.GaussRule(3, 2)
+    C = isotropic_C()
+    ref, _ = oracle_csc(orc, "elastic", "H8", fes, fens, u, rule, C)
+    nnz, n = ref[2].size, u.nalldofs()
+    assert nnz >= (1 << 20)
+    if pinned:
+        import torch
+        out = (torch.empty(n + 1, dtype=torch.int64, pin_memory=True).numpy(), torch.empty(nnz + 3, dtype=torch.int64, pin_memory=True).numpy()[3:],
+               torch.empty(nnz, dtype=torch.float64, pin_memory=True).numpy())
+    else:
+        out = (np.empty(n + 1, np.int64), np.empty(nnz + 1, np.int64)[1:], np.empty(nnz + 1, np.float64)[1:])  # odd alignment on purpose
+    got, a = gpu_csc(fe, "elastic", fes, fens, u, rule, C, out=out)
+    assert got[1] is out[1] and got[2] is out[2]
+    assert_parity(ref, got)
+    vals = np.full(nnz, np.nan)
+    a.fetch_values(vals)
+    np.testing.assert_array_equal(vals, got[2])
