@@ -1,6 +1,7 @@
 // C ABI of libfinegpu.so (include/fegpu.h): handles, uploads, the three bilinear forms, the generic assembler protocol,
 // result access.  No CPU fallback anywhere: every compute call ends in a kernel launch on the context's stream.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "fegpu_internal.h"
@@ -78,6 +79,19 @@ __global__ void k_elem_active(const int32_t *__restrict__ conn, int64_t nelem, i
   flag[e] = f;
 }
 
+// compact upper-block layout -> full element matrix, emission order (thread per full entry)
+__global__ void k_expand_compact(const double *__restrict__ Vc, double *__restrict__ Vf, int64_t nelem, int nne, int ndn) {
+  const int EM = nne * ndn;
+  const int64_t EM2 = (int64_t)EM * EM, CS = (int64_t)(nne * (nne + 1) / 2) * ndn * ndn;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nelem * EM2) return;
+  const int64_t e = i / EM2;
+  const int k = (int)(i - e * EM2), c = k / EM, r = k - c * EM;
+  const int li = r / ndn, p = r - li * ndn, lc = c / ndn, q = c - lc * ndn, nd2 = ndn * ndn;
+  const int off = (li <= lc) ? nd2 * (lc * (lc + 1) / 2 + li) + q * ndn + p : nd2 * (li * (li + 1) / 2 + lc) + p * ndn + q;
+  Vf[i] = Vc[e * CS + off];
+}
+
 __global__ void k_compact(const int32_t *__restrict__ flag, const int64_t *__restrict__ pos, int64_t nelem, int32_t *__restrict__ list) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < nelem && flag[e]) list[pos[e]] = (int32_t)e;
@@ -115,6 +129,15 @@ struct DeviceGuard {
 };
 
 }  // namespace
+
+int32_t fe_expand_compact(fegpu_ctx *ctx, const double *d_Vc, double *d_Vfull, int64_t nelem, int nne, int ndn) {
+  const int64_t n = nelem * (int64_t)(nne * ndn) * (nne * ndn);
+  if (n == 0) return FEGPU_OK;
+  k_expand_compact<<<grid_for(n, 256), 256, 0, ctx->stream>>>(d_Vc, d_Vfull, nelem, nne, ndn);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return FEGPU_OK;
+}
 
 extern "C" {
 
@@ -458,14 +481,10 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
   cudaStream_t st = ctx->stream;
   const int EM = mesh->nne * fa.ndn;
   const int64_t ntrip = mesh->nactive * (int64_t)EM * EM;
-  FE_TRY(fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(ntrip, 1)));
-  as->V_n = ntrip;
-  as->last_EM = EM;
   as->have_result = false;
   as->started = false;
+  // 1. symbolic phase first (cached in the dof map): it decides the layout the integration kernel writes
   CUDA_TRY(ctx, cudaEventRecord(as->ev[0], st));
-  FE_TRY(fe_integrate(mesh, fa, as->d_V));
-  CUDA_TRY(ctx, cudaEventRecord(as->ev[1], st));
   bool fast = fe_pattern_usable(dm);
   as->pattern_cached = false;
   if (fast) {
@@ -476,11 +495,23 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
       as->pattern_cached = true;
     }
   }
+  CUDA_TRY(ctx, cudaEventRecord(as->ev[1], st));
+  // 2. element integration.  Symmetric forms on the mesh-structured path write only the upper block triangle
+  FormArgs fa2 = fa;
+  static const bool compact_off = std::getenv("FEGPU_COMPACT") && std::atoi(std::getenv("FEGPU_COMPACT")) == 0;  // A/B knob
+  fa2.compact = fast && fe_form_symmetric(fa.form) && !compact_off;
+  const int64_t per_elem = fa2.compact ? fe_compact_size(mesh->nne, fa.ndn) : (int64_t)EM * EM;
+  FE_TRY(fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(mesh->nactive * per_elem, 1)));
+  as->V_n = ntrip;
+  as->last_EM = EM;
+  as->V_compact = fa2.compact;
+  FE_TRY(fe_integrate(mesh, fa2, as->d_V));
   CUDA_TRY(ctx, cudaEventRecord(as->ev[2], st));
+  // 3. numeric CSC phase
   if (fast) {
     const int64_t nnz = fe_pattern_nnz(dm->pat);
     FE_TRY(fe_asm_reserve(as, &as->d_nzval, &as->nz_cap, (size_t)std::max<int64_t>(nnz, 1)));
-    FE_TRY(fe_gather(dm, as->d_V, as->d_nzval));
+    FE_TRY(fe_gather(dm, as->d_V, fa2.compact, as->d_nzval));
     as->nnz = nnz;
     as->nrows = dm->row_nall;
     as->ncols = dm->col_nall;
@@ -606,12 +637,12 @@ int32_t fegpu_makematrix(fegpu_asm *as) {
   int32_t s = fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(n, 1));
   if (s != FEGPU_OK) { cleanup(); return s; }
   GT(cudaEventRecord(as->ev[0], st));
+  GT(cudaEventRecord(as->ev[1], st));
   if (n) {
     GT(cudaMemcpyAsync(dI, as->hI.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
     GT(cudaMemcpyAsync(dJ, as->hJ.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
     GT(cudaMemcpyAsync(as->d_V, as->hV.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
   }
-  GT(cudaEventRecord(as->ev[1], st));
   GT(cudaEventRecord(as->ev[2], st));
   s = fe_coo_to_csc(as, n, dI, dJ, as->d_V, as->g_row_nall, as->g_col_nall);
   cleanup();
@@ -621,6 +652,7 @@ int32_t fegpu_makematrix(fegpu_asm *as) {
   as->ev_valid = true;
   as->have_result = true;
   as->pattern_cached = false;
+  as->V_compact = false;
   as->started = false;  // "_buffer_pointer = 1": ready for the next startassembly!  (AssemblyModule.jl:327)
   as->V_n = 0;
   return finish(ctx);
@@ -684,7 +716,18 @@ int32_t fegpu_coo_copy(fegpu_asm *as, fegpu_mesh *mesh, fegpu_dofmap *dm, int64_
     cudaFree(dJ);
     FE_TRY(s);
   }
-  if (V) CUDA_TRY(ctx, cudaMemcpyAsync(V, as->d_V, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (V && as->V_compact) {
+    // the fast path stored the compact symmetric layout: expand to the reference's emission order for export
+    double *dfull = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void **)&dfull, sizeof(double) * n));
+    int32_t s = fe_expand_compact(ctx, as->d_V, dfull, mesh->nactive, mesh->nne, dm->ndn);
+    if (s == FEGPU_OK && cudaMemcpyAsync(V, dfull, sizeof(double) * n, cudaMemcpyDeviceToHost, st) != cudaSuccess) s = FEGPU_ERR_CUDA;
+    cudaStreamSynchronize(st);
+    cudaFree(dfull);
+    FE_TRY(s);
+  } else if (V) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(V, as->d_V, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  }
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   return FEGPU_OK;
 }
@@ -695,8 +738,10 @@ int32_t fegpu_last_timings(fegpu_asm *as, double ms[4]) {
   DeviceGuard g(as->ctx->device);
   CUDA_TRY(as->ctx, cudaEventSynchronize(as->ev[3]));
   float t;
+  // recorded order: ev0 -symbolic- ev1 -integration- ev2 -numeric- ev3; reported order: integration, symbolic, numeric
+  static const int first[3] = {1, 0, 2};
   for (int i = 0; i < 3; i++) {
-    CUDA_TRY(as->ctx, cudaEventElapsedTime(&t, as->ev[i], as->ev[i + 1]));
+    CUDA_TRY(as->ctx, cudaEventElapsedTime(&t, as->ev[first[i]], as->ev[first[i] + 1]));
     ms[i] = t;
   }
   CUDA_TRY(as->ctx, cudaEventElapsedTime(&t, as->ev[0], as->ev[3]));

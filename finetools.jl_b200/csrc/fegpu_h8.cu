@@ -44,7 +44,9 @@ __device__ __forceinline__ void inv3(const double *J, double *inv, double &det) 
 #undef R
 }
 
-template <bool GENERAL>
+// COMPACT: only the upper triangle (36 values, packed by columns: entry (r <= c) at c(c+1)/2 + r) is written -- the layout
+// k_gather reads for symmetric forms on the mesh-structured path; otherwise the full 8x8 matrix in emission order.
+template <bool GENERAL, bool COMPACT>
 __global__ void __launch_bounds__(128) k_h8_diffusion(const H8Params P) {
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= P.nactive) return;
@@ -117,6 +119,12 @@ __global__ void __launch_bounds__(128) k_h8_diffusion(const H8Params P) {
         }
     }
   }
+  if (COMPACT) {
+    double2 *out = reinterpret_cast<double2 *>(P.V + slot * 36);
+#pragma unroll
+    for (int i = 0; i < 36; i += 2) out[i >> 1] = make_double2(acc[i], acc[i + 1]);
+    return;
+  }
   // complete_lt! + emission order: V[slot][c*8 + r]
   double2 *out = reinterpret_cast<double2 *>(P.V + slot * 64);
 #pragma unroll
@@ -133,8 +141,9 @@ __global__ void __launch_bounds__(128) k_h8_diffusion(const H8Params P) {
 // ------------------------------------------------------------------------------------------------ elasticity
 constexpr int EL_EPB = 32;                 // elements per block
 constexpr int EL_GSTRIDE = 25;             // doubles per (element, point): 24 gradients + Jw
-// shared: G [8 pts][25][32 elems] doubles = 51200 B; staging for 16 elements: 16*576*8 = 73728 B (aliases G)
-constexpr int EL_SMEM_BYTES = 16 * 578 * 8;
+// shared: G [8 pts][25][32 elems] doubles = 51200 B; staging for 16 elements aliases G
+constexpr int EL_SMEM_FULL = 16 * 577 * 8;          // staging is the larger user
+constexpr int EL_SMEM_COMPACT = 8 * EL_GSTRIDE * EL_EPB * 8;  // G is (16 * 325 * 8 = 41600 B of staging fits inside)
 
 __device__ __forceinline__ void db_col(const double *g, double Jw, double DB[18]) {
   // DB[:, j] = Jw * D * B_b[:, j], B_b column j has 3 non-zeros (DeforModelRedModule.jl:463-468, Rm = I)
@@ -158,7 +167,10 @@ __device__ __forceinline__ void block_acc(double *k9, const double *ga, const do
   }
 }
 
-constexpr int EL_MSTRIDE = 578;           // staged element-matrix stride (doubles): 576 + pad against bank conflicts
+// staged element-matrix strides (doubles).  Odd => the 16 lanes of a half-warp (one element each, same offset) hit 16
+// distinct 8-byte bank pairs: conflict-free staging stores.
+constexpr int EL_MSTRIDE_FULL = 577;      // 576 values, emission order
+constexpr int EL_MSTRIDE_COMPACT = 325;   // 36 upper 3x3 blocks: block (a <= b) at 9*(b(b+1)/2 + a), column-major inside
 
 // Phase B + staging for the warp owning column nodes B1 = t and B2 = 7 - t.  All warps run the SAME code (t is a
 // warp-uniform runtime value): slots 0..4 always belong to column B2, slot 8 always to B1, slots 5..7 to B2 iff
@@ -173,7 +185,10 @@ __device__ __forceinline__ void load3(double *d, const double *g, int node) {
   d[2] = g[(node * 3 + 2) * EL_EPB];
 }
 
+template <bool COMPACT>
 __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, const int t, const int64_t slot0, const H8Params &P) {
+  constexpr int MSTRIDE = COMPACT ? EL_MSTRIDE_COMPACT : EL_MSTRIDE_FULL;
+  constexpr int MSIZE = COMPACT ? 324 : 576;
   const int B1 = t, B2 = 7 - t, NB2 = 8 - t;
   double K[9][9];
 #pragma unroll
@@ -211,43 +226,57 @@ __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, cons
   }
   block_bar();  // everyone is done reading G: the staging buffer may overwrite it
 
-  // ---- stage + write: two halves of 16 elements, element matrix = 576 doubles, column-major
+  // ---- stage + write: two halves of 16 elements
   for (int half = 0; half < 2; half++) {
     if ((lane >> 4) == half) {
-      double *M = sm + (size_t)(lane & 15) * EL_MSTRIDE;
+      double *M = sm + (size_t)(lane & 15) * MSTRIDE;
 #pragma unroll
       for (int s = 0; s < 9; s++) {
         const int a = (s < NB2) ? s : s - NB2;
         const int b = (s < NB2) ? B2 : B1;
         const bool diag = (a == b);
-        double *Mu = M + (b * 3) * 24 + a * 3;  // (row a-block, column b-block)
-        double *Ml = M + (a * 3) * 24 + b * 3;  // mirrored block
+        if (COMPACT) {
+          double *Mb = M + 9 * (b * (b + 1) / 2 + a);  // 3x3 block (row node a, column node b), column-major
 #pragma unroll
-        for (int jx = 0; jx < 3; jx++)
+          for (int jx = 0; jx < 3; jx++)
 #pragma unroll
-          for (int ix = 0; ix < 3; ix++)
-            if (!diag || ix <= jx) {  // diagonal block: only its upper triangle is the reference's value
-              const double v = K[s][ix + 3 * jx];
-              Mu[jx * 24 + ix] = v;
-              Ml[ix * 24 + jx] = v;  // complete_lt!
-            }
+            for (int ix = 0; ix < 3; ix++)
+              if (!diag || ix <= jx) {  // diagonal block: its upper triangle is the reference's value, mirrored (complete_lt!)
+                const double v = K[s][ix + 3 * jx];
+                Mb[jx * 3 + ix] = v;
+                if (diag && ix != jx) Mb[ix * 3 + jx] = v;
+              }
+        } else {
+          double *Mu = M + (b * 3) * 24 + a * 3;  // (row a-block, column b-block)
+          double *Ml = M + (a * 3) * 24 + b * 3;  // mirrored block
+#pragma unroll
+          for (int jx = 0; jx < 3; jx++)
+#pragma unroll
+            for (int ix = 0; ix < 3; ix++)
+              if (!diag || ix <= jx) {  // diagonal block: only its upper triangle is the reference's value
+                const double v = K[s][ix + 3 * jx];
+                Mu[jx * 24 + ix] = v;
+                Ml[ix * 24 + jx] = v;  // complete_lt!
+              }
+        }
       }
     }
     block_bar();
     const int64_t sbase = slot0 + half * 16;
     const int64_t nvalid = min((int64_t)16, P.nactive - sbase);
     if (nvalid > 0) {
-      const int nvec = (int)(nvalid * 288);  // double2 count; contiguous slots are contiguous in V
-      double2 *dst = reinterpret_cast<double2 *>(P.V + sbase * 576);
-      for (int i = threadIdx.x; i < nvec; i += 128) {
-        const int el = i / 288, k = i - el * 288;
-        dst[i] = *reinterpret_cast<const double2 *>(sm + (size_t)el * EL_MSTRIDE + 2 * k);
+      const int nval = (int)(nvalid * MSIZE);  // contiguous slots are contiguous in V
+      double *dst = P.V + sbase * MSIZE;
+      for (int i = threadIdx.x; i < nval; i += 128) {
+        const int el = i / MSIZE, k = i - el * MSIZE;
+        dst[i] = sm[(size_t)el * MSTRIDE + k];
       }
     }
     block_bar();
   }
 }
 
+template <bool COMPACT>
 __global__ void __launch_bounds__(128, 2) k_h8_elastic(const H8Params P) {
   extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, t = threadIdx.x >> 5;  // lane = element in block, t = column pair
@@ -293,7 +322,7 @@ __global__ void __launch_bounds__(128, 2) k_h8_elastic(const H8Params P) {
     }
   }
   __syncthreads();
-  elastic_phase_b(sm, lane, t, slot0, P);
+  elastic_phase_b<COMPACT>(sm, lane, t, slot0, P);
 }
 
 }  // namespace
@@ -313,16 +342,23 @@ int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool 
   H8Params P{mesh->d_conn, mesh->d_xyz, mesh->nnodes, mesh->d_elem_list, mesh->nactive, d_V};
   if (diff) {
     unsigned grid = grid_for(mesh->nactive, 128);
-    if (fa.form == FORM_DIFF_GEN) k_h8_diffusion<true><<<grid, 128, 0, ctx->stream>>>(P);
-    else k_h8_diffusion<false><<<grid, 128, 0, ctx->stream>>>(P);
+    if (fa.form == FORM_DIFF_GEN) {
+      if (fa.compact) k_h8_diffusion<true, true><<<grid, 128, 0, ctx->stream>>>(P);
+      else k_h8_diffusion<true, false><<<grid, 128, 0, ctx->stream>>>(P);
+    } else {
+      if (fa.compact) k_h8_diffusion<false, true><<<grid, 128, 0, ctx->stream>>>(P);
+      else k_h8_diffusion<false, false><<<grid, 128, 0, ctx->stream>>>(P);
+    }
   } else {
     static bool attr_set = false;
     if (!attr_set) {
-      CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic, cudaFuncAttributeMaxDynamicSharedMemorySize, EL_SMEM_BYTES));
+      CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EL_SMEM_COMPACT));
+      CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EL_SMEM_FULL));
       attr_set = true;
     }
     unsigned grid = grid_for(mesh->nactive, EL_EPB);
-    k_h8_elastic<<<grid, 128, EL_SMEM_BYTES, ctx->stream>>>(P);
+    if (fa.compact) k_h8_elastic<true><<<grid, 128, EL_SMEM_COMPACT, ctx->stream>>>(P);
+    else k_h8_elastic<false><<<grid, 128, EL_SMEM_FULL, ctx->stream>>>(P);
   }
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());

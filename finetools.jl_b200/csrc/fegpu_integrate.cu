@@ -24,7 +24,8 @@ struct IntegParams {
   const double *tab;         // N [npts][NNE], then dN [npts][MDIM][NNE]
   const double *w;           // [npts]
   int npts;
-  double *V;                 // [nactive][EM*EM]
+  double *V;                 // [nactive][EM*EM], or [nactive][fe_compact_size] when compact
+  int compact;
   double coef[36];
   int m;
   double otherdim;
@@ -249,7 +250,20 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
       }
     }
     // emission: V[slot][c*EM + r]; the mirrored entry is complete_lt!
-    if (live) {
+    if (live && SYM && P.compact) {
+      // compact upper-block layout (fegpu_internal.h): block (a <= b) at NDN^2 * (b(b+1)/2 + a), column-major inside
+      double *Ve = P.V + slot * (int64_t)(NNE * (NNE + 1) / 2 * NDN * NDN);
+#pragma unroll
+      for (int k = 0; k < EPT; k++) {
+        if (t + k * TPE < NENT) {
+          const int r = er[k], c = ec[k];
+          const int a = r / NDN, i = r % NDN, b = c / NDN, j = c % NDN;
+          double *Vb = Ve + NDN * NDN * (b * (b + 1) / 2 + a);
+          Vb[j * NDN + i] = acc[k];
+          if (a == b && i != j) Vb[i * NDN + j] = acc[k];
+        }
+      }
+    } else if (live) {
       double *Ve = P.V + slot * (int64_t)(EM * EM);
 #pragma unroll
       for (int k = 0; k < EPT; k++) {
@@ -272,6 +286,7 @@ int32_t launch_generic(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
   IntegParams P;
   P.conn = mesh->d_conn; P.xyz = mesh->d_xyz; P.nnodes = mesh->nnodes; P.elem_list = mesh->d_elem_list;
   P.nactive = mesh->nactive; P.tab = mesh->d_tab; P.w = mesh->d_w; P.npts = mesh->npts; P.V = d_V;
+  P.compact = (fa.compact && FORM != FORM_DOT) ? 1 : 0;
   for (int i = 0; i < 36; i++) P.coef[i] = fa.coef[i];
   P.m = fa.m; P.otherdim = fa.otherdim;
   if (mesh->nactive == 0) return FEGPU_OK;

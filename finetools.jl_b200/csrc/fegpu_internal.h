@@ -62,6 +62,7 @@ struct fegpu_asm {
   size_t V_cap = 0;  // doubles
   int64_t V_n = 0;
   int last_EM = 0;
+  bool V_compact = false;  // d_V holds the compact symmetric layout (fe_compact_size per element)
   // result
   int64_t nrows = 0, ncols = 0, nnz = 0;
   const int64_t *d_colptr = nullptr;  // borrowed from a Pattern or == own_colptr
@@ -115,7 +116,13 @@ struct FormArgs {
   double coef[36];  // kappa (mdim x mdim col-major) | C (6x6 col-major) | c (ndn x ndn col-major); coef[0] = scalar kappa
   int m;            // bilform_dot manifold dimension
   double otherdim;
+  bool compact;     // symmetric forms only: write the compact upper-block layout (fe_compact_size) instead of full matrices
 };
+// Compact layout of a symmetric element matrix (nne nodes x ndn dofs): the upper block triangle, block (a <= b) of
+// ndn x ndn values (column-major: row comp i, col comp j at j*ndn + i) at ndn*ndn*(b(b+1)/2 + a); diagonal blocks are stored
+// in full (mirrored).  This is what the symmetric forms write on the mesh-structured path: (1 + 1/nne)/2 of the bytes.
+static inline int fe_compact_size(int nne, int ndn) { return nne * (nne + 1) / 2 * ndn * ndn; }
+static inline bool fe_form_symmetric(int form) { return form != 3 /* FORM_DOT */; }
 int32_t fe_integrate(fegpu_mesh *mesh, const FormArgs &fa, double *d_V);
 
 // ---- pattern + gather (fegpu_pattern.cu) ---------------------------------------------------------------
@@ -125,7 +132,9 @@ int64_t fe_pattern_nnz(const Pattern *p);
 const int64_t *fe_pattern_colptr(const Pattern *p);
 const int64_t *fe_pattern_rowval(const Pattern *p);
 bool fe_pattern_usable(const fegpu_dofmap *dm);  // mesh-structured fast path applicable?
-int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, double *d_nzval);
+int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_nzval);
+// compact symmetric layout -> full element matrices in emission order (raw-COO export only)
+int32_t fe_expand_compact(fegpu_ctx *ctx, const double *d_Vc, double *d_Vfull, int64_t nelem, int nne, int ndn);
 
 // ---- generic COO -> CSC by sort (fegpu_sort.cu) --------------------------------------------------------
 // d_I, d_J 1-based int64, n triplets in emission order.  Fills the assembler's own colptr/rowval/nzval.

@@ -16,6 +16,8 @@
 //
 // The pattern equals sparse()'s: one entry per (row dof, col dof) pair sharing an element, explicit zeros kept, rows
 // strictly increasing in a column, 1-based int64 colptr/rowval.
+#include <cstdlib>
+
 #include "fegpu_internal.h"
 
 struct Pattern {
@@ -37,6 +39,7 @@ namespace {
 
 constexpr int WPB = 4;  // warps per block in the per-node symbolic kernels
 constexpr int GWPB = 8; // warps per block in the gather
+// GBATCH (template): adjacent elements whose loads are in flight together (k_gather, one-value-per-lane path)
 
 struct SymParams {
   const int32_t *conn;
@@ -160,6 +163,8 @@ __device__ __forceinline__ void sort_via_regs(uint32_t *work, int lane) {
 }
 
 // One warp per node.  Shared per warp (uint32 words): el[maxdeg] | cand[capc] | work[capc] | uq[capc]
+// NNE_T: nodes per element as a compile-time constant (0 = runtime) so the candidate decode needs no integer division.
+template <int NNE_T>
 __global__ void __launch_bounds__(WPB * 32) k_nbr(SymParams S, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ adj_slot,
                                                   int maxdeg, int capc, int32_t *__restrict__ nnbr_out, int32_t *__restrict__ U,
                                                   uint16_t *__restrict__ cslot, uint8_t *__restrict__ sorted_flag, int *any_unsorted) {
@@ -170,7 +175,7 @@ __global__ void __launch_bounds__(WPB * 32) k_nbr(SymParams S, const int64_t *__
   uint32_t *cand = el + maxdeg;
   uint32_t *work = cand + capc;
   uint32_t *uq = work + capc;
-  const int nne = S.nne, ndn = S.ndn;
+  const int nne = (NNE_T > 0) ? NNE_T : S.nne, ndn = S.ndn;
   for (int64_t n = (int64_t)blockIdx.x * WPB + w; n < S.nnodes; n += (int64_t)gridDim.x * WPB) {
     const int64_t ab = adjptr[n];
     const int deg = (int)(adjptr[n + 1] - ab);
@@ -238,12 +243,17 @@ __global__ void __launch_bounds__(WPB * 32) k_nbr(SymParams S, const int64_t *__
     // unique neighbour list to global; is the node-major dof order already ascending?
     int32_t *Un = U + ab * nne;
     for (int s = lane; s < nu; s += 32) Un[s] = (int32_t)uq[s];
+    // node-major dof order ascending?  per neighbour: its own dofs ascending and its last dof below the next neighbour's first
     bool ok = true;
-    const int nr = nu * ndn;
-    for (int i = lane; i + 1 < nr; i += 32) {
-      int s0 = i / ndn, p0 = i - s0 * ndn, s1 = (i + 1) / ndn, p1 = (i + 1) - s1 * ndn;
-      int d0 = S.dof[(int64_t)p0 * S.nnodes + uq[s0]], d1 = S.dof[(int64_t)p1 * S.nnodes + uq[s1]];
-      if (d0 >= d1) ok = false;
+    for (int s = lane; s < nu; s += 32) {
+      const int64_t u = uq[s];
+      int prev = S.dof[u];
+      for (int p = 1; p < ndn; p++) {
+        const int d = S.dof[(int64_t)p * S.nnodes + u];
+        if (d <= prev) ok = false;
+        prev = d;
+      }
+      if (s + 1 < nu && S.dof[uq[s + 1]] <= prev) ok = false;
     }
     ok = __all_sync(0xffffffffu, ok);
     if (lane == 0) {
@@ -263,6 +273,53 @@ __global__ void k_col_counts(SymParams S, const int32_t *nnbr, int64_t *colcount
   if (nnbr[n] > 0) colcount[S.dof[(int64_t)q * S.nnodes + n]] = (int64_t)nnbr[n] * S.ndn;
 }
 
+// rowval for the nodes whose node-major dof order is already ascending (the common case: every node unless the numbering
+// puts fixed dofs last).  LPN lanes per node so a warp keeps 32/LPN dependent-load chains (node -> neighbour -> dof) in
+// flight; NDN compile-time (0 = runtime) so the (slot, component) decode needs no division.
+template <int LPN, int NDN>
+__global__ void __launch_bounds__(256) k_rows_sorted(SymParams S, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ nnbr,
+                                                     const int64_t *__restrict__ nbrptr, const int32_t *__restrict__ U,
+                                                     const uint8_t *__restrict__ sorted_flag, const int64_t *__restrict__ colptr,
+                                                     int64_t *__restrict__ rowval, uint16_t *__restrict__ rank) {
+  constexpr int QMAX = (NDN > 0) ? NDN : 6;
+  constexpr int UNR = 4;  // row chunks whose neighbour -> dof loads are issued together
+  const int ndn = (NDN > 0) ? NDN : S.ndn;
+  const int gl = threadIdx.x % LPN;
+  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPN;
+  if (n >= S.nnodes) return;
+  const int nu = nnbr[n];
+  const uint8_t sf = sorted_flag[n];
+  const int64_t ab = adjptr[n];
+  int64_t cbase[QMAX];
+#pragma unroll
+  for (int q = 0; q < QMAX; q++) cbase[q] = (q < ndn) ? colptr[S.dof[(int64_t)q * S.nnodes + n]] - 1 : 0;
+  if (nu == 0 || !sf) return;
+  const int32_t *Un = U + ab * S.nne;
+  const int nr = nu * ndn;
+  const int64_t nb = rank ? nbrptr[n] : 0;
+  for (int i0 = 0; i0 < nr; i0 += UNR * LPN) {
+    int64_t rdof[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      const int i = i0 + u * LPN + gl;
+      if (i < nr) {
+        const int s = i / ndn, p = i - s * ndn;
+        rdof[u] = (int64_t)S.dof[(int64_t)p * S.nnodes + Un[s]] + 1;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      const int i = i0 + u * LPN + gl;
+      if (i < nr) {
+#pragma unroll
+        for (int q = 0; q < QMAX; q++)
+          if (q < ndn) rowval[cbase[q] + i] = rdof[u];
+        if (rank) rank[nb * ndn + i] = (uint16_t)i;
+      }
+    }
+  }
+}
+
 // rowval (+ rank).  One warp per node; shared per warp: cap2 uint64 keys, used only by nodes whose dof order needs a sort.
 __global__ void __launch_bounds__(WPB * 32) k_rows(SymParams S, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ nnbr,
                                                    const int64_t *__restrict__ nbrptr, const int32_t *__restrict__ U,
@@ -274,19 +331,14 @@ __global__ void __launch_bounds__(WPB * 32) k_rows(SymParams S, const int64_t *_
   const int ndn = S.ndn;
   for (int64_t n = (int64_t)blockIdx.x * WPB + w; n < S.nnodes; n += (int64_t)gridDim.x * WPB) {
     const int nu = nnbr[n];
-    if (nu == 0) continue;
+    if (nu == 0 || sorted_flag[n]) continue;
     const int32_t *Un = U + adjptr[n] * S.nne;
     const int64_t nb = nbrptr[n];
     const int nr = nu * ndn;
     int64_t cbase[6];
     for (int q = 0; q < ndn; q++) cbase[q] = colptr[S.dof[(int64_t)q * S.nnodes + n]] - 1;
     if (sorted_flag[n]) {
-      for (int i = lane; i < nr; i += 32) {
-        int s = i / ndn, p = i - s * ndn;
-        int64_t rdof = (int64_t)S.dof[(int64_t)p * S.nnodes + Un[s]] + 1;
-        for (int q = 0; q < ndn; q++) rowval[cbase[q] + i] = rdof;
-        if (rank) rank[nb * ndn + i] = (uint16_t)i;
-      }
+      continue;  // written by k_rows_sorted
     } else {
       const int q2 = next_pow2(nr);
       for (int i = lane; i < q2; i += 32) {
@@ -328,19 +380,34 @@ struct GatherParams {
   int maxnbr, maxdeg, maxcand;
 };
 
-// LPN lanes per node (32/LPN nodes per warp), NDN dofs per node (0 = runtime).
+// Offset (inside one element's values) of entry (row node li, row comp p; column node lc, column comp q).
+// Full layout: emission order, column (lc, q) then row (li, p).  Compact layout (symmetric forms, fegpu_internal.h): the
+// upper block (min, max), read transposed when the row node comes after the column node.
+template <bool COMPACT>
+__device__ __forceinline__ int elem_offset(int li, int p, int lc, int q, int ndn, int EM) {
+  if (!COMPACT) return (lc * ndn + q) * EM + li * ndn + p;
+  const int nd2 = ndn * ndn;
+  return (li <= lc) ? nd2 * (lc * (lc + 1) / 2 + li) + q * ndn + p : nd2 * (li * (li + 1) / 2 + lc) + p * ndn + q;
+}
+
+// Numeric CSC phase.  LPN lanes per column node (32/LPN nodes per warp), NDN dofs per node (0 = runtime), RPL element-
+// matrix rows per lane (>= ceil(EM/LPN); 0 = runtime loop), GBATCH adjacent elements whose loads are in flight together.
+// The kernel is bound by dependent-load latency (node -> adjacency -> element values -> column pointer), so the design
+// goal is many nodes in flight per SM (small LPN), all loads of a batch issued back to back, and the scalars of the
+// next node / the column bases fetched early.
 // Shared per node group: acc[maxnbr*ndn*ndn] doubles | base[maxdeg] int64 | cs[maxcand] uint16 (padded to 8 B)
-template <int LPN, int NDN>
+template <int LPN, int NDN, bool COMPACT, int GBATCH, int RPL>
 __global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
   extern __shared__ double sacc[];
   constexpr int NPW = 32 / LPN;
   constexpr int QMAX = (NDN > 0) ? NDN : 6;
+  constexpr int RMAX = (RPL > 0) ? RPL : 1;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int g = lane / LPN, gl = lane % LPN;
   const int ndn = (NDN > 0) ? NDN : G.ndn;
   const int nne = G.nne;
   const int EM = nne * ndn;
-  const int64_t EM2 = (int64_t)EM * EM;
+  const int64_t EM2 = COMPACT ? (int64_t)(nne * (nne + 1) / 2) * ndn * ndn : (int64_t)EM * EM;  // values per element
   const int acc_stride = G.maxnbr * ndn * ndn;
   const int cs_words = (G.maxcand + 3) / 4;
   const int grp_words = acc_stride + G.maxdeg + cs_words;
@@ -349,60 +416,95 @@ __global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
   uint16_t *cs = reinterpret_cast<uint16_t *>(base + G.maxdeg);
   const int64_t groups_total = (int64_t)gridDim.x * GWPB * NPW;
   const int64_t niter = (G.nnodes + groups_total - 1) / groups_total;
+  // rows of the element matrix this lane adds: r = gl + j*LPN
+  int rli[RMAX], rp[RMAX];
+  bool rok[RMAX];
+#pragma unroll
+  for (int j = 0; j < RMAX; j++) {
+    const int r = gl + j * LPN;
+    rok[j] = r < EM;
+    rli[j] = rok[j] ? r / ndn : 0;
+    rp[j] = rok[j] ? r - rli[j] * ndn : 0;
+  }
+  // scalars of the first node
+  int64_t n = (int64_t)blockIdx.x * (GWPB * NPW) + w * NPW + g;
+  int nn_pre = (n < G.nnodes) ? G.nnbr[n] : 0;
+  int64_t ab_pre = (n < G.nnodes) ? G.adjptr[n] : 0, ae_pre = (n < G.nnodes) ? G.adjptr[n + 1] : 0;
   for (int64_t it = 0; it < niter; it++) {
-    const int64_t n = (it * gridDim.x + blockIdx.x) * (GWPB * NPW) + w * NPW + g;
     const bool live = n < G.nnodes;
-    const int nn = live ? G.nnbr[n] : 0;
-    const int64_t ab = live ? G.adjptr[n] : 0;
-    const int deg = (live && nn > 0) ? (int)(G.adjptr[n + 1] - ab) : 0;
+    const int nn = nn_pre;
+    const int64_t ab = ab_pre;
+    const int deg = (live && nn > 0) ? (int)(ae_pre - ab) : 0;
     const int per_col = nn * ndn;
     const int total = per_col * ndn;
     // stage the node's metadata (one round trip to memory), clear the accumulators
-    for (int a = gl; a < deg; a += LPN) base[a] = (long long)G.adj_slot[ab + a] * EM2 + (long long)(G.adj_lc[ab + a] * ndn) * EM;
+    // element base (in values) with the column node's local index packed into the low 6 bits
+    for (int a = gl; a < deg; a += LPN) base[a] = (((long long)G.adj_slot[ab + a] * EM2) << 6) | (long long)G.adj_lc[ab + a];
     {
       const uint16_t *csg = G.cslot + ab * nne;
       for (int k = gl; k < deg * nne; k += LPN) cs[k] = csg[k];
+    }
+    // issued early, consumed late: column bases of this node, scalars of the next node
+    long long cb[QMAX];
+#pragma unroll
+    for (int q = 0; q < QMAX; q++) cb[q] = (q < ndn && deg > 0) ? G.colptr[G.dof[(int64_t)q * G.nnodes + n]] - 1 : 0;
+    const int64_t n_next = n + groups_total;
+    if (it + 1 < niter && n_next < G.nnodes) {
+      nn_pre = G.nnbr[n_next];
+      ab_pre = G.adjptr[n_next];
+      ae_pre = G.adjptr[n_next + 1];
+    } else {
+      nn_pre = 0; ab_pre = 0; ae_pre = 0;
     }
     for (int i = gl; i < total; i += LPN) acc[i] = 0.0;
     int maxdeg = deg;
 #pragma unroll
     for (int d = LPN; d < 32; d <<= 1) maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, d));
     __syncwarp();
-    if (EM <= LPN) {
-      // one value per lane and column: software-pipelined over the adjacent elements
-      const bool act = gl < EM;
-      const int li = gl / ndn, p = gl - li * ndn;
-      double cur[QMAX], nxt[QMAX];
-      if (act && deg > 0) {
-        const double *Vb = G.V + base[0] + gl;
+    if (RPL > 0) {
+      for (int a0 = 0; a0 < maxdeg; a0 += GBATCH) {
+        double v[GBATCH][RMAX][QMAX];
 #pragma unroll
-        for (int q = 0; q < QMAX; q++)
-          if (q < ndn) cur[q] = Vb[q * EM];
-      }
-      for (int a = 0; a < maxdeg; a++) {
-        if (act && a + 1 < deg) {
-          const double *Vb = G.V + base[a + 1] + gl;
+        for (int u = 0; u < GBATCH; u++) {
+          if (a0 + u < deg) {
+            const long long bu = base[a0 + u];
+            const double *Vb = G.V + (bu >> 6);
+            const int lc = (int)(bu & 63);
 #pragma unroll
-          for (int q = 0; q < QMAX; q++)
-            if (q < ndn) nxt[q] = Vb[q * EM];
-        }
-        if (act && a < deg) {
-          const unsigned s = cs[a * nne + li];
-          if (s != 0xffffu) {
-            double *dst = acc + s * ndn + p;
+            for (int j = 0; j < RMAX; j++)
+              if (rok[j]) {
 #pragma unroll
-            for (int q = 0; q < QMAX; q++)
-              if (q < ndn) dst[q * per_col] += cur[q];
+                for (int q = 0; q < QMAX; q++)
+                  if (q < ndn) v[u][j][q] = Vb[elem_offset<COMPACT>(rli[j], rp[j], lc, q, ndn, EM)];
+              }
           }
         }
 #pragma unroll
-        for (int q = 0; q < QMAX; q++) cur[q] = nxt[q];
-        __syncwarp();
+        for (int u = 0; u < GBATCH; u++) {
+          if (a0 + u < maxdeg) {  // warp-uniform
+            if (a0 + u < deg) {
+#pragma unroll
+              for (int j = 0; j < RMAX; j++)
+                if (rok[j]) {
+                  const unsigned s = cs[(a0 + u) * nne + rli[j]];
+                  if (s != 0xffffu) {
+                    double *dst = acc + s * ndn + rp[j];
+#pragma unroll
+                    for (int q = 0; q < QMAX; q++)
+                      if (q < ndn) dst[q * per_col] += v[u][j][q];
+                  }
+                }
+            }
+            __syncwarp();  // the next element may add into the same accumulator from another lane
+          }
+        }
       }
     } else {
       for (int a = 0; a < maxdeg; a++) {
         if (a < deg) {
-          const double *Vb = G.V + base[a];
+          const long long ba = base[a];
+          const double *Vb = G.V + (ba >> 6);
+          const int lc = (int)(ba & 63);
           for (int r = gl; r < EM; r += LPN) {
             const int li = r / ndn, p = r - li * ndn;
             const unsigned s = cs[a * nne + li];
@@ -410,7 +512,7 @@ __global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
               double *dst = acc + s * ndn + p;
 #pragma unroll
               for (int q = 0; q < QMAX; q++)
-                if (q < ndn) dst[q * per_col] += Vb[q * EM + r];
+                if (q < ndn) dst[q * per_col] += Vb[elem_offset<COMPACT>(li, p, lc, q, ndn, EM)];
             }
           }
         }
@@ -419,15 +521,18 @@ __global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
     }
     if (live && nn > 0) {
       const int64_t nb = G.rank ? G.nbrptr[n] : 0;
-      for (int q = 0; q < ndn; q++) {
-        const int64_t cbase = G.colptr[G.dof[(int64_t)q * G.nnodes + n]] - 1;
-        for (int rem = gl; rem < per_col; rem += LPN) {
-          const int pos = G.rank ? G.rank[nb * ndn + rem] : rem;
-          G.nzval[cbase + pos] = acc[q * per_col + rem];
+#pragma unroll
+      for (int q = 0; q < QMAX; q++) {
+        if (q < ndn) {
+          for (int rem = gl; rem < per_col; rem += LPN) {
+            const int pos = G.rank ? G.rank[nb * ndn + rem] : rem;
+            G.nzval[cb[q] + pos] = acc[q * per_col + rem];
+          }
         }
       }
     }
     __syncwarp();
+    n = n_next;
   }
 }
 
@@ -527,10 +632,23 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
   PT(dalloc(ctx, &d_U, (size_t)nadj * nne));
   PT(dalloc(ctx, &d_sorted, nn));
   PT(dalloc(ctx, &P->d_cslot, (size_t)nadj * nne));
-  PC(cudaFuncSetAttribute(k_nbr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   unsigned gridn = (unsigned)std::min<int64_t>((nn + WPB - 1) / WPB, (int64_t)ctx->sm_count * 64);
   if (gridn == 0) gridn = 1;
-  k_nbr<<<gridn, WPB * 32, smem1, st>>>(S, P->d_adjptr, P->d_adj_slot, maxdeg, capc, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1);
+#define LAUNCH_NBR(N)                                                                                                  \
+  do {                                                                                                                 \
+    PC(cudaFuncSetAttribute(k_nbr<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));                      \
+    k_nbr<N><<<gridn, WPB * 32, smem1, st>>>(S, P->d_adjptr, P->d_adj_slot, maxdeg, capc, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1); \
+  } while (0)
+  switch (nne) {
+    case 3: LAUNCH_NBR(3); break;
+    case 4: LAUNCH_NBR(4); break;
+    case 8: LAUNCH_NBR(8); break;
+    case 10: LAUNCH_NBR(10); break;
+    case 20: LAUNCH_NBR(20); break;
+    case 27: LAUNCH_NBR(27); break;
+    default: LAUNCH_NBR(0); break;
+  }
+#undef LAUNCH_NBR
   ctx->launches++;
   PT(dalloc(ctx, &P->d_nbrptr, nn + 1));
   int64_t total_nbr = 0;
@@ -562,8 +680,21 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
   const size_t smem2 = need_rank ? (size_t)WPB * cap2 * sizeof(unsigned long long) : 0;
   if (smem2 > 200 * 1024) return bail();
   if (smem2 > 48 * 1024) PC(cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-  k_rows<<<gridn, WPB * 32, smem2, st>>>(S, P->d_adjptr, P->d_nnbr, P->d_nbrptr, d_U, d_sorted, P->d_colptr, cap2, P->d_rowval, P->d_rank);
-  ctx->launches++;
+  {
+    constexpr int RL = 32;  // lanes per node (8 measured slower: 64-byte store segments)
+    const unsigned gr = grid_for(nn * RL, 256);
+    switch (ndn) {
+      case 1: k_rows_sorted<RL, 1><<<gr, 256, 0, st>>>(S, P->d_adjptr, P->d_nnbr, P->d_nbrptr, d_U, d_sorted, P->d_colptr, P->d_rowval, P->d_rank); break;
+      case 2: k_rows_sorted<RL, 2><<<gr, 256, 0, st>>>(S, P->d_adjptr, P->d_nnbr, P->d_nbrptr, d_U, d_sorted, P->d_colptr, P->d_rowval, P->d_rank); break;
+      case 3: k_rows_sorted<RL, 3><<<gr, 256, 0, st>>>(S, P->d_adjptr, P->d_nnbr, P->d_nbrptr, d_U, d_sorted, P->d_colptr, P->d_rowval, P->d_rank); break;
+      default: k_rows_sorted<RL, 0><<<gr, 256, 0, st>>>(S, P->d_adjptr, P->d_nnbr, P->d_nbrptr, d_U, d_sorted, P->d_colptr, P->d_rowval, P->d_rank); break;
+    }
+    ctx->launches++;
+  }
+  if (need_rank) {  // only the nodes whose dof order needs a sort
+    k_rows<<<gridn, WPB * 32, smem2, st>>>(S, P->d_adjptr, P->d_nnbr, P->d_nbrptr, d_U, d_sorted, P->d_colptr, cap2, P->d_rowval, P->d_rank);
+    ctx->launches++;
+  }
   PC(cudaGetLastError());
   cleanup();
 #undef PT
@@ -572,7 +703,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
   return FEGPU_OK;
 }
 
-int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, double *d_nzval) {
+int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_nzval) {
   fegpu_ctx *ctx = dm->ctx;
   Pattern *P = dm->pat;
   fegpu_mesh *mesh = dm->mesh;
@@ -581,32 +712,57 @@ int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, double *d_nzval) {
   GatherParams G{mesh->nnodes, mesh->nne, dm->ndn, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, P->d_nnbr, P->d_nbrptr, P->d_cslot,
                  P->d_rank, dm->d_dof, P->d_colptr, d_V, d_nzval, P->maxnbr, P->maxdeg, P->maxcand};
   const int EM = mesh->nne * dm->ndn;
-  const int lpn = (EM <= 8) ? 8 : (EM <= 16 ? 16 : 32);
+  // tuning knobs (measured defaults below): FEGPU_GATHER_LPN lanes per node, FEGPU_GATHER_BATCH elements in flight
+  static const int batch_env = std::getenv("FEGPU_GATHER_BATCH") ? std::atoi(std::getenv("FEGPU_GATHER_BATCH")) : 0;
+  static const int lpn_env = std::getenv("FEGPU_GATHER_LPN") ? std::atoi(std::getenv("FEGPU_GATHER_LPN")) : 0;
+  // measured on config 2 (profiles/r01_gather_knobs.txt): two rows per lane with one element in flight beats one row per lane
+  // for the compact layout; one row per lane keeps four elements in flight
+  int lpn = (EM <= 16) ? 8 : (EM <= 32 ? 16 : 32);
+  if (lpn_env == 8 || lpn_env == 16 || lpn_env == 32) lpn = lpn_env;
+  if (dm->ndn > 3) lpn = 32;  // runtime-ndn instantiation exists for 32 lanes only
+  int rpl = (EM + lpn - 1) / lpn;
+  if (rpl > 4) rpl = 0;  // runtime row loop
+  const int batch = (rpl == 1) ? ((batch_env == 1 || batch_env == 2) ? 1 : 4) : 1;
   const int npw = 32 / lpn;
   const size_t smem = (size_t)GWPB * npw * ((size_t)P->maxnbr * dm->ndn * dm->ndn + P->maxdeg + (P->maxcand + 3) / 4) * sizeof(double);
   if (smem > 200 * 1024) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: gather accumulators exceed shared memory");
   const int64_t per_block = (int64_t)GWPB * npw;
   unsigned grid = (unsigned)std::min<int64_t>((mesh->nnodes + per_block - 1) / per_block, (int64_t)ctx->sm_count * 32);
   if (grid == 0) grid = 1;
-#define LAUNCH_GATHER(L, N)                                                                                          \
-  do {                                                                                                               \
-    if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_gather<L, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_gather<L, N><<<grid, GWPB * 32, smem, ctx->stream>>>(G);                                                       \
+#define LG5(L, N, C, B, R)                                                                                                          \
+  do {                                                                                                                              \
+    if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_gather<L, N, C, B, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_gather<L, N, C, B, R><<<grid, GWPB * 32, smem, ctx->stream>>>(G);                                                             \
   } while (0)
-#define LAUNCH_GATHER_L(N)                         \
-  do {                                             \
-    if (lpn == 8) LAUNCH_GATHER(8, N);             \
-    else if (lpn == 16) LAUNCH_GATHER(16, N);      \
-    else LAUNCH_GATHER(32, N);                     \
+#define LG_R(L, N, C)                                                            \
+  do {                                                                           \
+    if (rpl == 1) { if (batch == 4) LG5(L, N, C, 4, 1); else LG5(L, N, C, 1, 1); } \
+    else if (rpl == 2) LG5(L, N, C, 1, 2);                                       \
+    else if (rpl == 3) LG5(L, N, C, 1, 3);                                       \
+    else if (rpl == 4) LG5(L, N, C, 1, 4);                                       \
+    else LG5(L, N, C, 1, 0);                                                     \
+  } while (0)
+#define LG_C(L, N)                     \
+  do {                                 \
+    if (compact) LG_R(L, N, true);     \
+    else LG_R(L, N, false);            \
+  } while (0)
+#define LG_L(N)                        \
+  do {                                 \
+    if (lpn == 8) LG_C(8, N);          \
+    else if (lpn == 16) LG_C(16, N);   \
+    else LG_C(32, N);                  \
   } while (0)
   switch (dm->ndn) {
-    case 1: LAUNCH_GATHER_L(1); break;
-    case 2: LAUNCH_GATHER_L(2); break;
-    case 3: LAUNCH_GATHER_L(3); break;
-    default: LAUNCH_GATHER_L(0); break;
+    case 1: LG_L(1); break;
+    case 2: LG_L(2); break;
+    case 3: LG_L(3); break;
+    default: LG_C(32, 0); break;
   }
-#undef LAUNCH_GATHER
-#undef LAUNCH_GATHER_L
+#undef LG5
+#undef LG_R
+#undef LG_C
+#undef LG_L
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return FEGPU_OK;

@@ -8,6 +8,7 @@ C=np.zeros((6,6)); C[:3,:3]=lam; C[np.arange(3),np.arange(3)]+=2*mu; C[3:,3:]=mu
 a = fe.SysmatAssemblerSparseGPU(0.0)
 femm = fe.FEMMBase(fe.IntegDomain(fes, fe.GaussRule(3,2)))
 geom = fe.NodalField(fens.xyz)
+a.setnomatrixresult(True)  # keep the CSC on the device: kernels only
 for i in range(2):
     a.invalidate_patterns()
     fe.bilform_lin_elastic(femm, a, geom, u, fe.DeforModelRed3D, fe.DataCache(C), raw=True)
