@@ -32,6 +32,7 @@ SIGNATURES = {
     "fegpu_dofmap_destroy": (C.c_int32, [VP]),
     "fegpu_asm_create": (C.c_int32, [VP, C.POINTER(VP)]),
     "fegpu_asm_destroy": (C.c_int32, [VP]),
+    "fegpu_asm_set_symmetric": (C.c_int32, [VP, C.c_int32]),
     "fegpu_bilform_diffusion": (C.c_int32, [VP, VP, C.c_int32, VP, VP]),
     "fegpu_bilform_lin_elastic": (C.c_int32, [VP, VP, VP, VP]),
     "fegpu_bilform_dot": (C.c_int32, [VP, VP, VP, C.c_int32, C.c_double, VP]),
@@ -41,6 +42,7 @@ SIGNATURES = {
     "fegpu_makematrix": (C.c_int32, [VP]),
     "fegpu_makematrix_sizes": (C.c_int32, [VP, c_i64p, c_i64p, c_i64p]),
     "fegpu_makematrix_copy": (C.c_int32, [VP, VP, VP, VP]),
+    "fegpu_makematrix_view": (C.c_int32, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32]),
     "fegpu_transfer_stats": (C.c_int32, [VP, c_i64p, c_i64p]),
     "fegpu_makematrix_copy_values": (C.c_int32, [VP, VP]),
     "fegpu_makematrix_device": (C.c_int32, [VP, C.POINTER(VP), C.POINTER(VP), C.POINTER(VP)]),

@@ -97,22 +97,39 @@ class SysmatAssemblerSparseGPU(AbstractSysmatAssembler):
         check(_lib.lib().fegpu_assemble(self.handle, fptr(m), fptr(dr), dr.size, fptr(dc), dc.size), self.ctx.handle)
         return self
 
-    def makematrix(self, raw=False, out=None):
-        """Returns scipy.sparse.csc_matrix (raw=False) or the 1-based (colptr, rowval, nzval, m, n) arrays exactly as they
-        would be handed to Julia's SparseMatrixCSC(m, n, colptr, rowval, nzval) (raw=True).  `out` = preallocated
-        (colptr, rowval, nzval) host arrays to fill (e.g. pinned), like a shim that reuses its result buffers."""
+    def _build(self):
+        """Device side of makematrix!: after this the CSC (or its current view) is resident on the GPU.  Returns False when
+        `nomatrixresult` asks for the dummy zero matrix instead (AssemblyModule.jl:309-317)."""
         L = _lib.lib()
         if self._mode == "generic":
             if self._nomatrixresult:
-                # the reference returns spzeros and keeps the triplets (AssemblyModule.jl:309-317); same here
-                return self._zeros(raw)
+                return False
             check(L.fegpu_makematrix(self.handle), self.ctx.handle)
             self._mode = "done"
         elif self._mode is None:
             raise _lib.FEGPUError(-17, "makematrix! before any assembly")
         elif self._nomatrixresult:
+            return False
+        return True
+
+    def makematrix(self, raw=False, out=None):
+        """Returns scipy.sparse.csc_matrix (raw=False) or the 1-based (colptr, rowval, nzval, m, n) arrays exactly as they
+        would be handed to Julia's SparseMatrixCSC(m, n, colptr, rowval, nzval) (raw=True).  `out` = preallocated
+        (colptr, rowval, nzval) host arrays to fill (e.g. pinned), like a shim that reuses its result buffers."""
+        if not self._build():
             return self._zeros(raw)
         return self._fetch(raw, out)
+
+    def view(self, row_first, row_last, col_first, col_last, drop_exact_zeros=False):
+        """Restrict the device-resident result to A[row_first:row_last, col_first:col_last] (1-based, inclusive) and/or drop
+        exact zeros; sizes()/_fetch() then refer to the view.  view_reset() restores the full matrix."""
+        check(_lib.lib().fegpu_makematrix_view(self.handle, int(row_first), int(row_last), int(col_first), int(col_last),
+                                               1 if drop_exact_zeros else 0), self.ctx.handle)
+        return self
+
+    def view_reset(self):
+        check(_lib.lib().fegpu_makematrix_view(self.handle, 1, self._row_nalldofs, 1, self._col_nalldofs, 0), self.ctx.handle)
+        return self
 
     # ---- helpers ------------------------------------------------------------------------------------------
     def setnomatrixresult(self, flag):
@@ -161,7 +178,7 @@ class SysmatAssemblerSparseGPU(AbstractSysmatAssembler):
         """Raw triplets (I, J, V) of the last bilform assembly, reference emission order (the `nomatrixresult` flow)."""
         if self._pending_form is None:
             raise _lib.FEGPUError(-17, "no bilform assembly to export")
-        mesh, dm, ntrip = self._pending_form
+        mesh, dm, ntrip = self._pending_form[:3]
         I, J, V = np.empty(ntrip, np.int64), np.empty(ntrip, np.int64), np.empty(ntrip, np.float64)
         check(_lib.lib().fegpu_coo_copy(self.handle, mesh, dm, fptr(I), fptr(J), fptr(V)), self.ctx.handle)
         return I, J, V
@@ -187,6 +204,125 @@ class SysmatAssemblerSparseGPU(AbstractSysmatAssembler):
                 self.handle = VP()
         except Exception:
             pass
+
+
+class SysmatAssemblerSparseSymmGPU(SysmatAssemblerSparseGPU):
+    """Drop-in for SysmatAssemblerSparseSymm (src/AssemblyModule.jl:342-583), the reference's DEFAULT assembler when none is
+    passed (FEMMBaseModule.jl:1374, 1408, 1543, 1822).  assemble! keeps the lower triangle of each element matrix (:517-530);
+    makematrix! returns S + transpose(S) with the doubled diagonal halved (:576-579).  Because SparseArrays' sparse `+` stores
+    only non-zero sums, entries that cancel to exactly 0.0 are absent from the result (unlike SysmatAssemblerSparse)."""
+
+    def __init__(self, z=0.0, nomatrixresult=False, ctx=None, device=0):
+        super().__init__(z, nomatrixresult, ctx, device)
+        check(_lib.lib().fegpu_asm_set_symmetric(self.handle, 1), self.ctx.handle)
+
+    def expectedntriples(self, elem_mat_nrows, elem_mat_ncols, n_elem_mats):
+        return int((elem_mat_nrows * elem_mat_ncols + elem_mat_nrows) / 2 * n_elem_mats)
+
+    def assemble(self, mat, dofnums_row, dofnums_col):
+        mat = np.asarray(mat, dtype=np.float64)
+        nr, nc = np.asarray(dofnums_row).size, np.asarray(dofnums_col).size
+        if nr != nc or mat.shape != (nr, nc):
+            raise _lib.FEGPUError(-15, "Size mismatch")
+        return super().assemble(mat, dofnums_row, dofnums_col)
+
+    def coo(self):
+        """Lower-triangle triplets (local i >= j) in the reference's emission order (AssemblyModule.jl:517-530)."""
+        I, J, V = super().coo()
+        em = int(round(np.sqrt(I.size / max(self._pending_form[3], 1)))) if I.size else 0
+        if em == 0:
+            return I, J, V
+        k = np.arange(em * em)
+        keep = np.tile((k % em) >= (k // em), I.size // (em * em))
+        return I[keep], J[keep], V[keep]
+
+
+class SysmatAssemblerFFBlock(AbstractSysmatAssembler):
+    """Drop-in for SysmatAssemblerFFBlock (src/AssemblyModule.jl:1149-1231): delegates to a wrapped GPU assembler and returns
+    the free-free block A[1:row_nfreedofs, 1:col_nfreedofs] of its matrix, cut out on the device (only the block crosses the
+    PCIe link)."""
+
+    def __init__(self, row_nfreedofs, col_nfreedofs=None, inner=None, ctx=None, device=0):
+        self._a = inner if inner is not None else SysmatAssemblerSparseGPU(0.0, ctx=ctx, device=device)
+        if not isinstance(self._a, SysmatAssemblerSparseGPU):
+            raise TypeError("SysmatAssemblerFFBlock wraps a GPU assembler (there is no CPU path)")
+        self._row_nfreedofs = int(row_nfreedofs)
+        self._col_nfreedofs = int(row_nfreedofs if col_nfreedofs is None else col_nfreedofs)
+
+    ctx = property(lambda self: self._a.ctx)
+
+    def eltype(self):
+        return self._a.eltype()
+
+    def expectedntriples(self, *args):
+        return self._a.expectedntriples(*args)
+
+    def startassembly(self, *args, **kw):
+        self._a.startassembly(*args, **kw)
+        return self
+
+    def assemble(self, mat, dofnums_row, dofnums_col):
+        self._a.assemble(mat, dofnums_row, dofnums_col)
+        return self
+
+    def makematrix(self, raw=False, out=None):
+        a = self._a
+        if not a._build():
+            return matrix_blocked_zeros(self._row_nfreedofs, self._col_nfreedofs, raw)
+        return matrix_blocked_ff(a, self._row_nfreedofs, self._col_nfreedofs, raw=raw, out=out)
+
+
+def matrix_blocked_zeros(m, n, raw):
+    if raw:
+        return np.ones(n + 1, np.int64), np.zeros(0, np.int64), np.zeros(0), m, n
+    import scipy.sparse as sp
+    return sp.csc_matrix((m, n))
+
+
+def _blocked(a, rows, cols, raw, out):
+    """One block of the matrix held on the device by assembler `a` (rows / cols = 1-based inclusive ranges)."""
+    if not isinstance(a, SysmatAssemblerSparseGPU):
+        raise TypeError("matrix_blocked_* cut blocks from the device-resident matrix of a GPU assembler; there is no CPU path")
+    m, n = a._row_nalldofs, a._col_nalldofs
+    if rows[1] > m:
+        raise _lib.FEGPUError(-2, "The ff block has too many rows")
+    if cols[1] > n:
+        raise _lib.FEGPUError(-2, "The ff block has too many columns")
+    if rows[1] - rows[0] + 1 <= 0 or cols[1] - cols[0] + 1 <= 0:
+        return matrix_blocked_zeros(max(rows[1] - rows[0] + 1, 0), max(cols[1] - cols[0] + 1, 0), raw)  # spzeros, :682-686
+    a.view(rows[0], rows[1], cols[0], cols[1])
+    try:
+        return a._fetch(raw, out)
+    finally:
+        a.view_reset()
+
+
+def matrix_blocked_ff(a, row_nfreedofs, col_nfreedofs=None, raw=False, out=None):
+    """A[1:row_nfreedofs, 1:col_nfreedofs] (src/MatrixUtilityModule.jl:675-688)."""
+    cn = row_nfreedofs if col_nfreedofs is None else col_nfreedofs
+    if row_nfreedofs > a._row_nalldofs:
+        raise _lib.FEGPUError(-2, "The ff block has too many rows")
+    if cn > a._col_nalldofs:
+        raise _lib.FEGPUError(-2, "The ff block has too many columns")
+    return _blocked(a, (1, row_nfreedofs), (1, cn), raw, out)
+
+
+def matrix_blocked_fd(a, row_nfreedofs, col_nfreedofs=None, raw=False, out=None):
+    """A[1:row_nfreedofs, col_nfreedofs+1:end] (src/MatrixUtilityModule.jl:707-724)."""
+    cn = row_nfreedofs if col_nfreedofs is None else col_nfreedofs
+    return _blocked(a, (1, row_nfreedofs), (cn + 1, a._col_nalldofs), raw, out)
+
+
+def matrix_blocked_df(a, row_nfreedofs, col_nfreedofs=None, raw=False, out=None):
+    """A[row_nfreedofs+1:end, 1:col_nfreedofs] (src/MatrixUtilityModule.jl:743-760)."""
+    cn = row_nfreedofs if col_nfreedofs is None else col_nfreedofs
+    return _blocked(a, (row_nfreedofs + 1, a._row_nalldofs), (1, cn), raw, out)
+
+
+def matrix_blocked_dd(a, row_nfreedofs, col_nfreedofs=None, raw=False, out=None):
+    """A[row_nfreedofs+1:end, col_nfreedofs+1:end] (src/MatrixUtilityModule.jl:779-793)."""
+    cn = row_nfreedofs if col_nfreedofs is None else col_nfreedofs
+    return _blocked(a, (row_nfreedofs + 1, a._row_nalldofs), (cn + 1, a._col_nalldofs), raw, out)
 
 
 def startassembly(a, *args, **kw):

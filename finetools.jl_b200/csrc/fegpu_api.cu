@@ -462,10 +462,18 @@ int32_t fegpu_asm_create(fegpu_ctx *ctx, fegpu_asm **out) {
   return FEGPU_OK;
 }
 
+int32_t fegpu_asm_set_symmetric(fegpu_asm *as, int32_t on) {
+  if (!as) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL assembler");
+  if (as->started) return fegpu_fail(as->ctx, FEGPU_ERR_STATE, "cannot switch the assembler kind inside an assembly");
+  as->symmetric = on != 0;
+  return FEGPU_OK;
+}
+
 int32_t fegpu_asm_destroy(fegpu_asm *a) {
   if (!a) return FEGPU_OK;
   DeviceGuard g(a->ctx->device);
   cudaFree(a->d_V); cudaFree(a->d_nzval); cudaFree(a->own_colptr); cudaFree(a->own_rowval);
+  cudaFree(a->view.own_colptr); cudaFree(a->view.own_rowval); cudaFree(a->view.own_nzval);
   for (auto &ev : a->ev)
     if (ev) cudaEventDestroy(ev);
   delete a;
@@ -482,6 +490,7 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
   const int EM = mesh->nne * fa.ndn;
   const int64_t ntrip = mesh->nactive * (int64_t)EM * EM;
   as->have_result = false;
+  as->view.active = false;
   as->started = false;
   // 1. symbolic phase first (cached in the dof map): it decides the layout the integration kernel writes
   CUDA_TRY(ctx, cudaEventRecord(as->ev[0], st));
@@ -532,6 +541,18 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
   CUDA_TRY(ctx, cudaEventRecord(as->ev[3], st));
   as->ev_valid = true;
   as->have_result = true;
+  if (as->symmetric) {
+    // SysmatAssemblerSparseSymm: the element matrices of these forms are symmetric, so S + transpose(S) (diagonal halved) is
+    // the full assembly up to summation order; what differs is the pattern: entries that sum to exactly 0.0 are not stored
+    bool symm = fe_form_symmetric(fa.form);
+    if (fa.form == FORM_DOT) {  // bilform_dot is symmetric exactly when its ndn x ndn coefficient is
+      symm = true;
+      for (int p = 0; p < fa.ndn; p++)
+        for (int q = 0; q < p; q++) symm = symm && fa.coef[p + fa.ndn * q] == fa.coef[q + fa.ndn * p];
+    }
+    if (!symm) return fegpu_fail(ctx, FEGPU_ERR_ARG, "the symmetric assembler needs symmetric element matrices (non-symmetric coefficient)");
+    FE_TRY(fe_csc_view(as, 1, as->nrows, 1, as->ncols, true));
+  }
   return finish(ctx);
 }
 
@@ -596,11 +617,12 @@ int32_t fegpu_startassembly(fegpu_asm *as, int64_t nr, int64_t nc, int64_t nmats
 int32_t fegpu_assemble(fegpu_asm *as, const double *mat, const int64_t *dr, int64_t nrows, const int64_t *dc, int64_t ncols) {
   if (!as || !mat || !dr || !dc) return fegpu_fail(as ? as->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
   if (!as->started) return fegpu_fail(as->ctx, FEGPU_ERR_STATE, "assemble! before startassembly!");
+  if (as->symmetric && nrows != ncols) return fegpu_fail(as->ctx, FEGPU_ERR_MATSIZE, "Size mismatch");  // AssemblyModule.jl:510
   for (int64_t j = 0; j < ncols; j++) {
     const int64_t dj = dc[j];
     if (dj < 1) return fegpu_fail(as->ctx, FEGPU_ERR_COL_LT1, "Column degree of freedom < 1");
     if (dj > as->g_col_nall) return fegpu_fail(as->ctx, FEGPU_ERR_COL_GT, "Column degree of freedom > size");
-    for (int64_t i = 0; i < nrows; i++) {
+    for (int64_t i = as->symmetric ? j : 0; i < nrows; i++) {  // symmetric: lower triangle only, :521
       const int64_t di = dr[i];
       if (di < 1) return fegpu_fail(as->ctx, FEGPU_ERR_ROW_LT1, "Row degree of freedom < 1");
       if (di > as->g_row_nall) return fegpu_fail(as->ctx, FEGPU_ERR_ROW_GT, "Row degree of freedom > size");
@@ -627,6 +649,17 @@ int32_t fegpu_makematrix(fegpu_asm *as) {
   if (!as->started) return fegpu_fail(ctx, FEGPU_ERR_STATE, "makematrix! without startassembly!");
   DeviceGuard g(ctx->device);
   cudaStream_t st = ctx->stream;
+  if (as->symmetric) {
+    // S + transpose(S) with the doubled diagonal halved (AssemblyModule.jl:576-579): the mirrored copy of every
+    // off-diagonal triplet is appended; the diagonal stays single, which equals (2 S_jj) * 0.5 exactly
+    const size_t n0 = as->hV.size();
+    for (size_t k = 0; k < n0; k++)
+      if (as->hI[k] != as->hJ[k]) {
+        as->hI.push_back(as->hJ[k]);
+        as->hJ.push_back(as->hI[k]);
+        as->hV.push_back(as->hV[k]);
+      }
+  }
   const int64_t n = (int64_t)as->hV.size();
   int64_t *dI = nullptr, *dJ = nullptr;
   cudaError_t e;
@@ -652,9 +685,11 @@ int32_t fegpu_makematrix(fegpu_asm *as) {
   as->ev_valid = true;
   as->have_result = true;
   as->pattern_cached = false;
+  as->view.active = false;
   as->V_compact = false;
   as->started = false;  // "_buffer_pointer = 1": ready for the next startassembly!  (AssemblyModule.jl:327)
   as->V_n = 0;
+  if (as->symmetric) FE_TRY(fe_csc_view(as, 1, as->nrows, 1, as->ncols, true));  // the sparse `+` keeps only non-zero sums
   return finish(ctx);
 }
 
@@ -662,9 +697,9 @@ int32_t fegpu_makematrix(fegpu_asm *as) {
 int32_t fegpu_makematrix_sizes(fegpu_asm *as, int64_t *nrows, int64_t *ncols, int64_t *nnz) {
   if (!as) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL assembler");
   if (!as->have_result) return fegpu_fail(as->ctx, FEGPU_ERR_STATE, "no assembled matrix");
-  if (nrows) *nrows = as->nrows;
-  if (ncols) *ncols = as->ncols;
-  if (nnz) *nnz = as->nnz;
+  if (nrows) *nrows = as->r_nrows();
+  if (ncols) *ncols = as->r_ncols();
+  if (nnz) *nnz = as->r_nnz();
   return FEGPU_OK;
 }
 
@@ -675,12 +710,19 @@ int32_t fegpu_makematrix_copy(fegpu_asm *as, int64_t *colptr, int64_t *rowval, d
   DeviceGuard g(ctx->device);
   cudaStream_t st = ctx->stream;
   // large results go through the transport of fegpu_transfer.cu (int32 row indices on the link, host-thread widening)
-  if (as->nnz >= ((int64_t)1 << 20) && as->nrows < INT32_MAX) return fe_copy_result(as, colptr, rowval, nzval);
-  if (colptr) CUDA_TRY(ctx, cudaMemcpyAsync(colptr, as->d_colptr, sizeof(int64_t) * (as->ncols + 1), cudaMemcpyDeviceToHost, st));
-  if (rowval && as->nnz) CUDA_TRY(ctx, cudaMemcpyAsync(rowval, as->d_rowval, sizeof(int64_t) * as->nnz, cudaMemcpyDeviceToHost, st));
-  if (nzval && as->nnz) CUDA_TRY(ctx, cudaMemcpyAsync(nzval, as->d_nzval, sizeof(double) * as->nnz, cudaMemcpyDeviceToHost, st));
+  if (as->r_nnz() >= ((int64_t)1 << 20) && as->nrows < INT32_MAX) return fe_copy_result(as, colptr, rowval, nzval);
+  if (colptr) CUDA_TRY(ctx, cudaMemcpyAsync(colptr, as->r_colptr(), sizeof(int64_t) * (as->r_ncols() + 1), cudaMemcpyDeviceToHost, st));
+  if (rowval && as->r_nnz()) CUDA_TRY(ctx, cudaMemcpyAsync(rowval, as->r_rowval(), sizeof(int64_t) * as->r_nnz(), cudaMemcpyDeviceToHost, st));
+  if (nzval && as->r_nnz()) CUDA_TRY(ctx, cudaMemcpyAsync(nzval, as->r_nzval(), sizeof(double) * as->r_nnz(), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   return FEGPU_OK;
+}
+
+int32_t fegpu_makematrix_view(fegpu_asm *as, int64_t row_first, int64_t row_last, int64_t col_first, int64_t col_last, int32_t drop_exact_zeros) {
+  if (!as) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL assembler");
+  if (!as->have_result) return fegpu_fail(as->ctx, FEGPU_ERR_STATE, "no assembled matrix");
+  DeviceGuard g(as->ctx->device);
+  return fe_csc_view(as, row_first, row_last, col_first, col_last, drop_exact_zeros != 0);
 }
 
 int32_t fegpu_makematrix_copy_values(fegpu_asm *as, double *nzval) { return fegpu_makematrix_copy(as, nullptr, nullptr, nzval); }
@@ -688,9 +730,9 @@ int32_t fegpu_makematrix_copy_values(fegpu_asm *as, double *nzval) { return fegp
 int32_t fegpu_makematrix_device(fegpu_asm *as, const int64_t **c, const int64_t **r, const double **v) {
   if (!as) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL assembler");
   if (!as->have_result) return fegpu_fail(as->ctx, FEGPU_ERR_STATE, "no assembled matrix");
-  if (c) *c = as->d_colptr;
-  if (r) *r = as->d_rowval;
-  if (v) *v = as->d_nzval;
+  if (c) *c = as->r_colptr();
+  if (r) *r = as->r_rowval();
+  if (v) *v = as->r_nzval();
   return FEGPU_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -73,8 +74,23 @@ struct fegpu_asm {
   size_t own_colptr_cap = 0, own_rowval_cap = 0;
   bool have_result = false;
   bool pattern_cached = false;
+  // optional view of the result (sub-block and/or exact zeros dropped, fegpu_csc_ops.cu); the accessors below pick it
+  struct View {
+    bool active = false;
+    int64_t nrows = 0, ncols = 0, nnz = 0;
+    int64_t *own_colptr = nullptr, *own_rowval = nullptr;
+    double *own_nzval = nullptr;
+    size_t colptr_cap = 0, rowval_cap = 0, nzval_cap = 0;
+  } view;
+  int64_t r_nrows() const { return view.active ? view.nrows : nrows; }
+  int64_t r_ncols() const { return view.active ? view.ncols : ncols; }
+  int64_t r_nnz() const { return view.active ? view.nnz : nnz; }
+  const int64_t *r_colptr() const { return view.active ? view.own_colptr : d_colptr; }
+  const int64_t *r_rowval() const { return view.active ? view.own_rowval : d_rowval; }
+  const double *r_nzval() const { return view.active ? view.own_nzval : d_nzval; }
   // generic protocol staging (host side, flushed to the device at makematrix)
   bool started = false;
+  bool symmetric = false;  // SysmatAssemblerSparseSymm semantics (fegpu_asm_set_symmetric)
   int64_t g_row_nall = 0, g_col_nall = 0;
   std::vector<int64_t> hI, hJ;
   std::vector<double> hV;
@@ -147,6 +163,8 @@ int32_t fe_emit_ij(fegpu_dofmap *dm, int64_t *d_I, int64_t *d_J);
 // device CSC -> caller's host arrays; rowval crosses the link as int32 and is widened by host threads
 int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *nzval);
 void fe_transfer_free(struct Transfer *t);
+// ---- views of the assembled CSC (fegpu_csc_ops.cu): A[r0:r1, c0:c1] (1-based, inclusive), optionally without exact zeros
+int32_t fe_csc_view(fegpu_asm *as, int64_t r0, int64_t r1, int64_t c0, int64_t c1, bool drop_zeros);
 
 int32_t fe_asm_reserve(fegpu_asm *as, double **buf, size_t *cap, size_t need_doubles);
 int32_t fe_reserve_bytes(fegpu_ctx *ctx, void **buf, size_t *cap, size_t need_bytes);

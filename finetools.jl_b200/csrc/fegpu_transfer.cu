@@ -208,7 +208,7 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
   cudaStream_t cs = T->stream;
   CUDA_TRY(ctx, cudaEventRecord(T->ready, ctx->stream));
   CUDA_TRY(ctx, cudaStreamWaitEvent(cs, T->ready, 0));
-  const int64_t nnz = as->nnz;
+  const int64_t nnz = as->r_nnz();
 
   StagedJob jobs[2];
   int njobs = 0;
@@ -216,18 +216,18 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
   const int64_t *direct_rv = nullptr;
   if (rowval && nnz) {
     if (!T->narrow && is_pinned(rowval)) {
-      direct_rv = as->d_rowval;
+      direct_rv = as->r_rowval();
     } else {
       StagedJob &j = jobs[njobs++];
-      j.d_src = as->d_rowval; j.h_dst = rowval; j.n = nnz; j.narrow = true; j.item_dev = 4; j.dst_pinned = is_pinned(rowval);
+      j.d_src = as->r_rowval(); j.h_dst = rowval; j.n = nnz; j.narrow = true; j.item_dev = 4; j.dst_pinned = is_pinned(rowval);
     }
   }
   if (nzval && nnz) {
     if (is_pinned(nzval)) {
-      direct_nz = as->d_nzval;
+      direct_nz = as->r_nzval();
     } else {
       StagedJob &j = jobs[njobs++];
-      j.d_src = as->d_nzval; j.h_dst = nzval; j.n = nnz; j.narrow = false; j.item_dev = 8;
+      j.d_src = as->r_nzval(); j.h_dst = nzval; j.n = nnz; j.narrow = false; j.item_dev = 8;
     }
   }
   int64_t total_chunks = 0;
@@ -235,7 +235,7 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
     jobs[k].per_chunk = (int64_t)(T->chunk_bytes / jobs[k].item_dev);
     total_chunks += (jobs[k].n + jobs[k].per_chunk - 1) / jobs[k].per_chunk;
   }
-  if (colptr) CUDA_TRY(ctx, cudaMemcpyAsync(colptr, as->d_colptr, sizeof(int64_t) * (as->ncols + 1), cudaMemcpyDeviceToHost, cs));
+  if (colptr) CUDA_TRY(ctx, cudaMemcpyAsync(colptr, as->r_colptr(), sizeof(int64_t) * (as->r_ncols() + 1), cudaMemcpyDeviceToHost, cs));
   if (direct_rv) CUDA_TRY(ctx, cudaMemcpyAsync(rowval, direct_rv, sizeof(int64_t) * nnz, cudaMemcpyDeviceToHost, cs));
 
   // page-locked nzval goes by plain DMA, sliced in between the staged chunks so the link never idles while the threads work

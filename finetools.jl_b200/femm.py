@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import VP, FEGPUError, check, fptr
-from .assembly import SysmatAssemblerSparseGPU
+from .assembly import SysmatAssemblerFFBlock, SysmatAssemblerSparseGPU
 from .datacache import DataCache
 from .integdomain import IntegDomain, integrationdata
 
@@ -139,8 +139,13 @@ def _device_mesh(assembler, fes, geom):
     return dm
 
 
+def _inner(assembler):
+    """The GPU assembler doing the device work (SysmatAssemblerFFBlock delegates to the one it wraps, AssemblyModule.jl:1149)."""
+    return assembler._a if isinstance(assembler, SysmatAssemblerFFBlock) else assembler
+
+
 def _eligible(self, assembler, geom, u, cf):
-    if not isinstance(assembler, SysmatAssemblerSparseGPU):
+    if not isinstance(_inner(assembler), SysmatAssemblerSparseGPU):
         raise TypeError("this package provides the GPU assembler path only (SysmatAssemblerSparseGPU); there is no CPU loop")
     if not isinstance(cf, DataCache):
         raise TypeError("coefficient must be a constant DataCache")
@@ -154,6 +159,7 @@ def _eligible(self, assembler, geom, u, cf):
 
 def _prepare(self, assembler, geom, u, node_owner=None, my_rank=0):
     fes = self.integdomain.fes
+    assembler = _inner(assembler)
     dmesh = _device_mesh(assembler, fes, geom)
     dmesh.set_rule(self.integdomain)
     dmesh.set_partition(node_owner, my_rank)
@@ -163,9 +169,10 @@ def _prepare(self, assembler, geom, u, node_owner=None, my_rank=0):
 
 def _finish(assembler, fes, dmesh, dof, u, raw, out=None):
     elmdim = fes.nne * u.ndofs()
-    assembler._mode = "form"
-    assembler._row_nalldofs = assembler._col_nalldofs = u.nalldofs()
-    assembler._pending_form = (dmesh.handle, dof, fes.count() * elmdim * elmdim if dmesh.partition_key is None else None)
+    a = _inner(assembler)
+    a._mode = "form"
+    a._row_nalldofs = a._col_nalldofs = u.nalldofs()
+    a._pending_form = (dmesh.handle, dof, fes.count() * elmdim * elmdim if dmesh.partition_key is None else None, fes.count())
     return assembler.makematrix(raw=raw, out=out)
 
 
@@ -184,7 +191,7 @@ def bilform_diffusion(self, assembler, geom, u, cf, raw=False, node_owner=None, 
         if kap.shape != (fes.mdim, fes.mdim):
             raise FEGPUError(-2, "conductivity matrix must be mdim x mdim")
         kind, k = 1, np.asfortranarray(kap)
-    check(_lib.lib().fegpu_bilform_diffusion(dmesh.handle, dof, kind, fptr(k), assembler.handle), assembler.ctx.handle)
+    check(_lib.lib().fegpu_bilform_diffusion(dmesh.handle, dof, kind, fptr(k), _inner(assembler).handle), assembler.ctx.handle)
     return _finish(assembler, fes, dmesh, dof, u, raw, out)
 
 
@@ -200,7 +207,7 @@ def bilform_lin_elastic(self, assembler, geom, u, mr, cf, raw=False, node_owner=
         raise FEGPUError(-2, "material stiffness must be 6 x 6")
     fes, dmesh, dof = _prepare(self, assembler, geom, u, node_owner, my_rank)
     Cf = np.asfortranarray(Cm)
-    check(_lib.lib().fegpu_bilform_lin_elastic(dmesh.handle, dof, fptr(Cf), assembler.handle), assembler.ctx.handle)
+    check(_lib.lib().fegpu_bilform_lin_elastic(dmesh.handle, dof, fptr(Cf), _inner(assembler).handle), assembler.ctx.handle)
     return _finish(assembler, fes, dmesh, dof, u, raw, out)
 
 
@@ -215,7 +222,7 @@ def bilform_dot(self, assembler, geom, u, cf, m=3, raw=False, node_owner=None, m
         raise FEGPUError(-2, "coefficient must be ndn x ndn")
     fes, dmesh, dof = _prepare(self, assembler, geom, u, node_owner, my_rank)
     cfm = np.asfortranarray(c)
-    check(_lib.lib().fegpu_bilform_dot(dmesh.handle, dof, fptr(cfm), int(m), float(self.integdomain.otherdimension), assembler.handle),
+    check(_lib.lib().fegpu_bilform_dot(dmesh.handle, dof, fptr(cfm), int(m), float(self.integdomain.otherdimension), _inner(assembler).handle),
           assembler.ctx.handle)
     return _finish(assembler, fes, dmesh, dof, u, raw, out)
 

@@ -16,7 +16,7 @@ import FinEtools.FEMMBaseModule: bilform_diffusion, bilform_lin_elastic, bilform
 using FinEtools.IntegDomainModule: integrationdata, otherdimensionunity
 using FinEtools.DeforModelRedModule: DeforModelRed3D
 
-export SysmatAssemblerSparseGPU
+export SysmatAssemblerSparseGPU, SysmatAssemblerSparseSymmGPU, gpu_matrix_blocked
 
 const LIB = get(ENV, "FEGPU_LIB", joinpath(@__DIR__, "..", "libfinegpu.so"))
 
@@ -98,6 +98,38 @@ function makematrix!(self::SysmatAssemblerSparseGPU)
     GC.@preserve colptr rowval nzval _check(ccall((:fegpu_makematrix_copy, LIB), Int32,
             (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}), self.handle, colptr, rowval, nzval), self.ctx)
     return SparseMatrixCSC(m[], n[], colptr, rowval, nzval)   # 1-based Int64 arrays, used as they are
+end
+
+"""
+    SysmatAssemblerSparseSymmGPU(z = 0.0)
+
+Same protocol and result as `SysmatAssemblerSparseSymm` (AssemblyModule.jl:342-583): lower triangles in, `S + transpose(S)`
+with the diagonal halved out (entries that sum to exactly 0.0 are not stored).  It is a `SysmatAssemblerSparseGPU` whose
+library handle is switched to symmetric semantics, so every method above and below applies unchanged.
+"""
+function SysmatAssemblerSparseSymmGPU(z::Float64 = 0.0, nomatrixresult = false; device = 0)
+    a = SysmatAssemblerSparseGPU(z, nomatrixresult; device)
+    _check(ccall((:fegpu_asm_set_symmetric, LIB), Int32, (Ptr{Cvoid}, Int32), a.handle, 1), a.ctx)
+    return a
+end
+
+"""
+    gpu_matrix_blocked(a::SysmatAssemblerSparseGPU, row_nfreedofs, col_nfreedofs = row_nfreedofs)
+
+`matrix_blocked_ff/fd/df/dd` (MatrixUtilityModule.jl:675-793) cut on the device from the assembler's resident matrix; only the
+blocks cross the PCIe link.  `SysmatAssemblerFFBlock(SysmatAssemblerSparseGPU(0.0), nf, nf)` works as it is (the wrapper
+delegates to the inner assembler, AssemblyModule.jl:1149-1231) but copies the full matrix first; this does not.
+"""
+function gpu_matrix_blocked(a::SysmatAssemblerSparseGPU, rf::Int, cf::Int = rf)
+    m, n = a._row_nalldofs, a._col_nalldofs
+    function block(r0, r1, c0, c1)
+        (r1 < r0 || c1 < c0) && return spzeros(max(r1 - r0 + 1, 0), max(c1 - c0 + 1, 0))
+        _check(ccall((:fegpu_makematrix_view, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int32), a.handle, r0, r1, c0, c1, 0), a.ctx)
+        B = makematrix!(a)
+        _check(ccall((:fegpu_makematrix_view, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int32), a.handle, 1, m, 1, n, 0), a.ctx)
+        return B
+    end
+    return (ff = block(1, rf, 1, cf), fd = block(1, rf, cf + 1, n), df = block(rf + 1, m, 1, cf), dd = block(rf + 1, m, cf + 1, n))
 end
 
 # ---- device twins of (fes, geom, u) -------------------------------------------------------------------------------------

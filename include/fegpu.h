@@ -86,6 +86,10 @@ int32_t fegpu_dofmap_destroy(fegpu_dofmap *dofmap);
 /* -- assembler ------------------------------------------------------------------------------------------ */
 int32_t fegpu_asm_create(fegpu_ctx *ctx, fegpu_asm **as);
 int32_t fegpu_asm_destroy(fegpu_asm *as);
+/* on != 0: SysmatAssemblerSparseSymm semantics (AssemblyModule.jl:342-583).  fegpu_assemble keeps the lower triangle of each
+ * (square) element matrix (:517-530, "Size mismatch" :510); fegpu_makematrix and the bilform calls deliver
+ * S + transpose(S) with the diagonal halved (:576-579), i.e. the symmetric matrix WITHOUT entries that sum to exactly 0.0. */
+int32_t fegpu_asm_set_symmetric(fegpu_asm *as, int32_t on);
 
 /* The three bilinear forms.  Each call = startassembly! + the whole element loop + makematrix!
  * (the CSC stays on the device until fegpu_makematrix_copy). */
@@ -115,6 +119,15 @@ int32_t fegpu_makematrix(fegpu_asm *as);
  * SparseMatrixCSC(m, n, colptr, rowval, nzval): 1-based int64. */
 int32_t fegpu_makematrix_sizes(fegpu_asm *as, int64_t *nrows, int64_t *ncols, int64_t *nnz);
 int32_t fegpu_makematrix_copy(fegpu_asm *as, int64_t *colptr /* ncols+1 */, int64_t *rowval /* nnz */, double *nzval /* nnz */);
+/* View of the assembled matrix (built on the device, the full result stays available for further views):
+ *   A[row_first:row_last, col_first:col_last] (1-based, inclusive; stored zeros kept, rows rebased) -- replaces
+ *   matrix_blocked_ff/fd/df/dd (MatrixUtilityModule.jl:675-793) and SysmatAssemblerFFBlock's makematrix!
+ *   (AssemblyModule.jl:1149-1231);
+ *   drop_exact_zeros != 0 removes entries equal to 0.0 -- what SysmatAssemblerSparseSymm's `S + transpose(S)` leaves
+ *   (AssemblyModule.jl:551-583; SparseArrays' zero-preserving map stores only non-zero sums).
+ * Afterwards sizes / copy / device refer to the view; (1, nrows, 1, ncols, 0) restores the full matrix. */
+int32_t fegpu_makematrix_view(fegpu_asm *as, int64_t row_first, int64_t row_last, int64_t col_first, int64_t col_last,
+                              int32_t drop_exact_zeros);
 /* Transport notes (fegpu_transfer.cu): for results above 1 M nonzeros rowval crosses the PCIe link as int32 and is widened
  * into `rowval` by host threads (FEGPU_HOST_THREADS, default min(cores, 4)); destinations may be pageable or page-locked.
  * fegpu_transfer_stats: staged (int32 + widen) and bypassed (plain int64 DMA) chunk counts so far. */

@@ -192,6 +192,50 @@ def sparse(I, J, V, m, n):
     return colptr, rowval[:nnz].copy(), nzval[:nnz].copy()
 
 
+def matrix_block(csc, r0, r1, c0, c1):
+    """Julia's A[r0:r1, c0:c1] on a SparseMatrixCSC given as 1-based (colptr, rowval, nzval): stored zeros are kept, rows are
+    rebased to 1 (what matrix_blocked_ff/fd/df/dd do, src/MatrixUtilityModule.jl:675-793).  Pure NumPy."""
+    colptr, rowval, nzval = csc
+    ncols = max(c1 - c0 + 1, 0)
+    cp = np.ones(ncols + 1, np.int64)
+    rv, nz = [], []
+    for k, c in enumerate(range(c0, c1 + 1)):
+        b, e = colptr[c - 1] - 1, colptr[c] - 1
+        r = rowval[b:e]
+        sel = (r >= r0) & (r <= r1)
+        rv.append(r[sel] - r0 + 1)
+        nz.append(nzval[b:e][sel])
+        cp[k + 1] = cp[k] + int(sel.sum())
+    rv = np.concatenate(rv) if rv else np.zeros(0, np.int64)
+    nz = np.concatenate(nz) if nz else np.zeros(0)
+    return cp, rv.astype(np.int64), nz
+
+
+def lower_triangle_mask(em, nelem):
+    """Positions, inside the full emission-order triplet stream (AssemblyModule.jl:261-280), of the entries
+    SysmatAssemblerSparseSymm's assemble! collects (local i >= j, src/AssemblyModule.jl:517-530)."""
+    k = np.arange(em * em)
+    return np.tile((k % em) >= (k // em), nelem)
+
+
+def sparse_symm(I, J, V, n):
+    """makematrix!(::SysmatAssemblerSparseSymm) (src/AssemblyModule.jl:551-583) on the lower-triangle triplets:
+    S = sparse(I, J, V, n, n); S = S + transpose(S); S[j, j] *= 0.5.  SparseArrays' sparse `+` is a zero-preserving map
+    (higherorderfns.jl `_map_zeropres!`), which stores a result only when it is non-zero: entries that cancel to exactly
+    0.0 (and stored zeros) are absent.  Restated from the published stdlib algorithm; Julia is not available here."""
+    cp, rv, nz = sparse(I, J, V, n, n)
+    cols = np.repeat(np.arange(1, n + 1), np.diff(cp))
+    # S[i,j] + S'[i,j]: at most one stored entry from each operand, so the two-term sum is order-independent
+    cp2, rv2, nz2 = sparse(np.concatenate([rv, cols]), np.concatenate([cols, rv]), np.concatenate([nz, nz]), n, n)
+    cols2 = np.repeat(np.arange(1, n + 1), np.diff(cp2))
+    keep = nz2 != 0.0
+    nz2 = np.where(rv2 == cols2, nz2 * 0.5, nz2)
+    rv3, nz3, cols3 = rv2[keep], nz2[keep], cols2[keep]
+    cp3 = np.ones(n + 1, np.int64)
+    np.add.at(cp3, cols3, 1)
+    return np.cumsum(cp3) - np.arange(n + 1), rv3, nz3
+
+
 def to_scipy(colptr, rowval, nzval, m, n):
     import scipy.sparse as sp
     return sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(m, n))

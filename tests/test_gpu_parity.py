@@ -465,3 +465,96 @@ def test_result_transport_large(fe, orc, gpu_ctx, pinned):
     vals = np.full(nnz, np.nan)
     a.fetch_values(vals)
     np.testing.assert_array_equal(vals, got[2])
+
+
+def test_symm_assembler_testA_on_gpu(fe, orc, gpu_ctx):
+    """test/test_basics.jl:119-129 through the generic protocol of the symmetric assembler."""
+    from test_oracle_pins import _testA_blocks
+    a = fe.SysmatAssemblerSparseSymmGPU(0.0)
+    assert a.expectedntriples(5, 5, 3) == 45
+    fe.startassembly(a, 5, 5, 3, 7, 7)
+    I, J, V = [], [], []
+    for m, ii in _testA_blocks():
+        fe.assemble(a, m, ii, ii)
+        for j in range(4):
+            for i in range(j, 4):
+                I.append(ii[i]); J.append(ii[j]); V.append(m[i, j])
+    got = fe.makematrix(a, raw=True)
+    ref = orc.sparse_symm(np.array(I), np.array(J), np.array(V), 7)
+    assert_parity(ref, got)
+    with pytest.raises(fe.FEGPUError, match="Size mismatch"):
+        fe.startassembly(a, 2, 3, 1, 7, 7)
+        fe.assemble(a, np.zeros((2, 3)), [1, 2], [1, 2, 3])
+
+
+@pytest.mark.parametrize("form,et,ndn", [("diffusion", "H8", 1), ("elastic", "H8", 3), ("dot", "T10", 1), ("elastic", "T4", 3)])
+def test_symm_assembler_forms(fe, orc, gpu_ctx, form, et, ndn):
+    """The reference's default assembler (SysmatAssemblerSparseSymm, FEMMBaseModule.jl:1374,1408,1543,1822) on a distorted
+    mesh (no exact cancellations): same pattern as the oracle's S + transpose(S), values within tolerance; on an axis-aligned
+    block the exact zeros must disappear from the pattern."""
+    fens, fes = _mesh(fe, et, 3)
+    _distort(fens)
+    u = make_field(fe, fens, ndn)
+    rule = _rule(fe, et)
+    coef = {"diffusion": KAPPA3, "elastic": isotropic_C(), "dot": np.array([[1.3]])}[form]
+    _, (I, J, V) = oracle_csc(orc, form, et, fes, fens, u, rule, coef)
+    low = orc.lower_triangle_mask(fes.nne * ndn, fes.count())
+    ref = orc.sparse_symm(I[low], J[low], V[low], u.nalldofs())
+    a = fe.SysmatAssemblerSparseSymmGPU(0.0)
+    got, _ = gpu_csc(fe, form, fes, fens, u, rule, coef, assembler=a)
+    assert_parity(ref, got)
+    A = orc.to_scipy(got[0], got[1], got[2], got[3], got[4])
+    assert abs(A - A.T).max() == 0.0
+
+
+def test_symm_assembler_drops_exact_zeros(fe, orc, gpu_ctx):
+    """Entries that sum to exactly 0.0 are stored by SysmatAssemblerSparse but not by the symmetric assembler.  A conductivity
+    with a zero row/column (kappa = diag(1, 0, 0)) on axis-aligned bricks decouples nodes that differ only in y or z: exact zeros."""
+    fens, fes = fe.H8block(2.0, 2.0, 2.0, 3, 3, 3)
+    u = make_field(fe, fens, 1)
+    rule = fe.GaussRule(3, 2)
+    for kap in (np.zeros((3, 3)), np.diag([1.0, 0.0, 0.0])):
+        full, _ = gpu_csc(fe, "diffusion", fes, fens, u, rule, kap)
+        symm, _ = gpu_csc(fe, "diffusion", fes, fens, u, rule, kap, assembler=fe.SysmatAssemblerSparseSymmGPU(0.0))
+        nzero = int((full[2] == 0.0).sum())
+        assert symm[2].size == full[2].size - nzero and (symm[2] != 0.0).all()
+        A, B = orc.to_scipy(*full[:3], full[3], full[4]), orc.to_scipy(*symm[:3], symm[3], symm[4])
+        assert abs(A - B).max() == 0.0
+        if not kap.any():
+            assert nzero == full[2].size and symm[2].size == 0 and (symm[0] == 1).all()
+
+
+def test_ffblock_assembler_and_matrix_blocked(fe, orc, gpu_ctx):
+    """test/test_forms.jl:542-566: SysmatAssemblerFFBlock(nfreedofs) == matrix_blocked_ff(full assembly); all four blocks
+    against the oracle's Julia-range-indexing restatement."""
+    fens, fes = fe.H8block(1.0, 2.0, 3.0, 5, 4, 3)
+    _distort(fens)
+    u = make_field(fe, fens, 3, fixed_nodes=np.array([1, 2, 3, 17, 40]), fixed_comp=None)
+    nf, n = u.nfreedofs(), u.nalldofs()
+    assert 0 < nf < n
+    rule = fe.GaussRule(3, 2)
+    C = isotropic_C()
+    ref, _ = oracle_csc(orc, "elastic", "H8", fes, fens, u, rule, C)
+    a = fe.SysmatAssemblerSparseGPU(0.0)
+    full, _ = gpu_csc(fe, "elastic", fes, fens, u, rule, C, assembler=a)
+    assert_parity(ref, full)
+    blocks = {"ff": (1, nf, 1, nf), "fd": (1, nf, nf + 1, n), "df": (nf + 1, n, 1, nf), "dd": (nf + 1, n, nf + 1, n)}
+    for name, rng in blocks.items():
+        got = getattr(fe, "matrix_blocked_" + name)(a, nf, nf, raw=True)
+        assert (got[3], got[4]) == (rng[1] - rng[0] + 1, rng[3] - rng[2] + 1)
+        assert_parity(orc.matrix_block(ref, *rng), got)
+    again = a.makematrix(raw=True)                      # the full matrix is still there after cutting blocks
+    assert_parity(ref, again)
+    ff = fe.SysmatAssemblerFFBlock(nf)
+    got, _ = gpu_csc(fe, "elastic", fes, fens, u, rule, C, assembler=ff)
+    assert_parity(orc.matrix_block(ref, 1, nf, 1, nf), got)
+    # generic protocol through the wrapper (AssemblyModule.jl:1169-1231)
+    ff2 = fe.SysmatAssemblerFFBlock(3, 2)
+    fe.startassembly(ff2, 2, 2, 2, 4, 4)
+    fe.assemble(ff2, np.array([[1.0, 2.0], [3.0, 4.0]]), [1, 4], [1, 2])
+    fe.assemble(ff2, np.array([[5.0, 0.0], [7.0, 8.0]]), [2, 3], [2, 3])
+    got = fe.makematrix(ff2, raw=True)
+    I, J, V = np.array([1, 4, 1, 4, 2, 3, 2, 3]), np.array([1, 1, 2, 2, 2, 2, 3, 3]), np.array([1.0, 3.0, 2.0, 4.0, 5.0, 7.0, 0.0, 8.0])
+    assert_parity(orc.matrix_block(orc.sparse(I, J, V, 4, 4), 1, 3, 1, 2), got)
+    with pytest.raises(fe.FEGPUError, match="too many rows"):
+        fe.matrix_blocked_ff(a, n + 1)

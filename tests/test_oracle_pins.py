@@ -300,3 +300,47 @@ def test_survey_fingerprints(orc, fe):
     cp, rv, nz = orc.sparse(I, J, V, u.nalldofs(), u.nalldofs())
     assert nz.size == 6789
     assert abs(nz.sum() - 10.881) < 1e-12
+
+
+def _testA_blocks():
+    m1 = np.array([[0.24406, 0.599773, 0.833404, 0.0420141], [0.786024, 0.00206713, 0.995379, 0.780298],
+                   [0.845816, 0.198459, 0.355149, 0.224996]])
+    m2 = np.array([[0.146618, 0.53471, 0.614342, 0.737833], [0.479719, 0.41354, 0.00760941, 0.836455],
+                   [0.254868, 0.476189, 0.460794, 0.00919633], [0.159064, 0.261821, 0.317078, 0.77646],
+                   [0.643538, 0.429817, 0.59788, 0.958909]])
+    return (m1.T @ m1, np.array([5, 2, 1, 4], dtype=np.int64)), (m2.T @ m2, np.array([2, 3, 1, 5], dtype=np.int64))
+
+
+def test_symm_assembler_testA(orc):
+    """test/test_basics.jl:119-129: SysmatAssemblerSparseSymm on the same two blocks equals the general assembler's
+    matrix and is symmetric; the empty rows/columns 6, 7 stay empty."""
+    I, J, V = [], [], []
+    M = np.zeros((7, 7))
+    for m, ii in _testA_blocks():
+        M[np.ix_(ii - 1, ii - 1)] += m
+        for j in range(4):            # lower triangle, column outer (AssemblyModule.jl:517-530)
+            for i in range(j, 4):
+                I.append(ii[i]); J.append(ii[j]); V.append(m[i, j])
+    cp, rv, nz = orc.sparse_symm(np.array(I), np.array(J), np.array(V), 7)
+    A = orc.to_scipy(cp, rv, nz, 7, 7).toarray()
+    assert np.abs(A - M).max() < 1e-5 and np.abs(A - A.T).max() == 0.0
+    assert cp[-1] == cp[5] and nz.size == 23        # 25 pattern entries minus the (3,4)/(4,3) pair that never meets
+    # exact cancellation is dropped by the sparse `+` (zero-preserving map), a stored zero too
+    cp, rv, nz = orc.sparse_symm(np.array([2, 2, 3], np.int64), np.array([1, 1, 3], np.int64), np.array([1.5, -1.5, 0.0]), 3)
+    assert nz.size == 0 and (cp == 1).all()
+
+
+def test_matrix_block_semantics(orc):
+    """matrix_blocked_ff/fd/df/dd = Julia range indexing (MatrixUtilityModule.jl:675-793): stored zeros survive, rows rebased."""
+    I = np.array([1, 3, 4, 2, 4, 1, 3], np.int64)
+    J = np.array([1, 1, 1, 2, 3, 4, 4], np.int64)
+    V = np.array([1.0, 0.0, 3.0, 4.0, 5.0, 6.0, 7.0])
+    csc = orc.sparse(I, J, V, 4, 4)
+    full = orc.to_scipy(*csc, 4, 4).toarray()
+    nf = 2
+    for (r0, r1, c0, c1) in ((1, nf, 1, nf), (1, nf, nf + 1, 4), (nf + 1, 4, 1, nf), (nf + 1, 4, nf + 1, 4)):
+        cp, rv, nz = orc.matrix_block(csc, r0, r1, c0, c1)
+        B = orc.to_scipy(cp, rv, nz, r1 - r0 + 1, c1 - c0 + 1).toarray()
+        assert np.array_equal(B, full[r0 - 1:r1, c0 - 1:c1])
+    cp, rv, nz = orc.matrix_block(csc, 3, 4, 1, 2)
+    assert list(cp) == [1, 3, 3] and list(rv) == [1, 2] and list(nz) == [0.0, 3.0]   # the stored zero of (3,1) is kept
