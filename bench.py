@@ -34,9 +34,13 @@ sys.path.insert(0, ROOT)
 METRIC = "elements/s assembled into CSC (H8 lin_elastic stiffness, fresh assembly incl. pattern build)"
 UNIT = "elements/s"
 N_EDGE = 128
-FLOPS_PER_ELEM = 51936          # H8 lin_elastic as the reference executes it
-BYTES_INTEGRATE = 64 + 8 * 576 + 49      # conn + values (8 B/triplet, keys are never materialised) + amortised node data
-BYTES_GATHER_PER_ELEM = 8 * 576          # V read; nzval/rowval/index traffic is added per nnz below
+FLOPS_PER_ELEM = 51936          # H8 lin_elastic as the reference executes it (incl. the structural zeros of B)
+FLOPS_EXECUTED_PER_ELEM = 25128  # what k_h8_elastic executes: 8 points x (333 geometry + 4 x 702 block) flops, zeros of B skipped
+COMPACT_VALUES = 324            # doubles per element actually stored: the 36 upper 3x3 blocks (symmetric form), not 576
+# compulsory bytes of THIS implementation (smaller than SURVEY 8(d)'s 16 B/triplet figures because keys are
+# never materialised and only the upper block triangle is stored, so frac cannot exceed 1 by accounting)
+BYTES_INTEGRATE = 32 + 8 * COMPACT_VALUES + 49      # int32 conn + values + amortised node data
+BYTES_GATHER_PER_ELEM = 8 * COMPACT_VALUES + 2 * 64  # values read once + 2-byte slot table (64 candidates per node ~ per element)
 
 
 def isotropic_C(E=1.0, nu=0.3):
@@ -321,18 +325,29 @@ def run_gpu(args):
     integ_gbs = BYTES_INTEGRATE * nel_rank / (ph["integrate_ms"] * 1e-3) / 1e9
     gather_bytes = BYTES_GATHER_PER_ELEM * nel_rank + nnz_local * 8
     gather_gbs = gather_bytes / (ph["numeric_ms"] * 1e-3) / 1e9
+    # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of the two kernels (one `ncu --set full` capture of this
+    # workload at N = 1, committed with its summary under profiles/)
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)
     if ph["integrate_ms"] >= ph["numeric_ms"]:
-        dom = {"kernel": "k_h8_elastic", "achieved": integ_gbs}
+        dom = {"kernel": "k_h8_elastic", "achieved": integ_gbs, "bytes": BYTES_INTEGRATE * nel_rank}
     else:
-        dom = {"kernel": "k_gather<3>", "achieved": gather_gbs}
+        dom = {"kernel": "k_gather", "achieved": gather_gbs, "bytes": gather_bytes}
     peaks = ctx.measure_peaks()
+    tr = traffic.get(dom["kernel"], {}).get("dram_bytes_per_launch") if world == 1 else None
     roofline = {"bound": "hbm", "achieved": dom["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["achieved"] / hbm_peak,
-                "traffic": None, "kernel": dom["kernel"], "peak_kind": peak_kind,
-                "kernels": {"k_h8_elastic": {"ms": ph["integrate_ms"], "algorithmic_GBps": integ_gbs,
-                                             "algorithmic_TFLOPs": FLOPS_PER_ELEM * nel_rank / (ph["integrate_ms"] * 1e-3) / 1e12,
-                                             "dfma_peak_TFLOPs_measured": peaks["dfma_tflops"]},
+                "traffic": tr, "algorithmic_bytes_per_launch": dom["bytes"], "kernel": dom["kernel"], "peak_kind": peak_kind,
+                "traffic_source": traffic.get("source") if tr else None,
+                "kernels": {"k_h8_elastic": {"ms": ph["integrate_ms"], "algorithmic_GBps": integ_gbs, "bound": "fp64",
+                                             "executed_TFLOPs": FLOPS_EXECUTED_PER_ELEM * nel_rank / (ph["integrate_ms"] * 1e-3) / 1e12,
+                                             "reference_count_TFLOPs": FLOPS_PER_ELEM * nel_rank / (ph["integrate_ms"] * 1e-3) / 1e12,
+                                             "dfma_peak_TFLOPs_measured": peaks["dfma_tflops"],
+                                             "frac_fp64_executed": FLOPS_EXECUTED_PER_ELEM * nel_rank / (ph["integrate_ms"] * 1e-3) / 1e12 / peaks["dfma_tflops"]},
                             "symbolic(pattern build)": {"ms": ph["symbolic_ms"]},
-                            "k_gather<3>": {"ms": ph["numeric_ms"], "algorithmic_GBps": gather_gbs}},
+                            "k_gather": {"ms": ph["numeric_ms"], "algorithmic_GBps": gather_gbs, "bound": "hbm"}},
                 "copy_gbs_measured_here": peaks["copy_gbs"]}
 
     # bounded serial CPU baseline (the reference's own single-threaded path)
@@ -349,7 +364,7 @@ def run_gpu(args):
         "config": {"workload": "BASELINE configs[1]: bilform_lin_elastic, H8 block 128x128x%d (%d elements, %d nnz), GaussRule(3,2), "
                                "isotropic C; %s" % (nz_edge, nelem_global, nnz_total,
                                                     "single GPU" if world == 1 else "%d node-owned row blocks (z-slabs), halo recomputed" % world),
-                   "l2": "working set (9.7 GB triplet values per rank) >> 126 MB L2; no flush needed",
+                   "l2": "working set (5.4 GB element values + 8.2 GB CSC per rank) >> 126 MB L2; no flush needed",
                    "step": "fresh assembly: pattern cache invalidated before every step"},
         "clocks": clocks,
         "e2e": {"value": nelem_global / (e2e_s / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -269,6 +269,16 @@ int32_t fegpu_mesh_upload(fegpu_ctx *ctx, int32_t etype, int64_t nelem, const in
     fegpu_mesh_destroy(m);
     return fegpu_fail(ctx, code, msg);
   };
+  for (int d = 0; d < sdim; d++) {  // bounding box (host pass over the coordinates the caller just handed us)
+    double lo = nnodes ? xyz[(size_t)d * nnodes] : 0.0, hi = lo;
+    for (int64_t i = 1; i < nnodes; i++) {
+      const double v = xyz[(size_t)d * nnodes + i];
+      lo = v < lo ? v : lo;
+      hi = v > hi ? v : hi;
+    }
+    m->bbox_lo[d] = lo;
+    m->bbox_hi[d] = hi;
+  }
   const size_t nc = (size_t)nelem * nne;
   cudaError_t e;
 #define MT(expr) if ((e = (expr)) != cudaSuccess) return fail(FEGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e))

@@ -43,6 +43,7 @@ struct fegpu_mesh {
   uint8_t *d_rowowned = nullptr;    // per node, nullptr = all owned
   uint64_t topo_version = 1;        // bumped when the active set / ownership changes
   bool degenerate = false;          // some element lists a node twice -> generic sort path
+  double bbox_lo[3] = {0, 0, 0}, bbox_hi[3] = {0, 0, 0};  // of the coordinates at upload (node visiting order of the gather)
 };
 
 struct fegpu_dofmap {
@@ -158,6 +159,8 @@ int32_t fe_coo_to_csc(fegpu_asm *as, int64_t n, const int64_t *d_I, const int64_
                       int64_t ncols);
 // emit the reference-order (I, J) of a bilform assembly (AssemblyModule.jl:266-279) from conn + dof map
 int32_t fe_emit_ij(fegpu_dofmap *dm, int64_t *d_I, int64_t *d_J);
+// Morton order of (a subset of) the nodes (spatial locality for the gather's L2 reuse): d_order [n]
+int32_t fe_morton_order(fegpu_mesh *mesh, const int32_t *d_nodes /* subset or nullptr = all */, int64_t n, int32_t *d_order);
 
 // ---- result transport (fegpu_transfer.cu) --------------------------------------------------------------
 // device CSC -> caller's host arrays; rowval crosses the link as int32 and is widened by host threads

@@ -31,6 +31,8 @@ struct Pattern {
   int64_t *d_nbrptr = nullptr;    // [nnodes+1]
   uint16_t *d_cslot = nullptr;    // per node at adjptr[n]*nne + a*nne + li: neighbour slot of that candidate (0xffff = dropped)
   uint16_t *d_rank = nullptr;     // per node nnbr*ndn entries at nbrptr[n]*ndn, nullptr when identity everywhere
+  int32_t *d_order = nullptr;     // node visiting order of the gather: the active nodes in Morton order of their coordinates
+  int64_t norder = 0;             // (nullptr = all nodes, natural order)
   int maxdeg = 0, maxcand = 0, maxnbr = 0;
   cudaStream_t stream = 0;
 };
@@ -50,7 +52,21 @@ struct SymParams {
   const uint8_t *rowowned;
   const int32_t *dof;  // [ndn][nnodes]
   int ndn;
+  // nodes that have at least one active element (ascending), nullptr = all nodes; the per-node kernels visit only these, so
+  // a rank's symbolic cost follows its own share of the mesh (row-block partitions, boundary skins)
+  const int32_t *anodes;
+  int64_t na;
 };
+__device__ __forceinline__ int64_t active_node(const SymParams &S, int64_t idx) { return S.anodes ? (int64_t)S.anodes[idx] : idx; }
+
+__global__ void k_flag_active(const int32_t *__restrict__ deg, int64_t nnodes, int32_t *__restrict__ flag) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < nnodes) flag[n] = deg[n] > 0 ? 1 : 0;
+}
+__global__ void k_compact_active(const int32_t *__restrict__ flag, const int64_t *__restrict__ pos, int64_t nnodes, int32_t *__restrict__ list) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < nnodes && flag[n]) list[pos[n]] = (int32_t)n;
+}
 
 __global__ void k_count_adj(SymParams S, int32_t *deg, int *degenerate) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -78,9 +94,10 @@ __global__ void k_fill_adj(SymParams S, const int64_t *adjptr, int32_t *cursor, 
 }
 
 // ascending slot order inside every node's list (the atomics above deliver an arbitrary order)
-__global__ void k_sort_adj(int64_t nnodes, const int64_t *adjptr, int32_t *adj_slot, uint8_t *adj_lc) {
-  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nnodes) return;
+__global__ void k_sort_adj(SymParams S, const int64_t *adjptr, int32_t *adj_slot, uint8_t *adj_lc) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S.na) return;
+  const int64_t n = active_node(S, idx);
   int64_t b = adjptr[n], e = adjptr[n + 1];
   for (int64_t i = b + 1; i < e; i++) {
     int32_t s = adj_slot[i];
@@ -176,7 +193,8 @@ __global__ void __launch_bounds__(WPB * 32) k_nbr(SymParams S, const int64_t *__
   uint32_t *work = cand + capc;
   uint32_t *uq = work + capc;
   const int nne = (NNE_T > 0) ? NNE_T : S.nne, ndn = S.ndn;
-  for (int64_t n = (int64_t)blockIdx.x * WPB + w; n < S.nnodes; n += (int64_t)gridDim.x * WPB) {
+  for (int64_t idx = (int64_t)blockIdx.x * WPB + w; idx < S.na; idx += (int64_t)gridDim.x * WPB) {
+    const int64_t n = active_node(S, idx);
     const int64_t ab = adjptr[n];
     const int deg = (int)(adjptr[n + 1] - ab);
     if (deg == 0) {
@@ -285,8 +303,9 @@ __global__ void __launch_bounds__(256) k_rows_sorted(SymParams S, const int64_t 
   constexpr int UNR = 4;  // row chunks whose neighbour -> dof loads are issued together
   const int ndn = (NDN > 0) ? NDN : S.ndn;
   const int gl = threadIdx.x % LPN;
-  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPN;
-  if (n >= S.nnodes) return;
+  const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPN;
+  if (idx >= S.na) return;
+  const int64_t n = active_node(S, idx);
   const int nu = nnbr[n];
   const uint8_t sf = sorted_flag[n];
   const int64_t ab = adjptr[n];
@@ -329,7 +348,8 @@ __global__ void __launch_bounds__(WPB * 32) k_rows(SymParams S, const int64_t *_
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   unsigned long long *keys = sk + (size_t)w * cap2;
   const int ndn = S.ndn;
-  for (int64_t n = (int64_t)blockIdx.x * WPB + w; n < S.nnodes; n += (int64_t)gridDim.x * WPB) {
+  for (int64_t idx = (int64_t)blockIdx.x * WPB + w; idx < S.na; idx += (int64_t)gridDim.x * WPB) {
+    const int64_t n = active_node(S, idx);
     const int nu = nnbr[n];
     if (nu == 0 || sorted_flag[n]) continue;
     const int32_t *Un = U + adjptr[n] * S.nne;
@@ -378,6 +398,8 @@ struct GatherParams {
   const double *V;
   double *nzval;
   int maxnbr, maxdeg, maxcand;
+  const int32_t *order;  // visiting order (active nodes, Morton-sorted) or nullptr = all nodes in natural order
+  int64_t npos;          // visiting positions
 };
 
 // Offset (inside one element's values) of entry (row node li, row comp p; column node lc, column comp q).
@@ -415,7 +437,7 @@ __global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
   long long *base = reinterpret_cast<long long *>(acc + acc_stride);
   uint16_t *cs = reinterpret_cast<uint16_t *>(base + G.maxdeg);
   const int64_t groups_total = (int64_t)gridDim.x * GWPB * NPW;
-  const int64_t niter = (G.nnodes + groups_total - 1) / groups_total;
+  const int64_t niter = (G.npos + groups_total - 1) / groups_total;
   // rows of the element matrix this lane adds: r = gl + j*LPN
   int rli[RMAX], rp[RMAX];
   bool rok[RMAX];
@@ -426,8 +448,10 @@ __global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
     rli[j] = rok[j] ? r / ndn : 0;
     rp[j] = rok[j] ? r - rli[j] * ndn : 0;
   }
-  // scalars of the first node
-  int64_t n = (int64_t)blockIdx.x * (GWPB * NPW) + w * NPW + g;
+  // visiting position -> node (Morton order when G.order); node ids are prefetched two iterations ahead, scalars one
+  int64_t pos = (int64_t)blockIdx.x * (GWPB * NPW) + w * NPW + g;
+  int64_t n = (pos < G.npos) ? (G.order ? (int64_t)G.order[pos] : pos) : G.nnodes;
+  int64_t n_next = (pos + groups_total < G.npos) ? (G.order ? (int64_t)G.order[pos + groups_total] : pos + groups_total) : G.nnodes;
   int nn_pre = (n < G.nnodes) ? G.nnbr[n] : 0;
   int64_t ab_pre = (n < G.nnodes) ? G.adjptr[n] : 0, ae_pre = (n < G.nnodes) ? G.adjptr[n + 1] : 0;
   for (int64_t it = 0; it < niter; it++) {
@@ -448,8 +472,9 @@ __global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
     long long cb[QMAX];
 #pragma unroll
     for (int q = 0; q < QMAX; q++) cb[q] = (q < ndn && deg > 0) ? G.colptr[G.dof[(int64_t)q * G.nnodes + n]] - 1 : 0;
-    const int64_t n_next = n + groups_total;
-    if (it + 1 < niter && n_next < G.nnodes) {
+    const int64_t pos2 = pos + 2 * groups_total;
+    const int64_t n_next2 = (pos2 < G.npos) ? (G.order ? (int64_t)G.order[pos2] : pos2) : G.nnodes;
+    if (n_next < G.nnodes) {
       nn_pre = G.nnbr[n_next];
       ab_pre = G.adjptr[n_next];
       ae_pre = G.adjptr[n_next + 1];
@@ -533,6 +558,8 @@ __global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
     }
     __syncwarp();
     n = n_next;
+    n_next = n_next2;
+    pos += groups_total;
   }
 }
 
@@ -549,7 +576,7 @@ int32_t dalloc(fegpu_ctx *ctx, T **p, size_t n) {
 void fe_pattern_free(Pattern *p) {
   if (!p) return;
   cudaStream_t st = p->stream;  // stream-ordered frees: blocks go back to the pool, no device synchronisation
-  void *ptrs[] = {p->d_colptr, p->d_rowval, p->d_adjptr, p->d_adj_slot, p->d_adj_lc, p->d_nnbr, p->d_nbrptr, p->d_cslot, p->d_rank};
+  void *ptrs[] = {p->d_colptr, p->d_rowval, p->d_adjptr, p->d_adj_slot, p->d_adj_lc, p->d_nnbr, p->d_nbrptr, p->d_cslot, p->d_rank, p->d_order};
   for (void *q : ptrs)
     if (q) cudaFreeAsync(q, st);
   delete p;
@@ -574,14 +601,15 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
   P->nrows = dm->row_nall;
   const int64_t nn = mesh->nnodes;
   const int nne = mesh->nne, ndn = dm->ndn;
-  SymParams S{mesh->d_conn, mesh->d_elem_list, mesh->nactive, nne, nn, mesh->d_rowowned, dm->d_dof, ndn};
+  SymParams S{mesh->d_conn, mesh->d_elem_list, mesh->nactive, nne, nn, mesh->d_rowowned, dm->d_dof, ndn, nullptr, nn};
   const int64_t nadj = mesh->nactive * nne;
 
-  int32_t *d_deg = nullptr, *d_cursor = nullptr, *d_U = nullptr;
+  int32_t *d_deg = nullptr, *d_cursor = nullptr, *d_U = nullptr, *d_aflag = nullptr, *d_anodes = nullptr;
+  int64_t *d_apos = nullptr;
   uint8_t *d_sorted = nullptr;
   int *d_flags = nullptr;  // [0] degenerate, [1] some node needs a dof sort
   auto cleanup = [&]() {
-    void *ptrs[] = {d_deg, d_cursor, d_U, d_sorted, d_flags};
+    void *ptrs[] = {d_deg, d_cursor, d_U, d_sorted, d_flags, d_aflag, d_anodes, d_apos};
     for (void *q : ptrs)
       if (q) cudaFreeAsync(q, st);
   };
@@ -608,6 +636,22 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
   PT(fe_exclusive_scan_i32_to_i64(ctx, d_deg, P->d_adjptr, nn, 0, true, nullptr));
   int32_t maxdeg = 0;
   PT(fe_max_i32(ctx, d_deg, nn, &maxdeg));
+  // active nodes (at least one active element): compacted list, dropped again when it is every node
+  int64_t na = nn;
+  if (nn > 0) {
+    PT(dalloc(ctx, &d_aflag, nn));
+    PT(dalloc(ctx, &d_apos, nn + 1));
+    k_flag_active<<<grid_for(nn, 256), 256, 0, st>>>(d_deg, nn, d_aflag);
+    ctx->launches++;
+    PT(fe_exclusive_scan_i32_to_i64(ctx, d_aflag, d_apos, nn, 0, true, &na));
+    if (na < nn) {
+      PT(dalloc(ctx, &d_anodes, na));
+      k_compact_active<<<grid_for(nn, 256), 256, 0, st>>>(d_aflag, d_apos, nn, d_anodes);
+      ctx->launches++;
+      S.anodes = d_anodes;
+      S.na = na;
+    }
+  }
   int h_flags[2] = {0, 0};
   PC(cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
   PC(cudaStreamSynchronize(st));
@@ -625,14 +669,18 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
   PT(dalloc(ctx, &P->d_adj_lc, nadj));
   if (nadj > 0) {
     k_fill_adj<<<grid_for(nadj, 256), 256, 0, st>>>(S, P->d_adjptr, d_cursor, P->d_adj_slot, P->d_adj_lc);
-    k_sort_adj<<<grid_for(nn, 128), 128, 0, st>>>(nn, P->d_adjptr, P->d_adj_slot, P->d_adj_lc);
+    k_sort_adj<<<grid_for(S.na, 128), 128, 0, st>>>(S, P->d_adjptr, P->d_adj_slot, P->d_adj_lc);
     ctx->launches += 2;
   }
   PT(dalloc(ctx, &P->d_nnbr, nn));
   PT(dalloc(ctx, &d_U, (size_t)nadj * nne));
   PT(dalloc(ctx, &d_sorted, nn));
   PT(dalloc(ctx, &P->d_cslot, (size_t)nadj * nne));
-  unsigned gridn = (unsigned)std::min<int64_t>((nn + WPB - 1) / WPB, (int64_t)ctx->sm_count * 64);
+  if (S.anodes) {  // the per-node kernels skip inactive nodes: their outputs must still be defined
+    PC(cudaMemsetAsync(P->d_nnbr, 0, sizeof(int32_t) * nn, st));
+    PC(cudaMemsetAsync(d_sorted, 1, nn, st));
+  }
+  unsigned gridn = (unsigned)std::min<int64_t>((S.na + WPB - 1) / WPB, (int64_t)ctx->sm_count * 64);
   if (gridn == 0) gridn = 1;
 #define LAUNCH_NBR(N)                                                                                                  \
   do {                                                                                                                 \
@@ -681,14 +729,27 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
   if (smem2 > 200 * 1024) return bail();
   if (smem2 > 48 * 1024) PC(cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   {
-    constexpr int RL = 32;  // lanes per node (8 measured slower: 64-byte store segments)
-    const unsigned gr = grid_for(nn * RL, 256);
+    // lanes per node: a warp for vector fields (rows per column >= 81 for H8), 8 lanes for scalar fields (27 rows: four
+    // nodes per warp keep four dependent-load chains in flight).  FEGPU_ROWS_LPN overrides (tuning knob).
+    static const int lpn_env = std::getenv("FEGPU_ROWS_LPN") ? std::atoi(std::getenv("FEGPU_ROWS_LPN")) : 0;
+    int rl = (ndn >= 3) ? 32 : (ndn == 2 ? 16 : 8);
+    if (lpn_env == 8 || lpn_env == 16 || lpn_env == 32) rl = lpn_env;
+    const unsigned gr = grid_for(S.na * rl, 256);
+#define ROWS_ARGS S, P->d_adjptr, P->d_nnbr, P->d_nbrptr, d_U, d_sorted, P->d_colptr, P->d_rowval, P->d_rank
+#define ROWS_L(N)                                                              \
+  do {                                                                         \
+    if (rl == 8) k_rows_sorted<8, N><<<gr, 256, 0, st>>>(ROWS_ARGS);           \
+    else if (rl == 16) k_rows_sorted<16, N><<<gr, 256, 0, st>>>(ROWS_ARGS);    \
+    else k_rows_sorted<32, N><<<gr, 256, 0, st>>>(ROWS_ARGS);                  \
+  } while (0)
     switch (ndn) {
-      case 1: k_rows_sorted<RL, 1><<<gr, 256, 0, st>>>(S, P->d_adjptr, P->d_nnbr, P->d_nbrptr, d_U, d_sorted, P->d_colptr, P->d_rowval, P->d_rank); break;
-      case 2: k_rows_sorted<RL, 2><<<gr, 256, 0, st>>>(S, P->d_adjptr, P->d_nnbr, P->d_nbrptr, d_U, d_sorted, P->d_colptr, P->d_rowval, P->d_rank); break;
-      case 3: k_rows_sorted<RL, 3><<<gr, 256, 0, st>>>(S, P->d_adjptr, P->d_nnbr, P->d_nbrptr, d_U, d_sorted, P->d_colptr, P->d_rowval, P->d_rank); break;
-      default: k_rows_sorted<RL, 0><<<gr, 256, 0, st>>>(S, P->d_adjptr, P->d_nnbr, P->d_nbrptr, d_U, d_sorted, P->d_colptr, P->d_rowval, P->d_rank); break;
+      case 1: ROWS_L(1); break;
+      case 2: ROWS_L(2); break;
+      case 3: ROWS_L(3); break;
+      default: ROWS_L(0); break;
     }
+#undef ROWS_L
+#undef ROWS_ARGS
     ctx->launches++;
   }
   if (need_rank) {  // only the nodes whose dof order needs a sort
@@ -696,6 +757,20 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
     ctx->launches++;
   }
   PC(cudaGetLastError());
+  {  // node visiting order of the gather.  Morton order (FEGPU_GATHER_ORDER=1) was measured on configs 2-4: it costs a
+     // radix sort of the nodes per pattern build (+0.2 ms at 2.1 M nodes, +3 ms at 17 M) and saves < 0.1 ms of gather on
+     // meshes whose numbering is already local, so the default is the natural order of the active nodes.
+    static const bool order_off = !(std::getenv("FEGPU_GATHER_ORDER") && std::atoi(std::getenv("FEGPU_GATHER_ORDER")) == 1);
+    if (!order_off && S.na > 0) {
+      PT(dalloc(ctx, &P->d_order, S.na));
+      PT(fe_morton_order(mesh, S.anodes, S.na, P->d_order));
+      P->norder = S.na;
+    } else if (S.anodes && S.na > 0) {  // natural order, active nodes only
+      PT(dalloc(ctx, &P->d_order, S.na));
+      PC(cudaMemcpyAsync(P->d_order, S.anodes, sizeof(int32_t) * S.na, cudaMemcpyDeviceToDevice, st));
+      P->norder = S.na;
+    }
+  }
   cleanup();
 #undef PT
 #undef PC
@@ -710,7 +785,7 @@ int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_n
   if (!P) return fegpu_fail(ctx, FEGPU_ERR_STATE, "no pattern");
   if (P->nnz == 0) return FEGPU_OK;
   GatherParams G{mesh->nnodes, mesh->nne, dm->ndn, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, P->d_nnbr, P->d_nbrptr, P->d_cslot,
-                 P->d_rank, dm->d_dof, P->d_colptr, d_V, d_nzval, P->maxnbr, P->maxdeg, P->maxcand};
+                 P->d_rank, dm->d_dof, P->d_colptr, d_V, d_nzval, P->maxnbr, P->maxdeg, P->maxcand, P->d_order, P->d_order ? P->norder : mesh->nnodes};
   const int EM = mesh->nne * dm->ndn;
   // tuning knobs (measured defaults below): FEGPU_GATHER_LPN lanes per node, FEGPU_GATHER_BATCH elements in flight
   static const int batch_env = std::getenv("FEGPU_GATHER_BATCH") ? std::atoi(std::getenv("FEGPU_GATHER_BATCH")) : 0;
@@ -727,7 +802,7 @@ int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_n
   const size_t smem = (size_t)GWPB * npw * ((size_t)P->maxnbr * dm->ndn * dm->ndn + P->maxdeg + (P->maxcand + 3) / 4) * sizeof(double);
   if (smem > 200 * 1024) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: gather accumulators exceed shared memory");
   const int64_t per_block = (int64_t)GWPB * npw;
-  unsigned grid = (unsigned)std::min<int64_t>((mesh->nnodes + per_block - 1) / per_block, (int64_t)ctx->sm_count * 32);
+  unsigned grid = (unsigned)std::min<int64_t>((G.npos + per_block - 1) / per_block, (int64_t)ctx->sm_count * 32);
   if (grid == 0) grid = 1;
 #define LG5(L, N, C, B, R)                                                                                                          \
   do {                                                                                                                              \

@@ -189,6 +189,94 @@ static const char *dof_msg(int code) {
   }
 }
 
+// Stable LSD radix sort of (key, id) pairs over the given digit shifts; *kin/*iin end up pointing at the sorted buffers.
+static int32_t radix_sort_pairs(fegpu_ctx *ctx, int64_t n, const std::vector<int> &shifts, unsigned long long **kin, unsigned long long **kout,
+                                uint32_t **iin, uint32_t **iout, int32_t *hist, int64_t *offs) {
+  const int64_t ntiles = (n + RS_TILE - 1) / RS_TILE;
+  for (int sh : shifts) {
+    k_rs_hist<<<(unsigned)ntiles, RS_THREADS, 0, ctx->stream>>>(*kin, n, sh, hist, ntiles);
+    ctx->launches++;
+    FE_TRY(fe_exclusive_scan_i32_to_i64(ctx, hist, offs, 256 * ntiles, 0, false, nullptr));
+    k_rs_scatter<<<(unsigned)ntiles, RS_THREADS, 0, ctx->stream>>>(*kin, *iin, *kout, *iout, n, sh, offs, ntiles);
+    ctx->launches++;
+    std::swap(*kin, *kout);
+    std::swap(*iin, *iout);
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  return FEGPU_OK;
+}
+
+namespace {
+// 30-bit Morton code of a node's position inside the mesh bounding box (10 bits per axis)
+__device__ __forceinline__ unsigned spread10(unsigned v) {
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__global__ void k_morton_keys(const double *__restrict__ xyz, int64_t nnodes, const int32_t *__restrict__ nodes, int64_t count, int sdim,
+                              double lx, double ly, double lz, double sx, double sy, double sz, unsigned long long *__restrict__ keys,
+                              uint32_t *__restrict__ ids) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t n = nodes ? (int64_t)nodes[i] : i;
+  const unsigned qx = (unsigned)fmin(fmax((xyz[n] - lx) * sx, 0.0), 1023.0);
+  const unsigned qy = sdim > 1 ? (unsigned)fmin(fmax((xyz[nnodes + n] - ly) * sy, 0.0), 1023.0) : 0u;
+  const unsigned qz = sdim > 2 ? (unsigned)fmin(fmax((xyz[2 * nnodes + n] - lz) * sz, 0.0), 1023.0) : 0u;
+  keys[i] = (unsigned long long)(spread10(qx) | (spread10(qy) << 1) | (spread10(qz) << 2));
+  ids[i] = (uint32_t)n;
+}
+__global__ void k_ids_to_i32(const uint32_t *__restrict__ ids, int32_t *__restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int32_t)ids[i];
+}
+}  // namespace
+
+// Node visiting order with spatial locality (Morton order of the coordinates): nodes that share elements are processed close
+// together in time, so element data read by several column nodes is still in L2 the second time.  d_order: [nnodes].
+int32_t fe_morton_order(fegpu_mesh *mesh, const int32_t *d_nodes, int64_t n, int32_t *d_order) {
+  fegpu_ctx *ctx = mesh->ctx;
+  cudaStream_t st = ctx->stream;
+  if (n == 0) return FEGPU_OK;
+  unsigned long long *kA = nullptr, *kB = nullptr;
+  uint32_t *iA = nullptr, *iB = nullptr;
+  int32_t *hist = nullptr;
+  int64_t *offs = nullptr;
+  const int64_t ntiles = (n + RS_TILE - 1) / RS_TILE;
+  auto cleanup = [&]() {
+    void *ptrs[] = {kA, kB, iA, iB, hist, offs};
+    for (void *q : ptrs)
+      if (q) cudaFreeAsync(q, st);
+  };
+#define MC(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fegpu_fail(ctx, FEGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+  MC(cudaMallocAsync((void **)&kA, sizeof(unsigned long long) * n, st));
+  MC(cudaMallocAsync((void **)&kB, sizeof(unsigned long long) * n, st));
+  MC(cudaMallocAsync((void **)&iA, sizeof(uint32_t) * n, st));
+  MC(cudaMallocAsync((void **)&iB, sizeof(uint32_t) * n, st));
+  MC(cudaMallocAsync((void **)&hist, sizeof(int32_t) * 256 * ntiles, st));
+  MC(cudaMallocAsync((void **)&offs, sizeof(int64_t) * (256 * ntiles + 1), st));
+#undef MC
+  double s[3];
+  for (int d = 0; d < 3; d++) {
+    const double ext = mesh->bbox_hi[d] - mesh->bbox_lo[d];
+    s[d] = ext > 0 ? 1023.999 / ext : 0.0;
+  }
+  k_morton_keys<<<grid_for(n, 256), 256, 0, st>>>(mesh->d_xyz, mesh->nnodes, d_nodes, n, mesh->sdim, mesh->bbox_lo[0], mesh->bbox_lo[1], mesh->bbox_lo[2], s[0], s[1], s[2], kA, iA);
+  ctx->launches++;
+  unsigned long long *kin = kA, *kout = kB;
+  uint32_t *iin = iA, *iout = iB;
+  const std::vector<int> shifts = {0, 8, 16, 24};
+  int32_t rc = radix_sort_pairs(ctx, n, shifts, &kin, &kout, &iin, &iout, hist, offs);
+  if (rc == FEGPU_OK) {
+    k_ids_to_i32<<<grid_for(n, 256), 256, 0, st>>>(iin, d_order, n);
+    ctx->launches++;
+  }
+  cleanup();
+  return rc;
+}
+
 int32_t fe_coo_to_csc(fegpu_asm *as, int64_t n, const int64_t *d_I, const int64_t *d_J, const double *d_V, int64_t nrows, int64_t ncols) {
   fegpu_ctx *ctx = as->ctx;
   cudaStream_t st = ctx->stream;
@@ -246,16 +334,7 @@ int32_t fe_coo_to_csc(fegpu_asm *as, int64_t n, const int64_t *d_I, const int64_
   for (int s = 0; s < cb; s += 8) shifts.push_back(32 + s);
   unsigned long long *kin = kA, *kout = kB;
   uint32_t *iin = iA, *iout = iB;
-  for (int sh : shifts) {
-    k_rs_hist<<<(unsigned)ntiles, RS_THREADS, 0, st>>>(kin, n, sh, hist, ntiles);
-    ctx->launches++;
-    ST(fe_exclusive_scan_i32_to_i64(ctx, hist, offs, 256 * ntiles, 0, false, nullptr));
-    k_rs_scatter<<<(unsigned)ntiles, RS_THREADS, 0, st>>>(kin, iin, kout, iout, n, sh, offs, ntiles);
-    ctx->launches++;
-    std::swap(kin, kout);
-    std::swap(iin, iout);
-  }
-  SC(cudaGetLastError());
+  ST(radix_sort_pairs(ctx, n, shifts, &kin, &kout, &iin, &iout, hist, offs));
   // segments
   SC(cudaMalloc((void **)&head, sizeof(int32_t) * n));
   SC(cudaMalloc((void **)&segid, sizeof(int64_t) * (n + 1)));
