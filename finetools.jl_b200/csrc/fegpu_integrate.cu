@@ -11,6 +11,8 @@
 // At the end the triangle is mirrored (complete_lt! :164) and written in the reference's emission order
 // (AssemblyModule.jl:261-280: column-major, p = e*EM*EM + (j-1)*EM + i) as values only -- the (I,J) keys are
 // implied by conn + dofnums and never materialised on the fast path.
+#include <cstdlib>
+
 #include "fegpu_internal.h"
 
 namespace {
@@ -325,7 +327,8 @@ int32_t dispatch_form(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
 
 }  // namespace
 
-int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool *handled);  // fegpu_h8.cu
+int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool *handled);             // fegpu_h8.cu
+int32_t fe_integrate_elastic_tiled(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool *handled);  // fegpu_elastic.cu
 
 int32_t fe_integrate(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
   if (mesh->npts <= 0) return fegpu_fail(mesh->ctx, FEGPU_ERR_STATE, "no quadrature rule set (fegpu_rule_set)");
@@ -333,6 +336,15 @@ int32_t fe_integrate(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
     bool handled = false;
     FE_TRY(fe_integrate_h8(mesh, fa, d_V, &handled));
     if (handled) return FEGPU_OK;
+  }
+  if (fa.form == FORM_ELASTIC && mesh->sdim == 3 && mesh->mdim == 3) {
+    // register-tiled kernel (fegpu_elastic.cu); FEGPU_ELASTIC_TILED=0 keeps the entry-per-thread kernel for A/B measurements
+    static const bool tiled_off = std::getenv("FEGPU_ELASTIC_TILED") && std::atoi(std::getenv("FEGPU_ELASTIC_TILED")) == 0;
+    if (!tiled_off) {
+      bool handled = false;
+      FE_TRY(fe_integrate_elastic_tiled(mesh, fa, d_V, &handled));
+      if (handled) return FEGPU_OK;
+    }
   }
   switch (mesh->etype) {
     case FEGPU_T3:

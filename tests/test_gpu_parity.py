@@ -558,3 +558,34 @@ def test_ffblock_assembler_and_matrix_blocked(fe, orc, gpu_ctx):
     assert_parity(orc.matrix_block(orc.sparse(I, J, V, 4, 4), 1, 3, 1, 2), got)
     with pytest.raises(fe.FEGPUError, match="too many rows"):
         fe.matrix_blocked_ff(a, n + 1)
+
+
+@pytest.mark.parametrize("et,rule_order", [("H8", 3), ("T10", None), ("H20", None), ("T4", None)])
+def test_elastic_sort_path_full_layout(fe, orc, gpu_ctx, et, rule_order):
+    """Elasticity through the generic sort path (a dof shared by two nodes rules out the mesh-structured pattern): the
+    integration kernels then write full element matrices in emission order, including H8 with a rule the dedicated H8
+    kernel does not take (3x3x3)."""
+    fens, fes = _mesh(fe, et, 2)
+    _distort(fens)
+    u = make_field(fe, fens, 3)
+    u.dofnums[u.dofnums == u.nalldofs()] = 2
+    rule = fe.GaussRule(3, rule_order) if rule_order else _rule(fe, et)
+    C = isotropic_C()
+    C[1, 4] = C[4, 1] = -0.07
+    ref, _ = oracle_csc(orc, "elastic", et, fes, fens, u, rule, C)
+    got, _ = gpu_csc(fe, "elastic", fes, fens, u, rule, C)
+    assert_parity(ref, got)
+
+
+def test_elastic_h8_gauss3_structured_path(fe, orc, gpu_ctx):
+    """H8 with GaussRule(3,3): the register-tiled elasticity kernel writing the compact layout."""
+    fens, fes = _mesh(fe, "H8", 3)
+    _distort(fens)
+    u = make_field(fe, fens, 3)
+    rule = fe.GaussRule(3, 3)
+    ref, (I, J, V) = oracle_csc(orc, "elastic", "H8", fes, fens, u, rule, isotropic_C())
+    got, a = gpu_csc(fe, "elastic", fes, fens, u, rule, isotropic_C())
+    assert_parity(ref, got)
+    gi, gj, gv = a.coo()                       # raw-COO export expands the compact layout back to emission order
+    assert np.array_equal(gi, I) and np.array_equal(gj, J)
+    assert np.abs(gv - V).max() <= 1e-12 * np.abs(V).max()
