@@ -518,7 +518,7 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
   // 2. element integration.  Symmetric forms on the mesh-structured path write only the upper block triangle
   FormArgs fa2 = fa;
   static const bool compact_off = std::getenv("FEGPU_COMPACT") && std::atoi(std::getenv("FEGPU_COMPACT")) == 0;  // A/B knob
-  fa2.compact = fast && fe_form_symmetric(fa.form) && !compact_off;
+  fa2.compact = fast && fe_integrate_supports_compact(mesh, fa) && !compact_off;
   const int64_t per_elem = fa2.compact ? fe_compact_size(mesh->nne, fa.ndn) : (int64_t)EM * EM;
   FE_TRY(fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(mesh->nactive * per_elem, 1)));
   as->V_n = ntrip;

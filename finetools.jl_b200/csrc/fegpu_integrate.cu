@@ -330,8 +330,16 @@ int32_t dispatch_form(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
 int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool *handled);             // fegpu_h8.cu
 int32_t fe_integrate_elastic_tiled(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool *handled);  // fegpu_elastic.cu
 
+bool fe_dot_scalar_applies(const fegpu_mesh *mesh, const FormArgs &fa);              // fegpu_dot.cu
+int32_t fe_integrate_dot_scalar(fegpu_mesh *mesh, const FormArgs &fa, double *d_V);  // fegpu_dot.cu
+
+bool fe_integrate_supports_compact(const fegpu_mesh *mesh, const FormArgs &fa) {
+  return fe_form_symmetric(fa.form) || fe_dot_scalar_applies(mesh, fa);  // a 1 x 1 coefficient makes bilform_dot symmetric
+}
+
 int32_t fe_integrate(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
   if (mesh->npts <= 0) return fegpu_fail(mesh->ctx, FEGPU_ERR_STATE, "no quadrature rule set (fegpu_rule_set)");
+  if (fe_dot_scalar_applies(mesh, fa)) return fe_integrate_dot_scalar(mesh, fa, d_V);
   if (mesh->etype == FEGPU_H8) {
     bool handled = false;
     FE_TRY(fe_integrate_h8(mesh, fa, d_V, &handled));

@@ -141,6 +141,8 @@ struct FormArgs {
 static inline int fe_compact_size(int nne, int ndn) { return nne * (nne + 1) / 2 * ndn * ndn; }
 static inline bool fe_form_symmetric(int form) { return form != 3 /* FORM_DOT */; }
 int32_t fe_integrate(fegpu_mesh *mesh, const FormArgs &fa, double *d_V);
+// does the integration kernel that will run write the compact symmetric layout when fa.compact is set?
+bool fe_integrate_supports_compact(const fegpu_mesh *mesh, const FormArgs &fa);
 
 // ---- pattern + gather (fegpu_pattern.cu) ---------------------------------------------------------------
 int32_t fe_pattern_build(fegpu_dofmap *dm);

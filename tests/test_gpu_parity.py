@@ -589,3 +589,17 @@ def test_elastic_h8_gauss3_structured_path(fe, orc, gpu_ctx):
     gi, gj, gv = a.coo()                       # raw-COO export expands the compact layout back to emission order
     assert np.array_equal(gi, I) and np.array_equal(gj, J)
     assert np.abs(gv - V).max() <= 1e-12 * np.abs(V).max()
+
+
+@pytest.mark.parametrize("et", ["Q4", "T3"])
+def test_planar_dot_parity(fe, orc, gpu_ctx, et):
+    """Mass matrix of a planar (sdim = 2) mesh, m = 2 and m = 3 with a non-unit other dimension (thickness)."""
+    fens, fes = (fe.Q4block(2.0, 1.0, 5, 4) if et == "Q4" else fe.T3block(2.0, 1.0, 5, 4))
+    fens.xyz[:, 0] += 0.03 * np.sin(3 * fens.xyz[:, 1])
+    u = make_field(fe, fens, 1)
+    rule = fe.GaussRule(2, 2) if et == "Q4" else fe.TriRule(3)
+    c = np.array([[2.5]])
+    for m in (2, 3):
+        ref, _ = oracle_csc(orc, "dot", et, fes, fens, u, rule, c, m=m, otherdim=1.0)
+        got, _ = gpu_csc(fe, "dot", fes, fens, u, rule, c, m=m)
+        assert_parity(ref, got)
