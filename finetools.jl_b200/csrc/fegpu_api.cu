@@ -500,6 +500,7 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
   const int EM = mesh->nne * fa.ndn;
   const int64_t ntrip = mesh->nactive * (int64_t)EM * EM;
   as->have_result = false;
+  as->pat_src = nullptr;
   as->view.active = false;
   as->started = false;
   // 1. symbolic phase first (cached in the dof map): it decides the layout the integration kernel writes
@@ -536,6 +537,7 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
     as->ncols = dm->col_nall;
     as->d_colptr = fe_pattern_colptr(dm->pat);
     as->d_rowval = fe_pattern_rowval(dm->pat);
+    as->pat_src = dm->pat;
   } else {
     if (mesh->partitioned) return fegpu_fail(ctx, FEGPU_ERR_ARG, "row-block partitioning needs an injective dof map and non-degenerate elements");
     int64_t *dI = nullptr, *dJ = nullptr;
@@ -694,6 +696,7 @@ int32_t fegpu_makematrix(fegpu_asm *as) {
 #undef GT
   as->ev_valid = true;
   as->have_result = true;
+  as->pat_src = nullptr;
   as->pattern_cached = false;
   as->view.active = false;
   as->V_compact = false;

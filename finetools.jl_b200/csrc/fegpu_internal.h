@@ -69,6 +69,7 @@ struct fegpu_asm {
   int64_t nrows = 0, ncols = 0, nnz = 0;
   const int64_t *d_colptr = nullptr;  // borrowed from a Pattern or == own_colptr
   const int64_t *d_rowval = nullptr;
+  const Pattern *pat_src = nullptr;   // the pattern d_colptr/d_rowval are borrowed from (nullptr: the assembler's own arrays)
   double *d_nzval = nullptr;
   size_t nz_cap = 0;
   int64_t *own_colptr = nullptr, *own_rowval = nullptr;
@@ -150,6 +151,9 @@ void fe_pattern_free(Pattern *p);
 int64_t fe_pattern_nnz(const Pattern *p);
 const int64_t *fe_pattern_colptr(const Pattern *p);
 const int64_t *fe_pattern_rowval(const Pattern *p);
+// compressed row structure for the transport (false when the pattern keeps none): per-node ascending neighbour lists + dof map
+bool fe_pattern_compressed(const Pattern *p, const int32_t **nbr, const int64_t **nbrptr, int64_t *total_nbr, const int32_t **dof, int *ndn,
+                           int64_t *nnodes);
 bool fe_pattern_usable(const fegpu_dofmap *dm);  // mesh-structured fast path applicable?
 int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_nzval);
 // compact symmetric layout -> full element matrices in emission order (raw-COO export only)

@@ -33,6 +33,13 @@ struct Pattern {
   uint16_t *d_rank = nullptr;     // per node nnbr*ndn entries at nbrptr[n]*ndn, nullptr when identity everywhere
   int32_t *d_order = nullptr;     // node visiting order of the gather: the active nodes in Morton order of their coordinates
   int64_t norder = 0;             // (nullptr = all nodes, natural order)
+  // compressed form of rowval for the result transport (vector fields whose node-major dof order is ascending everywhere):
+  // the rows of every column of node n are { dof[p][nbr[nbrptr[n] + s]] + 1 : s ascending, p ascending }
+  int32_t *d_nbr = nullptr;       // [total_nbr] neighbour nodes, ascending per node
+  int64_t total_nbr = 0;
+  const int32_t *d_dof = nullptr; // borrowed from the dof map that owns this pattern
+  int ndn = 0;
+  int64_t nnodes = 0;
   int maxdeg = 0, maxcand = 0, maxnbr = 0;
   cudaStream_t stream = 0;
 };
@@ -283,6 +290,183 @@ __global__ void __launch_bounds__(WPB * 32) k_nbr(SymParams S, const int64_t *__
   }
 }
 
+// Bitonic sort of 32*KPL uint32 keys held KPL per lane in LANE-MAJOR order (position i = lane*KPL + r), ascending.  The
+// stages with j < KPL compare registers of one lane (no shuffle); the others exchange register r with lane ^ (j/KPL).
+template <int KPL>
+__device__ __forceinline__ void reg_bitonic_lm(uint32_t (&v)[KPL], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * KPL; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j < KPL) {
+#pragma unroll
+        for (int r = 0; r < KPL; r++) {
+          const int rp = r ^ j;
+          if (rp > r) {
+            const bool up = (((lane * KPL + r) & k) == 0);
+            const uint32_t lo = min(v[r], v[rp]), hi = max(v[r], v[rp]);
+            v[r] = up ? lo : hi;
+            v[rp] = up ? hi : lo;
+          }
+        }
+      } else {
+        const int lj = j / KPL;
+        const bool take_min = (((lane & lj) == 0) == (((lane * KPL) & k) == 0));
+#pragma unroll
+        for (int r = 0; r < KPL; r++) {
+          const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], lj);
+          v[r] = take_min ? min(v[r], o) : max(v[r], o);
+        }
+      }
+    }
+  }
+}
+
+// Neighbour lists of one node from packed keys (node << KB | candidate index), everything in registers.
+//   keys: candidate k = a*nne + li of the node's adjacent element a (ascending element order) -> (conn[el_a][li] << KB) | k;
+//         rows not owned by this rank keep k but carry the all-ones node field; padding is all ones
+//   sort (lane-major bitonic network), head flags by comparing node fields of consecutive positions, slot = number of heads
+//   before the position; every sorted key scatters its slot to cslot[k] (no search), heads write the unique list U.
+template <int KPL, bool CHECK>
+__device__ __forceinline__ void nbr_node(const SymParams &S, const int64_t n, const int64_t ab, const int deg, const int lane, const int KB,
+                                         const int32_t *__restrict__ adj_slot, int32_t *__restrict__ nnbr_out, int32_t *__restrict__ U,
+                                         uint16_t *__restrict__ cslot, uint8_t *__restrict__ sorted_flag, int *any_unsorted, int32_t *smF,
+                                         int32_t *smL) {
+  const int nne = S.nne;
+  const int ncand = deg * nne;
+  const uint32_t nne_magic = 65536u / (uint32_t)nne + 1u;  // k / nne == (k * magic) >> 16 for k < 2048 (nne <= 32)
+  const uint32_t kmask = (1u << KB) - 1u, dropped = 0xffffffffu >> KB;
+  uint32_t el = 0;
+  if (lane < deg) {
+    const int64_t slot = adj_slot[ab + lane];
+    el = (uint32_t)(S.elem_list ? S.elem_list[slot] : slot);
+  }
+  uint32_t v[KPL];
+#pragma unroll
+  for (int r = 0; r < KPL; r++) {
+    const int k = r * 32 + lane;  // coalesced reads of the connectivity rows
+    const int a = (k < ncand) ? (int)(((uint32_t)k * nne_magic) >> 16) : 0;
+    const uint32_t e = __shfl_sync(0xffffffffu, el, a);
+    uint32_t key = 0xffffffffu;
+    if (k < ncand) {
+      const int li = k - a * nne;
+      uint32_t m = (uint32_t)S.conn[(int64_t)e * nne + li];
+      if (S.rowowned && !S.rowowned[m]) m = dropped;
+      key = (m << KB) | (uint32_t)k;
+    }
+    v[r] = key;
+  }
+  reg_bitonic_lm<KPL>(v, lane);
+  // heads: position i = lane*KPL + r; the predecessor of r = 0 is the last register of the previous lane
+  const uint32_t prev_lane_last = __shfl_up_sync(0xffffffffu, v[KPL - 1], 1);
+  bool head[KPL];
+  unsigned bal[KPL];
+  int nu = 0;
+#pragma unroll
+  for (int r = 0; r < KPL; r++) {
+    const uint32_t node = v[r] >> KB;
+    const uint32_t pnode = (r == 0) ? (prev_lane_last >> KB) : (v[r - 1] >> KB);
+    head[r] = (node != dropped) && ((r == 0 && lane == 0) || node != pnode);
+    bal[r] = __ballot_sync(0xffffffffu, head[r]);
+    nu += __popc(bal[r]);
+  }
+  // heads at positions before (lane, r): all registers of the lower lanes + registers r' <= r of this lane
+  const unsigned lt = (1u << lane) - 1u;
+  int before = 0;
+#pragma unroll
+  for (int r = 0; r < KPL; r++) before += __popc(bal[r] & lt);
+  uint16_t *cs = cslot + ab * nne;
+  int32_t *Un = U + ab * nne;
+  bool ok = true;
+#pragma unroll
+  for (int r = 0; r < KPL; r++) {
+    before += head[r] ? 1 : 0;
+    const uint32_t node = v[r] >> KB, k = v[r] & kmask;
+    if ((int)k < ncand) {  // padding carries k = 2^KB - 1 >= ncand (a node with ncand == 2^KB has no padding)
+      if (node == dropped) cs[k] = 0xffffu;
+      else cs[k] = (uint16_t)(before - 1);
+    }
+    if (head[r]) {
+      Un[before - 1] = (int32_t)node;
+      if (CHECK) {
+        int prev = S.dof[node];
+        smF[before - 1] = prev;
+        for (int p = 1; p < S.ndn; p++) {
+          const int d = S.dof[(int64_t)p * S.nnodes + node];
+          if (d <= prev) ok = false;
+          prev = d;
+        }
+        smL[before - 1] = prev;
+      }
+    }
+  }
+  if (CHECK) {
+    __syncwarp();
+    for (int s = lane; s + 1 < nu; s += 32)
+      if (smF[s + 1] <= smL[s]) ok = false;
+    ok = __all_sync(0xffffffffu, ok);
+    __syncwarp();
+  }
+  if (lane == 0) {
+    nnbr_out[n] = nu;
+    if (CHECK) {
+      sorted_flag[n] = ok ? 1 : 0;
+      if (!ok) *any_unsorted = 1;
+    }
+  }
+}
+
+// One warp per node, register-only version of k_nbr.  Preconditions (checked by the host): maxdeg <= 32, node ids and candidate
+// indices fit one 32-bit key (nnodes <= 2^(32-KB) - 2 with 2^KB >= padded candidates).  CHECK = false when the dof map is
+// node-major ascending everywhere (k_dof_monotone): no per-node order test, sorted_flag is not written.
+template <int MAXKPL, bool CHECK>
+__global__ void __launch_bounds__(WPB * 32) k_nbr_fast(SymParams S, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ adj_slot,
+                                                       int capc, int KB, int32_t *__restrict__ nnbr_out, int32_t *__restrict__ U,
+                                                       uint16_t *__restrict__ cslot, uint8_t *__restrict__ sorted_flag, int *any_unsorted) {
+  extern __shared__ int32_t sfl[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int32_t *smF = CHECK ? sfl + (size_t)w * 2 * capc : nullptr;
+  int32_t *smL = CHECK ? smF + capc : nullptr;
+  const int nne = S.nne;
+  for (int64_t idx = (int64_t)blockIdx.x * WPB + w; idx < S.na; idx += (int64_t)gridDim.x * WPB) {
+    const int64_t n = active_node(S, idx);
+    const int64_t ab = adjptr[n];
+    const int deg = (int)(adjptr[n + 1] - ab);
+    if (deg == 0) {
+      if (lane == 0) {
+        nnbr_out[n] = 0;
+        if (CHECK) sorted_flag[n] = 1;
+      }
+      continue;
+    }
+    const int ncand = deg * nne;
+#define NBR_ARGS S, n, ab, deg, lane, KB, adj_slot, nnbr_out, U, cslot, sorted_flag, any_unsorted, smF, smL
+    // MAXKPL (from the mesh's largest candidate count) bounds the variants compiled in, and with them the register count
+    if (ncand <= 32) nbr_node<1, CHECK>(NBR_ARGS);
+    else if (MAXKPL <= 2 || ncand <= 64) nbr_node<2, CHECK>(NBR_ARGS);
+    else if (MAXKPL <= 4 || ncand <= 128) nbr_node<4, CHECK>(NBR_ARGS);
+    else if (ncand <= 256) nbr_node<8, CHECK>(NBR_ARGS);
+    else nbr_node<16, CHECK>(NBR_ARGS);
+#undef NBR_ARGS
+  }
+}
+
+// is the dof map node-major ascending (dofs of a node ascending by component, below every dof of the next node)?  Then the
+// rows of every column are ascending in (neighbour, component) order and no node needs an order test or a rank table.
+__global__ void k_dof_monotone(const int32_t *__restrict__ dof, int64_t nnodes, int ndn, int *violated) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnodes) return;
+  int prev = dof[n];
+  bool bad = false;
+  for (int p = 1; p < ndn; p++) {
+    const int d = dof[(int64_t)p * nnodes + n];
+    bad = bad || d <= prev;
+    prev = d;
+  }
+  if (n + 1 < nnodes && dof[n + 1] <= prev) bad = true;
+  if (bad) *violated = 1;
+}
+
 __global__ void k_col_counts(SymParams S, const int32_t *nnbr, int64_t *colcount) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S.nnodes * S.ndn) return;
@@ -298,7 +482,7 @@ template <int LPN, int NDN>
 __global__ void __launch_bounds__(256) k_rows_sorted(SymParams S, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ nnbr,
                                                      const int64_t *__restrict__ nbrptr, const int32_t *__restrict__ U,
                                                      const uint8_t *__restrict__ sorted_flag, const int64_t *__restrict__ colptr,
-                                                     int64_t *__restrict__ rowval, uint16_t *__restrict__ rank) {
+                                                     int64_t *__restrict__ rowval, uint16_t *__restrict__ rank, int32_t *__restrict__ nbr_compact) {
   constexpr int QMAX = (NDN > 0) ? NDN : 6;
   constexpr int UNR = 4;  // row chunks whose neighbour -> dof loads are issued together
   const int ndn = (NDN > 0) ? NDN : S.ndn;
@@ -315,7 +499,9 @@ __global__ void __launch_bounds__(256) k_rows_sorted(SymParams S, const int64_t 
   if (nu == 0 || !sf) return;
   const int32_t *Un = U + ab * S.nne;
   const int nr = nu * ndn;
-  const int64_t nb = rank ? nbrptr[n] : 0;
+  const int64_t nb = (rank || nbr_compact) ? nbrptr[n] : 0;
+  if (nbr_compact)
+    for (int s = gl; s < nu; s += LPN) nbr_compact[nb + s] = Un[s];
   for (int i0 = 0; i0 < nr; i0 += UNR * LPN) {
     int64_t rdof[UNR];
 #pragma unroll
@@ -576,7 +762,7 @@ int32_t dalloc(fegpu_ctx *ctx, T **p, size_t n) {
 void fe_pattern_free(Pattern *p) {
   if (!p) return;
   cudaStream_t st = p->stream;  // stream-ordered frees: blocks go back to the pool, no device synchronisation
-  void *ptrs[] = {p->d_colptr, p->d_rowval, p->d_adjptr, p->d_adj_slot, p->d_adj_lc, p->d_nnbr, p->d_nbrptr, p->d_cslot, p->d_rank, p->d_order};
+  void *ptrs[] = {p->d_colptr, p->d_rowval, p->d_adjptr, p->d_adj_slot, p->d_adj_lc, p->d_nnbr, p->d_nbrptr, p->d_cslot, p->d_rank, p->d_order, p->d_nbr};
   for (void *q : ptrs)
     if (q) cudaFreeAsync(q, st);
   delete p;
@@ -584,6 +770,12 @@ void fe_pattern_free(Pattern *p) {
 int64_t fe_pattern_nnz(const Pattern *p) { return p->nnz; }
 const int64_t *fe_pattern_colptr(const Pattern *p) { return p->d_colptr; }
 const int64_t *fe_pattern_rowval(const Pattern *p) { return p->d_rowval; }
+bool fe_pattern_compressed(const Pattern *p, const int32_t **nbr, const int64_t **nbrptr, int64_t *total_nbr, const int32_t **dof, int *ndn,
+                           int64_t *nnodes) {
+  if (!p || !p->d_nbr) return false;
+  *nbr = p->d_nbr; *nbrptr = p->d_nbrptr; *total_nbr = p->total_nbr; *dof = p->d_dof; *ndn = p->ndn; *nnodes = p->nnodes;
+  return true;
+}
 
 bool fe_pattern_usable(const fegpu_dofmap *dm) {
   return dm->injective && !dm->mesh->degenerate && dm->row_nall == dm->col_nall && dm->mesh->nne <= 32;
@@ -607,7 +799,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
   int32_t *d_deg = nullptr, *d_cursor = nullptr, *d_U = nullptr, *d_aflag = nullptr, *d_anodes = nullptr;
   int64_t *d_apos = nullptr;
   uint8_t *d_sorted = nullptr;
-  int *d_flags = nullptr;  // [0] degenerate, [1] some node needs a dof sort
+  int *d_flags = nullptr;  // [0] degenerate, [1] some node needs a dof sort, [2] the dof map is not node-major ascending
   auto cleanup = [&]() {
     void *ptrs[] = {d_deg, d_cursor, d_U, d_sorted, d_flags, d_aflag, d_anodes, d_apos};
     for (void *q : ptrs)
@@ -624,10 +816,14 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
 #define PC(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fegpu_fail(ctx, FEGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
   PT(dalloc(ctx, &d_deg, nn));
   PT(dalloc(ctx, &d_cursor, nn));
-  PT(dalloc(ctx, &d_flags, 2));
+  PT(dalloc(ctx, &d_flags, 3));
   PC(cudaMemsetAsync(d_deg, 0, sizeof(int32_t) * nn, st));
   PC(cudaMemsetAsync(d_cursor, 0, sizeof(int32_t) * nn, st));
-  PC(cudaMemsetAsync(d_flags, 0, sizeof(int) * 2, st));
+  PC(cudaMemsetAsync(d_flags, 0, sizeof(int) * 3, st));
+  if (nn > 0) {
+    k_dof_monotone<<<grid_for(nn, 256), 256, 0, st>>>(dm->d_dof, nn, ndn, d_flags + 2);
+    ctx->launches++;
+  }
   if (nadj > 0) {
     k_count_adj<<<grid_for(nadj, 256), 256, 0, st>>>(S, d_deg, d_flags);
     ctx->launches++;
@@ -652,10 +848,11 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
       S.na = na;
     }
   }
-  int h_flags[2] = {0, 0};
-  PC(cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+  int h_flags[3] = {0, 0, 0};
+  PC(cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * 3, cudaMemcpyDeviceToHost, st));
   PC(cudaStreamSynchronize(st));
   if (h_flags[0]) return bail();
+  const bool monotone = h_flags[2] == 0;
   if (maxdeg < 1) maxdeg = 1;
   P->maxdeg = maxdeg;
   P->maxcand = maxdeg * nne;
@@ -682,21 +879,40 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
   }
   unsigned gridn = (unsigned)std::min<int64_t>((S.na + WPB - 1) / WPB, (int64_t)ctx->sm_count * 64);
   if (gridn == 0) gridn = 1;
+  int KB = 5;
+  while ((1 << KB) < capc) KB++;
+  static const bool nbr_fast_off = std::getenv("FEGPU_NBR_FAST") && std::atoi(std::getenv("FEGPU_NBR_FAST")) == 0;  // A/B knob
+  const bool nbr_fast = !nbr_fast_off && maxdeg <= 32 && capc <= 512 && (uint64_t)nn <= (uint64_t)(0xffffffffu >> KB);
+  if (nbr_fast) {
+    // register-only kernel; the per-node order test (and its shared memory) only when the dof map is not node-major ascending
+    const size_t smf = monotone ? 0 : (size_t)WPB * 2 * capc * sizeof(int32_t);
+#define LAUNCH_FAST(M)                                                                                                              \
+  do {                                                                                                                              \
+    if (monotone) k_nbr_fast<M, false><<<gridn, WPB * 32, 0, st>>>(S, P->d_adjptr, P->d_adj_slot, capc, KB, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1); \
+    else k_nbr_fast<M, true><<<gridn, WPB * 32, smf, st>>>(S, P->d_adjptr, P->d_adj_slot, capc, KB, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1);       \
+  } while (0)
+    if (capc <= 64) LAUNCH_FAST(2);
+    else if (capc <= 128) LAUNCH_FAST(4);
+    else LAUNCH_FAST(16);
+#undef LAUNCH_FAST
+    if (monotone) PC(cudaMemsetAsync(d_sorted, 1, nn, st));  // every node is in order; the kernel did not write the flags
+  } else {
 #define LAUNCH_NBR(N)                                                                                                  \
   do {                                                                                                                 \
     PC(cudaFuncSetAttribute(k_nbr<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));                      \
     k_nbr<N><<<gridn, WPB * 32, smem1, st>>>(S, P->d_adjptr, P->d_adj_slot, maxdeg, capc, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1); \
   } while (0)
-  switch (nne) {
-    case 3: LAUNCH_NBR(3); break;
-    case 4: LAUNCH_NBR(4); break;
-    case 8: LAUNCH_NBR(8); break;
-    case 10: LAUNCH_NBR(10); break;
-    case 20: LAUNCH_NBR(20); break;
-    case 27: LAUNCH_NBR(27); break;
-    default: LAUNCH_NBR(0); break;
-  }
+    switch (nne) {
+      case 3: LAUNCH_NBR(3); break;
+      case 4: LAUNCH_NBR(4); break;
+      case 8: LAUNCH_NBR(8); break;
+      case 10: LAUNCH_NBR(10); break;
+      case 20: LAUNCH_NBR(20); break;
+      case 27: LAUNCH_NBR(27); break;
+      default: LAUNCH_NBR(0); break;
+    }
 #undef LAUNCH_NBR
+  }
   ctx->launches++;
   PT(dalloc(ctx, &P->d_nbrptr, nn + 1));
   int64_t total_nbr = 0;
@@ -723,6 +939,9 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
   const bool need_rank = h_flags[1] != 0;
   PT(dalloc(ctx, &P->d_rowval, (size_t)P->nnz));
   if (need_rank) PT(dalloc(ctx, &P->d_rank, (size_t)(total_nbr * ndn)));
+  P->total_nbr = total_nbr; P->d_dof = dm->d_dof; P->ndn = ndn; P->nnodes = nn;
+  // neighbour lists kept for the transport: only where they are smaller than int32 row indices (ndn^2 columns-rows per pair)
+  if (!need_rank && ndn >= 2 && total_nbr > 0) PT(dalloc(ctx, &P->d_nbr, (size_t)total_nbr));
   int cap2 = 32;
   while (cap2 < P->maxnbr * ndn) cap2 <<= 1;
   const size_t smem2 = need_rank ? (size_t)WPB * cap2 * sizeof(unsigned long long) : 0;
@@ -735,7 +954,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
     int rl = (ndn >= 3) ? 32 : (ndn == 2 ? 16 : 8);
     if (lpn_env == 8 || lpn_env == 16 || lpn_env == 32) rl = lpn_env;
     const unsigned gr = grid_for(S.na * rl, 256);
-#define ROWS_ARGS S, P->d_adjptr, P->d_nnbr, P->d_nbrptr, d_U, d_sorted, P->d_colptr, P->d_rowval, P->d_rank
+#define ROWS_ARGS S, P->d_adjptr, P->d_nnbr, P->d_nbrptr, d_U, d_sorted, P->d_colptr, P->d_rowval, P->d_rank, P->d_nbr
 #define ROWS_L(N)                                                              \
   do {                                                                         \
     if (rl == 8) k_rows_sorted<8, N><<<gr, 256, 0, st>>>(ROWS_ARGS);           \

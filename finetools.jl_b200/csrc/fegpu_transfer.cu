@@ -59,11 +59,19 @@ class HostPool {
   int size() const { return n_; }
   // runs fn(tid, nthreads) on every worker and returns when all are done
   void run(const std::function<void(int, int)> &fn) {
-    std::unique_lock<std::mutex> lk(mu_);
+    start(fn);
+    wait();
+  }
+  // asynchronous form: fn must stay alive until wait() returns
+  void start(const std::function<void(int, int)> &fn) {
+    std::lock_guard<std::mutex> lk(mu_);
     fn_ = &fn;
     pending_ = n_;
     gen_++;
     cv_.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(mu_);
     done_.wait(lk, [this] { return pending_ == 0; });
     fn_ = nullptr;
   }
@@ -127,6 +135,76 @@ void widen_scalar(const int32_t *src, int64_t *dst, size_t n) {
   for (size_t i = 0; i < n; i++) dst[i] = src[i];
 }
 
+// dst <- src (n int64) with non-temporal stores (full 32-byte stores on the aligned body; callers pass long runs, a short
+// run would leave partially filled write-combining buffers, which is far slower than cached stores)
+__attribute__((target("avx2"))) void stream_copy_avx2(int64_t *dst, const int64_t *src, size_t n) {
+  size_t i = 0;
+  while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 63)) { dst[i] = src[i]; i++; }
+  for (; i + 8 <= n; i += 8) {
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i)));
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 4), _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 4)));
+  }
+  for (; i < n; i++) dst[i] = src[i];
+}
+
+// Collects the row lists a thread produces while their destinations are consecutive in rowval (they are whenever the
+// columns of consecutive nodes are consecutive, i.e. for node-major numberings) and writes them out as long streams.
+struct RowSink {
+  static constexpr size_t CAP = 16384;  // int64 entries (128 KB, L2 resident)
+  std::vector<int64_t> buf;
+  size_t n = 0;
+  int64_t *start = nullptr;
+  bool avx2;
+  explicit RowSink(bool a) : buf(CAP), avx2(a) {}
+  void flush() {
+    if (!n) return;
+    if (avx2 && n >= 64) stream_copy_avx2(start, buf.data(), n);
+    else std::memcpy(start, buf.data(), n * sizeof(int64_t));
+    n = 0;
+  }
+  void put(int64_t *dst, const int64_t *src, size_t len) {
+    if (len > CAP) { flush(); std::memcpy(dst, src, len * sizeof(int64_t)); return; }
+    if (n && (dst != start + n || n + len > CAP)) flush();
+    if (!n) start = dst;
+    std::memcpy(buf.data() + n, src, len * sizeof(int64_t));
+    n += len;
+  }
+};
+
+// Row indices of the columns of nodes [n_lo, n_hi) from the compressed pattern: the rows of every column of node n are the
+// dofs of its neighbour nodes in (neighbour ascending, component ascending) order -- the same list for the node's ndn
+// columns.  A decoder of what the device's symbolic phase produced (k_nbr / k_rows_sorted), not a pattern computation: no
+// connectivity is touched on the host.
+void expand_rows(const int32_t *nbr, const int64_t *nbrptr, const int32_t *dof, int ndn, int64_t nnodes, const int64_t *colptr, int64_t *rowval,
+                 int64_t n_lo, int64_t n_hi, bool avx2) {
+  std::vector<int64_t> rows;
+  RowSink sink(avx2);
+  for (int64_t n = n_lo; n < n_hi; n++) {
+    const int64_t b = nbrptr[n], nu = nbrptr[n + 1] - b;
+    if (nu == 0) continue;
+    const size_t nr = (size_t)nu * ndn;
+    if (rows.size() < nr) rows.resize(nr);
+    int64_t *r = rows.data();
+    if (ndn == 3) {
+      const int32_t *d0 = dof, *d1 = dof + nnodes, *d2 = dof + 2 * nnodes;
+      for (int64_t s = 0; s < nu; s++) {
+        const int32_t m = nbr[b + s];
+        r[3 * s] = (int64_t)d0[m] + 1;
+        r[3 * s + 1] = (int64_t)d1[m] + 1;
+        r[3 * s + 2] = (int64_t)d2[m] + 1;
+      }
+    } else {
+      for (int64_t s = 0; s < nu; s++) {
+        const int32_t m = nbr[b + s];
+        for (int p = 0; p < ndn; p++) r[s * ndn + p] = (int64_t)dof[(int64_t)p * nnodes + m] + 1;
+      }
+    }
+    for (int q = 0; q < ndn; q++) sink.put(rowval + (colptr[dof[(int64_t)q * nnodes + n]] - 1), r, nr);
+  }
+  sink.flush();
+  _mm_sfence();
+}
+
 }  // namespace
 
 struct Transfer {
@@ -139,9 +217,17 @@ struct Transfer {
   int simd = 0;                            // 0 scalar, 1 AVX2, 2 AVX-512
   size_t chunk_bytes = XF_CHUNK_MAX;       // FEGPU_XFER_CHUNK_MB (tuning knob, <= 32)
   bool narrow = true;                      // FEGPU_XFER_NARROW=0: plain int64 DMA (A/B measurements)
+  int widen_threads = 4;                   // threads of the pool that widen / copy staged chunks
+  bool compress = true;                    // FEGPU_XFER_COMPRESS=0: never send neighbour lists instead of row indices
   int64_t staged = 0, bypassed = 0;        // chunk counters (diagnostics)
+  int64_t compressed = 0;                  // results whose row indices were rebuilt from neighbour lists
+  void *h_meta = nullptr;                  // pinned: neighbour lists, their offsets, the dof map, colptr
+  size_t meta_cap = 0;
+  cudaEvent_t meta_done = nullptr;
   ~Transfer() {
     delete pool;
+    if (h_meta) cudaFreeHost(h_meta);
+    if (meta_done) cudaEventDestroy(meta_done);
     for (int b = 0; b < XF_NBUF; b++) {
       if (d_stage[b]) cudaFree(d_stage[b]);
       if (h_stage[b]) cudaFreeHost(h_stage[b]);
@@ -160,6 +246,7 @@ static int32_t transfer_get(fegpu_ctx *ctx, Transfer **out) {
   ctx->xfer = t;  // owned by the context from here on (also on error paths)
   CUDA_TRY(ctx, cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
   CUDA_TRY(ctx, cudaEventCreateWithFlags(&t->ready, cudaEventDisableTiming));
+  CUDA_TRY(ctx, cudaEventCreateWithFlags(&t->meta_done, cudaEventDisableTiming));
   for (int b = 0; b < XF_NBUF; b++) {
     CUDA_TRY(ctx, cudaEventCreateWithFlags(&t->done[b], cudaEventDisableTiming));
     CUDA_TRY(ctx, cudaMalloc(&t->d_stage[b], XF_CHUNK_MAX));
@@ -167,8 +254,12 @@ static int32_t transfer_get(fegpu_ctx *ctx, Transfer **out) {
   }
   int nt = (int)std::thread::hardware_concurrency();
   if (nt < 1) nt = 1;
-  nt = std::min(nt, 4);  // measured on the B200 hosts: 4 threads keep up with the link; more only steal memory bandwidth from the DMA
+  // measured on the B200 hosts (profiles/r01_xfer_sweep.jsonl, r01_xfer_compress.jsonl): widening int32 chunks is fastest with 4
+  // threads (more only steal memory bandwidth from the DMA); decoding row indices from neighbour lists (non-temporal streams) is at the nzval DMA time with 4-8
+  nt = std::min(nt, 8);
   if (const char *e = std::getenv("FEGPU_HOST_THREADS")) nt = std::max(1, std::atoi(e));
+  t->widen_threads = std::min(nt, 4);
+  if (const char *e = std::getenv("FEGPU_WIDEN_THREADS")) t->widen_threads = std::max(1, std::min(nt, std::atoi(e)));
   t->pool = new HostPool(nt);
   __builtin_cpu_init();
   t->simd = __builtin_cpu_supports("avx2") ? 1 : 0;  // AVX-512 (FEGPU_XFER_SIMD=2) measured no faster: the loop is memory-bound
@@ -176,6 +267,7 @@ static int32_t transfer_get(fegpu_ctx *ctx, Transfer **out) {
   else if (const char *e = std::getenv("FEGPU_XFER_SIMD")) t->simd = std::min(t->simd, std::max(0, std::atoi(e)));
   if (const char *e = std::getenv("FEGPU_XFER_CHUNK_MB")) t->chunk_bytes = std::min(XF_CHUNK_MAX, (size_t)std::max(1, std::atoi(e)) << 20);
   if (const char *e = std::getenv("FEGPU_XFER_NARROW")) t->narrow = std::atoi(e) != 0;
+  if (const char *e = std::getenv("FEGPU_XFER_COMPRESS")) t->compress = std::atoi(e) != 0;
   *out = t;
   return FEGPU_OK;
 }
@@ -214,7 +306,54 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
   int njobs = 0;
   const double *direct_nz = nullptr;
   const int64_t *direct_rv = nullptr;
-  if (rowval && nnz) {
+
+  // Row indices of a vector-field pattern: ndn^2 entries of rowval per (column node, neighbour node) pair, so the pair list
+  // (int32 per pair) + the dof map cross the link instead -- config 2: 0.27 GB instead of 2.05 GB -- and the host threads
+  // rebuild rowval while nzval is in flight.
+  const int32_t *c_nbr = nullptr, *c_dof = nullptr;
+  const int64_t *c_nbrptr = nullptr;
+  int64_t c_total = 0, c_nnodes = 0;
+  int c_ndn = 0;
+  bool compressed = rowval && nnz && T->compress && !as->view.active && as->pat_src &&
+                    fe_pattern_compressed(as->pat_src, &c_nbr, &c_nbrptr, &c_total, &c_dof, &c_ndn, &c_nnodes);
+  const int32_t *h_nbr = nullptr, *h_dof = nullptr;
+  const int64_t *h_nbrptr = nullptr, *h_colptr = nullptr;
+  if (compressed) {
+    const size_t b_nbr = ((size_t)c_total * 4 + 63) & ~(size_t)63, b_ptr = ((size_t)(c_nnodes + 1) * 8 + 63) & ~(size_t)63;
+    const size_t b_dof = ((size_t)c_nnodes * c_ndn * 4 + 63) & ~(size_t)63, b_col = ((size_t)(as->ncols + 1) * 8 + 63) & ~(size_t)63;
+    const size_t need = b_nbr + b_ptr + b_dof + b_col;
+    if (T->meta_cap < need) {
+      if (T->h_meta) cudaFreeHost(T->h_meta);
+      T->h_meta = nullptr; T->meta_cap = 0;
+      CUDA_TRY(ctx, cudaHostAlloc(&T->h_meta, need, cudaHostAllocDefault));
+      T->meta_cap = need;
+    }
+    char *hm = static_cast<char *>(T->h_meta);
+    // small pieces first so the threads can start on the first nodes as early as possible
+    CUDA_TRY(ctx, cudaMemcpyAsync(hm, as->d_colptr, (size_t)(as->ncols + 1) * 8, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(hm + b_col, c_nbrptr, (size_t)(c_nnodes + 1) * 8, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(hm + b_col + b_ptr, c_dof, (size_t)c_nnodes * c_ndn * 4, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(hm + b_col + b_ptr + b_dof, c_nbr, (size_t)c_total * 4, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(ctx, cudaEventRecord(T->meta_done, cs));
+    h_colptr = reinterpret_cast<const int64_t *>(hm);
+    h_nbrptr = reinterpret_cast<const int64_t *>(hm + b_col);
+    h_dof = reinterpret_cast<const int32_t *>(hm + b_col + b_ptr);
+    h_nbr = reinterpret_cast<const int32_t *>(hm + b_col + b_ptr + b_dof);
+    T->compressed++;
+  }
+  // node range [lo, hi) of slice k of K, balanced by neighbour-list length
+  auto node_slice = [&](int64_t k, int64_t K, int64_t *lo, int64_t *hi) {
+    auto cut = [&](int64_t j) -> int64_t {
+      if (j <= 0) return 0;
+      if (j >= K) return c_nnodes;
+      const int64_t target = (int64_t)((__int128)c_total * j / K);
+      return std::upper_bound(h_nbrptr, h_nbrptr + c_nnodes + 1, target) - h_nbrptr - 1;
+    };
+    *lo = cut(k); *hi = cut(k + 1);
+  };
+  int64_t exp_done = 0, exp_total = 0;  // node slices of the expansion handed to the threads so far / in all
+
+  if (rowval && nnz && !compressed) {
     if (!T->narrow && is_pinned(rowval)) {
       direct_rv = as->r_rowval();
     } else {
@@ -235,7 +374,7 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
     jobs[k].per_chunk = (int64_t)(T->chunk_bytes / jobs[k].item_dev);
     total_chunks += (jobs[k].n + jobs[k].per_chunk - 1) / jobs[k].per_chunk;
   }
-  if (colptr) CUDA_TRY(ctx, cudaMemcpyAsync(colptr, as->r_colptr(), sizeof(int64_t) * (as->r_ncols() + 1), cudaMemcpyDeviceToHost, cs));
+  if (colptr && !compressed) CUDA_TRY(ctx, cudaMemcpyAsync(colptr, as->r_colptr(), sizeof(int64_t) * (as->r_ncols() + 1), cudaMemcpyDeviceToHost, cs));
   if (direct_rv) CUDA_TRY(ctx, cudaMemcpyAsync(rowval, direct_rv, sizeof(int64_t) * nnz, cudaMemcpyDeviceToHost, cs));
 
   // page-locked nzval goes by plain DMA, sliced in between the staged chunks so the link never idles while the threads work
@@ -248,6 +387,30 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
     nz_issued += len;
     return FEGPU_OK;
   };
+
+  std::function<void(int, int)> expand_all;
+  if (compressed) {
+    exp_total = std::max<int64_t>(total_chunks, 1);
+    if (total_chunks == 0) {
+      // nothing is staged (nzval page-locked or not requested): the link carries nzval by plain DMA while the threads expand
+      while (direct_nz && nz_issued < nnz) FE_TRY(issue_direct_nz());
+      CUDA_TRY(ctx, cudaEventSynchronize(T->meta_done));
+      expand_all = [&](int tid, int nth) {
+        int64_t lo, hi;
+        node_slice(tid, nth, &lo, &hi);
+        expand_rows(h_nbr, h_nbrptr, h_dof, c_ndn, c_nnodes, h_colptr, rowval, lo, hi, T->simd >= 1);
+        if (colptr) {  // the caller's colptr: each thread copies its share
+          const int64_t n = as->ncols + 1, per = (n + nth - 1) / nth, a = std::min(n, per * tid), b = std::min(n, a + per);
+          if (b > a) std::memcpy(colptr + a, h_colptr + a, (size_t)(b - a) * 8);
+        }
+      };
+      T->pool->run(expand_all);
+      exp_done = exp_total;
+    } else {
+      CUDA_TRY(ctx, cudaEventSynchronize(T->meta_done));
+      if (colptr) std::memcpy(colptr, h_colptr, (size_t)(as->ncols + 1) * 8);
+    }
+  }
 
   struct Pending { int buf, job; int64_t off, len; };
   Pending ring[XF_NBUF];
@@ -299,8 +462,17 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
     const StagedJob &j = jobs[p.job];
     const void *src = T->h_stage[p.buf];
     const int simd = T->simd;
-    std::function<void(int, int)> fn = [&j, src, p, simd](int tid, int nth) {
+    const int64_t exp_k = (compressed && exp_done < exp_total) ? exp_done++ : -1;
+    const int wth = T->widen_threads;
+    std::function<void(int, int)> fn = [&, src, p, simd, exp_k, wth](int tid, int nth) {
+      if (exp_k >= 0) {  // this chunk's share of the row-index expansion
+        int64_t lo, hi;
+        node_slice(exp_k * nth + tid, exp_total * nth, &lo, &hi);
+        expand_rows(h_nbr, h_nbrptr, h_dof, c_ndn, c_nnodes, h_colptr, rowval, lo, hi, T->simd >= 1);
+      }
       // slices are multiples of 16 items so the vector loops stay aligned
+      if (tid >= wth) return;
+      nth = wth;
       const int64_t per = (((p.len + nth - 1) / nth) + 15) & ~(int64_t)15;
       const int64_t lo = std::min<int64_t>(p.len, per * tid), hi = std::min<int64_t>(p.len, lo + per);
       if (hi <= lo) return;
@@ -327,5 +499,11 @@ extern "C" int32_t fegpu_transfer_stats(fegpu_ctx *ctx, int64_t *staged, int64_t
   if (!ctx) return FEGPU_ERR_ARG;
   if (staged) *staged = ctx->xfer ? ctx->xfer->staged : 0;
   if (bypassed) *bypassed = ctx->xfer ? ctx->xfer->bypassed : 0;
+  return FEGPU_OK;
+}
+
+extern "C" int32_t fegpu_transfer_compressed(fegpu_ctx *ctx, int64_t *results) {
+  if (!ctx || !results) return FEGPU_ERR_ARG;
+  *results = ctx->xfer ? ctx->xfer->compressed : 0;
   return FEGPU_OK;
 }

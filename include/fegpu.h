@@ -132,6 +132,11 @@ int32_t fegpu_makematrix_view(fegpu_asm *as, int64_t row_first, int64_t row_last
  * into `rowval` by host threads (FEGPU_HOST_THREADS, default min(cores, 4)); destinations may be pageable or page-locked.
  * fegpu_transfer_stats: staged (int32 + widen) and bypassed (plain int64 DMA) chunk counts so far. */
 int32_t fegpu_transfer_stats(fegpu_ctx *ctx, int64_t *staged_chunks, int64_t *bypassed_chunks);
+/* Vector fields (ndn >= 2) whose node-major dof order is ascending at every node: rowval does not cross the link at all; the
+ * per-node neighbour lists of the device's symbolic phase (int32 per node pair, 1/ndn^2 of the row indices) and the dof map
+ * do, and the host threads decode them into `rowval` while nzval is in flight (FEGPU_XFER_COMPRESS=0 turns it off).
+ * fegpu_transfer_compressed: number of results delivered that way so far. */
+int32_t fegpu_transfer_compressed(fegpu_ctx *ctx, int64_t *results);
 /* nzval only (re-assembly on a cached pattern: colptr/rowval did not change) */
 int32_t fegpu_makematrix_copy_values(fegpu_asm *as, double *nzval);
 /* device pointers of the current result (valid until the next assembly on this assembler) */

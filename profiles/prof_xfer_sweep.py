@@ -29,6 +29,8 @@ def child():
     m_, n_, nnz = a.sizes()
     pin = lambda cnt, dt: torch.empty(cnt, dtype=dt, pin_memory=True).numpy()
     out = (pin(n_ + 1, torch.int64), pin(nnz, torch.int64), pin(nnz, torch.float64))
+    if os.environ.get("FEGPU_PAGEABLE") == "1":
+        out = (np.zeros(n_ + 1, np.int64), np.zeros(nnz, np.int64), np.zeros(nnz, np.float64))
     a._fetch(True, out)
     ts = []
     for _ in range(4):
@@ -38,6 +40,12 @@ def child():
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "compress":  # the compressed row-index transport against the int32 one
+        settings = [{"FEGPU_XFER_COMPRESS": "0"}] + [{"FEGPU_HOST_THREADS": th} for th in ("4", "8", "12", "16")]
+        for pg in ("0",):
+            settings.append({"FEGPU_XFER_COMPRESS": "0", "FEGPU_PAGEABLE": "1"})
+            settings.append({"FEGPU_HOST_THREADS": "8", "FEGPU_PAGEABLE": "1"})
+        return sweep(settings)
     settings = [{"FEGPU_XFER_NARROW": "0"}]
     for th in ("4", "8", "16"):
         for simd in ("1", "2"):
@@ -45,6 +53,10 @@ def main():
     for mb in ("4", "8", "16"):
         settings.append({"FEGPU_HOST_THREADS": "8", "FEGPU_XFER_SIMD": "2", "FEGPU_XFER_CHUNK_MB": mb})
     settings.append({"FEGPU_XFER_NARROW": "0"})
+    sweep(settings)
+
+
+def sweep(settings):
     for s in settings:
         env = dict(os.environ); env.update(s)
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True)

@@ -467,6 +467,51 @@ def test_result_transport_large(fe, orc, gpu_ctx, pinned):
     np.testing.assert_array_equal(vals, got[2])
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("variant", ["natural", "ebc", "partition", "dot2"])
+def test_result_transport_compressed_rows(fe, orc, gpu_ctx, pinned, variant):
+    """Vector fields: rowval is rebuilt on the host from the device's neighbour lists + dof map (fegpu_transfer.cu) instead
+    of crossing the link; the arrays that arrive must be the oracle's.  'ebc' (free-first numbering: node-major dof order not
+    ascending everywhere) must fall back to the int32 transport; a row-block partition and a 2-dof field must not."""
+    fens, fes = fe.H8block(1.0, 2.0, 3.0, 22, 22, 22)
+    _distort(fens)
+    rule = fe.GaussRule(3, 2)
+    kw = {}
+    if variant == "dot2":
+        u = make_field(fe, fens, 2)
+        form, coef, et = "dot", np.array([[2.0, 0.5], [0.25, 3.0]]), "H8"
+    else:
+        fixed = list(range(5, fens.count(), 37)) if variant == "ebc" else None
+        u = make_field(fe, fens, 3, fixed_nodes=fixed, fixed_comp=None)
+        form, coef, et = "elastic", isotropic_C(), "H8"
+    ref, _ = oracle_csc(orc, form, et, fes, fens, u, rule, coef)
+    n = u.nalldofs()
+    if variant == "partition":
+        owner = fe.slab_owner(fens.count(), 2)
+        kw = dict(node_owner=owner, my_rank=1)
+        keep = np.zeros(n, bool)
+        keep[(u.dofnums[owner == 1] - 1).reshape(-1)] = True
+        mask = keep[ref[1] - 1]  # the rank's block: the rows of its nodes, every column
+        col_of = np.repeat(np.arange(n), np.diff(ref[0]))
+        cnt = np.bincount(col_of[mask], minlength=n)
+        ref = (np.concatenate(([1], 1 + np.cumsum(cnt))).astype(np.int64), ref[1][mask], ref[2][mask])
+    nnz = ref[2].size
+    assert nnz >= (1 << 20)
+    before = gpu_ctx.transfer_stats()["compressed_results"]
+    if pinned:
+        import torch
+        out = (torch.empty(n + 1, dtype=torch.int64, pin_memory=True).numpy(), torch.empty(nnz + 3, dtype=torch.int64, pin_memory=True).numpy()[3:],
+               torch.empty(nnz, dtype=torch.float64, pin_memory=True).numpy())
+    else:
+        out = (np.empty(n + 1, np.int64), np.empty(nnz + 1, np.int64)[1:], np.empty(nnz + 1, np.float64)[1:])
+    for o in out:
+        o[...] = -7
+    got, a = gpu_csc(fe, form, fes, fens, u, rule, coef, out=out, **kw)
+    assert_parity(ref, got)
+    used = gpu_ctx.transfer_stats()["compressed_results"] - before
+    assert used == (0 if variant == "ebc" else 1)
+
+
 def test_symm_assembler_testA_on_gpu(fe, orc, gpu_ctx):
     """test/test_basics.jl:119-129 through the generic protocol of the symmetric assembler."""
     from test_oracle_pins import _testA_blocks
