@@ -55,9 +55,10 @@ __device__ __forceinline__ void block_acc(double *k9, const double *ga, const do
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     const double *d = T + 6 * j;
-    k9[0 + 3 * j] += ga[0] * d[0] + ga[1] * d[3] + ga[2] * d[4];
-    k9[1 + 3 * j] += ga[1] * d[1] + ga[0] * d[3] + ga[2] * d[5];
-    k9[2 + 3 * j] += ga[2] * d[2] + ga[0] * d[4] + ga[1] * d[5];
+    // three DFMA straight into the accumulator (instead of DMUL + 2 DFMA + DADD)
+    k9[0 + 3 * j] = fma(ga[2], d[4], fma(ga[1], d[3], fma(ga[0], d[0], k9[0 + 3 * j])));
+    k9[1 + 3 * j] = fma(ga[2], d[5], fma(ga[0], d[3], fma(ga[1], d[1], k9[1 + 3 * j])));
+    k9[2 + 3 * j] = fma(ga[1], d[5], fma(ga[0], d[4], fma(ga[2], d[2], k9[2 + 3 * j])));
   }
 }
 

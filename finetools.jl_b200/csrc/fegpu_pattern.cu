@@ -451,6 +451,173 @@ __global__ void __launch_bounds__(WPB * 32) k_nbr_fast(SymParams S, const int64_
   }
 }
 
+// Same algorithm with LPN lanes per node (32/LPN nodes per warp) and KPL keys per lane: for small elements (H8: 64
+// candidates = 16 lanes x 4 keys, two nodes per warp; Q4/T3: 8 lanes x 4 keys, four nodes per warp) every instruction of the
+// network serves several nodes, and more stages stay inside a lane.  Preconditions: maxdeg <= LPN, candidates <= LPN*KPL.
+template <int LPN, int KPL>
+__device__ __forceinline__ void group_bitonic(uint32_t (&v)[KPL], int gl) {
+  // Bitonic sorter written with ascending comparators only: the first step of every merge pairs position i with
+  // i ^ (k-1) (the mirrored position), the following steps with i ^ j.  The lower position always keeps the minimum, so
+  // in-lane steps are a plain (min, max) pair and cross-lane steps one predicated min/max per key.
+#pragma unroll
+  for (int k = 2; k <= LPN * KPL; k <<= 1) {
+    if (k <= KPL) {
+#pragma unroll
+      for (int r = 0; r < KPL; r++) {
+        const int rp = r ^ (k - 1);
+        if (rp > r) {
+          const uint32_t lo = min(v[r], v[rp]), hi = max(v[r], v[rp]);
+          v[r] = lo;
+          v[rp] = hi;
+        }
+      }
+    } else {
+      const int lm = k / KPL - 1;                          // lane part of the mirror mask; the register part is r ^ (KPL-1)
+      const bool lower = (gl & (k / (2 * KPL))) == 0;      // the highest flipped bit decides which side this lane is on
+      uint32_t o[KPL];
+#pragma unroll
+      for (int r = 0; r < KPL; r++) o[r] = __shfl_xor_sync(0xffffffffu, v[KPL - 1 - r], lm);
+#pragma unroll
+      for (int r = 0; r < KPL; r++) v[r] = lower ? min(v[r], o[r]) : max(v[r], o[r]);
+    }
+#pragma unroll
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      if (j < KPL) {
+#pragma unroll
+        for (int r = 0; r < KPL; r++) {
+          const int rp = r ^ j;
+          if (rp > r) {
+            const uint32_t lo = min(v[r], v[rp]), hi = max(v[r], v[rp]);
+            v[r] = lo;
+            v[rp] = hi;
+          }
+        }
+      } else {
+        const int lj = j / KPL;
+        const bool lower = (gl & lj) == 0;
+#pragma unroll
+        for (int r = 0; r < KPL; r++) {
+          const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], lj);
+          v[r] = lower ? min(v[r], o) : max(v[r], o);
+        }
+      }
+    }
+  }
+}
+
+template <int LPN, int KPL, bool CHECK>
+__global__ void __launch_bounds__(WPB * 32) k_nbr_group(SymParams S, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ adj_slot,
+                                                        int capc, int KB, int32_t *__restrict__ nnbr_out, int32_t *__restrict__ U,
+                                                        uint16_t *__restrict__ cslot, uint8_t *__restrict__ sorted_flag, int *any_unsorted) {
+  extern __shared__ int32_t sfl[];
+  constexpr int NPW = 32 / LPN;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = lane / LPN, gl = lane % LPN;
+  int32_t *smF = CHECK ? sfl + (size_t)(w * NPW + g) * 2 * capc : nullptr;
+  int32_t *smL = CHECK ? smF + capc : nullptr;
+  const int nne = S.nne;
+  const uint32_t nne_magic = 65536u / (uint32_t)nne + 1u;
+  const uint32_t kmask = (1u << KB) - 1u, dropped = 0xffffffffu >> KB;
+  const unsigned gmask = (LPN == 32) ? 0xffffffffu : (((1u << LPN) - 1u) << (g * LPN));
+  const unsigned lt = ((1u << lane) - 1u) & gmask;  // lower lanes of this node's group
+  const int64_t stride = (int64_t)gridDim.x * WPB * NPW;
+  const int64_t first = ((int64_t)blockIdx.x * WPB + w) * NPW;  // warp-uniform; the groups of a warp take consecutive nodes
+  // software pipeline: the adjacency range and element ids of the next node are fetched while this one is sorted
+  int64_t ab = 0;
+  int deg = 0;
+  uint32_t el = 0;
+  int64_t n = -1;
+  auto fetch = [&](int64_t idx) {
+    n = -1; ab = 0; deg = 0; el = 0;
+    if (idx < S.na) {
+      n = active_node(S, idx);
+      ab = adjptr[n];
+      deg = (int)(adjptr[n + 1] - ab);
+      if (gl < deg) {
+        const int64_t slot = adj_slot[ab + gl];
+        el = (uint32_t)(S.elem_list ? S.elem_list[slot] : slot);
+      }
+    }
+  };
+  fetch(first + g);
+  for (int64_t base = first; base < S.na; base += stride) {  // trip count is warp-uniform
+    const int64_t n_cur = n, ab_cur = ab;
+    const int deg_cur = deg;
+    const uint32_t el_cur = el;
+    const int ncand = deg_cur * nne;
+    uint32_t v[KPL];
+#pragma unroll
+    for (int r = 0; r < KPL; r++) {
+      const int k = r * LPN + gl;
+      const int a = (k < ncand) ? (int)(((uint32_t)k * nne_magic) >> 16) : 0;
+      const uint32_t e = __shfl_sync(0xffffffffu, el_cur, g * LPN + a);
+      uint32_t key = 0xffffffffu;
+      if (k < ncand) {
+        const int li = k - a * nne;
+        uint32_t m = (uint32_t)S.conn[(int64_t)e * nne + li];
+        if (S.rowowned && !S.rowowned[m]) m = dropped;
+        key = (m << KB) | (uint32_t)k;
+      }
+      v[r] = key;
+    }
+    fetch(base + stride + g);
+    group_bitonic<LPN, KPL>(v, gl);
+    const uint32_t prev_lane_last = __shfl_up_sync(0xffffffffu, v[KPL - 1], 1);
+    bool head[KPL];
+    int nu = 0, before = 0;
+#pragma unroll
+    for (int r = 0; r < KPL; r++) {
+      const uint32_t node = v[r] >> KB;
+      const uint32_t pnode = (r == 0) ? (prev_lane_last >> KB) : (v[r - 1] >> KB);
+      head[r] = (node != dropped) && ((r == 0 && gl == 0) || node != pnode);
+      const unsigned bal = __ballot_sync(0xffffffffu, head[r]);
+      nu += __popc(bal & gmask);
+      before += __popc(bal & lt);
+    }
+    if (deg_cur > 0) {
+      uint16_t *cs = cslot + ab_cur * nne;
+      int32_t *Un = U + ab_cur * nne;
+      bool ok = true;
+#pragma unroll
+      for (int r = 0; r < KPL; r++) {
+        before += head[r] ? 1 : 0;
+        const uint32_t node = v[r] >> KB, k = v[r] & kmask;
+        if ((int)k < ncand) cs[k] = (node == dropped) ? (uint16_t)0xffffu : (uint16_t)(before - 1);
+        if (head[r]) {
+          Un[before - 1] = (int32_t)node;
+          if (CHECK) {
+            int prev = S.dof[node];
+            smF[before - 1] = prev;
+            for (int p = 1; p < S.ndn; p++) {
+              const int d = S.dof[(int64_t)p * S.nnodes + node];
+              if (d <= prev) ok = false;
+              prev = d;
+            }
+            smL[before - 1] = prev;
+          }
+        }
+      }
+      if (CHECK) {
+        __syncwarp(gmask);
+        for (int s2 = gl; s2 + 1 < nu; s2 += LPN)
+          if (smF[s2 + 1] <= smL[s2]) ok = false;
+        ok = (__ballot_sync(gmask, !ok) & gmask) == 0;
+        __syncwarp(gmask);
+      }
+      if (gl == 0) {
+        nnbr_out[n_cur] = nu;
+        if (CHECK) {
+          sorted_flag[n_cur] = ok ? 1 : 0;
+          if (!ok) *any_unsorted = 1;
+        }
+      }
+    } else if (n_cur >= 0 && gl == 0) {
+      nnbr_out[n_cur] = 0;
+      if (CHECK) sorted_flag[n_cur] = 1;
+    }
+  }
+}
+
 // is the dof map node-major ascending (dofs of a node ascending by component, below every dof of the next node)?  Then the
 // rows of every column are ascending in (neighbour, component) order and no node needs an order test or a rank table.
 __global__ void k_dof_monotone(const int32_t *__restrict__ dof, int64_t nnodes, int ndn, int *violated) {
@@ -891,9 +1058,19 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
     if (monotone) k_nbr_fast<M, false><<<gridn, WPB * 32, 0, st>>>(S, P->d_adjptr, P->d_adj_slot, capc, KB, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1); \
     else k_nbr_fast<M, true><<<gridn, WPB * 32, smf, st>>>(S, P->d_adjptr, P->d_adj_slot, capc, KB, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1);       \
   } while (0)
-    if (capc <= 64) LAUNCH_FAST(2);
+#define LAUNCH_GROUP(L, K)                                                                                                          \
+  do {                                                                                                                              \
+    const unsigned gg = (unsigned)std::max<int64_t>(1, std::min<int64_t>((S.na + WPB * (32 / L) - 1) / (WPB * (32 / L)), (int64_t)ctx->sm_count * 64)); \
+    if (monotone) k_nbr_group<L, K, false><<<gg, WPB * 32, 0, st>>>(S, P->d_adjptr, P->d_adj_slot, capc, KB, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1); \
+    else k_nbr_group<L, K, true><<<gg, WPB * 32, smf * (32 / L), st>>>(S, P->d_adjptr, P->d_adj_slot, capc, KB, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1); \
+  } while (0)
+    static const bool group_off = std::getenv("FEGPU_NBR_GROUP") && std::atoi(std::getenv("FEGPU_NBR_GROUP")) == 0;  // A/B knob
+    if (!group_off && capc <= 32 && maxdeg <= 8) LAUNCH_GROUP(8, 4);          // Q4 / T3 skins, T3/Q4 planar: four nodes per warp
+    else if (!group_off && capc <= 64 && maxdeg <= 16) LAUNCH_GROUP(16, 4);   // H8: two nodes per warp
+    else if (capc <= 64) LAUNCH_FAST(2);
     else if (capc <= 128) LAUNCH_FAST(4);
     else LAUNCH_FAST(16);
+#undef LAUNCH_GROUP
 #undef LAUNCH_FAST
     if (monotone) PC(cudaMemsetAsync(d_sorted, 1, nn, st));  // every node is in order; the kernel did not write the flags
   } else {
