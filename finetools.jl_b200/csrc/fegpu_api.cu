@@ -521,7 +521,7 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
   static const bool compact_off = std::getenv("FEGPU_COMPACT") && std::atoi(std::getenv("FEGPU_COMPACT")) == 0;  // A/B knob
   fa2.compact = fast && fe_integrate_supports_compact(mesh, fa) && !compact_off;
   const int64_t per_elem = fa2.compact ? fe_compact_size(mesh->nne, fa.ndn) : (int64_t)EM * EM;
-  FE_TRY(fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(mesh->nactive * per_elem, 1)));
+  FE_TRY(fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(mesh->nactive * per_elem, 1) + 2));  // +2: k_gather_blk reads aligned 16-byte chunks
   as->V_n = ntrip;
   as->last_EM = EM;
   as->V_compact = fa2.compact;

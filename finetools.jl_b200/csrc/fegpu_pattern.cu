@@ -772,7 +772,7 @@ __device__ __forceinline__ int elem_offset(int li, int p, int lc, int q, int ndn
 // next node / the column bases fetched early.
 // Shared per node group: acc[maxnbr*ndn*ndn] doubles | base[maxdeg] int64 | cs[maxcand] uint16 (padded to 8 B)
 template <int LPN, int NDN, bool COMPACT, int GBATCH, int RPL>
-__global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
+__global__ void __launch_bounds__(GWPB * 32, 5) k_gather(const GatherParams G) {
   extern __shared__ double sacc[];
   constexpr int NPW = 32 / LPN;
   constexpr int QMAX = (NDN > 0) ? NDN : 6;
@@ -789,8 +789,10 @@ __global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
   double *acc = sacc + (size_t)(w * NPW + g) * grp_words;
   long long *base = reinterpret_cast<long long *>(acc + acc_stride);
   uint16_t *cs = reinterpret_cast<uint16_t *>(base + G.maxdeg);
-  const int64_t groups_total = (int64_t)gridDim.x * GWPB * NPW;
-  const int64_t niter = (G.npos + groups_total - 1) / groups_total;
+  // node counts fit 32 bits (dof numbers are int32 on the device): 32-bit loop state keeps the kernel at 48 registers
+  const int nnodes = (int)G.nnodes, npos = (int)G.npos;
+  const int groups_total = (int)gridDim.x * GWPB * NPW;
+  const int niter = (npos + groups_total - 1) / groups_total;
   // rows of the element matrix this lane adds: r = gl + j*LPN
   int rli[RMAX], rp[RMAX];
   bool rok[RMAX];
@@ -802,16 +804,18 @@ __global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
     rp[j] = rok[j] ? r - rli[j] * ndn : 0;
   }
   // visiting position -> node (Morton order when G.order); node ids are prefetched two iterations ahead, scalars one
-  int64_t pos = (int64_t)blockIdx.x * (GWPB * NPW) + w * NPW + g;
-  int64_t n = (pos < G.npos) ? (G.order ? (int64_t)G.order[pos] : pos) : G.nnodes;
-  int64_t n_next = (pos + groups_total < G.npos) ? (G.order ? (int64_t)G.order[pos + groups_total] : pos + groups_total) : G.nnodes;
-  int nn_pre = (n < G.nnodes) ? G.nnbr[n] : 0;
-  int64_t ab_pre = (n < G.nnodes) ? G.adjptr[n] : 0, ae_pre = (n < G.nnodes) ? G.adjptr[n + 1] : 0;
-  for (int64_t it = 0; it < niter; it++) {
-    const bool live = n < G.nnodes;
+  int pos = (int)blockIdx.x * (GWPB * NPW) + w * NPW + g;
+  auto node_at = [&](int p) -> int { return (p < npos && p >= 0) ? (G.order ? G.order[p] : p) : nnodes; };
+  int n = node_at(pos);
+  int n_next = node_at(pos + groups_total);
+  int nn_pre = (n < nnodes) ? G.nnbr[n] : 0;
+  int64_t ab_pre = (n < nnodes) ? G.adjptr[n] : 0;
+  int deg_pre = (n < nnodes) ? (int)(G.adjptr[n + 1] - ab_pre) : 0;
+  for (int it = 0; it < niter; it++) {
+    const bool live = n < nnodes;
     const int nn = nn_pre;
     const int64_t ab = ab_pre;
-    const int deg = (live && nn > 0) ? (int)(ae_pre - ab) : 0;
+    const int deg = (live && nn > 0) ? deg_pre : 0;
     const int per_col = nn * ndn;
     const int total = per_col * ndn;
     // stage the node's metadata (one round trip to memory), clear the accumulators
@@ -825,14 +829,13 @@ __global__ void __launch_bounds__(GWPB * 32) k_gather(const GatherParams G) {
     long long cb[QMAX];
 #pragma unroll
     for (int q = 0; q < QMAX; q++) cb[q] = (q < ndn && deg > 0) ? G.colptr[G.dof[(int64_t)q * G.nnodes + n]] - 1 : 0;
-    const int64_t pos2 = pos + 2 * groups_total;
-    const int64_t n_next2 = (pos2 < G.npos) ? (G.order ? (int64_t)G.order[pos2] : pos2) : G.nnodes;
-    if (n_next < G.nnodes) {
+    const int n_next2 = node_at(pos + 2 * groups_total);
+    if (n_next < nnodes) {
       nn_pre = G.nnbr[n_next];
       ab_pre = G.adjptr[n_next];
-      ae_pre = G.adjptr[n_next + 1];
+      deg_pre = (int)(G.adjptr[n_next + 1] - ab_pre);
     } else {
-      nn_pre = 0; ab_pre = 0; ae_pre = 0;
+      nn_pre = 0; ab_pre = 0; deg_pre = 0;
     }
     for (int i = gl; i < total; i += LPN) acc[i] = 0.0;
     int maxdeg = deg;
@@ -1198,11 +1201,16 @@ int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_n
   const size_t smem = (size_t)GWPB * npw * ((size_t)P->maxnbr * dm->ndn * dm->ndn + P->maxdeg + (P->maxcand + 3) / 4) * sizeof(double);
   if (smem > 200 * 1024) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: gather accumulators exceed shared memory");
   const int64_t per_block = (int64_t)GWPB * npw;
-  unsigned grid = (unsigned)std::min<int64_t>((G.npos + per_block - 1) / per_block, (int64_t)ctx->sm_count * 32);
-  if (grid == 0) grid = 1;
+  // persistent launch: exactly the CTAs that are resident at once (occupancy x SMs), so there is no partial last wave
+  static const int waves_env = std::getenv("FEGPU_GATHER_WAVES") ? std::atoi(std::getenv("FEGPU_GATHER_WAVES")) : 0;
+  const int64_t need_blocks = std::max<int64_t>(1, (G.npos + per_block - 1) / per_block);
+  unsigned grid = 1;
 #define LG5(L, N, C, B, R)                                                                                                          \
   do {                                                                                                                              \
     if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_gather<L, N, C, B, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    int occ = 0;                                                                                                                    \
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gather<L, N, C, B, R>, GWPB * 32, smem));                   \
+    grid = (unsigned)std::min<int64_t>(need_blocks, (int64_t)ctx->sm_count * std::max(occ, 1) * (waves_env > 0 ? waves_env : 1)); \
     k_gather<L, N, C, B, R><<<grid, GWPB * 32, smem, ctx->stream>>>(G);                                                             \
   } while (0)
 #define LG_R(L, N, C)                                                            \
