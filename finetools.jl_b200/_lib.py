@@ -20,6 +20,7 @@ SIGNATURES = {
     "fegpu_last_error": (C.c_char_p, [VP]),
     "fegpu_set_stream": (C.c_int32, [VP, VP]),
     "fegpu_set_async": (C.c_int32, [VP, C.c_int32]),
+    "fegpu_set_overlap": (C.c_int32, [VP, C.c_int32]),
     "fegpu_synchronize": (C.c_int32, [VP]),
     "fegpu_launch_count": (C.c_int64, [VP]),
     "fegpu_measure_peaks": (C.c_int32, [VP, c_f64p, c_f64p]),

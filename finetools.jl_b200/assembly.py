@@ -35,6 +35,10 @@ class GPUContext:
     def set_async(self, on):
         check(_lib.lib().fegpu_set_async(self.handle, 1 if on else 0), self.handle)
 
+    def set_overlap(self, on):
+        """Fresh assemblies overlap element integration (second stream) with the symbolic phase; off = strictly serial phases."""
+        check(_lib.lib().fegpu_set_overlap(self.handle, 1 if on else 0), self.handle)
+
     def synchronize(self):
         check(_lib.lib().fegpu_synchronize(self.handle), self.handle)
 

@@ -165,7 +165,20 @@ int32_t fegpu_create(fegpu_ctx **out, int32_t device) {
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
   }
+  {  // the symbolic phase of a fresh assembly runs on this stream at the highest priority (see run_bilform)
+    int lo = 0, hi = 0;
+    CUDA_TRY(nullptr, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(nullptr, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
+  }
+  CUDA_TRY(nullptr, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  if (const char *e = std::getenv("FEGPU_OVERLAP")) ctx->overlap = std::atoi(e) != 0;
   *out = ctx;
+  return FEGPU_OK;
+}
+
+int32_t fegpu_set_overlap(fegpu_ctx *ctx, int32_t on) {
+  if (!ctx) return FEGPU_ERR_ARG;
+  ctx->overlap = on != 0;
   return FEGPU_OK;
 }
 
@@ -173,6 +186,8 @@ int32_t fegpu_destroy(fegpu_ctx *ctx) {
   if (!ctx) return FEGPU_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->xfer) fe_transfer_free(ctx->xfer);
   delete ctx;
   return FEGPU_OK;
@@ -503,30 +518,63 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
   as->pat_src = nullptr;
   as->view.active = false;
   as->started = false;
-  // 1. symbolic phase first (cached in the dof map): it decides the layout the integration kernel writes
+  // 1. symbolic phase (cached in the dof map) and 2. element integration.  The symbolic phase decides the layout the
+  // integration kernel writes (compact only on the structured path), but nothing else connects the two, so on a fresh
+  // assembly the pattern build runs on the context's second, high-priority stream and the integration is launched on the
+  // caller's stream as soon as the build knows it will take the structured path; the numeric phase waits for both.
   CUDA_TRY(ctx, cudaEventRecord(as->ev[0], st));
   bool fast = fe_pattern_usable(dm);
   as->pattern_cached = false;
+  FormArgs fa2 = fa;
+  static const bool compact_off = std::getenv("FEGPU_COMPACT") && std::atoi(std::getenv("FEGPU_COMPACT")) == 0;  // A/B knob
+  as->V_n = ntrip;
+  as->last_EM = EM;
+  auto integrate = [&](bool compact) -> int32_t {  // always on the caller's stream
+    fa2.compact = compact;
+    const int64_t per_elem = compact ? fe_compact_size(mesh->nne, fa.ndn) : (int64_t)EM * EM;
+    ctx->stream = st;
+    FE_TRY(fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(mesh->nactive * per_elem, 1)));
+    as->V_compact = compact;
+    CUDA_TRY(ctx, cudaEventRecord(as->ev[4], st));
+    FE_TRY(fe_integrate(mesh, fa2, as->d_V));
+    CUDA_TRY(ctx, cudaEventRecord(as->ev[2], st));
+    return FEGPU_OK;
+  };
+  bool integrated = false, sym_timed = false;
   if (fast) {
     if (!dm->pat || dm->pat_topo_version != mesh->topo_version) {
-      FE_TRY(fe_pattern_build(dm));
+      const bool want_compact = fe_integrate_supports_compact(mesh, fa) && !compact_off;
+      const bool ov = ctx->overlap && ctx->stream2;
+      cudaStream_t sym = ov ? ctx->stream2 : st;
+      std::function<int32_t()> fork = [&]() -> int32_t {  // called from inside the build, which runs on `sym`
+        integrated = true;
+        const int32_t r = integrate(want_compact);
+        ctx->stream = sym;
+        return r;
+      };
+      if (ov) {  // the symbolic phase starts after everything queued on the caller's stream so far
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(sym, ctx->ev_fork, 0));
+        ctx->stream = sym;
+      }
+      const int32_t bs = fe_pattern_build(dm, ov ? &fork : nullptr);
+      ctx->stream = st;
+      FE_TRY(bs);
       fast = fe_pattern_usable(dm) && dm->pat;  // the build may discover a degenerate mesh
+      if (ov) {
+        if (dm->pat) fe_pattern_set_stream(dm->pat, st);  // its stream-ordered frees follow the caller's stream from now on
+        CUDA_TRY(ctx, cudaEventRecord(as->ev[1], sym));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st, as->ev[1], 0));  // join
+        sym_timed = true;
+      }
     } else {
       as->pattern_cached = true;
     }
   }
-  CUDA_TRY(ctx, cudaEventRecord(as->ev[1], st));
-  // 2. element integration.  Symmetric forms on the mesh-structured path write only the upper block triangle
-  FormArgs fa2 = fa;
-  static const bool compact_off = std::getenv("FEGPU_COMPACT") && std::atoi(std::getenv("FEGPU_COMPACT")) == 0;  // A/B knob
-  fa2.compact = fast && fe_integrate_supports_compact(mesh, fa) && !compact_off;
-  const int64_t per_elem = fa2.compact ? fe_compact_size(mesh->nne, fa.ndn) : (int64_t)EM * EM;
-  FE_TRY(fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(mesh->nactive * per_elem, 1) + 2));  // +2: k_gather_blk reads aligned 16-byte chunks
-  as->V_n = ntrip;
-  as->last_EM = EM;
-  as->V_compact = fa2.compact;
-  FE_TRY(fe_integrate(mesh, fa2, as->d_V));
-  CUDA_TRY(ctx, cudaEventRecord(as->ev[2], st));
+  if (!sym_timed) CUDA_TRY(ctx, cudaEventRecord(as->ev[1], st));
+  if (integrated && !fast && fa2.compact) integrated = false;  // late fall-back to the sort path: it needs full element matrices
+  if (!integrated) FE_TRY(integrate(fast && fe_integrate_supports_compact(mesh, fa) && !compact_off));
+  CUDA_TRY(ctx, cudaEventRecord(as->ev[5], st));
   // 3. numeric CSC phase
   if (fast) {
     const int64_t nnz = fe_pattern_nnz(dm->pat);
@@ -683,12 +731,14 @@ int32_t fegpu_makematrix(fegpu_asm *as) {
   if (s != FEGPU_OK) { cleanup(); return s; }
   GT(cudaEventRecord(as->ev[0], st));
   GT(cudaEventRecord(as->ev[1], st));
+  GT(cudaEventRecord(as->ev[4], st));
   if (n) {
     GT(cudaMemcpyAsync(dI, as->hI.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
     GT(cudaMemcpyAsync(dJ, as->hJ.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
     GT(cudaMemcpyAsync(as->d_V, as->hV.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
   }
   GT(cudaEventRecord(as->ev[2], st));
+  GT(cudaEventRecord(as->ev[5], st));
   s = fe_coo_to_csc(as, n, dI, dJ, as->d_V, as->g_row_nall, as->g_col_nall);
   cleanup();
   FE_TRY(s);
@@ -793,10 +843,11 @@ int32_t fegpu_last_timings(fegpu_asm *as, double ms[4]) {
   DeviceGuard g(as->ctx->device);
   CUDA_TRY(as->ctx, cudaEventSynchronize(as->ev[3]));
   float t;
-  // recorded order: ev0 -symbolic- ev1 -integration- ev2 -numeric- ev3; reported order: integration, symbolic, numeric
-  static const int first[3] = {1, 0, 2};
+  // reported order: integration (ev4 -> ev2, possibly on the second stream and concurrent with the symbolic phase),
+  // symbolic (ev0 -> ev1), numeric (ev5 -> ev3)
+  static const int first[3] = {4, 0, 5}, last[3] = {2, 1, 3};
   for (int i = 0; i < 3; i++) {
-    CUDA_TRY(as->ctx, cudaEventElapsedTime(&t, as->ev[first[i]], as->ev[first[i] + 1]));
+    CUDA_TRY(as->ctx, cudaEventElapsedTime(&t, as->ev[first[i]], as->ev[last[i]]));
     ms[i] = t;
   }
   CUDA_TRY(as->ctx, cudaEventElapsedTime(&t, as->ev[0], as->ev[3]));

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -16,6 +17,11 @@
 struct fegpu_ctx {
   int device = 0;
   cudaStream_t stream = 0;
+  // fresh assemblies run the element integration on a second stream while the symbolic phase (pattern build) runs on
+  // `stream`: the two are independent until the numeric phase (FP64-bound vs. integer/latency-bound kernels)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr;
+  bool overlap = true;  // fegpu_set_overlap / FEGPU_OVERLAP=0: strictly serial phases (per-kernel timing)
   bool async = false;
   int64_t launches = 0;
   int sm_count = 148;
@@ -97,7 +103,8 @@ struct fegpu_asm {
   std::vector<int64_t> hI, hJ;
   std::vector<double> hV;
   // timings
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // [0] start, [1] symbolic done, [2] integration done, [3] end, [4] integration start, [5] numeric start
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
 };
 
@@ -146,8 +153,11 @@ int32_t fe_integrate(fegpu_mesh *mesh, const FormArgs &fa, double *d_V);
 bool fe_integrate_supports_compact(const fegpu_mesh *mesh, const FormArgs &fa);
 
 // ---- pattern + gather (fegpu_pattern.cu) ---------------------------------------------------------------
-int32_t fe_pattern_build(fegpu_dofmap *dm);
+// `fork` (optional) is invoked once, on the calling thread, as soon as the build knows it will not fall back to the sort path
+// for an early reason (degenerate elements, encoding limits): the caller launches independent work on another stream there
+int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork = nullptr);
 void fe_pattern_free(Pattern *p);
+void fe_pattern_set_stream(Pattern *p, cudaStream_t s);  // stream its stream-ordered frees are queued on
 int64_t fe_pattern_nnz(const Pattern *p);
 const int64_t *fe_pattern_colptr(const Pattern *p);
 const int64_t *fe_pattern_rowval(const Pattern *p);

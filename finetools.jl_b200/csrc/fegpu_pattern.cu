@@ -937,6 +937,7 @@ void fe_pattern_free(Pattern *p) {
     if (q) cudaFreeAsync(q, st);
   delete p;
 }
+void fe_pattern_set_stream(Pattern *p, cudaStream_t s) { p->stream = s; }
 int64_t fe_pattern_nnz(const Pattern *p) { return p->nnz; }
 const int64_t *fe_pattern_colptr(const Pattern *p) { return p->d_colptr; }
 const int64_t *fe_pattern_rowval(const Pattern *p) { return p->d_rowval; }
@@ -951,7 +952,7 @@ bool fe_pattern_usable(const fegpu_dofmap *dm) {
   return dm->injective && !dm->mesh->degenerate && dm->row_nall == dm->col_nall && dm->mesh->nne <= 32;
 }
 
-int32_t fe_pattern_build(fegpu_dofmap *dm) {
+int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork) {
   fegpu_ctx *ctx = dm->ctx;
   fegpu_mesh *mesh = dm->mesh;
   cudaStream_t st = ctx->stream;
@@ -1031,6 +1032,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm) {
   // limits of the packed encodings: neighbour slots and rows per column < 65535
   const size_t smem1 = (size_t)WPB * (maxdeg + 3 * (size_t)capc) * sizeof(uint32_t);
   if (P->maxcand >= 65535 || (int64_t)P->maxcand * ndn >= 65535 || smem1 > 200 * 1024) return bail();
+  if (fork) PT((*fork)());  // the structured path will be taken: independent work may start on another stream now
 
   PT(dalloc(ctx, &P->d_adj_slot, nadj));
   PT(dalloc(ctx, &P->d_adj_lc, nadj));

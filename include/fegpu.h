@@ -56,6 +56,10 @@ const char *fegpu_last_error(fegpu_ctx *ctx); /* ctx may be NULL: last error of 
 /* run all kernels on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); default = stream 0 */
 int32_t fegpu_set_stream(fegpu_ctx *ctx, void *cuda_stream);
 int32_t fegpu_set_async(fegpu_ctx *ctx, int32_t async_on);
+/* Fresh assemblies (no cached pattern) run the element integration on a second stream, concurrently with the symbolic
+ * phase; both are joined before the numeric phase.  overlap_on = 0 (or FEGPU_OVERLAP=0) makes the phases strictly serial,
+ * which is what per-kernel timings (fegpu_last_timings) should be taken with.  Default: on.                  */
+int32_t fegpu_set_overlap(fegpu_ctx *ctx, int32_t overlap_on);
 int32_t fegpu_synchronize(fegpu_ctx *ctx);
 /* number of CUDA kernels this context has launched so far (bench.py's gpu_launches)                     */
 int64_t fegpu_launch_count(fegpu_ctx *ctx);
