@@ -37,6 +37,8 @@ SIGNATURES = {
     "fegpu_bilform_diffusion": (C.c_int32, [VP, VP, C.c_int32, VP, VP]),
     "fegpu_bilform_lin_elastic": (C.c_int32, [VP, VP, VP, VP]),
     "fegpu_bilform_dot": (C.c_int32, [VP, VP, VP, C.c_int32, C.c_double, VP]),
+    "fegpu_bilform_convection": (C.c_int32, [VP, VP, VP, C.c_double, VP]),
+    "fegpu_bilform_div_grad": (C.c_int32, [VP, VP, C.c_double, VP]),
     "fegpu_startassembly": (C.c_int32, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "fegpu_assemble": (C.c_int32, [VP, VP, VP, C.c_int64, VP, C.c_int64]),
     "fegpu_triplets_append": (C.c_int32, [VP, C.c_int64, VP, VP, VP]),

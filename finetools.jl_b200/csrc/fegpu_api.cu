@@ -322,6 +322,7 @@ int32_t fegpu_mesh_upload(fegpu_ctx *ctx, int32_t etype, int64_t nelem, const in
 int32_t fegpu_mesh_destroy(fegpu_mesh *m) {
   if (!m) return FEGPU_OK;
   DeviceGuard g(m->ctx->device);
+  cudaFree(m->d_uvel);
   cudaFree(m->d_conn); cudaFree(m->d_xyz); cudaFree(m->d_tab); cudaFree(m->d_w); cudaFree(m->d_elem_list); cudaFree(m->d_rowowned);
   delete m;
   return FEGPU_OK;
@@ -604,7 +605,7 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
   if (as->symmetric) {
     // SysmatAssemblerSparseSymm: the element matrices of these forms are symmetric, so S + transpose(S) (diagonal halved) is
     // the full assembly up to summation order; what differs is the pattern: entries that sum to exactly 0.0 are not stored
-    bool symm = fe_form_symmetric(fa.form);
+    bool symm = fe_form_values_symmetric(fa.form);
     if (fa.form == FORM_DOT) {  // bilform_dot is symmetric exactly when its ndn x ndn coefficient is
       symm = true;
       for (int p = 0; p < fa.ndn; p++)
@@ -655,6 +656,40 @@ int32_t fegpu_bilform_dot(fegpu_mesh *mesh, fegpu_dofmap *dm, const double *c, i
   for (int i = 0; i < dm->ndn * dm->ndn; i++) fa.coef[i] = c[i];
   fa.m = m;
   fa.otherdim = otherdim;
+  return run_bilform(mesh, dm, fa, as);
+}
+
+int32_t fegpu_bilform_convection(fegpu_mesh *mesh, fegpu_dofmap *dm, const double *uvel, double rho, fegpu_asm *as) {
+  if (!mesh || !dm || !uvel) return fegpu_fail(mesh ? mesh->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  if (mesh->sdim != mesh->mdim) return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "bilform_convection needs sdim == manifold dimension");
+  fegpu_ctx *ctx = mesh->ctx;
+  DeviceGuard g(ctx->device);
+  const size_t n = (size_t)mesh->nnodes * mesh->sdim;
+  if (!mesh->d_uvel) CUDA_TRY(ctx, cudaMalloc((void **)&mesh->d_uvel, sizeof(double) * std::max<size_t>(n, 1)));
+  if (n) CUDA_TRY(ctx, cudaMemcpyAsync(mesh->d_uvel, uvel, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the host array may go away after return
+  FormArgs fa;
+  std::memset(&fa, 0, sizeof(fa));
+  fa.form = FORM_CONVECTION;
+  fa.ndn = 1;
+  fa.coef[0] = rho;  // evaluated by the reference but not used in its integrand (FEMMBaseModule.jl:1606-1617)
+  fa.m = 3;
+  fa.otherdim = 1.0;
+  fa.d_uvel = mesh->d_uvel;
+  return run_bilform(mesh, dm, fa, as);
+}
+
+int32_t fegpu_bilform_div_grad(fegpu_mesh *mesh, fegpu_dofmap *dm, double mu, fegpu_asm *as) {
+  if (!mesh || !dm) return fegpu_fail(mesh ? mesh->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  if (mesh->sdim != mesh->mdim) return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "bilform_div_grad needs sdim == manifold dimension");
+  if (dm->ndn != mesh->sdim) return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "bilform_div_grad needs one dof per space dimension at every node");
+  FormArgs fa;
+  std::memset(&fa, 0, sizeof(fa));
+  fa.form = FORM_DIV_GRAD;
+  fa.ndn = dm->ndn;
+  fa.coef[0] = mu;
+  fa.m = 3;
+  fa.otherdim = 1.0;
   return run_bilform(mesh, dm, fa, as);
 }
 

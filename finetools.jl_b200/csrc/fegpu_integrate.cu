@@ -31,6 +31,7 @@ struct IntegParams {
   double coef[36];
   int m;
   double otherdim;
+  const double *uvel;        // [SDIM][nnodes] convective velocity (FORM_CONVECTION)
 };
 
 template <int TPE>
@@ -97,11 +98,11 @@ __device__ __forceinline__ void bcol(int comp, const double *g, int rows[3], dou
 template <int NNE, int MDIM, int SDIM, int NDN, int FORM, int TPE>
 __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const IntegParams P) {
   constexpr int EM = NNE * NDN;
-  constexpr bool SYM = (FORM != FORM_DOT);
+  constexpr bool SYM = (FORM == FORM_DIFF_ISO || FORM == FORM_DIFF_GEN || FORM == FORM_ELASTIC);
   constexpr int NENT = SYM ? EM * (EM + 1) / 2 : EM * EM;
   constexpr int EPT = (NENT + TPE - 1) / TPE;
   constexpr int GPB = (TPE <= 32) ? 128 / TPE : 1;  // element groups per block
-  constexpr int NAUX = (FORM == FORM_ELASTIC) ? 6 * EM : (FORM == FORM_DIFF_GEN ? MDIM * NNE : 1);
+  constexpr int NAUX = (FORM == FORM_ELASTIC) ? 6 * EM : (FORM == FORM_DIFF_GEN ? MDIM * NNE : (FORM == FORM_CONVECTION ? NNE * SDIM : 1));
 
   extern __shared__ double smem[];
   // layout: tables [npts*NNE*(1+MDIM)] | w [npts] | per group: X [NNE*SDIM], G [NNE*MDIM], AUX [NAUX]
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
     for (int i = t; i < NNE * SDIM; i += TPE) {
       int a = i % NNE, s = i / NNE;
       sX[a * SDIM + s] = P.xyz[(int64_t)s * P.nnodes + conn[a]];
+      if (FORM == FORM_CONVECTION) sA[a * SDIM + s] = P.uvel[(int64_t)s * P.nnodes + conn[a]];  // gathervalues_asmat!(u, eus, conn)
     }
     group_sync<TPE>();
 
@@ -200,6 +202,16 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
           }
         }
         group_sync<TPE>();
+        double us[SDIM];
+        if (FORM == FORM_CONVECTION) {
+          // u_s = sum_q Ns[q] * eus[q, s]                                            FEMMBaseModule.jl:1611-1614
+#pragma unroll
+          for (int s = 0; s < SDIM; s++) {
+            double a = 0.0;
+            for (int q = 0; q < NNE; q++) a += N[q] * sA[q * SDIM + s];
+            us[s] = a;
+          }
+        }
         if (FORM == FORM_DIFF_GEN) {
           // kappa_bargradNT[mx, nx] = Jac_w * sum_px kappa[mx,px]*gradN[nx,px]     MatrixUtilityModule.jl:134-142
           for (int i = t; i < MDIM * NNE; i += TPE) {
@@ -239,6 +251,21 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
 #pragma unroll
             for (int px = 0; px < MDIM; px++) a += sG[r * MDIM + px] * sA[px + MDIM * c];
             acc[k] += a;
+          } else if (FORM == FORM_CONVECTION) {
+            // elmat[p, r] += Ns[p] * (sum_s u_s * gradN[r, s]) * (Jac * w)               FEMMBaseModule.jl:1608-1618
+            double a = 0.0;
+#pragma unroll
+            for (int s = 0; s < SDIM; s++) a += us[s] * sG[c * MDIM + s];
+            acc[k] += N[r] * a * Jw;
+          } else if (FORM == FORM_DIV_GRAD) {
+            // p = (a, s), r = (b, t): factor * (delta_st * sum_q gradN[a,q] gradN[b,q] + gradN[a,t] gradN[b,s])   :1694-1707
+            const double factor = P.coef[0] * Jw;
+            const int na = r / NDN, s = r % NDN, nb = c / NDN, tt = c % NDN;
+            if (s == tt) {
+#pragma unroll
+              for (int q = 0; q < NDN; q++) acc[k] += factor * sG[na * MDIM + q] * sG[nb * MDIM + q];
+            }
+            acc[k] += factor * sG[na * MDIM + tt] * sG[nb * MDIM + s];
           } else {  // FORM_ELASTIC: accum = sum_px B[px,mx]*DB[px,nx]
             int rows[3];
             double vals[3];
@@ -284,13 +311,13 @@ int32_t launch_generic(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
   fegpu_ctx *ctx = mesh->ctx;
   constexpr int EM = NNE * NDN;
   constexpr int GPB = (TPE <= 32) ? 128 / TPE : 1;
-  constexpr int NAUX = (FORM == FORM_ELASTIC) ? 6 * EM : (FORM == FORM_DIFF_GEN ? MDIM * NNE : 1);
+  constexpr int NAUX = (FORM == FORM_ELASTIC) ? 6 * EM : (FORM == FORM_DIFF_GEN ? MDIM * NNE : (FORM == FORM_CONVECTION ? NNE * SDIM : 1));
   IntegParams P;
   P.conn = mesh->d_conn; P.xyz = mesh->d_xyz; P.nnodes = mesh->nnodes; P.elem_list = mesh->d_elem_list;
   P.nactive = mesh->nactive; P.tab = mesh->d_tab; P.w = mesh->d_w; P.npts = mesh->npts; P.V = d_V;
-  P.compact = (fa.compact && FORM != FORM_DOT) ? 1 : 0;
+  P.compact = (fa.compact && fe_form_symmetric(FORM)) ? 1 : 0;
   for (int i = 0; i < 36; i++) P.coef[i] = fa.coef[i];
-  P.m = fa.m; P.otherdim = fa.otherdim;
+  P.m = fa.m; P.otherdim = fa.otherdim; P.uvel = fa.d_uvel;
   if (mesh->nactive == 0) return FEGPU_OK;
   size_t smem = sizeof(double) * ((size_t)mesh->npts * NNE * (1 + MDIM) + mesh->npts + (size_t)GPB * (NNE * SDIM + NNE * MDIM + NAUX));
   auto kern = k_integrate<NNE, MDIM, SDIM, NDN, FORM, TPE>;
@@ -321,6 +348,12 @@ int32_t dispatch_form(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
       if (fa.ndn == 2) return launch_generic<NNE, MDIM, SDIM, 2, FORM_DOT, TPE_V>(mesh, fa, d_V);
       if (fa.ndn == 3) return launch_generic<NNE, MDIM, SDIM, 3, FORM_DOT, TPE_V>(mesh, fa, d_V);
       return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "bilform_dot: 1, 2 or 3 dofs per node are supported");
+    case FORM_CONVECTION:
+      if (SDIM != MDIM) break;
+      return launch_generic<NNE, MDIM, (SDIM == MDIM ? SDIM : MDIM), 1, FORM_CONVECTION, TPE_S>(mesh, fa, d_V);
+    case FORM_DIV_GRAD:
+      if (SDIM != MDIM) break;
+      return launch_generic<NNE, MDIM, (SDIM == MDIM ? SDIM : MDIM), (SDIM == MDIM ? SDIM : MDIM), FORM_DIV_GRAD, TPE_V>(mesh, fa, d_V);
   }
   return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "form not defined for this element manifold / space dimension");
 }

@@ -37,6 +37,7 @@ struct fegpu_mesh {
   int64_t nelem = 0, nnodes = 0;
   int32_t *d_conn = nullptr;  // [nelem][nne] 0-based
   double *d_xyz = nullptr;    // [sdim][nnodes]
+  double *d_uvel = nullptr;   // [sdim][nnodes] nodal field of bilform_convection (fegpu_bilform_convection uploads it)
   // quadrature tables (device copy): N [npts][nne], dN [npts][mdim][nne], w [npts]
   int npts = 0;
   double *d_tab = nullptr;  // N then dN
@@ -134,20 +135,24 @@ int32_t fe_exclusive_scan_i32_to_i64(fegpu_ctx *ctx, const int32_t *d_in, int64_
 int32_t fe_max_i32(fegpu_ctx *ctx, const int32_t *d_in, int64_t n, int32_t *max_host);
 
 // ---- integration (fegpu_integrate.cu) ------------------------------------------------------------------
-enum { FORM_DIFF_ISO = 0, FORM_DIFF_GEN = 1, FORM_ELASTIC = 2, FORM_DOT = 3 };
+enum { FORM_DIFF_ISO = 0, FORM_DIFF_GEN = 1, FORM_ELASTIC = 2, FORM_DOT = 3, FORM_CONVECTION = 4, FORM_DIV_GRAD = 5 };
 struct FormArgs {
   int form;
   int ndn;
   double coef[36];  // kappa (mdim x mdim col-major) | C (6x6 col-major) | c (ndn x ndn col-major); coef[0] = scalar kappa
   int m;            // bilform_dot manifold dimension
   double otherdim;
+  const double *d_uvel = nullptr;  // bilform_convection: nodal convective velocity on the device, [sdim][nnodes]
   bool compact;     // symmetric forms only: write the compact upper-block layout (fe_compact_size) instead of full matrices
 };
 // Compact layout of a symmetric element matrix (nne nodes x ndn dofs): the upper block triangle, block (a <= b) of
 // ndn x ndn values (column-major: row comp i, col comp j at j*ndn + i) at ndn*ndn*(b(b+1)/2 + a); diagonal blocks are stored
 // in full (mirrored).  This is what the symmetric forms write on the mesh-structured path: (1 + 1/nne)/2 of the bytes.
 static inline int fe_compact_size(int nne, int ndn) { return nne * (nne + 1) / 2 * ndn * ndn; }
-static inline bool fe_form_symmetric(int form) { return form != 3 /* FORM_DOT */; }
+// forms whose kernels compute the upper triangle once and mirror it (they may write the compact layout); bilform_div_grad's
+// element matrices are symmetric too but the reference forms them in full (FEMMBaseModule.jl:1694-1707), and so do we
+static inline bool fe_form_symmetric(int form) { return form <= 2; }
+static inline bool fe_form_values_symmetric(int form) { return form <= 2 || form == 5; }
 int32_t fe_integrate(fegpu_mesh *mesh, const FormArgs &fa, double *d_V);
 // does the integration kernel that will run write the compact symmetric layout when fa.compact is set?
 bool fe_integrate_supports_compact(const fegpu_mesh *mesh, const FormArgs &fa);

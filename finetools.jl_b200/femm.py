@@ -1,7 +1,7 @@
-"""FEMMBase and the three bilinear forms, dispatched to the GPU when the assembler is a SysmatAssemblerSparseGPU.
+"""FEMMBase and its bilinear forms, dispatched to the GPU when the assembler is a SysmatAssemblerSparseGPU.
 
 Mirrors src/FEMMBaseModule.jl: FEMMBase :72-84, bilform_dot :1335-1366, innerproduct :1388-1401, bilform_diffusion
-:1462-1535, bilform_lin_elastic :1774-1813.  User code keeps the reference's call shape
+:1462-1535, bilform_convection :1583-1625, bilform_div_grad :1672-1713, bilform_lin_elastic :1774-1813.  User code keeps the reference's call shape
     K = bilform_diffusion(femm, assembler, geom, u, DataCache(kappa))
 The eligibility checks of SURVEY.md section 8(b) raise instead of silently falling back to a CPU loop.
 """
@@ -224,6 +224,33 @@ def bilform_dot(self, assembler, geom, u, cf, m=3, raw=False, node_owner=None, m
     cfm = np.asfortranarray(c)
     check(_lib.lib().fegpu_bilform_dot(dmesh.handle, dof, fptr(cfm), int(m), float(self.integdomain.otherdimension), _inner(assembler).handle),
           assembler.ctx.handle)
+    return _finish(assembler, fes, dmesh, dof, u, raw, out)
+
+
+def bilform_convection(self, assembler, geom, u, Q, rhof, raw=False, node_owner=None, my_rank=0, out=None):
+    """K_pr = int N_p (u . grad N_r): u = nodal convective velocity field, Q = scalar field that numbers the dofs
+    (FEMMBaseModule.jl:1583-1625).  Non-symmetric: the symmetric assembler refuses it."""
+    _eligible(self, assembler, geom, Q, rhof)
+    if Q.ndofs() != 1:
+        raise FEGPUError(-15, "Wrong size of matrix")
+    fes, dmesh, dof = _prepare(self, assembler, geom, Q, node_owner, my_rank)
+    sdim = geom.values.shape[1]
+    if fes.mdim != sdim or u.values.shape != (geom.values.shape[0], sdim):
+        raise FEGPUError(-2, "bilform_convection needs a velocity component per space dimension and sdim == manifold dimension")
+    uv = _lib.colmajor_f64(u.values)
+    check(_lib.lib().fegpu_bilform_convection(dmesh.handle, dof, fptr(uv), float(rhof.data), _inner(assembler).handle), assembler.ctx.handle)
+    return _finish(assembler, fes, dmesh, dof, Q, raw, out)
+
+
+def bilform_div_grad(self, assembler, geom, u, viscf, raw=False, node_owner=None, my_rank=0, out=None):
+    """G = int mu (grad w : grad u + grad w : grad u^T), vector field with one dof per space dimension
+    (FEMMBaseModule.jl:1672-1713)."""
+    _eligible(self, assembler, geom, u, viscf)
+    fes, dmesh, dof = _prepare(self, assembler, geom, u, node_owner, my_rank)
+    sdim = geom.values.shape[1]
+    if fes.mdim != sdim or u.ndofs() != sdim:
+        raise FEGPUError(-2, "bilform_div_grad needs one dof per space dimension and sdim == manifold dimension")
+    check(_lib.lib().fegpu_bilform_div_grad(dmesh.handle, dof, float(viscf.data), _inner(assembler).handle), assembler.ctx.handle)
     return _finish(assembler, fes, dmesh, dof, u, raw, out)
 
 

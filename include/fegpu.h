@@ -105,6 +105,12 @@ int32_t fegpu_bilform_lin_elastic(fegpu_mesh *mesh, fegpu_dofmap *dofmap, const 
 /* bilform_dot, FEMMBaseModule.jl:1335-1366.  c: ndn x ndn col-major; m: manifold dimension kwarg;
  * otherdim: the constant other-dimension of the IntegDomain (IntegDomainModule.jl:150-152: 1.0) */
 int32_t fegpu_bilform_dot(fegpu_mesh *mesh, fegpu_dofmap *dofmap, const double *c, int32_t m, double otherdim, fegpu_asm *as);
+/* bilform_convection, FEMMBaseModule.jl:1583-1625.  dofmap: the scalar field Q (1 dof per node);
+ * uvel: nodal values of the convective velocity field u, nnodes x sdim col-major (NodalField.values), copied to the device
+ * by the call; rho: the constant of rhof (evaluated by the reference but absent from its integrand).  Non-symmetric. */
+int32_t fegpu_bilform_convection(fegpu_mesh *mesh, fegpu_dofmap *dofmap, const double *uvel, double rho, fegpu_asm *as);
+/* bilform_div_grad, FEMMBaseModule.jl:1672-1713.  dofmap: vector field with sdim dofs per node; mu: constant viscosity */
+int32_t fegpu_bilform_div_grad(fegpu_mesh *mesh, fegpu_dofmap *dofmap, double mu, fegpu_asm *as);
 
 /* Generic assembler protocol for any other caller (AssemblyModule.jl:209-282): host triplets are staged to
  * the device and the CSC is built there by a 64-bit key sort + segmented sum. */

@@ -696,6 +696,134 @@ ORC_API int orc_bilform_dot(int et, int64_t nelem, const int64_t *conn, int64_t 
   return rc;
 }
 
+/* bilform_convection: FEMMBaseModule.jl:1583-1625.  Scalar field Q (1 dof/node), convective velocity u given at the nodes
+ * (uvals nnodes x nsd col-major, nsd = sdim), rho constant.  Non-symmetric: the full element matrix is formed. */
+ORC_API int orc_bilform_convection(int et, int64_t nelem, const int64_t *conn, int64_t nnodes, int sdim, const double *xyz,
+                                   const double *uvals, int nsd, const int64_t *dofnums, int64_t nalldofs, int npts, const double *pc,
+                                   const double *w, double rho, int64_t *I, int64_t *J, double *V) {
+  formctx f;
+  if (form_setup(&f, et, nelem, conn, nnodes, sdim, xyz, 1, dofnums, nalldofs, npts, pc, w)) return -1;
+  int nne = f.nne, mdim = f.mdim;
+  if (sdim != mdim || nsd != sdim) { form_free(&f); return -2; }
+  double ecoords[27 * 3], eus[27 * 3], loc[3], Jm[9], gradN[27 * 3];
+  double *elmat = (double *)malloc(sizeof(double) * nne * nne);
+  int64_t dofs[27];
+  int64_t p = 0;
+  int rc = 0;
+  (void)rho; /* the reference evaluates rhof but never uses the value: FEMMBaseModule.jl:1606-1617 */
+  for (int64_t i = 0; i < nelem && !rc; i++) {
+    gather_elem(&f, i, ecoords, dofs);
+    const int64_t *c = f.conn + i * nne;
+    for (int a = 0; a < nne; a++)
+      for (int s = 0; s < nsd; s++) eus[a + nne * s] = uvals[(c[a] - 1) + nnodes * s]; /* gathervalues_asmat!(u, eus, conn) :1599 */
+    memset(elmat, 0, sizeof(double) * nne * nne);
+    for (int j = 0; j < npts; j++) {
+      const double *N = f.Ns + (size_t)j * nne, *dN = f.dNs + (size_t)j * nne * mdim;
+      locjac(loc, Jm, ecoords, N, dN, nne, sdim, mdim);
+      double Jac = (mdim == 3) ? jacobian3(Jm) : jacobian2(Jm, sdim) * 1.0;
+      if (mdim == 3) gradN3(gradN, dN, Jm, nne); else gradN2(gradN, dN, Jm, nne);
+      for (int pp = 0; pp < nne; pp++)
+        for (int r = 0; r < nne; r++) {
+          double accum = 0.0;
+          for (int s = 0; s < nsd; s++) {
+            double u_s = 0.0;
+            for (int q = 0; q < nne; q++) u_s += N[q] * eus[q + nne * s];
+            accum += u_s * gradN[r + nne * s];
+          }
+          elmat[pp + (size_t)nne * r] += N[pp] * accum * (Jac * w[j]);
+        }
+    }
+    rc = assemble(I, J, V, &p, elmat, dofs, nne, dofs, nne, nalldofs, nalldofs);
+  }
+  free(elmat);
+  form_free(&f);
+  return rc;
+}
+
+/* bilform_div_grad: FEMMBaseModule.jl:1672-1713.  Vector field u with ndn = sdim dofs per node, constant viscosity mu. */
+ORC_API int orc_bilform_div_grad(int et, int64_t nelem, const int64_t *conn, int64_t nnodes, int sdim, const double *xyz, int ndn,
+                                 const int64_t *dofnums, int64_t nalldofs, int npts, const double *pc, const double *w, double mu,
+                                 int64_t *I, int64_t *J, double *V) {
+  formctx f;
+  if (form_setup(&f, et, nelem, conn, nnodes, sdim, xyz, ndn, dofnums, nalldofs, npts, pc, w)) return -1;
+  int nne = f.nne, mdim = f.mdim;
+  if (sdim != mdim || ndn != sdim) { form_free(&f); return -2; }
+  int K = ndn * nne;
+  double ecoords[27 * 3], loc[3], Jm[9], gradN[27 * 3];
+  double *elmat = (double *)malloc(sizeof(double) * K * K);
+  int64_t dofs[81];
+  int64_t p = 0;
+  int rc = 0;
+  for (int64_t i = 0; i < nelem && !rc; i++) {
+    gather_elem(&f, i, ecoords, dofs);
+    memset(elmat, 0, sizeof(double) * K * K);
+    for (int j = 0; j < npts; j++) {
+      const double *N = f.Ns + (size_t)j * nne, *dN = f.dNs + (size_t)j * nne * mdim;
+      locjac(loc, Jm, ecoords, N, dN, nne, sdim, mdim);
+      double Jac = (mdim == 3) ? jacobian3(Jm) : jacobian2(Jm, sdim) * 1.0;
+      if (mdim == 3) gradN3(gradN, dN, Jm, nne); else gradN2(gradN, dN, Jm, nne);
+      double factor = mu * (Jac * w[j]);
+      for (int a = 0; a < nne; a++)
+        for (int b = 0; b < nne; b++)
+          for (int s = 0; s < ndn; s++) {
+            int pr = a * ndn + s, r = b * ndn + s;
+            for (int q = 0; q < ndn; q++) elmat[pr + (size_t)K * r] += factor * gradN[a + nne * q] * gradN[b + nne * q];
+            for (int q = 0; q < ndn; q++) {
+              r = b * ndn + q;
+              elmat[pr + (size_t)K * r] += factor * gradN[a + nne * q] * gradN[b + nne * s];
+            }
+          }
+    }
+    rc = assemble(I, J, V, &p, elmat, dofs, K, dofs, K, nalldofs, nalldofs);
+  }
+  free(elmat);
+  form_free(&f);
+  return rc;
+}
+
+/* linform_dot (= distribloads with a constant ForceIntensity): FEMMBaseModule.jl:1207-1244, SysvecAssembler
+ * AssemblyModule.jl:853-917.  force is ndn values; F has nalldofs entries (zeroed here like startassembly!). */
+ORC_API int orc_linform_dot(int et, int64_t nelem, const int64_t *conn, int64_t nnodes, int sdim, const double *xyz, int ndn,
+                            const int64_t *dofnums, int64_t nalldofs, int npts, const double *pc, const double *w, const double *force,
+                            int m, double otherdim, double *F) {
+  formctx f;
+  if (form_setup(&f, et, nelem, conn, nnodes, sdim, xyz, ndn, dofnums, nalldofs, npts, pc, w)) return -1;
+  int nne = f.nne, mdim = f.mdim;
+  int K = ndn * nne;
+  if ((mdim == 3 && m != 3) || (mdim == 2 && (m < 2 || m > 3))) { form_free(&f); return -3; }
+  double ecoords[27 * 3], loc[3], Jm[9];
+  double *elvec = (double *)malloc(sizeof(double) * K);
+  int64_t *dofs = (int64_t *)malloc(sizeof(int64_t) * K);
+  for (int64_t k = 0; k < nalldofs; k++) F[k] = 0.0;
+  int rc = 0;
+  for (int64_t i = 0; i < nelem && !rc; i++) {
+    gather_elem(&f, i, ecoords, dofs);
+    for (int k = 0; k < K; k++) elvec[k] = 0.0;
+    for (int j = 0; j < npts; j++) {
+      const double *N = f.Ns + (size_t)j * nne, *dN = f.dNs + (size_t)j * nne * mdim;
+      locjac(loc, Jm, ecoords, N, dN, nne, sdim, mdim);
+      double Jac;
+      if (mdim == 3) Jac = jacobian3(Jm);
+      else { Jac = jacobian2(Jm, sdim); if (m == 3) Jac = Jac * otherdim; }
+      double Factor = (Jac * w[j]);
+      int rx = 0;
+      for (int kx = 0; kx < nne; kx++) {
+        double NkxF = N[kx] * Factor;
+        for (int mx = 0; mx < ndn; mx++) { elvec[rx] = elvec[rx] + NkxF * force[mx]; rx++; }
+      }
+    }
+    for (int k = 0; k < K && !rc; k++) { /* assemble!(::SysvecAssembler, vec, dofnums) :899-906 */
+      int64_t gi = dofs[k];
+      if (gi < 1) rc = 3;
+      else if (gi > nalldofs) rc = 4;
+      else F[gi - 1] += elvec[k];
+    }
+  }
+  free(elvec); free(dofs);
+  form_free(&f);
+  return rc;
+}
+
 /* ------------------------------------------------------ sparse(I,J,V,m,n) */
 /* Restatement of Julia's SparseArrays.sparse!(I,J,V,m,n,+) (stdlib, pinned by Julia ^1.12, not vendored in the
  * reference; call site AssemblyModule.jl:319-325).  Published algorithm (after Tim Davis' CSparse / HALFPERM):

@@ -73,6 +73,9 @@ def lib():
         L.orc_bilform_lin_elastic.argtypes = common + [_i64p, C.c_int64, C.c_int, _f64p, _f64p, _f64p, _i64p, _i64p, _f64p]
         L.orc_bilform_dot.argtypes = common + [C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double,
                                                _i64p, _i64p, _f64p]
+        L.orc_bilform_convection.argtypes = common + [_f64p, C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, C.c_double, _i64p, _i64p, _f64p]
+        L.orc_bilform_div_grad.argtypes = common + [C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, C.c_double, _i64p, _i64p, _f64p]
+        L.orc_linform_dot.argtypes = common + [C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double, _f64p]
         L.orc_sparse.argtypes = [C.c_int64, _i64p, _i64p, _f64p, C.c_int64, C.c_int64, _i64p, C.c_void_p, C.c_void_p]
         L.orc_sparse.restype = C.c_int64
         _lib = L
@@ -171,6 +174,43 @@ def bilform_dot_coo(et, conn, xyz, dofnums, nalldofs, pc, w, c, m=3, otherdim=1.
     if rc:
         raise RuntimeError(_ERR.get(rc, "oracle error %d" % rc))
     return I, J, V
+
+
+def bilform_convection_coo(et, conn, xyz, uvals, dofnums, nalldofs, pc, w, rho=1.0):
+    """Reference-order COO triplets of bilform_convection (FEMMBaseModule.jl:1583-1625); uvals = nodal velocities nnodes x sdim."""
+    conn, nelem, nne, X, nnodes, sdim, dn, ndn, P, W, npts = _prep(et, conn, xyz, dofnums, pc, w)
+    assert ndn == 1
+    uv = np.asarray(uvals, dtype=np.float64).reshape(nnodes, -1)
+    n = nelem * nne * nne
+    I, J, V = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n)
+    rc = lib().orc_bilform_convection(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, _F(uv), uv.shape[1], dn, nalldofs, npts, P, W,
+                                      float(rho), I, J, V)
+    if rc:
+        raise RuntimeError(_ERR.get(rc, "oracle error %d" % rc))
+    return I, J, V
+
+
+def bilform_div_grad_coo(et, conn, xyz, dofnums, nalldofs, pc, w, mu):
+    """Reference-order COO triplets of bilform_div_grad (FEMMBaseModule.jl:1672-1713)."""
+    conn, nelem, nne, X, nnodes, sdim, dn, ndn, P, W, npts = _prep(et, conn, xyz, dofnums, pc, w)
+    n = nelem * (ndn * nne) ** 2
+    I, J, V = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n)
+    rc = lib().orc_bilform_div_grad(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, ndn, dn, nalldofs, npts, P, W, float(mu), I, J, V)
+    if rc:
+        raise RuntimeError(_ERR.get(rc, "oracle error %d" % rc))
+    return I, J, V
+
+
+def linform_dot(et, conn, xyz, dofnums, nalldofs, pc, w, force, m=3, otherdim=1.0):
+    """The assembled vector of linform_dot / distribloads with a constant force (FEMMBaseModule.jl:1207-1244)."""
+    conn, nelem, nne, X, nnodes, sdim, dn, ndn, P, W, npts = _prep(et, conn, xyz, dofnums, pc, w)
+    fv = np.ascontiguousarray(np.asarray(force, dtype=np.float64).reshape(-1))
+    assert fv.size == ndn
+    F = np.zeros(nalldofs)
+    rc = lib().orc_linform_dot(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, ndn, dn, nalldofs, npts, P, W, fv, m, otherdim, F)
+    if rc:
+        raise RuntimeError(_ERR.get(rc, "oracle error %d" % rc))
+    return F
 
 
 _ERR = {1: "Column degree of freedom < 1", 2: "Column degree of freedom > size", 3: "Row degree of freedom < 1",

@@ -16,6 +16,10 @@ def oracle_csc(orc, form, etname, fes, fens, u, rule, coef, **kw):
         I, J, V = orc.bilform_diffusion_coo(etname, fes.conn, fens.xyz, u.dofnums, n, rule.param_coords, rule.weights, coef)
     elif form == "elastic":
         I, J, V = orc.bilform_lin_elastic_coo(etname, fes.conn, fens.xyz, u.dofnums, n, rule.param_coords, rule.weights, coef)
+    elif form == "convection":  # coef = nodal velocity values (nnodes x sdim)
+        I, J, V = orc.bilform_convection_coo(etname, fes.conn, fens.xyz, coef, u.dofnums, n, rule.param_coords, rule.weights, 1.0)
+    elif form == "div_grad":
+        I, J, V = orc.bilform_div_grad_coo(etname, fes.conn, fens.xyz, u.dofnums, n, rule.param_coords, rule.weights, coef)
     else:
         I, J, V = orc.bilform_dot_coo(etname, fes.conn, fens.xyz, u.dofnums, n, rule.param_coords, rule.weights, coef, **kw)
     return orc.sparse(I, J, V, n, n), (I, J, V)
@@ -29,6 +33,10 @@ def gpu_csc(fe, form, fes, fens, u, rule, coef, assembler=None, m=3, **kw):
         out = fe.bilform_diffusion(femm, a, geom, u, fe.DataCache(coef), raw=True, **kw)
     elif form == "elastic":
         out = fe.bilform_lin_elastic(femm, a, geom, u, fe.DeforModelRed3D, fe.DataCache(coef), raw=True, **kw)
+    elif form == "convection":
+        out = fe.bilform_convection(femm, a, geom, fe.NodalField(coef), u, fe.DataCache(1.0), raw=True, **kw)
+    elif form == "div_grad":
+        out = fe.bilform_div_grad(femm, a, geom, u, fe.DataCache(coef), raw=True, **kw)
     else:
         out = fe.bilform_dot(femm, a, geom, u, fe.DataCache(coef), m=m, raw=True, **kw)
     return out, a

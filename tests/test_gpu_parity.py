@@ -648,3 +648,93 @@ def test_planar_dot_parity(fe, orc, gpu_ctx, et):
         ref, _ = oracle_csc(orc, "dot", et, fes, fens, u, rule, c, m=m, otherdim=1.0)
         got, _ = gpu_csc(fe, "dot", fes, fens, u, rule, c, m=m)
         assert_parity(ref, got)
+
+
+def _planar_mesh(fe, et):
+    fens, fes = (fe.Q4block(2.0, 3.0, 5, 4) if et == "Q4" else fe.T3block(2.0, 3.0, 5, 4))
+    x = fens.xyz
+    x[:, 0] += 0.04 * np.sin(3 * x[:, 1])
+    x[:, 1] += 0.04 * np.sin(2 * x[:, 0])
+    return fens, fes
+
+
+@pytest.mark.parametrize("et", ["H8", "H20", "T4", "T10", "Q4", "T3"])
+def test_convection_parity(fe, orc, gpu_ctx, et):
+    """bilform_convection (FEMMBaseModule.jl:1583-1625): non-symmetric scalar form with a nodal velocity
+    field; pattern bit-exact, values within 1e-12; plus the reference's own identity Psi' K Q = (u . grad q) V for linear q
+    (test/test_forms.jl:196-231)."""
+    planar = et in ("Q4", "T3")
+    if planar:
+        fens, fes = _planar_mesh(fe, et)
+        rule = fe.GaussRule(2, 2) if et == "Q4" else fe.TriRule(3)
+    else:
+        fens, fes = _mesh(fe, et)
+        _distort(fens)
+        rule = _rule(fe, et)
+    sdim = fens.xyz.shape[1]
+    q = make_field(fe, fens, 1)
+    x = fens.xyz
+    uvals = np.stack([3.1 + 0.2 * x[:, 1], -2.7 + 0.1 * x[:, 0], 0.4 - 0.3 * x[:, 0]][:sdim], axis=1)
+    ref, _ = oracle_csc(orc, "convection", et, fes, fens, q, rule, uvals)
+    got, _ = gpu_csc(fe, "convection", fes, fens, q, rule, uvals)
+    assert_parity(ref, got)
+    # identity with a constant velocity and linear q, on the undistorted block (known volume)
+    uc = np.tile([3.1, -2.7, 0.4][:sdim], (fens.count(), 1))
+    if not planar:
+        import scipy.sparse as sp
+        fens2, fes2 = _mesh(fe, et)
+        q2 = make_field(fe, fens2, 1)
+        got, _ = gpu_csc(fe, "convection", fes2, fens2, q2, rule, uc)
+        n = q2.nalldofs()
+        K = sp.csc_matrix((got[2], got[1] - 1, got[0] - 1), shape=(n, n))
+        grad = np.array([0.3, 0.4, 0.5])
+        Q = np.zeros(n)
+        Q[q2.dofnums[:, 0] - 1] = -0.1 + fens2.xyz @ grad
+        vol = 1.3 * 3.1 * 2.7
+        assert abs(np.ones(n) @ (K @ Q) - (grad @ uc[0]) * vol) <= 1e-9 * vol
+    with pytest.raises(fe.FEGPUError):  # "must be able to assemble unsymmetric matrices", FEMMBaseModule.jl:1634
+        gpu_csc(fe, "convection", fes, fens, q, rule, uc, assembler=fe.SysmatAssemblerSparseSymmGPU(0.0))
+
+
+@pytest.mark.parametrize("et", ["H8", "H20", "H27", "T4", "T10", "Q4", "T3"])
+def test_div_grad_parity(fe, orc, gpu_ctx, et):
+    """bilform_div_grad (FEMMBaseModule.jl:1672-1713): parity with the oracle; the reference's identities v' G v = 0 for a
+    constant field and = 2 mu V |sym grad u|^2 for a linear one (test/test_forms.jl:234-300) on the undistorted hexahedra."""
+    planar = et in ("Q4", "T3")
+    if planar:
+        fens, fes = _planar_mesh(fe, et)
+        rule = fe.GaussRule(2, 2) if et == "Q4" else fe.TriRule(3)
+    else:
+        fens, fes = _mesh(fe, et, 2)
+        _distort(fens)
+        rule = _rule(fe, et)
+    sdim = fens.xyz.shape[1]
+    u = make_field(fe, fens, sdim)
+    mu = 0.13377
+    ref, _ = oracle_csc(orc, "div_grad", et, fes, fens, u, rule, mu)
+    got, _ = gpu_csc(fe, "div_grad", fes, fens, u, rule, mu)
+    assert_parity(ref, got)
+    import scipy.sparse as sp
+    n = u.nalldofs()
+    G = sp.csc_matrix((got[2], got[1] - 1, got[0] - 1), shape=(n, n))
+    vc = np.zeros(n)
+    vc[u.dofnums - 1] = np.array([3.1, -2.7, -0.77][:sdim])
+    assert abs(vc @ (G @ vc)) <= 1e-9 * np.abs(got[2]).max() * n
+    assert abs(G - G.T).max() <= 1e-14 * np.abs(got[2]).max()  # symmetric to rounding ((factor*g_a)*g_b vs (factor*g_b)*g_a), as in the reference
+    if et == "H8":
+        W, L, t = 11.1, 12.0, 7.32
+        fens, fes = fe.H8block(L, W, t, 2, 4, 3)
+        u = make_field(fe, fens, 3)
+        a, b, c, d = (-0.33, 2 / 3, -1.67, 2 / 7)
+        x = fens.xyz
+        vals = np.stack([a + b * x[:, 0] + c * x[:, 1] + d * x[:, 2], b + c * x[:, 0] + d * x[:, 1] + a * x[:, 2],
+                         c + d * x[:, 0] + a * x[:, 1] + b * x[:, 2]], 1)
+        got, _ = gpu_csc(fe, "div_grad", fes, fens, u, fe.GaussRule(3, 2), mu)
+        n = u.nalldofs()
+        G = sp.csc_matrix((got[2], got[1] - 1, got[0] - 1), shape=(n, n))
+        v = np.zeros(n)
+        v[u.dofnums - 1] = vals
+        gradu = np.array([[b, c, d], [c, d, a], [d, a, b]])
+        gs = (gradu + gradu.T) / 2
+        true = 2 * mu * W * L * t * (gs ** 2).sum()
+        assert abs(v @ (G @ v) - true) <= 1e-5 * true

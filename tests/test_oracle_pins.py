@@ -344,3 +344,43 @@ def test_matrix_block_semantics(orc):
         assert np.array_equal(B, full[r0 - 1:r1, c0 - 1:c1])
     cp, rv, nz = orc.matrix_block(csc, 3, 4, 1, 2)
     assert list(cp) == [1, 3, 3] and list(rv) == [1, 2] and list(nz) == [0.0, 3.0]   # the stored zero of (3,1) is kept
+
+
+def test_sibling_form_identities_of_the_reference(orc, fe):
+    """SURVEY.md 8(f) rank 3 restatements pinned to the reference's own tests: bilform_div_grad v'Gv = 0 for a constant field
+    and = 2 mu V |sym grad u|^2 for a linear one (test/test_forms.jl:234-300), bilform_convection Psi' K Q = (u . grad q) V
+    (:196-231, here on H8), distribloads / linform_dot sum(F) = f V (:158-193)."""
+    import scipy.sparse as sp
+    W, L, t = 11.1, 12.0, 7.32
+    fens, fes = fe.H8block(L, W, t, 2, 4, 3)
+    x = fens.xyz
+    rule = fe.GaussRule(3, 2)
+    u = fe.NodalField(np.zeros((fens.count(), 3)))
+    fe.numberdofs(u)
+    n = u.nalldofs()
+    a, b, c, d = (-0.33, 2 / 3, -1.67, 2 / 7)
+    mu = 0.13377
+    I, J, V = orc.bilform_div_grad_coo("H8", fes.conn, x, u.dofnums, n, rule.param_coords, rule.weights, mu)
+    cp, rv, nz = orc.sparse(I, J, V, n, n)
+    G = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(n, n))
+    v = np.zeros(n)
+    v[u.dofnums - 1] = np.stack([a + b * x[:, 0] + c * x[:, 1] + d * x[:, 2], b + c * x[:, 0] + d * x[:, 1] + a * x[:, 2],
+                                 c + d * x[:, 0] + a * x[:, 1] + b * x[:, 2]], 1)
+    gradu = np.array([[b, c, d], [c, d, a], [d, a, b]])
+    true = 2 * mu * W * L * t * (((gradu + gradu.T) / 2) ** 2).sum()
+    assert abs(v @ (G @ v) - true) / true <= 1.0e-5
+    vc = np.zeros(n)
+    vc[u.dofnums - 1] = np.array([3.1, -2.7, -0.77])
+    assert abs(vc @ (G @ vc)) / (W * L * t) <= 1.0e-5
+    q = fe.NodalField(np.zeros((fens.count(), 1)))
+    fe.numberdofs(q)
+    nq = q.nalldofs()
+    uv = np.tile([3.1, -2.7, 0.4], (fens.count(), 1))
+    I, J, V = orc.bilform_convection_coo("H8", fes.conn, x, uv, q.dofnums, nq, rule.param_coords, rule.weights, 1.0)
+    cp, rv, nz = orc.sparse(I, J, V, nq, nq)
+    K = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(nq, nq))
+    Q = np.zeros(nq)
+    Q[q.dofnums[:, 0] - 1] = -0.1 + 0.3 * x[:, 0] + 0.4 * x[:, 1] + 0.5 * x[:, 2]
+    assert abs(np.ones(nq) @ (K @ Q) - (0.3 * 3.1 + 0.4 * -2.7 + 0.5 * 0.4) * W * L * t) / (W * L * t) <= 1.0e-5
+    F = orc.linform_dot("H8", fes.conn, x, q.dofnums, nq, rule.param_coords, rule.weights, [11.0])
+    assert abs(F.sum() - L * W * t * 11.0) / 667 <= 1.0e-5
