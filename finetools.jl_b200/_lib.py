@@ -39,6 +39,12 @@ SIGNATURES = {
     "fegpu_bilform_dot": (C.c_int32, [VP, VP, VP, C.c_int32, C.c_double, VP]),
     "fegpu_bilform_convection": (C.c_int32, [VP, VP, VP, C.c_double, VP]),
     "fegpu_bilform_div_grad": (C.c_int32, [VP, VP, C.c_double, VP]),
+    "fegpu_linform_dot": (C.c_int32, [VP, VP, VP, C.c_int32, C.c_double, VP]),
+    "fegpu_vec_startassembly": (C.c_int32, [VP, C.c_int64]),
+    "fegpu_vec_assemble": (C.c_int32, [VP, VP, VP, C.c_int64]),
+    "fegpu_makevector": (C.c_int32, [VP]),
+    "fegpu_makevector_size": (C.c_int32, [VP, c_i64p]),
+    "fegpu_makevector_copy": (C.c_int32, [VP, VP]),
     "fegpu_startassembly": (C.c_int32, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "fegpu_assemble": (C.c_int32, [VP, VP, VP, C.c_int64, VP, C.c_int64]),
     "fegpu_triplets_append": (C.c_int32, [VP, C.c_int64, VP, VP, VP]),

@@ -212,6 +212,63 @@ class SysmatAssemblerSparseGPU(AbstractSysmatAssembler):
             pass
 
 
+class AbstractSysvecAssembler:
+    pass
+
+
+class SysvecAssemblerGPU(AbstractSysvecAssembler):
+    """SysvecAssembler (AssemblyModule.jl:853-917) on the device: startassembly!(a, row_nalldofs), assemble!(a, vec, dofnums),
+    makevector!(a).  linform_dot / distribloads (femm.py) fill it without the element loop on the host.  It can share the
+    device mesh / dof-map cache of a matrix assembler (`like=`), so the node -> element adjacency is built once."""
+
+    def __init__(self, z=0.0, ctx=None, device=0, like=None):
+        if not isinstance(z, float):
+            raise TypeError("SysvecAssemblerGPU assembles Float64 vectors only")
+        self.ctx = like.ctx if like is not None else (ctx if ctx is not None else GPUContext.default(device))
+        self.handle = VP()
+        check(_lib.lib().fegpu_asm_create(self.ctx.handle, C.byref(self.handle)), self.ctx.handle)
+        self._device_cache = like._device_cache if like is not None else {}
+        self._row_nalldofs = 1  # the reference's blank assembler holds a one-entry buffer (AssemblyModule.jl:861)
+
+    def startassembly(self, row_nalldofs):
+        check(_lib.lib().fegpu_vec_startassembly(self.handle, int(row_nalldofs)), self.ctx.handle)
+        self._row_nalldofs = int(row_nalldofs)
+        return self
+
+    def assemble(self, vec, dofnums):
+        d = np.ascontiguousarray(np.asarray(dofnums, dtype=np.int64).reshape(-1))
+        v = np.ascontiguousarray(np.asarray(vec, dtype=np.float64).reshape(-1))
+        if v.size < d.size:
+            raise _lib.FEGPUError(-15, "Wrong size of vector")
+        check(_lib.lib().fegpu_vec_assemble(self.handle, fptr(v), fptr(d), d.size), self.ctx.handle)
+        return self
+
+    def makevector(self, out=None):
+        check(_lib.lib().fegpu_makevector(self.handle), self.ctx.handle)
+        return self._fetch(out)
+
+    def _fetch(self, out=None):
+        n = C.c_int64(0)
+        check(_lib.lib().fegpu_makevector_size(self.handle, C.byref(n)), self.ctx.handle)
+        F = out if out is not None else np.empty(n.value, dtype=np.float64)
+        if F.size != n.value or F.dtype != np.float64 or not F.flags.c_contiguous:
+            raise _lib.FEGPUError(-2, "output vector must be a contiguous Float64 array of length nalldofs")
+        check(_lib.lib().fegpu_makevector_copy(self.handle, fptr(F)), self.ctx.handle)
+        return F
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().fegpu_asm_destroy(self.handle)
+                self.handle = VP()
+        except Exception:
+            pass
+
+
+def makevector(a, out=None):
+    return a.makevector(out=out)
+
+
 class SysmatAssemblerSparseSymmGPU(SysmatAssemblerSparseGPU):
     """Drop-in for SysmatAssemblerSparseSymm (src/AssemblyModule.jl:342-583), the reference's DEFAULT assembler when none is
     passed (FEMMBaseModule.jl:1374, 1408, 1543, 1822).  assemble! keeps the lower triangle of each element matrix (:517-530);

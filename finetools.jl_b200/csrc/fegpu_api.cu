@@ -498,7 +498,7 @@ int32_t fegpu_asm_set_symmetric(fegpu_asm *as, int32_t on) {
 int32_t fegpu_asm_destroy(fegpu_asm *a) {
   if (!a) return FEGPU_OK;
   DeviceGuard g(a->ctx->device);
-  cudaFree(a->d_V); cudaFree(a->d_nzval); cudaFree(a->own_colptr); cudaFree(a->own_rowval);
+  cudaFree(a->d_V); cudaFree(a->d_nzval); cudaFree(a->own_colptr); cudaFree(a->own_rowval); cudaFree(a->d_F);
   cudaFree(a->view.own_colptr); cudaFree(a->view.own_rowval); cudaFree(a->view.own_nzval);
   for (auto &ev : a->ev)
     if (ev) cudaEventDestroy(ev);
@@ -691,6 +691,162 @@ int32_t fegpu_bilform_div_grad(fegpu_mesh *mesh, fegpu_dofmap *dm, double mu, fe
   fa.m = 3;
   fa.otherdim = 1.0;
   return run_bilform(mesh, dm, fa, as);
+}
+
+// ---- vectors: linform_dot / distribloads and the SysvecAssembler protocol
+namespace {
+// dense F[row_nall] from (row, value) pairs: the pairs go through the generic sort path as an n x 1 matrix (duplicates summed
+// left to right, the reference's range errors), then the column is scattered into the zeroed vector
+__global__ void k_scatter_column(const int64_t *__restrict__ rowval, const double *__restrict__ nzval, int64_t nnz, double *__restrict__ F) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nnz) F[rowval[i] - 1] = nzval[i];
+}
+__global__ void k_fill_i64(int64_t *p, int64_t n, int64_t v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void k_emit_rows(const int32_t *__restrict__ conn, const int32_t *__restrict__ elem_list, int64_t nactive, int nne, int ndn,
+                            int64_t nnodes, const int32_t *__restrict__ dof, int64_t *__restrict__ I) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int EM = nne * ndn;
+  if (i >= nactive * EM) return;
+  const int64_t slot = i / EM;
+  const int r = (int)(i - slot * EM);
+  const int64_t e = elem_list ? elem_list[slot] : slot;
+  I[i] = (int64_t)dof[(int64_t)(r % ndn) * nnodes + conn[e * nne + r / ndn]] + 1;
+}
+
+int32_t vector_from_pairs(fegpu_asm *as, int64_t n, const int64_t *dI, const double *dV, int64_t row_nall) {
+  fegpu_ctx *ctx = as->ctx;
+  cudaStream_t st = ctx->stream;
+  int64_t *dJ = nullptr;
+  CUDA_TRY(ctx, cudaMalloc((void **)&dJ, sizeof(int64_t) * std::max<int64_t>(n, 1)));
+  if (n) k_fill_i64<<<grid_for(n, 256), 256, 0, st>>>(dJ, n, 1);
+  int32_t s = fe_coo_to_csc(as, n, dI, dJ, dV, row_nall, 1);
+  cudaStreamSynchronize(st);
+  cudaFree(dJ);
+  FE_TRY(s);
+  FE_TRY(fe_asm_reserve(as, &as->d_F, &as->F_cap, (size_t)std::max<int64_t>(row_nall, 1)));
+  CUDA_TRY(ctx, cudaMemsetAsync(as->d_F, 0, sizeof(double) * (size_t)std::max<int64_t>(row_nall, 1), st));
+  if (as->nnz) {
+    k_scatter_column<<<grid_for(as->nnz, 256), 256, 0, st>>>(as->d_rowval, as->d_nzval, as->nnz, as->d_F);
+    ctx->launches++;
+  }
+  as->have_result = false;  // the n x 1 matrix was scaffolding
+  as->F_n = row_nall;
+  as->have_vector = true;
+  return FEGPU_OK;
+}
+}  // namespace
+
+int32_t fegpu_linform_dot(fegpu_mesh *mesh, fegpu_dofmap *dm, const double *force, int32_t m, double otherdim, fegpu_asm *as) {
+  if (!mesh || !dm || !force || !as) return fegpu_fail(mesh ? mesh->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  fegpu_ctx *ctx = mesh->ctx;
+  if (dm->mesh != mesh || as->ctx != ctx || dm->ctx != ctx) return fegpu_fail(ctx, FEGPU_ERR_ARG, "handles belong to different meshes / contexts");
+  if (mesh->mdim == 3 && m != 3) return fegpu_fail(ctx, FEGPU_ERR_MANIFOLD, "That is the only acceptable option here.");
+  if (mesh->mdim == 2 && (m < 2 || m > 3)) return fegpu_fail(ctx, FEGPU_ERR_MANIFOLD, "Those are the only acceptable options here.");
+  if (dm->ndn > 3) return fegpu_fail(ctx, FEGPU_ERR_ARG, "linform_dot: up to 3 dofs per node");
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  as->have_vector = false;
+  FormArgs fa;
+  std::memset(&fa, 0, sizeof(fa));
+  fa.form = FORM_LINDOT;
+  fa.ndn = dm->ndn;
+  for (int i = 0; i < dm->ndn; i++) fa.coef[i] = force[i];
+  fa.m = m;
+  fa.otherdim = otherdim;
+  const int EM = mesh->nne * dm->ndn;
+  const int64_t nv = mesh->nactive * (int64_t)EM;
+  FE_TRY(fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(nv, 1)));
+  as->V_n = 0;  // the element-matrix buffer now holds element vectors
+  as->have_result = false;
+  FE_TRY(fe_integrate(mesh, fa, as->d_V));
+  bool fast = fe_pattern_usable(dm);
+  if (fast && (!dm->pat || dm->pat_topo_version != mesh->topo_version)) {
+    FE_TRY(fe_pattern_build(dm));
+    fast = fe_pattern_usable(dm) && dm->pat;
+  }
+  if (fast) {
+    FE_TRY(fe_asm_reserve(as, &as->d_F, &as->F_cap, (size_t)std::max<int64_t>(dm->row_nall, 1)));
+    FE_TRY(fe_vec_gather(dm, as->d_V, as->d_F));
+    as->F_n = dm->row_nall;
+    as->have_vector = true;
+  } else {
+    if (mesh->partitioned) return fegpu_fail(ctx, FEGPU_ERR_ARG, "row-block partitioning needs an injective dof map and non-degenerate elements");
+    int64_t *dI = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void **)&dI, sizeof(int64_t) * std::max<int64_t>(nv, 1)));
+    if (nv) k_emit_rows<<<grid_for(nv, 256), 256, 0, st>>>(mesh->d_conn, mesh->d_elem_list, mesh->nactive, mesh->nne, dm->ndn, mesh->nnodes, dm->d_dof, dI);
+    const int32_t s = vector_from_pairs(as, nv, dI, as->d_V, dm->row_nall);
+    cudaStreamSynchronize(st);
+    cudaFree(dI);
+    FE_TRY(s);
+  }
+  return finish(ctx);
+}
+
+int32_t fegpu_vec_startassembly(fegpu_asm *as, int64_t row_nall) {
+  if (!as) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL assembler");
+  if (row_nall < 0 || row_nall >= INT32_MAX) return fegpu_fail(as->ctx, FEGPU_ERR_ARG, "vector length outside int32 range");
+  as->hvI.clear();
+  as->hvV.clear();
+  as->v_row_nall = row_nall;
+  as->vec_started = true;
+  as->have_vector = false;
+  return FEGPU_OK;
+}
+
+int32_t fegpu_vec_assemble(fegpu_asm *as, const double *vec, const int64_t *dofnums, int64_t n) {
+  if (!as || (n > 0 && (!vec || !dofnums))) return fegpu_fail(as ? as->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  if (!as->vec_started) return fegpu_fail(as->ctx, FEGPU_ERR_STATE, "assemble! before startassembly!");
+  for (int64_t i = 0; i < n; i++) {  // AssemblyModule.jl:899-906
+    const int64_t gi = dofnums[i];
+    if (gi < 1) return fegpu_fail(as->ctx, FEGPU_ERR_ROW_LT1, "Row degree of freedom < 1");
+    if (gi > as->v_row_nall) return fegpu_fail(as->ctx, FEGPU_ERR_ROW_GT, "Row degree of freedom > size");
+    as->hvI.push_back(gi);
+    as->hvV.push_back(vec[i]);
+  }
+  return FEGPU_OK;
+}
+
+int32_t fegpu_makevector(fegpu_asm *as) {
+  if (!as) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL assembler");
+  fegpu_ctx *ctx = as->ctx;
+  if (!as->vec_started) return fegpu_fail(ctx, FEGPU_ERR_STATE, "makevector! without startassembly!");
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int64_t n = (int64_t)as->hvV.size();
+  int64_t *dI = nullptr;
+  CUDA_TRY(ctx, cudaMalloc((void **)&dI, sizeof(int64_t) * std::max<int64_t>(n, 1)));
+  int32_t s = fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(n, 1));
+  if (s == FEGPU_OK && n) {
+    if (cudaMemcpyAsync(dI, as->hvI.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(as->d_V, as->hvV.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st) != cudaSuccess)
+      s = fegpu_fail(ctx, FEGPU_ERR_CUDA, "upload of the staged vector entries failed");
+  }
+  as->V_n = 0;
+  if (s == FEGPU_OK) s = vector_from_pairs(as, n, dI, as->d_V, as->v_row_nall);
+  cudaStreamSynchronize(st);
+  cudaFree(dI);
+  FE_TRY(s);
+  return finish(ctx);
+}
+
+int32_t fegpu_makevector_size(fegpu_asm *as, int64_t *n) {
+  if (!as || !n) return fegpu_fail(as ? as->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  if (!as->have_vector) return fegpu_fail(as->ctx, FEGPU_ERR_STATE, "no assembled vector");
+  *n = as->F_n;
+  return FEGPU_OK;
+}
+
+int32_t fegpu_makevector_copy(fegpu_asm *as, double *F) {
+  if (!as || !F) return fegpu_fail(as ? as->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  fegpu_ctx *ctx = as->ctx;
+  if (!as->have_vector) return fegpu_fail(ctx, FEGPU_ERR_STATE, "no assembled vector");
+  DeviceGuard g(ctx->device);
+  if (as->F_n) CUDA_TRY(ctx, cudaMemcpyAsync(F, as->d_F, sizeof(double) * (size_t)as->F_n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return FEGPU_OK;
 }
 
 // ---- generic protocol

@@ -99,7 +99,7 @@ template <int NNE, int MDIM, int SDIM, int NDN, int FORM, int TPE>
 __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const IntegParams P) {
   constexpr int EM = NNE * NDN;
   constexpr bool SYM = (FORM == FORM_DIFF_ISO || FORM == FORM_DIFF_GEN || FORM == FORM_ELASTIC);
-  constexpr int NENT = SYM ? EM * (EM + 1) / 2 : EM * EM;
+  constexpr int NENT = (FORM == FORM_LINDOT) ? EM : (SYM ? EM * (EM + 1) / 2 : EM * EM);  // linform_dot: a vector
   constexpr int EPT = (NENT + TPE - 1) / TPE;
   constexpr int GPB = (TPE <= 32) ? 128 / TPE : 1;  // element groups per block
   constexpr int NAUX = (FORM == FORM_ELASTIC) ? 6 * EM : (FORM == FORM_DIFF_GEN ? MDIM * NNE : (FORM == FORM_CONVECTION ? NNE * SDIM : 1));
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
       ec[k] = c;
     } else {
       er[k] = idx % EM;
-      ec[k] = idx / EM;
+      ec[k] = idx / EM;  // 0 for the element vector of linform_dot
     }
   }
 
@@ -174,7 +174,16 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
         }
       }
       double Jac = jac_measure<SDIM, MDIM>(J);
-      if (FORM == FORM_DOT) {
+      if (FORM == FORM_LINDOT) {
+        // elvec[rx] += (Ns[kx] * (Jac * w)) * force[mx]                                FEMMBaseModule.jl:1230-1239
+        if (MDIM == 2 && P.m == 3) Jac = Jac * P.otherdim;
+        const double Factor = Jac * sw[j];
+#pragma unroll
+        for (int k = 0; k < EPT; k++) {
+          const int r = er[k];
+          acc[k] += (N[r / NDN] * Factor) * P.coef[r % NDN];
+        }
+      } else if (FORM == FORM_DOT) {
         if (MDIM == 2 && P.m == 3) Jac = Jac * P.otherdim;
         const double Jw = Jac * sw[j];
 #pragma unroll
@@ -279,7 +288,13 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
       }
     }
     // emission: V[slot][c*EM + r]; the mirrored entry is complete_lt!
-    if (live && SYM && P.compact) {
+    if (FORM == FORM_LINDOT) {
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < EPT; k++)
+          if (t + k * TPE < NENT) P.V[slot * (int64_t)EM + er[k]] = acc[k];
+      }
+    } else if (live && SYM && P.compact) {
       // compact upper-block layout (fegpu_internal.h): block (a <= b) at NDN^2 * (b(b+1)/2 + a), column-major inside
       double *Ve = P.V + slot * (int64_t)(NNE * (NNE + 1) / 2 * NDN * NDN);
 #pragma unroll
@@ -348,6 +363,11 @@ int32_t dispatch_form(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
       if (fa.ndn == 2) return launch_generic<NNE, MDIM, SDIM, 2, FORM_DOT, TPE_V>(mesh, fa, d_V);
       if (fa.ndn == 3) return launch_generic<NNE, MDIM, SDIM, 3, FORM_DOT, TPE_V>(mesh, fa, d_V);
       return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "bilform_dot: 1, 2 or 3 dofs per node are supported");
+    case FORM_LINDOT:
+      if (fa.ndn == 1) return launch_generic<NNE, MDIM, SDIM, 1, FORM_LINDOT, TPE_S>(mesh, fa, d_V);
+      if (fa.ndn == 2) return launch_generic<NNE, MDIM, SDIM, 2, FORM_LINDOT, TPE_S>(mesh, fa, d_V);
+      if (fa.ndn == 3) return launch_generic<NNE, MDIM, SDIM, 3, FORM_LINDOT, TPE_S>(mesh, fa, d_V);
+      return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "linform_dot: 1, 2 or 3 dofs per node are supported");
     case FORM_CONVECTION:
       if (SDIM != MDIM) break;
       return launch_generic<NNE, MDIM, (SDIM == MDIM ? SDIM : MDIM), 1, FORM_CONVECTION, TPE_S>(mesh, fa, d_V);

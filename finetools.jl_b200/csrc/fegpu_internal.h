@@ -83,6 +83,14 @@ struct fegpu_asm {
   size_t own_colptr_cap = 0, own_rowval_cap = 0;
   bool have_result = false;
   bool pattern_cached = false;
+  // assembled vector (SysvecAssembler semantics: linform_dot / distribloads and the generic vector protocol)
+  double *d_F = nullptr;
+  size_t F_cap = 0;
+  int64_t F_n = 0;
+  bool have_vector = false, vec_started = false;
+  int64_t v_row_nall = 0;
+  std::vector<int64_t> hvI;
+  std::vector<double> hvV;
   // optional view of the result (sub-block and/or exact zeros dropped, fegpu_csc_ops.cu); the accessors below pick it
   struct View {
     bool active = false;
@@ -135,7 +143,8 @@ int32_t fe_exclusive_scan_i32_to_i64(fegpu_ctx *ctx, const int32_t *d_in, int64_
 int32_t fe_max_i32(fegpu_ctx *ctx, const int32_t *d_in, int64_t n, int32_t *max_host);
 
 // ---- integration (fegpu_integrate.cu) ------------------------------------------------------------------
-enum { FORM_DIFF_ISO = 0, FORM_DIFF_GEN = 1, FORM_ELASTIC = 2, FORM_DOT = 3, FORM_CONVECTION = 4, FORM_DIV_GRAD = 5 };
+enum { FORM_DIFF_ISO = 0, FORM_DIFF_GEN = 1, FORM_ELASTIC = 2, FORM_DOT = 3, FORM_CONVECTION = 4, FORM_DIV_GRAD = 5,
+       FORM_LINDOT = 6 /* linform_dot: element VECTORS, [nactive][EM] */ };
 struct FormArgs {
   int form;
   int ndn;
@@ -171,6 +180,9 @@ bool fe_pattern_compressed(const Pattern *p, const int32_t **nbr, const int64_t 
                            int64_t *nnodes);
 bool fe_pattern_usable(const fegpu_dofmap *dm);  // mesh-structured fast path applicable?
 int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_nzval);
+// element vectors [nactive][nne*ndn] -> dense vector F[row_nall] (zeroed here): every node sums its adjacent elements'
+// entries in ascending element order (= the reference's element loop); rows of nodes this rank does not own stay zero
+int32_t fe_vec_gather(fegpu_dofmap *dm, const double *d_elvec, double *d_F);
 // compact symmetric layout -> full element matrices in emission order (raw-COO export only)
 int32_t fe_expand_compact(fegpu_ctx *ctx, const double *d_Vc, double *d_Vfull, int64_t nelem, int nne, int ndn);
 

@@ -919,6 +919,24 @@ __global__ void __launch_bounds__(GWPB * 32, 5) k_gather(const GatherParams G) {
   }
 }
 
+// Vector assembly (SysvecAssembler, AssemblyModule.jl:853-917) on the node -> element adjacency of the pattern: thread per
+// (node, component) adds the node's entry of every adjacent element vector in ascending element order.
+__global__ void k_vec_gather(int64_t nnodes, int nne, int ndn, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ adj_slot,
+                             const uint8_t *__restrict__ adj_lc, const int32_t *__restrict__ dof, const uint8_t *__restrict__ rowowned,
+                             const double *__restrict__ elvec, double *__restrict__ F) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnodes * ndn) return;
+  const int64_t n = i / ndn;
+  const int p = (int)(i - n * ndn);
+  if (rowowned && !rowowned[n]) return;
+  const int64_t b = adjptr[n], e = adjptr[n + 1];
+  if (b == e) return;
+  const int EM = nne * ndn;
+  double acc = 0.0;
+  for (int64_t a = b; a < e; a++) acc += elvec[(int64_t)adj_slot[a] * EM + adj_lc[a] * ndn + p];
+  F[dof[(int64_t)p * nnodes + n]] = acc;
+}
+
 template <typename T>
 int32_t dalloc(fegpu_ctx *ctx, T **p, size_t n) {
   *p = nullptr;
@@ -1244,6 +1262,21 @@ int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_n
 #undef LG_R
 #undef LG_C
 #undef LG_L
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return FEGPU_OK;
+}
+
+int32_t fe_vec_gather(fegpu_dofmap *dm, const double *d_elvec, double *d_F) {
+  fegpu_ctx *ctx = dm->ctx;
+  Pattern *P = dm->pat;
+  fegpu_mesh *mesh = dm->mesh;
+  if (!P) return fegpu_fail(ctx, FEGPU_ERR_STATE, "no pattern");
+  CUDA_TRY(ctx, cudaMemsetAsync(d_F, 0, sizeof(double) * (size_t)std::max<int64_t>(dm->row_nall, 1), ctx->stream));
+  const int64_t n = mesh->nnodes * dm->ndn;
+  if (n == 0) return FEGPU_OK;
+  k_vec_gather<<<grid_for(n, 256), 256, 0, ctx->stream>>>(mesh->nnodes, mesh->nne, dm->ndn, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, dm->d_dof,
+                                                         mesh->d_rowowned, d_elvec, d_F);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return FEGPU_OK;

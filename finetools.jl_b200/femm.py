@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import VP, FEGPUError, check, fptr
-from .assembly import SysmatAssemblerFFBlock, SysmatAssemblerSparseGPU
+from .assembly import SysmatAssemblerFFBlock, SysmatAssemblerSparseGPU, SysvecAssemblerGPU
 from .datacache import DataCache
 from .integdomain import IntegDomain, integrationdata
 
@@ -252,6 +252,41 @@ def bilform_div_grad(self, assembler, geom, u, viscf, raw=False, node_owner=None
         raise FEGPUError(-2, "bilform_div_grad needs one dof per space dimension and sdim == manifold dimension")
     check(_lib.lib().fegpu_bilform_div_grad(dmesh.handle, dof, float(viscf.data), _inner(assembler).handle), assembler.ctx.handle)
     return _finish(assembler, fes, dmesh, dof, u, raw, out)
+
+
+class ForceIntensity:
+    """Constant distributed-load intensity (src/ForceIntensityModule.jl: the constant constructors wrap the vector in a
+    DataCache); only constant intensities are GPU-eligible."""
+
+    def __init__(self, force):
+        self._cache = DataCache(np.atleast_1d(np.asarray(force, dtype=np.float64)))
+
+
+def linform_dot(self, assembler, geom, P, f, m, node_owner=None, my_rank=0, out=None):
+    """F_i = int N_i f over the m-dimensional manifold (FEMMBaseModule.jl:1207-1244); f: constant DataCache of ndn values."""
+    if not isinstance(assembler, SysvecAssemblerGPU):
+        raise TypeError("this package provides the GPU vector assembler only (SysvecAssemblerGPU); there is no CPU loop")
+    if not isinstance(f, DataCache):
+        raise TypeError("the load must be a constant DataCache")
+    if self.integdomain.axisymmetric:
+        raise FEGPUError(-2, "axisymmetric integration domains are not GPU-eligible")
+    if geom.values.dtype != np.float64 or P.dofnums.dtype != np.int64:
+        raise FEGPUError(-2, "geom must be Float64 and dofnums Int64")
+    force = np.ascontiguousarray(np.atleast_1d(f.data).astype(np.float64).reshape(-1))
+    if force.size != P.ndofs():
+        raise FEGPUError(-2, "the load needs one component per degree of freedom of a node")
+    fes, dmesh, dof = _prepare(self, assembler, geom, P, node_owner, my_rank)
+    check(_lib.lib().fegpu_linform_dot(dmesh.handle, dof, fptr(force), int(m), float(self.integdomain.otherdimension), assembler.handle),
+          assembler.ctx.handle)
+    assembler._row_nalldofs = P.nalldofs()
+    return assembler._fetch(out)
+
+
+def distribloads(self, assembler, geom, P, fi, m, **kw):
+    """FEMMBaseModule.jl:1277-1286: linform_dot with the ForceIntensity's cache."""
+    if not isinstance(fi, ForceIntensity):
+        raise TypeError("distribloads needs a ForceIntensity")
+    return linform_dot(self, assembler, geom, P, fi._cache, m, **kw)
 
 
 def innerproduct(self, assembler, geom, afield, raw=False):

@@ -112,6 +112,20 @@ int32_t fegpu_bilform_convection(fegpu_mesh *mesh, fegpu_dofmap *dofmap, const d
 /* bilform_div_grad, FEMMBaseModule.jl:1672-1713.  dofmap: vector field with sdim dofs per node; mu: constant viscosity */
 int32_t fegpu_bilform_div_grad(fegpu_mesh *mesh, fegpu_dofmap *dofmap, double mu, fegpu_asm *as);
 
+/* -- vectors: linform_dot / distribloads and SysvecAssembler ---------------------- */
+/* linform_dot, FEMMBaseModule.jl:1207-1244 (distribloads :1277-1297 forwards a ForceIntensity's cache to it): F_i = int N_i f
+ * over the m-dimensional manifold Jacobian; force: ndn constant components.  The element vectors are summed per node in
+ * ascending element order on the mesh's node -> element adjacency (no atomics).  Result: fegpu_makevector_copy.        */
+int32_t fegpu_linform_dot(fegpu_mesh *mesh, fegpu_dofmap *dofmap, const double *force, int32_t m, double otherdim, fegpu_asm *as);
+/* SysvecAssembler protocol, AssemblyModule.jl:853-917: startassembly!(a, row_nalldofs), assemble!(a, vec, dofnums) with the
+ * reference's "Row degree of freedom < 1" / "> size" errors, makevector!(a).  Entries are staged on the host and summed on
+ * the device (duplicates left to right). */
+int32_t fegpu_vec_startassembly(fegpu_asm *as, int64_t row_nalldofs);
+int32_t fegpu_vec_assemble(fegpu_asm *as, const double *vec, const int64_t *dofnums, int64_t n);
+int32_t fegpu_makevector(fegpu_asm *as);
+int32_t fegpu_makevector_size(fegpu_asm *as, int64_t *n);
+int32_t fegpu_makevector_copy(fegpu_asm *as, double *F /* [row_nalldofs] */);
+
 /* Generic assembler protocol for any other caller (AssemblyModule.jl:209-282): host triplets are staged to
  * the device and the CSC is built there by a 64-bit key sort + segmented sum. */
 int32_t fegpu_startassembly(fegpu_asm *as, int64_t elem_mat_nrows, int64_t elem_mat_ncols, int64_t n_elem_mats,

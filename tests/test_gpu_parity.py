@@ -738,3 +738,84 @@ def test_div_grad_parity(fe, orc, gpu_ctx, et):
         gs = (gradu + gradu.T) / 2
         true = 2 * mu * W * L * t * (gs ** 2).sum()
         assert abs(v @ (G @ v) - true) <= 1e-5 * true
+
+
+@pytest.mark.parametrize("et,ndn", [("H8", 1), ("H8", 3), ("H20", 3), ("H27", 1), ("T4", 3), ("T10", 1), ("T10", 3)])
+def test_linform_dot_volume_parity(fe, orc, gpu_ctx, et, ndn):
+    """linform_dot / distribloads (FEMMBaseModule.jl:1207-1297) into a SysvecAssembler: every entry of the assembled vector
+    against the oracle (same element order of the sums: tolerance 1e-12 of the largest entry is rounding from FMA only)."""
+    fens, fes = _mesh(fe, et)
+    _distort(fens)
+    rule = _rule(fe, et)
+    P = make_field(fe, fens, ndn, fixed_nodes=[2, 5] if ndn == 3 else None, fixed_comp=None)
+    force = np.array([11.0, -3.5, 0.25][:ndn])
+    ref = orc.linform_dot(et, fes.conn, fens.xyz, P.dofnums, P.nalldofs(), rule.param_coords, rule.weights, force)
+    femm = fe.FEMMBase(fe.IntegDomain(fes, rule))
+    a = fe.SysvecAssemblerGPU(0.0)
+    F = fe.linform_dot(femm, a, fe.NodalField(fens.xyz), P, fe.DataCache(force), 3)
+    assert F.shape == ref.shape
+    assert np.abs(F - ref).max() <= 1e-12 * np.abs(ref).max()
+    F2 = fe.distribloads(femm, a, fe.NodalField(fens.xyz), P, fe.ForceIntensity(force), 3)
+    np.testing.assert_array_equal(F, F2)  # repeated assembly is bit-identical (no atomics)
+
+
+@pytest.mark.parametrize("et", ["Q4", "T3"])
+def test_linform_dot_surface_traction(fe, orc, gpu_ctx, et):
+    """Surface tractions: the boundary of a block (Q4 / T3 in 3-D), m = 2; sum(F) = traction x area."""
+    if et == "Q4":
+        fens, vol = fe.H8block(1.0, 2.0, 3.0, 3, 4, 5)
+        rule = fe.GaussRule(2, 2)
+    else:
+        fens, vol = fe.T4block(1.0, 2.0, 3.0, 3, 4, 5)
+        rule = fe.TriRule(3)
+    bfes = fe.meshboundary(vol)
+    P = make_field(fe, fens, 3)
+    force = np.array([2.0, -1.0, 0.5])
+    ref = orc.linform_dot(et, bfes.conn, fens.xyz, P.dofnums, P.nalldofs(), rule.param_coords, rule.weights, force, m=2)
+    femm = fe.FEMMBase(fe.IntegDomain(bfes, rule))
+    F = fe.linform_dot(femm, fe.SysvecAssemblerGPU(0.0), fe.NodalField(fens.xyz), P, fe.DataCache(force), 2)
+    assert np.abs(F - ref).max() <= 1e-12 * np.abs(ref).max()
+    area = 2 * (1 * 2 + 2 * 3 + 1 * 3)
+    comp = F[P.dofnums - 1].sum(axis=0)
+    assert np.abs(comp - force * area).max() <= 1e-10 * area
+    with pytest.raises(fe.FEGPUError):
+        fe.linform_dot(femm, fe.SysvecAssemblerGPU(0.0), fe.NodalField(fens.xyz), P, fe.DataCache(force), 1)
+
+
+def test_distribloads_reference_identity_and_partition(fe, orc, gpu_ctx):
+    """test/test_forms.jl:158-193: sum(F) = L W t f; and the row blocks of a 2-way partition add up to the vector."""
+    W, L, t = 1.1, 12.0, 4.32
+    fens, fes = fe.H8block(L, W, t, 2, 4, 3)
+    psi = make_field(fe, fens, 1)
+    femm = fe.FEMMBase(fe.IntegDomain(fes, fe.GaussRule(3, 2)))
+    geom = fe.NodalField(fens.xyz)
+    F = fe.distribloads(femm, fe.SysvecAssemblerGPU(0.0), geom, psi, fe.ForceIntensity([11.0]), 3)
+    assert abs(F.sum() - L * W * t * 11.0) / 667 <= 1.0e-5
+    F2 = fe.distribloads(femm, fe.SysvecAssemblerGPU(0.0), geom, psi, fe.ForceIntensity(11.0), 3)
+    np.testing.assert_array_equal(F, F2)
+    owner = fe.slab_owner(fens.count(), 2)
+    parts = [fe.linform_dot(femm, fe.SysvecAssemblerGPU(0.0), geom, psi, fe.DataCache(np.array([11.0])), 3, node_owner=owner, my_rank=p)
+             for p in range(2)]
+    for p in range(2):
+        notmine = np.ones(psi.nalldofs(), bool)
+        notmine[psi.dofnums[owner == p, 0] - 1] = False
+        assert not parts[p][notmine].any()
+    np.testing.assert_array_equal(parts[0] + parts[1], F)
+
+
+def test_sysvec_assembler_protocol(fe, gpu_ctx):
+    """startassembly!/assemble!/makevector! of SysvecAssembler (AssemblyModule.jl:884-917) with the reference's range errors."""
+    a = fe.SysvecAssemblerGPU(0.0)
+    a.startassembly(7)
+    a.assemble(np.array([1.0, 2.0, 3.0]), [5, 2, 1])
+    a.assemble(np.array([10.0, 20.0]), [2, 7])
+    a.assemble(np.array([0.5]), [2])
+    F = fe.makevector(a)
+    np.testing.assert_array_equal(F, [3.0, 12.5, 0.0, 0.0, 1.0, 0.0, 20.0])
+    a.startassembly(3)
+    with pytest.raises(fe.FEGPUError, match="Row degree of freedom < 1"):
+        a.assemble(np.array([1.0]), [0])
+    with pytest.raises(fe.FEGPUError, match="Row degree of freedom > size"):
+        a.assemble(np.array([1.0]), [4])
+    a.startassembly(3)
+    np.testing.assert_array_equal(fe.makevector(a), [0.0, 0.0, 0.0])
