@@ -11,12 +11,14 @@ module FinEtoolsGPU
 
 using FinEtools
 using SparseArrays
-import FinEtools.AssemblyModule: AbstractSysmatAssembler, startassembly!, assemble!, makematrix!, eltype, expectedntriples
-import FinEtools.FEMMBaseModule: bilform_diffusion, bilform_lin_elastic, bilform_dot, FEMMBase, finite_elements
+import FinEtools.AssemblyModule: AbstractSysmatAssembler, AbstractSysvecAssembler, startassembly!, assemble!, makematrix!,
+    makevector!, eltype, expectedntriples
+import FinEtools.FEMMBaseModule: bilform_diffusion, bilform_lin_elastic, bilform_dot, bilform_convection, bilform_div_grad,
+    linform_dot, FEMMBase, finite_elements
 using FinEtools.IntegDomainModule: integrationdata, otherdimensionunity
 using FinEtools.DeforModelRedModule: DeforModelRed3D
 
-export SysmatAssemblerSparseGPU, SysmatAssemblerSparseSymmGPU, gpu_matrix_blocked
+export SysmatAssemblerSparseGPU, SysmatAssemblerSparseSymmGPU, SysvecAssemblerGPU, gpu_matrix_blocked
 
 const LIB = get(ENV, "FEGPU_LIB", joinpath(@__DIR__, "..", "libfinegpu.so"))
 
@@ -143,7 +145,7 @@ function _eligible(self::FEMMBase, geom, u, cf)
     return nothing
 end
 
-function _device(self::FEMMBase, a::SysmatAssemblerSparseGPU, geom, u)
+function _device(self::FEMMBase, a, geom, u)   # a: SysmatAssemblerSparseGPU or SysvecAssemblerGPU (same device-twin cache)
     fes = finite_elements(self)
     xyz = geom.values                                      # nnodes x sdim, column-major already
     entry = get(a.meshes, fes, nothing)
@@ -178,8 +180,10 @@ function _device(self::FEMMBase, a::SysmatAssemblerSparseGPU, geom, u)
         dms[copy(dn)] = d[]
         dh = d[]
     end
-    a._row_nalldofs = a._col_nalldofs = nalldofs(u)
-    a._generic = false
+    if a isa SysmatAssemblerSparseGPU
+        a._row_nalldofs = a._col_nalldofs = nalldofs(u)
+        a._generic = false
+    end
     return mh, dh
 end
 
@@ -215,6 +219,88 @@ function bilform_dot(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, geom::
     GC.@preserve c _check(ccall((:fegpu_bilform_dot, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Ptr{Cvoid}),
             mh, dh, c, m, 1.0, assembler.handle), assembler.ctx)
     return makematrix!(assembler)
+end
+
+# ---- SURVEY.md 8(f) rank 3: sibling forms on the same per-element pipeline ----------------------------------------------
+# bilform_convection (FEMMBaseModule.jl:1583-1625): `u` is the nodal convective velocity field, `Q` numbers the dofs
+function bilform_convection(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, geom::NodalField{FT}, u::NodalField{T},
+    Q::NodalField{QT}, rhof::DC) where {FT,T,QT,DC<:DataCache}
+    _eligible(self, geom, Q, rhof)
+    mh, dh = _device(self, assembler, geom, Q)
+    uv = Matrix{Float64}(u.values)           # nnodes x sdim, column-major
+    GC.@preserve uv _check(ccall((:fegpu_bilform_convection, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Float64, Ptr{Cvoid}),
+            mh, dh, uv, Float64(rhof._cache), assembler.handle), assembler.ctx)
+    return makematrix!(assembler)
+end
+
+# bilform_div_grad (FEMMBaseModule.jl:1672-1713)
+function bilform_div_grad(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, geom::NodalField{FT}, u::NodalField{T},
+    viscf::DC) where {FT,T,DC<:DataCache}
+    _eligible(self, geom, u, viscf)
+    mh, dh = _device(self, assembler, geom, u)
+    _check(ccall((:fegpu_bilform_div_grad, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Ptr{Cvoid}),
+            mh, dh, Float64(viscf._cache), assembler.handle), assembler.ctx)
+    return makematrix!(assembler)
+end
+
+"""
+    SysvecAssemblerGPU(like::SysmatAssemblerSparseGPU)
+
+Same protocol as `SysvecAssembler` (AssemblyModule.jl:853-917).  It shares the context and the device twins (mesh, dof maps,
+node -> element adjacency) of the matrix assembler it is built from.  `distribloads(femm, SysvecAssemblerGPU(a), geom, P, fi, m)`
+works through the reference's own forwarding method (FEMMBaseModule.jl:1277-1286) and the `linform_dot` method below.
+"""
+mutable struct SysvecAssemblerGPU{T} <: AbstractSysvecAssembler
+    ctx::Ptr{Cvoid}
+    handle::Ptr{Cvoid}
+    meshes::IdDict{Any,Any}
+    _row_nalldofs::Int
+end
+
+function SysvecAssemblerGPU(like::SysmatAssemblerSparseGPU)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    _check(ccall((:fegpu_asm_create, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), like.ctx, h), like.ctx)
+    a = SysvecAssemblerGPU{Float64}(like.ctx, h[], like.meshes, 1)
+    finalizer(x -> ccall((:fegpu_asm_destroy, LIB), Int32, (Ptr{Cvoid},), x.handle), a)
+    return a
+end
+
+function startassembly!(self::SysvecAssemblerGPU, row_nalldofs::IT) where {IT<:Integer}
+    _check(ccall((:fegpu_vec_startassembly, LIB), Int32, (Ptr{Cvoid}, Int64), self.handle, row_nalldofs), self.ctx)
+    self._row_nalldofs = row_nalldofs
+    return self
+end
+
+function assemble!(self::SysvecAssemblerGPU, vec::MV, dofnums::IV) where {MV,IV}
+    v = Vector{Float64}(vec); d = Vector{Int64}(dofnums)
+    GC.@preserve v d _check(ccall((:fegpu_vec_assemble, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64),
+            self.handle, v, d, length(d)), self.ctx)
+end
+
+function _fetchvector(self::SysvecAssemblerGPU)
+    n = Ref{Int64}(0)
+    _check(ccall((:fegpu_makevector_size, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), self.handle, n), self.ctx)
+    F = Vector{Float64}(undef, n[])
+    GC.@preserve F _check(ccall((:fegpu_makevector_copy, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), self.handle, F), self.ctx)
+    return F
+end
+
+function makevector!(self::SysvecAssemblerGPU)
+    _check(ccall((:fegpu_makevector, LIB), Int32, (Ptr{Cvoid},), self.handle), self.ctx)
+    return _fetchvector(self)
+end
+
+# linform_dot (FEMMBaseModule.jl:1207-1244): constant DataCache only
+function linform_dot(self::FEMMBase, assembler::SysvecAssemblerGPU, geom::NodalField{FT}, P::NodalField{T}, f::DC,
+    m) where {FT<:Number,T,DC<:DataCache}
+    _eligible(self, geom, P, f)
+    mh, dh = _device(self, assembler, geom, P)
+    force = Vector{Float64}(vec(collect(f._cache)))
+    length(force) == ndofs(P) || error("the load needs one component per degree of freedom of a node")
+    GC.@preserve force _check(ccall((:fegpu_linform_dot, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Ptr{Cvoid}),
+            mh, dh, force, m, 1.0, assembler.handle), assembler.ctx)
+    assembler._row_nalldofs = nalldofs(P)
+    return _fetchvector(assembler)
 end
 
 end # module
