@@ -63,6 +63,9 @@ struct SymParams {
   // a rank's symbolic cost follows its own share of the mesh (row-block partitions, boundary skins)
   const int32_t *anodes;
   int64_t na;
+  // when set, the number of entries of `anodes` lives on the device (class lists built by k_classify_nodes) and `na` is only
+  // an upper bound used to size the grid
+  const int64_t *na_dev;
 };
 __device__ __forceinline__ int64_t active_node(const SymParams &S, int64_t idx) { return S.anodes ? (int64_t)S.anodes[idx] : idx; }
 
@@ -428,7 +431,8 @@ __global__ void __launch_bounds__(WPB * 32) k_nbr_fast(SymParams S, const int64_
   int32_t *smF = CHECK ? sfl + (size_t)w * 2 * capc : nullptr;
   int32_t *smL = CHECK ? smF + capc : nullptr;
   const int nne = S.nne;
-  for (int64_t idx = (int64_t)blockIdx.x * WPB + w; idx < S.na; idx += (int64_t)gridDim.x * WPB) {
+  const int64_t na = S.na_dev ? *S.na_dev : S.na;
+  for (int64_t idx = (int64_t)blockIdx.x * WPB + w; idx < na; idx += (int64_t)gridDim.x * WPB) {
     const int64_t n = active_node(S, idx);
     const int64_t ab = adjptr[n];
     const int deg = (int)(adjptr[n + 1] - ab);
@@ -615,6 +619,31 @@ __global__ void __launch_bounds__(WPB * 32) k_nbr_group(SymParams S, const int64
       nnbr_out[n_cur] = 0;
       if (CHECK) sorted_flag[n_cur] = 1;
     }
+  }
+}
+
+// Meshes whose nodes differ a lot in valence (T10: vertex nodes see ~24 elements, edge nodes ~5; H20: corners 8, edges 4):
+// the nodes are binned by candidate count so that the many small nodes run the small-register instantiation of k_nbr_fast.
+// Lists are filled with warp-aggregated atomics (their internal order is irrelevant: every node writes its own outputs).
+__global__ void k_classify_nodes(SymParams S, const int32_t *__restrict__ deg, int32_t *__restrict__ l0, int32_t *__restrict__ l1,
+                                 int32_t *__restrict__ l2, unsigned long long *__restrict__ counts) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int cls = -1;
+  int32_t n = 0;
+  if (idx < S.na) {
+    n = (int32_t)active_node(S, idx);
+    const int ncand = deg[n] * S.nne;
+    cls = (ncand == 0) ? -1 : (ncand <= 64 ? 0 : (ncand <= 128 ? 1 : 2));
+  }
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+    if (m == 0) continue;
+    unsigned long long base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(&counts[c], (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (cls == c) (c == 0 ? l0 : (c == 1 ? l1 : l2))[base + __popc(m & ((1u << lane) - 1u))] = n;
   }
 }
 
@@ -982,15 +1011,16 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   P->nrows = dm->row_nall;
   const int64_t nn = mesh->nnodes;
   const int nne = mesh->nne, ndn = dm->ndn;
-  SymParams S{mesh->d_conn, mesh->d_elem_list, mesh->nactive, nne, nn, mesh->d_rowowned, dm->d_dof, ndn, nullptr, nn};
+  SymParams S{mesh->d_conn, mesh->d_elem_list, mesh->nactive, nne, nn, mesh->d_rowowned, dm->d_dof, ndn, nullptr, nn, nullptr};
   const int64_t nadj = mesh->nactive * nne;
 
-  int32_t *d_deg = nullptr, *d_cursor = nullptr, *d_U = nullptr, *d_aflag = nullptr, *d_anodes = nullptr;
+  int32_t *d_deg = nullptr, *d_cursor = nullptr, *d_U = nullptr, *d_aflag = nullptr, *d_anodes = nullptr, *d_cls = nullptr;
+  unsigned long long *d_clscnt = nullptr;
   int64_t *d_apos = nullptr;
   uint8_t *d_sorted = nullptr;
   int *d_flags = nullptr;  // [0] degenerate, [1] some node needs a dof sort, [2] the dof map is not node-major ascending
   auto cleanup = [&]() {
-    void *ptrs[] = {d_deg, d_cursor, d_U, d_sorted, d_flags, d_aflag, d_anodes, d_apos};
+    void *ptrs[] = {d_deg, d_cursor, d_U, d_sorted, d_flags, d_aflag, d_anodes, d_apos, d_cls, d_clscnt};
     for (void *q : ptrs)
       if (q) cudaFreeAsync(q, st);
   };
@@ -1091,8 +1121,33 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
     if (!group_off && capc <= 32 && maxdeg <= 8) LAUNCH_GROUP(8, 4);          // Q4 / T3 skins, T3/Q4 planar: four nodes per warp
     else if (!group_off && capc <= 64 && maxdeg <= 16) LAUNCH_GROUP(16, 4);   // H8: two nodes per warp
     else if (capc <= 64) LAUNCH_FAST(2);
-    else if (capc <= 128) LAUNCH_FAST(4);
-    else LAUNCH_FAST(16);
+    else {
+      // mixed valences: one launch per candidate-count class, each over its own node list
+      static const bool classes_off = std::getenv("FEGPU_NBR_CLASSES") && std::atoi(std::getenv("FEGPU_NBR_CLASSES")) == 0;  // A/B knob
+      if (classes_off) {
+        if (capc <= 128) LAUNCH_FAST(4);
+        else LAUNCH_FAST(16);
+      } else {
+        PT(dalloc(ctx, &d_cls, (size_t)S.na * 3));
+        PT(dalloc(ctx, &d_clscnt, 3));
+        PC(cudaMemsetAsync(d_clscnt, 0, sizeof(unsigned long long) * 3, st));
+        PC(cudaMemsetAsync(P->d_nnbr, 0, sizeof(int32_t) * nn, st));  // nodes without elements are in no list
+        if (!monotone) PC(cudaMemsetAsync(d_sorted, 1, nn, st));
+        k_classify_nodes<<<grid_for(S.na, 256), 256, 0, st>>>(S, d_deg, d_cls, d_cls + S.na, d_cls + 2 * S.na, d_clscnt);
+        ctx->launches++;
+        const SymParams S_all = S;
+        for (int c = 0; c < 3; c++) {
+          S.anodes = d_cls + (size_t)c * S_all.na;
+          S.na_dev = reinterpret_cast<const int64_t *>(d_clscnt + c);
+          if (c == 0) LAUNCH_FAST(2);
+          else if (c == 1) LAUNCH_FAST(4);
+          else if (capc > 128) LAUNCH_FAST(16);
+          ctx->launches++;
+        }
+        S = S_all;
+        ctx->launches--;  // the common increment below counts one of them
+      }
+    }
 #undef LAUNCH_GROUP
 #undef LAUNCH_FAST
     if (monotone) PC(cudaMemsetAsync(d_sorted, 1, nn, st));  // every node is in order; the kernel did not write the flags
