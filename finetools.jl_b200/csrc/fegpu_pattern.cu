@@ -332,17 +332,27 @@ __device__ __forceinline__ void reg_bitonic_lm(uint32_t (&v)[KPL], int lane) {
 //   before the position; every sorted key scatters its slot to cslot[k] (no search), heads write the unique list U.
 template <int KPL, bool CHECK>
 __device__ __forceinline__ void nbr_node(const SymParams &S, const int64_t n, const int64_t ab, const int deg, const int lane, const int KB,
-                                         const int32_t *__restrict__ adj_slot, int32_t *__restrict__ nnbr_out, int32_t *__restrict__ U,
+                                         int32_t *__restrict__ adj_slot, uint8_t *__restrict__ adj_lc, int32_t *__restrict__ nnbr_out,
+                                         int32_t *__restrict__ U,
                                          uint16_t *__restrict__ cslot, uint8_t *__restrict__ sorted_flag, int *any_unsorted, int32_t *smF,
                                          int32_t *smL) {
   const int nne = S.nne;
   const int ncand = deg * nne;
   const uint32_t nne_magic = 65536u / (uint32_t)nne + 1u;  // k / nne == (k * magic) >> 16 for k < 2048 (nne <= 32)
   const uint32_t kmask = (1u << KB) - 1u, dropped = 0xffffffffu >> KB;
+  // the adjacency list arrives in the arbitrary order of k_fill_adj's atomics: sort it here (slot << 5 | local index, one key
+  // per lane) and write it back -- ascending element order is what makes the numeric phase reproduce the reference's sums
   uint32_t el = 0;
-  if (lane < deg) {
-    const int64_t slot = adj_slot[ab + lane];
-    el = (uint32_t)(S.elem_list ? S.elem_list[slot] : slot);
+  {
+    uint32_t key[1] = {0xffffffffu};
+    if (lane < deg) key[0] = ((uint32_t)adj_slot[ab + lane] << 5) | (uint32_t)adj_lc[ab + lane];
+    reg_bitonic_lm<1>(key, lane);
+    if (lane < deg) {
+      const int64_t slot = key[0] >> 5;
+      adj_slot[ab + lane] = (int32_t)slot;
+      adj_lc[ab + lane] = (uint8_t)(key[0] & 31u);
+      el = (uint32_t)(S.elem_list ? S.elem_list[slot] : slot);
+    }
   }
   uint32_t v[KPL];
 #pragma unroll
@@ -423,8 +433,9 @@ __device__ __forceinline__ void nbr_node(const SymParams &S, const int64_t n, co
 // indices fit one 32-bit key (nnodes <= 2^(32-KB) - 2 with 2^KB >= padded candidates).  CHECK = false when the dof map is
 // node-major ascending everywhere (k_dof_monotone): no per-node order test, sorted_flag is not written.
 template <int MAXKPL, bool CHECK>
-__global__ void __launch_bounds__(WPB * 32) k_nbr_fast(SymParams S, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ adj_slot,
-                                                       int capc, int KB, int32_t *__restrict__ nnbr_out, int32_t *__restrict__ U,
+__global__ void __launch_bounds__(WPB * 32) k_nbr_fast(SymParams S, const int64_t *__restrict__ adjptr, int32_t *__restrict__ adj_slot,
+                                                       uint8_t *__restrict__ adj_lc, int capc, int KB, int32_t *__restrict__ nnbr_out,
+                                                       int32_t *__restrict__ U,
                                                        uint16_t *__restrict__ cslot, uint8_t *__restrict__ sorted_flag, int *any_unsorted) {
   extern __shared__ int32_t sfl[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -444,7 +455,7 @@ __global__ void __launch_bounds__(WPB * 32) k_nbr_fast(SymParams S, const int64_
       continue;
     }
     const int ncand = deg * nne;
-#define NBR_ARGS S, n, ab, deg, lane, KB, adj_slot, nnbr_out, U, cslot, sorted_flag, any_unsorted, smF, smL
+#define NBR_ARGS S, n, ab, deg, lane, KB, adj_slot, adj_lc, nnbr_out, U, cslot, sorted_flag, any_unsorted, smF, smL
     // MAXKPL (from the mesh's largest candidate count) bounds the variants compiled in, and with them the register count
     if (ncand <= 32) nbr_node<1, CHECK>(NBR_ARGS);
     else if (MAXKPL <= 2 || ncand <= 64) nbr_node<2, CHECK>(NBR_ARGS);
@@ -510,8 +521,9 @@ __device__ __forceinline__ void group_bitonic(uint32_t (&v)[KPL], int gl) {
 }
 
 template <int LPN, int KPL, bool CHECK>
-__global__ void __launch_bounds__(WPB * 32) k_nbr_group(SymParams S, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ adj_slot,
-                                                        int capc, int KB, int32_t *__restrict__ nnbr_out, int32_t *__restrict__ U,
+__global__ void __launch_bounds__(WPB * 32) k_nbr_group(SymParams S, const int64_t *__restrict__ adjptr, int32_t *__restrict__ adj_slot,
+                                                        uint8_t *__restrict__ adj_lc, int capc, int KB, int32_t *__restrict__ nnbr_out,
+                                                        int32_t *__restrict__ U,
                                                         uint16_t *__restrict__ cslot, uint8_t *__restrict__ sorted_flag, int *any_unsorted) {
   extern __shared__ int32_t sfl[];
   constexpr int NPW = 32 / LPN;
@@ -531,20 +543,27 @@ __global__ void __launch_bounds__(WPB * 32) k_nbr_group(SymParams S, const int64
   int deg = 0;
   uint32_t el = 0;
   int64_t n = -1;
-  auto fetch = [&](int64_t idx) {
+  const int64_t na = S.na_dev ? *S.na_dev : S.na;
+  auto fetch = [&](int64_t idx) {  // called by all lanes of the warp together
     n = -1; ab = 0; deg = 0; el = 0;
-    if (idx < S.na) {
+    uint32_t key[1] = {0xffffffffu};
+    if (idx < na) {
       n = active_node(S, idx);
       ab = adjptr[n];
       deg = (int)(adjptr[n + 1] - ab);
-      if (gl < deg) {
-        const int64_t slot = adj_slot[ab + gl];
-        el = (uint32_t)(S.elem_list ? S.elem_list[slot] : slot);
-      }
+      if (gl < deg) key[0] = ((uint32_t)adj_slot[ab + gl] << 5) | (uint32_t)adj_lc[ab + gl];
+    }
+    // sort the node's adjacency (k_fill_adj's atomics deliver an arbitrary order) and write it back, see nbr_node
+    group_bitonic<LPN, 1>(key, gl);
+    if (gl < deg) {
+      const int64_t slot = key[0] >> 5;
+      adj_slot[ab + gl] = (int32_t)slot;
+      adj_lc[ab + gl] = (uint8_t)(key[0] & 31u);
+      el = (uint32_t)(S.elem_list ? S.elem_list[slot] : slot);
     }
   };
   fetch(first + g);
-  for (int64_t base = first; base < S.na; base += stride) {  // trip count is warp-uniform
+  for (int64_t base = first; base < na; base += stride) {  // trip count is warp-uniform
     const int64_t n_cur = n, ab_cur = ab;
     const int deg_cur = deg;
     const uint32_t el_cur = el;
@@ -1084,10 +1103,19 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
 
   PT(dalloc(ctx, &P->d_adj_slot, nadj));
   PT(dalloc(ctx, &P->d_adj_lc, nadj));
+  int KB = 5;
+  while ((1 << KB) < capc) KB++;
+  static const bool nbr_fast_off = std::getenv("FEGPU_NBR_FAST") && std::atoi(std::getenv("FEGPU_NBR_FAST")) == 0;  // A/B knob
+  // register-only neighbour kernels: adjacency in one register per lane, (node, candidate) and (slot, local index) keys in 32 bits
+  const bool nbr_fast = !nbr_fast_off && maxdeg <= 32 && capc <= 512 && (uint64_t)nn <= (uint64_t)(0xffffffffu >> KB) &&
+                        mesh->nactive < ((int64_t)1 << 27);
   if (nadj > 0) {
     k_fill_adj<<<grid_for(nadj, 256), 256, 0, st>>>(S, P->d_adjptr, d_cursor, P->d_adj_slot, P->d_adj_lc);
-    k_sort_adj<<<grid_for(S.na, 128), 128, 0, st>>>(S, P->d_adjptr, P->d_adj_slot, P->d_adj_lc);
-    ctx->launches += 2;
+    ctx->launches++;
+    if (!nbr_fast) {  // the register-only kernels sort every node's list themselves
+      k_sort_adj<<<grid_for(S.na, 128), 128, 0, st>>>(S, P->d_adjptr, P->d_adj_slot, P->d_adj_lc);
+      ctx->launches++;
+    }
   }
   PT(dalloc(ctx, &P->d_nnbr, nn));
   PT(dalloc(ctx, &d_U, (size_t)nadj * nne));
@@ -1099,23 +1127,19 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   }
   unsigned gridn = (unsigned)std::min<int64_t>((S.na + WPB - 1) / WPB, (int64_t)ctx->sm_count * 64);
   if (gridn == 0) gridn = 1;
-  int KB = 5;
-  while ((1 << KB) < capc) KB++;
-  static const bool nbr_fast_off = std::getenv("FEGPU_NBR_FAST") && std::atoi(std::getenv("FEGPU_NBR_FAST")) == 0;  // A/B knob
-  const bool nbr_fast = !nbr_fast_off && maxdeg <= 32 && capc <= 512 && (uint64_t)nn <= (uint64_t)(0xffffffffu >> KB);
   if (nbr_fast) {
     // register-only kernel; the per-node order test (and its shared memory) only when the dof map is not node-major ascending
     const size_t smf = monotone ? 0 : (size_t)WPB * 2 * capc * sizeof(int32_t);
 #define LAUNCH_FAST(M)                                                                                                              \
   do {                                                                                                                              \
-    if (monotone) k_nbr_fast<M, false><<<gridn, WPB * 32, 0, st>>>(S, P->d_adjptr, P->d_adj_slot, capc, KB, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1); \
-    else k_nbr_fast<M, true><<<gridn, WPB * 32, smf, st>>>(S, P->d_adjptr, P->d_adj_slot, capc, KB, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1);       \
+    if (monotone) k_nbr_fast<M, false><<<gridn, WPB * 32, 0, st>>>(S, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, capc, KB, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1); \
+    else k_nbr_fast<M, true><<<gridn, WPB * 32, smf, st>>>(S, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, capc, KB, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1);       \
   } while (0)
 #define LAUNCH_GROUP(L, K)                                                                                                          \
   do {                                                                                                                              \
     const unsigned gg = (unsigned)std::max<int64_t>(1, std::min<int64_t>((S.na + WPB * (32 / L) - 1) / (WPB * (32 / L)), (int64_t)ctx->sm_count * 64)); \
-    if (monotone) k_nbr_group<L, K, false><<<gg, WPB * 32, 0, st>>>(S, P->d_adjptr, P->d_adj_slot, capc, KB, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1); \
-    else k_nbr_group<L, K, true><<<gg, WPB * 32, smf * (32 / L), st>>>(S, P->d_adjptr, P->d_adj_slot, capc, KB, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1); \
+    if (monotone) k_nbr_group<L, K, false><<<gg, WPB * 32, 0, st>>>(S, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, capc, KB, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1); \
+    else k_nbr_group<L, K, true><<<gg, WPB * 32, smf * (32 / L), st>>>(S, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, capc, KB, P->d_nnbr, d_U, P->d_cslot, d_sorted, d_flags + 1); \
   } while (0)
     static const bool group_off = std::getenv("FEGPU_NBR_GROUP") && std::atoi(std::getenv("FEGPU_NBR_GROUP")) == 0;  // A/B knob
     if (!group_off && capc <= 32 && maxdeg <= 8) LAUNCH_GROUP(8, 4);          // Q4 / T3 skins, T3/Q4 planar: four nodes per warp
@@ -1139,8 +1163,10 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
         for (int c = 0; c < 3; c++) {
           S.anodes = d_cls + (size_t)c * S_all.na;
           S.na_dev = reinterpret_cast<const int64_t *>(d_clscnt + c);
-          if (c == 0) LAUNCH_FAST(2);
-          else if (c == 1) LAUNCH_FAST(4);
+          if (c == 0) {  // <= 64 candidates: deg <= 16 for nne >= 4, so two nodes share a warp
+            if (!group_off && nne >= 4) LAUNCH_GROUP(16, 4);
+            else LAUNCH_FAST(2);
+          } else if (c == 1) LAUNCH_FAST(4);
           else if (capc > 128) LAUNCH_FAST(16);
           ctx->launches++;
         }
