@@ -34,11 +34,13 @@ SIGNATURES = {
     "fegpu_asm_create": (C.c_int32, [VP, C.POINTER(VP)]),
     "fegpu_asm_destroy": (C.c_int32, [VP]),
     "fegpu_asm_set_symmetric": (C.c_int32, [VP, C.c_int32]),
+    "fegpu_asm_set_lumping": (C.c_int32, [VP, C.c_int32]),
     "fegpu_bilform_diffusion": (C.c_int32, [VP, VP, C.c_int32, VP, VP]),
     "fegpu_bilform_lin_elastic": (C.c_int32, [VP, VP, VP, VP]),
     "fegpu_bilform_dot": (C.c_int32, [VP, VP, VP, C.c_int32, C.c_double, VP]),
     "fegpu_bilform_convection": (C.c_int32, [VP, VP, VP, C.c_double, VP]),
     "fegpu_bilform_div_grad": (C.c_int32, [VP, VP, C.c_double, VP]),
+    "fegpu_bilform_masslike": (C.c_int32, [VP, VP, VP, C.c_int32, C.c_double, VP]),
     "fegpu_linform_dot": (C.c_int32, [VP, VP, VP, C.c_int32, C.c_double, VP]),
     "fegpu_vec_startassembly": (C.c_int32, [VP, C.c_int64]),
     "fegpu_vec_assemble": (C.c_int32, [VP, VP, VP, C.c_int64]),

@@ -1,11 +1,12 @@
 """Public names, following FinEtools' exports for the assembly hot path (src/FinEtools.jl:25-673, the subset on the path)."""
 from ._lib import FEGPUError, LIB_PATH  # noqa: F401
 from .assembly import (AbstractSysmatAssembler, AbstractSysvecAssembler, GPUContext, SysvecAssemblerGPU, makevector,  # noqa: F401
+                       SysmatAssemblerSparseDiagGPU, SysmatAssemblerSparseHRZLumpingSymmGPU,
                        SysmatAssemblerFFBlock, SysmatAssemblerSparseGPU,  # noqa: F401
                        SysmatAssemblerSparseSymmGPU, assemble, expectedntriples, makematrix, matrix_blocked_dd,
                        matrix_blocked_df, matrix_blocked_fd, matrix_blocked_ff, setnomatrixresult, startassembly)
 from .datacache import DataCache  # noqa: F401
-from .femm import (CSys, DeforModelRed3D, FEMMBase, ForceIntensity, distribloads, linform_dot,  # noqa: F401
+from .femm import (CSys, DeforModelRed3D, FEMMBase, ForceIntensity, bilform_masslike, distribloads, linform_dot,  # noqa: F401
                    bilform_convection, bilform_diffusion, bilform_div_grad, bilform_dot,  # noqa: F401
                    bilform_lin_elastic, innerproduct)  # noqa: F401
 from .fesets import (ETYPE, FESET_BY_NAME, FESetH8, FESetH20, FESetH27, FESetQ4, FESetT3, FESetT4, FESetT10)  # noqa: F401

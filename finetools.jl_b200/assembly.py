@@ -300,6 +300,30 @@ class SysmatAssemblerSparseSymmGPU(SysmatAssemblerSparseGPU):
         return I[keep], J[keep], V[keep]
 
 
+class SysmatAssemblerSparseDiagGPU(SysmatAssemblerSparseGPU):
+    """SysmatAssemblerSparseDiag (AssemblyModule.jl:599-794): only the diagonals of the square element matrices are assembled;
+    the result is sparse(I = J = dof, V)."""
+    _LUMP = 1
+
+    def __init__(self, z=0.0, nomatrixresult=False, ctx=None, device=0):
+        super().__init__(z, nomatrixresult, ctx, device)
+        check(_lib.lib().fegpu_asm_set_lumping(self.handle, self._LUMP), self.ctx.handle)
+
+    def expectedntriples(self, elem_mat_nrows, elem_mat_ncols, n_elem_mats):
+        return max(elem_mat_nrows, elem_mat_ncols) * n_elem_mats  # :616-621, :963-968
+
+    def assemble(self, mat, dofnums_row, dofnums_col):
+        if np.asarray(dofnums_row).size != np.asarray(dofnums_col).size or np.asarray(mat).shape != (np.asarray(dofnums_row).size,) * 2:
+            raise _lib.FEGPUError(-15, "Size mismatch")  # :724-729
+        return super().assemble(mat, dofnums_row, dofnums_col)
+
+
+class SysmatAssemblerSparseHRZLumpingSymmGPU(SysmatAssemblerSparseDiagGPU):
+    """SysmatAssemblerSparseHRZLumpingSymm (AssemblyModule.jl:943-1141): the diagonal of every element matrix scaled by
+    sum(mat) / trace(mat) (Hinton-Rock-Zienkiewicz lumping), assembled into a diagonal matrix."""
+    _LUMP = 2
+
+
 class SysmatAssemblerFFBlock(AbstractSysmatAssembler):
     """Drop-in for SysmatAssemblerFFBlock (src/AssemblyModule.jl:1149-1231): delegates to a wrapped GPU assembler and returns
     the free-free block A[1:row_nfreedofs, 1:col_nfreedofs] of its matrix, cut out on the device (only the block crosses the

@@ -495,6 +495,14 @@ int32_t fegpu_asm_set_symmetric(fegpu_asm *as, int32_t on) {
   return FEGPU_OK;
 }
 
+int32_t fegpu_asm_set_lumping(fegpu_asm *as, int32_t mode) {
+  if (!as) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL assembler");
+  if (mode < 0 || mode > 2) return fegpu_fail(as->ctx, FEGPU_ERR_ARG, "lumping mode must be 0 (none), 1 (diagonal) or 2 (HRZ)");
+  if (as->started) return fegpu_fail(as->ctx, FEGPU_ERR_STATE, "cannot switch the assembler kind inside an assembly");
+  as->lump = mode;
+  return FEGPU_OK;
+}
+
 int32_t fegpu_asm_destroy(fegpu_asm *a) {
   if (!a) return FEGPU_OK;
   DeviceGuard g(a->ctx->device);
@@ -506,11 +514,14 @@ int32_t fegpu_asm_destroy(fegpu_asm *a) {
   return FEGPU_OK;
 }
 
+static int32_t run_lumped(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &fa, fegpu_asm *as);  // diagonal / HRZ assemblers
+
 static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &fa, fegpu_asm *as) {
   if (!mesh || !dm || !as) return fegpu_fail(mesh ? mesh->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
   fegpu_ctx *ctx = mesh->ctx;
   if (dm->mesh != mesh || as->ctx != ctx || dm->ctx != ctx) return fegpu_fail(ctx, FEGPU_ERR_ARG, "handles belong to different meshes / contexts");
   if (dm->ndn != fa.ndn) return fegpu_fail(ctx, FEGPU_ERR_ARG, "Wrong size of matrix: dofs per node of the field do not fit the form");
+  if (as->lump) return run_lumped(mesh, dm, fa, as);
   DeviceGuard g(ctx->device);
   cudaStream_t st = ctx->stream;
   const int EM = mesh->nne * fa.ndn;
@@ -716,6 +727,46 @@ __global__ void k_emit_rows(const int32_t *__restrict__ conn, const int32_t *__r
   I[i] = (int64_t)dof[(int64_t)(r % ndn) * nnodes + conn[e * nne + r / ndn]] + 1;
 }
 
+// Diagonal / HRZ-lumped assemblers (AssemblyModule.jl:599-794, 943-1141): one warp per square element matrix (column-major,
+// size msize[e] or EM) -> its diagonal, for HRZ scaled by ffactor = sum(mat) / trace(mat) (:1085-1090).  The lanes sum the
+// entries in memory order and combine by a fixed shuffle tree, so the result is reproducible.
+__global__ void k_lump(const double *__restrict__ V, int64_t nmat, int EM, const int64_t *__restrict__ moff, const int64_t *__restrict__ doff,
+                       const int32_t *__restrict__ msize, int hrz, double *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (e >= nmat) return;
+  const int n = msize ? msize[e] : EM;
+  const double *M = V + (moff ? moff[e] : e * (int64_t)EM * EM);
+  double *o = out + (doff ? doff[e] : e * (int64_t)EM);
+  double ff = 1.0;
+  if (hrz) {
+    double em2 = 0.0, dem2 = 0.0;
+    for (int i = lane; i < n * n; i += 32) em2 += M[i];
+    for (int i = lane; i < n; i += 32) dem2 += M[i + (int64_t)n * i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      em2 += __shfl_xor_sync(0xffffffffu, em2, d);
+      dem2 += __shfl_xor_sync(0xffffffffu, dem2, d);
+    }
+    ff = em2 / dem2;
+  }
+  for (int j = lane; j < n; j += 32) o[j] = M[j + (int64_t)n * j] * ff;
+}
+
+// (I, J) of bilform_masslike's triplets in the reference's emission order: element e contributes an ndn x EM matrix whose rows
+// are the element's own ndn global rows (e-1)*ndn + 1 .. e*ndn (FEMMBaseModule.jl:1907-1908)
+__global__ void k_emit_masslike_ij(const int32_t *__restrict__ conn, int64_t nelem, int nne, int ndn, int64_t nnodes,
+                                   const int32_t *__restrict__ dof, int64_t *__restrict__ I, int64_t *__restrict__ J) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = ndn * nne * ndn;
+  if (t >= nelem * per) return;
+  const int64_t e = t / per;
+  const int rem = (int)(t - e * per);
+  const int p = rem % ndn, c = rem / ndn;
+  I[t] = e * ndn + p + 1;
+  J[t] = (int64_t)dof[(int64_t)(c % ndn) * nnodes + conn[e * nne + c / ndn]] + 1;
+}
+
 int32_t vector_from_pairs(fegpu_asm *as, int64_t n, const int64_t *dI, const double *dV, int64_t row_nall) {
   fegpu_ctx *ctx = as->ctx;
   cudaStream_t st = ctx->stream;
@@ -738,6 +789,109 @@ int32_t vector_from_pairs(fegpu_asm *as, int64_t n, const int64_t *dI, const dou
   return FEGPU_OK;
 }
 }  // namespace
+
+// A bilinear form into a SysmatAssemblerSparseDiag / SysmatAssemblerSparseHRZLumpingSymm: full element matrices, their (scaled)
+// diagonals, and sparse(I = J = dof, V) through the sort path -- exactly the reference's makematrix! (:770-778, :1123-1131), so
+// only dofs that appear in an element get a stored entry.
+static int32_t run_lumped(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &fa, fegpu_asm *as) {
+  fegpu_ctx *ctx = mesh->ctx;
+  if (mesh->partitioned) return fegpu_fail(ctx, FEGPU_ERR_ARG, "the lumped / diagonal assemblers do not take row-block partitions");
+  if (dm->row_nall != dm->col_nall) return fegpu_fail(ctx, FEGPU_ERR_ARG, "Row and column info do not agree");  // :689, :1041
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int EM = mesh->nne * fa.ndn;
+  const int64_t nv = mesh->nactive * (int64_t)EM;
+  as->have_result = false;
+  as->pat_src = nullptr;
+  as->view.active = false;
+  as->started = false;
+  as->pattern_cached = false;
+  FormArgs fa2 = fa;
+  fa2.compact = false;
+  FE_TRY(fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(nv * EM, 1)));
+  as->V_n = nv * EM;
+  as->last_EM = EM;
+  as->V_compact = false;
+  CUDA_TRY(ctx, cudaEventRecord(as->ev[0], st));
+  CUDA_TRY(ctx, cudaEventRecord(as->ev[1], st));
+  CUDA_TRY(ctx, cudaEventRecord(as->ev[4], st));
+  FE_TRY(fe_integrate(mesh, fa2, as->d_V));
+  CUDA_TRY(ctx, cudaEventRecord(as->ev[2], st));
+  CUDA_TRY(ctx, cudaEventRecord(as->ev[5], st));
+  int64_t *dI = nullptr;
+  double *dD = nullptr;
+  CUDA_TRY(ctx, cudaMalloc((void **)&dI, sizeof(int64_t) * std::max<int64_t>(nv, 1)));
+  if (cudaMalloc((void **)&dD, sizeof(double) * std::max<int64_t>(nv, 1)) != cudaSuccess) {
+    cudaFree(dI);
+    return fegpu_fail(ctx, FEGPU_ERR_CUDA, "out of device memory");
+  }
+  if (nv) {
+    k_emit_rows<<<grid_for(nv, 256), 256, 0, st>>>(mesh->d_conn, mesh->d_elem_list, mesh->nactive, mesh->nne, fa.ndn, mesh->nnodes, dm->d_dof, dI);
+    k_lump<<<grid_for(mesh->nactive * 32, 256), 256, 0, st>>>(as->d_V, mesh->nactive, EM, nullptr, nullptr, nullptr, as->lump == 2 ? 1 : 0, dD);
+    ctx->launches += 2;
+  }
+  const int32_t s = fe_coo_to_csc(as, nv, dI, dI, dD, dm->row_nall, dm->col_nall);
+  cudaStreamSynchronize(st);
+  cudaFree(dI);
+  cudaFree(dD);
+  FE_TRY(s);
+  CUDA_TRY(ctx, cudaEventRecord(as->ev[3], st));
+  as->ev_valid = true;
+  as->have_result = true;
+  return finish(ctx);
+}
+
+int32_t fegpu_bilform_masslike(fegpu_mesh *mesh, fegpu_dofmap *dm, const double *c, int32_t m, double otherdim, fegpu_asm *as) {
+  if (!mesh || !dm || !c || !as) return fegpu_fail(mesh ? mesh->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  fegpu_ctx *ctx = mesh->ctx;
+  if (dm->mesh != mesh || as->ctx != ctx || dm->ctx != ctx) return fegpu_fail(ctx, FEGPU_ERR_ARG, "handles belong to different meshes / contexts");
+  if (mesh->mdim == 3 && m != 3) return fegpu_fail(ctx, FEGPU_ERR_MANIFOLD, "That is the only acceptable option here.");
+  if (mesh->mdim == 2 && (m < 2 || m > 3)) return fegpu_fail(ctx, FEGPU_ERR_MANIFOLD, "Those are the only acceptable options here.");
+  if (dm->ndn > 3) return fegpu_fail(ctx, FEGPU_ERR_ARG, "bilform_masslike: up to 3 dofs per node");
+  if (mesh->partitioned) return fegpu_fail(ctx, FEGPU_ERR_ARG, "bilform_masslike numbers its rows by element: no row-block partitions");
+  if (as->symmetric || as->lump) return fegpu_fail(ctx, FEGPU_ERR_ARG, "bilform_masslike assembles a rectangular matrix: use the plain sparse assembler");
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = ctx->stream;
+  FormArgs fa;
+  std::memset(&fa, 0, sizeof(fa));
+  fa.form = FORM_MASSLIKE;
+  fa.ndn = dm->ndn;
+  for (int i = 0; i < dm->ndn * dm->ndn; i++) fa.coef[i] = c[i];
+  fa.m = m;
+  fa.otherdim = otherdim;
+  const int per = dm->ndn * mesh->nne * dm->ndn;
+  const int64_t n = mesh->nelem * (int64_t)per;
+  as->have_result = false;
+  as->pat_src = nullptr;
+  as->view.active = false;
+  as->started = false;
+  as->pattern_cached = false;
+  FE_TRY(fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(n, 1)));
+  as->V_n = 0;
+  as->V_compact = false;
+  for (int k : {0, 1, 4}) CUDA_TRY(ctx, cudaEventRecord(as->ev[k], st));
+  FE_TRY(fe_integrate(mesh, fa, as->d_V));
+  for (int k : {2, 5}) CUDA_TRY(ctx, cudaEventRecord(as->ev[k], st));
+  int64_t *dI = nullptr, *dJ = nullptr;
+  CUDA_TRY(ctx, cudaMalloc((void **)&dI, sizeof(int64_t) * std::max<int64_t>(n, 1)));
+  if (cudaMalloc((void **)&dJ, sizeof(int64_t) * std::max<int64_t>(n, 1)) != cudaSuccess) {
+    cudaFree(dI);
+    return fegpu_fail(ctx, FEGPU_ERR_CUDA, "out of device memory");
+  }
+  if (n) {
+    k_emit_masslike_ij<<<grid_for(n, 256), 256, 0, st>>>(mesh->d_conn, mesh->nelem, mesh->nne, dm->ndn, mesh->nnodes, dm->d_dof, dI, dJ);
+    ctx->launches++;
+  }
+  const int32_t s = fe_coo_to_csc(as, n, dI, dJ, as->d_V, mesh->nelem * dm->ndn, dm->col_nall);
+  cudaStreamSynchronize(st);
+  cudaFree(dI);
+  cudaFree(dJ);
+  FE_TRY(s);
+  CUDA_TRY(ctx, cudaEventRecord(as->ev[3], st));
+  as->ev_valid = true;
+  as->have_result = true;
+  return finish(ctx);
+}
 
 int32_t fegpu_linform_dot(fegpu_mesh *mesh, fegpu_dofmap *dm, const double *force, int32_t m, double otherdim, fegpu_asm *as) {
   if (!mesh || !dm || !force || !as) return fegpu_fail(mesh ? mesh->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
@@ -854,8 +1008,10 @@ int32_t fegpu_startassembly(fegpu_asm *as, int64_t nr, int64_t nc, int64_t nmats
   if (!as) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL assembler");
   if (nr < 0 || nc < 0 || nmats < 0 || row_nall < 0 || col_nall < 0) return fegpu_fail(as->ctx, FEGPU_ERR_ARG, "negative size");
   // like the reference (AssemblyModule.jl:221-229) sizes are only taken when no assembly is in flight
+  if (as->lump && nr != nc) return fegpu_fail(as->ctx, FEGPU_ERR_ARG, "Diagonal sparse matrix is assumed to be assembled from square matrices");
+  if (as->lump && row_nall != col_nall) return fegpu_fail(as->ctx, FEGPU_ERR_ARG, "Row and column info do not agree");
   if (!as->started) {
-    as->hI.clear(); as->hJ.clear(); as->hV.clear();
+    as->hI.clear(); as->hJ.clear(); as->hV.clear(); as->hN.clear();
     const size_t expect = (size_t)(nr * nc * nmats);  // expectedntriples, :54-59
     as->hI.reserve(expect); as->hJ.reserve(expect); as->hV.reserve(expect);
     as->g_row_nall = row_nall;
@@ -869,6 +1025,18 @@ int32_t fegpu_assemble(fegpu_asm *as, const double *mat, const int64_t *dr, int6
   if (!as || !mat || !dr || !dc) return fegpu_fail(as ? as->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
   if (!as->started) return fegpu_fail(as->ctx, FEGPU_ERR_STATE, "assemble! before startassembly!");
   if (as->symmetric && nrows != ncols) return fegpu_fail(as->ctx, FEGPU_ERR_MATSIZE, "Size mismatch");  // AssemblyModule.jl:510
+  if (as->lump) {
+    // diagonal / HRZ: the whole square matrix is staged (the scaling factor needs every entry), its column dofs, its size
+    if (nrows != ncols) return fegpu_fail(as->ctx, FEGPU_ERR_MATSIZE, "Size mismatch");  // :724, :1077
+    for (int64_t j = 0; j < ncols; j++) {
+      if (dc[j] < 1) return fegpu_fail(as->ctx, FEGPU_ERR_COL_LT1, "Column degree of freedom < 1");
+      if (dc[j] > as->g_col_nall) return fegpu_fail(as->ctx, FEGPU_ERR_COL_GT, "Column degree of freedom > size");
+    }
+    as->hV.insert(as->hV.end(), mat, mat + nrows * ncols);
+    as->hJ.insert(as->hJ.end(), dc, dc + ncols);
+    as->hN.push_back((int32_t)ncols);
+    return FEGPU_OK;
+  }
   for (int64_t j = 0; j < ncols; j++) {
     const int64_t dj = dc[j];
     if (dj < 1) return fegpu_fail(as->ctx, FEGPU_ERR_COL_LT1, "Column degree of freedom < 1");
@@ -900,6 +1068,55 @@ int32_t fegpu_makematrix(fegpu_asm *as) {
   if (!as->started) return fegpu_fail(ctx, FEGPU_ERR_STATE, "makematrix! without startassembly!");
   DeviceGuard g(ctx->device);
   cudaStream_t st = ctx->stream;
+  if (as->lump) {
+    // staged square matrices -> their (HRZ-scaled) diagonals on the device -> sparse(I = J = dof, V)
+    const int64_t nmat = (int64_t)as->hN.size(), nval = (int64_t)as->hV.size(), nd = (int64_t)as->hJ.size();
+    std::vector<int64_t> moff(nmat + 1, 0), doff(nmat + 1, 0);
+    for (int64_t k = 0; k < nmat; k++) {
+      moff[k + 1] = moff[k] + (int64_t)as->hN[k] * as->hN[k];
+      doff[k + 1] = doff[k] + as->hN[k];
+    }
+    int64_t *dJ = nullptr, *dmo = nullptr, *ddo = nullptr;
+    int32_t *dsz = nullptr;
+    double *dD = nullptr;
+    auto cleanup = [&]() { cudaFree(dJ); cudaFree(dmo); cudaFree(ddo); cudaFree(dsz); cudaFree(dD); };
+    int32_t s = fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(nval, 1));
+    cudaError_t e = cudaSuccess;
+    if (s == FEGPU_OK) {
+      if ((e = cudaMalloc((void **)&dJ, sizeof(int64_t) * std::max<int64_t>(nd, 1))) == cudaSuccess &&
+          (e = cudaMalloc((void **)&dmo, sizeof(int64_t) * (nmat + 1))) == cudaSuccess &&
+          (e = cudaMalloc((void **)&ddo, sizeof(int64_t) * (nmat + 1))) == cudaSuccess &&
+          (e = cudaMalloc((void **)&dsz, sizeof(int32_t) * std::max<int64_t>(nmat, 1))) == cudaSuccess &&
+          (e = cudaMalloc((void **)&dD, sizeof(double) * std::max<int64_t>(nd, 1))) == cudaSuccess) {
+        if (nval) cudaMemcpyAsync(as->d_V, as->hV.data(), sizeof(double) * nval, cudaMemcpyHostToDevice, st);
+        if (nd) cudaMemcpyAsync(dJ, as->hJ.data(), sizeof(int64_t) * nd, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dmo, moff.data(), sizeof(int64_t) * (nmat + 1), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(ddo, doff.data(), sizeof(int64_t) * (nmat + 1), cudaMemcpyHostToDevice, st);
+        if (nmat) cudaMemcpyAsync(dsz, as->hN.data(), sizeof(int32_t) * nmat, cudaMemcpyHostToDevice, st);
+        for (int k : {0, 1, 4, 2, 5}) cudaEventRecord(as->ev[k], st);
+        if (nmat) {
+          k_lump<<<grid_for(nmat * 32, 256), 256, 0, st>>>(as->d_V, nmat, 0, dmo, ddo, dsz, as->lump == 2 ? 1 : 0, dD);
+          ctx->launches++;
+        }
+        s = fe_coo_to_csc(as, nd, dJ, dJ, dD, as->g_row_nall, as->g_col_nall);
+        cudaStreamSynchronize(st);  // the host offset vectors go out of scope
+      } else {
+        s = fegpu_fail(ctx, FEGPU_ERR_CUDA, cudaGetErrorString(e));
+      }
+    }
+    cleanup();
+    FE_TRY(s);
+    CUDA_TRY(ctx, cudaEventRecord(as->ev[3], st));
+    as->ev_valid = true;
+    as->have_result = true;
+    as->pat_src = nullptr;
+    as->pattern_cached = false;
+    as->view.active = false;
+    as->V_compact = false;
+    as->started = false;
+    as->V_n = 0;
+    return finish(ctx);
+  }
   if (as->symmetric) {
     // S + transpose(S) with the doubled diagonal halved (AssemblyModule.jl:576-579): the mirrored copy of every
     // off-diagonal triplet is appended; the diagonal stays single, which equals (2 S_jj) * 0.5 exactly

@@ -99,7 +99,8 @@ template <int NNE, int MDIM, int SDIM, int NDN, int FORM, int TPE>
 __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const IntegParams P) {
   constexpr int EM = NNE * NDN;
   constexpr bool SYM = (FORM == FORM_DIFF_ISO || FORM == FORM_DIFF_GEN || FORM == FORM_ELASTIC);
-  constexpr int NENT = (FORM == FORM_LINDOT) ? EM : (SYM ? EM * (EM + 1) / 2 : EM * EM);  // linform_dot: a vector
+  // linform_dot: a vector; bilform_masslike: an NDN x EM matrix
+  constexpr int NENT = (FORM == FORM_LINDOT) ? EM : (FORM == FORM_MASSLIKE ? NDN * EM : (SYM ? EM * (EM + 1) / 2 : EM * EM));
   constexpr int EPT = (NENT + TPE - 1) / TPE;
   constexpr int GPB = (TPE <= 32) ? 128 / TPE : 1;  // element groups per block
   constexpr int NAUX = (FORM == FORM_ELASTIC) ? 6 * EM : (FORM == FORM_DIFF_GEN ? MDIM * NNE : (FORM == FORM_CONVECTION ? NNE * SDIM : 1));
@@ -131,6 +132,9 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
       while ((c + 1) * (c + 2) / 2 <= idx) c++;
       er[k] = idx - c * (c + 1) / 2;
       ec[k] = c;
+    } else if (FORM == FORM_MASSLIKE) {
+      er[k] = idx % NDN;  // row p of the NDN x EM element matrix
+      ec[k] = idx / NDN;  // column (b, q)
     } else {
       er[k] = idx % EM;
       ec[k] = idx / EM;  // 0 for the element vector of linform_dot
@@ -174,7 +178,15 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
         }
       }
       double Jac = jac_measure<SDIM, MDIM>(J);
-      if (FORM == FORM_LINDOT) {
+      if (FORM == FORM_MASSLIKE) {
+        // factor = Ns[b] * Jac * w ; elmat[p, (b, q)] += factor * c[p, q]               FEMMBaseModule.jl:1896-1903
+        if (MDIM == 2 && P.m == 3) Jac = Jac * P.otherdim;
+#pragma unroll
+        for (int k = 0; k < EPT; k++) {
+          const int p = er[k], c = ec[k];
+          acc[k] += (N[c / NDN] * Jac * sw[j]) * P.coef[p + NDN * (c % NDN)];
+        }
+      } else if (FORM == FORM_LINDOT) {
         // elvec[rx] += (Ns[kx] * (Jac * w)) * force[mx]                                FEMMBaseModule.jl:1230-1239
         if (MDIM == 2 && P.m == 3) Jac = Jac * P.otherdim;
         const double Factor = Jac * sw[j];
@@ -288,11 +300,11 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
       }
     }
     // emission: V[slot][c*EM + r]; the mirrored entry is complete_lt!
-    if (FORM == FORM_LINDOT) {
-      if (live) {
+    if (FORM == FORM_LINDOT || FORM == FORM_MASSLIKE) {
+      if (live) {  // entry idx = t + k*TPE is the position in the element vector / the column-major NDN x EM matrix
 #pragma unroll
         for (int k = 0; k < EPT; k++)
-          if (t + k * TPE < NENT) P.V[slot * (int64_t)EM + er[k]] = acc[k];
+          if (t + k * TPE < NENT) P.V[slot * (int64_t)NENT + t + k * TPE] = acc[k];
       }
     } else if (live && SYM && P.compact) {
       // compact upper-block layout (fegpu_internal.h): block (a <= b) at NDN^2 * (b(b+1)/2 + a), column-major inside
@@ -368,6 +380,11 @@ int32_t dispatch_form(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
       if (fa.ndn == 2) return launch_generic<NNE, MDIM, SDIM, 2, FORM_LINDOT, TPE_S>(mesh, fa, d_V);
       if (fa.ndn == 3) return launch_generic<NNE, MDIM, SDIM, 3, FORM_LINDOT, TPE_S>(mesh, fa, d_V);
       return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "linform_dot: 1, 2 or 3 dofs per node are supported");
+    case FORM_MASSLIKE:
+      if (fa.ndn == 1) return launch_generic<NNE, MDIM, SDIM, 1, FORM_MASSLIKE, TPE_S>(mesh, fa, d_V);
+      if (fa.ndn == 2) return launch_generic<NNE, MDIM, SDIM, 2, FORM_MASSLIKE, TPE_S>(mesh, fa, d_V);
+      if (fa.ndn == 3) return launch_generic<NNE, MDIM, SDIM, 3, FORM_MASSLIKE, TPE_V>(mesh, fa, d_V);
+      return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "bilform_masslike: 1, 2 or 3 dofs per node are supported");
     case FORM_CONVECTION:
       if (SDIM != MDIM) break;
       return launch_generic<NNE, MDIM, (SDIM == MDIM ? SDIM : MDIM), 1, FORM_CONVECTION, TPE_S>(mesh, fa, d_V);

@@ -108,6 +108,8 @@ struct fegpu_asm {
   // generic protocol staging (host side, flushed to the device at makematrix)
   bool started = false;
   bool symmetric = false;  // SysmatAssemblerSparseSymm semantics (fegpu_asm_set_symmetric)
+  int lump = 0;            // 0 none, 1 SysmatAssemblerSparseDiag, 2 SysmatAssemblerSparseHRZLumpingSymm (fegpu_asm_set_lumping)
+  std::vector<int32_t> hN; // generic protocol with lumping: size of every staged square element matrix
   int64_t g_row_nall = 0, g_col_nall = 0;
   std::vector<int64_t> hI, hJ;
   std::vector<double> hV;
@@ -144,7 +146,8 @@ int32_t fe_max_i32(fegpu_ctx *ctx, const int32_t *d_in, int64_t n, int32_t *max_
 
 // ---- integration (fegpu_integrate.cu) ------------------------------------------------------------------
 enum { FORM_DIFF_ISO = 0, FORM_DIFF_GEN = 1, FORM_ELASTIC = 2, FORM_DOT = 3, FORM_CONVECTION = 4, FORM_DIV_GRAD = 5,
-       FORM_LINDOT = 6 /* linform_dot: element VECTORS, [nactive][EM] */ };
+       FORM_LINDOT = 6 /* linform_dot: element VECTORS, [nactive][EM] */,
+       FORM_MASSLIKE = 7 /* bilform_masslike: rectangular ndn x EM element matrices, [nactive][ndn*EM] column-major */ };
 struct FormArgs {
   int form;
   int ndn;

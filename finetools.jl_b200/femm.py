@@ -254,6 +254,27 @@ def bilform_div_grad(self, assembler, geom, u, viscf, raw=False, node_owner=None
     return _finish(assembler, fes, dmesh, dof, u, raw, out)
 
 
+def bilform_masslike(self, assembler, geom, phi, cf, m=3, raw=False, out=None):
+    """int chi c phi with chi the indicator function of each element (FEMMBaseModule.jl:1865-1912): a rectangular
+    (count(fes) * ndn) x nalldofs(phi) matrix, element i owning rows (i-1)*ndn+1 .. i*ndn."""
+    _eligible(self, assembler, geom, phi, cf)
+    ndn = phi.ndofs()
+    c = cf.data
+    if c.ndim == 0:
+        c = c.reshape(1, 1)
+    if c.shape != (ndn, ndn):
+        raise FEGPUError(-2, "coefficient must be ndn x ndn")
+    fes, dmesh, dof = _prepare(self, assembler, geom, phi)
+    cfm = np.asfortranarray(c)
+    a = _inner(assembler)
+    check(_lib.lib().fegpu_bilform_masslike(dmesh.handle, dof, fptr(cfm), int(m), float(self.integdomain.otherdimension), a.handle),
+          assembler.ctx.handle)
+    a._mode = "form"
+    a._row_nalldofs, a._col_nalldofs = fes.count() * ndn, phi.nalldofs()
+    a._pending_form = None
+    return assembler.makematrix(raw=raw, out=out)
+
+
 class ForceIntensity:
     """Constant distributed-load intensity (src/ForceIntensityModule.jl: the constant constructors wrap the vector in a
     DataCache); only constant intensities are GPU-eligible."""

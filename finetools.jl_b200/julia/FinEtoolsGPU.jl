@@ -14,11 +14,12 @@ using SparseArrays
 import FinEtools.AssemblyModule: AbstractSysmatAssembler, AbstractSysvecAssembler, startassembly!, assemble!, makematrix!,
     makevector!, eltype, expectedntriples
 import FinEtools.FEMMBaseModule: bilform_diffusion, bilform_lin_elastic, bilform_dot, bilform_convection, bilform_div_grad,
-    linform_dot, FEMMBase, finite_elements
+    bilform_masslike, linform_dot, FEMMBase, finite_elements
 using FinEtools.IntegDomainModule: integrationdata, otherdimensionunity
 using FinEtools.DeforModelRedModule: DeforModelRed3D
 
-export SysmatAssemblerSparseGPU, SysmatAssemblerSparseSymmGPU, SysvecAssemblerGPU, gpu_matrix_blocked
+export SysmatAssemblerSparseGPU, SysmatAssemblerSparseSymmGPU, SysmatAssemblerSparseDiagGPU, SysmatAssemblerSparseHRZLumpingSymmGPU,
+    SysvecAssemblerGPU, gpu_matrix_blocked
 
 const LIB = get(ENV, "FEGPU_LIB", joinpath(@__DIR__, "..", "libfinegpu.so"))
 
@@ -114,6 +115,21 @@ function SysmatAssemblerSparseSymmGPU(z::Float64 = 0.0, nomatrixresult = false; 
     _check(ccall((:fegpu_asm_set_symmetric, LIB), Int32, (Ptr{Cvoid}, Int32), a.handle, 1), a.ctx)
     return a
 end
+
+"""
+    SysmatAssemblerSparseDiagGPU(z = 0.0), SysmatAssemblerSparseHRZLumpingSymmGPU(z = 0.0)
+
+`SysmatAssemblerSparseDiag` (AssemblyModule.jl:599-794) and `SysmatAssemblerSparseHRZLumpingSymm` (:943-1141): the handle is
+switched to diagonal (1) / HRZ (2) lumping, every method of `SysmatAssemblerSparseGPU` applies unchanged, e.g.
+`M = bilform_dot(femm, SysmatAssemblerSparseHRZLumpingSymmGPU(0.0), geom, u, DataCache(rho * I(3)))`.
+"""
+function SysmatAssemblerSparseDiagGPU(z::Float64 = 0.0, nomatrixresult = false; device = 0, mode = 1)
+    a = SysmatAssemblerSparseGPU(z, nomatrixresult; device)
+    _check(ccall((:fegpu_asm_set_lumping, LIB), Int32, (Ptr{Cvoid}, Int32), a.handle, mode), a.ctx)
+    return a
+end
+SysmatAssemblerSparseHRZLumpingSymmGPU(z::Float64 = 0.0, nomatrixresult = false; device = 0) =
+    SysmatAssemblerSparseDiagGPU(z, nomatrixresult; device, mode = 2)
 
 """
     gpu_matrix_blocked(a::SysmatAssemblerSparseGPU, row_nfreedofs, col_nfreedofs = row_nfreedofs)
@@ -240,6 +256,18 @@ function bilform_div_grad(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, g
     mh, dh = _device(self, assembler, geom, u)
     _check(ccall((:fegpu_bilform_div_grad, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Ptr{Cvoid}),
             mh, dh, Float64(viscf._cache), assembler.handle), assembler.ctx)
+    return makematrix!(assembler)
+end
+
+# bilform_masslike (FEMMBaseModule.jl:1865-1912): rectangular (count(fes)*ndn) x nalldofs(phi), rows numbered by element
+function bilform_masslike(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, geom::NodalField{FT}, phi::NodalField{T}, cf::DC;
+    m = 3) where {FT,T,DC<:DataCache}
+    _eligible(self, geom, phi, cf)
+    mh, dh = _device(self, assembler, geom, phi)
+    c = Matrix{Float64}(reshape(collect(cf._cache), ndofs(phi), ndofs(phi)))
+    GC.@preserve c _check(ccall((:fegpu_bilform_masslike, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Ptr{Cvoid}),
+            mh, dh, c, m, 1.0, assembler.handle), assembler.ctx)
+    assembler._row_nalldofs, assembler._col_nalldofs = count(finite_elements(self)) * ndofs(phi), nalldofs(phi)
     return makematrix!(assembler)
 end
 

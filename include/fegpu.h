@@ -94,6 +94,12 @@ int32_t fegpu_asm_destroy(fegpu_asm *as);
  * (square) element matrix (:517-530, "Size mismatch" :510); fegpu_makematrix and the bilform calls deliver
  * S + transpose(S) with the diagonal halved (:576-579), i.e. the symmetric matrix WITHOUT entries that sum to exactly 0.0. */
 int32_t fegpu_asm_set_symmetric(fegpu_asm *as, int32_t on);
+/* SysmatAssemblerSparseDiag (AssemblyModule.jl:599-794; mode 1) and SysmatAssemblerSparseHRZLumpingSymm (:943-1141; mode 2):
+ * every square element matrix contributes only its diagonal, for HRZ scaled by sum(mat) / trace(mat) (:1085-1090); the result
+ * is sparse(I = J = dof, V): a diagonal matrix with a stored entry for every dof that appears in an element.  Applies to the
+ * bilinear forms and to the generic startassembly!/assemble!/makematrix! protocol ("Size mismatch", "Row and column info do
+ * not agree", "Diagonal sparse matrix is assumed to be assembled from square matrices" as in the reference).  Mode 0 = off. */
+int32_t fegpu_asm_set_lumping(fegpu_asm *as, int32_t mode);
 
 /* The three bilinear forms.  Each call = startassembly! + the whole element loop + makematrix!
  * (the CSC stays on the device until fegpu_makematrix_copy). */
@@ -111,6 +117,10 @@ int32_t fegpu_bilform_dot(fegpu_mesh *mesh, fegpu_dofmap *dofmap, const double *
 int32_t fegpu_bilform_convection(fegpu_mesh *mesh, fegpu_dofmap *dofmap, const double *uvel, double rho, fegpu_asm *as);
 /* bilform_div_grad, FEMMBaseModule.jl:1672-1713.  dofmap: vector field with sdim dofs per node; mu: constant viscosity */
 int32_t fegpu_bilform_div_grad(fegpu_mesh *mesh, fegpu_dofmap *dofmap, double mu, fegpu_asm *as);
+/* bilform_masslike, FEMMBaseModule.jl:1865-1912: the test function is the indicator of each element, so the matrix is
+ * (nelem * ndn) x nalldofs with element e owning rows (e-1)*ndn + 1 .. e*ndn; c: ndn x ndn col-major.  Built through the
+ * generic sort path (plain sparse assembler only, no row-block partitions). */
+int32_t fegpu_bilform_masslike(fegpu_mesh *mesh, fegpu_dofmap *dofmap, const double *c, int32_t m, double otherdim, fegpu_asm *as);
 
 /* -- vectors: linform_dot / distribloads and SysvecAssembler ---------------------- */
 /* linform_dot, FEMMBaseModule.jl:1207-1244 (distribloads :1277-1297 forwards a ForceIntensity's cache to it): F_i = int N_i f

@@ -781,6 +781,45 @@ ORC_API int orc_bilform_div_grad(int et, int64_t nelem, const int64_t *conn, int
   return rc;
 }
 
+/* bilform_masslike: FEMMBaseModule.jl:1865-1912.  Rows are numbered by element: element i owns rows (i-1)*ndn+1 .. i*ndn;
+ * c is ndn x ndn col-major; emits nelem * ndn * (nne*ndn) triplets. */
+ORC_API int orc_bilform_masslike(int et, int64_t nelem, const int64_t *conn, int64_t nnodes, int sdim, const double *xyz, int ndn,
+                                 const int64_t *dofnums, int64_t nalldofs, int npts, const double *pc, const double *w, const double *c,
+                                 int m, double otherdim, int64_t *I, int64_t *J, double *V) {
+  formctx f;
+  if (form_setup(&f, et, nelem, conn, nnodes, sdim, xyz, ndn, dofnums, nalldofs, npts, pc, w)) return -1;
+  int nne = f.nne, mdim = f.mdim;
+  int elrows = ndn, elcols = nne * ndn;
+  if ((mdim == 3 && m != 3) || (mdim == 2 && (m < 2 || m > 3))) { form_free(&f); return -3; }
+  double ecoords[27 * 3], loc[3], Jm[9];
+  double *elmat = (double *)malloc(sizeof(double) * elrows * elcols);
+  int64_t *dofs = (int64_t *)malloc(sizeof(int64_t) * elcols);
+  int64_t rowdofs[6];
+  int64_t p = 0;
+  int rc = 0;
+  for (int64_t i = 0; i < nelem && !rc; i++) {
+    gather_elem(&f, i, ecoords, dofs);
+    memset(elmat, 0, sizeof(double) * elrows * elcols);
+    for (int j = 0; j < npts; j++) {
+      const double *N = f.Ns + (size_t)j * nne, *dN = f.dNs + (size_t)j * nne * mdim;
+      locjac(loc, Jm, ecoords, N, dN, nne, sdim, mdim);
+      double Jac;
+      if (mdim == 3) Jac = jacobian3(Jm);
+      else { Jac = jacobian2(Jm, sdim); if (m == 3) Jac = Jac * otherdim; }
+      for (int b = 0; b < nne; b++) {
+        double factor = N[b] * Jac * w[j];
+        for (int pp = 0; pp < ndn; pp++)
+          for (int q = 0; q < ndn; q++) elmat[pp + (size_t)elrows * (b * ndn + q)] += factor * c[pp + ndn * q];
+      }
+    }
+    for (int r = 0; r < elrows; r++) rowdofs[r] = i * elrows + r + 1; /* collect(((i-1)*elrows + 1):(i*elrows)) */
+    rc = assemble(I, J, V, &p, elmat, rowdofs, elrows, dofs, elcols, nelem * elrows, nalldofs);
+  }
+  free(elmat); free(dofs);
+  form_free(&f);
+  return rc;
+}
+
 /* linform_dot (= distribloads with a constant ForceIntensity): FEMMBaseModule.jl:1207-1244, SysvecAssembler
  * AssemblyModule.jl:853-917.  force is ndn values; F has nalldofs entries (zeroed here like startassembly!). */
 ORC_API int orc_linform_dot(int et, int64_t nelem, const int64_t *conn, int64_t nnodes, int sdim, const double *xyz, int ndn,

@@ -75,6 +75,8 @@ def lib():
                                                _i64p, _i64p, _f64p]
         L.orc_bilform_convection.argtypes = common + [_f64p, C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, C.c_double, _i64p, _i64p, _f64p]
         L.orc_bilform_div_grad.argtypes = common + [C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, C.c_double, _i64p, _i64p, _f64p]
+        L.orc_bilform_masslike.argtypes = common + [C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double,
+                                                    _i64p, _i64p, _f64p]
         L.orc_linform_dot.argtypes = common + [C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double, _f64p]
         L.orc_sparse.argtypes = [C.c_int64, _i64p, _i64p, _f64p, C.c_int64, C.c_int64, _i64p, C.c_void_p, C.c_void_p]
         L.orc_sparse.restype = C.c_int64
@@ -201,6 +203,18 @@ def bilform_div_grad_coo(et, conn, xyz, dofnums, nalldofs, pc, w, mu):
     return I, J, V
 
 
+def bilform_masslike_coo(et, conn, xyz, dofnums, nalldofs, pc, w, c, m=3, otherdim=1.0):
+    """Reference-order COO of bilform_masslike (FEMMBaseModule.jl:1865-1912): (nelem*ndn) x nalldofs, rows numbered by element."""
+    conn, nelem, nne, X, nnodes, sdim, dn, ndn, P, W, npts = _prep(et, conn, xyz, dofnums, pc, w)
+    n = nelem * ndn * nne * ndn
+    I, J, V = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n)
+    cm = _F(np.asarray(c, dtype=np.float64).reshape(ndn, ndn))
+    rc = lib().orc_bilform_masslike(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, ndn, dn, nalldofs, npts, P, W, cm, m, otherdim, I, J, V)
+    if rc:
+        raise RuntimeError(_ERR.get(rc, "oracle error %d" % rc))
+    return I, J, V
+
+
 def linform_dot(et, conn, xyz, dofnums, nalldofs, pc, w, force, m=3, otherdim=1.0):
     """The assembled vector of linform_dot / distribloads with a constant force (FEMMBaseModule.jl:1207-1244)."""
     conn, nelem, nne, X, nnodes, sdim, dn, ndn, P, W, npts = _prep(et, conn, xyz, dofnums, pc, w)
@@ -230,6 +244,23 @@ def sparse(I, J, V, m, n):
     if nnz < 0:
         raise ValueError("row/column index out of range")
     return colptr, rowval[:nnz].copy(), nzval[:nnz].copy()
+
+
+def lumped_coo(I, J, V, em, mode):
+    """COO of SysmatAssemblerSparseDiag (mode 1, AssemblyModule.jl:718-743: V = mat[j, j]) or
+    SysmatAssemblerSparseHRZLumpingSymm (mode 2, :1070-1101: V = mat[j, j] * sum(mat) / trace(mat)) from the full reference-order
+    triplets of `nelem` square em x em element matrices; feed the result to sparse(I, I, V, n, n) (:770-778, :1123-1131)."""
+    nelem = V.size // (em * em)
+    mats = V.reshape(nelem, em, em).transpose(0, 2, 1)          # [e][row][col] from the column-major emission order
+    cols = J.reshape(nelem, em, em)[:, :, 0]                     # column dof of every column
+    diag = np.einsum("eii->ei", mats).copy()
+    if mode == 2:
+        em2 = mats.sum(axis=1).sum(axis=1)                       # sum(sum(mat, dims = 1))
+        dem2 = np.zeros(nelem)
+        for i in range(em):                                      # dem2 += mat[i, i], in order
+            dem2 = dem2 + mats[:, i, i]
+        diag = diag * (em2 / dem2)[:, None]
+    return cols.reshape(-1).copy(), diag.reshape(-1)
 
 
 def matrix_block(csc, r0, r1, c0, c1):

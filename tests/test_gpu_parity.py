@@ -819,3 +819,87 @@ def test_sysvec_assembler_protocol(fe, gpu_ctx):
         a.assemble(np.array([1.0]), [4])
     a.startassembly(3)
     np.testing.assert_array_equal(fe.makevector(a), [0.0, 0.0, 0.0])
+
+
+@pytest.mark.parametrize("kind", ["diag", "hrz"])
+@pytest.mark.parametrize("et,ndn", [("H8", 3), ("T10", 1), ("H20", 3), ("T4", 3)])
+def test_lumped_mass_assemblers(fe, orc, gpu_ctx, kind, et, ndn):
+    """SysmatAssemblerSparseDiag / SysmatAssemblerSparseHRZLumpingSymm (AssemblyModule.jl:599-794, 943-1141) fed by bilform_dot:
+    pattern (the diagonal entries of the dofs that appear in an element) bit-exact, values within 1e-12; HRZ preserves the mass:
+    sum(M_lumped) = ndn * rho * V."""
+    fens, fes = _mesh(fe, et)
+    _distort(fens)
+    rule = _rule(fe, et)
+    u = make_field(fe, fens, ndn, fixed_nodes=[3, 4] if ndn == 3 else None, fixed_comp=None)
+    c = 2.5 * np.eye(ndn)
+    n = u.nalldofs()
+    I, J, V = orc.bilform_dot_coo(et, fes.conn, fens.xyz, u.dofnums, n, rule.param_coords, rule.weights, c)
+    Id, Vd = orc.lumped_coo(I, J, V, fes.nne * ndn, 1 if kind == "diag" else 2)
+    ref = orc.sparse(Id, Id, Vd, n, n)
+    a = fe.SysmatAssemblerSparseDiagGPU(0.0) if kind == "diag" else fe.SysmatAssemblerSparseHRZLumpingSymmGPU(0.0)
+    assert a.expectedntriples(24, 24, 10) == 240
+    got, _ = gpu_csc(fe, "dot", fes, fens, u, rule, c, assembler=a)
+    assert_parity(ref, got)
+    assert np.array_equal(np.repeat(np.arange(1, n + 1), np.diff(got[0])), got[1])  # diagonal
+    if kind == "hrz":
+        full = orc.sparse(I, J, V, n, n)
+        assert abs(got[2].sum() - full[2].sum()) <= 1e-10 * abs(full[2].sum())
+
+
+def test_lumped_assemblers_generic_protocol(fe, orc, gpu_ctx):
+    """startassembly!/assemble!/makematrix! of the diagonal and HRZ assemblers with host element matrices, and their errors."""
+    rng = np.random.default_rng(5)
+    mats = [rng.random((k, k)) + k * np.eye(k) for k in (4, 4, 3)]
+    dofs = [[1, 4, 6, 2], [2, 3, 7, 1], [7, 5, 1]]
+    for cls, mode in ((fe.SysmatAssemblerSparseDiagGPU, 1), (fe.SysmatAssemblerSparseHRZLumpingSymmGPU, 2)):
+        a = cls(0.0)
+        a.startassembly(4, 4, 3, 7, 7)
+        for m, d in zip(mats, dofs):
+            a.assemble(m, d, d)
+        colptr, rowval, nzval, mm, nn = a.makematrix(raw=True)
+        I = np.concatenate([np.asarray(d, np.int64) for d in dofs])
+        V = np.concatenate([np.diag(m) * ((m.sum() / np.trace(m)) if mode == 2 else 1.0) for m in mats])
+        ref = orc.sparse(I, I, V, 7, 7)
+        assert (mm, nn) == (7, 7)
+        np.testing.assert_array_equal(colptr, ref[0])
+        np.testing.assert_array_equal(rowval, ref[1])
+        assert np.abs(nzval - ref[2]).max() <= 1e-13 * np.abs(ref[2]).max()
+        with pytest.raises(fe.FEGPUError, match="Size mismatch"):
+            a.startassembly(4, 4, 1, 7, 7)
+            a.assemble(np.ones((4, 3)), [1, 2, 3, 4], [1, 2, 3])
+        b = cls(0.0)
+        with pytest.raises(fe.FEGPUError, match="square matrices"):
+            b.startassembly(4, 3, 1, 7, 7)
+        with pytest.raises(fe.FEGPUError, match="Row and column info do not agree"):
+            b.startassembly(4, 4, 1, 7, 8)
+
+
+@pytest.mark.parametrize("et,ndn,m", [("H8", 1, 3), ("T10", 3, 3), ("H20", 1, 3), ("Q4", 1, 2), ("T3", 2, 2)])
+def test_masslike_parity(fe, orc, gpu_ctx, et, ndn, m):
+    """bilform_masslike (FEMMBaseModule.jl:1865-1912): rectangular matrix with element-numbered rows; pattern bit-exact, values
+    within 1e-12; row sums of a scalar field are c times the element measures."""
+    if et in ("Q4", "T3"):
+        fens, vol = (fe.H8block if et == "Q4" else fe.T4block)(1.0, 2.0, 3.0, 3, 2, 2)
+        fes = fe.meshboundary(vol)
+        rule = fe.GaussRule(2, 2) if et == "Q4" else fe.TriRule(3)
+    else:
+        fens, fes = _mesh(fe, et)
+        _distort(fens)
+        rule = _rule(fe, et)
+    phi = make_field(fe, fens, ndn)
+    c = np.array([[2.0, 0.3, -0.1], [0.0, 1.5, 0.2], [0.4, 0.0, 3.0]])[:ndn, :ndn]
+    n = phi.nalldofs()
+    I, J, V = orc.bilform_masslike_coo(et, fes.conn, fens.xyz, phi.dofnums, n, rule.param_coords, rule.weights, c, m=m)
+    ref = orc.sparse(I, J, V, fes.count() * ndn, n)
+    femm = fe.FEMMBase(fe.IntegDomain(fes, rule))
+    got = fe.bilform_masslike(femm, fe.SysmatAssemblerSparseGPU(0.0), fe.NodalField(fens.xyz), phi, fe.DataCache(c), m=m, raw=True)
+    assert (got[3], got[4]) == (fes.count() * ndn, n)
+    assert_parity(ref, got)
+    if ndn == 1:
+        import scipy.sparse as sp
+        M = sp.csc_matrix((got[2], got[1] - 1, got[0] - 1), shape=(got[3], got[4]))
+        measure = np.asarray(M.sum(axis=1)).reshape(-1) / c[0, 0]
+        total = {"H8": 1.3 * 3.1 * 2.7, "H20": 1.3 * 3.1 * 2.7, "Q4": 2 * (2 + 6 + 3)}.get(et)
+        assert (measure > 0).all()
+        if total is not None and et == "Q4":
+            assert abs(measure.sum() - total) <= 1e-10 * total
