@@ -359,6 +359,12 @@ int32_t fegpu_rule_set(fegpu_mesh *m, int32_t npts, const double *Ns, const doub
   return FEGPU_OK;
 }
 
+int32_t fegpu_otherdimension_set(fegpu_mesh *m, double otherdim) {
+  if (!m) return FEGPU_ERR_ARG;
+  m->otherdim = otherdim;
+  return FEGPU_OK;
+}
+
 int32_t fegpu_partition_set(fegpu_mesh *m, const int32_t *node_owner, int32_t my_rank) {
   if (!m) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL mesh");
   fegpu_ctx *ctx = m->ctx;
@@ -638,7 +644,7 @@ int32_t fegpu_bilform_diffusion(fegpu_mesh *mesh, fegpu_dofmap *dm, int32_t kapp
   const int nk = (kappa_kind == 0) ? 1 : mesh->mdim * mesh->mdim;
   for (int i = 0; i < nk; i++) fa.coef[i] = kappa[i];
   fa.m = 3;
-  fa.otherdim = 1.0;
+  fa.otherdim = mesh->otherdim;
   return run_bilform(mesh, dm, fa, as);
 }
 
@@ -685,7 +691,7 @@ int32_t fegpu_bilform_convection(fegpu_mesh *mesh, fegpu_dofmap *dm, const doubl
   fa.ndn = 1;
   fa.coef[0] = rho;  // evaluated by the reference but not used in its integrand (FEMMBaseModule.jl:1606-1617)
   fa.m = 3;
-  fa.otherdim = 1.0;
+  fa.otherdim = mesh->otherdim;
   fa.d_uvel = mesh->d_uvel;
   return run_bilform(mesh, dm, fa, as);
 }
@@ -700,7 +706,7 @@ int32_t fegpu_bilform_div_grad(fegpu_mesh *mesh, fegpu_dofmap *dm, double mu, fe
   fa.ndn = dm->ndn;
   fa.coef[0] = mu;
   fa.m = 3;
-  fa.otherdim = 1.0;
+  fa.otherdim = mesh->otherdim;
   return run_bilform(mesh, dm, fa, as);
 }
 

@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
         // gradN rows
         double inv[MDIM * MDIM];
         if (SDIM == MDIM) jac_inverse<MDIM>(J, inv);
+        if (MDIM == 2) Jac = Jac * P.otherdim;  // Jacobianvolume of a 2-manifold: surface Jacobian x other dimension (IntegDomainModule.jl:504-517)
         const double Jw = Jac * sw[j];
         group_sync<TPE>();  // previous point's G / AUX reads are done
         for (int a = t; a < NNE; a += TPE) {

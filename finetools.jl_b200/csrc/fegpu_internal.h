@@ -37,6 +37,7 @@ struct fegpu_mesh {
   int64_t nelem = 0, nnodes = 0;
   int32_t *d_conn = nullptr;  // [nelem][nne] 0-based
   double *d_xyz = nullptr;    // [sdim][nnodes]
+  double otherdim = 1.0;      // constant other-dimension of the IntegDomain (thickness of a 2-manifold, fegpu_otherdimension_set)
   double *d_uvel = nullptr;   // [sdim][nnodes] nodal field of bilform_convection (fegpu_bilform_convection uploads it)
   // quadrature tables (device copy): N [npts][nne], dN [npts][mdim][nne], w [npts]
   int npts = 0;

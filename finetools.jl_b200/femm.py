@@ -65,6 +65,7 @@ class _DeviceMesh:
         check(_lib.lib().fegpu_geom_update(self.handle, fptr(xyz)), self.ctx.handle)
 
     def set_rule(self, integdomain):
+        check(_lib.lib().fegpu_otherdimension_set(self.handle, float(integdomain.otherdimension)), self.ctx.handle)
         rule = integdomain.integration_rule
         key = (id(rule), rule.npts)
         if key == self.rule_key:

@@ -154,12 +154,15 @@ end
 function _eligible(self::FEMMBase, geom, u, cf)
     self.mcsys.isidentity || error("only the identity material coordinate system is GPU-eligible")
     self.integdomain.axisymmetric && error("axisymmetric integration domains are not GPU-eligible")
-    (self.integdomain.otherdimension === otherdimensionunity) || error("only the unit other-dimension is GPU-eligible")
+    # other dimension: unity, or the constant closure of IntegDomain(fes, rule, t) (IntegDomainModule.jl:73-82); _otherdim evaluates it
     # DataCache: only the constant constructor (DataCacheModule.jl:77-89) may cross the boundary
     eltype(geom.values) == Float64 || error("geom must be Float64")
     eltype(u.dofnums) == Int64 || error("dofnums must be Int64")
     return nothing
 end
+
+# constant other-dimension: the closure ignores its arguments (IntegDomainModule.jl:76-78), so one evaluation gives the constant
+_otherdim(self::FEMMBase) = Float64(self.integdomain.otherdimension(zeros(1, 3), finite_elements(self).conn[1], zeros(1)))
 
 function _device(self::FEMMBase, a, geom, u)   # a: SysmatAssemblerSparseGPU or SysvecAssemblerGPU (same device-twin cache)
     fes = finite_elements(self)
@@ -186,6 +189,7 @@ function _device(self::FEMMBase, a, geom, u)   # a: SysmatAssemblerSparseGPU or 
         GC.@preserve xyz _check(ccall((:fegpu_geom_update, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), entry[1], xyz), a.ctx)
     end
     mh, dms = entry
+    _check(ccall((:fegpu_otherdimension_set, LIB), Int32, (Ptr{Cvoid}, Float64), mh, _otherdim(self)), a.ctx)
     dh = get(dms, u.dofnums, C_NULL)
     if dh == C_NULL
         d = Ref{Ptr{Cvoid}}(C_NULL)
@@ -233,7 +237,7 @@ function bilform_dot(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, geom::
     mh, dh = _device(self, assembler, geom, u)
     c = Matrix{Float64}(cf._cache)          # densifies LinearAlgebra.I(ndofs) (a Diagonal{Bool}), see innerproduct :1388-1401
     GC.@preserve c _check(ccall((:fegpu_bilform_dot, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Ptr{Cvoid}),
-            mh, dh, c, m, 1.0, assembler.handle), assembler.ctx)
+            mh, dh, c, m, _otherdim(self), assembler.handle), assembler.ctx)
     return makematrix!(assembler)
 end
 
@@ -266,7 +270,7 @@ function bilform_masslike(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, g
     mh, dh = _device(self, assembler, geom, phi)
     c = Matrix{Float64}(reshape(collect(cf._cache), ndofs(phi), ndofs(phi)))
     GC.@preserve c _check(ccall((:fegpu_bilform_masslike, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Ptr{Cvoid}),
-            mh, dh, c, m, 1.0, assembler.handle), assembler.ctx)
+            mh, dh, c, m, _otherdim(self), assembler.handle), assembler.ctx)
     assembler._row_nalldofs, assembler._col_nalldofs = count(finite_elements(self)) * ndofs(phi), nalldofs(phi)
     return makematrix!(assembler)
 end
@@ -326,7 +330,7 @@ function linform_dot(self::FEMMBase, assembler::SysvecAssemblerGPU, geom::NodalF
     force = Vector{Float64}(vec(collect(f._cache)))
     length(force) == ndofs(P) || error("the load needs one component per degree of freedom of a node")
     GC.@preserve force _check(ccall((:fegpu_linform_dot, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Ptr{Cvoid}),
-            mh, dh, force, m, 1.0, assembler.handle), assembler.ctx)
+            mh, dh, force, m, _otherdim(self), assembler.handle), assembler.ctx)
     assembler._row_nalldofs = nalldofs(P)
     return _fetchvector(assembler)
 end

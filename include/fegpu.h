@@ -76,6 +76,10 @@ int32_t fegpu_geom_update(fegpu_mesh *mesh, const double *xyz);
 /* quadrature tables exactly as the caller's integrationdata() produced them (IntegDomainModule.jl:631-648):
  * Ns [npts][nne], gradNpar [npts][mdim][nne] (i.e. each point's nne x mdim matrix, column-major), w [npts] */
 int32_t fegpu_rule_set(fegpu_mesh *mesh, int32_t npts, const double *Ns, const double *gradNpar, const double *w);
+/* constant other-dimension of the IntegDomain (IntegDomainModule.jl:73-82, 150-152): the thickness that multiplies the
+ * surface Jacobian of a 2-manifold in Jacobianvolume (:504-517); used by the gradient forms (diffusion, convection,
+ * div_grad) on planar meshes.  Default 1.0 (otherdimensionunity).  bilform_dot / masslike / linform_dot take it per call. */
+int32_t fegpu_otherdimension_set(fegpu_mesh *mesh, double otherdimension);
 /* multi-GPU row-block ownership (pointpartitioning semantics, MeshModificationModule.jl:1029): this context
  * integrates every element touching a node with node_owner[n] == my_rank and keeps the matrix rows of those
  * nodes' dofs.  node_owner == NULL restores the single-GPU behaviour. */

@@ -588,7 +588,7 @@ static const double IDENT2[4] = {1, 0, 0, 1};
  * Emits nelem*nne^2 triplets into I,J,V (reference emission order).  If elmats != NULL also stores element matrices. */
 ORC_API int orc_bilform_diffusion(int et, int64_t nelem, const int64_t *conn, int64_t nnodes, int sdim, const double *xyz,
                                   const int64_t *dofnums, int64_t nalldofs, int npts, const double *pc, const double *w,
-                                  int kappa_kind, const double *kappa, int64_t *I, int64_t *J, double *V) {
+                                  int kappa_kind, const double *kappa, double otherdim, int64_t *I, int64_t *J, double *V) {
   formctx f;
   if (form_setup(&f, et, nelem, conn, nnodes, sdim, xyz, 1, dofnums, nalldofs, npts, pc, w)) return -1;
   int nne = f.nne, mdim = f.mdim;
@@ -604,8 +604,8 @@ ORC_API int orc_bilform_diffusion(int et, int64_t nelem, const int64_t *conn, in
     for (int j = 0; j < npts; j++) {
       const double *N = f.Ns + (size_t)j * nne, *dN = f.dNs + (size_t)j * nne * mdim;
       locjac(loc, Jm, ecoords, N, dN, nne, sdim, mdim);
-      /* Jacobianvolume: IntegDomainModule.jl:567 (3-manifold), :504 (2-manifold x otherdimension == 1.0) */
-      double Jac = (mdim == 3) ? jacobian3(Jm) : jacobian2(Jm, sdim) * 1.0;
+      /* Jacobianvolume: IntegDomainModule.jl:567 (3-manifold), :504 (2-manifold x the constant otherdimension) */
+      double Jac = (mdim == 3) ? jacobian3(Jm) : jacobian2(Jm, sdim) * otherdim;
       if (kappa_kind == 1) {
         mulCAtB(RmTJ, mdim, mdim, (mdim == 3) ? IDENT3 : IDENT2, Jm, mdim); /* csmat = identity: FEMMBaseModule.jl:1496 */
         if (mdim == 3) gradN3(gradN, dN, RmTJ, nne); else gradN2(gradN, dN, RmTJ, nne);
@@ -700,7 +700,7 @@ ORC_API int orc_bilform_dot(int et, int64_t nelem, const int64_t *conn, int64_t 
  * (uvals nnodes x nsd col-major, nsd = sdim), rho constant.  Non-symmetric: the full element matrix is formed. */
 ORC_API int orc_bilform_convection(int et, int64_t nelem, const int64_t *conn, int64_t nnodes, int sdim, const double *xyz,
                                    const double *uvals, int nsd, const int64_t *dofnums, int64_t nalldofs, int npts, const double *pc,
-                                   const double *w, double rho, int64_t *I, int64_t *J, double *V) {
+                                   const double *w, double rho, double otherdim, int64_t *I, int64_t *J, double *V) {
   formctx f;
   if (form_setup(&f, et, nelem, conn, nnodes, sdim, xyz, 1, dofnums, nalldofs, npts, pc, w)) return -1;
   int nne = f.nne, mdim = f.mdim;
@@ -720,7 +720,7 @@ ORC_API int orc_bilform_convection(int et, int64_t nelem, const int64_t *conn, i
     for (int j = 0; j < npts; j++) {
       const double *N = f.Ns + (size_t)j * nne, *dN = f.dNs + (size_t)j * nne * mdim;
       locjac(loc, Jm, ecoords, N, dN, nne, sdim, mdim);
-      double Jac = (mdim == 3) ? jacobian3(Jm) : jacobian2(Jm, sdim) * 1.0;
+      double Jac = (mdim == 3) ? jacobian3(Jm) : jacobian2(Jm, sdim) * otherdim;
       if (mdim == 3) gradN3(gradN, dN, Jm, nne); else gradN2(gradN, dN, Jm, nne);
       for (int pp = 0; pp < nne; pp++)
         for (int r = 0; r < nne; r++) {
@@ -743,7 +743,7 @@ ORC_API int orc_bilform_convection(int et, int64_t nelem, const int64_t *conn, i
 /* bilform_div_grad: FEMMBaseModule.jl:1672-1713.  Vector field u with ndn = sdim dofs per node, constant viscosity mu. */
 ORC_API int orc_bilform_div_grad(int et, int64_t nelem, const int64_t *conn, int64_t nnodes, int sdim, const double *xyz, int ndn,
                                  const int64_t *dofnums, int64_t nalldofs, int npts, const double *pc, const double *w, double mu,
-                                 int64_t *I, int64_t *J, double *V) {
+                                 double otherdim, int64_t *I, int64_t *J, double *V) {
   formctx f;
   if (form_setup(&f, et, nelem, conn, nnodes, sdim, xyz, ndn, dofnums, nalldofs, npts, pc, w)) return -1;
   int nne = f.nne, mdim = f.mdim;
@@ -760,7 +760,7 @@ ORC_API int orc_bilform_div_grad(int et, int64_t nelem, const int64_t *conn, int
     for (int j = 0; j < npts; j++) {
       const double *N = f.Ns + (size_t)j * nne, *dN = f.dNs + (size_t)j * nne * mdim;
       locjac(loc, Jm, ecoords, N, dN, nne, sdim, mdim);
-      double Jac = (mdim == 3) ? jacobian3(Jm) : jacobian2(Jm, sdim) * 1.0;
+      double Jac = (mdim == 3) ? jacobian3(Jm) : jacobian2(Jm, sdim) * otherdim;
       if (mdim == 3) gradN3(gradN, dN, Jm, nne); else gradN2(gradN, dN, Jm, nne);
       double factor = mu * (Jac * w[j]);
       for (int a = 0; a < nne; a++)

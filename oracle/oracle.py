@@ -69,12 +69,12 @@ def lib():
         L.orc_complete_lt.restype = None
         L.orc_assemble.argtypes = [_i64p, _i64p, _f64p, _i64p, _f64p, _i64p, C.c_int, _i64p, C.c_int, C.c_int64, C.c_int64]
         common = [C.c_int, C.c_int64, _i64p, C.c_int64, C.c_int, _f64p]
-        L.orc_bilform_diffusion.argtypes = common + [_i64p, C.c_int64, C.c_int, _f64p, _f64p, C.c_int, _f64p, _i64p, _i64p, _f64p]
+        L.orc_bilform_diffusion.argtypes = common + [_i64p, C.c_int64, C.c_int, _f64p, _f64p, C.c_int, _f64p, C.c_double, _i64p, _i64p, _f64p]
         L.orc_bilform_lin_elastic.argtypes = common + [_i64p, C.c_int64, C.c_int, _f64p, _f64p, _f64p, _i64p, _i64p, _f64p]
         L.orc_bilform_dot.argtypes = common + [C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double,
                                                _i64p, _i64p, _f64p]
-        L.orc_bilform_convection.argtypes = common + [_f64p, C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, C.c_double, _i64p, _i64p, _f64p]
-        L.orc_bilform_div_grad.argtypes = common + [C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, C.c_double, _i64p, _i64p, _f64p]
+        L.orc_bilform_convection.argtypes = common + [_f64p, C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, C.c_double, C.c_double, _i64p, _i64p, _f64p]
+        L.orc_bilform_div_grad.argtypes = common + [C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, C.c_double, C.c_double, _i64p, _i64p, _f64p]
         L.orc_bilform_masslike.argtypes = common + [C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double,
                                                     _i64p, _i64p, _f64p]
         L.orc_linform_dot.argtypes = common + [C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double, _f64p]
@@ -139,7 +139,7 @@ def _prep(et, conn, xyz, dofnums, pc, w):
     return conn, nelem, nne, _F(xyz), nnodes, sdim, _I(dofnums), ndn, _F(pc), np.ascontiguousarray(w, dtype=np.float64).reshape(-1), npts
 
 
-def bilform_diffusion_coo(et, conn, xyz, dofnums, nalldofs, pc, w, kappa):
+def bilform_diffusion_coo(et, conn, xyz, dofnums, nalldofs, pc, w, kappa, otherdim=1.0):
     """Reference-order COO triplets (I, J, V) of bilform_diffusion; kappa scalar -> iso path, matrix -> general."""
     conn, nelem, nne, X, nnodes, sdim, dn, ndn, P, W, npts = _prep(et, conn, xyz, dofnums, pc, w)
     assert ndn == 1
@@ -147,7 +147,7 @@ def bilform_diffusion_coo(et, conn, xyz, dofnums, nalldofs, pc, w, kappa):
     I, J, V = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n)
     kind = 0 if np.ndim(kappa) == 0 else 1
     kap = _F(np.atleast_2d(np.asarray(kappa, dtype=np.float64)))
-    rc = lib().orc_bilform_diffusion(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, dn, nalldofs, npts, P, W, kind, kap, I, J, V)
+    rc = lib().orc_bilform_diffusion(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, dn, nalldofs, npts, P, W, kind, kap, float(otherdim), I, J, V)
     if rc:
         raise RuntimeError(_ERR.get(rc, "oracle error %d" % rc))
     return I, J, V
@@ -178,7 +178,7 @@ def bilform_dot_coo(et, conn, xyz, dofnums, nalldofs, pc, w, c, m=3, otherdim=1.
     return I, J, V
 
 
-def bilform_convection_coo(et, conn, xyz, uvals, dofnums, nalldofs, pc, w, rho=1.0):
+def bilform_convection_coo(et, conn, xyz, uvals, dofnums, nalldofs, pc, w, rho=1.0, otherdim=1.0):
     """Reference-order COO triplets of bilform_convection (FEMMBaseModule.jl:1583-1625); uvals = nodal velocities nnodes x sdim."""
     conn, nelem, nne, X, nnodes, sdim, dn, ndn, P, W, npts = _prep(et, conn, xyz, dofnums, pc, w)
     assert ndn == 1
@@ -186,18 +186,18 @@ def bilform_convection_coo(et, conn, xyz, uvals, dofnums, nalldofs, pc, w, rho=1
     n = nelem * nne * nne
     I, J, V = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n)
     rc = lib().orc_bilform_convection(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, _F(uv), uv.shape[1], dn, nalldofs, npts, P, W,
-                                      float(rho), I, J, V)
+                                      float(rho), float(otherdim), I, J, V)
     if rc:
         raise RuntimeError(_ERR.get(rc, "oracle error %d" % rc))
     return I, J, V
 
 
-def bilform_div_grad_coo(et, conn, xyz, dofnums, nalldofs, pc, w, mu):
+def bilform_div_grad_coo(et, conn, xyz, dofnums, nalldofs, pc, w, mu, otherdim=1.0):
     """Reference-order COO triplets of bilform_div_grad (FEMMBaseModule.jl:1672-1713)."""
     conn, nelem, nne, X, nnodes, sdim, dn, ndn, P, W, npts = _prep(et, conn, xyz, dofnums, pc, w)
     n = nelem * (ndn * nne) ** 2
     I, J, V = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n)
-    rc = lib().orc_bilform_div_grad(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, ndn, dn, nalldofs, npts, P, W, float(mu), I, J, V)
+    rc = lib().orc_bilform_div_grad(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, ndn, dn, nalldofs, npts, P, W, float(mu), float(otherdim), I, J, V)
     if rc:
         raise RuntimeError(_ERR.get(rc, "oracle error %d" % rc))
     return I, J, V

@@ -903,3 +903,42 @@ def test_masslike_parity(fe, orc, gpu_ctx, et, ndn, m):
         assert (measure > 0).all()
         if total is not None and et == "Q4":
             assert abs(measure.sum() - total) <= 1e-10 * total
+
+
+@pytest.mark.parametrize("et", ["Q4", "T3"])
+def test_planar_forms_with_thickness(fe, orc, gpu_ctx, et):
+    """A constant other-dimension (IntegDomain(fes, rule, t), IntegDomainModule.jl:73-82): Jacobianvolume of a 2-manifold is the
+    surface Jacobian times the thickness (:504-517).  Diffusion, convection and div_grad against the oracle, and the reference's
+    convection identity Psi' K Q = (b u_x + c u_y) W L t (test/test_forms.jl:196-231, there on Q8)."""
+    import scipy.sparse as sp
+    W, L, t = 6.1, 12.0, 2.32
+    fens, fes = (fe.Q4block(L, W, 3, 4) if et == "Q4" else fe.T3block(L, W, 3, 4))
+    rule = fe.GaussRule(2, 2) if et == "Q4" else fe.TriRule(3)
+    geom = fe.NodalField(fens.xyz)
+    femm = fe.FEMMBase(fe.IntegDomain(fes, rule, t))
+    q = make_field(fe, fens, 1)
+    n = q.nalldofs()
+    x = fens.xyz
+    # convection
+    uv = np.tile([3.1, -2.7], (fens.count(), 1))
+    I, J, V = orc.bilform_convection_coo(et, fes.conn, x, uv, q.dofnums, n, rule.param_coords, rule.weights, 1.0, otherdim=t)
+    ref = orc.sparse(I, J, V, n, n)
+    got = fe.bilform_convection(femm, fe.SysmatAssemblerSparseGPU(0.0), geom, fe.NodalField(uv), q, fe.DataCache(1.0), raw=True)
+    assert_parity(ref, got)
+    K = sp.csc_matrix((got[2], got[1] - 1, got[0] - 1), shape=(n, n))
+    a_, b_, c_ = (-0.1, +0.3, +0.4)
+    Q = np.zeros(n)
+    Q[q.dofnums[:, 0] - 1] = a_ + b_ * x[:, 0] + c_ * x[:, 1]
+    assert abs(np.ones(n) @ (K @ Q) - (b_ * 3.1 + c_ * -2.7) * (W * L * t)) / (W * L * t) <= 1.0e-5
+    # diffusion
+    kap = np.array([[1.5, 0.2], [0.2, 2.5]])
+    I, J, V = orc.bilform_diffusion_coo(et, fes.conn, x, q.dofnums, n, rule.param_coords, rule.weights, kap, otherdim=t)
+    got = fe.bilform_diffusion(femm, fe.SysmatAssemblerSparseGPU(0.0), geom, q, fe.DataCache(kap), raw=True)
+    assert_parity(orc.sparse(I, J, V, n, n), got)
+    I1, J1, V1 = orc.bilform_diffusion_coo(et, fes.conn, x, q.dofnums, n, rule.param_coords, rule.weights, kap)
+    assert np.abs(V - t * V1).max() <= 1e-13 * np.abs(V).max()
+    # div_grad
+    u = make_field(fe, fens, 2)
+    I, J, V = orc.bilform_div_grad_coo(et, fes.conn, x, u.dofnums, u.nalldofs(), rule.param_coords, rule.weights, 0.13, otherdim=t)
+    got = fe.bilform_div_grad(femm, fe.SysmatAssemblerSparseGPU(0.0), geom, u, fe.DataCache(0.13), raw=True)
+    assert_parity(orc.sparse(I, J, V, u.nalldofs(), u.nalldofs()), got)
