@@ -29,6 +29,7 @@ SIGNATURES = {
     "fegpu_geom_update": (C.c_int32, [VP, VP]),
     "fegpu_rule_set": (C.c_int32, [VP, C.c_int32, VP, VP, VP]),
     "fegpu_otherdimension_set": (C.c_int32, [VP, C.c_double]),
+    "fegpu_csys_set": (C.c_int32, [VP, VP]),
     "fegpu_partition_set": (C.c_int32, [VP, VP, C.c_int32]),
     "fegpu_dofmap_upload": (C.c_int32, [VP, VP, C.c_int32, VP, C.c_int64, C.c_int64, C.POINTER(VP)]),
     "fegpu_dofmap_destroy": (C.c_int32, [VP]),

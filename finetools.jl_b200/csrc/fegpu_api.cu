@@ -359,6 +359,21 @@ int32_t fegpu_rule_set(fegpu_mesh *m, int32_t npts, const double *Ns, const doub
   return FEGPU_OK;
 }
 
+int32_t fegpu_csys_set(fegpu_mesh *m, const double *csmat) {
+  if (!m) return FEGPU_ERR_ARG;
+  if (csmat && m->sdim != m->mdim) return fegpu_fail(m->ctx, FEGPU_ERR_ARG, "a material coordinate system matrix needs sdim == manifold dimension");
+  m->use_rm = csmat != nullptr;
+  const int n = m->sdim * m->mdim;
+  for (int i = 0; i < 9; i++) m->rm[i] = (csmat && i < n) ? csmat[i] : 0.0;
+  if (m->use_rm) {  // the identity takes the specialised kernels
+    bool ident = true;
+    for (int a = 0; a < m->sdim; a++)
+      for (int b = 0; b < m->mdim; b++) ident = ident && m->rm[a + m->sdim * b] == (a == b ? 1.0 : 0.0);
+    if (ident) m->use_rm = false;
+  }
+  return FEGPU_OK;
+}
+
 int32_t fegpu_otherdimension_set(fegpu_mesh *m, double otherdim) {
   if (!m) return FEGPU_ERR_ARG;
   m->otherdim = otherdim;
@@ -645,6 +660,8 @@ int32_t fegpu_bilform_diffusion(fegpu_mesh *mesh, fegpu_dofmap *dm, int32_t kapp
   for (int i = 0; i < nk; i++) fa.coef[i] = kappa[i];
   fa.m = 3;
   fa.otherdim = mesh->otherdim;
+  fa.use_rm = mesh->use_rm;
+  for (int i = 0; i < 9; i++) fa.rm[i] = mesh->rm[i];
   return run_bilform(mesh, dm, fa, as);
 }
 
@@ -658,6 +675,8 @@ int32_t fegpu_bilform_lin_elastic(fegpu_mesh *mesh, fegpu_dofmap *dm, const doub
   for (int i = 0; i < 36; i++) fa.coef[i] = C[i];
   fa.m = 3;
   fa.otherdim = 1.0;
+  fa.use_rm = mesh->use_rm;
+  for (int i = 0; i < 9; i++) fa.rm[i] = mesh->rm[i];
   return run_bilform(mesh, dm, fa, as);
 }
 

@@ -32,6 +32,8 @@ struct IntegParams {
   int m;
   double otherdim;
   const double *uvel;        // [SDIM][nnodes] convective velocity (FORM_CONVECTION)
+  double rm[9];              // constant material coordinate system matrix Rm, SDIM x MDIM column-major
+  int use_rm;                // 0 = identity
 };
 
 template <int TPE>
@@ -85,6 +87,17 @@ __device__ __forceinline__ void jac_inverse(const double *J, double *inv) {
 
 // Nonzero rows of column (node, comp) of the 3-D strain-displacement matrix (DeforModelRedModule.jl:463-468 with Rm = I):
 // comp x: rows xx(g1) xy(g2) xz(g3); comp y: yy(g2) xy(g1) yz(g3); comp z: zz(g3) xz(g1) yz(g2).  Rows ascending.
+// Column (node, comp) of B for a constant non-identity material coordinate system (DeforModelRedModule.jl:463-468): all six rows
+__device__ __forceinline__ void bcol_rm(int comp, const double *g, const double *rm, double b[6]) {
+  const double r1 = rm[comp], r2 = rm[comp + 3], r3 = rm[comp + 6];  // Rm[j, 1..3]
+  b[0] = g[0] * r1;
+  b[1] = g[1] * r2;
+  b[2] = g[2] * r3;
+  b[3] = g[1] * r1 + g[0] * r2;
+  b[4] = g[2] * r1 + g[0] * r3;
+  b[5] = g[2] * r2 + g[1] * r3;
+}
+
 __device__ __forceinline__ void bcol(int comp, const double *g, int rows[3], double vals[3]) {
   if (comp == 0) {
     rows[0] = 0; vals[0] = g[0]; rows[1] = 3; vals[1] = g[1]; rows[2] = 4; vals[2] = g[2];
@@ -210,7 +223,24 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
       } else {
         // gradN rows
         double inv[MDIM * MDIM];
-        if (SDIM == MDIM) jac_inverse<MDIM>(J, inv);
+        if (SDIM == MDIM) {
+          if (P.use_rm && (FORM == FORM_DIFF_GEN || FORM == FORM_ELASTIC)) {
+            // RmTJ = Rm' * J (mulCAtB! / At_mul_B!, FEMMBaseModule.jl:1496, 1802): gradients in the material directions
+            double R[MDIM * MDIM];
+#pragma unroll
+            for (int a = 0; a < MDIM; a++)
+#pragma unroll
+              for (int b = 0; b < MDIM; b++) {
+                double acc2 = 0.0;
+#pragma unroll
+                for (int k2 = 0; k2 < SDIM; k2++) acc2 += P.rm[k2 + SDIM * a] * J[k2 + SDIM * b];
+                R[a + MDIM * b] = acc2;
+              }
+            jac_inverse<MDIM>(R, inv);
+          } else {
+            jac_inverse<MDIM>(J, inv);
+          }
+        }
         if (MDIM == 2) Jac = Jac * P.otherdim;  // Jacobianvolume of a 2-manifold: surface Jacobian x other dimension (IntegDomainModule.jl:504-517)
         const double Jw = Jac * sw[j];
         group_sync<TPE>();  // previous point's G / AUX reads are done
@@ -247,15 +277,27 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
         } else if (FORM == FORM_ELASTIC) {
           // DB[:, c] = Jac_w * D * B[:, c]                                          MatrixUtilityModule.jl:198-206
           for (int c = t; c < EM; c += TPE) {
-            int rows[3];
-            double vals[3];
-            bcol(c % 3, sG + (c / 3) * 3, rows, vals);
+            if (P.use_rm) {
+              double b6[6];
+              bcol_rm(c % 3, sG + (c / 3) * 3, P.rm, b6);
 #pragma unroll
-            for (int mx = 0; mx < 6; mx++) {
-              double a = 0.0;
+              for (int mx = 0; mx < 6; mx++) {
+                double a = 0.0;
 #pragma unroll
-              for (int q = 0; q < 3; q++) a += P.coef[mx + 6 * rows[q]] * vals[q];
-              sA[mx + 6 * c] = Jw * a;
+                for (int px = 0; px < 6; px++) a += P.coef[mx + 6 * px] * b6[px];
+                sA[mx + 6 * c] = Jw * a;
+              }
+            } else {
+              int rows[3];
+              double vals[3];
+              bcol(c % 3, sG + (c / 3) * 3, rows, vals);
+#pragma unroll
+              for (int mx = 0; mx < 6; mx++) {
+                double a = 0.0;
+#pragma unroll
+                for (int q = 0; q < 3; q++) a += P.coef[mx + 6 * rows[q]] * vals[q];
+                sA[mx + 6 * c] = Jw * a;
+              }
             }
           }
           group_sync<TPE>();
@@ -288,6 +330,13 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
               for (int q = 0; q < NDN; q++) acc[k] += factor * sG[na * MDIM + q] * sG[nb * MDIM + q];
             }
             acc[k] += factor * sG[na * MDIM + tt] * sG[nb * MDIM + s];
+          } else if (P.use_rm) {  // FORM_ELASTIC with a material coordinate system: dense columns of B
+            double b6[6];
+            bcol_rm(r % 3, sG + (r / 3) * 3, P.rm, b6);
+            double a = 0.0;
+#pragma unroll
+            for (int px = 0; px < 6; px++) a += b6[px] * sA[px + 6 * c];
+            acc[k] += a;
           } else {  // FORM_ELASTIC: accum = sum_px B[px,mx]*DB[px,nx]
             int rows[3];
             double vals[3];
@@ -346,6 +395,8 @@ int32_t launch_generic(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
   P.compact = (fa.compact && fe_form_symmetric(FORM)) ? 1 : 0;
   for (int i = 0; i < 36; i++) P.coef[i] = fa.coef[i];
   P.m = fa.m; P.otherdim = fa.otherdim; P.uvel = fa.d_uvel;
+  for (int i = 0; i < 9; i++) P.rm[i] = fa.rm[i];
+  P.use_rm = fa.use_rm ? 1 : 0;
   if (mesh->nactive == 0) return FEGPU_OK;
   size_t smem = sizeof(double) * ((size_t)mesh->npts * NNE * (1 + MDIM) + mesh->npts + (size_t)GPB * (NNE * SDIM + NNE * MDIM + NAUX));
   auto kern = k_integrate<NNE, MDIM, SDIM, NDN, FORM, TPE>;
@@ -411,12 +462,13 @@ bool fe_integrate_supports_compact(const fegpu_mesh *mesh, const FormArgs &fa) {
 int32_t fe_integrate(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
   if (mesh->npts <= 0) return fegpu_fail(mesh->ctx, FEGPU_ERR_STATE, "no quadrature rule set (fegpu_rule_set)");
   if (fe_dot_scalar_applies(mesh, fa)) return fe_integrate_dot_scalar(mesh, fa, d_V);
-  if (mesh->etype == FEGPU_H8) {
+  const bool rotated = fa.use_rm && (fa.form == FORM_DIFF_GEN || fa.form == FORM_ELASTIC);  // only the generic kernel knows Rm
+  if (mesh->etype == FEGPU_H8 && !rotated) {
     bool handled = false;
     FE_TRY(fe_integrate_h8(mesh, fa, d_V, &handled));
     if (handled) return FEGPU_OK;
   }
-  if (fa.form == FORM_ELASTIC && mesh->sdim == 3 && mesh->mdim == 3) {
+  if (fa.form == FORM_ELASTIC && mesh->sdim == 3 && mesh->mdim == 3 && !rotated) {
     // register-tiled kernel (fegpu_elastic.cu); FEGPU_ELASTIC_TILED=0 keeps the entry-per-thread kernel for A/B measurements
     static const bool tiled_off = std::getenv("FEGPU_ELASTIC_TILED") && std::atoi(std::getenv("FEGPU_ELASTIC_TILED")) == 0;
     if (!tiled_off) {

@@ -37,6 +37,8 @@ struct fegpu_mesh {
   int64_t nelem = 0, nnodes = 0;
   int32_t *d_conn = nullptr;  // [nelem][nne] 0-based
   double *d_xyz = nullptr;    // [sdim][nnodes]
+  double rm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // constant material coordinate system matrix, sdim x mdim col-major (fegpu_csys_set)
+  bool use_rm = false;        // false = identity (the FEMMBase default, FEMMBaseModule.jl:82-84)
   double otherdim = 1.0;      // constant other-dimension of the IntegDomain (thickness of a 2-manifold, fegpu_otherdimension_set)
   double *d_uvel = nullptr;   // [sdim][nnodes] nodal field of bilform_convection (fegpu_bilform_convection uploads it)
   // quadrature tables (device copy): N [npts][nne], dN [npts][mdim][nne], w [npts]
@@ -155,6 +157,8 @@ struct FormArgs {
   double coef[36];  // kappa (mdim x mdim col-major) | C (6x6 col-major) | c (ndn x ndn col-major); coef[0] = scalar kappa
   int m;            // bilform_dot manifold dimension
   double otherdim;
+  double rm[9];     // constant CSys matrix (sdim x mdim col-major) for the general diffusion and the elasticity forms
+  bool use_rm;      // false = identity
   const double *d_uvel = nullptr;  // bilform_convection: nodal convective velocity on the device, [sdim][nnodes]
   bool compact;     // symmetric forms only: write the compact upper-block layout (fe_compact_size) instead of full matrices
 };

@@ -22,12 +22,21 @@ class DeforModelRed3D:
 
 
 class CSys:
-    """Material coordinate system; only the identity (the FEMMBase default, FEMMBaseModule.jl:82-84) is GPU-eligible."""
+    """Material coordinate system (src/CSysModule.jl): CSys(dim) = identity (the FEMMBase default, FEMMBaseModule.jl:82-84),
+    CSys(csmat) = a given constant matrix (:133-144).  Position-dependent systems (a compute callback) are not GPU-eligible."""
 
-    def __init__(self, sdim=3, mdim=None, isidentity=True):
+    def __init__(self, sdim=3, mdim=None, isidentity=True, csmat=None):
+        if isinstance(sdim, np.ndarray):  # CSys(csmat)
+            csmat, sdim = sdim, sdim.shape[0]
         self.isconstant = True
-        self.isidentity = bool(isidentity)
-        self.sdim, self.mdim = sdim, sdim if mdim is None else mdim
+        if csmat is not None:
+            self.csmat = np.array(csmat, dtype=np.float64)
+            self.sdim, self.mdim = self.csmat.shape
+            self.isidentity = False
+        else:
+            self.isidentity = bool(isidentity)
+            self.sdim, self.mdim = sdim, sdim if mdim is None else mdim
+            self.csmat = np.eye(self.sdim, self.mdim) if self.isidentity else None
 
 
 class FEMMBase:
@@ -150,8 +159,8 @@ def _eligible(self, assembler, geom, u, cf):
         raise TypeError("this package provides the GPU assembler path only (SysmatAssemblerSparseGPU); there is no CPU loop")
     if not isinstance(cf, DataCache):
         raise TypeError("coefficient must be a constant DataCache")
-    if not self.mcsys.isidentity:
-        raise FEGPUError(-2, "only the identity material coordinate system is GPU-eligible")
+    if not self.mcsys.isconstant or self.mcsys.csmat is None:
+        raise FEGPUError(-2, "only constant material coordinate systems (CSys(dim) or CSys(csmat)) are GPU-eligible")
     if self.integdomain.axisymmetric:
         raise FEGPUError(-2, "axisymmetric integration domains are not GPU-eligible")
     if geom.values.dtype != np.float64 or u.dofnums.dtype != np.int64:
@@ -163,6 +172,13 @@ def _prepare(self, assembler, geom, u, node_owner=None, my_rank=0):
     assembler = _inner(assembler)
     dmesh = _device_mesh(assembler, fes, geom)
     dmesh.set_rule(self.integdomain)
+    if self.mcsys.isidentity:
+        check(_lib.lib().fegpu_csys_set(dmesh.handle, None), assembler.ctx.handle)
+    else:
+        if self.mcsys.csmat.shape != (fes.mdim, fes.mdim) or geom.values.shape[1] != fes.mdim:
+            raise FEGPUError(-2, "the material coordinate system matrix must be sdim x mdim with sdim == mdim")
+        rm = np.asfortranarray(self.mcsys.csmat)
+        check(_lib.lib().fegpu_csys_set(dmesh.handle, fptr(rm)), assembler.ctx.handle)
     dmesh.set_partition(node_owner, my_rank)
     dof = dmesh.dofmap(u)
     return fes, dmesh, dof

@@ -17,6 +17,7 @@ import FinEtools.FEMMBaseModule: bilform_diffusion, bilform_lin_elastic, bilform
     bilform_masslike, linform_dot, FEMMBase, finite_elements
 using FinEtools.IntegDomainModule: integrationdata, otherdimensionunity
 using FinEtools.DeforModelRedModule: DeforModelRed3D
+using FinEtools.CSysModule: csmat
 
 export SysmatAssemblerSparseGPU, SysmatAssemblerSparseSymmGPU, SysmatAssemblerSparseDiagGPU, SysmatAssemblerSparseHRZLumpingSymmGPU,
     SysvecAssemblerGPU, gpu_matrix_blocked
@@ -152,7 +153,7 @@ end
 
 # ---- device twins of (fes, geom, u) -------------------------------------------------------------------------------------
 function _eligible(self::FEMMBase, geom, u, cf)
-    self.mcsys.isidentity || error("only the identity material coordinate system is GPU-eligible")
+    self.mcsys.isconstant || error("only constant material coordinate systems (CSys(dim), CSys(csmat)) are GPU-eligible")
     self.integdomain.axisymmetric && error("axisymmetric integration domains are not GPU-eligible")
     # other dimension: unity, or the constant closure of IntegDomain(fes, rule, t) (IntegDomainModule.jl:73-82); _otherdim evaluates it
     # DataCache: only the constant constructor (DataCacheModule.jl:77-89) may cross the boundary
@@ -190,6 +191,12 @@ function _device(self::FEMMBase, a, geom, u)   # a: SysmatAssemblerSparseGPU or 
     end
     mh, dms = entry
     _check(ccall((:fegpu_otherdimension_set, LIB), Int32, (Ptr{Cvoid}, Float64), mh, _otherdim(self)), a.ctx)
+    if self.mcsys.isidentity
+        _check(ccall((:fegpu_csys_set, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), mh, C_NULL), a.ctx)
+    else
+        rm = Matrix{Float64}(csmat(self.mcsys))       # constant: the buffer already holds the matrix (CSysModule.jl:133-144)
+        GC.@preserve rm _check(ccall((:fegpu_csys_set, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), mh, rm), a.ctx)
+    end
     dh = get(dms, u.dofnums, C_NULL)
     if dh == C_NULL
         d = Ref{Ptr{Cvoid}}(C_NULL)

@@ -76,6 +76,10 @@ int32_t fegpu_geom_update(fegpu_mesh *mesh, const double *xyz);
 /* quadrature tables exactly as the caller's integrationdata() produced them (IntegDomainModule.jl:631-648):
  * Ns [npts][nne], gradNpar [npts][mdim][nne] (i.e. each point's nne x mdim matrix, column-major), w [npts] */
 int32_t fegpu_rule_set(fegpu_mesh *mesh, int32_t npts, const double *Ns, const double *gradNpar, const double *w);
+/* constant material coordinate system of the FEMM, CSys(csmat) (CSysModule.jl:133-144): csmat sdim x mdim column-major, NULL =
+ * identity (CSys(dim), the FEMMBase default FEMMBaseModule.jl:82-84).  Used by the general bilform_diffusion (RmTJ = Rm' J,
+ * :1495-1497) and by bilform_lin_elastic (:1801-1803, blmat! with Rm).  Position-dependent systems are not eligible. */
+int32_t fegpu_csys_set(fegpu_mesh *mesh, const double *csmat);
 /* constant other-dimension of the IntegDomain (IntegDomainModule.jl:73-82, 150-152): the thickness that multiplies the
  * surface Jacobian of a 2-manifold in Jacobianvolume (:504-517); used by the gradient forms (diffusion, convection,
  * div_grad) on planar meshes.  Default 1.0 (otherdimensionunity).  bilform_dot / masslike / linform_dot take it per call. */

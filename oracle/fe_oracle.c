@@ -588,7 +588,8 @@ static const double IDENT2[4] = {1, 0, 0, 1};
  * Emits nelem*nne^2 triplets into I,J,V (reference emission order).  If elmats != NULL also stores element matrices. */
 ORC_API int orc_bilform_diffusion(int et, int64_t nelem, const int64_t *conn, int64_t nnodes, int sdim, const double *xyz,
                                   const int64_t *dofnums, int64_t nalldofs, int npts, const double *pc, const double *w,
-                                  int kappa_kind, const double *kappa, double otherdim, int64_t *I, int64_t *J, double *V) {
+                                  int kappa_kind, const double *kappa, double otherdim, const double *Rm, int64_t *I, int64_t *J,
+                                  double *V) {
   formctx f;
   if (form_setup(&f, et, nelem, conn, nnodes, sdim, xyz, 1, dofnums, nalldofs, npts, pc, w)) return -1;
   int nne = f.nne, mdim = f.mdim;
@@ -607,7 +608,8 @@ ORC_API int orc_bilform_diffusion(int et, int64_t nelem, const int64_t *conn, in
       /* Jacobianvolume: IntegDomainModule.jl:567 (3-manifold), :504 (2-manifold x the constant otherdimension) */
       double Jac = (mdim == 3) ? jacobian3(Jm) : jacobian2(Jm, sdim) * otherdim;
       if (kappa_kind == 1) {
-        mulCAtB(RmTJ, mdim, mdim, (mdim == 3) ? IDENT3 : IDENT2, Jm, mdim); /* csmat = identity: FEMMBaseModule.jl:1496 */
+        /* mulCAtB!(RmTJ, csmat(self.mcsys), J) FEMMBaseModule.jl:1496; csmat: the constant mcsys matrix (NULL = identity) */
+        mulCAtB(RmTJ, mdim, mdim, Rm ? Rm : ((mdim == 3) ? IDENT3 : IDENT2), Jm, mdim);
         if (mdim == 3) gradN3(gradN, dN, RmTJ, nne); else gradN2(gradN, dN, RmTJ, nne);
         orc_add_gkgt_ut_only(elmat, gradN, (Jac * w[j]), kappa, kg, nne, mdim);
       } else {
@@ -626,7 +628,7 @@ ORC_API int orc_bilform_diffusion(int et, int64_t nelem, const int64_t *conn, in
 /* bilform_lin_elastic with DeforModelRed3D: FEMMBaseModule.jl:1774-1813.  C is 6x6 col-major. */
 ORC_API int orc_bilform_lin_elastic(int et, int64_t nelem, const int64_t *conn, int64_t nnodes, int sdim, const double *xyz,
                                     const int64_t *dofnums, int64_t nalldofs, int npts, const double *pc, const double *w,
-                                    const double *C, int64_t *I, int64_t *J, double *V) {
+                                    const double *C, const double *Rm, int64_t *I, int64_t *J, double *V) {
   formctx f;
   if (form_setup(&f, et, nelem, conn, nnodes, sdim, xyz, 3, dofnums, nalldofs, npts, pc, w)) return -1;
   int nne = f.nne, mdim = f.mdim;
@@ -645,9 +647,9 @@ ORC_API int orc_bilform_lin_elastic(int et, int64_t nelem, const int64_t *conn, 
       const double *N = f.Ns + (size_t)j * nne, *dN = f.dNs + (size_t)j * nne * mdim;
       locjac(loc, Jm, ecoords, N, dN, nne, sdim, mdim);
       double Jac = jacobian3(Jm);
-      mulCAtB(RmTJ, 3, 3, IDENT3, Jm, 3); /* At_mul_B!(RmTJ, csmat, J) :1802 */
+      mulCAtB(RmTJ, 3, 3, Rm ? Rm : IDENT3, Jm, 3); /* At_mul_B!(RmTJ, csmat, J) :1802 */
       gradN3(gradN, dN, RmTJ, nne);
-      blmat3d(B, gradN, IDENT3, nne);
+      blmat3d(B, gradN, Rm ? Rm : IDENT3, nne);
       orc_add_btdb_ut_only(elmat, B, Jac * w[j], C, DB, 6, K);
     }
     orc_complete_lt(elmat, K);

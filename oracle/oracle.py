@@ -69,8 +69,8 @@ def lib():
         L.orc_complete_lt.restype = None
         L.orc_assemble.argtypes = [_i64p, _i64p, _f64p, _i64p, _f64p, _i64p, C.c_int, _i64p, C.c_int, C.c_int64, C.c_int64]
         common = [C.c_int, C.c_int64, _i64p, C.c_int64, C.c_int, _f64p]
-        L.orc_bilform_diffusion.argtypes = common + [_i64p, C.c_int64, C.c_int, _f64p, _f64p, C.c_int, _f64p, C.c_double, _i64p, _i64p, _f64p]
-        L.orc_bilform_lin_elastic.argtypes = common + [_i64p, C.c_int64, C.c_int, _f64p, _f64p, _f64p, _i64p, _i64p, _f64p]
+        L.orc_bilform_diffusion.argtypes = common + [_i64p, C.c_int64, C.c_int, _f64p, _f64p, C.c_int, _f64p, C.c_double, C.c_void_p, _i64p, _i64p, _f64p]
+        L.orc_bilform_lin_elastic.argtypes = common + [_i64p, C.c_int64, C.c_int, _f64p, _f64p, _f64p, C.c_void_p, _i64p, _i64p, _f64p]
         L.orc_bilform_dot.argtypes = common + [C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double,
                                                _i64p, _i64p, _f64p]
         L.orc_bilform_convection.argtypes = common + [_f64p, C.c_int, _i64p, C.c_int64, C.c_int, _f64p, _f64p, C.c_double, C.c_double, _i64p, _i64p, _f64p]
@@ -139,7 +139,15 @@ def _prep(et, conn, xyz, dofnums, pc, w):
     return conn, nelem, nne, _F(xyz), nnodes, sdim, _I(dofnums), ndn, _F(pc), np.ascontiguousarray(w, dtype=np.float64).reshape(-1), npts
 
 
-def bilform_diffusion_coo(et, conn, xyz, dofnums, nalldofs, pc, w, kappa, otherdim=1.0):
+def _rm(Rm):
+    """constant material coordinate system matrix (CSys(csmat), CSysModule.jl:133-144) as a column-major buffer, or NULL = identity"""
+    if Rm is None:
+        return None, None
+    buf = _F(np.asarray(Rm, dtype=np.float64))
+    return buf, buf.ctypes.data_as(C.c_void_p)
+
+
+def bilform_diffusion_coo(et, conn, xyz, dofnums, nalldofs, pc, w, kappa, otherdim=1.0, Rm=None):
     """Reference-order COO triplets (I, J, V) of bilform_diffusion; kappa scalar -> iso path, matrix -> general."""
     conn, nelem, nne, X, nnodes, sdim, dn, ndn, P, W, npts = _prep(et, conn, xyz, dofnums, pc, w)
     assert ndn == 1
@@ -147,13 +155,14 @@ def bilform_diffusion_coo(et, conn, xyz, dofnums, nalldofs, pc, w, kappa, otherd
     I, J, V = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n)
     kind = 0 if np.ndim(kappa) == 0 else 1
     kap = _F(np.atleast_2d(np.asarray(kappa, dtype=np.float64)))
-    rc = lib().orc_bilform_diffusion(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, dn, nalldofs, npts, P, W, kind, kap, float(otherdim), I, J, V)
+    rmbuf, rmp = _rm(Rm)
+    rc = lib().orc_bilform_diffusion(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, dn, nalldofs, npts, P, W, kind, kap, float(otherdim), rmp, I, J, V)
     if rc:
         raise RuntimeError(_ERR.get(rc, "oracle error %d" % rc))
     return I, J, V
 
 
-def bilform_lin_elastic_coo(et, conn, xyz, dofnums, nalldofs, pc, w, Cmat, out=None):
+def bilform_lin_elastic_coo(et, conn, xyz, dofnums, nalldofs, pc, w, Cmat, out=None, Rm=None):
     """out = preallocated (I, J, V) contiguous slices for these elements (lets several threads fill one COO buffer;
     ctypes drops the GIL during the call)."""
     conn, nelem, nne, X, nnodes, sdim, dn, ndn, P, W, npts = _prep(et, conn, xyz, dofnums, pc, w)
@@ -161,7 +170,8 @@ def bilform_lin_elastic_coo(et, conn, xyz, dofnums, nalldofs, pc, w, Cmat, out=N
     n = nelem * (3 * nne) ** 2
     I, J, V = out if out is not None else (np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n))
     assert I.size == n
-    rc = lib().orc_bilform_lin_elastic(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, dn, nalldofs, npts, P, W, _F(Cmat), I, J, V)
+    rmbuf, rmp = _rm(Rm)
+    rc = lib().orc_bilform_lin_elastic(ET[et], nelem, conn.reshape(-1), nnodes, sdim, X, dn, nalldofs, npts, P, W, _F(Cmat), rmp, I, J, V)
     if rc:
         raise RuntimeError(_ERR.get(rc, "oracle error %d" % rc))
     return I, J, V

@@ -942,3 +942,49 @@ def test_planar_forms_with_thickness(fe, orc, gpu_ctx, et):
     I, J, V = orc.bilform_div_grad_coo(et, fes.conn, x, u.dofnums, u.nalldofs(), rule.param_coords, rule.weights, 0.13, otherdim=t)
     got = fe.bilform_div_grad(femm, fe.SysmatAssemblerSparseGPU(0.0), geom, u, fe.DataCache(0.13), raw=True)
     assert_parity(orc.sparse(I, J, V, u.nalldofs(), u.nalldofs()), got)
+
+
+def _rotation():
+    a, b = 0.7, -0.4
+    Rz = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    Rx = np.array([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]])
+    return Rz @ Rx
+
+
+@pytest.mark.parametrize("et", ["H8", "T10", "H20", "T4"])
+def test_constant_material_csys(fe, orc, gpu_ctx, et):
+    """FEMMBase(integdomain, CSys(csmat)) with a constant rotation (CSysModule.jl:133-144): orthotropic elasticity and anisotropic
+    diffusion in rotated material axes against the oracle; an isotropic material must not see the rotation; diffusion with
+    (Rm, kappa) equals diffusion with (I, Rm kappa Rm')."""
+    fens, fes = _mesh(fe, et, 2)
+    _distort(fens)
+    rule = _rule(fe, et)
+    Rm = _rotation()
+    geom = fe.NodalField(fens.xyz)
+    u = make_field(fe, fens, 3)
+    n = u.nalldofs()
+    Corth = isotropic_C() + np.diag([3.0, 0.5, 1.0, 0.2, 0.7, 0.1])
+    Corth[0, 1] = Corth[1, 0] = 0.9
+    femm_r = fe.FEMMBase(fe.IntegDomain(fes, rule), fe.CSys(Rm))
+    femm_i = fe.FEMMBase(fe.IntegDomain(fes, rule))
+    I, J, V = orc.bilform_lin_elastic_coo(et, fes.conn, fens.xyz, u.dofnums, n, rule.param_coords, rule.weights, Corth, Rm=Rm)
+    ref = orc.sparse(I, J, V, n, n)
+    got = fe.bilform_lin_elastic(femm_r, fe.SysmatAssemblerSparseGPU(0.0), geom, u, fe.DeforModelRed3D, fe.DataCache(Corth), raw=True)
+    assert_parity(ref, got)
+    got_id = fe.bilform_lin_elastic(femm_i, fe.SysmatAssemblerSparseGPU(0.0), geom, u, fe.DeforModelRed3D, fe.DataCache(Corth), raw=True)
+    assert np.abs(got[2] - got_id[2]).max() > 1e-3 * np.abs(got[2]).max()  # the rotation matters for an orthotropic material
+    iso_r = fe.bilform_lin_elastic(femm_r, fe.SysmatAssemblerSparseGPU(0.0), geom, u, fe.DeforModelRed3D, fe.DataCache(isotropic_C()), raw=True)
+    iso_i = fe.bilform_lin_elastic(femm_i, fe.SysmatAssemblerSparseGPU(0.0), geom, u, fe.DeforModelRed3D, fe.DataCache(isotropic_C()), raw=True)
+    np.testing.assert_array_equal(iso_r[1], iso_i[1])
+    assert np.abs(iso_r[2] - iso_i[2]).max() <= 1e-12 * np.abs(iso_i[2]).max()
+    q = make_field(fe, fens, 1)
+    nq = q.nalldofs()
+    I, J, V = orc.bilform_diffusion_coo(et, fes.conn, fens.xyz, q.dofnums, nq, rule.param_coords, rule.weights, KAPPA3, Rm=Rm)
+    got = fe.bilform_diffusion(femm_r, fe.SysmatAssemblerSparseGPU(0.0), geom, q, fe.DataCache(KAPPA3), raw=True)
+    assert_parity(orc.sparse(I, J, V, nq, nq), got)
+    rot = fe.bilform_diffusion(femm_i, fe.SysmatAssemblerSparseGPU(0.0), geom, q, fe.DataCache(Rm @ KAPPA3 @ Rm.T), raw=True)
+    assert np.abs(got[2] - rot[2]).max() <= 1e-12 * np.abs(rot[2]).max()
+    # the scalar (iso) diffusion path never looks at the coordinate system (FEMMBaseModule.jl:1508-1535)
+    s_r = fe.bilform_diffusion(femm_r, fe.SysmatAssemblerSparseGPU(0.0), geom, q, fe.DataCache(1.7), raw=True)
+    s_i = fe.bilform_diffusion(femm_i, fe.SysmatAssemblerSparseGPU(0.0), geom, q, fe.DataCache(1.7), raw=True)
+    np.testing.assert_array_equal(s_r[2], s_i[2])
