@@ -92,6 +92,28 @@ __global__ void k_expand_compact(const double *__restrict__ Vc, double *__restri
   Vf[i] = Vc[e * CS + off];
 }
 
+// smallest and largest node id used by the active elements: win[0] = max(~node) (so that a zero-initialised slot means "no node"),
+// win[1] = max(node + 1).  The symbolic phase runs its per-node passes over [lo, hi) only.
+__global__ void k_active_window(const int32_t *__restrict__ conn, int64_t nelem, int nne, const int32_t *__restrict__ flag, int *__restrict__ win) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int lo = INT32_MAX, hi = 0;
+  if (e < nelem && flag[e]) {
+    for (int a = 0; a < nne; a++) {
+      const int n = conn[e * nne + a];
+      lo = min(lo, n);
+      hi = max(hi, n + 1);
+    }
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+  }
+  if ((threadIdx.x & 31) == 0 && hi > 0) {
+    atomicMax(&win[0], INT32_MAX - lo);
+    atomicMax(&win[1], hi);
+  }
+}
+
 __global__ void k_compact(const int32_t *__restrict__ flag, const int64_t *__restrict__ pos, int64_t nelem, int32_t *__restrict__ list) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < nelem && flag[e]) list[pos[e]] = (int32_t)e;
@@ -276,6 +298,8 @@ int32_t fegpu_mesh_upload(fegpu_ctx *ctx, int32_t etype, int64_t nelem, const in
   fegpu_mesh *m = new fegpu_mesh();
   m->ctx = ctx; m->etype = etype; m->nne = nne; m->mdim = mdim_of(etype); m->sdim = sdim; m->nelem = nelem; m->nnodes = nnodes;
   m->nactive = nelem;
+  m->win_lo = 0;
+  m->win_hi = nnodes;
   cudaStream_t st = ctx->stream;
   int64_t *d_c64 = nullptr;
   int *d_err = nullptr;
@@ -392,10 +416,13 @@ int32_t fegpu_partition_set(fegpu_mesh *m, const int32_t *node_owner, int32_t my
   m->d_rowowned = nullptr;
   m->partitioned = false;
   m->nactive = m->nelem;
+  m->win_lo = 0;
+  m->win_hi = m->nnodes;
   if (!node_owner) return FEGPU_OK;
   int32_t *d_owner = nullptr, *d_flag = nullptr;
   int64_t *d_pos = nullptr;
-  auto cleanup = [&]() { cudaFree(d_owner); cudaFree(d_flag); cudaFree(d_pos); };
+  int *d_win = nullptr;
+  auto cleanup = [&]() { cudaFree(d_owner); cudaFree(d_flag); cudaFree(d_pos); cudaFree(d_win); };
   cudaError_t e;
 #define PT(expr) if ((e = (expr)) != cudaSuccess) { cleanup(); return fegpu_fail(ctx, FEGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e)); }
   PT(cudaMalloc((void **)&d_owner, sizeof(int32_t) * std::max<int64_t>(m->nnodes, 1)));
@@ -414,11 +441,26 @@ int32_t fegpu_partition_set(fegpu_mesh *m, const int32_t *node_owner, int32_t my
     k_compact<<<grid_for(m->nelem, 256), 256, 0, st>>>(d_flag, d_pos, m->nelem, m->d_elem_list);
     ctx->launches++;
   }
+  // node window of the active elements (a z-slab of a block mesh owns a contiguous node range)
+  int h_win[2] = {0, 0};
+  PT(cudaMalloc((void **)&d_win, sizeof(int) * 2));
+  PT(cudaMemsetAsync(d_win, 0, sizeof(int) * 2, st));
+  if (m->nelem) {
+    k_active_window<<<grid_for(m->nelem, 256), 256, 0, st>>>(m->d_conn, m->nelem, m->nne, d_flag, d_win);
+    ctx->launches++;
+  }
+  PT(cudaMemcpyAsync(h_win, d_win, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
   PT(cudaStreamSynchronize(st));
 #undef PT
   cleanup();
   m->nactive = nact;
   m->partitioned = true;
+  if (h_win[1] > 0) {
+    m->win_lo = (int64_t)(INT32_MAX - h_win[0]);
+    m->win_hi = (int64_t)h_win[1];
+  } else {
+    m->win_lo = m->win_hi = 0;  // no active element
+  }
   return FEGPU_OK;
 }
 

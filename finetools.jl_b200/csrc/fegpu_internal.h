@@ -51,6 +51,7 @@ struct fegpu_mesh {
   int64_t nactive = 0;              // == nelem when not partitioned
   int32_t *d_elem_list = nullptr;   // active element ids ascending (nullptr = identity)
   uint8_t *d_rowowned = nullptr;    // per node, nullptr = all owned
+  int64_t win_lo = 0, win_hi = 0;   // node window [lo, hi) that contains every node of an active element ([0, nnodes) when not partitioned)
   uint64_t topo_version = 1;        // bumped when the active set / ownership changes
   bool degenerate = false;          // some element lists a node twice -> generic sort path
   double bbox_lo[3] = {0, 0, 0}, bbox_hi[3] = {0, 0, 0};  // of the coordinates at upload (node visiting order of the gather)
@@ -146,6 +147,7 @@ int32_t fe_exclusive_scan_i64(fegpu_ctx *ctx, const int64_t *d_in, int64_t *d_ou
 int32_t fe_exclusive_scan_i32_to_i64(fegpu_ctx *ctx, const int32_t *d_in, int64_t *d_out, int64_t n, int64_t base, bool write_total,
                                      int64_t *total_host);
 int32_t fe_max_i32(fegpu_ctx *ctx, const int32_t *d_in, int64_t n, int32_t *max_host);
+int32_t fe_max_i32_dev(fegpu_ctx *ctx, const int32_t *d_in, int64_t n, int32_t *d_out);
 
 // ---- integration (fegpu_integrate.cu) ------------------------------------------------------------------
 enum { FORM_DIFF_ISO = 0, FORM_DIFF_GEN = 1, FORM_ELASTIC = 2, FORM_DOT = 3, FORM_CONVECTION = 4, FORM_DIV_GRAD = 5,

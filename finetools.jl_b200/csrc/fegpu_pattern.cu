@@ -69,13 +69,27 @@ struct SymParams {
 };
 __device__ __forceinline__ int64_t active_node(const SymParams &S, int64_t idx) { return S.anodes ? (int64_t)S.anodes[idx] : idx; }
 
-__global__ void k_flag_active(const int32_t *__restrict__ deg, int64_t nnodes, int32_t *__restrict__ flag) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < nnodes) flag[n] = deg[n] > 0 ? 1 : 0;
+// The per-node passes of the symbolic phase run over the mesh's node window [lo, lo + nw) (fegpu_mesh::win_lo/hi: every node
+// of an active element lies inside; the whole mesh when it is not partitioned), so that a rank's fixed costs follow its own
+// share of the mesh.  flag / pos are window-relative, the list holds global node ids.
+__global__ void k_flag_active(const int32_t *__restrict__ deg, int64_t lo, int64_t nw, int32_t *__restrict__ flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nw) flag[i] = deg[lo + i] > 0 ? 1 : 0;
 }
-__global__ void k_compact_active(const int32_t *__restrict__ flag, const int64_t *__restrict__ pos, int64_t nnodes, int32_t *__restrict__ list) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < nnodes && flag[n]) list[pos[n]] = (int32_t)n;
+__global__ void k_compact_active(const int32_t *__restrict__ flag, const int64_t *__restrict__ pos, int64_t lo, int64_t nw,
+                                 int32_t *__restrict__ list) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nw && flag[i]) list[pos[i]] = (int32_t)(lo + i);
+}
+// Entries outside [lo, hi] of a windowed prefix array (adjptr, nbrptr, colptr): `before` ahead of the window, the window's
+// total (a[hi]) behind it, so every consumer still sees a complete, non-decreasing array.  Two arrays per launch.
+__global__ void k_fill_outside(int64_t *__restrict__ a0, int64_t *__restrict__ a1, int64_t len, int64_t lo, int64_t hi, int64_t before) {
+  const int64_t nout = len - (hi - lo + 1);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nout) return;
+  const int64_t idx = (i < lo) ? i : i + (hi - lo + 1);
+  if (a0) a0[idx] = (i < lo) ? before : a0[hi];
+  if (a1) a1[idx] = (i < lo) ? before : a1[hi];
 }
 
 __global__ void k_count_adj(SymParams S, int32_t *deg, int *degenerate) {
@@ -668,25 +682,43 @@ __global__ void k_classify_nodes(SymParams S, const int32_t *__restrict__ deg, i
 
 // is the dof map node-major ascending (dofs of a node ascending by component, below every dof of the next node)?  Then the
 // rows of every column are ascending in (neighbour, component) order and no node needs an order test or a rank table.
-__global__ void k_dof_monotone(const int32_t *__restrict__ dof, int64_t nnodes, int ndn, int *violated) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nnodes) return;
-  int prev = dof[n];
+// Over the node window only (every row and column node of the pattern is in it).  Also the dof range of the window's nodes,
+// the part of colptr that needs a scan: range[0] = max(INT32_MAX - dof), range[1] = max(dof + 1) (zero-initialised slots).
+__global__ void k_dof_monotone(const int32_t *__restrict__ dof, int64_t nnodes, int ndn, int64_t lo, int64_t nw, int *violated,
+                               int *__restrict__ range) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int dmin = INT32_MAX, dmax = -1;
   bool bad = false;
-  for (int p = 1; p < ndn; p++) {
-    const int d = dof[(int64_t)p * nnodes + n];
-    bad = bad || d <= prev;
-    prev = d;
+  if (i < nw) {
+    const int64_t n = lo + i;
+    int prev = dof[n];
+    dmin = prev;
+    dmax = prev;
+    for (int p = 1; p < ndn; p++) {
+      const int d = dof[(int64_t)p * nnodes + n];
+      bad = bad || d <= prev;
+      prev = d;
+      dmin = min(dmin, d);
+      dmax = max(dmax, d);
+    }
+    if (i + 1 < nw && dof[n + 1] <= prev) bad = true;
   }
-  if (n + 1 < nnodes && dof[n + 1] <= prev) bad = true;
+  for (int d = 16; d > 0; d >>= 1) {
+    dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, d));
+    dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, d));
+  }
+  if ((threadIdx.x & 31) == 0 && dmax >= 0) {
+    atomicMax(&range[0], INT32_MAX - dmin);
+    atomicMax(&range[1], dmax + 1);
+  }
   if (bad) *violated = 1;
 }
 
-__global__ void k_col_counts(SymParams S, const int32_t *nnbr, int64_t *colcount) {
+__global__ void k_col_counts(SymParams S, const int32_t *nnbr, int64_t lo, int64_t nw, int64_t *colcount) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S.nnodes * S.ndn) return;
-  int64_t n = i % S.nnodes;
-  int q = (int)(i / S.nnodes);
+  if (i >= nw * S.ndn) return;
+  int64_t n = lo + i % nw;
+  int q = (int)(i / nw);
   if (nnbr[n] > 0) colcount[S.dof[(int64_t)q * S.nnodes + n]] = (int64_t)nnbr[n] * S.ndn;
 }
 
@@ -1037,7 +1069,10 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   unsigned long long *d_clscnt = nullptr;
   int64_t *d_apos = nullptr;
   uint8_t *d_sorted = nullptr;
-  int *d_flags = nullptr;  // [0] degenerate, [1] some node needs a dof sort, [2] the dof map is not node-major ascending
+  // [0] degenerate, [1] some node needs a dof sort, [2] the dof map is not node-major ascending, [3] INT32_MAX - smallest dof and
+  // [4] 1 + largest dof of the window's nodes, [5] largest node degree, [6] largest neighbour count
+  int *d_flags = nullptr;
+  constexpr int NFLAGS = 8;
   auto cleanup = [&]() {
     void *ptrs[] = {d_deg, d_cursor, d_U, d_sorted, d_flags, d_aflag, d_anodes, d_apos, d_cls, d_clscnt};
     for (void *q : ptrs)
@@ -1052,14 +1087,18 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   };
 #define PT(expr) do { int32_t _s = (expr); if (_s != FEGPU_OK) { cleanup(); return _s; } } while (0)
 #define PC(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fegpu_fail(ctx, FEGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+  // node window of the active elements: every per-node pass below runs over [lo, hi) only
+  const int64_t lo = mesh->win_lo, hi = mesh->win_hi, nw = hi - lo;
   PT(dalloc(ctx, &d_deg, nn));
   PT(dalloc(ctx, &d_cursor, nn));
-  PT(dalloc(ctx, &d_flags, 3));
-  PC(cudaMemsetAsync(d_deg, 0, sizeof(int32_t) * nn, st));
-  PC(cudaMemsetAsync(d_cursor, 0, sizeof(int32_t) * nn, st));
-  PC(cudaMemsetAsync(d_flags, 0, sizeof(int) * 3, st));
-  if (nn > 0) {
-    k_dof_monotone<<<grid_for(nn, 256), 256, 0, st>>>(dm->d_dof, nn, ndn, d_flags + 2);
+  PT(dalloc(ctx, &d_flags, NFLAGS));
+  if (nw > 0) {
+    PC(cudaMemsetAsync(d_deg + lo, 0, sizeof(int32_t) * nw, st));
+    PC(cudaMemsetAsync(d_cursor + lo, 0, sizeof(int32_t) * nw, st));
+  }
+  PC(cudaMemsetAsync(d_flags, 0, sizeof(int) * NFLAGS, st));
+  if (nw > 0) {
+    k_dof_monotone<<<grid_for(nw, 256), 256, 0, st>>>(dm->d_dof, nn, ndn, lo, nw, d_flags + 2, d_flags + 3);
     ctx->launches++;
   }
   if (nadj > 0) {
@@ -1067,29 +1106,36 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
     ctx->launches++;
   }
   PT(dalloc(ctx, &P->d_adjptr, nn + 1));
-  PT(fe_exclusive_scan_i32_to_i64(ctx, d_deg, P->d_adjptr, nn, 0, true, nullptr));
-  int32_t maxdeg = 0;
-  PT(fe_max_i32(ctx, d_deg, nn, &maxdeg));
+  PT(fe_exclusive_scan_i32_to_i64(ctx, d_deg + lo, P->d_adjptr + lo, nw, 0, true, nullptr));
+  PT(fe_max_i32_dev(ctx, d_deg + lo, nw, d_flags + 5));
   // active nodes (at least one active element): compacted list, dropped again when it is every node
   int64_t na = nn;
-  if (nn > 0) {
-    PT(dalloc(ctx, &d_aflag, nn));
-    PT(dalloc(ctx, &d_apos, nn + 1));
-    k_flag_active<<<grid_for(nn, 256), 256, 0, st>>>(d_deg, nn, d_aflag);
+  PT(dalloc(ctx, &d_aflag, nw));
+  PT(dalloc(ctx, &d_apos, nw + 1));
+  PT(dalloc(ctx, &d_anodes, nw));
+  if (nw > 0) {
+    k_flag_active<<<grid_for(nw, 256), 256, 0, st>>>(d_deg, lo, nw, d_aflag);
     ctx->launches++;
-    PT(fe_exclusive_scan_i32_to_i64(ctx, d_aflag, d_apos, nn, 0, true, &na));
-    if (na < nn) {
-      PT(dalloc(ctx, &d_anodes, na));
-      k_compact_active<<<grid_for(nn, 256), 256, 0, st>>>(d_aflag, d_apos, nn, d_anodes);
-      ctx->launches++;
-      S.anodes = d_anodes;
-      S.na = na;
-    }
   }
-  int h_flags[3] = {0, 0, 0};
-  PC(cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * 3, cudaMemcpyDeviceToHost, st));
+  PT(fe_exclusive_scan_i32_to_i64(ctx, d_aflag, d_apos, nw, 0, true, nullptr));
+  if (nw > 0) {
+    k_compact_active<<<grid_for(nw, 256), 256, 0, st>>>(d_aflag, d_apos, lo, nw, d_anodes);
+    ctx->launches++;
+  }
+  // one round trip for every scalar the host needs here
+  int h_flags[NFLAGS] = {0};
+  PC(cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * NFLAGS, cudaMemcpyDeviceToHost, st));
+  PC(cudaMemcpyAsync(&na, d_apos + nw, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   PC(cudaStreamSynchronize(st));
   if (h_flags[0]) return bail();
+  if (na < nn) {
+    S.anodes = d_anodes;
+    S.na = na;
+  }
+  int32_t maxdeg = h_flags[5];
+  // dof range of the window's nodes: the only part of colptr that is counted and scanned
+  const int64_t dlo = h_flags[4] > 0 ? (int64_t)(INT32_MAX - h_flags[3]) : 0;
+  const int64_t dhi = h_flags[4] > 0 ? (int64_t)h_flags[4] : 0;  // exclusive
   const bool monotone = h_flags[2] == 0;
   if (maxdeg < 1) maxdeg = 1;
   P->maxdeg = maxdeg;
@@ -1121,9 +1167,10 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   PT(dalloc(ctx, &d_U, (size_t)nadj * nne));
   PT(dalloc(ctx, &d_sorted, nn));
   PT(dalloc(ctx, &P->d_cslot, (size_t)nadj * nne));
-  if (S.anodes) {  // the per-node kernels skip inactive nodes: their outputs must still be defined
-    PC(cudaMemsetAsync(P->d_nnbr, 0, sizeof(int32_t) * nn, st));
-    PC(cudaMemsetAsync(d_sorted, 1, nn, st));
+  if (S.anodes && nw > 0) {  // the per-node kernels skip inactive nodes: their outputs must still be defined (inside the window;
+                             // nothing reads these two arrays outside it)
+    PC(cudaMemsetAsync(P->d_nnbr + lo, 0, sizeof(int32_t) * nw, st));
+    PC(cudaMemsetAsync(d_sorted + lo, 1, nw, st));
   }
   unsigned gridn = (unsigned)std::min<int64_t>((S.na + WPB - 1) / WPB, (int64_t)ctx->sm_count * 64);
   if (gridn == 0) gridn = 1;
@@ -1155,8 +1202,10 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
         PT(dalloc(ctx, &d_cls, (size_t)S.na * 3));
         PT(dalloc(ctx, &d_clscnt, 3));
         PC(cudaMemsetAsync(d_clscnt, 0, sizeof(unsigned long long) * 3, st));
-        PC(cudaMemsetAsync(P->d_nnbr, 0, sizeof(int32_t) * nn, st));  // nodes without elements are in no list
-        if (!monotone) PC(cudaMemsetAsync(d_sorted, 1, nn, st));
+        if (nw > 0) {
+          PC(cudaMemsetAsync(P->d_nnbr + lo, 0, sizeof(int32_t) * nw, st));  // nodes without elements are in no list
+          if (!monotone) PC(cudaMemsetAsync(d_sorted + lo, 1, nw, st));
+        }
         k_classify_nodes<<<grid_for(S.na, 256), 256, 0, st>>>(S, d_deg, d_cls, d_cls + S.na, d_cls + 2 * S.na, d_clscnt);
         ctx->launches++;
         const SymParams S_all = S;
@@ -1176,7 +1225,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
     }
 #undef LAUNCH_GROUP
 #undef LAUNCH_FAST
-    if (monotone) PC(cudaMemsetAsync(d_sorted, 1, nn, st));  // every node is in order; the kernel did not write the flags
+    if (monotone && nw > 0) PC(cudaMemsetAsync(d_sorted + lo, 1, nw, st));  // every node is in order; the kernel did not write the flags
   } else {
 #define LAUNCH_NBR(N)                                                                                                  \
   do {                                                                                                                 \
@@ -1197,26 +1246,36 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   ctx->launches++;
   PT(dalloc(ctx, &P->d_nbrptr, nn + 1));
   int64_t total_nbr = 0;
-  PT(fe_exclusive_scan_i32_to_i64(ctx, P->d_nnbr, P->d_nbrptr, nn, 0, true, &total_nbr));
-  int32_t maxnbr = 0;
-  PT(fe_max_i32(ctx, P->d_nnbr, nn, &maxnbr));
-  P->maxnbr = std::max(maxnbr, 1);
-  // column pointers
+  PT(fe_exclusive_scan_i32_to_i64(ctx, P->d_nnbr + lo, P->d_nbrptr + lo, nw, 0, true, nullptr));
+  PT(fe_max_i32_dev(ctx, P->d_nnbr + lo, nw, d_flags + 6));
+  if (nw < nn) {  // adjptr / nbrptr stay complete prefix arrays for the consumers that walk every node (vector gather, transport)
+    k_fill_outside<<<grid_for(nn - nw, 256), 256, 0, st>>>(P->d_adjptr, P->d_nbrptr, nn + 1, lo, hi, 0);
+    ctx->launches++;
+  }
+  // column pointers: counts and scan over the dof range of the window, constants on both sides of it
+  const int64_t ndw = dhi - dlo;
   PT(dalloc(ctx, &P->d_colptr, P->ncols + 1));
-  PC(cudaMemsetAsync(P->d_colptr, 0, sizeof(int64_t) * (P->ncols + 1), st));
-  if (nn * ndn > 0) {
-    k_col_counts<<<grid_for(nn * ndn, 256), 256, 0, st>>>(S, P->d_nnbr, P->d_colptr);
+  if (ndw > 0) PC(cudaMemsetAsync(P->d_colptr + dlo, 0, sizeof(int64_t) * ndw, st));
+  if (nw * ndn > 0) {
+    k_col_counts<<<grid_for(nw * ndn, 256), 256, 0, st>>>(S, P->d_nnbr, lo, nw, P->d_colptr);
     ctx->launches++;
   }
   int64_t tot = 0;
-  PT(fe_exclusive_scan_i64(ctx, P->d_colptr, P->d_colptr, P->ncols, 1, true, &tot));
+  PT(fe_exclusive_scan_i64(ctx, P->d_colptr + dlo, P->d_colptr + dlo, ndw, 1, true, nullptr));
+  if (ndw < P->ncols) {
+    k_fill_outside<<<grid_for(P->ncols - ndw, 256), 256, 0, st>>>(P->d_colptr, nullptr, P->ncols + 1, dlo, dhi, 1);
+    ctx->launches++;
+  }
+  PC(cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * NFLAGS, cudaMemcpyDeviceToHost, st));
+  PC(cudaMemcpyAsync(&total_nbr, P->d_nbrptr + hi, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  PC(cudaMemcpyAsync(&tot, P->d_colptr + dhi, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  PC(cudaStreamSynchronize(st));
+  P->maxnbr = std::max(h_flags[6], 1);
   P->nnz = tot - 1;
   if (P->nnz != total_nbr * ndn * ndn) {
     cleanup();
     return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: pattern size mismatch");
   }
-  PC(cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
-  PC(cudaStreamSynchronize(st));
   const bool need_rank = h_flags[1] != 0;
   PT(dalloc(ctx, &P->d_rowval, (size_t)P->nnz));
   if (need_rank) PT(dalloc(ctx, &P->d_rank, (size_t)(total_nbr * ndn)));

@@ -142,6 +142,18 @@ int32_t fe_exclusive_scan_i32_to_i64(fegpu_ctx *ctx, const int32_t *d_in, int64_
   return scan_impl<int32_t>(ctx, d_in, d_out, n, base, write_total, total_host);
 }
 
+// max(*d_out, in[0..n)) left on the device: no synchronisation (the caller initialises the slot and reads it back with its
+// other scalars)
+int32_t fe_max_i32_dev(fegpu_ctx *ctx, const int32_t *d_in, int64_t n, int32_t *d_out) {
+  if (n > 0) {
+    unsigned g = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    k_max_i32<<<g, 256, 0, ctx->stream>>>(d_in, n, d_out);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+  }
+  return FEGPU_OK;
+}
+
 int32_t fe_max_i32(fegpu_ctx *ctx, const int32_t *d_in, int64_t n, int32_t *max_host) {
   int32_t *d_m = nullptr;
   int32_t init = INT32_MIN;

@@ -313,6 +313,72 @@ def test_row_block_partition_reassembles_the_matrix(fe, orc, gpu_ctx, nparts):
     assert abs(diff).max() <= 1e-12 * np.abs(ref[2]).max()
 
 
+def _row_block(ref, keep_rows, n):
+    """The rows `keep_rows` (bool per dof) of the CSC triple `ref`, every column kept."""
+    mask = keep_rows[ref[1] - 1]
+    col_of = np.repeat(np.arange(n), np.diff(ref[0]))
+    cnt = np.bincount(col_of[mask], minlength=n)
+    return np.concatenate(([1], 1 + np.cumsum(cnt))).astype(np.int64), ref[1][mask], ref[2][mask]
+
+
+@pytest.mark.parametrize("variant", ["slab_elastic", "slab_ebc", "inertial_scalar", "t10_three_slabs", "tail_nodes_unused"])
+def test_partition_node_window_variants(fe, orc, gpu_ctx, variant):
+    """The symbolic phase of a partitioned mesh runs over the node window of the rank's active elements (and colptr over
+    the dof range of that window).  Every rank's block must still be the oracle's rows-of-owned-nodes block, bit-exact in
+    colptr / rowval (complete colptr: constant before and after the window), for contiguous slabs, a numbering with the
+    fixed dofs last (non-monotone dof map, dof range != node window), a non-contiguous owner map (recursive inertial
+    bisection), mixed-valence T10 nodes, and a mesh whose last nodes belong to no element."""
+    rule = fe.GaussRule(3, 2)
+    if variant == "slab_elastic":
+        fens, fes = fe.H8block(1.0, 1.0, 1.0, 3, 4, 9)
+        u = make_field(fe, fens, 3)
+        form, et, coef, nparts = "elastic", "H8", isotropic_C(), 4
+        owner = fe.slab_owner(fens.count(), nparts)
+    elif variant == "slab_ebc":
+        fens, fes = fe.H8block(1.0, 1.0, 1.0, 3, 3, 8)
+        u = make_field(fe, fens, 3, fixed_nodes=np.arange(5, fens.count(), 7) + 1, fixed_comp=[1, 3])
+        form, et, coef, nparts = "elastic", "H8", isotropic_C(), 3
+        owner = fe.slab_owner(fens.count(), nparts)
+    elif variant == "inertial_scalar":
+        fens, fes = fe.H8block(2.0, 1.0, 1.5, 6, 4, 5)
+        u = make_field(fe, fens, 1)
+        form, et, coef, nparts = "diffusion", "H8", KAPPA3, 4
+        owner = fe.pointpartitioning(fens.xyz, nparts) - 1
+    elif variant == "t10_three_slabs":
+        fens, fes = fe.T10block(1.0, 1.0, 1.0, 2, 2, 5)
+        u = make_field(fe, fens, 1)
+        rule = fe.TetRule(4)
+        form, et, coef, nparts = "dot", "T10", np.array([[1.0]]), 3
+        owner = fe.slab_owner(fens.count(), nparts)
+    else:
+        fens, fes = fe.H8block(1.0, 1.0, 1.0, 3, 3, 6)
+        fes = fes.subset(np.arange(27))  # the three lowest element layers: the upper nodes belong to no element
+        u = make_field(fe, fens, 1)
+        form, et, coef, nparts = "diffusion", "H8", 1.7, 2
+        owner = fe.slab_owner(fens.count(), nparts)
+    owner = np.asarray(owner, dtype=np.int32)
+    ref, _ = oracle_csc(orc, form, et, fes, fens, u, rule, coef)
+    n = u.nalldofs()
+    nnz_sum = 0
+    for p in range(nparts):
+        keep = np.zeros(n, bool)
+        keep[(u.dofnums[owner == p] - 1).reshape(-1)] = True
+        blk = _row_block(ref, keep, n)
+        got, a = gpu_csc(fe, form, fes, fens, u, rule, coef, node_owner=owner, my_rank=p)
+        scale = np.abs(ref[2]).max()
+        np.testing.assert_array_equal(got[0], blk[0])
+        np.testing.assert_array_equal(got[1], blk[1])
+        assert got[2].size == blk[2].size
+        if blk[2].size:
+            assert np.abs(got[2] - blk[2]).max() <= 1e-12 * scale
+        # a second, cached assembly on the same partition is bit-identical
+        got2, _ = gpu_csc(fe, form, fes, fens, u, rule, coef, assembler=a, node_owner=owner, my_rank=p)
+        assert a.pattern_was_cached()
+        np.testing.assert_array_equal(got2[2], got[2])
+        nnz_sum += got[2].size
+    assert nnz_sum == ref[2].size
+
+
 def _sampled_symmetry(colptr, rowval, nzval, cols):
     """K[i,j] == K[j,i] bit for bit on the entries of the sampled columns (binary search in the partner column)."""
     for j in cols:
