@@ -4,7 +4,9 @@ element loop, triplet storage and COO->CSC conversion run on a B200 through libf
 Protocol mirrored: startassembly! (:209-238), assemble! (:250-282), makematrix! (:304-329), setnomatrixresult (:29),
 expectedntriples (:54-59), eltype (:27).  Julia's `!` is dropped from the names.  Error strings are the reference's.
 """
+import contextlib
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -33,7 +35,24 @@ class GPUContext:
         check(_lib.lib().fegpu_set_stream(self.handle, VP(int(cuda_stream_ptr))), self.handle)
 
     def set_async(self, on):
+        """Form calls return once their work is queued (the result calls synchronise); off = every call blocks (default)."""
+        self._async = bool(on)
         check(_lib.lib().fegpu_set_async(self.handle, 1 if on else 0), self.handle)
+
+    @contextlib.contextmanager
+    def queued_forms(self, enable=True):
+        """Scope in which a form call only queues its device work, for callers that fetch the result right after: the
+        transport then ships the pattern's arrays (and the host threads rebuild rowval) while the integration and the
+        numeric phase are still running.  Restores the caller's own set_async choice on exit."""
+        prev = getattr(self, "_async", False)
+        enable = enable and os.environ.get("FEGPU_QUEUED_FORMS", "1") != "0"  # A/B knob
+        if enable and not prev:
+            self.set_async(True)
+        try:
+            yield self
+        finally:
+            if enable and not prev:
+                self.set_async(False)
 
     def set_overlap(self, on):
         """Fresh assemblies overlap element integration (second stream) with the symbolic phase; off = strictly serial phases."""

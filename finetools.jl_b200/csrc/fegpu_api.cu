@@ -94,10 +94,12 @@ __global__ void k_expand_compact(const double *__restrict__ Vc, double *__restri
 
 // smallest and largest node id used by the active elements: win[0] = max(~node) (so that a zero-initialised slot means "no node"),
 // win[1] = max(node + 1).  The symbolic phase runs its per-node passes over [lo, hi) only.
-__global__ void k_active_window(const int32_t *__restrict__ conn, int64_t nelem, int nne, const int32_t *__restrict__ flag, int *__restrict__ win) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_active_window(const int32_t *__restrict__ conn, int64_t nelem, int nne, const int32_t *__restrict__ flag,
+                                                       int *__restrict__ win) {
+  __shared__ int s_lo[8], s_hi[8];
   int lo = INT32_MAX, hi = 0;
-  if (e < nelem && flag[e]) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += (int64_t)gridDim.x * blockDim.x) {
+    if (!flag[e]) continue;
     for (int a = 0; a < nne; a++) {
       const int n = conn[e * nne + a];
       lo = min(lo, n);
@@ -108,9 +110,20 @@ __global__ void k_active_window(const int32_t *__restrict__ conn, int64_t nelem,
     lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
     hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
   }
-  if ((threadIdx.x & 31) == 0 && hi > 0) {
-    atomicMax(&win[0], INT32_MAX - lo);
-    atomicMax(&win[1], hi);
+  if ((threadIdx.x & 31) == 0) {
+    s_lo[threadIdx.x >> 5] = lo;
+    s_hi[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; k++) {
+      lo = min(lo, s_lo[k]);
+      hi = max(hi, s_hi[k]);
+    }
+    if (hi > 0) {
+      atomicMax(&win[0], INT32_MAX - lo);
+      atomicMax(&win[1], hi);
+    }
   }
 }
 
@@ -446,7 +459,7 @@ int32_t fegpu_partition_set(fegpu_mesh *m, const int32_t *node_owner, int32_t my
   PT(cudaMalloc((void **)&d_win, sizeof(int) * 2));
   PT(cudaMemsetAsync(d_win, 0, sizeof(int) * 2, st));
   if (m->nelem) {
-    k_active_window<<<grid_for(m->nelem, 256), 256, 0, st>>>(m->d_conn, m->nelem, m->nne, d_flag, d_win);
+    k_active_window<<<(unsigned)std::min<int64_t>(grid_for(m->nelem, 256), (int64_t)ctx->sm_count * 8), 256, 0, st>>>(m->d_conn, m->nelem, m->nne, d_flag, d_win);
     ctx->launches++;
   }
   PT(cudaMemcpyAsync(h_win, d_win, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
@@ -650,6 +663,7 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
   if (integrated && !fast && fa2.compact) integrated = false;  // late fall-back to the sort path: it needs full element matrices
   if (!integrated) FE_TRY(integrate(fast && fe_integrate_supports_compact(mesh, fa) && !compact_off));
   CUDA_TRY(ctx, cudaEventRecord(as->ev[5], st));
+  FE_TRACE("bilform: before numeric phase");
   // 3. numeric CSC phase
   if (fast) {
     const int64_t nnz = fe_pattern_nnz(dm->pat);
@@ -674,6 +688,7 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
     FE_TRY(s);
   }
   CUDA_TRY(ctx, cudaEventRecord(as->ev[3], st));
+  FE_TRACE("bilform: gather queued");
   as->ev_valid = true;
   as->have_result = true;
   if (as->symmetric) {

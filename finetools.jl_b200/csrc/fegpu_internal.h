@@ -137,6 +137,10 @@ int32_t fegpu_fail(fegpu_ctx *ctx, int32_t code, const std::string &msg);
     if (_s != FEGPU_OK) return _s;  \
   } while (0)
 
+// FEGPU_TRACE=1: host wall-clock marks (microseconds since the previous mark) on stderr, to find host-side stalls
+void fe_trace(const char *label);
+#define FE_TRACE(label) fe_trace(label)
+
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 // ---- primitives (fegpu_prims.cu) -----------------------------------------------------------------------
@@ -182,6 +186,7 @@ bool fe_integrate_supports_compact(const fegpu_mesh *mesh, const FormArgs &fa);
 int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork = nullptr);
 void fe_pattern_free(Pattern *p);
 void fe_pattern_set_stream(Pattern *p, cudaStream_t s);  // stream its stream-ordered frees are queued on
+cudaEvent_t fe_pattern_ready_event(const Pattern *p);    // completes when every array of the pattern is final
 int64_t fe_pattern_nnz(const Pattern *p);
 const int64_t *fe_pattern_colptr(const Pattern *p);
 const int64_t *fe_pattern_rowval(const Pattern *p);

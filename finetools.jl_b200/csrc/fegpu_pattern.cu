@@ -42,6 +42,8 @@ struct Pattern {
   int64_t nnodes = 0;
   int maxdeg = 0, maxcand = 0, maxnbr = 0;
   cudaStream_t stream = 0;
+  cudaEvent_t ready = nullptr;    // recorded when the build's last kernel is queued: the result transport may ship the pattern's
+                                  // arrays while the integration and the numeric phase of the same call are still running
 };
 
 namespace {
@@ -92,7 +94,9 @@ __global__ void k_fill_outside(int64_t *__restrict__ a0, int64_t *__restrict__ a
   if (a1) a1[idx] = (i < lo) ? before : a1[hi];
 }
 
-__global__ void k_count_adj(SymParams S, int32_t *deg, int *degenerate) {
+// The count pass keeps what its atomic returns -- the position of this (element, local node) inside the node's list -- so that
+// the fill pass is a plain scatter without a second round of atomics.
+__global__ void k_count_adj(SymParams S, int32_t *deg, uint16_t *__restrict__ arank, int *degenerate) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S.nactive * S.nne) return;
   int64_t slot = i / S.nne;
@@ -100,19 +104,20 @@ __global__ void k_count_adj(SymParams S, int32_t *deg, int *degenerate) {
   int64_t e = S.elem_list ? S.elem_list[slot] : slot;
   const int32_t *c = S.conn + e * S.nne;
   int n = c[lc];
-  atomicAdd(&deg[n], 1);
+  arank[i] = (uint16_t)atomicAdd(&deg[n], 1);  // degrees >= 65535 / nne leave the structured path before the fill runs
   for (int k = 0; k < lc; k++)
     if (c[k] == n) *degenerate = 1;
 }
 
-__global__ void k_fill_adj(SymParams S, const int64_t *adjptr, int32_t *cursor, int32_t *adj_slot, uint8_t *adj_lc) {
+__global__ void k_fill_adj(SymParams S, const int64_t *__restrict__ adjptr, const uint16_t *__restrict__ arank, int32_t *__restrict__ adj_slot,
+                           uint8_t *__restrict__ adj_lc) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S.nactive * S.nne) return;
   int64_t slot = i / S.nne;
   int lc = (int)(i % S.nne);
   int64_t e = S.elem_list ? S.elem_list[slot] : slot;
   int n = S.conn[e * S.nne + lc];
-  int64_t pos = adjptr[n] + atomicAdd(&cursor[n], 1);
+  int64_t pos = adjptr[n] + arank[i];
   adj_slot[pos] = (int32_t)slot;
   adj_lc[pos] = (uint8_t)lc;
 }
@@ -684,16 +689,16 @@ __global__ void k_classify_nodes(SymParams S, const int32_t *__restrict__ deg, i
 // rows of every column are ascending in (neighbour, component) order and no node needs an order test or a rank table.
 // Over the node window only (every row and column node of the pattern is in it).  Also the dof range of the window's nodes,
 // the part of colptr that needs a scan: range[0] = max(INT32_MAX - dof), range[1] = max(dof + 1) (zero-initialised slots).
-__global__ void k_dof_monotone(const int32_t *__restrict__ dof, int64_t nnodes, int ndn, int64_t lo, int64_t nw, int *violated,
-                               int *__restrict__ range) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_dof_monotone(const int32_t *__restrict__ dof, int64_t nnodes, int ndn, int64_t lo, int64_t nw,
+                                                      int *violated, int *__restrict__ range) {
+  __shared__ int s_min[8], s_max[8];
   int dmin = INT32_MAX, dmax = -1;
   bool bad = false;
-  if (i < nw) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t n = lo + i;
     int prev = dof[n];
-    dmin = prev;
-    dmax = prev;
+    dmin = min(dmin, prev);
+    dmax = max(dmax, prev);
     for (int p = 1; p < ndn; p++) {
       const int d = dof[(int64_t)p * nnodes + n];
       bad = bad || d <= prev;
@@ -707,11 +712,22 @@ __global__ void k_dof_monotone(const int32_t *__restrict__ dof, int64_t nnodes, 
     dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, d));
     dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, d));
   }
-  if ((threadIdx.x & 31) == 0 && dmax >= 0) {
-    atomicMax(&range[0], INT32_MAX - dmin);
-    atomicMax(&range[1], dmax + 1);
+  if ((threadIdx.x & 31) == 0) {
+    s_min[threadIdx.x >> 5] = dmin;
+    s_max[threadIdx.x >> 5] = dmax;
   }
   if (bad) *violated = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {  // one pair of atomics per block: they all land on the same two words
+    for (int k = 1; k < 8; k++) {
+      dmin = min(dmin, s_min[k]);
+      dmax = max(dmax, s_max[k]);
+    }
+    if (dmax >= 0) {
+      atomicMax(&range[0], INT32_MAX - dmin);
+      atomicMax(&range[1], dmax + 1);
+    }
+  }
 }
 
 __global__ void k_col_counts(SymParams S, const int32_t *nnbr, int64_t lo, int64_t nw, int64_t *colcount) {
@@ -1029,13 +1045,17 @@ int32_t dalloc(fegpu_ctx *ctx, T **p, size_t n) {
 
 void fe_pattern_free(Pattern *p) {
   if (!p) return;
+  FE_TRACE("pattern_free: enter");
   cudaStream_t st = p->stream;  // stream-ordered frees: blocks go back to the pool, no device synchronisation
   void *ptrs[] = {p->d_colptr, p->d_rowval, p->d_adjptr, p->d_adj_slot, p->d_adj_lc, p->d_nnbr, p->d_nbrptr, p->d_cslot, p->d_rank, p->d_order, p->d_nbr};
   for (void *q : ptrs)
     if (q) cudaFreeAsync(q, st);
+  if (p->ready) cudaEventDestroy(p->ready);
   delete p;
+  FE_TRACE("pattern_free: done");
 }
 void fe_pattern_set_stream(Pattern *p, cudaStream_t s) { p->stream = s; }
+cudaEvent_t fe_pattern_ready_event(const Pattern *p) { return p ? p->ready : nullptr; }
 int64_t fe_pattern_nnz(const Pattern *p) { return p->nnz; }
 const int64_t *fe_pattern_colptr(const Pattern *p) { return p->d_colptr; }
 const int64_t *fe_pattern_rowval(const Pattern *p) { return p->d_rowval; }
@@ -1065,7 +1085,8 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   SymParams S{mesh->d_conn, mesh->d_elem_list, mesh->nactive, nne, nn, mesh->d_rowowned, dm->d_dof, ndn, nullptr, nn, nullptr};
   const int64_t nadj = mesh->nactive * nne;
 
-  int32_t *d_deg = nullptr, *d_cursor = nullptr, *d_U = nullptr, *d_aflag = nullptr, *d_anodes = nullptr, *d_cls = nullptr;
+  uint16_t *d_arank = nullptr;
+  int32_t *d_deg = nullptr, *d_U = nullptr, *d_aflag = nullptr, *d_anodes = nullptr, *d_cls = nullptr;
   unsigned long long *d_clscnt = nullptr;
   int64_t *d_apos = nullptr;
   uint8_t *d_sorted = nullptr;
@@ -1074,7 +1095,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   int *d_flags = nullptr;
   constexpr int NFLAGS = 8;
   auto cleanup = [&]() {
-    void *ptrs[] = {d_deg, d_cursor, d_U, d_sorted, d_flags, d_aflag, d_anodes, d_apos, d_cls, d_clscnt};
+    void *ptrs[] = {d_deg, d_arank, d_U, d_sorted, d_flags, d_aflag, d_anodes, d_apos, d_cls, d_clscnt};
     for (void *q : ptrs)
       if (q) cudaFreeAsync(q, st);
   };
@@ -1087,22 +1108,22 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   };
 #define PT(expr) do { int32_t _s = (expr); if (_s != FEGPU_OK) { cleanup(); return _s; } } while (0)
 #define PC(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fegpu_fail(ctx, FEGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+  FE_TRACE("build: enter");
   // node window of the active elements: every per-node pass below runs over [lo, hi) only
   const int64_t lo = mesh->win_lo, hi = mesh->win_hi, nw = hi - lo;
   PT(dalloc(ctx, &d_deg, nn));
-  PT(dalloc(ctx, &d_cursor, nn));
+  PT(dalloc(ctx, &d_arank, nadj));
   PT(dalloc(ctx, &d_flags, NFLAGS));
   if (nw > 0) {
     PC(cudaMemsetAsync(d_deg + lo, 0, sizeof(int32_t) * nw, st));
-    PC(cudaMemsetAsync(d_cursor + lo, 0, sizeof(int32_t) * nw, st));
   }
   PC(cudaMemsetAsync(d_flags, 0, sizeof(int) * NFLAGS, st));
   if (nw > 0) {
-    k_dof_monotone<<<grid_for(nw, 256), 256, 0, st>>>(dm->d_dof, nn, ndn, lo, nw, d_flags + 2, d_flags + 3);
+    k_dof_monotone<<<(unsigned)std::min<int64_t>(grid_for(nw, 256), (int64_t)ctx->sm_count * 8), 256, 0, st>>>(dm->d_dof, nn, ndn, lo, nw, d_flags + 2, d_flags + 3);
     ctx->launches++;
   }
   if (nadj > 0) {
-    k_count_adj<<<grid_for(nadj, 256), 256, 0, st>>>(S, d_deg, d_flags);
+    k_count_adj<<<grid_for(nadj, 256), 256, 0, st>>>(S, d_deg, d_arank, d_flags);
     ctx->launches++;
   }
   PT(dalloc(ctx, &P->d_adjptr, nn + 1));
@@ -1125,8 +1146,10 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   // one round trip for every scalar the host needs here
   int h_flags[NFLAGS] = {0};
   PC(cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * NFLAGS, cudaMemcpyDeviceToHost, st));
+  FE_TRACE("build: first passes queued");
   PC(cudaMemcpyAsync(&na, d_apos + nw, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   PC(cudaStreamSynchronize(st));
+  FE_TRACE("build: sync A done");
   if (h_flags[0]) return bail();
   if (na < nn) {
     S.anodes = d_anodes;
@@ -1146,6 +1169,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   const size_t smem1 = (size_t)WPB * (maxdeg + 3 * (size_t)capc) * sizeof(uint32_t);
   if (P->maxcand >= 65535 || (int64_t)P->maxcand * ndn >= 65535 || smem1 > 200 * 1024) return bail();
   if (fork) PT((*fork)());  // the structured path will be taken: independent work may start on another stream now
+  FE_TRACE("build: fork (integration queued)");
 
   PT(dalloc(ctx, &P->d_adj_slot, nadj));
   PT(dalloc(ctx, &P->d_adj_lc, nadj));
@@ -1156,7 +1180,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   const bool nbr_fast = !nbr_fast_off && maxdeg <= 32 && capc <= 512 && (uint64_t)nn <= (uint64_t)(0xffffffffu >> KB) &&
                         mesh->nactive < ((int64_t)1 << 27);
   if (nadj > 0) {
-    k_fill_adj<<<grid_for(nadj, 256), 256, 0, st>>>(S, P->d_adjptr, d_cursor, P->d_adj_slot, P->d_adj_lc);
+    k_fill_adj<<<grid_for(nadj, 256), 256, 0, st>>>(S, P->d_adjptr, d_arank, P->d_adj_slot, P->d_adj_lc);
     ctx->launches++;
     if (!nbr_fast) {  // the register-only kernels sort every node's list themselves
       k_sort_adj<<<grid_for(S.na, 128), 128, 0, st>>>(S, P->d_adjptr, P->d_adj_slot, P->d_adj_lc);
@@ -1268,8 +1292,10 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   }
   PC(cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * NFLAGS, cudaMemcpyDeviceToHost, st));
   PC(cudaMemcpyAsync(&total_nbr, P->d_nbrptr + hi, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  FE_TRACE("build: nbr + scans queued");
   PC(cudaMemcpyAsync(&tot, P->d_colptr + dhi, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   PC(cudaStreamSynchronize(st));
+  FE_TRACE("build: sync B done");
   P->maxnbr = std::max(h_flags[6], 1);
   P->nnz = tot - 1;
   if (P->nnz != total_nbr * ndn * ndn) {
@@ -1330,7 +1356,11 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
       P->norder = S.na;
     }
   }
+  PC(cudaEventCreateWithFlags(&P->ready, cudaEventDisableTiming));
+  PC(cudaEventRecord(P->ready, st));
+  FE_TRACE("build: rows queued");
   cleanup();
+  FE_TRACE("build: temporaries freed");
 #undef PT
 #undef PC
   dm->pat_topo_version = mesh->topo_version;

@@ -2,6 +2,28 @@
 // recursive scan of the totals, offset add.  These run in the symbolic phase and the generic sort path.
 #include "fegpu_internal.h"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
+void fe_trace(const char *label) {
+  static const bool on = std::getenv("FEGPU_TRACE") && std::atoi(std::getenv("FEGPU_TRACE")) != 0;
+  if (!on) return;
+  static auto last = std::chrono::steady_clock::now();
+  const auto now = std::chrono::steady_clock::now();
+  // the stream-ordered pool's footprint: growth between two steps means freed blocks were not reused
+  uint64_t reserved = 0, used = 0;
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+  }
+  std::fprintf(stderr, "[fegpu trace] %10.1f us  %-36s pool reserved %7.2f GB used %7.2f GB\n",
+               std::chrono::duration<double, std::micro>(now - last).count(), label, reserved / 1e9, used / 1e9);
+  last = std::chrono::steady_clock::now();
+}
+
 namespace {
 
 constexpr int SCAN_THREADS = 256;

@@ -299,8 +299,13 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
   FE_TRY(transfer_get(ctx, &T));
   cudaStream_t cs = T->stream;
   CUDA_TRY(ctx, cudaEventRecord(T->ready, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamWaitEvent(cs, T->ready, 0));
   const int64_t nnz = as->r_nnz();
+  bool joined = false;  // has the copy stream been ordered after everything queued on the caller's stream?
+  auto join = [&]() -> int32_t {
+    if (!joined) CUDA_TRY(ctx, cudaStreamWaitEvent(cs, T->ready, 0));
+    joined = true;
+    return FEGPU_OK;
+  };
 
   StagedJob jobs[2];
   int njobs = 0;
@@ -329,18 +334,27 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
       T->meta_cap = need;
     }
     char *hm = static_cast<char *>(T->h_meta);
+    // The pattern's arrays are final when its build is (the event of the pattern): when the form call was asynchronous
+    // (fegpu_set_async) they cross the link while the integration and the numeric phase are still running, and the host
+    // threads can start on rowval before nzval exists.
+    static const bool early_off = std::getenv("FEGPU_EARLY_META") && std::atoi(std::getenv("FEGPU_EARLY_META")) == 0;  // A/B knob
+    cudaEvent_t pr = early_off ? nullptr : fe_pattern_ready_event(as->pat_src);
+    if (pr) CUDA_TRY(ctx, cudaStreamWaitEvent(cs, pr, 0));
+    else FE_TRY(join());
     // small pieces first so the threads can start on the first nodes as early as possible
     CUDA_TRY(ctx, cudaMemcpyAsync(hm, as->d_colptr, (size_t)(as->ncols + 1) * 8, cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(ctx, cudaMemcpyAsync(hm + b_col, c_nbrptr, (size_t)(c_nnodes + 1) * 8, cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(ctx, cudaMemcpyAsync(hm + b_col + b_ptr, c_dof, (size_t)c_nnodes * c_ndn * 4, cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(ctx, cudaMemcpyAsync(hm + b_col + b_ptr + b_dof, c_nbr, (size_t)c_total * 4, cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(ctx, cudaEventRecord(T->meta_done, cs));
+    FE_TRY(join());
     h_colptr = reinterpret_cast<const int64_t *>(hm);
     h_nbrptr = reinterpret_cast<const int64_t *>(hm + b_col);
     h_dof = reinterpret_cast<const int32_t *>(hm + b_col + b_ptr);
     h_nbr = reinterpret_cast<const int32_t *>(hm + b_col + b_ptr + b_dof);
     T->compressed++;
   }
+  FE_TRY(join());
   // node range [lo, hi) of slice k of K, balanced by neighbour-list length
   auto node_slice = [&](int64_t k, int64_t K, int64_t *lo, int64_t *hi) {
     auto cut = [&](int64_t j) -> int64_t {

@@ -208,8 +208,9 @@ def bilform_diffusion(self, assembler, geom, u, cf, raw=False, node_owner=None, 
         if kap.shape != (fes.mdim, fes.mdim):
             raise FEGPUError(-2, "conductivity matrix must be mdim x mdim")
         kind, k = 1, np.asfortranarray(kap)
-    check(_lib.lib().fegpu_bilform_diffusion(dmesh.handle, dof, kind, fptr(k), _inner(assembler).handle), assembler.ctx.handle)
-    return _finish(assembler, fes, dmesh, dof, u, raw, out)
+    with assembler.ctx.queued_forms(not _inner(assembler)._nomatrixresult):
+        check(_lib.lib().fegpu_bilform_diffusion(dmesh.handle, dof, kind, fptr(k), _inner(assembler).handle), assembler.ctx.handle)
+        return _finish(assembler, fes, dmesh, dof, u, raw, out)
 
 
 def bilform_lin_elastic(self, assembler, geom, u, mr, cf, raw=False, node_owner=None, my_rank=0, out=None):
@@ -224,8 +225,9 @@ def bilform_lin_elastic(self, assembler, geom, u, mr, cf, raw=False, node_owner=
         raise FEGPUError(-2, "material stiffness must be 6 x 6")
     fes, dmesh, dof = _prepare(self, assembler, geom, u, node_owner, my_rank)
     Cf = np.asfortranarray(Cm)
-    check(_lib.lib().fegpu_bilform_lin_elastic(dmesh.handle, dof, fptr(Cf), _inner(assembler).handle), assembler.ctx.handle)
-    return _finish(assembler, fes, dmesh, dof, u, raw, out)
+    with assembler.ctx.queued_forms(not _inner(assembler)._nomatrixresult):
+        check(_lib.lib().fegpu_bilform_lin_elastic(dmesh.handle, dof, fptr(Cf), _inner(assembler).handle), assembler.ctx.handle)
+        return _finish(assembler, fes, dmesh, dof, u, raw, out)
 
 
 def bilform_dot(self, assembler, geom, u, cf, m=3, raw=False, node_owner=None, my_rank=0, out=None):
@@ -239,9 +241,10 @@ def bilform_dot(self, assembler, geom, u, cf, m=3, raw=False, node_owner=None, m
         raise FEGPUError(-2, "coefficient must be ndn x ndn")
     fes, dmesh, dof = _prepare(self, assembler, geom, u, node_owner, my_rank)
     cfm = np.asfortranarray(c)
-    check(_lib.lib().fegpu_bilform_dot(dmesh.handle, dof, fptr(cfm), int(m), float(self.integdomain.otherdimension), _inner(assembler).handle),
-          assembler.ctx.handle)
-    return _finish(assembler, fes, dmesh, dof, u, raw, out)
+    with assembler.ctx.queued_forms(not _inner(assembler)._nomatrixresult):
+        check(_lib.lib().fegpu_bilform_dot(dmesh.handle, dof, fptr(cfm), int(m), float(self.integdomain.otherdimension), _inner(assembler).handle),
+              assembler.ctx.handle)
+        return _finish(assembler, fes, dmesh, dof, u, raw, out)
 
 
 def bilform_convection(self, assembler, geom, u, Q, rhof, raw=False, node_owner=None, my_rank=0, out=None):
@@ -255,8 +258,9 @@ def bilform_convection(self, assembler, geom, u, Q, rhof, raw=False, node_owner=
     if fes.mdim != sdim or u.values.shape != (geom.values.shape[0], sdim):
         raise FEGPUError(-2, "bilform_convection needs a velocity component per space dimension and sdim == manifold dimension")
     uv = _lib.colmajor_f64(u.values)
-    check(_lib.lib().fegpu_bilform_convection(dmesh.handle, dof, fptr(uv), float(rhof.data), _inner(assembler).handle), assembler.ctx.handle)
-    return _finish(assembler, fes, dmesh, dof, Q, raw, out)
+    with assembler.ctx.queued_forms(not _inner(assembler)._nomatrixresult):
+        check(_lib.lib().fegpu_bilform_convection(dmesh.handle, dof, fptr(uv), float(rhof.data), _inner(assembler).handle), assembler.ctx.handle)
+        return _finish(assembler, fes, dmesh, dof, Q, raw, out)
 
 
 def bilform_div_grad(self, assembler, geom, u, viscf, raw=False, node_owner=None, my_rank=0, out=None):
@@ -267,8 +271,9 @@ def bilform_div_grad(self, assembler, geom, u, viscf, raw=False, node_owner=None
     sdim = geom.values.shape[1]
     if fes.mdim != sdim or u.ndofs() != sdim:
         raise FEGPUError(-2, "bilform_div_grad needs one dof per space dimension and sdim == manifold dimension")
-    check(_lib.lib().fegpu_bilform_div_grad(dmesh.handle, dof, float(viscf.data), _inner(assembler).handle), assembler.ctx.handle)
-    return _finish(assembler, fes, dmesh, dof, u, raw, out)
+    with assembler.ctx.queued_forms(not _inner(assembler)._nomatrixresult):
+        check(_lib.lib().fegpu_bilform_div_grad(dmesh.handle, dof, float(viscf.data), _inner(assembler).handle), assembler.ctx.handle)
+        return _finish(assembler, fes, dmesh, dof, u, raw, out)
 
 
 def bilform_masslike(self, assembler, geom, phi, cf, m=3, raw=False, out=None):

@@ -214,6 +214,18 @@ function _device(self::FEMMBase, a, geom, u)   # a: SysmatAssemblerSparseGPU or 
     return mh, dh
 end
 
+# A form call only queues its device work when the result is fetched right after (makematrix! synchronises): the transport
+# then ships the pattern's arrays, and the host threads rebuild rowval, while the integration and the numeric phase still run.
+function _queued(f, a)
+    on = !(a isa SysmatAssemblerSparseGPU) || !a._nomatrixresult
+    on && ccall((:fegpu_set_async, LIB), Int32, (Ptr{Cvoid}, Int32), a.ctx, 1)
+    try
+        return f()
+    finally
+        on && ccall((:fegpu_set_async, LIB), Int32, (Ptr{Cvoid}, Int32), a.ctx, 0)
+    end
+end
+
 # ---- the three forms: more specific methods than the generic drivers (FEMMBaseModule.jl:1335, 1462, 1774) ---------------
 function bilform_diffusion(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, geom::NodalField{FT}, u::NodalField{T},
     cf::DC) where {FT,T,DC<:DataCache}
@@ -222,9 +234,11 @@ function bilform_diffusion(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, 
     kappa = cf._cache
     kind = isempty(size(kappa)) ? 0 : 1
     k = kind == 0 ? Float64[kappa] : Matrix{Float64}(kappa)
-    GC.@preserve k _check(ccall((:fegpu_bilform_diffusion, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Cvoid}),
-            mh, dh, kind, k, assembler.handle), assembler.ctx)
-    return makematrix!(assembler)
+    return _queued(assembler) do
+        GC.@preserve k _check(ccall((:fegpu_bilform_diffusion, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Cvoid}),
+                mh, dh, kind, k, assembler.handle), assembler.ctx)
+        makematrix!(assembler)
+    end
 end
 
 function bilform_lin_elastic(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, geom::NodalField{FT}, u::NodalField{T},
@@ -233,9 +247,11 @@ function bilform_lin_elastic(self::FEMMBase, assembler::SysmatAssemblerSparseGPU
     mh, dh = _device(self, assembler, geom, u)
     C = Matrix{Float64}(cf._cache)
     size(C) == (6, 6) || error("Wrong dimensions")
-    GC.@preserve C _check(ccall((:fegpu_bilform_lin_elastic, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}),
-            mh, dh, C, assembler.handle), assembler.ctx)
-    return makematrix!(assembler)
+    return _queued(assembler) do
+        GC.@preserve C _check(ccall((:fegpu_bilform_lin_elastic, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}),
+                mh, dh, C, assembler.handle), assembler.ctx)
+        makematrix!(assembler)
+    end
 end
 
 function bilform_dot(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, geom::NodalField{FT}, u::NodalField{T}, cf::DC;
@@ -243,9 +259,11 @@ function bilform_dot(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, geom::
     _eligible(self, geom, u, cf)
     mh, dh = _device(self, assembler, geom, u)
     c = Matrix{Float64}(cf._cache)          # densifies LinearAlgebra.I(ndofs) (a Diagonal{Bool}), see innerproduct :1388-1401
-    GC.@preserve c _check(ccall((:fegpu_bilform_dot, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Ptr{Cvoid}),
-            mh, dh, c, m, _otherdim(self), assembler.handle), assembler.ctx)
-    return makematrix!(assembler)
+    return _queued(assembler) do
+        GC.@preserve c _check(ccall((:fegpu_bilform_dot, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Ptr{Cvoid}),
+                mh, dh, c, m, _otherdim(self), assembler.handle), assembler.ctx)
+        makematrix!(assembler)
+    end
 end
 
 # ---- SURVEY.md 8(f) rank 3: sibling forms on the same per-element pipeline ----------------------------------------------
@@ -255,9 +273,11 @@ function bilform_convection(self::FEMMBase, assembler::SysmatAssemblerSparseGPU,
     _eligible(self, geom, Q, rhof)
     mh, dh = _device(self, assembler, geom, Q)
     uv = Matrix{Float64}(u.values)           # nnodes x sdim, column-major
-    GC.@preserve uv _check(ccall((:fegpu_bilform_convection, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Float64, Ptr{Cvoid}),
-            mh, dh, uv, Float64(rhof._cache), assembler.handle), assembler.ctx)
-    return makematrix!(assembler)
+    return _queued(assembler) do
+        GC.@preserve uv _check(ccall((:fegpu_bilform_convection, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Float64, Ptr{Cvoid}),
+                mh, dh, uv, Float64(rhof._cache), assembler.handle), assembler.ctx)
+        makematrix!(assembler)
+    end
 end
 
 # bilform_div_grad (FEMMBaseModule.jl:1672-1713)
@@ -265,9 +285,11 @@ function bilform_div_grad(self::FEMMBase, assembler::SysmatAssemblerSparseGPU, g
     viscf::DC) where {FT,T,DC<:DataCache}
     _eligible(self, geom, u, viscf)
     mh, dh = _device(self, assembler, geom, u)
-    _check(ccall((:fegpu_bilform_div_grad, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Ptr{Cvoid}),
-            mh, dh, Float64(viscf._cache), assembler.handle), assembler.ctx)
-    return makematrix!(assembler)
+    return _queued(assembler) do
+        _check(ccall((:fegpu_bilform_div_grad, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Ptr{Cvoid}),
+                mh, dh, Float64(viscf._cache), assembler.handle), assembler.ctx)
+        makematrix!(assembler)
+    end
 end
 
 # bilform_masslike (FEMMBaseModule.jl:1865-1912): rectangular (count(fes)*ndn) x nalldofs(phi), rows numbered by element

@@ -55,6 +55,10 @@ int32_t fegpu_destroy(fegpu_ctx *ctx);
 const char *fegpu_last_error(fegpu_ctx *ctx); /* ctx may be NULL: last error of the calling thread        */
 /* run all kernels on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); default = stream 0 */
 int32_t fegpu_set_stream(fegpu_ctx *ctx, void *cuda_stream);
+/* async_on = 1: the form calls (fegpu_bilform_*, fegpu_linform_dot) return once their device work is queued; every call that
+ * hands results to the host (fegpu_makematrix_copy*, fegpu_coo_copy, fegpu_last_timings, ...) synchronises.  A shim that
+ * fetches the matrix right after the form switches it on around the pair: fegpu_makematrix_copy then ships the pattern's
+ * arrays, and its host threads rebuild rowval, while the integration and the numeric phase are still running.  Default: off. */
 int32_t fegpu_set_async(fegpu_ctx *ctx, int32_t async_on);
 /* Fresh assemblies (no cached pattern) run the element integration on a second stream, concurrently with the symbolic
  * phase; both are joined before the numeric phase.  overlap_on = 0 (or FEGPU_OVERLAP=0) makes the phases strictly serial,
