@@ -193,13 +193,6 @@ int32_t fegpu_create(fegpu_ctx **out, int32_t device) {
   cudaDeviceProp prop;
   CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
-  {  // stream-ordered allocator: never hand freed blocks back to the OS, so re-building a pattern costs no cudaMalloc
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      uint64_t thr = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-  }
   {  // the symbolic phase of a fresh assembly runs on this stream at the highest priority (see run_bilform)
     int lo = 0, hi = 0;
     CUDA_TRY(nullptr, cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -224,6 +217,7 @@ int32_t fegpu_destroy(fegpu_ctx *ctx) {
   if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->xfer) fe_transfer_free(ctx->xfer);
+  fe_dev_cache_destroy(ctx);
   delete ctx;
   return FEGPU_OK;
 }

@@ -27,6 +27,7 @@ struct fegpu_ctx {
   int sm_count = 148;
   std::string err;
   struct Transfer *xfer = nullptr;  // staging ring + host threads of the result transport (fegpu_transfer.cu), lazily built
+  struct BlockCache *blocks = nullptr;  // device-memory block cache of the symbolic phase (fegpu_blockcache.cu), lazily built
 };
 
 struct Pattern;  // fegpu_pattern.cu
@@ -139,9 +140,16 @@ int32_t fegpu_fail(fegpu_ctx *ctx, int32_t code, const std::string &msg);
 
 // FEGPU_TRACE=1: host wall-clock marks (microseconds since the previous mark) on stderr, to find host-side stalls
 void fe_trace(const char *label);
+bool fe_trace_on();
 #define FE_TRACE(label) fe_trace(label)
 
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// ---- device-memory block cache (fegpu_blockcache.cu): stream-ordered alloc / free without driver calls on the hot path
+int32_t fe_dev_alloc(fegpu_ctx *ctx, void **p, size_t bytes, cudaStream_t stream);
+void fe_dev_free(fegpu_ctx *ctx, void *p, cudaStream_t stream);  // p may be reused by work queued on `stream` from now on
+void fe_dev_cache_stats(fegpu_ctx *ctx, int64_t *hits, int64_t *misses, size_t *free_bytes);
+void fe_dev_cache_destroy(fegpu_ctx *ctx);
 
 // ---- primitives (fegpu_prims.cu) -----------------------------------------------------------------------
 // out[i] = sum_{k<i} in[k] (+ base); out may alias in for the int64 version.  n+1 entries are written when

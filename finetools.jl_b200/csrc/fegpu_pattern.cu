@@ -18,9 +18,12 @@
 // strictly increasing in a column, 1-based int64 colptr/rowval.
 #include <cstdlib>
 
+#include <cstdio>
+
 #include "fegpu_internal.h"
 
 struct Pattern {
+  fegpu_ctx *ctx = nullptr;
   int64_t nnz = 0, ncols = 0, nrows = 0;
   int64_t *d_colptr = nullptr;    // [ncols+1] 1-based
   int64_t *d_rowval = nullptr;    // [nnz] 1-based
@@ -41,7 +44,8 @@ struct Pattern {
   int ndn = 0;
   int64_t nnodes = 0;
   int maxdeg = 0, maxcand = 0, maxnbr = 0;
-  cudaStream_t stream = 0;
+  cudaStream_t stream = 0;        // consumer stream (the numeric phase and the transport read the arrays here)
+  cudaStream_t alloc_stream = 0;  // stream the arrays were allocated on (the build's); they are freed on it, see fe_pattern_free
   cudaEvent_t ready = nullptr;    // recorded when the build's last kernel is queued: the result transport may ship the pattern's
                                   // arrays while the integration and the numeric phase of the same call are still running
 };
@@ -940,19 +944,35 @@ __global__ void __launch_bounds__(GWPB * 32, 5) k_gather(const GatherParams G) {
     __syncwarp();
     if (RPL > 0) {
       for (int a0 = 0; a0 < maxdeg; a0 += GBATCH) {
+        // Compact layout: the block of (row node li, column node lc) is stored once, as block (min, max) with the entry
+        // (component i of min, component k of max) at k*ndn + i.  When li > lc the block is read in the SAME address order
+        // as an upper block (lane component fastest: neighbouring lanes read neighbouring words) and what the lane holds is
+        // then the transposed entry -- row component q, column component rp -- which only changes the accumulator index.
         double v[GBATCH][RMAX][QMAX];
+        int lcs[GBATCH];
 #pragma unroll
         for (int u = 0; u < GBATCH; u++) {
+          lcs[u] = 0;
           if (a0 + u < deg) {
             const long long bu = base[a0 + u];
             const double *Vb = G.V + (bu >> 6);
             const int lc = (int)(bu & 63);
+            lcs[u] = lc;
 #pragma unroll
             for (int j = 0; j < RMAX; j++)
               if (rok[j]) {
+                if (COMPACT) {
+                  const int li = rli[j];
+                  const int blk = (li <= lc) ? lc * (lc + 1) / 2 + li : li * (li + 1) / 2 + lc;
+                  const double *Bp = Vb + ndn * ndn * blk + rp[j];
 #pragma unroll
-                for (int q = 0; q < QMAX; q++)
-                  if (q < ndn) v[u][j][q] = Vb[elem_offset<COMPACT>(rli[j], rp[j], lc, q, ndn, EM)];
+                  for (int q = 0; q < QMAX; q++)
+                    if (q < ndn) v[u][j][q] = Bp[q * ndn];
+                } else {
+#pragma unroll
+                  for (int q = 0; q < QMAX; q++)
+                    if (q < ndn) v[u][j][q] = Vb[elem_offset<false>(rli[j], rp[j], lc, q, ndn, EM)];
+                }
               }
           }
         }
@@ -965,10 +985,14 @@ __global__ void __launch_bounds__(GWPB * 32, 5) k_gather(const GatherParams G) {
                 if (rok[j]) {
                   const unsigned s = cs[(a0 + u) * nne + rli[j]];
                   if (s != 0xffffu) {
-                    double *dst = acc + s * ndn + rp[j];
+                    // transposed block: v[q] is (row component q, column component rp); selects, not branches (the lanes
+                    // of a warp differ)
+                    const bool tr = COMPACT && rli[j] > lcs[u];
+                    double *dst = acc + (tr ? rp[j] * per_col + (int)s * ndn : (int)s * ndn + rp[j]);
+                    const int stride = tr ? 1 : per_col;
 #pragma unroll
                     for (int q = 0; q < QMAX; q++)
-                      if (q < ndn) dst[q * per_col] += v[u][j][q];
+                      if (q < ndn) dst[q * stride] += v[u][j][q];
                   }
                 }
             }
@@ -1033,12 +1057,11 @@ __global__ void k_vec_gather(int64_t nnodes, int nne, int ndn, const int64_t *__
   F[dof[(int64_t)p * nnodes + n]] = acc;
 }
 
+// every array of the symbolic phase comes from the context's block cache (fegpu_blockcache.cu)
 template <typename T>
 int32_t dalloc(fegpu_ctx *ctx, T **p, size_t n) {
   *p = nullptr;
-  if (n == 0) n = 1;
-  CUDA_TRY(ctx, cudaMallocAsync((void **)p, sizeof(T) * n, ctx->stream));
-  return FEGPU_OK;
+  return fe_dev_alloc(ctx, (void **)p, sizeof(T) * std::max<size_t>(n, 1), ctx->stream);
 }
 
 }  // namespace
@@ -1046,10 +1069,20 @@ int32_t dalloc(fegpu_ctx *ctx, T **p, size_t n) {
 void fe_pattern_free(Pattern *p) {
   if (!p) return;
   FE_TRACE("pattern_free: enter");
-  cudaStream_t st = p->stream;  // stream-ordered frees: blocks go back to the pool, no device synchronisation
+  // Stream-ordered frees into the context's block cache, no device synchronisation.  They are ordered on the stream the
+  // blocks were ALLOCATED on (the build stream), behind the last use on the consumer stream by an event: a rebuild allocates
+  // on that same stream again and gets the blocks back by plain stream order.
+  cudaStream_t st = p->alloc_stream;
+  if (p->stream != p->alloc_stream) {
+    if (!p->ready) cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming);
+    if (!p->ready || cudaEventRecord(p->ready, p->stream) != cudaSuccess || cudaStreamWaitEvent(st, p->ready, 0) != cudaSuccess) {
+      cudaGetLastError();
+      cudaDeviceSynchronize();
+    }
+  }
   void *ptrs[] = {p->d_colptr, p->d_rowval, p->d_adjptr, p->d_adj_slot, p->d_adj_lc, p->d_nnbr, p->d_nbrptr, p->d_cslot, p->d_rank, p->d_order, p->d_nbr};
   for (void *q : ptrs)
-    if (q) cudaFreeAsync(q, st);
+    if (q) fe_dev_free(p->ctx, q, st);
   if (p->ready) cudaEventDestroy(p->ready);
   delete p;
   FE_TRACE("pattern_free: done");
@@ -1077,7 +1110,9 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   if (dm->pat) { fe_pattern_free(dm->pat); dm->pat = nullptr; }
   Pattern *P = new Pattern();
   dm->pat = P;  // owned by the dofmap from here on (freed with it, also on error paths)
+  P->ctx = ctx;
   P->stream = st;
+  P->alloc_stream = st;
   P->ncols = dm->col_nall;
   P->nrows = dm->row_nall;
   const int64_t nn = mesh->nnodes;
@@ -1097,7 +1132,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   auto cleanup = [&]() {
     void *ptrs[] = {d_deg, d_arank, d_U, d_sorted, d_flags, d_aflag, d_anodes, d_apos, d_cls, d_clscnt};
     for (void *q : ptrs)
-      if (q) cudaFreeAsync(q, st);
+      if (q) fe_dev_free(ctx, q, st);
   };
   auto bail = [&]() {  // the mesh cannot use the structured path: free everything, the caller takes the sort path
     mesh->degenerate = true;
@@ -1109,6 +1144,12 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
 #define PT(expr) do { int32_t _s = (expr); if (_s != FEGPU_OK) { cleanup(); return _s; } } while (0)
 #define PC(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fegpu_fail(ctx, FEGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
   FE_TRACE("build: enter");
+  if (fe_trace_on()) {
+    int64_t hits = 0, misses = 0;
+    size_t fb = 0;
+    fe_dev_cache_stats(ctx, &hits, &misses, &fb);
+    std::fprintf(stderr, "[fegpu trace] block cache: %lld hits, %lld misses (driver allocations), %.2f GB cached\n", (long long)hits, (long long)misses, fb / 1e9);
+  }
   // node window of the active elements: every per-node pass below runs over [lo, hi) only
   const int64_t lo = mesh->win_lo, hi = mesh->win_hi, nw = hi - lo;
   PT(dalloc(ctx, &d_deg, nn));
@@ -1268,6 +1309,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
 #undef LAUNCH_NBR
   }
   ctx->launches++;
+  FE_TRACE("build: nbr kernel queued");
   PT(dalloc(ctx, &P->d_nbrptr, nn + 1));
   int64_t total_nbr = 0;
   PT(fe_exclusive_scan_i32_to_i64(ctx, P->d_nnbr + lo, P->d_nbrptr + lo, nw, 0, true, nullptr));

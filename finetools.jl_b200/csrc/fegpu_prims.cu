@@ -6,21 +6,16 @@
 #include <cstdio>
 #include <cstdlib>
 
-void fe_trace(const char *label) {
+bool fe_trace_on() {
   static const bool on = std::getenv("FEGPU_TRACE") && std::atoi(std::getenv("FEGPU_TRACE")) != 0;
-  if (!on) return;
+  return on;
+}
+
+void fe_trace(const char *label) {
+  if (!fe_trace_on()) return;
   static auto last = std::chrono::steady_clock::now();
   const auto now = std::chrono::steady_clock::now();
-  // the stream-ordered pool's footprint: growth between two steps means freed blocks were not reused
-  uint64_t reserved = 0, used = 0;
-  int dev = 0;
-  cudaMemPool_t pool;
-  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
-    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
-  }
-  std::fprintf(stderr, "[fegpu trace] %10.1f us  %-36s pool reserved %7.2f GB used %7.2f GB\n",
-               std::chrono::duration<double, std::micro>(now - last).count(), label, reserved / 1e9, used / 1e9);
+  std::fprintf(stderr, "[fegpu trace] %10.1f us  %s\n", std::chrono::duration<double, std::micro>(now - last).count(), label);
   last = std::chrono::steady_clock::now();
 }
 
@@ -122,7 +117,7 @@ int32_t scan_impl(fegpu_ctx *ctx, const TIN *d_in, int64_t *d_out, int64_t n, in
   }
   const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   int64_t *d_tiles = nullptr;  // ntiles sums, then scanned in place into ntiles+1 offsets
-  CUDA_TRY(ctx, cudaMallocAsync((void **)&d_tiles, sizeof(int64_t) * (size_t)(2 * ntiles + 2), st));
+  FE_TRY(fe_dev_alloc(ctx, (void **)&d_tiles, sizeof(int64_t) * (size_t)(2 * ntiles + 2), st));
   int64_t *d_sums = d_tiles, *d_offs = d_tiles + ntiles;  // offs has ntiles+1 entries
   k_scan_tiles<TIN><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(d_in, d_out, n, d_sums);
   ctx->launches++;
@@ -141,7 +136,7 @@ int32_t scan_impl(fegpu_ctx *ctx, const TIN *d_in, int64_t *d_out, int64_t n, in
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     *total_host = t + base;
   }
-  CUDA_TRY(ctx, cudaFreeAsync(d_tiles, st));
+  fe_dev_free(ctx, d_tiles, st);
   CUDA_TRY(ctx, cudaGetLastError());
   return FEGPU_OK;
 }
@@ -179,7 +174,7 @@ int32_t fe_max_i32_dev(fegpu_ctx *ctx, const int32_t *d_in, int64_t n, int32_t *
 int32_t fe_max_i32(fegpu_ctx *ctx, const int32_t *d_in, int64_t n, int32_t *max_host) {
   int32_t *d_m = nullptr;
   int32_t init = INT32_MIN;
-  CUDA_TRY(ctx, cudaMallocAsync((void **)&d_m, sizeof(int32_t), ctx->stream));
+  FE_TRY(fe_dev_alloc(ctx, (void **)&d_m, sizeof(int32_t), ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_m, &init, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   if (n > 0) {
     unsigned g = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8);
@@ -188,6 +183,6 @@ int32_t fe_max_i32(fegpu_ctx *ctx, const int32_t *d_in, int64_t n, int32_t *max_
   }
   CUDA_TRY(ctx, cudaMemcpyAsync(max_host, d_m, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  CUDA_TRY(ctx, cudaFreeAsync(d_m, ctx->stream));
+  fe_dev_free(ctx, d_m, ctx->stream);
   return FEGPU_OK;
 }

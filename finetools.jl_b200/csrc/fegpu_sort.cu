@@ -248,15 +248,17 @@ int32_t fe_morton_order(fegpu_mesh *mesh, const int32_t *d_nodes, int64_t n, int
   auto cleanup = [&]() {
     void *ptrs[] = {kA, kB, iA, iB, hist, offs};
     for (void *q : ptrs)
-      if (q) cudaFreeAsync(q, st);
+      if (q) fe_dev_free(ctx, q, st);
   };
 #define MC(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fegpu_fail(ctx, FEGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
-  MC(cudaMallocAsync((void **)&kA, sizeof(unsigned long long) * n, st));
-  MC(cudaMallocAsync((void **)&kB, sizeof(unsigned long long) * n, st));
-  MC(cudaMallocAsync((void **)&iA, sizeof(uint32_t) * n, st));
-  MC(cudaMallocAsync((void **)&iB, sizeof(uint32_t) * n, st));
-  MC(cudaMallocAsync((void **)&hist, sizeof(int32_t) * 256 * ntiles, st));
-  MC(cudaMallocAsync((void **)&offs, sizeof(int64_t) * (256 * ntiles + 1), st));
+#define MT(expr) do { int32_t _s = (expr); if (_s != FEGPU_OK) { cleanup(); return _s; } } while (0)
+  MT(fe_dev_alloc(ctx, (void **)&kA, sizeof(unsigned long long) * n, st));
+  MT(fe_dev_alloc(ctx, (void **)&kB, sizeof(unsigned long long) * n, st));
+  MT(fe_dev_alloc(ctx, (void **)&iA, sizeof(uint32_t) * n, st));
+  MT(fe_dev_alloc(ctx, (void **)&iB, sizeof(uint32_t) * n, st));
+  MT(fe_dev_alloc(ctx, (void **)&hist, sizeof(int32_t) * 256 * ntiles, st));
+  MT(fe_dev_alloc(ctx, (void **)&offs, sizeof(int64_t) * (256 * ntiles + 1), st));
+#undef MT
 #undef MC
   double s[3];
   for (int d = 0; d < 3; d++) {
