@@ -461,6 +461,7 @@ bool fe_integrate_supports_compact(const fegpu_mesh *mesh, const FormArgs &fa) {
 
 int32_t fe_integrate(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
   if (mesh->npts <= 0) return fegpu_fail(mesh->ctx, FEGPU_ERR_STATE, "no quadrature rule set (fegpu_rule_set)");
+  if (mesh->nactive <= 0) return FEGPU_OK;  // empty FESet, or a rank that owns no node: nothing to integrate
   if (fe_dot_scalar_applies(mesh, fa)) return fe_integrate_dot_scalar(mesh, fa, d_V);
   const bool rotated = fa.use_rm && (fa.form == FORM_DIFF_GEN || fa.form == FORM_ELASTIC);  // only the generic kernel knows Rm
   if (mesh->etype == FEGPU_H8 && !rotated) {

@@ -746,7 +746,9 @@ __global__ void k_col_counts(SymParams S, const int32_t *nnbr, int64_t lo, int64
 // puts fixed dofs last).  LPN lanes per node so a warp keeps 32/LPN dependent-load chains (node -> neighbour -> dof) in
 // flight; NDN compile-time (0 = runtime) so the (slot, component) decode needs no division.
 template <int LPN, int NDN>
-__global__ void __launch_bounds__(256) k_rows_sorted(SymParams S, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ nnbr,
+// vector fields: 32 registers and all 64 warps of an SM resident (the kernel waits on its node -> neighbour -> dof load chain:
+// 1.39 -> 1.22 ms on config 2); the scalar instantiations spill at 32 registers and were slower, they keep 40
+__global__ void __launch_bounds__(256, (NDN == 2 || NDN == 3) ? 8 : 6) k_rows_sorted(SymParams S, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ nnbr,
                                                      const int64_t *__restrict__ nbrptr, const int32_t *__restrict__ U,
                                                      const uint8_t *__restrict__ sorted_flag, const int64_t *__restrict__ colptr,
                                                      int64_t *__restrict__ rowval, uint16_t *__restrict__ rank, int32_t *__restrict__ nbr_compact) {
@@ -1361,7 +1363,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
     static const int lpn_env = std::getenv("FEGPU_ROWS_LPN") ? std::atoi(std::getenv("FEGPU_ROWS_LPN")) : 0;
     int rl = (ndn >= 3) ? 32 : (ndn == 2 ? 16 : 8);
     if (lpn_env == 8 || lpn_env == 16 || lpn_env == 32) rl = lpn_env;
-    const unsigned gr = grid_for(S.na * rl, 256);
+    const unsigned gr = std::max(1u, grid_for(S.na * rl, 256));  // S.na == 0: an empty FESet, or a rank without nodes
 #define ROWS_ARGS S, P->d_adjptr, P->d_nnbr, P->d_nbrptr, d_U, d_sorted, P->d_colptr, P->d_rowval, P->d_rank, P->d_nbr
 #define ROWS_L(N)                                                              \
   do {                                                                         \

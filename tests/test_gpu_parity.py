@@ -379,6 +379,37 @@ def test_partition_node_window_variants(fe, orc, gpu_ctx, variant):
     assert nnz_sum == ref[2].size
 
 
+@pytest.mark.parametrize("ndn", [1, 3])
+def test_empty_feset_and_rank_without_nodes(fe, orc, gpu_ctx, ndn):
+    """Edge cases of the mesh-structured path: (a) an FESet without elements -- the reference's startassembly!(…, 0, …) +
+    makematrix! gives sparse(Int[], Int[], Float64[], n, n): colptr all ones, no stored entry; (b) a rank that owns no node
+    (empty node window): the same empty block, and the other rank's block is then the whole matrix; (c) one single element."""
+    rule = fe.GaussRule(3, 2)
+    fens, fes = fe.H8block(1.0, 2.0, 3.0, 2, 2, 2)
+    u = make_field(fe, fens, ndn)
+    n = u.nalldofs()
+    form, coef = ("elastic", isotropic_C()) if ndn == 3 else ("diffusion", KAPPA3)
+    # (a)
+    got, a = gpu_csc(fe, form, fes.subset(np.arange(0)), fens, u, rule, coef)
+    np.testing.assert_array_equal(got[0], np.ones(n + 1, np.int64))
+    assert got[1].size == 0 and got[2].size == 0 and (got[3], got[4]) == (n, n)
+    cp, rv, nz = orc.sparse(np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0), n, n)
+    np.testing.assert_array_equal(got[0], cp)
+    # (b)
+    ref, _ = oracle_csc(orc, form, "H8", fes, fens, u, rule, coef)
+    owner = np.zeros(fens.count(), np.int32)
+    got1, _ = gpu_csc(fe, form, fes, fens, u, rule, coef, node_owner=owner, my_rank=1)
+    np.testing.assert_array_equal(got1[0], np.ones(n + 1, np.int64))
+    assert got1[1].size == 0 and got1[2].size == 0
+    got0, _ = gpu_csc(fe, form, fes, fens, u, rule, coef, node_owner=owner, my_rank=0)
+    assert_parity(ref, got0)
+    # (c)
+    one = fes.subset(np.arange(3, 4))
+    ref1, _ = oracle_csc(orc, form, "H8", one, fens, u, rule, coef)
+    gotc, _ = gpu_csc(fe, form, one, fens, u, rule, coef)
+    assert_parity(ref1, gotc)
+
+
 def _sampled_symmetry(colptr, rowval, nzval, cols):
     """K[i,j] == K[j,i] bit for bit on the entries of the sampled columns (binary search in the partner column)."""
     for j in cols:
