@@ -22,6 +22,7 @@ SIGNATURES = {
     "fegpu_set_async": (C.c_int32, [VP, C.c_int32]),
     "fegpu_set_overlap": (C.c_int32, [VP, C.c_int32]),
     "fegpu_synchronize": (C.c_int32, [VP]),
+    "fegpu_cache_release": (C.c_int32, [VP]),
     "fegpu_launch_count": (C.c_int64, [VP]),
     "fegpu_measure_peaks": (C.c_int32, [VP, c_f64p, c_f64p]),
     "fegpu_mesh_upload": (C.c_int32, [VP, C.c_int32, C.c_int64, VP, C.c_int64, C.c_int32, VP, C.POINTER(VP)]),

@@ -61,6 +61,10 @@ class GPUContext:
     def synchronize(self):
         check(_lib.lib().fegpu_synchronize(self.handle), self.handle)
 
+    def release_cache(self):
+        """Hand the device blocks cached by the symbolic phase back to the driver (results and handles stay valid)."""
+        check(_lib.lib().fegpu_cache_release(self.handle), self.handle)
+
     def launch_count(self):
         return int(_lib.lib().fegpu_launch_count(self.handle))
 

@@ -232,6 +232,12 @@ int32_t fegpu_set_async(fegpu_ctx *ctx, int32_t on) {
   ctx->async = on != 0;
   return FEGPU_OK;
 }
+int32_t fegpu_cache_release(fegpu_ctx *ctx) {
+  if (!ctx) return FEGPU_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  fe_dev_cache_trim(ctx);
+  return FEGPU_OK;
+}
 int32_t fegpu_synchronize(fegpu_ctx *ctx) {
   if (!ctx) return FEGPU_ERR_ARG;
   DeviceGuard g(ctx->device);

@@ -76,7 +76,8 @@ int32_t fe_dev_alloc(fegpu_ctx *ctx, void **p, size_t bytes, cudaStream_t stream
     return FEGPU_OK;
   }
   c->misses++;
-  if (c->free_bytes + bytes > c->limit) release_free_blocks(c);
+  // many meshes of different sizes through one context: do not let the list (linear scan) or the footprint grow without bound
+  if (c->free_bytes + bytes > c->limit || c->free_list.size() > 512) release_free_blocks(c);
   cudaError_t e = cudaMalloc(p, bytes);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -109,6 +110,10 @@ void fe_dev_cache_stats(fegpu_ctx *ctx, int64_t *hits, int64_t *misses, size_t *
   if (hits) *hits = c->hits;
   if (misses) *misses = c->misses;
   if (free_bytes) *free_bytes = c->free_bytes;
+}
+
+void fe_dev_cache_trim(fegpu_ctx *ctx) {
+  if (ctx->blocks) release_free_blocks(ctx->blocks);
 }
 
 void fe_dev_cache_destroy(fegpu_ctx *ctx) {

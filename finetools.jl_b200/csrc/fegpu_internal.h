@@ -149,6 +149,7 @@ static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + b
 int32_t fe_dev_alloc(fegpu_ctx *ctx, void **p, size_t bytes, cudaStream_t stream);
 void fe_dev_free(fegpu_ctx *ctx, void *p, cudaStream_t stream);  // p may be reused by work queued on `stream` from now on
 void fe_dev_cache_stats(fegpu_ctx *ctx, int64_t *hits, int64_t *misses, size_t *free_bytes);
+void fe_dev_cache_trim(fegpu_ctx *ctx);     // cudaFree every cached (free) block
 void fe_dev_cache_destroy(fegpu_ctx *ctx);
 
 // ---- primitives (fegpu_prims.cu) -----------------------------------------------------------------------

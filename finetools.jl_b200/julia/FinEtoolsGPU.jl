@@ -20,7 +20,7 @@ using FinEtools.DeforModelRedModule: DeforModelRed3D
 using FinEtools.CSysModule: csmat
 
 export SysmatAssemblerSparseGPU, SysmatAssemblerSparseSymmGPU, SysmatAssemblerSparseDiagGPU, SysmatAssemblerSparseHRZLumpingSymmGPU,
-    SysvecAssemblerGPU, gpu_matrix_blocked
+    SysvecAssemblerGPU, gpu_matrix_blocked, gpu_release_cache
 
 const LIB = get(ENV, "FEGPU_LIB", joinpath(@__DIR__, "..", "libfinegpu.so"))
 
@@ -213,6 +213,14 @@ function _device(self::FEMMBase, a, geom, u)   # a: SysmatAssemblerSparseGPU or 
     end
     return mh, dh
 end
+
+"""
+    gpu_release_cache(assembler)
+
+Hand the device blocks that the symbolic phase keeps for re-use (pattern arrays, temporaries) back to the CUDA driver, e.g. before
+another library needs the memory.  Results and cached patterns stay valid.
+"""
+gpu_release_cache(a) = (_check(ccall((:fegpu_cache_release, LIB), Int32, (Ptr{Cvoid},), a.ctx), a.ctx); a)
 
 # A form call only queues its device work when the result is fetched right after (makematrix! synchronises): the transport
 # then ships the pattern's arrays, and the host threads rebuild rowval, while the integration and the numeric phase still run.

@@ -65,6 +65,10 @@ int32_t fegpu_set_async(fegpu_ctx *ctx, int32_t async_on);
  * which is what per-kernel timings (fegpu_last_timings) should be taken with.  Default: on.                  */
 int32_t fegpu_set_overlap(fegpu_ctx *ctx, int32_t overlap_on);
 int32_t fegpu_synchronize(fegpu_ctx *ctx);
+/* The symbolic phase keeps every device block it frees (pattern arrays, temporaries) in a per-context cache so that rebuilding
+ * a pattern makes no driver allocation call.  This hands the cached blocks back to the driver (after a device
+ * synchronisation), e.g. before another library needs the memory; handles and their results stay valid.               */
+int32_t fegpu_cache_release(fegpu_ctx *ctx);
 /* number of CUDA kernels this context has launched so far (bench.py's gpu_launches)                     */
 int64_t fegpu_launch_count(fegpu_ctx *ctx);
 /* roofline denominators measured by the library itself: FP64 FMA peak (TFLOP/s) and copy bandwidth (GB/s) */

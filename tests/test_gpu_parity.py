@@ -410,6 +410,30 @@ def test_empty_feset_and_rank_without_nodes(fe, orc, gpu_ctx, ndn):
     assert_parity(ref1, gotc)
 
 
+def test_block_cache_release_keeps_results_valid(fe, orc, gpu_ctx):
+    """fegpu_cache_release hands the symbolic phase's cached device blocks back to the driver: the resident result, the cached
+    pattern and later fresh assemblies (which allocate anew) are unaffected, bit for bit."""
+    fens, fes = fe.H8block(1.0, 1.0, 1.0, 5, 4, 3)
+    u = make_field(fe, fens, 3)
+    rule = fe.GaussRule(3, 2)
+    ref, _ = oracle_csc(orc, "elastic", "H8", fes, fens, u, rule, isotropic_C())
+    got, a = gpu_csc(fe, "elastic", fes, fens, u, rule, isotropic_C())
+    assert_parity(ref, got)
+    a.ctx.release_cache()
+    again = a._fetch(True)                       # the resident CSC is still there
+    np.testing.assert_array_equal(again[1], got[1])
+    np.testing.assert_array_equal(again[2], got[2])
+    got2, _ = gpu_csc(fe, "elastic", fes, fens, u, rule, isotropic_C(), assembler=a)   # cached pattern
+    assert a.pattern_was_cached()
+    np.testing.assert_array_equal(got2[2], got[2])
+    a.invalidate_patterns()
+    a.ctx.release_cache()
+    got3, _ = gpu_csc(fe, "elastic", fes, fens, u, rule, isotropic_C(), assembler=a)   # fresh build from an empty cache
+    assert not a.pattern_was_cached()
+    assert_parity(ref, got3)
+    np.testing.assert_array_equal(got3[2], got[2])
+
+
 def _sampled_symmetry(colptr, rowval, nzval, cols):
     """K[i,j] == K[j,i] bit for bit on the entries of the sampled columns (binary search in the partner column)."""
     for j in cols:
