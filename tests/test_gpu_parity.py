@@ -434,6 +434,46 @@ def test_block_cache_release_keeps_results_valid(fe, orc, gpu_ctx):
     np.testing.assert_array_equal(got3[2], got[2])
 
 
+@pytest.mark.parametrize("et,ndn,form", [("H8", 3, "elastic"), ("T10", 1, "dot"), ("H20", 1, "diffusion"), ("T4", 3, "elastic")])
+def test_scrambled_mesh_numbering_parity(fe, orc, gpu_ctx, et, ndn, form):
+    """Nothing in the path may lean on the block generators' numbering: the nodes are renumbered by a random permutation, the
+    elements shuffled, and the dof numbers are an arbitrary permutation of 1..nalldofs (a3 of SURVEY 8: "arbitrary
+    permutation") -- no locality, no node-major order, every column needs the sorted-rows path.  Whole matrix and a 3-way
+    partition by recursive inertial bisection (owner map without locality in the node ids: the node window is everything)."""
+    rng = np.random.default_rng(7)
+    fens, fes = _mesh(fe, et, 3 if et in ("H8", "T4") else 2)
+    _distort(fens)
+    nn = fens.count()
+    perm = rng.permutation(nn)                      # old node i becomes node perm[i]
+    xyz = np.empty_like(fens.xyz)
+    xyz[perm] = fens.xyz
+    conn = perm[fes.conn - 1] + 1
+    conn = np.ascontiguousarray(conn[rng.permutation(conn.shape[0])])
+    fens2, fes2 = fe.FENodeSet(xyz), type(fes)(conn)
+    u = fe.NodalField(np.zeros((nn, ndn)))
+    u.dofnums[:] = (rng.permutation(nn * ndn) + 1).reshape(nn, ndn)
+    u._dofver += 1
+    rule = _rule(fe, et)
+    coef = {"elastic": isotropic_C(), "dot": np.array([[1.0]]), "diffusion": KAPPA3}[form]
+    ref, _ = oracle_csc(orc, form, et, fes2, fens2, u, rule, coef)
+    got, _ = gpu_csc(fe, form, fes2, fens2, u, rule, coef)
+    assert_parity(ref, got)
+    n = u.nalldofs()
+    owner = np.asarray(fe.pointpartitioning(fens2.xyz, 3) - 1, dtype=np.int32)
+    nnz_sum = 0
+    for p in range(int(owner.max()) + 1):
+        keep = np.zeros(n, bool)
+        keep[(u.dofnums[owner == p] - 1).reshape(-1)] = True
+        blk = _row_block(ref, keep, n)
+        gotp, _ = gpu_csc(fe, form, fes2, fens2, u, rule, coef, node_owner=owner, my_rank=p)
+        np.testing.assert_array_equal(gotp[0], blk[0])
+        np.testing.assert_array_equal(gotp[1], blk[1])
+        if blk[2].size:
+            assert np.abs(gotp[2] - blk[2]).max() <= 1e-12 * np.abs(ref[2]).max()
+        nnz_sum += gotp[2].size
+    assert nnz_sum == ref[2].size
+
+
 def _sampled_symmetry(colptr, rowval, nzval, cols):
     """K[i,j] == K[j,i] bit for bit on the entries of the sampled columns (binary search in the partner column)."""
     for j in cols:
