@@ -54,6 +54,9 @@ namespace {
 
 constexpr int WPB = 4;  // warps per block in the per-node symbolic kernels
 constexpr int GWPB = 8; // warps per block in the gather
+#ifndef GATHER_MIN_CTAS
+#define GATHER_MIN_CTAS 5  // 48 registers; 6 (40 registers, small spills) was measured: config 2 gather 3.32 -> 4.67 ms, config 4 unchanged
+#endif
 // GBATCH (template): adjacent elements whose loads are in flight together (k_gather, one-value-per-lane path)
 
 struct SymParams {
@@ -874,7 +877,7 @@ __device__ __forceinline__ int elem_offset(int li, int p, int lc, int q, int ndn
 // next node / the column bases fetched early.
 // Shared per node group: acc[maxnbr*ndn*ndn] doubles | base[maxdeg] int64 | cs[maxcand] uint16 (padded to 8 B)
 template <int LPN, int NDN, bool COMPACT, int GBATCH, int RPL>
-__global__ void __launch_bounds__(GWPB * 32, 5) k_gather(const GatherParams G) {
+__global__ void __launch_bounds__(GWPB * 32, GATHER_MIN_CTAS) k_gather(const GatherParams G) {
   extern __shared__ double sacc[];
   constexpr int NPW = 32 / LPN;
   constexpr int QMAX = (NDN > 0) ? NDN : 6;
