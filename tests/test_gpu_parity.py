@@ -550,6 +550,58 @@ def test_full_size_config4_properties(fe, gpu_ctx):
     assert nnz_blocks == nzval.size
 
 
+def test_config5_mixed_surface_volume_properties(fe, gpu_ctx):
+    """BASELINE config 5 (mixed surface / volume run), one rank's share of it: H20 elasticity (GaussRule(3,3), the register-tiled
+    lane-per-tile kernel) on a 40^3 block, and the boundary mass of the FULL 96^3 skins (Q4 GaussRule(2,2), T3 TriRule(3),
+    m = 2).  Size-independent properties: nnz of the serendipity pattern 9 (234 n^3 + 141 n^2 + 24 n + 1),
+    rows ascending, exact symmetry, rigid translations in the null space, a 4-way slab partition's blocks adding up to nnz;
+    the skin mass matrices sum to the surface area 6."""
+    import scipy.sparse as sp
+    n = 40
+    fens, fes = fe.H20block(1.0, 1.0, 1.0, n, n, n)
+    u = make_field(fe, fens, 3)
+    rule = fe.GaussRule(3, 3)
+    a = fe.SysmatAssemblerSparseGPU(0.0)
+    femm = fe.FEMMBase(fe.IntegDomain(fes, rule))
+    geom = fe.NodalField(fens.xyz)
+    colptr, rowval, nzval, m_, n_ = fe.bilform_lin_elastic(femm, a, geom, u, fe.DeforModelRed3D, fe.DataCache(isotropic_C()), raw=True)
+    assert nzval.size == 9 * (234 * n ** 3 + 141 * n ** 2 + 24 * n + 1) and m_ == n_ == 3 * fens.count()
+    d = np.diff(rowval)
+    d[colptr[1:-1] - 2] = 1
+    assert np.all(d > 0)
+    del d
+    K = sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(m_, n_))
+    scale = np.abs(nzval).max()
+    for comp in range(3):
+        v = np.zeros(m_)
+        v[u.dofnums[:, comp] - 1] = 1.0
+        assert np.abs(K @ v).max() <= 1e-10 * scale
+    del K
+    _sampled_symmetry(colptr, rowval, nzval, np.arange(0, n_, 50021))
+    owner = fe.slab_owner(fens.count(), 4)
+    a.setnomatrixresult(True)
+    nnz_blocks = 0
+    for p in range(4):
+        fe.bilform_lin_elastic(femm, a, geom, u, fe.DeforModelRed3D, fe.DataCache(isotropic_C()), raw=True, node_owner=owner, my_rank=p)
+        nnz_blocks += a.sizes()[2]
+    assert nnz_blocks == nzval.size
+    del colptr, rowval, nzval
+    # the skins at BASELINE size
+    nb = 96
+    for mesher, srule in ((fe.H8block, fe.GaussRule(2, 2)), (fe.T4block, fe.TriRule(3))):
+        vf, vol = mesher(1.0, 1.0, 1.0, nb, nb, nb)
+        skin = fe.meshboundary(vol)
+        psi = make_field(fe, vf, 1)
+        sa = fe.SysmatAssemblerSparseGPU(0.0)
+        sfemm = fe.FEMMBase(fe.IntegDomain(skin, srule))
+        cp, rv, nz, sm, sn = fe.bilform_dot(sfemm, sa, fe.NodalField(vf.xyz), psi, fe.DataCache(np.array([[1.0]])), m=2, raw=True)
+        assert sm == sn == vf.count() and cp[-1] == nz.size + 1
+        assert abs(nz.sum() - 6.0) <= 1e-9
+        on_skin = np.unique(skin.conn) - 1
+        cols = np.diff(cp)
+        assert np.count_nonzero(cols) == on_skin.size and np.all(cols[psi.dofnums[on_skin, 0] - 1] > 0)
+
+
 def test_full_size_config3_t10_mass_cached_reassembly(fe, gpu_ctx):
     """BASELINE config 3: consistent mass on a distorted T10 block (100^3 cells, 6 M quadratic tets), TetRule(4), then
     re-assembly on the cached pattern after the geometry moved.  1'M1 = sum of the tet volumes (straight-edged T10)."""
