@@ -138,3 +138,57 @@ def test_golden_fixtures_against_oracle(orc, fe):
         np.testing.assert_array_equal(cp, g["colptr"])
         np.testing.assert_array_equal(rv, g["rowval"])
         assert np.abs(nz - g["nzval"]).max() <= 1e-15 * np.abs(g["nzval"]).max()
+
+
+def _julia_ccalls(src):
+    """Every `ccall((:name, LIB), Ret, (T1, T2, ...), args...)` of the Julia shim: (name, return type, [argument types])."""
+    import re
+    out = []
+    for m in re.finditer(r"ccall\(\(:(\w+),\s*LIB\),\s*(\w+),\s*\(", src):
+        i, depth = m.end(), 1
+        while depth:  # balanced scan of the argument-type tuple
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        tup = src[m.end():i - 1]
+        parts, depth, cur = [], 0, ""
+        for ch in tup:
+            if ch == "," and depth == 0:
+                parts.append(cur.strip())
+                cur = ""
+            else:
+                depth += {"{": 1, "}": -1}.get(ch, 0)
+                cur += ch
+        if cur.strip():
+            parts.append(cur.strip())
+        out.append((m.group(1), m.group(2), parts))
+    return out
+
+
+def test_julia_shim_ccalls_match_the_abi(fe):
+    """The Julia shim cannot be executed here (no julia on the image), so its FFI layer is checked statically: every ccall
+    names a symbol of include/fegpu.h and passes the right number and kind of arguments (pointer / Int32 / Int64 / Float64),
+    judged against the ctypes table that the header test pins and the GPU tests exercise."""
+    import ctypes as C
+    from finetools_jl_b200 import _lib
+    src = open(os.path.join(ROOT, "finetools.jl_b200", "julia", "FinEtoolsGPU.jl")).read()
+    calls = _julia_ccalls(src)
+    assert len(calls) >= 35
+    kind_c = {C.c_int32: "i32", C.c_int64: "i64", C.c_double: "f64"}
+    kind_jl = {"Int32": "i32", "Cint": "i32", "Int64": "i64", "Float64": "f64", "Cdouble": "f64"}
+    ret_jl = {"Int32": C.c_int32, "Int64": C.c_int64, "Cstring": C.c_char_p, "Ptr{UInt8}": C.c_char_p}
+    seen = set()
+    for name, ret, args in calls:
+        assert name in _lib.SIGNATURES, "Julia shim calls unknown symbol %s" % name
+        restype, argtypes = _lib.SIGNATURES[name]
+        assert ret_jl.get(ret) is restype, "%s: return type %s" % (name, ret)
+        assert len(args) == len(argtypes), "%s: %d arguments in the shim, %d in the ABI" % (name, len(args), len(argtypes))
+        for k, (a, t) in enumerate(zip(args, argtypes)):
+            want = kind_c.get(t, "ptr")
+            got = "ptr" if a.startswith(("Ptr{", "Ref{")) else kind_jl.get(a)
+            assert got == want, "%s: argument %d is %s in the shim, %s in the ABI" % (name, k + 1, a, want)
+        seen.add(name)
+    # the path's own entry points are all bound by the shim
+    for must in ("fegpu_create", "fegpu_mesh_upload", "fegpu_dofmap_upload", "fegpu_rule_set", "fegpu_bilform_diffusion",
+                 "fegpu_bilform_lin_elastic", "fegpu_bilform_dot", "fegpu_startassembly", "fegpu_assemble", "fegpu_makematrix",
+                 "fegpu_makematrix_sizes", "fegpu_makematrix_copy", "fegpu_set_async", "fegpu_cache_release"):
+        assert must in seen, must
