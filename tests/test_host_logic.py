@@ -192,3 +192,40 @@ def test_julia_shim_ccalls_match_the_abi(fe):
                  "fegpu_bilform_lin_elastic", "fegpu_bilform_dot", "fegpu_startassembly", "fegpu_assemble", "fegpu_makematrix",
                  "fegpu_makematrix_sizes", "fegpu_makematrix_copy", "fegpu_set_async", "fegpu_cache_release"):
         assert must in seen, must
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) prints exactly one JSON line with the keys of
+    the contract; a non-zero rank under torchrun prints nothing and exits 0.  Tiny sample so the test takes a second."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3", "--ref-edge", "6",
+           "--ref-threads", "2", "--gpus", "2"]
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "elements/s" and d["higher_is_better"] is True and d["n_gpus"] == 2
+    assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 3 and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 2 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["gpu_launches"] == 0
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_bench_gpu_arm_refuses_to_run_without_a_device():
+    """No CPU fallback anywhere on the measured path: without a CUDA device the GPU arm of bench.py exits with an error instead
+    of timing something else.  (Skipped on a GPU box, where the arm would really run.)"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode != 0
+    assert "no CPU fallback" in (out.stderr + out.stdout)
+    assert not [ln for ln in out.stdout.splitlines() if ln.strip().startswith("{")]
