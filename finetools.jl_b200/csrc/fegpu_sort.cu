@@ -260,16 +260,25 @@ int32_t fe_morton_order(fegpu_mesh *mesh, const int32_t *d_nodes, int64_t n, int
   MT(fe_dev_alloc(ctx, (void **)&offs, sizeof(int64_t) * (256 * ntiles + 1), st));
 #undef MT
 #undef MC
+  // FEGPU_GATHER_ORDER_BITS (1..10, default 10): resolution of the Morton grid per axis.  The sort is a stable LSD radix sort,
+  // so with a coarse grid the nodes of a cell keep their natural (ascending id) order -- bricks of nodes visited one after the
+  // other, each walked in the mesh's own numbering -- and the sort needs ceil(3 bits / 8) passes instead of four.
+  static const int bits = [] {
+    const char *e = std::getenv("FEGPU_GATHER_ORDER_BITS");
+    const int b = e ? std::atoi(e) : 10;
+    return (b >= 1 && b <= 10) ? b : 10;
+  }();
   double s[3];
   for (int d = 0; d < 3; d++) {
     const double ext = mesh->bbox_hi[d] - mesh->bbox_lo[d];
-    s[d] = ext > 0 ? 1023.999 / ext : 0.0;
+    s[d] = ext > 0 ? ((double)(1 << bits) - 0.001) / ext : 0.0;
   }
   k_morton_keys<<<grid_for(n, 256), 256, 0, st>>>(mesh->d_xyz, mesh->nnodes, d_nodes, n, mesh->sdim, mesh->bbox_lo[0], mesh->bbox_lo[1], mesh->bbox_lo[2], s[0], s[1], s[2], kA, iA);
   ctx->launches++;
   unsigned long long *kin = kA, *kout = kB;
   uint32_t *iin = iA, *iout = iB;
-  const std::vector<int> shifts = {0, 8, 16, 24};
+  std::vector<int> shifts;
+  for (int sh = 0; sh < 3 * bits; sh += 8) shifts.push_back(sh);
   int32_t rc = radix_sort_pairs(ctx, n, shifts, &kin, &kout, &iin, &iout, hist, offs);
   if (rc == FEGPU_OK) {
     k_ids_to_i32<<<grid_for(n, 256), 256, 0, st>>>(iin, d_order, n);
