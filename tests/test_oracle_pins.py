@@ -384,3 +384,69 @@ def test_sibling_form_identities_of_the_reference(orc, fe):
     assert abs(np.ones(nq) @ (K @ Q) - (0.3 * 3.1 + 0.4 * -2.7 + 0.5 * 0.4) * W * L * t) / (W * L * t) <= 1.0e-5
     F = orc.linform_dot("H8", fes.conn, x, q.dofnums, nq, rule.param_coords, rule.weights, [11.0])
     assert abs(F.sum() - L * W * t * 11.0) / 667 <= 1.0e-5
+
+
+def _assemble_blocks(orc, blocks, nrows, ncols, cap=64):
+    L = orc.lib()
+    I, J, V = np.zeros(cap, np.int64), np.zeros(cap, np.int64), np.zeros(cap)
+    p = np.zeros(1, np.int64)
+    for m, dr, dc in blocks:
+        m = np.asarray(m, dtype=np.float64)
+        rc = L.orc_assemble(I, J, V, p, np.ascontiguousarray(m.T).reshape(-1), np.asarray(dr, np.int64), len(dr),
+                            np.asarray(dc, np.int64), len(dc), nrows, ncols)
+        assert rc == 0
+    n = int(p[0])
+    return I[:n], J[:n], V[:n]
+
+
+RECT_M1 = [[0.24406, 0.599773, 0.833404, 0.0420141], [0.786024, 0.00206713, 0.995379, 0.780298], [0.845816, 0.198459, 0.355149, 0.224996]]
+RECT_M2 = [[0.146618, 0.53471, 0.614342, 0.737833], [0.479719, 0.41354, 0.00760941, 0.836455], [0.254868, 0.476189, 0.460794, 0.00919633],
+           [0.159064, 0.261821, 0.317078, 0.77646], [0.643538, 0.429817, 0.59788, 0.958909]]
+
+
+def test_assembler_rectangular_blocks_kat(orc):
+    """test/test_basics.jl:1465-1496: a 3x4 and a 5x4 block with different row and column dof lists into a 7x7 matrix; the result
+    equals the dense scatter-add refa[rows, cols] += m (tolerance of the reference's test: 1e-5; here exact up to one rounding)."""
+    blocks = [(RECT_M1, [1, 7, 5], [5, 2, 1, 4]), (RECT_M2, [2, 3, 1, 4, 5], [6, 7, 3, 4])]
+    refa = np.zeros((7, 7))
+    for m, dr, dc in blocks:
+        refa[np.ix_(np.array(dr) - 1, np.array(dc) - 1)] += np.array(m)
+    I, J, V = _assemble_blocks(orc, blocks, 7, 7)
+    assert I.size == 12 + 20
+    # emission order of assemble! (AssemblyModule.jl:261-280): column by column, rows inner
+    assert list(I[:3]) == [1, 7, 5] and list(J[:3]) == [5, 5, 5] and V[1] == 0.786024
+    cp, rv, nz = orc.sparse(I, J, V, 7, 7)
+    A = orc.to_scipy(cp, rv, nz, 7, 7).toarray()
+    assert np.abs(refa - A).max() < 1e-15
+    assert nz.size == np.count_nonzero(refa) == 12 + 20 - 2   # (1,4) and (5,4) are hit by both blocks
+
+
+def test_assembler_nomatrixresult_flow_kat(orc):
+    """test/test_basics.jl:1580-1608: the second block goes to rows [2 3 1 7 5]; the reference pins five entries of the matrix built
+    after `setnomatrixresult(a, false)`: A[1,1] = 0.833404, A[5,1] = 0.355149, A[7,6] = 0.159064, A[3,7] = 0.41354, A[7,7] = 0.261821."""
+    blocks = [(RECT_M1, [1, 7, 5], [5, 2, 1, 4]), (RECT_M2, [2, 3, 1, 7, 5], [6, 7, 3, 4])]
+    I, J, V = _assemble_blocks(orc, blocks, 7, 7)
+    cp, rv, nz = orc.sparse(I, J, V, 7, 7)
+    A = orc.to_scipy(cp, rv, nz, 7, 7).toarray()
+    for (i, j), v in {(1, 1): 0.833404, (5, 1): 0.355149, (7, 6): 0.159064, (3, 7): 0.41354, (7, 7): 0.261821}.items():
+        assert abs(A[i - 1, j - 1] - v) <= 1e-12, (i, j)
+
+
+def test_assembler_rectangular_blocks_golden_matrix(orc):
+    """test/test_miscellaneous.jl:1944-1976: the same two rectangular blocks (rows [1 7 5] / [2 3 1 7 5]) against the full 7x7
+    golden matrix of the reference's test (5 significant digits, tolerance 1e-5 as there; note that the reference's check is
+    one-sided, maximum(G - A) < 1e-5 -- here both signs)."""
+    G = np.array([[0.833404, 0.599773, 0.460794, 0.0512104, 0.24406, 0.254868, 0.476189],
+                  [0.0, 0.0, 0.614342, 0.737833, 0.0, 0.146618, 0.53471],
+                  [0.0, 0.0, 0.00760941, 0.836455, 0.0, 0.479719, 0.41354],
+                  [0.0] * 7,
+                  [0.355149, 0.198459, 0.59788, 1.1839, 0.845816, 0.643538, 0.429817],
+                  [0.0] * 7,
+                  [0.995379, 0.00206713, 0.317078, 1.55676, 0.786024, 0.159064, 0.261821]])
+    blocks = [(RECT_M1, [1, 7, 5], [5, 2, 1, 4]), (RECT_M2, [2, 3, 1, 7, 5], [6, 7, 3, 4])]
+    I, J, V = _assemble_blocks(orc, blocks, 7, 7)
+    cp, rv, nz = orc.sparse(I, J, V, 7, 7)
+    A = orc.to_scipy(cp, rv, nz, 7, 7).toarray()
+    assert np.abs(G - A).max() < 1.0e-5
+    # the three entries hit by both blocks are sums in assembly order: (1,4), (5,4), (7,4)
+    assert A[0, 3] == 0.0420141 + 0.00919633 and A[4, 3] == 0.224996 + 0.958909 and A[6, 3] == 0.780298 + 0.77646
