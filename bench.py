@@ -1,21 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- elements/s assembled into CSC on B200 (BASELINE.json metric).
+"""bench.py -- elements/s assembled into CSC on B200 (BASELINE.json metric), strong scaling over 1/2/4/8 GPUs.
 
-Workload (N = 1): BASELINE.json configs[1] -- bilform_lin_elastic on a 128^3 H8 block (2 097 152 elements, 24x24 element
-matrices, 1 207 959 552 triplets, nnz = 9*385^3 = 513 599 625), GaussRule(3,2), isotropic C (E = 1, nu = 0.3).
-N > 1 (weak scaling): the block grows to 128 x 128 x 128N elements and is split into N node-owned row blocks (z-slabs,
-contiguous node ranges); every rank integrates the elements touching its nodes (halo recomputed) and builds the CSC of
-its rows; no collective on the data path.
+Headline workload: BASELINE.json configs[3], the north-star target -- bilform_diffusion (kappa 3x3) on a 256^3 H8 block
+(16 777 216 elements, 64 triplets each, nnz = 769^3 = 454 756 609), GaussRule(3,2).  With N GPUs the SAME mesh is split into
+N node-owned row blocks (z-slabs = contiguous node ranges); every rank integrates the elements that touch one of its nodes
+(halo recomputed) and builds the CSC of its rows; there is no collective on the data path (scaling: "strong").
 
-A "step" is one complete fresh assembly: element integration -> triplet values -> symbolic pattern -> CSC gather-sum.
-The sparsity-pattern cache is INVALIDATED before every timed step so no work is skipped; the cached re-assembly rate is
-reported separately under "cached".
+A "step" is one complete fresh assembly of the rank's block: symbolic phase (node -> element adjacency, neighbour lists,
+colptr / rowval) -> element integration -> numeric gather-sum into nzval.  The sparsity-pattern cache is INVALIDATED before
+every timed step, so no work is skipped; the cached re-assembly rate is reported separately under "cached".
 
-  value  : inputs resident in HBM, CUDA-event time over K steps (max over ranks)
-  e2e    : same step through the public Python API (the reference's call shape) with host buffers: coordinates go
-           host->device and colptr/rowval/nzval come back device->host inside the timed region
+  value  : inputs resident in HBM, CUDA-event time over K steps, max over ranks
+  e2e    : the same step through the public API (the reference's call shape) with HOST buffers: coordinates go host -> device
+           and colptr / rowval / nzval come back device -> host inside the timed region (pinned result arrays; the pageable
+           figure a shim without page-locked buffers gets is reported beside it)
+  config2: BASELINE configs[1] (128^3 H8 bilform_lin_elastic) measured the same way, as a secondary block of the line
   --impl reference : the CPU oracle (C restatement of FinEtools.jl's serial path; Julia is not available) on a bounded
-           sample of the same workload
+           sample of the headline workload
 """
 import argparse
 import json
@@ -31,16 +32,9 @@ _emit = None
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "elements/s assembled into CSC (H8 lin_elastic stiffness, fresh assembly incl. pattern build)"
+METRIC = "elements/s assembled into CSC (H8 diffusion stiffness, fresh assembly incl. pattern build)"
 UNIT = "elements/s"
-N_EDGE = 128
-FLOPS_PER_ELEM = 51936          # H8 lin_elastic as the reference executes it (incl. the structural zeros of B)
-FLOPS_EXECUTED_PER_ELEM = 24168  # what k_h8_elastic executes: 8 points x (333 geometry + 4 x 672 block) flops, zeros of B skipped
-COMPACT_VALUES = 324            # doubles per element actually stored: the 36 upper 3x3 blocks (symmetric form), not 576
-# compulsory bytes of THIS implementation (smaller than SURVEY 8(d)'s 16 B/triplet figures because keys are
-# never materialised and only the upper block triangle is stored, so frac cannot exceed 1 by accounting)
-BYTES_INTEGRATE = 32 + 8 * COMPACT_VALUES + 49      # int32 conn + values + amortised node data
-BYTES_GATHER_PER_ELEM = 8 * COMPACT_VALUES + 2 * 64  # values read once + 2-byte slot table (64 candidates per node ~ per element)
+KAPPA3 = np.array([[1.5, 0.2, 0.1], [0.2, 2.5, 0.3], [0.1, 0.3, 3.5]])
 
 
 def isotropic_C(E=1.0, nu=0.3):
@@ -51,6 +45,20 @@ def isotropic_C(E=1.0, nu=0.3):
     C[np.arange(3), np.arange(3)] += 2 * mu
     C[3:, 3:] = mu * np.eye(3)
     return C
+
+
+# Per-element figures of the two workloads.
+#   flops_ref   : SURVEY.md 8(a), counted as the reference's loops execute
+#   flops_exec  : FP64 operations the integration kernel executes per element (FMA = 2), from its SASS
+#   vals        : doubles stored per element (compact upper block triangle of the symmetric element matrix)
+# Compulsory bytes of THIS implementation are below SURVEY 8(d)'s 16 B / triplet figures (no keys, int32 indices, upper block
+# triangle only), so every fraction is reported against the implementation's own compulsory traffic.
+WORKLOADS = {
+    "c4": dict(label="BASELINE configs[3]: bilform_diffusion (kappa 3x3), H8 block", edge=256, ndn=1, form="diffusion",
+               flops_ref=6816, flops_exec=5600, vals=36, kernel="k_h8_diffusion"),
+    "c2": dict(label="BASELINE configs[1]: bilform_lin_elastic (isotropic C), H8 block", edge=128, ndn=3, form="elastic",
+               flops_ref=51936, flops_exec=25128, vals=324, kernel="k_h8_elastic"),
+}
 
 
 class ClockSampler:
@@ -105,38 +113,40 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_run(n_edge, threads):
-    """One assembly of an n_edge^3 H8 elasticity block with the CPU oracle.  threads == 1 is the reference's own serial
-    path; threads > 1 shards the ELEMENT LOOP over threads writing disjoint slices of one COO buffer (what
-    FinEtoolsMultithreading does for the reference) and keeps the serial sparse()."""
+def cpu_reference_run(n_edge, threads, form="diffusion"):
+    """One assembly of an n_edge^3 H8 block with the CPU oracle.  threads == 1 is the reference's own serial path; threads > 1
+    shards the ELEMENT LOOP over threads writing disjoint slices of one COO buffer (what FinEtoolsMultithreading does for
+    the reference) and keeps the serial sparse()."""
     import finetools_jl_b200 as fe   # host-side mesh generator only
     from oracle import oracle as orc
     fens, fes = fe.H8block(1.0, 1.0, 1.0, n_edge, n_edge, n_edge)
-    u = fe.NodalField(np.zeros((fens.count(), 3)))
+    ndn = 1 if form == "diffusion" else 3
+    u = fe.NodalField(np.zeros((fens.count(), ndn)))
     fe.numberdofs(u)
     rule = fe.GaussRule(3, 2)
-    C = isotropic_C()
+    coef = KAPPA3 if form == "diffusion" else isotropic_C()
+    fn = orc.bilform_diffusion_coo if form == "diffusion" else orc.bilform_lin_elastic_coo
     nall = u.nalldofs()
     nel = fes.count()
+    em2 = (8 * ndn) ** 2
     t0 = time.perf_counter()
     if threads <= 1:
-        I, J, V = orc.bilform_lin_elastic_coo("H8", fes.conn, fens.xyz, u.dofnums, nall, rule.param_coords, rule.weights, C)
+        I, J, V = fn("H8", fes.conn, fens.xyz, u.dofnums, nall, rule.param_coords, rule.weights, coef)
     else:
         from concurrent.futures import ThreadPoolExecutor
-        nt = nel * 576
+        nt = nel * em2
         I, J, V = np.empty(nt, np.int64), np.empty(nt, np.int64), np.empty(nt)
         bounds = np.linspace(0, nel, threads + 1).astype(np.int64)
 
         def work(k):
             lo, hi = int(bounds[k]), int(bounds[k + 1])
-            sl = slice(lo * 576, hi * 576)
-            orc.bilform_lin_elastic_coo("H8", fes.conn[lo:hi], fens.xyz, u.dofnums, nall, rule.param_coords, rule.weights, C,
-                                        out=(I[sl], J[sl], V[sl]))
+            sl = slice(lo * em2, hi * em2)
+            fn("H8", fes.conn[lo:hi], fens.xyz, u.dofnums, nall, rule.param_coords, rule.weights, coef, out=(I[sl], J[sl], V[sl]))
         with ThreadPoolExecutor(threads) as ex:
             list(ex.map(work, range(threads)))
     t1 = time.perf_counter()
@@ -162,11 +172,11 @@ def run_reference(args):
         t += dt
         nel += ne
     val = nel / t
-    sample = "%d^3 H8 lin_elastic block (%d elements) per step; element loop on %d process(es), serial sparse()" % (n, n ** 3, threads)
+    sample = "%d^3 H8 diffusion block (%d elements) per step; element loop on %d thread(s), serial sparse()" % (n, n ** 3, threads)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: bilform_lin_elastic, H8 block, GaussRule(3,2) -- bounded sample", "sample_edge": n},
+            "config": {"workload": WORKLOADS["c4"]["label"] + ", GaussRule(3,2) -- bounded sample of the 256^3 block", "sample_edge": n},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -175,10 +185,68 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+class Workload:
+    """One BASELINE configuration on this rank: host mesh, fields, the public-API objects and the C-ABI handles."""
+
+    def __init__(self, key, fe, ctx, world, rank, torch):
+        from finetools_jl_b200 import _lib
+        self.spec, self.fe, self.ctx, self.world, self.rank, self._lib, self.torch = WORKLOADS[key], fe, ctx, world, rank, _lib, torch
+        n = self.spec["edge"]
+        self.fens, self.fes = fe.H8block(1.0, 1.0, 1.0, n, n, n)
+        self.u = fe.NodalField(np.zeros((self.fens.count(), self.spec["ndn"])))
+        fe.numberdofs(self.u)
+        self.rule = fe.GaussRule(3, 2)
+        self.femm = fe.FEMMBase(fe.IntegDomain(self.fes, self.rule))
+        self.geom = fe.NodalField(self.fens.xyz)
+        # the step's input (node coordinates) lives in page-locked, column-major host memory, as the contract asks
+        pinned = torch.empty(self.geom.values.shape[::-1], dtype=torch.float64, pin_memory=True).numpy().T
+        pinned[:] = self.geom.values
+        self.geom.values = pinned
+        self.owner = fe.slab_owner(self.fens.count(), world) if world > 1 else None
+        self.coef = KAPPA3 if self.spec["form"] == "diffusion" else isotropic_C()
+        self.cache = fe.DataCache(self.coef)
+        self.coef_f = np.asfortranarray(self.coef)
+        self.a = fe.SysmatAssemblerSparseGPU(0.0, ctx=ctx)
+        self.nelem = self.fes.count()
+        # first call: uploads, builds everything (also the warm-up of the allocator)
+        self.api_call(self.a, out=None, fetch=False)
+        self.dmesh = ctx.device_mesh(self.fes)
+        self.dof = self.dmesh.dofmap(self.u)
+        self.m, self.n, self.nnz = self.a.sizes()
+        self.win = self.dmesh.window()  # (lo, hi, nactive)
+
+    def api_call(self, a, out, fetch=True):
+        """The call a user makes: bilform_*(femm, assembler, geom, u, DataCache(...)) -> CSC in host arrays."""
+        fe = self.fe
+        if not fetch:
+            a.setnomatrixresult(True)
+        try:
+            if self.spec["form"] == "diffusion":
+                return fe.bilform_diffusion(self.femm, a, self.geom, self.u, self.cache, raw=True, node_owner=self.owner, my_rank=self.rank, out=out)
+            return fe.bilform_lin_elastic(self.femm, a, self.geom, self.u, fe.DeforModelRed3D, self.cache, raw=True, node_owner=self.owner,
+                                          my_rank=self.rank, out=out)
+        finally:
+            if not fetch:
+                a.setnomatrixresult(False)
+
+    def device_step(self, fresh=True):
+        L, _lib = self._lib.lib(), self._lib
+        if fresh:
+            _lib.check(L.fegpu_pattern_invalidate(self.dof), self.ctx.handle)
+        if self.spec["form"] == "diffusion":
+            _lib.check(L.fegpu_bilform_diffusion(self.dmesh.handle, self.dof, 1, _lib.fptr(self.coef_f), self.a.handle), self.ctx.handle)
+        else:
+            _lib.check(L.fegpu_bilform_lin_elastic(self.dmesh.handle, self.dof, _lib.fptr(self.coef_f), self.a.handle), self.ctx.handle)
+
+    def release(self):
+        self.a = None
+        self.ctx.release_meshes()
+        self.ctx.release_cache()
+
+
 def run_gpu(args):
     import torch
     import finetools_jl_b200 as fe
-    from finetools_jl_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -190,45 +258,28 @@ def run_gpu(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    n = N_EDGE
-    nz_edge = n * world
-    fens, fes = fe.H8block(1.0, 1.0, float(world), n, n, nz_edge)
-    u = fe.NodalField(np.zeros((fens.count(), 3)))
-    fe.numberdofs(u)
-    rule = fe.GaussRule(3, 2)
-    C = isotropic_C()
-    nelem_global = fes.count()
-    owner = fe.slab_owner(fens.count(), world) if world > 1 else None
-
     ctx = fe.GPUContext(local_rank, stream=torch.cuda.current_stream().cuda_stream)
-    a = fe.SysmatAssemblerSparseGPU(0.0, ctx=ctx)
-    femm = fe.FEMMBase(fe.IntegDomain(fes, rule))
-    geom = fe.NodalField(fens.xyz)
-    # the step's input (node coordinates) lives in page-locked, column-major host memory, as the contract asks
-    pinned_xyz = torch.empty(geom.values.shape[::-1], dtype=torch.float64, pin_memory=True).numpy().T
-    pinned_xyz[:] = geom.values
-    geom.values = pinned_xyz
-    cache = fe.DataCache(C)
-    L = _lib.lib()
-
-    # first call: uploads, builds everything (also the warm-up of the allocator)
-    fe.bilform_lin_elastic(femm, a, geom, u, fe.DeforModelRed3D, cache, raw=True, node_owner=owner, my_rank=rank)
-    dmesh = a._device_cache[id(fes)]
-    dof = dmesh.dofmap(u)
-    Cf = np.asfortranarray(C)
-    m_, n_, nnz_local = a.sizes()
-
-    def device_step(fresh=True):
-        if fresh:
-            _lib.check(L.fegpu_pattern_invalidate(dof), ctx.handle)
-        _lib.check(L.fegpu_bilform_lin_elastic(dmesh.handle, dof, _lib.fptr(Cf), a.handle), ctx.handle)
+    hbm_peak, peak_kind = measured_peaks()
 
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def allmax(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum_int(x):
+        if dist is None:
+            return int(x)
+        t = torch.tensor([x], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        return int(t.item())
 
     def timed(fn, steps):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -238,163 +289,206 @@ def run_gpu(args):
             fn()
         ev1.record()
         barrier()
-        ms = ev0.elapsed_time(ev1)
-        if dist is not None:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return allmax(ev0.elapsed_time(ev1))
 
-    ctx.set_async(True)
-    launches0 = ctx.launch_count()
-    for _ in range(args.warmup):
-        device_step(True)
+    def wall(fn, steps):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        barrier()
+        return allmax(time.perf_counter() - t0)
+
+    def measure(key, steps, warmup, sampler=None):
+        """Everything measured for one workload; returns a dict (identical code path for headline and secondary block)."""
+        W = Workload(key, fe, ctx, world, rank, torch)
+        spec = W.spec
+        ctx.set_async(True)
+        for _ in range(warmup):
+            W.device_step(True)
+        if sampler is not None and rank == 0:
+            sampler.start()
+        launches0 = ctx.launch_count()
+        ms_total = timed(lambda: W.device_step(True), steps)
+        launches = ctx.launch_count() - launches0
+        # per-kernel device times of ONE fresh step (named CUDA events on the launching stream), phases strictly serial: the
+        # timed steps above overlap the element integration (second stream) with the symbolic phase, which would smear the
+        # per-kernel durations the roofline figures are computed from
+        ctx.set_overlap(False)
+        phases, marks = [], []
+        for _ in range(max(3, min(steps, 5))):
+            ctx.marks_begin()
+            W.device_step(True)
+            ctx.synchronize()
+            marks.append(dict(ctx.marks_read()))
+            phases.append(W.a.timings())
+        ph = {k: float(np.median([p[k] for p in phases])) for k in phases[0]}
+        mk = {k: float(np.median([m.get(k, 0.0) for m in marks])) for k in marks[0]}
+        ctx.set_overlap(True)
+        # cached re-assembly (pattern reused: integration + gather-sum only)
+        for _ in range(2):
+            W.device_step(False)
+        ms_cached = timed(lambda: W.device_step(False), steps)
+        clocks = sampler.stop() if (sampler is not None and rank == 0) else None
+        ctx.set_async(False)
+
+        # ---- e2e through the public API with host buffers
+        m_, n_, nnz_local = W.a.sizes()
+        pin = lambda cnt, dt: torch.empty(max(cnt, 1), dtype=dt, pin_memory=True).numpy()[:cnt]
+        out = (pin(n_ + 1, torch.int64), pin(nnz_local, torch.int64), pin(nnz_local, torch.float64))
+
+        def e2e_fresh_pinned():
+            W.a.invalidate_patterns()
+            W.api_call(W.a, out)
+
+        def e2e_fresh_pageable():  # what a shim that allocates fresh Vectors per makematrix! gets (FinEtoolsGPU.jl without reuse)
+            W.a.invalidate_patterns()
+            W.api_call(W.a, None)
+
+        def e2e_cached_values():   # re-assembly on the cached pattern: only coordinates in, nzval out
+            W.api_call(W.a, None, fetch=False)
+            W.a.fetch_values(out[2])
+
+        e2e_fresh_pinned()
+        xfer0 = ctx.transfer_stats()
+        e2e_steps = max(1, steps)
+        e2e_s = wall(e2e_fresh_pinned, e2e_steps) / e2e_steps
+        xfer1 = ctx.transfer_stats()
+        side = max(1, min(steps, 3))
+        e2e_pageable_s = wall(e2e_fresh_pageable, side) / side
+        e2e_cached_values()
+        e2e_cached_s = wall(e2e_cached_values, side) / side
+        h2d = W.dmesh.h2d_bytes_last
+        d2h = (n_ + 1) * 8 + nnz_local * 16
+        nn = W.fens.count()
+        if xfer1["compressed_results"] - xfer0["compressed_results"] >= e2e_steps:
+            # rowval did not cross the link: colptr + per-node neighbour lists (int32 per node pair) + their offsets + the
+            # int32 dof map + nzval did; the host threads decoded rowval from them (fegpu_transfer.cu)
+            nd2 = spec["ndn"] ** 2
+            link = (n_ + 1) * 8 + (nnz_local // nd2) * 4 + (nn + 1) * 8 + nn * spec["ndn"] * 4 + nnz_local * 8
+            link_note = ("rowval is rebuilt on the host from the device's neighbour lists (int32 per node pair) + dof map by the library's "
+                         "host threads while nzval is in flight")
+        else:
+            link = d2h - 4 * nnz_local
+            link_note = "rowval crosses the link as int32 and is widened by host threads"
+        nnz_total = allsum_int(nnz_local)
+        nact_total = allsum_int(W.win[2])
+        nelem = W.nelem
+
+        ms_step = ms_total / steps
+        nact = W.win[2]                      # elements this rank integrates (its share + halo)
+        nnodes_rank = W.win[1] - W.win[0]    # node window of the rank
+        vals = spec["vals"]
+        ndn = spec["ndn"]
+        # compulsory bytes per launch of the three device stages on THIS rank (DESIGN.md section 3)
+        b_int = nact * (32 + 8 * vals) + nnodes_rank * (24 + 0)           # int32 conn + values written + coordinates read once
+        b_gather = nact * 8 * vals + nnz_local * 8 + nact * 8 * 8 * 2 + nact * 8 * 5   # values read once + nzval + cslot (2 B/candidate) + adjacency
+        b_sym = nnz_local * 8 + (n_ + 1) * 8 + nact * 8 * 8 * 2 + nact * 8 * (4 + 5 + 4)  # rowval + colptr + cslot written; conn read, adjacency written and read
+        peaks = ctx.measure_peaks()
+        k_int_ms, k_gather_ms = mk.get("integrate", ph["integrate_ms"]), mk.get("gather", ph["numeric_ms"])
+        sym_kernels = {k[4:]: v for k, v in mk.items() if k.startswith("sym:")}
+        kern = {
+            spec["kernel"]: {"ms": k_int_ms, "bound": "fp64", "algorithmic_GBps": b_int / (k_int_ms * 1e-3) / 1e9,
+                             "executed_TFLOPs": spec["flops_exec"] * nact / (k_int_ms * 1e-3) / 1e12,
+                             "reference_count_TFLOPs": spec["flops_ref"] * nact / (k_int_ms * 1e-3) / 1e12,
+                             "dfma_peak_TFLOPs_measured_here": peaks["dfma_tflops"],
+                             "frac_fp64_executed": spec["flops_exec"] * nact / (k_int_ms * 1e-3) / 1e12 / peaks["dfma_tflops"],
+                             # element-integration roofline of the north star: the slower of flops / FP64 peak and bytes / HBM peak
+                             "frac_of_integration_roofline": max(spec["flops_exec"] * nact / (peaks["dfma_tflops"] * 1e12),
+                                                                 b_int / (hbm_peak * 1e9)) / (k_int_ms * 1e-3)},
+            "k_gather": {"ms": k_gather_ms, "bound": "hbm", "algorithmic_GBps": b_gather / (k_gather_ms * 1e-3) / 1e9,
+                         "frac": b_gather / (k_gather_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": b_gather},
+            "symbolic": {"ms": ph["symbolic_ms"], "bound": "hbm", "algorithmic_GBps": b_sym / (ph["symbolic_ms"] * 1e-3) / 1e9,
+                         "frac": b_sym / (ph["symbolic_ms"] * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": b_sym, "kernels_ms": sym_kernels},
+        }
+        res = {
+            "workload": "%s %d^3 (%d elements, %d nnz), GaussRule(3,2); %s" % (
+                spec["label"], spec["edge"], nelem, nnz_total,
+                "single GPU" if world == 1 else "%d node-owned row blocks (z-slabs), halo recomputed: %d element integrations in total" % (world, nact_total)),
+            "value": nelem / (ms_step * 1e-3), "ms_per_step": ms_step, "launches": int(launches), "phases_ms": ph, "marks_ms": mk,
+            "cached": {"value": nelem / (ms_cached / steps * 1e-3), "unit": UNIT, "ms_per_step": ms_cached / steps,
+                       "note": "re-assembly on the cached pattern (integration + gather-sum), reported separately"},
+            "nnz_per_s_csc_construction": nnz_total / ((ph["symbolic_ms"] + ph["numeric_ms"]) * 1e-3),
+            "e2e": {"value": nelem / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "ms_per_step": e2e_s * 1e3,
+                    "note": "per rank: coordinates H2D (pinned; a partitioned rank ships its node window) + full CSC (colptr,rowval,nzval) into "
+                            "pinned host Int64/Float64 arrays (d2h_bytes_per_step = the bytes of those arrays); " + link_note,
+                    "link_d2h_bytes_per_step": int(link),
+                    "pageable": {"value": nelem / e2e_pageable_s, "ms_per_step": e2e_pageable_s * 1e3, "steps": side,
+                                 "note": "same call with fresh pageable result arrays per step (no buffer reuse)"},
+                    "cached_pattern_values_only": {"value": nelem / e2e_cached_s, "ms_per_step": e2e_cached_s * 1e3, "steps": side,
+                                                   "note": "re-assembly on the cached pattern: coordinates in, nzval out (colptr/rowval kept by the caller)"},
+                    "transfer_stats": xfer1},
+            "kernels": kern, "clocks": clocks, "rank0": {"active_elements": nact, "node_window": nnodes_rank, "nnz": nnz_local},
+            "peaks": {"hbm_gbs": hbm_peak, "hbm_kind": peak_kind, "dfma_tflops_measured_here": peaks["dfma_tflops"], "copy_gbs_measured_here": peaks["copy_gbs"]},
+        }
+        W.release()
+        return res
+
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches1 = ctx.launch_count()
-    phase = np.zeros(4)
-
-    def step_and_log():
-        device_step(True)
-
-    ms_total = timed(step_and_log, args.steps)
-    launches = ctx.launch_count() - launches1
-    # per-phase device times of ONE fresh step (library CUDA events on the launching stream), phases strictly serial: the
-    # timed steps above overlap the element integration (second stream) with the symbolic phase, which would smear the
-    # per-kernel durations the roofline figures are computed from
-    ctx.set_overlap(False)
-    phases = []
-    for _ in range(max(3, min(args.steps, 5))):
-        device_step(True)
-        ctx.synchronize()
-        phases.append(a.timings())
-    ph = {k: float(np.median([p[k] for p in phases])) for k in phases[0]}
-    ctx.set_overlap(True)
-    # cached re-assembly (pattern reused: integration + gather-sum only)
-    for _ in range(2):
-        device_step(False)
-    ms_cached = timed(lambda: device_step(False), args.steps)
-    cached_ph = []
-    for _ in range(3):
-        device_step(False)
-        ctx.synchronize()
-        cached_ph.append(a.timings())
-    cph = {k: float(np.median([p[k] for p in cached_ph])) for k in cached_ph[0]}
-    clocks = sampler.stop() if rank == 0 else None
-    ctx.set_async(False)
-
-    # ---- e2e through the public API with host buffers (pinned result arrays, as a Julia shim would allocate once)
-    m_, n_, nnz_local = a.sizes()
-    pin = lambda cnt, dt: torch.empty(cnt, dtype=dt, pin_memory=True).numpy()
-    out = (pin(n_ + 1, torch.int64), pin(max(nnz_local, 1), torch.int64)[:nnz_local], pin(max(nnz_local, 1), torch.float64)[:nnz_local])
-
-    def e2e_step():
-        # the public call a user makes: coordinates host->device, fresh pattern, full CSC device->host
-        a.invalidate_patterns()
-        fe.bilform_lin_elastic(femm, a, geom, u, fe.DeforModelRed3D, cache, raw=True, node_owner=owner, my_rank=rank, out=out)
-
-    e2e_steps = max(1, min(args.steps, 3))
-    e2e_step()
-    barrier()
-    xfer0 = ctx.transfer_stats()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    h2d = fens.xyz.size * 8
-    d2h = (n_ + 1) * 8 + nnz_local * 16
-    xfer1 = ctx.transfer_stats()
-    if xfer1["compressed_results"] - xfer0["compressed_results"] >= e2e_steps:
-        # rowval did not cross the link: colptr + per-node neighbour lists (int32 per node pair = nnz/9) + their offsets + the
-        # int32 dof map + nzval did; the host threads decoded rowval from them (fegpu_transfer.cu)
-        link = (n_ + 1) * 8 + (nnz_local // 9) * 4 + (fens.count() + 1) * 8 + fens.count() * 3 * 4 + nnz_local * 8
-        link_note = ("rowval is rebuilt on the host from the device's neighbour lists (int32 per node pair) + dof map by the library's host "
-                     "threads while nzval is in flight")
-    else:
-        link = d2h - 4 * nnz_local
-        link_note = "rowval crosses the link as int32 and is widened by host threads"
-
-    nnz_total = nnz_local
-    nactive_local = None
-    if dist is not None:
-        t = torch.tensor([nnz_local], device="cuda", dtype=torch.int64)
-        dist.all_reduce(t)
-        nnz_total = int(t.item())
+    r4 = measure("c4", args.steps, args.warmup, sampler)
+    r2 = None
+    if not args.no_secondary:
+        r2 = measure("c2", max(3, min(args.steps, 10)), 3)
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    ms_step = ms_total / args.steps
-    value = nelem_global / (ms_step * 1e-3)
-    hbm_peak, peak_kind = measured_peaks()
-    nel_rank = nelem_global / world
-    # dominant kernel by device time: integration (k_h8_elastic) or the numeric gather (k_gather)
-    integ_gbs = BYTES_INTEGRATE * nel_rank / (ph["integrate_ms"] * 1e-3) / 1e9
-    gather_bytes = BYTES_GATHER_PER_ELEM * nel_rank + nnz_local * 8
-    gather_gbs = gather_bytes / (ph["numeric_ms"] * 1e-3) / 1e9
-    # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of the two kernels (one `ncu --set full` capture of this
-    # workload at N = 1, committed with its summary under profiles/)
+    # dominant device stage of the headline step by time
+    stages = {"symbolic": r4["kernels"]["symbolic"], "k_gather": r4["kernels"]["k_gather"], "k_h8_diffusion": r4["kernels"]["k_h8_diffusion"]}
+    dom_name = max(stages, key=lambda k: stages[k]["ms"])
+    dom = stages[dom_name]
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f)
-    if ph["integrate_ms"] >= ph["numeric_ms"]:
-        dom = {"kernel": "k_h8_elastic", "achieved": integ_gbs, "bytes": BYTES_INTEGRATE * nel_rank}
-    else:
-        dom = {"kernel": "k_gather", "achieved": gather_gbs, "bytes": gather_bytes}
-    peaks = ctx.measure_peaks()
-    tr = traffic.get(dom["kernel"], {}).get("dram_bytes_per_launch") if world == 1 else None
-    roofline = {"bound": "hbm", "achieved": dom["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["achieved"] / hbm_peak,
-                "traffic": tr, "algorithmic_bytes_per_launch": dom["bytes"], "kernel": dom["kernel"], "peak_kind": peak_kind,
-                "traffic_source": traffic.get("source") if tr else None,
-                "kernels": {"k_h8_elastic": {"ms": ph["integrate_ms"], "algorithmic_GBps": integ_gbs, "bound": "fp64",
-                                             "executed_TFLOPs": FLOPS_EXECUTED_PER_ELEM * nel_rank / (ph["integrate_ms"] * 1e-3) / 1e12,
-                                             "reference_count_TFLOPs": FLOPS_PER_ELEM * nel_rank / (ph["integrate_ms"] * 1e-3) / 1e12,
-                                             "dfma_peak_TFLOPs_measured": peaks["dfma_tflops"],
-                                             "frac_fp64_executed": FLOPS_EXECUTED_PER_ELEM * nel_rank / (ph["integrate_ms"] * 1e-3) / 1e12 / peaks["dfma_tflops"]},
-                            "symbolic(pattern build)": {"ms": ph["symbolic_ms"]},
-                            "k_gather": {"ms": ph["numeric_ms"], "algorithmic_GBps": gather_gbs, "bound": "hbm"}},
-                "copy_gbs_measured_here": peaks["copy_gbs"]}
+    tr = traffic.get("c4", {}).get(dom_name, {}).get("dram_bytes_per_launch") if world == 1 else None
+    if dom["bound"] == "hbm":
+        roofline = {"bound": "hbm", "achieved": dom["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["frac"],
+                    "traffic": tr, "algorithmic_bytes_per_launch": dom["algorithmic_bytes"]}
+    else:  # the FP64 integration kernel: both terms of the north star's roofline
+        roofline = {"bound": "fp64", "achieved": dom["executed_TFLOPs"], "peak": dom["dfma_peak_TFLOPs_measured_here"], "unit": "TFLOP/s",
+                    "frac": dom["frac_fp64_executed"], "traffic": tr, "hbm_GBps": dom["algorithmic_GBps"]}
+    roofline.update({"kernel": dom_name, "peak_kind": r4["peaks"]["hbm_kind"], "traffic_source": traffic.get("source") if tr else None,
+                     "kernels": r4["kernels"], "copy_gbs_measured_here": r4["peaks"]["copy_gbs_measured_here"],
+                     "note": "dominant stage of the fresh step by device time; 'symbolic' is the pattern build (k_adj_table + k_sym_tile + scans), "
+                             "its per-kernel times are under kernels.symbolic.kernels_ms"})
 
-    # bounded serial CPU baseline (the reference's own single-threaded path)
-    from oracle import oracle as orc
-    orc.build()
-    ne, dt, t_form, t_sparse, _ = cpu_reference_run(args.cpu_edge, 1)
-    cpu = {"value": ne / dt, "unit": UNIT, "cores": 1, "kind": "port",
-           "sample": "%d^3 H8 lin_elastic block (%d elements), one serial pass: element loop %.2f s + sparse() %.2f s; host has %d cores"
-                     % (args.cpu_edge, ne, t_form, t_sparse, os.cpu_count() or 0)}
+    cpu = None
+    if world == 1:
+        # bounded serial CPU baseline (the reference's own single-threaded path) on a sample of the headline workload
+        from oracle import oracle as orc
+        orc.build()
+        ne, dt, t_form, t_sparse, _ = cpu_reference_run(args.cpu_edge, 1)
+        cpu = {"value": ne / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%d^3 H8 diffusion block (%d elements), one serial pass: element loop %.2f s + sparse() %.2f s; host has %d cores"
+                         % (args.cpu_edge, ne, t_form, t_sparse, os.cpu_count() or 0)}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: bilform_lin_elastic, H8 block 128x128x%d (%d elements, %d nnz), GaussRule(3,2), "
-                               "isotropic C; %s" % (nz_edge, nelem_global, nnz_total,
-                                                    "single GPU" if world == 1 else "%d node-owned row blocks (z-slabs), halo recomputed" % world),
-                   "l2": "working set (5.4 GB element values + 8.2 GB CSC per rank) >> 126 MB L2; no flush needed",
+        "metric": METRIC, "value": r4["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r4["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": r4["workload"],
+                   "l2": "working set per rank (element values + CSC + pattern: GBs) >> 126 MB L2; no flush needed",
                    "step": "fresh assembly: pattern cache invalidated before every step; the element integration runs on a second "
-                           "stream concurrently with the symbolic phase (phases_ms are measured with that overlap switched off)"},
-        "clocks": clocks,
-        "e2e": {"value": nelem_global / (e2e_s / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "note": "per rank: xyz H2D (pinned) + full CSC (colptr,rowval,nzval) delivered into pinned host Int64/Float64 arrays "
-                        "(d2h_bytes_per_step = the bytes of those arrays); " + link_note,
-                "link_d2h_bytes_per_step": int(link), "transfer_stats": xfer1},
-        "gpu_launches": int(launches),
+                           "stream concurrently with the symbolic phase (phases_ms / marks_ms are measured with that overlap switched off)"},
+        "clocks": r4["clocks"],
+        "e2e": r4["e2e"],
+        "gpu_launches": r4["launches"],
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "phases_ms": ph,
-        "cached": {"value": nelem_global / (ms_cached / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms_cached / args.steps,
-                   "phases_ms": cph, "note": "re-assembly on the cached pattern (integration + gather-sum), reported separately"},
-        "nnz_per_s_csc_construction": nnz_total / ((ph["symbolic_ms"] + ph["numeric_ms"]) * 1e-3),
+        "phases_ms": r4["phases_ms"], "marks_ms": r4["marks_ms"],
+        "cached": r4["cached"],
+        "nnz_per_s_csc_construction": r4["nnz_per_s_csc_construction"],
+        "rank0": r4["rank0"],
     }
+    if r2 is not None:
+        line["config2"] = {k: r2[k] for k in ("workload", "value", "ms_per_step", "phases_ms", "marks_ms", "cached", "e2e", "kernels", "launches",
+                                              "nnz_per_s_csc_construction")}
+    if cpu is None:
+        del line["cpu_baseline"]
     _emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -406,9 +500,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
-    ap.add_argument("--ref-threads", type=int, default=0, help="reference arm: processes for the element loop (0 = all cores)")
-    ap.add_argument("--ref-edge", type=int, default=48, help="reference arm: block edge of the bounded sample")
-    ap.add_argument("--cpu-edge", type=int, default=40, help="cpu_baseline leg: block edge of the bounded serial sample")
+    ap.add_argument("--ref-threads", type=int, default=0, help="reference arm: threads for the element loop (0 = all cores)")
+    ap.add_argument("--ref-edge", type=int, default=80, help="reference arm: block edge of the bounded sample")
+    ap.add_argument("--cpu-edge", type=int, default=128, help="cpu_baseline leg: block edge of the bounded serial sample")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-2 block")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

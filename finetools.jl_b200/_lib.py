@@ -25,6 +25,10 @@ SIGNATURES = {
     "fegpu_cache_release": (C.c_int32, [VP]),
     "fegpu_launch_count": (C.c_int64, [VP]),
     "fegpu_measure_peaks": (C.c_int32, [VP, c_f64p, c_f64p]),
+    "fegpu_marks_begin": (C.c_int32, [VP]),
+    "fegpu_marks_read": (C.c_int32, [VP, VP, C.c_int64]),
+    "fegpu_geom_update_window": (C.c_int32, [VP, VP]),
+    "fegpu_mesh_window": (C.c_int32, [VP, c_i64p, c_i64p, c_i64p]),
     "fegpu_mesh_upload": (C.c_int32, [VP, C.c_int32, C.c_int64, VP, C.c_int64, C.c_int32, VP, C.POINTER(VP)]),
     "fegpu_mesh_destroy": (C.c_int32, [VP]),
     "fegpu_geom_update": (C.c_int32, [VP, VP]),
@@ -65,6 +69,7 @@ SIGNATURES = {
     "fegpu_last_timings": (C.c_int32, [VP, c_f64p]),
     "fegpu_pattern_was_cached": (C.c_int32, [VP]),
     "fegpu_pattern_invalidate": (C.c_int32, [VP]),
+    "fegpu_pattern_path": (C.c_int32, [VP]),
 }
 
 _lib = None

@@ -4,6 +4,7 @@ element loop, triplet storage and COO->CSC conversion run on a B200 through libf
 Protocol mirrored: startassembly! (:209-238), assemble! (:250-282), makematrix! (:304-329), setnomatrixresult (:29),
 expectedntriples (:54-59), eltype (:27).  Julia's `!` is dropped from the names.  Error strings are the reference's.
 """
+import collections
 import contextlib
 import ctypes as C
 import os
@@ -17,13 +18,42 @@ from ._lib import VP, check, fptr
 class GPUContext:
     """One CUDA device + stream; owner of every device handle created through it."""
     _default = {}
+    MAX_MESHES = 4  # device twins of FESets kept per context (least recently used ones are destroyed beyond this)
 
     def __init__(self, device=0, stream=None):
         self.handle = VP()
         check(_lib.lib().fegpu_create(C.byref(self.handle), int(device)))
         self.device = int(device)
+        # device meshes / dof maps / cached patterns, keyed by the FESet's connectivity array: they belong to the context,
+        # not to an assembler, so a fresh assembler per call (the reference's idiom) re-uses them
+        self._meshes = collections.OrderedDict()
         if stream is not None:
             self.set_stream(stream)
+
+    def device_mesh(self, fes):
+        """The device twin of `fes` on this context (None before its first assembly)."""
+        dm = self._meshes.get(id(fes.conn))
+        return dm if dm is not None and dm.conn_ref is fes.conn else None
+
+    def release_meshes(self):
+        """Destroy every device mesh / dof map / pattern of this context (assemblers keep their own results)."""
+        for dm in self._meshes.values():
+            dm.destroy()
+        self._meshes.clear()
+
+    def marks_begin(self):
+        check(_lib.lib().fegpu_marks_begin(self.handle), self.handle)
+
+    def marks_read(self):
+        """[(kernel or phase name, ms since the previous mark)] of the step run since marks_begin()."""
+        buf = C.create_string_buffer(8192)
+        check(_lib.lib().fegpu_marks_read(self.handle, buf, 8192), self.handle)
+        out = []
+        for item in buf.value.decode().split(";"):
+            if "=" in item:
+                k, v = item.rsplit("=", 1)
+                out.append((k, float(v)))
+        return out
 
     @classmethod
     def default(cls, device=0):
@@ -98,7 +128,12 @@ class SysmatAssemblerSparseGPU(AbstractSysmatAssembler):
         self._mode = None             # "form" after a bilform call, "generic" inside startassembly/assemble
         self._row_nalldofs = 0
         self._col_nalldofs = 0
-        self._device_cache = {}       # (mesh/dofmap handles keyed by the host objects), see femm.py
+        self._last_mesh = None        # device twin of the last form call (owned by the context, see femm.py)
+
+    @property
+    def _device_cache(self):
+        """The context's device meshes (kept under this name for callers that walk them)."""
+        return self.ctx._meshes
 
     # ---- reference protocol -----------------------------------------------------------------------------
     def eltype(self):
@@ -187,6 +222,11 @@ class SysmatAssemblerSparseGPU(AbstractSysmatAssembler):
             colptr, rowval, nzval = np.empty(n + 1, np.int64), np.empty(nnz, np.int64), np.empty(nnz, np.float64)
         else:
             colptr, rowval, nzval = out
+            for arr, cnt, dt, what in ((colptr, n + 1, np.int64, "colptr"), (rowval, nnz, np.int64, "rowval"), (nzval, nnz, np.float64, "nzval")):
+                # the C side writes cnt entries straight into these buffers: refuse anything that could overflow or reinterpret
+                if not isinstance(arr, np.ndarray) or arr.dtype != dt or arr.ndim != 1 or arr.size != cnt or not arr.flags.c_contiguous \
+                        or not arr.flags.writeable:
+                    raise _lib.FEGPUError(-2, "out[%s] must be a writeable contiguous %s array of length %d" % (what, np.dtype(dt).name, cnt))
         check(_lib.lib().fegpu_makematrix_copy(self.handle, fptr(colptr), fptr(rowval), fptr(nzval)), self.ctx.handle)
         if raw:
             return colptr, rowval, nzval, m, n
@@ -195,6 +235,9 @@ class SysmatAssemblerSparseGPU(AbstractSysmatAssembler):
 
     def fetch_values(self, nzval):
         """Only nzval (re-assembly on a cached pattern)."""
+        _, _, nnz = self.sizes()
+        if not isinstance(nzval, np.ndarray) or nzval.dtype != np.float64 or nzval.size != nnz or not nzval.flags.c_contiguous:
+            raise _lib.FEGPUError(-2, "nzval must be a contiguous float64 array of length %d" % nnz)
         check(_lib.lib().fegpu_makematrix_copy_values(self.handle, fptr(nzval)), self.ctx.handle)
         return nzval
 
@@ -218,10 +261,9 @@ class SysmatAssemblerSparseGPU(AbstractSysmatAssembler):
         return {"integrate_ms": ms[0], "symbolic_ms": ms[1], "numeric_ms": ms[2], "total_ms": ms[3]}
 
     def invalidate_patterns(self):
-        """Drop every cached sparsity pattern held for this assembler's meshes (next assembly rebuilds it)."""
-        for dm in self._device_cache.values():
-            for _, _, h in dm.dofmaps:
-                check(_lib.lib().fegpu_pattern_invalidate(h), self.ctx.handle)
+        """Drop every cached sparsity pattern of the context's meshes (the next assembly rebuilds it)."""
+        for dm in self.ctx._meshes.values():
+            dm.invalidate_patterns()
 
     def pattern_was_cached(self):
         return bool(_lib.lib().fegpu_pattern_was_cached(self.handle))
@@ -250,7 +292,7 @@ class SysvecAssemblerGPU(AbstractSysvecAssembler):
         self.ctx = like.ctx if like is not None else (ctx if ctx is not None else GPUContext.default(device))
         self.handle = VP()
         check(_lib.lib().fegpu_asm_create(self.ctx.handle, C.byref(self.handle)), self.ctx.handle)
-        self._device_cache = like._device_cache if like is not None else {}
+        self._last_mesh = None
         self._row_nalldofs = 1  # the reference's blank assembler holds a one-entry buffer (AssemblyModule.jl:861)
 
     def startassembly(self, row_nalldofs):

@@ -1,10 +1,12 @@
 // C ABI of libfinegpu.so (include/fegpu.h): handles, uploads, the three bilinear forms, the generic assembler protocol,
 // result access.  No CPU fallback anywhere: every compute call ends in a kernel launch on the context's stream.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
 #include "fegpu_internal.h"
+#include "fegpu_pattern.h"
 
 static thread_local std::string g_last_error;
 
@@ -151,6 +153,14 @@ int32_t finish(fegpu_ctx *ctx) {
   return FEGPU_OK;
 }
 
+// the assembler's result borrows colptr / rowval of a pattern: hold a reference while it does
+void asm_set_pattern(fegpu_asm *as, Pattern *p) {
+  if (as->pat_src == p) return;
+  if (p) fe_pattern_retain(p);
+  if (as->pat_src) fe_pattern_free(as->pat_src);
+  as->pat_src = p;
+}
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) {
@@ -245,6 +255,33 @@ int32_t fegpu_synchronize(fegpu_ctx *ctx) {
   return FEGPU_OK;
 }
 int64_t fegpu_launch_count(fegpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t fegpu_marks_begin(fegpu_ctx *ctx) {
+  if (!ctx) return FEGPU_ERR_ARG;
+  ctx->marks_on = true;
+  ctx->nmarks = 0;
+  return FEGPU_OK;
+}
+
+int32_t fegpu_marks_read(fegpu_ctx *ctx, char *buf, int64_t cap) {
+  if (!ctx || !buf || cap < 1) return fegpu_fail(ctx, FEGPU_ERR_ARG, "NULL argument");
+  DeviceGuard g(ctx->device);
+  ctx->marks_on = false;
+  std::string out;
+  if (ctx->nmarks > 0) CUDA_TRY(ctx, cudaEventSynchronize(ctx->marks[ctx->nmarks - 1].ev));
+  for (int i = 1; i < ctx->nmarks; i++) {
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->marks[i - 1].ev, ctx->marks[i].ev));
+    char tmp[160];
+    std::snprintf(tmp, sizeof(tmp), "%s=%.6f;", ctx->marks[i].name, (double)ms);
+    out += tmp;
+  }
+  ctx->nmarks = 0;
+  const size_t n = std::min<size_t>(out.size(), (size_t)cap - 1);
+  std::memcpy(buf, out.data(), n);
+  buf[n] = 0;
+  return FEGPU_OK;
+}
 
 int32_t fegpu_measure_peaks(fegpu_ctx *ctx, double *dfma_tflops, double *copy_gbs) {
   if (!ctx) return FEGPU_ERR_ARG;
@@ -373,6 +410,26 @@ int32_t fegpu_geom_update(fegpu_mesh *m, const double *xyz) {
   return FEGPU_OK;
 }
 
+int32_t fegpu_geom_update_window(fegpu_mesh *m, const double *xyz) {
+  if (!m || !xyz) return fegpu_fail(m ? m->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
+  DeviceGuard g(m->ctx->device);
+  const int64_t lo = m->win_lo, nw = m->win_hi - m->win_lo;
+  if (nw > 0)
+    for (int d = 0; d < m->sdim; d++)
+      CUDA_TRY(m->ctx, cudaMemcpyAsync(m->d_xyz + (size_t)d * m->nnodes + lo, xyz + (size_t)d * m->nnodes + lo, sizeof(double) * (size_t)nw,
+                                       cudaMemcpyHostToDevice, m->ctx->stream));
+  CUDA_TRY(m->ctx, cudaStreamSynchronize(m->ctx->stream));  // the host array may go away after return
+  return FEGPU_OK;
+}
+
+int32_t fegpu_mesh_window(fegpu_mesh *m, int64_t *lo, int64_t *hi, int64_t *nactive) {
+  if (!m) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "NULL mesh");
+  if (lo) *lo = m->win_lo;
+  if (hi) *hi = m->win_hi;
+  if (nactive) *nactive = m->nactive;
+  return FEGPU_OK;
+}
+
 int32_t fegpu_rule_set(fegpu_mesh *m, int32_t npts, const double *Ns, const double *gradNpar, const double *w) {
   if (!m || !Ns || !gradNpar || !w) return fegpu_fail(m ? m->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
   fegpu_ctx *ctx = m->ctx;
@@ -431,7 +488,22 @@ int32_t fegpu_partition_set(fegpu_mesh *m, const int32_t *node_owner, int32_t my
   m->nactive = m->nelem;
   m->win_lo = 0;
   m->win_hi = m->nnodes;
+  m->own_contig = false;
+  m->own_lo = m->own_hi = 0;
   if (!node_owner) return FEGPU_OK;
+  {  // are the owned nodes one contiguous range (slab partitions, meshes reordered by partition)?  Then the kernels test row
+     // ownership with two comparisons instead of a byte load per candidate
+    int64_t first = -1, last = -1, cnt = 0;
+    for (int64_t i = 0; i < m->nnodes; i++)
+      if (node_owner[i] == my_rank) {
+        if (first < 0) first = i;
+        last = i;
+        cnt++;
+      }
+    m->own_contig = cnt > 0 && cnt == last - first + 1;
+    m->own_lo = cnt > 0 ? first : 0;
+    m->own_hi = cnt > 0 ? last + 1 : 0;
+  }
   int32_t *d_owner = nullptr, *d_flag = nullptr;
   int64_t *d_pos = nullptr;
   int *d_win = nullptr;
@@ -553,6 +625,11 @@ int32_t fegpu_pattern_invalidate(fegpu_dofmap *d) {
   return FEGPU_OK;
 }
 
+int32_t fegpu_pattern_path(fegpu_dofmap *d) {
+  if (!d || !d->pat || d->pat_topo_version != d->mesh->topo_version) return 0;
+  return d->pat->tile ? 2 : 1;
+}
+
 // ------------------------------------------------------------------------------------------------- assembler
 int32_t fegpu_asm_create(fegpu_ctx *ctx, fegpu_asm **out) {
   if (!ctx || !out) return fegpu_fail(ctx, FEGPU_ERR_ARG, "NULL argument");
@@ -582,6 +659,7 @@ int32_t fegpu_asm_set_lumping(fegpu_asm *as, int32_t mode) {
 int32_t fegpu_asm_destroy(fegpu_asm *a) {
   if (!a) return FEGPU_OK;
   DeviceGuard g(a->ctx->device);
+  asm_set_pattern(a, nullptr);
   cudaFree(a->d_V); cudaFree(a->d_nzval); cudaFree(a->own_colptr); cudaFree(a->own_rowval); cudaFree(a->d_F);
   cudaFree(a->view.own_colptr); cudaFree(a->view.own_rowval); cudaFree(a->view.own_nzval);
   for (auto &ev : a->ev)
@@ -603,7 +681,7 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
   const int EM = mesh->nne * fa.ndn;
   const int64_t ntrip = mesh->nactive * (int64_t)EM * EM;
   as->have_result = false;
-  as->pat_src = nullptr;
+  asm_set_pattern(as, nullptr);
   as->view.active = false;
   as->started = false;
   // 1. symbolic phase (cached in the dof map) and 2. element integration.  The symbolic phase decides the layout the
@@ -611,6 +689,7 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
   // assembly the pattern build runs on the context's second, high-priority stream and the integration is launched on the
   // caller's stream as soon as the build knows it will take the structured path; the numeric phase waits for both.
   CUDA_TRY(ctx, cudaEventRecord(as->ev[0], st));
+  fe_mark(ctx, "start");
   bool fast = fe_pattern_usable(dm);
   as->pattern_cached = false;
   FormArgs fa2 = fa;
@@ -626,6 +705,7 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
     CUDA_TRY(ctx, cudaEventRecord(as->ev[4], st));
     FE_TRY(fe_integrate(mesh, fa2, as->d_V));
     CUDA_TRY(ctx, cudaEventRecord(as->ev[2], st));
+    fe_mark(ctx, "integrate");
     return FEGPU_OK;
   };
   bool integrated = false, sym_timed = false;
@@ -669,12 +749,13 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
     const int64_t nnz = fe_pattern_nnz(dm->pat);
     FE_TRY(fe_asm_reserve(as, &as->d_nzval, &as->nz_cap, (size_t)std::max<int64_t>(nnz, 1)));
     FE_TRY(fe_gather(dm, as->d_V, fa2.compact, as->d_nzval));
+    fe_mark(ctx, "gather");
     as->nnz = nnz;
     as->nrows = dm->row_nall;
     as->ncols = dm->col_nall;
     as->d_colptr = fe_pattern_colptr(dm->pat);
     as->d_rowval = fe_pattern_rowval(dm->pat);
-    as->pat_src = dm->pat;
+    asm_set_pattern(as, dm->pat);
   } else {
     if (mesh->partitioned) return fegpu_fail(ctx, FEGPU_ERR_ARG, "row-block partitioning needs an injective dof map and non-degenerate elements");
     int64_t *dI = nullptr, *dJ = nullptr;
@@ -884,7 +965,7 @@ static int32_t run_lumped(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &fa
   const int EM = mesh->nne * fa.ndn;
   const int64_t nv = mesh->nactive * (int64_t)EM;
   as->have_result = false;
-  as->pat_src = nullptr;
+  asm_set_pattern(as, nullptr);
   as->view.active = false;
   as->started = false;
   as->pattern_cached = false;
@@ -944,7 +1025,7 @@ int32_t fegpu_bilform_masslike(fegpu_mesh *mesh, fegpu_dofmap *dm, const double 
   const int per = dm->ndn * mesh->nne * dm->ndn;
   const int64_t n = mesh->nelem * (int64_t)per;
   as->have_result = false;
-  as->pat_src = nullptr;
+  asm_set_pattern(as, nullptr);
   as->view.active = false;
   as->started = false;
   as->pattern_cached = false;
@@ -1191,7 +1272,7 @@ int32_t fegpu_makematrix(fegpu_asm *as) {
     CUDA_TRY(ctx, cudaEventRecord(as->ev[3], st));
     as->ev_valid = true;
     as->have_result = true;
-    as->pat_src = nullptr;
+    asm_set_pattern(as, nullptr);
     as->pattern_cached = false;
     as->view.active = false;
     as->V_compact = false;
@@ -1236,7 +1317,7 @@ int32_t fegpu_makematrix(fegpu_asm *as) {
 #undef GT
   as->ev_valid = true;
   as->have_result = true;
-  as->pat_src = nullptr;
+  asm_set_pattern(as, nullptr);
   as->pattern_cached = false;
   as->view.active = false;
   as->V_compact = false;

@@ -10,14 +10,16 @@
 //                   The 24x24 matrix is staged through shared memory and written with coalesced 128-bit stores in the
 //                   reference's emission order.
 // Only GaussRule(3,2) (8 points) takes these paths; other rules use the generic kernel.
+#include <cstring>
+
 #include "fegpu_internal.h"
 
 namespace {
 
-__constant__ double c_dN[8 * 3 * 8];  // [point][dim][node]
-__constant__ double c_w[8];
-__constant__ double c_coef[36];
-
+// The quadrature tables and the coefficient travel as KERNEL PARAMETERS (1.9 KB of the 4 KB parameter space): they land in
+// the launch's own constant bank, i.e. they are uniform operands of the DFMAs exactly like __constant__ data, but they belong
+// to this launch -- two contexts on one device (or two queued forms on different streams) cannot overwrite each other's
+// tables between upload and kernel, and no cudaMemcpyToSymbol precedes the launch.
 struct H8Params {
   const int32_t *conn;
   const double *xyz;
@@ -25,6 +27,9 @@ struct H8Params {
   const int32_t *elem_list;
   int64_t nactive;
   double *V;
+  double dN[8 * 3 * 8];  // [point][dim][node]
+  double w[8];
+  double coef[36];
 };
 
 __device__ __forceinline__ void inv3(const double *J, double *inv, double &det) {
@@ -47,7 +52,8 @@ __device__ __forceinline__ void inv3(const double *J, double *inv, double &det) 
 // COMPACT: only the upper triangle (36 values, packed by columns: entry (r <= c) at c(c+1)/2 + r) is written -- the layout
 // k_gather reads for symmetric forms on the mesh-structured path; otherwise the full 8x8 matrix in emission order.
 template <bool GENERAL, bool COMPACT>
-__global__ void __launch_bounds__(128) k_h8_diffusion(const H8Params P) {
+__global__ void __launch_bounds__(128) k_h8_diffusion(const __grid_constant__ H8Params P) {
+  const double *c_dN = P.dN, *c_w = P.w, *c_coef = P.coef;
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= P.nactive) return;
   const int64_t e = P.elem_list ? P.elem_list[slot] : slot;
@@ -145,7 +151,7 @@ constexpr int EL_GSTRIDE = 25;             // doubles per (element, point): 24 g
 constexpr int EL_SMEM_FULL = 16 * 577 * 8;          // staging is the larger user
 constexpr int EL_SMEM_COMPACT = 8 * EL_GSTRIDE * EL_EPB * 8;  // G is (16 * 325 * 8 = 41600 B of staging fits inside)
 
-__device__ __forceinline__ void db_col(const double *g, double Jw, double DB[18]) {
+__device__ __forceinline__ void db_col(const double *g, double Jw, double DB[18], const double *c_coef) {
   // DB[:, j] = D * (Jw * B_b[:, j]), B_b column j has 3 non-zeros (DeforModelRedModule.jl:463-468, Rm = I)
   // comp x: rows 0(g0) 3(g1) 4(g2); comp y: rows 1(g1) 3(g0) 5(g2); comp z: rows 2(g2) 4(g0) 5(g1)
   // The scalar Jac*w multiplies the three gradients once (3 DMUL) instead of the 18 entries: 57 instead of 72 FP64
@@ -205,7 +211,7 @@ __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, cons
     const double Jw = g[24 * EL_EPB];
     double gb[3], ga[3], DB[18];
     load3(gb, g, B2);
-    db_col(gb, Jw, DB);
+    db_col(gb, Jw, DB, P.coef);
 #pragma unroll
     for (int s = 0; s < 5; s++) {
       load3(ga, g, s);
@@ -218,7 +224,7 @@ __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, cons
         block_acc(K[s], ga, DB);
       }
     load3(gb, g, B1);
-    db_col(gb, Jw, DB);
+    db_col(gb, Jw, DB, P.coef);
 #pragma unroll
     for (int s = 5; s < 8; s++)
       if (s >= NB2) {
@@ -281,7 +287,8 @@ __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, cons
 }
 
 template <bool COMPACT>
-__global__ void __launch_bounds__(128, 2) k_h8_elastic(const H8Params P) {
+__global__ void __launch_bounds__(128, 2) k_h8_elastic(const __grid_constant__ H8Params P) {
+  const double *c_dN = P.dN, *c_w = P.w;
   extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, t = threadIdx.x >> 5;  // lane = element in block, t = column pair
   const int64_t slot0 = (int64_t)blockIdx.x * EL_EPB;
@@ -339,11 +346,11 @@ int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool 
   const bool elast = (fa.form == FORM_ELASTIC);
   if (!diff && !elast) return FEGPU_OK;
   if (mesh->nactive == 0) { *handled = true; return FEGPU_OK; }
+  H8Params P{mesh->d_conn, mesh->d_xyz, mesh->nnodes, mesh->d_elem_list, mesh->nactive, d_V, {0}, {0}, {0}};
   // dN part of the host table: [npts][3][8] starting after N [npts][8]
-  CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_dN, mesh->h_tab.data() + 8 * 8, sizeof(double) * 8 * 24, 0, cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_w, mesh->h_w.data(), sizeof(double) * 8, 0, cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_coef, fa.coef, sizeof(double) * 36, 0, cudaMemcpyHostToDevice, ctx->stream));
-  H8Params P{mesh->d_conn, mesh->d_xyz, mesh->nnodes, mesh->d_elem_list, mesh->nactive, d_V};
+  std::memcpy(P.dN, mesh->h_tab.data() + 8 * 8, sizeof(double) * 8 * 24);
+  std::memcpy(P.w, mesh->h_w.data(), sizeof(double) * 8);
+  std::memcpy(P.coef, fa.coef, sizeof(double) * 36);
   if (diff) {
     unsigned grid = grid_for(mesh->nactive, 128);
     if (fa.form == FORM_DIFF_GEN) {
@@ -354,12 +361,9 @@ int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool 
       else k_h8_diffusion<false, false><<<grid, 128, 0, ctx->stream>>>(P);
     }
   } else {
-    static bool attr_set = false;
-    if (!attr_set) {
-      CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EL_SMEM_COMPACT));
-      CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EL_SMEM_FULL));
-      attr_set = true;
-    }
+    // the attribute is per device (a process may hold contexts on several): set it on every launch, like every other kernel here
+    if (fa.compact) CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EL_SMEM_COMPACT));
+    else CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EL_SMEM_FULL));
     unsigned grid = grid_for(mesh->nactive, EL_EPB);
     if (fa.compact) k_h8_elastic<true><<<grid, 128, EL_SMEM_COMPACT, ctx->stream>>>(P);
     else k_h8_elastic<false><<<grid, 128, EL_SMEM_FULL, ctx->stream>>>(P);

@@ -28,7 +28,19 @@ struct fegpu_ctx {
   std::string err;
   struct Transfer *xfer = nullptr;  // staging ring + host threads of the result transport (fegpu_transfer.cu), lazily built
   struct BlockCache *blocks = nullptr;  // device-memory block cache of the symbolic phase (fegpu_blockcache.cu), lazily built
+  // named timing marks on the context's stream (fegpu_marks_begin / fegpu_marks_read): per-kernel times of one serial step
+  bool marks_on = false;
+  struct Mark {
+    const char *name;
+    cudaEvent_t ev;
+  };
+  std::vector<Mark> marks;
+  int nmarks = 0;
+  // quadrature tables / coefficients of the specialised H8 kernels live in __constant__ memory, which every context of a
+  // device shares: the owner of the current contents (fegpu_h8.cu re-uploads when another context or other data come along)
+  uint64_t const_epoch = 0;
 };
+void fe_mark(fegpu_ctx *ctx, const char *name);  // records an event named `name` on ctx->stream when marks are on
 
 struct Pattern;  // fegpu_pattern.cu
 
@@ -52,6 +64,8 @@ struct fegpu_mesh {
   int64_t nactive = 0;              // == nelem when not partitioned
   int32_t *d_elem_list = nullptr;   // active element ids ascending (nullptr = identity)
   uint8_t *d_rowowned = nullptr;    // per node, nullptr = all owned
+  bool own_contig = false;          // the owned nodes are exactly the range [own_lo, own_hi) (slab / reordered partitions)
+  int64_t own_lo = 0, own_hi = 0;
   int64_t win_lo = 0, win_hi = 0;   // node window [lo, hi) that contains every node of an active element ([0, nnodes) when not partitioned)
   uint64_t topo_version = 1;        // bumped when the active set / ownership changes
   bool degenerate = false;          // some element lists a node twice -> generic sort path
@@ -67,6 +81,7 @@ struct fegpu_dofmap {
   bool injective = true;
   Pattern *pat = nullptr;
   uint64_t pat_topo_version = 0;
+  uint64_t tile_failed_version = 0;  // mesh->topo_version for which the thread-per-node path's preconditions failed (fegpu_tile.cu)
 };
 
 struct fegpu_asm {
@@ -81,7 +96,7 @@ struct fegpu_asm {
   int64_t nrows = 0, ncols = 0, nnz = 0;
   const int64_t *d_colptr = nullptr;  // borrowed from a Pattern or == own_colptr
   const int64_t *d_rowval = nullptr;
-  const Pattern *pat_src = nullptr;   // the pattern d_colptr/d_rowval are borrowed from (nullptr: the assembler's own arrays)
+  Pattern *pat_src = nullptr;         // the pattern d_colptr/d_rowval are borrowed from, retained (nullptr: the assembler's own arrays)
   double *d_nzval = nullptr;
   size_t nz_cap = 0;
   int64_t *own_colptr = nullptr, *own_rowval = nullptr;
@@ -193,7 +208,13 @@ bool fe_integrate_supports_compact(const fegpu_mesh *mesh, const FormArgs &fa);
 // `fork` (optional) is invoked once, on the calling thread, as soon as the build knows it will not fall back to the sort path
 // for an early reason (degenerate elements, encoding limits): the caller launches independent work on another stream there
 int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork = nullptr);
-void fe_pattern_free(Pattern *p);
+// Patterns are shared: the dof map that built one and every assembler whose result borrows its colptr / rowval hold a
+// reference (an invalidated or rebuilt pattern must not pull the arrays from under a result that is still being read).
+void fe_pattern_retain(Pattern *p);
+void fe_pattern_free(Pattern *p);  // drops one reference; the arrays go back to the block cache with the last one
+// thread-per-node kernels for small stencils (fegpu_tile.cu); *taken = false: preconditions not met, run the general path
+int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork, bool *taken);
+int32_t fe_tile_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_nzval, bool *taken);
 void fe_pattern_set_stream(Pattern *p, cudaStream_t s);  // stream its stream-ordered frees are queued on
 cudaEvent_t fe_pattern_ready_event(const Pattern *p);    // completes when every array of the pattern is final
 int64_t fe_pattern_nnz(const Pattern *p);

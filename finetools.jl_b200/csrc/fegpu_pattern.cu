@@ -21,34 +21,8 @@
 #include <cstdio>
 
 #include "fegpu_internal.h"
+#include "fegpu_pattern.h"
 
-struct Pattern {
-  fegpu_ctx *ctx = nullptr;
-  int64_t nnz = 0, ncols = 0, nrows = 0;
-  int64_t *d_colptr = nullptr;    // [ncols+1] 1-based
-  int64_t *d_rowval = nullptr;    // [nnz] 1-based
-  int64_t *d_adjptr = nullptr;    // [nnodes+1]
-  int32_t *d_adj_slot = nullptr;  // active-element slot
-  uint8_t *d_adj_lc = nullptr;    // local node index of this node in that element
-  int32_t *d_nnbr = nullptr;      // [nnodes]
-  int64_t *d_nbrptr = nullptr;    // [nnodes+1]
-  uint16_t *d_cslot = nullptr;    // per node at adjptr[n]*nne + a*nne + li: neighbour slot of that candidate (0xffff = dropped)
-  uint16_t *d_rank = nullptr;     // per node nnbr*ndn entries at nbrptr[n]*ndn, nullptr when identity everywhere
-  int32_t *d_order = nullptr;     // node visiting order of the gather: the active nodes in Morton order of their coordinates
-  int64_t norder = 0;             // (nullptr = all nodes, natural order)
-  // compressed form of rowval for the result transport (vector fields whose node-major dof order is ascending everywhere):
-  // the rows of every column of node n are { dof[p][nbr[nbrptr[n] + s]] + 1 : s ascending, p ascending }
-  int32_t *d_nbr = nullptr;       // [total_nbr] neighbour nodes, ascending per node
-  int64_t total_nbr = 0;
-  const int32_t *d_dof = nullptr; // borrowed from the dof map that owns this pattern
-  int ndn = 0;
-  int64_t nnodes = 0;
-  int maxdeg = 0, maxcand = 0, maxnbr = 0;
-  cudaStream_t stream = 0;        // consumer stream (the numeric phase and the transport read the arrays here)
-  cudaStream_t alloc_stream = 0;  // stream the arrays were allocated on (the build's); they are freed on it, see fe_pattern_free
-  cudaEvent_t ready = nullptr;    // recorded when the build's last kernel is queued: the result transport may ship the pattern's
-                                  // arrays while the integration and the numeric phase of the same call are still running
-};
 
 namespace {
 
@@ -1071,8 +1045,13 @@ int32_t dalloc(fegpu_ctx *ctx, T **p, size_t n) {
 
 }  // namespace
 
+void fe_pattern_retain(Pattern *p) {
+  if (p) p->refs++;
+}
+
 void fe_pattern_free(Pattern *p) {
   if (!p) return;
+  if (--p->refs > 0) return;  // an assembler result (or the dof map) still reads the arrays
   FE_TRACE("pattern_free: enter");
   // Stream-ordered frees into the context's block cache, no device synchronisation.  They are ordered on the stream the
   // blocks were ALLOCATED on (the build stream), behind the last use on the consumer stream by an event: a rebuild allocates
@@ -1112,6 +1091,11 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   fegpu_ctx *ctx = dm->ctx;
   fegpu_mesh *mesh = dm->mesh;
   cudaStream_t st = ctx->stream;
+  {  // small stencils with a node-major affine dof map: thread-per-node kernels (fegpu_tile.cu)
+    bool taken = false;
+    FE_TRY(fe_tile_build(dm, fork, &taken));
+    if (taken) return FEGPU_OK;
+  }
   if (dm->pat) { fe_pattern_free(dm->pat); dm->pat = nullptr; }
   Pattern *P = new Pattern();
   dm->pat = P;  // owned by the dofmap from here on (freed with it, also on error paths)
@@ -1172,6 +1156,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
     k_count_adj<<<grid_for(nadj, 256), 256, 0, st>>>(S, d_deg, d_arank, d_flags);
     ctx->launches++;
   }
+  fe_mark(ctx, "sym:k_count_adj");
   PT(dalloc(ctx, &P->d_adjptr, nn + 1));
   PT(fe_exclusive_scan_i32_to_i64(ctx, d_deg + lo, P->d_adjptr + lo, nw, 0, true, nullptr));
   PT(fe_max_i32_dev(ctx, d_deg + lo, nw, d_flags + 5));
@@ -1196,6 +1181,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   PC(cudaMemcpyAsync(&na, d_apos + nw, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   PC(cudaStreamSynchronize(st));
   FE_TRACE("build: sync A done");
+  fe_mark(ctx, "sym:scans_a");
   if (h_flags[0]) return bail();
   if (na < nn) {
     S.anodes = d_anodes;
@@ -1233,6 +1219,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
       ctx->launches++;
     }
   }
+  fe_mark(ctx, "sym:k_fill_adj");
   PT(dalloc(ctx, &P->d_nnbr, nn));
   PT(dalloc(ctx, &d_U, (size_t)nadj * nne));
   PT(dalloc(ctx, &d_sorted, nn));
@@ -1314,6 +1301,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
 #undef LAUNCH_NBR
   }
   ctx->launches++;
+  fe_mark(ctx, "sym:k_nbr");
   FE_TRACE("build: nbr kernel queued");
   PT(dalloc(ctx, &P->d_nbrptr, nn + 1));
   int64_t total_nbr = 0;
@@ -1343,6 +1331,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   PC(cudaMemcpyAsync(&tot, P->d_colptr + dhi, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   PC(cudaStreamSynchronize(st));
   FE_TRACE("build: sync B done");
+  fe_mark(ctx, "sym:scans_b");
   P->maxnbr = std::max(h_flags[6], 1);
   P->nnz = tot - 1;
   if (P->nnz != total_nbr * ndn * ndn) {
@@ -1389,6 +1378,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
     ctx->launches++;
   }
   PC(cudaGetLastError());
+  fe_mark(ctx, "sym:k_rows");
   {  // node visiting order of the gather.  Morton order (FEGPU_GATHER_ORDER=1) was measured on configs 2-4: it costs a
      // radix sort of the nodes per pattern build (+0.2 ms at 2.1 M nodes, +3 ms at 17 M) and saves < 0.1 ms of gather on
      // meshes whose numbering is already local, so the default is the natural order of the active nodes.
@@ -1405,6 +1395,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   }
   PC(cudaEventCreateWithFlags(&P->ready, cudaEventDisableTiming));
   PC(cudaEventRecord(P->ready, st));
+  fe_mark(ctx, "sym:finish");
   FE_TRACE("build: rows queued");
   cleanup();
   FE_TRACE("build: temporaries freed");
@@ -1420,6 +1411,11 @@ int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_n
   fegpu_mesh *mesh = dm->mesh;
   if (!P) return fegpu_fail(ctx, FEGPU_ERR_STATE, "no pattern");
   if (P->nnz == 0) return FEGPU_OK;
+  {
+    bool taken = false;
+    FE_TRY(fe_tile_gather(dm, d_V, compact, d_nzval, &taken));
+    if (taken) return FEGPU_OK;
+  }
   GatherParams G{mesh->nnodes, mesh->nne, dm->ndn, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, P->d_nnbr, P->d_nbrptr, P->d_cslot,
                  P->d_rank, dm->d_dof, P->d_colptr, d_V, d_nzval, P->maxnbr, P->maxdeg, P->maxcand, P->d_order, P->d_order ? P->norder : mesh->nnodes};
   const int EM = mesh->nne * dm->ndn;

@@ -19,6 +19,17 @@ void fe_trace(const char *label) {
   last = std::chrono::steady_clock::now();
 }
 
+void fe_mark(fegpu_ctx *ctx, const char *name) {
+  if (!ctx->marks_on) return;
+  if (ctx->nmarks >= (int)ctx->marks.size()) {
+    fegpu_ctx::Mark m{name, nullptr};
+    if (cudaEventCreate(&m.ev) != cudaSuccess) return;
+    ctx->marks.push_back(m);
+  }
+  ctx->marks[ctx->nmarks].name = name;
+  if (cudaEventRecord(ctx->marks[ctx->nmarks].ev, ctx->stream) == cudaSuccess) ctx->nmarks++;
+}
+
 namespace {
 
 constexpr int SCAN_THREADS = 256;

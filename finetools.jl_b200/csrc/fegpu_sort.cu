@@ -156,7 +156,16 @@ int32_t fe_reserve_bytes(fegpu_ctx *ctx, void **buf, size_t *cap, size_t need) {
   *buf = nullptr;
   *cap = 0;
   size_t want = need ? need : 8;
-  CUDA_TRY(ctx, cudaMalloc(buf, want));
+  cudaError_t e = cudaMalloc(buf, want);
+  if (e != cudaSuccess) {  // the symbolic phase's block cache may be sitting on freed blocks: hand them back and retry once
+    cudaGetLastError();
+    fe_dev_cache_trim(ctx);
+    e = cudaMalloc(buf, want);
+  }
+  if (e != cudaSuccess) {
+    *buf = nullptr;
+    return fegpu_fail(ctx, FEGPU_ERR_CUDA, std::string("cudaMalloc of ") + std::to_string(want) + " bytes: " + cudaGetErrorString(e));
+  }
   *cap = want;
   return FEGPU_OK;
 }

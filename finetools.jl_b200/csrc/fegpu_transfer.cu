@@ -257,6 +257,12 @@ static int32_t transfer_get(fegpu_ctx *ctx, Transfer **out) {
   // measured on the B200 hosts (profiles/r01_xfer_sweep.jsonl, r01_xfer_compress.jsonl): widening int32 chunks is fastest with 4
   // threads (more only steal memory bandwidth from the DMA); decoding row indices from neighbour lists (non-temporal streams) is at the nzval DMA time with 4-8
   nt = std::min(nt, 8);
+  // one process per GPU on a shared host (torchrun exports LOCAL_WORLD_SIZE): the ranks' pools together must not oversubscribe
+  // the cores -- 8 ranks x 8 threads on a 32-core box slowed every rank's decode down (round-1 SCALE run)
+  if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) {
+    const int lw = std::max(1, std::atoi(e));
+    nt = std::max(2, std::min(nt, (int)std::thread::hardware_concurrency() / lw));
+  }
   if (const char *e = std::getenv("FEGPU_HOST_THREADS")) nt = std::max(1, std::atoi(e));
   t->widen_threads = std::min(nt, 4);
   if (const char *e = std::getenv("FEGPU_WIDEN_THREADS")) t->widen_threads = std::max(1, std::min(nt, std::atoi(e)));

@@ -50,8 +50,18 @@ class FEMMBase:
         return self.integdomain.fes
 
 
+def _frozen(arr):
+    """True when nobody can have edited `arr` in place since we last saw it (read-only array, or a read-only view chain)."""
+    return isinstance(arr, np.ndarray) and not arr.flags.writeable
+
+
 class _DeviceMesh:
-    """Device twin of (fes, geom, rule): created once per FESet, coordinates refreshed on every form call."""
+    """Device twin of (fes, geom, rule), owned by the GPUContext (one per FESet connectivity, shared by every assembler on that
+    device, so the reference's idiom of a fresh assembler per call -- FEMMBaseModule.jl:1374, 1408 -- still finds the uploaded
+    mesh and the cached sparsity pattern).  Coordinates are refreshed on every form call.
+
+    Cache keys are content-safe: a hit is accepted on object identity only when the host array is read-only (what
+    numberdofs / slab_owner / pointpartitioning hand out), otherwise the arrays are compared in full."""
 
     def __init__(self, ctx, fes, geom):
         self.ctx = ctx
@@ -61,22 +71,37 @@ class _DeviceMesh:
         conn = np.ascontiguousarray(fes.conn, dtype=np.int64)
         check(_lib.lib().fegpu_mesh_upload(ctx.handle, fes.etype, conn.shape[0], fptr(conn), self.nnodes, self.sdim, fptr(xyz),
                                            C.byref(self.handle)), ctx.handle)
-        self.conn_ref = fes.conn
+        self.conn_ref = fes.conn    # keeps the array (and therefore its id) alive while the twin exists
         self.rule_key = None
-        self.dofmaps = []   # [(host copy of dofnums, nalldofs, handle)]
-        self._dofkeys = {}  # handle -> (id(u), numbering version, id(dofnums)) it was last matched with
+        self.dofmaps = []           # [(host copy or frozen original of dofnums, nalldofs, handle)]
+        self._dofkeys = {}          # handle -> (id(u), numbering version, id(dofnums)) it was last matched with
         self.partition_key = None
+        self._owner_copy = None
+        self.h2d_bytes_last = xyz.nbytes
 
     def update_geometry(self, geom):
+        """Coordinates host -> device; a partitioned mesh ships only the node window of its active elements."""
         xyz = _lib.colmajor_f64(geom.values)
         if xyz.shape != (self.nnodes, self.sdim):
             raise FEGPUError(-2, "geometry field changed shape; build a new FESet / assembler")
-        check(_lib.lib().fegpu_geom_update(self.handle, fptr(xyz)), self.ctx.handle)
+        if self.partition_key is None:
+            check(_lib.lib().fegpu_geom_update(self.handle, fptr(xyz)), self.ctx.handle)
+            self.h2d_bytes_last = xyz.nbytes
+        else:
+            check(_lib.lib().fegpu_geom_update_window(self.handle, fptr(xyz)), self.ctx.handle)
+            lo, hi, _ = self.window()
+            self.h2d_bytes_last = (hi - lo) * self.sdim * 8
+
+    def window(self):
+        lo, hi, na = C.c_int64(), C.c_int64(), C.c_int64()
+        check(_lib.lib().fegpu_mesh_window(self.handle, C.byref(lo), C.byref(hi), C.byref(na)), self.ctx.handle)
+        return lo.value, hi.value, na.value
 
     def set_rule(self, integdomain):
         check(_lib.lib().fegpu_otherdimension_set(self.handle, float(integdomain.otherdimension)), self.ctx.handle)
         rule = integdomain.integration_rule
-        key = (id(rule), rule.npts)
+        # keyed on the rule's own numbers, not on its identity (ids are recycled; two rules may share a point count)
+        key = (rule.npts, np.asarray(rule.param_coords, dtype=np.float64).tobytes(), np.asarray(rule.weights, dtype=np.float64).tobytes())
         if key == self.rule_key:
             return
         npts, Ns, gradNparams, w, _ = integrationdata(integdomain)
@@ -87,31 +112,33 @@ class _DeviceMesh:
         self.rule_key = key
 
     def set_partition(self, node_owner, my_rank):
-        key = None if node_owner is None else (id(node_owner), int(my_rank))
-        if key == self.partition_key:
-            return
         if node_owner is None:
-            check(_lib.lib().fegpu_partition_set(self.handle, None, 0), self.ctx.handle)
-        else:
-            own = np.ascontiguousarray(node_owner, dtype=np.int32)
-            if own.size != self.nnodes:
-                raise FEGPUError(-2, "node_owner must have one entry per node")
-            check(_lib.lib().fegpu_partition_set(self.handle, fptr(own), int(my_rank)), self.ctx.handle)
-            self._owner_keepalive = node_owner
-        self.partition_key = key
+            if self.partition_key is not None:
+                check(_lib.lib().fegpu_partition_set(self.handle, None, 0), self.ctx.handle)
+                self.partition_key, self._owner_copy = None, None
+            return
+        own = np.ascontiguousarray(node_owner, dtype=np.int32)
+        if own.size != self.nnodes:
+            raise FEGPUError(-2, "node_owner must have one entry per node")
+        if self.partition_key is not None and self.partition_key[1] == int(my_rank):
+            same_obj = self.partition_key[0] == id(node_owner) and _frozen(node_owner)
+            if same_obj or np.array_equal(self._owner_copy, own):
+                return
+        check(_lib.lib().fegpu_partition_set(self.handle, fptr(own), int(my_rank)), self.ctx.handle)
+        # a frozen array is kept by reference (its id stays valid); anything else is copied and compared by content next time
+        self._owner_copy = node_owner if _frozen(node_owner) else own.copy()
+        self.partition_key = (id(node_owner), int(my_rank))
 
     def dofmap(self, u):
         dn = u.dofnums
         nall = u.nalldofs()
         key = (id(u), getattr(u, "_dofver", None), id(dn))
-        step = max(1, dn.size // 4096)
         for host, n, h in self.dofmaps:
             if n != nall or host.shape != dn.shape:
                 continue
-            # same field object and numbering version: a strided sample guards against in-place edits; otherwise compare all
-            if (key[1] is not None and self._dofkeys.get(h.value) == key and host.flags.f_contiguous == dn.flags.f_contiguous
-                    and np.array_equal(host.ravel(order="K")[::step], dn.ravel(order="K")[::step])) \
-                    or np.array_equal(host, dn):
+            # identity + numbering version is trusted only for a read-only dofnums array (numberdofs freezes it: in-place edits
+            # raise, a replaced array has another id); anything else is compared in full
+            if (key[1] is not None and self._dofkeys.get(h.value) == key and _frozen(dn)) or np.array_equal(host, dn):
                 self._dofkeys[h.value] = key
                 return h
         if dn.shape[0] != self.nnodes:
@@ -119,13 +146,17 @@ class _DeviceMesh:
         d = _lib.colmajor_i64(dn)
         h = VP()
         check(_lib.lib().fegpu_dofmap_upload(self.ctx.handle, self.handle, dn.shape[1], fptr(d), nall, nall, C.byref(h)), self.ctx.handle)
-        self.dofmaps.append((dn.copy(order="K"), nall, h))
+        self.dofmaps.append((dn if _frozen(dn) else dn.copy(order="K"), nall, h))
         self._dofkeys[h.value] = key
         if len(self.dofmaps) > 4:
             _, _, old = self.dofmaps.pop(0)
             self._dofkeys.pop(old.value, None)
             _lib.lib().fegpu_dofmap_destroy(old)
         return h
+
+    def invalidate_patterns(self):
+        for _, _, h in self.dofmaps:
+            check(_lib.lib().fegpu_pattern_invalidate(h), self.ctx.handle)
 
     def destroy(self):
         for _, _, h in self.dofmaps:
@@ -137,16 +168,24 @@ class _DeviceMesh:
 
 
 def _device_mesh(assembler, fes, geom):
-    cache = assembler._device_cache
-    dm = cache.get(id(fes))
-    if dm is None or dm.conn_ref is not fes.conn:
-        if dm is not None:
-            dm.destroy()
-        dm = _DeviceMesh(assembler.ctx, fes, geom)
-        cache[id(fes)] = dm
-    else:
-        dm.update_geometry(geom)
-    return dm
+    """The context's twin of this FESet (created on first use, least recently used twins are destroyed beyond
+    GPUContext.MAX_MESHES).  The geometry is NOT refreshed here: _prepare does it after the partition is known."""
+    ctx = assembler.ctx
+    cache = ctx._meshes
+    key = id(fes.conn)
+    dm = cache.get(key)
+    if dm is not None and dm.conn_ref is fes.conn:
+        cache.move_to_end(key)
+        return dm, False
+    if dm is not None:
+        dm.destroy()
+        del cache[key]
+    dm = _DeviceMesh(ctx, fes, geom)
+    cache[key] = dm
+    while len(cache) > ctx.MAX_MESHES:
+        _, old = cache.popitem(last=False)
+        old.destroy()
+    return dm, True
 
 
 def _inner(assembler):
@@ -170,7 +209,7 @@ def _eligible(self, assembler, geom, u, cf):
 def _prepare(self, assembler, geom, u, node_owner=None, my_rank=0):
     fes = self.integdomain.fes
     assembler = _inner(assembler)
-    dmesh = _device_mesh(assembler, fes, geom)
+    dmesh, fresh = _device_mesh(assembler, fes, geom)
     dmesh.set_rule(self.integdomain)
     if self.mcsys.isidentity:
         check(_lib.lib().fegpu_csys_set(dmesh.handle, None), assembler.ctx.handle)
@@ -180,7 +219,10 @@ def _prepare(self, assembler, geom, u, node_owner=None, my_rank=0):
         rm = np.asfortranarray(self.mcsys.csmat)
         check(_lib.lib().fegpu_csys_set(dmesh.handle, fptr(rm)), assembler.ctx.handle)
     dmesh.set_partition(node_owner, my_rank)
+    if not fresh:
+        dmesh.update_geometry(geom)  # the upload of a new twin already carried the coordinates
     dof = dmesh.dofmap(u)
+    assembler._last_mesh = dmesh
     return fes, dmesh, dof
 
 

@@ -77,7 +77,12 @@ def numberdofs(self, entperm=None, kinds=(DOF_KIND_FREE, DOF_KIND_DATA)):
         flat[sel] = np.arange(nxt, nxt + sel.size)
         self.ranges.append((nxt, nxt + sel.size - 1))
         nxt += sel.size
-    self.dofnums[perm, :] = flat.reshape(n, dim)
+    dn = np.zeros(self.values.shape, dtype=np.int64, order="F")
+    dn[perm, :] = flat.reshape(n, dim)
+    # a NEW, read-only array per numbering: device dof maps are cached against (field, version, array) and a frozen array cannot
+    # be edited behind the cache's back (an in-place write raises; whoever wants other numbers renumbers or replaces the array)
+    dn.flags.writeable = False
+    self.dofnums = dn
     self._dofver = getattr(self, "_dofver", 0) + 1
     return self
 

@@ -10,7 +10,9 @@ import numpy as np
 
 def slab_owner(nnodes, nparts):
     """owner = floor(node * P / nnodes), 0-based ranks, contiguous ascending node ranges."""
-    return ((np.arange(nnodes, dtype=np.int64) * int(nparts)) // int(nnodes)).astype(np.int32)
+    own = ((np.arange(nnodes, dtype=np.int64) * int(nparts)) // int(nnodes)).astype(np.int32)
+    own.flags.writeable = False  # device partitions are cached against the array: frozen = trusted by identity
+    return own
 
 
 def pointpartitioning(xyz, npartitions=2):

@@ -73,6 +73,12 @@ int32_t fegpu_cache_release(fegpu_ctx *ctx);
 int64_t fegpu_launch_count(fegpu_ctx *ctx);
 /* roofline denominators measured by the library itself: FP64 FMA peak (TFLOP/s) and copy bandwidth (GB/s) */
 int32_t fegpu_measure_peaks(fegpu_ctx *ctx, double *dfma_tflops, double *copy_gbs);
+/* Per-kernel device times of ONE step: fegpu_marks_begin starts recording named CUDA events on the context's stream at the
+ * boundaries of the library's kernels (run the step with fegpu_set_overlap(ctx, 0) so that it stays on one stream);
+ * fegpu_marks_read synchronises, stops recording and writes "name=ms;name=ms;..." -- the time since the previous mark --
+ * into buf (NUL-terminated, truncated at cap).  Measurement aid of bench.py (roofline.achieved); nothing of the reference. */
+int32_t fegpu_marks_begin(fegpu_ctx *ctx);
+int32_t fegpu_marks_read(fegpu_ctx *ctx, char *buf, int64_t cap);
 
 /* -- mesh: replaces the per-element gathers of fes.conn (FESetModule.jl:61) and geom.values
  *    (gathervalues_asmat!, FieldModule.jl:263-275): uploaded once ------------------------------------- */
@@ -81,6 +87,11 @@ int32_t fegpu_mesh_upload(fegpu_ctx *ctx, int32_t etype, int64_t nelem, const in
 int32_t fegpu_mesh_destroy(fegpu_mesh *mesh);
 /* new coordinates for the same connectivity (pattern cache stays valid) */
 int32_t fegpu_geom_update(fegpu_mesh *mesh, const double *xyz);
+/* The same for a partitioned mesh (fegpu_partition_set): only the coordinates of the node window [lo, hi) that holds every
+ * node of this rank's active elements cross the link (xyz is still the whole nnodes x sdim array).  fegpu_mesh_window
+ * reports that window (0-based, hi exclusive; the whole mesh when it is not partitioned) and the active element count. */
+int32_t fegpu_geom_update_window(fegpu_mesh *mesh, const double *xyz);
+int32_t fegpu_mesh_window(fegpu_mesh *mesh, int64_t *lo, int64_t *hi, int64_t *nactive);
 /* quadrature tables exactly as the caller's integrationdata() produced them (IntegDomainModule.jl:631-648):
  * Ns [npts][nne], gradNpar [npts][mdim][nne] (i.e. each point's nne x mdim matrix, column-major), w [npts] */
 int32_t fegpu_rule_set(fegpu_mesh *mesh, int32_t npts, const double *Ns, const double *gradNpar, const double *w);
@@ -203,6 +214,9 @@ int32_t fegpu_last_timings(fegpu_asm *as, double ms[4]);
 int32_t fegpu_pattern_was_cached(fegpu_asm *as);
 /* forget a dofmap's cached pattern (forces the next assembly to rebuild it) */
 int32_t fegpu_pattern_invalidate(fegpu_dofmap *dofmap);
+/* Which symbolic path built the dof map's cached pattern: 0 = none cached, 1 = group / warp kernels (fegpu_pattern.cu: every
+ * element type and numbering), 2 = thread-per-node kernels (fegpu_tile.cu: small stencils, node-major affine dof map). */
+int32_t fegpu_pattern_path(fegpu_dofmap *dofmap);
 
 #ifdef __cplusplus
 }

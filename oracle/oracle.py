@@ -147,12 +147,14 @@ def _rm(Rm):
     return buf, buf.ctypes.data_as(C.c_void_p)
 
 
-def bilform_diffusion_coo(et, conn, xyz, dofnums, nalldofs, pc, w, kappa, otherdim=1.0, Rm=None):
-    """Reference-order COO triplets (I, J, V) of bilform_diffusion; kappa scalar -> iso path, matrix -> general."""
+def bilform_diffusion_coo(et, conn, xyz, dofnums, nalldofs, pc, w, kappa, otherdim=1.0, Rm=None, out=None):
+    """Reference-order COO triplets (I, J, V) of bilform_diffusion; kappa scalar -> iso path, matrix -> general.
+    out = preallocated (I, J, V) contiguous slices for these elements (several threads may fill one COO buffer)."""
     conn, nelem, nne, X, nnodes, sdim, dn, ndn, P, W, npts = _prep(et, conn, xyz, dofnums, pc, w)
     assert ndn == 1
     n = nelem * nne * nne
-    I, J, V = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n)
+    I, J, V = out if out is not None else (np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n))
+    assert I.size == n
     kind = 0 if np.ndim(kappa) == 0 else 1
     kap = _F(np.atleast_2d(np.asarray(kappa, dtype=np.float64)))
     rmbuf, rmp = _rm(Rm)
