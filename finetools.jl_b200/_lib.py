@@ -25,6 +25,8 @@ SIGNATURES = {
     "fegpu_cache_release": (C.c_int32, [VP]),
     "fegpu_launch_count": (C.c_int64, [VP]),
     "fegpu_measure_peaks": (C.c_int32, [VP, c_f64p, c_f64p]),
+    "fegpu_host_alloc": (C.c_int32, [C.POINTER(VP), C.c_int64]),
+    "fegpu_host_free": (C.c_int32, [VP]),
     "fegpu_marks_begin": (C.c_int32, [VP]),
     "fegpu_marks_read": (C.c_int32, [VP, VP, C.c_int64]),
     "fegpu_geom_update_window": (C.c_int32, [VP, VP]),

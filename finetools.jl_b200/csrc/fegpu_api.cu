@@ -82,13 +82,16 @@ __global__ void k_elem_active(const int32_t *__restrict__ conn, int64_t nelem, i
 }
 
 // compact upper-block layout -> full element matrix, emission order (thread per full entry)
-__global__ void k_expand_compact(const double *__restrict__ Vc, double *__restrict__ Vf, int64_t nelem, int nne, int ndn) {
+// perm (optional): output element r is the element of slot perm[r]
+__global__ void k_expand_compact(const double *__restrict__ Vc, double *__restrict__ Vf, int64_t nelem, int nne, int ndn,
+                                 const int32_t *__restrict__ perm) {
   const int EM = nne * ndn;
   const int64_t EM2 = (int64_t)EM * EM, CS = (int64_t)(nne * (nne + 1) / 2) * ndn * ndn;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nelem * EM2) return;
-  const int64_t e = i / EM2;
-  const int k = (int)(i - e * EM2), c = k / EM, r = k - c * EM;
+  const int64_t eo = i / EM2;
+  const int64_t e = perm ? (int64_t)perm[eo] : eo;
+  const int k = (int)(i - eo * EM2), c = k / EM, r = k - c * EM;
   const int li = r / ndn, p = r - li * ndn, lc = c / ndn, q = c - lc * ndn, nd2 = ndn * ndn;
   const int off = (li <= lc) ? nd2 * (lc * (lc + 1) / 2 + li) + q * ndn + p : nd2 * (li * (li + 1) / 2 + lc) + p * ndn + q;
   Vf[i] = Vc[e * CS + off];
@@ -175,10 +178,18 @@ struct DeviceGuard {
 
 }  // namespace
 
-int32_t fe_expand_compact(fegpu_ctx *ctx, const double *d_Vc, double *d_Vfull, int64_t nelem, int nne, int ndn) {
+// full element matrices permuted: out[r] = in[perm[r]]
+__global__ void k_permute_records(const double *__restrict__ in, double *__restrict__ out, int64_t nelem, int64_t rec, const int32_t *__restrict__ perm) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nelem * rec) return;
+  const int64_t eo = i / rec;
+  out[i] = in[(int64_t)perm[eo] * rec + (i - eo * rec)];
+}
+
+int32_t fe_expand_compact(fegpu_ctx *ctx, const double *d_Vc, double *d_Vfull, int64_t nelem, int nne, int ndn, const int32_t *d_perm) {
   const int64_t n = nelem * (int64_t)(nne * ndn) * (nne * ndn);
   if (n == 0) return FEGPU_OK;
-  k_expand_compact<<<grid_for(n, 256), 256, 0, ctx->stream>>>(d_Vc, d_Vfull, nelem, nne, ndn);
+  k_expand_compact<<<grid_for(n, 256), 256, 0, ctx->stream>>>(d_Vc, d_Vfull, nelem, nne, ndn, d_perm);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return FEGPU_OK;
@@ -255,6 +266,19 @@ int32_t fegpu_synchronize(fegpu_ctx *ctx) {
   return FEGPU_OK;
 }
 int64_t fegpu_launch_count(fegpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t fegpu_host_alloc(void **p, int64_t bytes) {
+  if (!p || bytes < 0) return fegpu_fail(nullptr, FEGPU_ERR_ARG, "bad argument");
+  *p = nullptr;
+  cudaError_t e = cudaHostAlloc(p, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocPortable);
+  if (e != cudaSuccess) return fegpu_fail(nullptr, FEGPU_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  return FEGPU_OK;
+}
+
+int32_t fegpu_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+  return FEGPU_OK;
+}
 
 int32_t fegpu_marks_begin(fegpu_ctx *ctx) {
   if (!ctx) return FEGPU_ERR_ARG;
@@ -389,6 +413,12 @@ int32_t fegpu_mesh_upload(fegpu_ctx *ctx, int32_t etype, int64_t nelem, const in
   if (h_err) return fail(FEGPU_ERR_ARG, "connectivity refers to a node outside 1..nnodes");
   cudaFree(d_c64);
   cudaFree(d_err);
+  d_c64 = nullptr;
+  d_err = nullptr;
+  {  // internal element order: ascending smallest node id (locality of the element records with respect to the node-ordered output)
+    const int32_t s = fe_order_elements(m);
+    if (s != FEGPU_OK) { fegpu_mesh_destroy(m); return s; }
+  }
   *out = m;
   return FEGPU_OK;
 }
@@ -397,6 +427,7 @@ int32_t fegpu_mesh_destroy(fegpu_mesh *m) {
   if (!m) return FEGPU_OK;
   DeviceGuard g(m->ctx->device);
   cudaFree(m->d_uvel);
+  cudaFree(m->d_orig);
   cudaFree(m->d_conn); cudaFree(m->d_xyz); cudaFree(m->d_tab); cudaFree(m->d_w); cudaFree(m->d_elem_list); cudaFree(m->d_rowowned);
   delete m;
   return FEGPU_OK;
@@ -918,7 +949,7 @@ __global__ void k_lump(const double *__restrict__ V, int64_t nmat, int EM, const
 
 // (I, J) of bilform_masslike's triplets in the reference's emission order: element e contributes an ndn x EM matrix whose rows
 // are the element's own ndn global rows (e-1)*ndn + 1 .. e*ndn (FEMMBaseModule.jl:1907-1908)
-__global__ void k_emit_masslike_ij(const int32_t *__restrict__ conn, int64_t nelem, int nne, int ndn, int64_t nnodes,
+__global__ void k_emit_masslike_ij(const int32_t *__restrict__ conn, const int32_t *__restrict__ orig, int64_t nelem, int nne, int ndn, int64_t nnodes,
                                    const int32_t *__restrict__ dof, int64_t *__restrict__ I, int64_t *__restrict__ J) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int per = ndn * nne * ndn;
@@ -926,7 +957,7 @@ __global__ void k_emit_masslike_ij(const int32_t *__restrict__ conn, int64_t nel
   const int64_t e = t / per;
   const int rem = (int)(t - e * per);
   const int p = rem % ndn, c = rem / ndn;
-  I[t] = e * ndn + p + 1;
+  I[t] = (orig ? (int64_t)orig[e] : e) * ndn + p + 1;  // rows are numbered by the CALLER's element ids
   J[t] = (int64_t)dof[(int64_t)(c % ndn) * nnodes + conn[e * nne + c / ndn]] + 1;
 }
 
@@ -1042,7 +1073,7 @@ int32_t fegpu_bilform_masslike(fegpu_mesh *mesh, fegpu_dofmap *dm, const double 
     return fegpu_fail(ctx, FEGPU_ERR_CUDA, "out of device memory");
   }
   if (n) {
-    k_emit_masslike_ij<<<grid_for(n, 256), 256, 0, st>>>(mesh->d_conn, mesh->nelem, mesh->nne, dm->ndn, mesh->nnodes, dm->d_dof, dI, dJ);
+    k_emit_masslike_ij<<<grid_for(n, 256), 256, 0, st>>>(mesh->d_conn, mesh->d_orig, mesh->nelem, mesh->nne, dm->ndn, mesh->nnodes, dm->d_dof, dI, dJ);
     ctx->launches++;
   }
   const int32_t s = fe_coo_to_csc(as, n, dI, dJ, as->d_V, mesh->nelem * dm->ndn, dm->col_nall);
@@ -1379,32 +1410,42 @@ int32_t fegpu_coo_copy(fegpu_asm *as, fegpu_mesh *mesh, fegpu_dofmap *dm, int64_
   DeviceGuard g(ctx->device);
   cudaStream_t st = ctx->stream;
   if (n == 0) return FEGPU_OK;
+  // the element values sit in internal (slot) order; the reference emits element after element in ITS order
+  int32_t *d_perm = nullptr;
+  CUDA_TRY(ctx, cudaMalloc((void **)&d_perm, sizeof(int32_t) * (size_t)mesh->nactive));
+  int32_t ps = fe_emission_order(mesh, d_perm);
+  if (ps != FEGPU_OK) { cudaFree(d_perm); return ps; }
   if (I || J) {
     int64_t *dI = nullptr, *dJ = nullptr;
-    CUDA_TRY(ctx, cudaMalloc((void **)&dI, sizeof(int64_t) * n));
-    cudaError_t e = cudaMalloc((void **)&dJ, sizeof(int64_t) * n);
-    if (e != cudaSuccess) { cudaFree(dI); return fegpu_fail(ctx, FEGPU_ERR_CUDA, cudaGetErrorString(e)); }
-    int32_t s = fe_emit_ij(dm, dI, dJ);
+    cudaError_t e = cudaMalloc((void **)&dI, sizeof(int64_t) * n);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dJ, sizeof(int64_t) * n);
+    if (e != cudaSuccess) { cudaFree(dI); cudaFree(d_perm); return fegpu_fail(ctx, FEGPU_ERR_CUDA, cudaGetErrorString(e)); }
+    int32_t s = fe_emit_ij(dm, dI, dJ, d_perm);
     if (s == FEGPU_OK && I && cudaMemcpyAsync(I, dI, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st) != cudaSuccess) s = FEGPU_ERR_CUDA;
     if (s == FEGPU_OK && J && cudaMemcpyAsync(J, dJ, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st) != cudaSuccess) s = FEGPU_ERR_CUDA;
     cudaStreamSynchronize(st);
     cudaFree(dI);
     cudaFree(dJ);
-    FE_TRY(s);
+    if (s != FEGPU_OK) { cudaFree(d_perm); return s; }
   }
-  if (V && as->V_compact) {
-    // the fast path stored the compact symmetric layout: expand to the reference's emission order for export
+  if (V) {
     double *dfull = nullptr;
-    CUDA_TRY(ctx, cudaMalloc((void **)&dfull, sizeof(double) * n));
-    int32_t s = fe_expand_compact(ctx, as->d_V, dfull, mesh->nactive, mesh->nne, dm->ndn);
+    cudaError_t e = cudaMalloc((void **)&dfull, sizeof(double) * n);
+    if (e != cudaSuccess) { cudaFree(d_perm); return fegpu_fail(ctx, FEGPU_ERR_CUDA, cudaGetErrorString(e)); }
+    int32_t s = FEGPU_OK;
+    if (as->V_compact) {  // the fast path stored the compact symmetric layout: expand to full matrices on the way
+      s = fe_expand_compact(ctx, as->d_V, dfull, mesh->nactive, mesh->nne, dm->ndn, d_perm);
+    } else {
+      k_permute_records<<<grid_for(n, 256), 256, 0, st>>>(as->d_V, dfull, mesh->nactive, (int64_t)EM * EM, d_perm);
+      ctx->launches++;
+    }
     if (s == FEGPU_OK && cudaMemcpyAsync(V, dfull, sizeof(double) * n, cudaMemcpyDeviceToHost, st) != cudaSuccess) s = FEGPU_ERR_CUDA;
     cudaStreamSynchronize(st);
     cudaFree(dfull);
-    FE_TRY(s);
-  } else if (V) {
-    CUDA_TRY(ctx, cudaMemcpyAsync(V, as->d_V, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (s != FEGPU_OK) { cudaFree(d_perm); return s; }
   }
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  cudaFree(d_perm);
   return FEGPU_OK;
 }
 

@@ -48,7 +48,8 @@ struct fegpu_mesh {
   fegpu_ctx *ctx = nullptr;
   int etype = 0, nne = 0, mdim = 0, sdim = 0;
   int64_t nelem = 0, nnodes = 0;
-  int32_t *d_conn = nullptr;  // [nelem][nne] 0-based
+  int32_t *d_conn = nullptr;  // [nelem][nne] 0-based, in INTERNAL element order (ascending smallest node id, fe_order_elements)
+  int32_t *d_orig = nullptr;  // [nelem] the caller's element id of internal element i (nullptr = identity)
   double *d_xyz = nullptr;    // [sdim][nnodes]
   double rm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // constant material coordinate system matrix, sdim x mdim col-major (fegpu_csys_set)
   bool use_rm = false;        // false = identity (the FEMMBase default, FEMMBaseModule.jl:82-84)
@@ -229,14 +230,17 @@ int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_n
 // entries in ascending element order (= the reference's element loop); rows of nodes this rank does not own stay zero
 int32_t fe_vec_gather(fegpu_dofmap *dm, const double *d_elvec, double *d_F);
 // compact symmetric layout -> full element matrices in emission order (raw-COO export only)
-int32_t fe_expand_compact(fegpu_ctx *ctx, const double *d_Vc, double *d_Vfull, int64_t nelem, int nne, int ndn);
+int32_t fe_expand_compact(fegpu_ctx *ctx, const double *d_Vc, double *d_Vfull, int64_t nelem, int nne, int ndn, const int32_t *d_perm = nullptr);
 
 // ---- generic COO -> CSC by sort (fegpu_sort.cu) --------------------------------------------------------
 // d_I, d_J 1-based int64, n triplets in emission order.  Fills the assembler's own colptr/rowval/nzval.
 int32_t fe_coo_to_csc(fegpu_asm *as, int64_t n, const int64_t *d_I, const int64_t *d_J, const double *d_V, int64_t nrows,
                       int64_t ncols);
 // emit the reference-order (I, J) of a bilform assembly (AssemblyModule.jl:266-279) from conn + dof map
-int32_t fe_emit_ij(fegpu_dofmap *dm, int64_t *d_I, int64_t *d_J);
+int32_t fe_emit_ij(fegpu_dofmap *dm, int64_t *d_I, int64_t *d_J, const int32_t *d_perm = nullptr);
+// internal element order (ascending smallest node id) at upload; emission-order permutation for the raw-COO export
+int32_t fe_order_elements(fegpu_mesh *mesh);
+int32_t fe_emission_order(fegpu_mesh *mesh, int32_t *d_perm /* [nactive]: rank in the caller's order -> slot */);
 // Morton order of (a subset of) the nodes (spatial locality for the gather's L2 reuse): d_order [n]
 int32_t fe_morton_order(fegpu_mesh *mesh, const int32_t *d_nodes /* subset or nullptr = all */, int64_t n, int32_t *d_order);
 

@@ -5,6 +5,8 @@
 //   key = (col-1) << 32 | (row-1)  -> stable LSD radix sort (8-bit digits, only the digits the matrix size needs) of
 //   (key, triplet id) -> segment heads -> colptr / rowval -> nzval[k] = sum of V[id] over the segment in ascending
 //   triplet id (stable sort => the reference's left-to-right sum).  Explicit zeros are kept.
+#include <cstdlib>
+
 #include "fegpu_internal.h"
 
 namespace {
@@ -127,14 +129,16 @@ __global__ void k_segsum(const uint32_t *__restrict__ ids, const double *__restr
   nzval[s] = v;
 }
 
+// perm (optional): output position r takes the element of slot perm[r] (the caller's element order for the raw-COO export)
 __global__ void k_emit_ij(const int32_t *__restrict__ conn, const int32_t *__restrict__ elem_list, int64_t nactive, int nne, int ndn,
-                          int64_t nnodes, const int32_t *__restrict__ dof, int64_t *__restrict__ I, int64_t *__restrict__ J) {
+                          int64_t nnodes, const int32_t *__restrict__ dof, int64_t *__restrict__ I, int64_t *__restrict__ J,
+                          const int32_t *__restrict__ perm) {
   const int EM = nne * ndn;
   const int64_t EM2 = (int64_t)EM * EM;
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nactive * EM2) return;
-  const int64_t slot = t / EM2;
-  const int loc = (int)(t - slot * EM2);
+  const int64_t slot = perm ? (int64_t)perm[t / EM2] : t / EM2;
+  const int loc = (int)(t - (t / EM2) * EM2);
   const int c = loc / EM, r = loc - c * EM;
   const int64_t e = elem_list ? elem_list[slot] : slot;
   const int32_t *cn = conn + e * nne;
@@ -177,13 +181,13 @@ int32_t fe_asm_reserve(fegpu_asm *as, double **buf, size_t *cap, size_t need_dou
   return s;
 }
 
-int32_t fe_emit_ij(fegpu_dofmap *dm, int64_t *d_I, int64_t *d_J) {
+int32_t fe_emit_ij(fegpu_dofmap *dm, int64_t *d_I, int64_t *d_J, const int32_t *d_perm) {
   fegpu_mesh *mesh = dm->mesh;
   const int EM = mesh->nne * dm->ndn;
   const int64_t n = mesh->nactive * EM * EM;
   if (n == 0) return FEGPU_OK;
   k_emit_ij<<<grid_for(n, 256), 256, 0, dm->ctx->stream>>>(mesh->d_conn, mesh->d_elem_list, mesh->nactive, mesh->nne, dm->ndn, mesh->nnodes,
-                                                          dm->d_dof, d_I, d_J);
+                                                          dm->d_dof, d_I, d_J, d_perm);
   dm->ctx->launches++;
   CUDA_TRY(dm->ctx, cudaGetLastError());
   return FEGPU_OK;
@@ -295,6 +299,124 @@ int32_t fe_morton_order(fegpu_mesh *mesh, const int32_t *d_nodes, int64_t n, int
   }
   cleanup();
   return rc;
+}
+
+namespace {
+__global__ void k_elem_minnode_keys(const int32_t *__restrict__ conn, int64_t nelem, int nne, unsigned long long *__restrict__ keys,
+                                    uint32_t *__restrict__ ids) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nelem) return;
+  int mn = conn[e * nne];
+  for (int k = 1; k < nne; k++) mn = min(mn, conn[e * nne + k]);
+  keys[e] = (unsigned long long)(unsigned)mn;
+  ids[e] = (uint32_t)e;
+}
+__global__ void k_permute_conn(const int32_t *__restrict__ conn_in, const uint32_t *__restrict__ ids, int64_t nelem, int nne,
+                               int32_t *__restrict__ conn_out, int32_t *__restrict__ orig) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nelem * nne) return;
+  const int64_t i = t / nne;
+  const int k = (int)(t - i * nne);
+  const uint32_t e = ids[i];
+  conn_out[t] = conn_in[(int64_t)e * nne + k];
+  if (k == 0) orig[i] = (int32_t)e;
+}
+__global__ void k_orig_keys(const int32_t *__restrict__ orig, const int32_t *__restrict__ elem_list, int64_t nactive,
+                            unsigned long long *__restrict__ keys, uint32_t *__restrict__ ids) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nactive) return;
+  const int64_t e = elem_list ? (int64_t)elem_list[s] : s;
+  keys[s] = (unsigned long long)(unsigned)(orig ? orig[e] : (int32_t)e);
+  ids[s] = (uint32_t)s;
+}
+__global__ void k_copy_u32(const uint32_t *__restrict__ in, int32_t *__restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int32_t)in[i];
+}
+
+// scratch of one radix sort of n (key, id) pairs
+struct SortScratch {
+  fegpu_ctx *ctx;
+  unsigned long long *kA = nullptr, *kB = nullptr;
+  uint32_t *iA = nullptr, *iB = nullptr;
+  int32_t *hist = nullptr;
+  int64_t *offs = nullptr;
+  explicit SortScratch(fegpu_ctx *c) : ctx(c) {}
+  int32_t alloc(int64_t n) {
+    const int64_t ntiles = (n + RS_TILE - 1) / RS_TILE;
+    cudaStream_t st = ctx->stream;
+    FE_TRY(fe_dev_alloc(ctx, (void **)&kA, sizeof(unsigned long long) * n, st));
+    FE_TRY(fe_dev_alloc(ctx, (void **)&kB, sizeof(unsigned long long) * n, st));
+    FE_TRY(fe_dev_alloc(ctx, (void **)&iA, sizeof(uint32_t) * n, st));
+    FE_TRY(fe_dev_alloc(ctx, (void **)&iB, sizeof(uint32_t) * n, st));
+    FE_TRY(fe_dev_alloc(ctx, (void **)&hist, sizeof(int32_t) * 256 * ntiles, st));
+    FE_TRY(fe_dev_alloc(ctx, (void **)&offs, sizeof(int64_t) * (256 * ntiles + 1), st));
+    return FEGPU_OK;
+  }
+  ~SortScratch() {
+    void *ptrs[] = {kA, kB, iA, iB, hist, offs};
+    for (void *q : ptrs)
+      if (q) fe_dev_free(ctx, q, ctx->stream);
+  }
+};
+}  // namespace
+
+// Internal element order = ascending smallest node id (stable: ties keep the caller's order).  The outputs of the assembly are in
+// node / dof order, so this is the order in which element records are produced and consumed with locality: the a-th adjacent
+// element of node n and of node n+1 then sit next to each other in the element-value array, whatever order the caller's FESet
+// lists its elements in (H8block numbers elements z-fastest and nodes x-fastest: neighbouring nodes' elements are 65 536
+// records apart).  conn is permuted in place (through a temporary); orig[i] = the caller's id of internal element i.
+int32_t fe_order_elements(fegpu_mesh *mesh) {
+  fegpu_ctx *ctx = mesh->ctx;
+  cudaStream_t st = ctx->stream;
+  const int64_t n = mesh->nelem;
+  static const bool off = std::getenv("FEGPU_ELEM_ORDER") && std::atoi(std::getenv("FEGPU_ELEM_ORDER")) == 0;  // A/B knob
+  if (n == 0 || off) return FEGPU_OK;
+  SortScratch S(ctx);
+  FE_TRY(S.alloc(n));
+  k_elem_minnode_keys<<<grid_for(n, 256), 256, 0, st>>>(mesh->d_conn, n, mesh->nne, S.kA, S.iA);
+  ctx->launches++;
+  std::vector<int> shifts;
+  for (int sh = 0; sh < bits_for(mesh->nnodes); sh += 8) shifts.push_back(sh);
+  unsigned long long *kin = S.kA, *kout = S.kB;
+  uint32_t *iin = S.iA, *iout = S.iB;
+  FE_TRY(radix_sort_pairs(ctx, n, shifts, &kin, &kout, &iin, &iout, S.hist, S.offs));
+  int32_t *conn_new = nullptr;
+  CUDA_TRY(ctx, cudaMalloc((void **)&conn_new, sizeof(int32_t) * (size_t)n * mesh->nne));
+  if (!mesh->d_orig) {
+    cudaError_t e = cudaMalloc((void **)&mesh->d_orig, sizeof(int32_t) * (size_t)n);
+    if (e != cudaSuccess) { cudaFree(conn_new); return fegpu_fail(ctx, FEGPU_ERR_CUDA, cudaGetErrorString(e)); }
+  }
+  k_permute_conn<<<grid_for(n * mesh->nne, 256), 256, 0, st>>>(mesh->d_conn, iin, n, mesh->nne, conn_new, mesh->d_orig);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  cudaFree(mesh->d_conn);
+  mesh->d_conn = conn_new;
+  return FEGPU_OK;
+}
+
+// d_perm[r] = slot (position in the active element list) of the r-th active element in the CALLER's element order: the raw-COO
+// export (AssemblyModule.jl:261-280: triplets in element call order) walks the element-value array through it.
+int32_t fe_emission_order(fegpu_mesh *mesh, int32_t *d_perm) {
+  fegpu_ctx *ctx = mesh->ctx;
+  cudaStream_t st = ctx->stream;
+  const int64_t n = mesh->nactive;
+  if (n == 0) return FEGPU_OK;
+  SortScratch S(ctx);
+  FE_TRY(S.alloc(n));
+  k_orig_keys<<<grid_for(n, 256), 256, 0, st>>>(mesh->d_orig, mesh->d_elem_list, n, S.kA, S.iA);
+  ctx->launches++;
+  std::vector<int> shifts;
+  for (int sh = 0; sh < bits_for(mesh->nelem); sh += 8) shifts.push_back(sh);
+  unsigned long long *kin = S.kA, *kout = S.kB;
+  uint32_t *iin = S.iA, *iout = S.iB;
+  FE_TRY(radix_sort_pairs(ctx, n, shifts, &kin, &kout, &iin, &iout, S.hist, S.offs));
+  k_copy_u32<<<grid_for(n, 256), 256, 0, st>>>(iin, d_perm, n);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));  // the scratch goes back to the block cache behind this point
+  return FEGPU_OK;
 }
 
 int32_t fe_coo_to_csc(fegpu_asm *as, int64_t n, const int64_t *d_I, const int64_t *d_J, const double *d_V, int64_t nrows, int64_t ncols) {

@@ -73,6 +73,11 @@ int32_t fegpu_cache_release(fegpu_ctx *ctx);
 int64_t fegpu_launch_count(fegpu_ctx *ctx);
 /* roofline denominators measured by the library itself: FP64 FMA peak (TFLOP/s) and copy bandwidth (GB/s) */
 int32_t fegpu_measure_peaks(fegpu_ctx *ctx, double *dfma_tflops, double *copy_gbs);
+/* Page-locked host memory for result arrays that are re-used across assemblies (colptr / rowval / nzval of a shim that keeps
+ * its buffers): DMA into pinned memory runs at link speed, into pageable memory at about half of it.  Plain cudaHostAlloc /
+ * cudaFreeHost; the caller owns the block. */
+int32_t fegpu_host_alloc(void **p, int64_t bytes);
+int32_t fegpu_host_free(void *p);
 /* Per-kernel device times of ONE step: fegpu_marks_begin starts recording named CUDA events on the context's stream at the
  * boundaries of the library's kernels (run the step with fegpu_set_overlap(ctx, 0) so that it stays on one stream);
  * fegpu_marks_read synchronises, stops recording and writes "name=ms;name=ms;..." -- the time since the previous mark --

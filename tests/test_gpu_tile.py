@@ -17,9 +17,10 @@ def _path(fe, ctx, fes, u):
 
 def _distort(fens, amp=0.07):
     x = fens.xyz.copy()
-    fens.xyz[:, 0] += amp * np.sin(2.1 * x[:, 1] + 0.3) * np.cos(1.7 * x[:, 2])
-    fens.xyz[:, 1] += amp * np.sin(1.3 * x[:, 2] + 0.1) * np.cos(2.3 * x[:, 0])
-    if fens.xyz.shape[1] > 2:
+    z = x[:, 2] if x.shape[1] > 2 else 0.37 * x[:, 0]
+    fens.xyz[:, 0] += amp * np.sin(2.1 * x[:, 1] + 0.3) * np.cos(1.7 * z)
+    fens.xyz[:, 1] += amp * np.sin(1.3 * z + 0.1) * np.cos(2.3 * x[:, 0])
+    if x.shape[1] > 2:
         fens.xyz[:, 2] += amp * np.sin(1.9 * x[:, 0] + 0.2) * np.cos(1.1 * x[:, 1])
 
 
@@ -127,6 +128,34 @@ def test_tile_path_many_tiles_and_unused_nodes(fe, orc, gpu_ctx):
     assert _path(fe, gpu_ctx, fes, u) == 2
     assert_parity(ref, got)
     assert np.count_nonzero(np.diff(got[0]) == 0) >= 2 * 37
+
+
+def test_internal_element_order_is_invisible(fe, orc, gpu_ctx):
+    """The library stores elements in its own order (ascending smallest node id); whatever order the FESet lists them in, the raw
+    COO export comes back in the CALLER's emission order (AssemblyModule.jl:261-280) and bilform_masslike numbers its rows by the
+    caller's element ids (FEMMBaseModule.jl:1907-1908) -- single GPU and as a rank of a partition."""
+    rng = np.random.default_rng(7)
+    fens, fes = fe.H8block(1.0, 2.0, 3.0, 5, 4, 6)
+    _distort(fens)
+    fes = type(fes)(np.ascontiguousarray(fes.conn[rng.permutation(fes.count())]))  # element order unrelated to the node numbering
+    rule = fe.GaussRule(3, 2)
+    for ndn, form, coef in ((1, "diffusion", KAPPA3), (3, "elastic", isotropic_C())):
+        u = make_field(fe, fens, ndn)
+        ref, (I, J, V) = oracle_csc(orc, form, "H8", fes, fens, u, rule, coef)
+        got, a = gpu_csc(fe, form, fes, fens, u, rule, coef)
+        assert_parity(ref, got)
+        gI, gJ, gV = a.coo()
+        np.testing.assert_array_equal(gI, I)
+        np.testing.assert_array_equal(gJ, J)
+        assert np.abs(gV - V).max() <= 1e-12 * np.abs(V).max()
+    # masslike: element-numbered rows
+    phi = make_field(fe, fens, 1)
+    c = np.array([[1.7]])
+    I, J, V = orc.bilform_masslike_coo("H8", fes.conn, fens.xyz, phi.dofnums, phi.nalldofs(), rule.param_coords, rule.weights, c)
+    refm = orc.sparse(I, J, V, fes.count(), phi.nalldofs())
+    am = fe.SysmatAssemblerSparseGPU(0.0)
+    gotm = fe.bilform_masslike(fe.FEMMBase(fe.IntegDomain(fes, rule)), am, fe.NodalField(fens.xyz), phi, fe.DataCache(c), raw=True)
+    assert_parity(refm, gotm)
 
 
 def test_general_path_still_taken_when_preconditions_fail(fe, orc, gpu_ctx):

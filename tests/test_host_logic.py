@@ -190,8 +190,45 @@ def test_julia_shim_ccalls_match_the_abi(fe):
     # the path's own entry points are all bound by the shim
     for must in ("fegpu_create", "fegpu_mesh_upload", "fegpu_dofmap_upload", "fegpu_rule_set", "fegpu_bilform_diffusion",
                  "fegpu_bilform_lin_elastic", "fegpu_bilform_dot", "fegpu_startassembly", "fegpu_assemble", "fegpu_makematrix",
-                 "fegpu_makematrix_sizes", "fegpu_makematrix_copy", "fegpu_set_async", "fegpu_cache_release"):
+                 "fegpu_makematrix_sizes", "fegpu_makematrix_copy", "fegpu_set_async", "fegpu_cache_release",
+                 # multi-GPU split, the nomatrixresult flow, values-only re-assembly, device-resident results, windowed geometry
+                 "fegpu_partition_set", "fegpu_coo_copy", "fegpu_makematrix_copy_values", "fegpu_makematrix_device",
+                 "fegpu_geom_update_window", "fegpu_pattern_was_cached", "fegpu_host_alloc", "fegpu_host_free", "fegpu_makematrix_view"):
         assert must in seen, must
+
+
+def test_julia_shim_eligibility_and_caching_rules():
+    """What the shim must refuse / must share, checked on its source (it cannot run here):
+    - a DataCache whose `_fillcache!` is not the constant constructor's closure is an error (DataCacheModule.jl:65-89), as is a
+      user-supplied other-dimension function (IntegDomainModule.jl:73-104): never the initial buffer read silently;
+    - ONE context per device and a per-device mesh cache, so an assembler per call (FEMMBaseModule.jl:1374) re-uses the device
+      mesh and the cached pattern; assemblers do not create or destroy contexts;
+    - the quadrature tables are compared on every call (two FEMMs on one FESet with different rules);
+    - SysmatAssemblerFFBlock{<:SysmatAssemblerSparseGPU} has its own bilform methods (no CPU element loop)."""
+    src = open(os.path.join(ROOT, "finetools.jl_b200", "julia", "FinEtoolsGPU.jl")).read()
+    assert re.search(r'occursin\("_fillcache_constant!", string\(nameof\(typeof\(cf\._fillcache!\)\)\)\)\s*\|\|\s*\n?\s*error\(', src)
+    assert "cf._cache" not in re.sub(r"function _constant_cache.*?\nend\n", "", src, flags=re.S), "forms must read the cache through _constant_cache"
+    assert re.search(r"f === otherdimensionunity && return 1\.0", src) and 'occursin("otherdimensionfu"' in src
+    assert re.search(r"function _otherdim.*?error\(\"only the unit or a constant other-dimension", src, flags=re.S)
+    # _eligible runs both checks before anything is uploaded, and every form calls _eligible first
+    elig = re.search(r"function _eligible.*?\nend\n", src, flags=re.S).group(0)
+    assert "_otherdim(self)" in elig and "_constant_cache(cf)" in elig
+    for form in ("bilform_diffusion", "bilform_lin_elastic", "bilform_dot", "bilform_convection", "bilform_div_grad", "bilform_masslike", "linform_dot"):
+        body = re.search(r"function %s\(self::FEMMBase, assembler::(SysmatAssemblerSparseGPU|SysvecAssemblerGPU).*?\nend\n" % form, src, flags=re.S).group(0)
+        assert body.index("_eligible(") < body.index("_device("), form
+    # one context per device; assemblers neither create nor destroy it
+    assert src.count(":fegpu_create") == 1 and "const _DEVICES = Dict{Int,DeviceState}()" in src
+    assert ":fegpu_destroy" not in src
+    ctor = re.search(r"function SysmatAssemblerSparseGPU\(z::Float64.*?\nend\n", src, flags=re.S).group(0)
+    assert "_device_state(device)" in ctor and ":fegpu_create" not in ctor
+    # rule tables compared on every call
+    dev = re.search(r"function _device\(self::FEMMBase.*?\nend\n", src, flags=re.S).group(0)
+    assert "t.rule != (npts, N, dN, ww)" in dev and ":fegpu_rule_set" in dev
+    assert "t.owner[1] != own" in dev and ":fegpu_partition_set" in dev
+    # FFBlock over a GPU assembler: dedicated methods for every bilinear form on the path
+    assert "const FFBlockGPU = SysmatAssemblerFFBlock{<:SysmatAssemblerSparseGPU}" in src
+    for form in ("bilform_diffusion", "bilform_lin_elastic", "bilform_dot"):
+        assert re.search(r"%s\(self::FEMMBase, assembler::FFBlockGPU" % form, src), form
 
 
 def test_bench_reference_arm_contract():
