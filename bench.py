@@ -374,6 +374,20 @@ def run_gpu(args):
         nnz_total = allsum_int(nnz_local)
         nact_total = allsum_int(W.win[2])
         nelem = W.nelem
+        # ---- the optional exchange step: the ranks' row blocks gathered into ONE CSC in the HBM of rank 0 (NCCL over NVLink for the
+        # counts and the rowval / nzval slabs + the library's plan / interleave kernels); reported beside the headline, not inside it
+        gather = None
+        if dist is not None and key == "c4":
+            W.device_step(False)
+            ctx.synchronize()
+            fe.gather_row_blocks_device(W.a, dist, dst=0, ordered=True)   # warm-up (NCCL channels, staging buffers)
+            reps = 3
+            g_s = wall(lambda: fe.gather_row_blocks_device(W.a, dist, dst=0, ordered=True), reps) / reps
+            nnz0 = nnz_local if rank == 0 else 0
+            nnz0 = allsum_int(nnz0)
+            wire = 16 * (nnz_total - nnz0) + 8 * n_ * world
+            gather = {"ms": g_s * 1e3, "wire_bytes": int(wire), "wire_GBps_into_rank0": wire / g_s / 1e9,
+                      "note": "wall time incl. host synchronisations, max over ranks; NVLink 5 into one GPU: 900 GB/s nominal per direction"}
 
         ms_step = ms_total / steps
         nact = W.win[2]                      # elements this rank integrates (its share + halo)
@@ -419,7 +433,7 @@ def run_gpu(args):
                     "cached_pattern_values_only": {"value": nelem / e2e_cached_s, "ms_per_step": e2e_cached_s * 1e3, "steps": side,
                                                    "note": "re-assembly on the cached pattern: coordinates in, nzval out (colptr/rowval kept by the caller)"},
                     "transfer_stats": xfer1},
-            "kernels": kern, "clocks": clocks, "rank0": {"active_elements": nact, "node_window": nnodes_rank, "nnz": nnz_local},
+            "gather_blocks": gather, "kernels": kern, "clocks": clocks, "rank0": {"active_elements": nact, "node_window": nnodes_rank, "nnz": nnz_local},
             "peaks": {"hbm_gbs": hbm_peak, "hbm_kind": peak_kind, "dfma_tflops_measured_here": peaks["dfma_tflops"], "copy_gbs_measured_here": peaks["copy_gbs"]},
         }
         W.release()
@@ -484,6 +498,10 @@ def run_gpu(args):
         "nnz_per_s_csc_construction": r4["nnz_per_s_csc_construction"],
         "rank0": r4["rank0"],
     }
+    if r4.get("gather_blocks"):
+        g = r4["gather_blocks"]
+        line["gather_blocks"] = dict(g, value_with_gather=r4["value"] * r4["ms_per_step"] / (r4["ms_per_step"] + g["ms"]),
+                                     value_without_gather=r4["value"])
     if r2 is not None:
         line["config2"] = {k: r2[k] for k in ("workload", "value", "ms_per_step", "phases_ms", "marks_ms", "cached", "e2e", "kernels", "launches",
                                               "nnz_per_s_csc_construction")}

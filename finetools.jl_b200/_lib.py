@@ -68,6 +68,10 @@ SIGNATURES = {
     "fegpu_makematrix_copy_values": (C.c_int32, [VP, VP]),
     "fegpu_makematrix_device": (C.c_int32, [VP, C.POINTER(VP), C.POINTER(VP), C.POINTER(VP)]),
     "fegpu_coo_copy": (C.c_int32, [VP, VP, VP, VP, VP, VP]),
+    "fegpu_block_counts": (C.c_int32, [VP, VP]),
+    "fegpu_gather_plan": (C.c_int32, [VP, VP, C.c_int32, C.c_int64, VP, VP]),
+    "fegpu_gather_place": (C.c_int32, [VP, VP, C.c_int32, C.c_int32, C.c_int64, VP, VP, VP, VP, VP]),
+    "fegpu_gather_sort_columns": (C.c_int32, [VP, C.c_int64, VP, VP, VP, c_i64p]),
     "fegpu_last_timings": (C.c_int32, [VP, c_f64p]),
     "fegpu_pattern_was_cached": (C.c_int32, [VP]),
     "fegpu_pattern_invalidate": (C.c_int32, [VP]),

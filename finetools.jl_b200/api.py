@@ -16,7 +16,7 @@ from .integdomain import IntegDomain, integrationdata, otherdimensionunity  # no
 from .integrule import GaussRule, TetRule, TriRule  # noqa: F401
 from .meshgen import (H8block, H8blockx, H8toH20, H8toH27, H20block, H27block, Q4block, Q4blockx, T3block, T3blockx,  # noqa: F401
                       T4block, T4blockx, T4toT10, T10block, linearspace, meshboundary)
-from .parallel import gather_row_blocks  # noqa: F401
+from .parallel import gather_row_blocks, gather_row_blocks_device, owned_ranges_ordered  # noqa: F401
 from .partition import pointpartitioning, slab_owner  # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -853,7 +853,7 @@ int32_t fegpu_bilform_dot(fegpu_mesh *mesh, fegpu_dofmap *dm, const double *c, i
   if (!mesh || !dm || !c) return fegpu_fail(mesh ? mesh->ctx : nullptr, FEGPU_ERR_ARG, "NULL argument");
   if (mesh->mdim == 3 && m != 3) return fegpu_fail(mesh->ctx, FEGPU_ERR_MANIFOLD, "That is the only acceptable option here.");
   if (mesh->mdim == 2 && (m < 2 || m > 3)) return fegpu_fail(mesh->ctx, FEGPU_ERR_MANIFOLD, "Those are the only acceptable options here.");
-  if (dm->ndn > 3) return fegpu_fail(mesh->ctx, FEGPU_ERR_ARG, "bilform_dot: up to 3 dofs per node");
+  // any number of dofs per node the dof map takes (1..6): above 3 the element matrices are formed as a Kronecker product
   FormArgs fa;
   std::memset(&fa, 0, sizeof(fa));
   fa.form = FORM_DOT;

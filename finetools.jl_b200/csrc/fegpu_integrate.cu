@@ -459,9 +459,51 @@ bool fe_integrate_supports_compact(const fegpu_mesh *mesh, const FormArgs &fa) {
   return fe_form_symmetric(fa.form) || fe_dot_scalar_applies(mesh, fa);  // a 1 x 1 coefficient makes bilform_dot symmetric
 }
 
+namespace {
+// bilform_dot with more than 3 dofs per node (the reference has no cap, FEMMBaseModule.jl:1355-1360): the element matrix is the
+// Kronecker product of the scalar one with the coefficient, elmat[(k,p),(m,q)] = (sum_j N_k N_m Jac w_j) c[p,q].  The reference
+// multiplies by c inside the quadrature loop; summing first differs from that by rounding only (c is constant).
+__global__ void k_kron_coef(const double *__restrict__ Ms, double *__restrict__ V, int64_t nactive, int nne, int ndn, const double *__restrict__ cdev) {
+  const int EM = nne * ndn;
+  const int64_t EM2 = (int64_t)EM * EM;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nactive * EM2) return;
+  const int64_t e = t / EM2;
+  const int loc = (int)(t - e * EM2);
+  const int col = loc / EM, row = loc - col * EM;  // emission order: column-major
+  const int m = col / ndn, q = col - m * ndn, k = row / ndn, p = row - k * ndn;
+  V[t] = Ms[e * (int64_t)(nne * nne) + (int64_t)m * nne + k] * cdev[p + ndn * q];
+}
+}  // namespace
+
 int32_t fe_integrate(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
   if (mesh->npts <= 0) return fegpu_fail(mesh->ctx, FEGPU_ERR_STATE, "no quadrature rule set (fegpu_rule_set)");
   if (mesh->nactive <= 0) return FEGPU_OK;  // empty FESet, or a rank that owns no node: nothing to integrate
+  if (fa.form == FORM_DOT && fa.ndn > 3) {
+    fegpu_ctx *ctx = mesh->ctx;
+    cudaStream_t st = ctx->stream;
+    FormArgs f1 = fa;
+    f1.ndn = 1;
+    f1.coef[0] = 1.0;
+    f1.compact = false;
+    double *d_Ms = nullptr, *d_c = nullptr;
+    const int nne = mesh->nne;
+    FE_TRY(fe_dev_alloc(ctx, (void **)&d_Ms, sizeof(double) * (size_t)mesh->nactive * nne * nne, st));
+    int32_t s = fe_dev_alloc(ctx, (void **)&d_c, sizeof(double) * 36, st);
+    if (s == FEGPU_OK) s = fe_integrate(mesh, f1, d_Ms);  // scalar mass matrices, full layout
+    if (s == FEGPU_OK && cudaMemcpyAsync(d_c, fa.coef, sizeof(double) * fa.ndn * fa.ndn, cudaMemcpyHostToDevice, st) != cudaSuccess)
+      s = fegpu_fail(ctx, FEGPU_ERR_CUDA, "coefficient upload failed");
+    if (s == FEGPU_OK) {
+      const int64_t n = mesh->nactive * (int64_t)(nne * fa.ndn) * (nne * fa.ndn);
+      k_kron_coef<<<grid_for(n, 256), 256, 0, st>>>(d_Ms, d_V, mesh->nactive, nne, fa.ndn, d_c);
+      ctx->launches++;
+      if (cudaGetLastError() != cudaSuccess) s = fegpu_fail(ctx, FEGPU_ERR_CUDA, "k_kron_coef launch failed");
+    }
+    if (s == FEGPU_OK && cudaStreamSynchronize(st) != cudaSuccess) s = fegpu_fail(ctx, FEGPU_ERR_CUDA, "synchronize failed");  // fa.coef is the caller's
+    if (d_c) fe_dev_free(ctx, d_c, st);
+    fe_dev_free(ctx, d_Ms, st);
+    return s;
+  }
   if (fe_dot_scalar_applies(mesh, fa)) return fe_integrate_dot_scalar(mesh, fa, d_V);
   const bool rotated = fa.use_rm && (fa.form == FORM_DIFF_GEN || fa.form == FORM_ELASTIC);  // only the generic kernel knows Rm
   if (mesh->etype == FEGPU_H8 && !rotated) {

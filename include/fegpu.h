@@ -214,6 +214,21 @@ int32_t fegpu_coo_copy(fegpu_asm *as, fegpu_mesh *mesh, fegpu_dofmap *dofmap, in
 /* device milliseconds (CUDA events) of the phases of the last bilform / makematrix call:
  * [0] element integration, [1] symbolic pattern build (0 when cached), [2] numeric CSC gather-sum or sort path,
  * [3] whole call */
+/* Optional gather of the ranks' row-block CSCs into ONE matrix on a device (multi-GPU; the reference's makematrix! returns one
+ * SparseMatrixCSC, AssemblyModule.jl:319-325).  All pointers are DEVICE pointers (e.g. torch tensors' data_ptr()); the collective
+ * steps in between -- an all-gather of the counts, contiguous rowval / nzval slabs to the destination -- are the host side's NCCL
+ * calls (finetools.jl_b200/parallel.py: torch.distributed).  No index array crosses the wire: positions follow from the counts.
+ *   fegpu_block_counts        d_counts[j] = entries of column j in this assembler's (block) result               [ncols]
+ *   fegpu_gather_plan         from the all-gathered counts [world][ncols]: global 1-based colptr [ncols+1], nnz per rank [world]
+ *   fegpu_gather_place        copy the block of rank src_rank (its rowval / nzval slabs as received) into the global arrays:
+ *                             column j lands at colptr[j] + (entries of the ranks below src_rank in column j)
+ *   fegpu_gather_sort_columns only when the ranks' dof ranges interleave (free-first numberings): sorts the columns whose
+ *                             concatenation is not ascending; *columns_sorted = how many needed it                         */
+int32_t fegpu_block_counts(fegpu_asm *as, int64_t *d_counts);
+int32_t fegpu_gather_plan(fegpu_ctx *ctx, const int64_t *d_allcounts, int32_t world, int64_t ncols, int64_t *d_colptr, int64_t *d_nnz_rank);
+int32_t fegpu_gather_place(fegpu_ctx *ctx, const int64_t *d_allcounts, int32_t world, int32_t src_rank, int64_t ncols, const int64_t *d_colptr,
+                           const int64_t *d_src_rowval, const double *d_src_nzval, int64_t *d_rowval, double *d_nzval);
+int32_t fegpu_gather_sort_columns(fegpu_ctx *ctx, int64_t ncols, const int64_t *d_colptr, int64_t *d_rowval, double *d_nzval, int64_t *columns_sorted);
 int32_t fegpu_last_timings(fegpu_asm *as, double ms[4]);
 /* was the sparsity pattern of the last bilform call served from the cache (1) or built (0)? */
 int32_t fegpu_pattern_was_cached(fegpu_asm *as);

@@ -158,6 +158,28 @@ def test_internal_element_order_is_invisible(fe, orc, gpu_ctx):
     assert_parity(refm, gotm)
 
 
+@pytest.mark.parametrize("et,ndn", [("H8", 4), ("H8", 6), ("T10", 5), ("Q4", 4)])
+def test_dot_more_than_three_dofs(fe, orc, gpu_ctx, et, ndn):
+    """bilform_dot has no cap on the dofs per node in the reference (FEMMBaseModule.jl:1355-1360): 4..6 (shell-like fields) go through
+    the Kronecker path of the integration and the runtime-ndn symbolic / numeric kernels."""
+    rng = np.random.default_rng(ndn)
+    if et == "H8":
+        fens, fes = fe.H8block(1.0, 2.0, 3.0, 4, 3, 5)
+        rule, kw = fe.GaussRule(3, 2), {}
+    elif et == "T10":
+        fens, fes = fe.T10block(1.0, 2.0, 3.0, 2, 3, 2)
+        rule, kw = fe.TetRule(4), {}
+    else:
+        fens, fes = fe.Q4block(2.0, 3.0, 7, 5)
+        rule, kw = fe.GaussRule(2, 2), {"m": 2}
+    _distort(fens, 0.03)
+    u = make_field(fe, fens, ndn)
+    c = rng.standard_normal((ndn, ndn))
+    ref, _ = oracle_csc(orc, "dot", et, fes, fens, u, rule, c, **kw)
+    got, _ = gpu_csc(fe, "dot", fes, fens, u, rule, c, **kw)
+    assert_parity(ref, got)
+
+
 def test_general_path_still_taken_when_preconditions_fail(fe, orc, gpu_ctx):
     """Free-first / fixed-last numbering (not affine) and a permuted dof map fall back to the group kernels -- same arrays."""
     fens, fes = fe.H8block(1.0, 2.0, 3.0, 6, 5, 7)
