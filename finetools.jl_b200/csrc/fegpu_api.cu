@@ -84,7 +84,7 @@ __global__ void k_elem_active(const int32_t *__restrict__ conn, int64_t nelem, i
 // compact upper-block layout -> full element matrix, emission order (thread per full entry)
 // perm (optional): output element r is the element of slot perm[r]
 __global__ void k_expand_compact(const double *__restrict__ Vc, double *__restrict__ Vf, int64_t nelem, int nne, int ndn,
-                                 const int32_t *__restrict__ perm) {
+                                 const int32_t *__restrict__ perm, int64_t vstride) {
   const int EM = nne * ndn;
   const int64_t EM2 = (int64_t)EM * EM, CS = (int64_t)(nne * (nne + 1) / 2) * ndn * ndn;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,7 +94,7 @@ __global__ void k_expand_compact(const double *__restrict__ Vc, double *__restri
   const int k = (int)(i - eo * EM2), c = k / EM, r = k - c * EM;
   const int li = r / ndn, p = r - li * ndn, lc = c / ndn, q = c - lc * ndn, nd2 = ndn * ndn;
   const int off = (li <= lc) ? nd2 * (lc * (lc + 1) / 2 + li) + q * ndn + p : nd2 * (li * (li + 1) / 2 + lc) + p * ndn + q;
-  Vf[i] = Vc[e * CS + off];
+  Vf[i] = vstride > 0 ? Vc[(int64_t)off * vstride + e] : Vc[e * CS + off];
 }
 
 // smallest and largest node id used by the active elements: win[0] = max(~node) (so that a zero-initialised slot means "no node"),
@@ -179,17 +179,18 @@ struct DeviceGuard {
 }  // namespace
 
 // full element matrices permuted: out[r] = in[perm[r]]
-__global__ void k_permute_records(const double *__restrict__ in, double *__restrict__ out, int64_t nelem, int64_t rec, const int32_t *__restrict__ perm) {
+__global__ void k_permute_records(const double *__restrict__ in, double *__restrict__ out, int64_t nelem, int64_t rec, const int32_t *__restrict__ perm,
+                                  int64_t vstride) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nelem * rec) return;
-  const int64_t eo = i / rec;
-  out[i] = in[(int64_t)perm[eo] * rec + (i - eo * rec)];
+  const int64_t eo = i / rec, k = i - eo * rec;
+  out[i] = vstride > 0 ? in[k * vstride + perm[eo]] : in[(int64_t)perm[eo] * rec + k];
 }
 
-int32_t fe_expand_compact(fegpu_ctx *ctx, const double *d_Vc, double *d_Vfull, int64_t nelem, int nne, int ndn, const int32_t *d_perm) {
+int32_t fe_expand_compact(fegpu_ctx *ctx, const double *d_Vc, double *d_Vfull, int64_t nelem, int nne, int ndn, const int32_t *d_perm, int64_t vstride) {
   const int64_t n = nelem * (int64_t)(nne * ndn) * (nne * ndn);
   if (n == 0) return FEGPU_OK;
-  k_expand_compact<<<grid_for(n, 256), 256, 0, ctx->stream>>>(d_Vc, d_Vfull, nelem, nne, ndn, d_perm);
+  k_expand_compact<<<grid_for(n, 256), 256, 0, ctx->stream>>>(d_Vc, d_Vfull, nelem, nne, ndn, d_perm, vstride);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return FEGPU_OK;
@@ -727,30 +728,37 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
   static const bool compact_off = std::getenv("FEGPU_COMPACT") && std::atoi(std::getenv("FEGPU_COMPACT")) == 0;  // A/B knob
   as->V_n = ntrip;
   as->last_EM = EM;
-  auto integrate = [&](bool compact) -> int32_t {  // always on the caller's stream
-    fa2.compact = compact;
-    const int64_t per_elem = compact ? fe_compact_size(mesh->nne, fa.ndn) : (int64_t)EM * EM;
-    ctx->stream = st;
-    FE_TRY(fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(mesh->nactive * per_elem, 1)));
-    as->V_compact = compact;
-    CUDA_TRY(ctx, cudaEventRecord(as->ev[4], st));
-    FE_TRY(fe_integrate(mesh, fa2, as->d_V));
-    CUDA_TRY(ctx, cudaEventRecord(as->ev[2], st));
-    fe_mark(ctx, "integrate");
-    return FEGPU_OK;
-  };
+  static const bool planes_off = std::getenv("FEGPU_PLANES") && std::atoi(std::getenv("FEGPU_PLANES")) == 0;  // A/B knob
+  const bool can_compact = fe_integrate_supports_compact(mesh, fa) && !compact_off;
+  const bool can_planes = fe_integrate_supports_planes(mesh, fa) && !planes_off;
   bool integrated = false, sym_timed = false;
+  auto integrate = [&](bool compact, bool planes) -> int32_t {  // always on the caller's stream
+    if (integrated && fa2.compact == compact && fa2.planes == planes) return FEGPU_OK;
+    fa2.compact = compact;
+    fa2.planes = planes;
+    fa2.vstride = planes ? ((mesh->nactive + 31) & ~(int64_t)31) : 0;
+    const int64_t per_elem = compact ? fe_compact_size(mesh->nne, fa.ndn) : (int64_t)EM * EM;
+    cudaStream_t cur = ctx->stream;
+    ctx->stream = st;
+    int32_t r = fe_asm_reserve(as, &as->d_V, &as->V_cap, (size_t)std::max<int64_t>(planes ? per_elem * fa2.vstride : mesh->nactive * per_elem, 1));
+    as->V_compact = compact;
+    as->V_planes = planes;
+    as->V_stride = fa2.vstride;
+    if (r == FEGPU_OK && cudaEventRecord(as->ev[4], st) != cudaSuccess) r = fegpu_fail(ctx, FEGPU_ERR_CUDA, "event record failed");
+    if (r == FEGPU_OK) r = fe_integrate(mesh, fa2, as->d_V);
+    if (r == FEGPU_OK && cudaEventRecord(as->ev[2], st) != cudaSuccess) r = fegpu_fail(ctx, FEGPU_ERR_CUDA, "event record failed");
+    if (r == FEGPU_OK) fe_mark(ctx, "integrate");
+    ctx->stream = cur;
+    integrated = r == FEGPU_OK;
+    return r;
+  };
   if (fast) {
     if (!dm->pat || dm->pat_topo_version != mesh->topo_version) {
-      const bool want_compact = fe_integrate_supports_compact(mesh, fa) && !compact_off;
       const bool ov = ctx->overlap && ctx->stream2;
       cudaStream_t sym = ov ? ctx->stream2 : st;
-      std::function<int32_t()> fork = [&]() -> int32_t {  // called from inside the build, which runs on `sym`
-        integrated = true;
-        const int32_t r = integrate(want_compact);
-        ctx->stream = sym;
-        return r;
-      };
+      // called from inside the build (which runs on `sym`) as soon as it knows which structured path it takes; a second call
+      // with another layout (the thread-per-node attempt failed its preconditions) integrates again
+      std::function<int32_t(bool)> fork = [&](bool tile) -> int32_t { return integrate(can_compact, tile && can_planes); };
       if (ov) {  // the symbolic phase starts after everything queued on the caller's stream so far
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
         CUDA_TRY(ctx, cudaStreamWaitEvent(sym, ctx->ev_fork, 0));
@@ -771,15 +779,15 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
     }
   }
   if (!sym_timed) CUDA_TRY(ctx, cudaEventRecord(as->ev[1], st));
-  if (integrated && !fast && fa2.compact) integrated = false;  // late fall-back to the sort path: it needs full element matrices
-  if (!integrated) FE_TRY(integrate(fast && fe_integrate_supports_compact(mesh, fa) && !compact_off));
+  // the layout the numeric phase needs: compact / planes only on the structured paths, full element-major for the sort path
+  FE_TRY(integrate(fast && can_compact, fast && can_planes && fe_pattern_is_tile(dm->pat)));
   CUDA_TRY(ctx, cudaEventRecord(as->ev[5], st));
   FE_TRACE("bilform: before numeric phase");
   // 3. numeric CSC phase
   if (fast) {
     const int64_t nnz = fe_pattern_nnz(dm->pat);
     FE_TRY(fe_asm_reserve(as, &as->d_nzval, &as->nz_cap, (size_t)std::max<int64_t>(nnz, 1)));
-    FE_TRY(fe_gather(dm, as->d_V, fa2.compact, as->d_nzval));
+    FE_TRY(fe_gather(dm, as->d_V, fa2.compact, as->d_nzval, fa2.planes, fa2.vstride));
     fe_mark(ctx, "gather");
     as->nnz = nnz;
     as->nrows = dm->row_nall;
@@ -1434,9 +1442,9 @@ int32_t fegpu_coo_copy(fegpu_asm *as, fegpu_mesh *mesh, fegpu_dofmap *dm, int64_
     if (e != cudaSuccess) { cudaFree(d_perm); return fegpu_fail(ctx, FEGPU_ERR_CUDA, cudaGetErrorString(e)); }
     int32_t s = FEGPU_OK;
     if (as->V_compact) {  // the fast path stored the compact symmetric layout: expand to full matrices on the way
-      s = fe_expand_compact(ctx, as->d_V, dfull, mesh->nactive, mesh->nne, dm->ndn, d_perm);
+      s = fe_expand_compact(ctx, as->d_V, dfull, mesh->nactive, mesh->nne, dm->ndn, d_perm, as->V_planes ? as->V_stride : 0);
     } else {
-      k_permute_records<<<grid_for(n, 256), 256, 0, st>>>(as->d_V, dfull, mesh->nactive, (int64_t)EM * EM, d_perm);
+      k_permute_records<<<grid_for(n, 256), 256, 0, st>>>(as->d_V, dfull, mesh->nactive, (int64_t)EM * EM, d_perm, as->V_planes ? as->V_stride : 0);
       ctx->launches++;
     }
     if (s == FEGPU_OK && cudaMemcpyAsync(V, dfull, sizeof(double) * n, cudaMemcpyDeviceToHost, st) != cudaSuccess) s = FEGPU_ERR_CUDA;

@@ -20,6 +20,7 @@ struct DotParams {
   int npts;
   double *V;
   int compact;
+  int64_t vstride;  // > 0: plane layout (FormArgs::planes)
   double c;         // the 1 x 1 coefficient
   int m;            // manifold dimension kwarg
   double otherdim;
@@ -76,7 +77,18 @@ __global__ void __launch_bounds__(128) k_dot_scalar(const DotParams P) {
         acc[mx * (mx + 1) / 2 + k] += factor * P.c;
       }
   }
-  if (P.compact) {
+  if (P.vstride > 0) {
+    double *out = P.V + slot;
+    if (P.compact) {
+#pragma unroll
+      for (int i = 0; i < NT; i++) out[(int64_t)i * P.vstride] = acc[i];
+    } else {
+#pragma unroll
+      for (int c = 0; c < NNE; c++)
+#pragma unroll
+        for (int r = 0; r < NNE; r++) out[(int64_t)(c * NNE + r) * P.vstride] = (r <= c) ? acc[c * (c + 1) / 2 + r] : acc[r * (r + 1) / 2 + c];
+    }
+  } else if (P.compact) {
     double *Ve = P.V + slot * NT;
 #pragma unroll
     for (int i = 0; i < NT; i++) Ve[i] = acc[i];
@@ -94,7 +106,7 @@ int32_t launch_dot(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
   fegpu_ctx *ctx = mesh->ctx;
   if (mesh->nactive == 0) return FEGPU_OK;
   DotParams P{mesh->d_conn, mesh->d_xyz, mesh->nnodes, mesh->d_elem_list, mesh->nactive, mesh->d_tab, mesh->d_w, mesh->npts, d_V,
-              fa.compact ? 1 : 0, fa.coef[0], fa.m, fa.otherdim};
+              fa.compact ? 1 : 0, fa.planes ? fa.vstride : 0, fa.coef[0], fa.m, fa.otherdim};
   const size_t smem = sizeof(double) * ((size_t)mesh->npts * NNE * (1 + MDIM) + mesh->npts);
   auto kern = k_dot_scalar<NNE, MDIM, SDIM>;
   if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -27,6 +27,7 @@ struct H8Params {
   const int32_t *elem_list;
   int64_t nactive;
   double *V;
+  int64_t vstride;       // > 0: plane layout, value k of slot s at V[k * vstride + s] (FormArgs::planes)
   double dN[8 * 3 * 8];  // [point][dim][node]
   double w[8];
   double coef[36];
@@ -124,6 +125,19 @@ __global__ void __launch_bounds__(128) k_h8_diffusion(const __grid_constant__ H8
           for (int mx = 0; mx <= nx; mx++) acc[nx * (nx + 1) / 2 + mx] += G[mx][px] * a;
         }
     }
+  }
+  if (P.vstride > 0) {  // planes: the lanes of a warp (consecutive slots) write consecutive words of every plane
+    double *out = P.V + slot;
+    if (COMPACT) {
+#pragma unroll
+      for (int i = 0; i < 36; i++) out[(int64_t)i * P.vstride] = acc[i];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+#pragma unroll
+        for (int r = 0; r < 8; r++) out[(int64_t)(c * 8 + r) * P.vstride] = (r <= c) ? acc[c * (c + 1) / 2 + r] : acc[r * (r + 1) / 2 + c];
+    }
+    return;
   }
   if (COMPACT) {
     double2 *out = reinterpret_cast<double2 *>(P.V + slot * 36);
@@ -274,7 +288,13 @@ __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, cons
     block_bar();
     const int64_t sbase = slot0 + half * 16;
     const int64_t nvalid = min((int64_t)16, P.nactive - sbase);
-    if (nvalid > 0) {
+    if (nvalid > 0 && P.vstride > 0) {
+      // planes: 16 consecutive slots of one value index per half-warp (128-byte runs); the staged matrices have an odd stride
+      for (int i = threadIdx.x; i < 16 * MSIZE; i += 128) {
+        const int k = i >> 4, el = i & 15;
+        if (el < nvalid) P.V[(int64_t)k * P.vstride + sbase + el] = sm[(size_t)el * MSTRIDE + k];
+      }
+    } else if (nvalid > 0) {
       const int nval = (int)(nvalid * MSIZE);  // contiguous slots are contiguous in V
       double *dst = P.V + sbase * MSIZE;
       for (int i = threadIdx.x; i < nval; i += 128) {
@@ -346,7 +366,7 @@ int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool 
   const bool elast = (fa.form == FORM_ELASTIC);
   if (!diff && !elast) return FEGPU_OK;
   if (mesh->nactive == 0) { *handled = true; return FEGPU_OK; }
-  H8Params P{mesh->d_conn, mesh->d_xyz, mesh->nnodes, mesh->d_elem_list, mesh->nactive, d_V, {0}, {0}, {0}};
+  H8Params P{mesh->d_conn, mesh->d_xyz, mesh->nnodes, mesh->d_elem_list, mesh->nactive, d_V, fa.planes ? fa.vstride : 0, {0}, {0}, {0}};
   // dN part of the host table: [npts][3][8] starting after N [npts][8]
   std::memcpy(P.dN, mesh->h_tab.data() + 8 * 8, sizeof(double) * 8 * 24);
   std::memcpy(P.w, mesh->h_w.data(), sizeof(double) * 8);

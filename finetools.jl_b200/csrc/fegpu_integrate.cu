@@ -28,6 +28,7 @@ struct IntegParams {
   int npts;
   double *V;                 // [nactive][EM*EM], or [nactive][fe_compact_size] when compact
   int compact;
+  int64_t vstride;           // > 0: plane layout, value k of slot s at V[k * vstride + s] (FormArgs::planes)
   double coef[36];
   int m;
   double otherdim;
@@ -357,26 +358,30 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
           if (t + k * TPE < NENT) P.V[slot * (int64_t)NENT + t + k * TPE] = acc[k];
       }
     } else if (live && SYM && P.compact) {
-      // compact upper-block layout (fegpu_internal.h): block (a <= b) at NDN^2 * (b(b+1)/2 + a), column-major inside
-      double *Ve = P.V + slot * (int64_t)(NNE * (NNE + 1) / 2 * NDN * NDN);
+      // compact upper-block layout (fegpu_internal.h): block (a <= b) at NDN^2 * (b(b+1)/2 + a), column-major inside;
+      // element-major records, or planes (value index x vstride + slot) for the thread-per-node numeric kernel
+      constexpr int64_t REC = (int64_t)(NNE * (NNE + 1) / 2 * NDN * NDN);
+      double *Ve = P.vstride > 0 ? P.V + slot : P.V + slot * REC;
+      const int64_t es = P.vstride > 0 ? P.vstride : 1;
 #pragma unroll
       for (int k = 0; k < EPT; k++) {
         if (t + k * TPE < NENT) {
           const int r = er[k], c = ec[k];
           const int a = r / NDN, i = r % NDN, b = c / NDN, j = c % NDN;
-          double *Vb = Ve + NDN * NDN * (b * (b + 1) / 2 + a);
-          Vb[j * NDN + i] = acc[k];
-          if (a == b && i != j) Vb[i * NDN + j] = acc[k];
+          const int o = NDN * NDN * (b * (b + 1) / 2 + a);
+          Ve[(o + j * NDN + i) * es] = acc[k];
+          if (a == b && i != j) Ve[(o + i * NDN + j) * es] = acc[k];
         }
       }
     } else if (live) {
-      double *Ve = P.V + slot * (int64_t)(EM * EM);
+      double *Ve = P.vstride > 0 ? P.V + slot : P.V + slot * (int64_t)(EM * EM);
+      const int64_t es = P.vstride > 0 ? P.vstride : 1;
 #pragma unroll
       for (int k = 0; k < EPT; k++) {
         if (t + k * TPE < NENT) {
           const int r = er[k], c = ec[k];
-          Ve[c * EM + r] = acc[k];
-          if (SYM && r != c) Ve[r * EM + c] = acc[k];
+          Ve[(c * EM + r) * es] = acc[k];
+          if (SYM && r != c) Ve[(r * EM + c) * es] = acc[k];
         }
       }
     }
@@ -393,6 +398,7 @@ int32_t launch_generic(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
   P.conn = mesh->d_conn; P.xyz = mesh->d_xyz; P.nnodes = mesh->nnodes; P.elem_list = mesh->d_elem_list;
   P.nactive = mesh->nactive; P.tab = mesh->d_tab; P.w = mesh->d_w; P.npts = mesh->npts; P.V = d_V;
   P.compact = (fa.compact && fe_form_symmetric(FORM)) ? 1 : 0;
+  P.vstride = (fa.planes && FORM != FORM_LINDOT && FORM != FORM_MASSLIKE) ? fa.vstride : 0;
   for (int i = 0; i < 36; i++) P.coef[i] = fa.coef[i];
   P.m = fa.m; P.otherdim = fa.otherdim; P.uvel = fa.d_uvel;
   for (int i = 0; i < 9; i++) P.rm[i] = fa.rm[i];
@@ -457,6 +463,20 @@ int32_t fe_integrate_dot_scalar(fegpu_mesh *mesh, const FormArgs &fa, double *d_
 
 bool fe_integrate_supports_compact(const fegpu_mesh *mesh, const FormArgs &fa) {
   return fe_form_symmetric(fa.form) || fe_dot_scalar_applies(mesh, fa);  // a 1 x 1 coefficient makes bilform_dot symmetric
+}
+
+// Which kernels write the plane layout: the H8 kernels, the scalar mass kernel and the generic entry-per-thread kernel -- i.e.
+// every bilinear form on the element types the thread-per-node path takes, except the register-tiled elasticity kernel (T4
+// elasticity keeps element-major records) and the Kronecker path of bilform_dot with more than 3 dofs per node.
+bool fe_integrate_supports_planes(const fegpu_mesh *mesh, const FormArgs &fa) {
+  if (fa.form == FORM_LINDOT || fa.form == FORM_MASSLIKE) return false;
+  if (fa.form == FORM_DOT && fa.ndn > 3) return false;
+  const bool rotated = fa.use_rm && (fa.form == FORM_DIFF_GEN || fa.form == FORM_ELASTIC);
+  if (fa.form == FORM_ELASTIC && mesh->sdim == 3 && mesh->mdim == 3 && !rotated && !(mesh->etype == FEGPU_H8 && mesh->npts == 8)) {
+    static const bool tiled_off = std::getenv("FEGPU_ELASTIC_TILED") && std::atoi(std::getenv("FEGPU_ELASTIC_TILED")) == 0;
+    if (!tiled_off) return false;  // k_elastic_tiled
+  }
+  return true;
 }
 
 namespace {

@@ -93,6 +93,8 @@ struct fegpu_asm {
   int64_t V_n = 0;
   int last_EM = 0;
   bool V_compact = false;  // d_V holds the compact symmetric layout (fe_compact_size per element)
+  bool V_planes = false;   // d_V is in plane form: value k of slot s at d_V[k * V_stride + s]
+  int64_t V_stride = 0;
   // result
   int64_t nrows = 0, ncols = 0, nnz = 0;
   const int64_t *d_colptr = nullptr;  // borrowed from a Pattern or == own_colptr
@@ -192,6 +194,10 @@ struct FormArgs {
   bool use_rm;      // false = identity
   const double *d_uvel = nullptr;  // bilform_convection: nodal convective velocity on the device, [sdim][nnodes]
   bool compact;     // symmetric forms only: write the compact upper-block layout (fe_compact_size) instead of full matrices
+  // struct-of-arrays output for the thread-per-node numeric kernel: value k of the element in slot s at V[k * vstride + s]
+  // (k = the position inside the compact / full element record).  Only the kernels of fe_integrate_supports_planes.
+  bool planes = false;
+  int64_t vstride = 0;
 };
 // Compact layout of a symmetric element matrix (nne nodes x ndn dofs): the upper block triangle, block (a <= b) of
 // ndn x ndn values (column-major: row comp i, col comp j at j*ndn + i) at ndn*ndn*(b(b+1)/2 + a); diagonal blocks are stored
@@ -204,18 +210,24 @@ static inline bool fe_form_values_symmetric(int form) { return form <= 2 || form
 int32_t fe_integrate(fegpu_mesh *mesh, const FormArgs &fa, double *d_V);
 // does the integration kernel that will run write the compact symmetric layout when fa.compact is set?
 bool fe_integrate_supports_compact(const fegpu_mesh *mesh, const FormArgs &fa);
+bool fe_integrate_supports_planes(const fegpu_mesh *mesh, const FormArgs &fa);  // ... the plane layout when fa.planes is set?
 
 // ---- pattern + gather (fegpu_pattern.cu) ---------------------------------------------------------------
 // `fork` (optional) is invoked once, on the calling thread, as soon as the build knows it will not fall back to the sort path
 // for an early reason (degenerate elements, encoding limits): the caller launches independent work on another stream there
-int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork = nullptr);
+// fork(tile): tile = the thread-per-node path is being taken (the integration may write the plane layout); it may be invoked a
+// second time with tile = false when that path's preconditions turn out violated
+int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork = nullptr);
 // Patterns are shared: the dof map that built one and every assembler whose result borrows its colptr / rowval hold a
 // reference (an invalidated or rebuilt pattern must not pull the arrays from under a result that is still being read).
 void fe_pattern_retain(Pattern *p);
 void fe_pattern_free(Pattern *p);  // drops one reference; the arrays go back to the block cache with the last one
 // thread-per-node kernels for small stencils (fegpu_tile.cu); *taken = false: preconditions not met, run the general path
-int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork, bool *taken);
-int32_t fe_tile_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_nzval, bool *taken);
+int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork, bool *taken);
+bool fe_tile_candidate(const fegpu_dofmap *dm);  // would fe_tile_build try the thread-per-node path for this dof map?
+bool fe_pattern_is_tile(const Pattern *p);
+int32_t fe_tile_gather(fegpu_dofmap *dm, const double *d_V, bool compact, bool planes, int64_t vstride, double *d_nzval);
+int32_t fe_tile_vec_gather(fegpu_dofmap *dm, const double *d_elvec, double *d_F);
 void fe_pattern_set_stream(Pattern *p, cudaStream_t s);  // stream its stream-ordered frees are queued on
 cudaEvent_t fe_pattern_ready_event(const Pattern *p);    // completes when every array of the pattern is final
 int64_t fe_pattern_nnz(const Pattern *p);
@@ -225,12 +237,13 @@ const int64_t *fe_pattern_rowval(const Pattern *p);
 bool fe_pattern_compressed(const Pattern *p, const int32_t **nbr, const int64_t **nbrptr, int64_t *total_nbr, const int32_t **dof, int *ndn,
                            int64_t *nnodes);
 bool fe_pattern_usable(const fegpu_dofmap *dm);  // mesh-structured fast path applicable?
-int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_nzval);
+int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_nzval, bool planes = false, int64_t vstride = 0);
 // element vectors [nactive][nne*ndn] -> dense vector F[row_nall] (zeroed here): every node sums its adjacent elements'
 // entries in ascending element order (= the reference's element loop); rows of nodes this rank does not own stay zero
 int32_t fe_vec_gather(fegpu_dofmap *dm, const double *d_elvec, double *d_F);
 // compact symmetric layout -> full element matrices in emission order (raw-COO export only)
-int32_t fe_expand_compact(fegpu_ctx *ctx, const double *d_Vc, double *d_Vfull, int64_t nelem, int nne, int ndn, const int32_t *d_perm = nullptr);
+int32_t fe_expand_compact(fegpu_ctx *ctx, const double *d_Vc, double *d_Vfull, int64_t nelem, int nne, int ndn, const int32_t *d_perm = nullptr,
+                          int64_t vstride = 0 /* > 0: d_Vc is in plane form */);
 
 // ---- generic COO -> CSC by sort (fegpu_sort.cu) --------------------------------------------------------
 // d_I, d_J 1-based int64, n triplets in emission order.  Fills the assembler's own colptr/rowval/nzval.

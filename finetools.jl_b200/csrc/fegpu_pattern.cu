@@ -1064,7 +1064,8 @@ void fe_pattern_free(Pattern *p) {
       cudaDeviceSynchronize();
     }
   }
-  void *ptrs[] = {p->d_colptr, p->d_rowval, p->d_adjptr, p->d_adj_slot, p->d_adj_lc, p->d_nnbr, p->d_nbrptr, p->d_cslot, p->d_rank, p->d_order, p->d_nbr};
+  void *ptrs[] = {p->d_colptr, p->d_rowval, p->d_adjptr, p->d_adj_slot, p->d_adj_lc, p->d_nnbr, p->d_nbrptr, p->d_cslot, p->d_rank, p->d_order, p->d_nbr,
+                  p->t_deg, p->t_adj, p->t_cs};
   for (void *q : ptrs)
     if (q) fe_dev_free(p->ctx, q, st);
   if (p->ready) cudaEventDestroy(p->ready);
@@ -1074,6 +1075,7 @@ void fe_pattern_free(Pattern *p) {
 void fe_pattern_set_stream(Pattern *p, cudaStream_t s) { p->stream = s; }
 cudaEvent_t fe_pattern_ready_event(const Pattern *p) { return p ? p->ready : nullptr; }
 int64_t fe_pattern_nnz(const Pattern *p) { return p->nnz; }
+bool fe_pattern_is_tile(const Pattern *p) { return p && p->tile; }
 const int64_t *fe_pattern_colptr(const Pattern *p) { return p->d_colptr; }
 const int64_t *fe_pattern_rowval(const Pattern *p) { return p->d_rowval; }
 bool fe_pattern_compressed(const Pattern *p, const int32_t **nbr, const int64_t **nbrptr, int64_t *total_nbr, const int32_t **dof, int *ndn,
@@ -1087,7 +1089,7 @@ bool fe_pattern_usable(const fegpu_dofmap *dm) {
   return dm->injective && !dm->mesh->degenerate && dm->row_nall == dm->col_nall && dm->mesh->nne <= 32;
 }
 
-int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork) {
+int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork) {
   fegpu_ctx *ctx = dm->ctx;
   fegpu_mesh *mesh = dm->mesh;
   cudaStream_t st = ctx->stream;
@@ -1200,7 +1202,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   // limits of the packed encodings: neighbour slots and rows per column < 65535
   const size_t smem1 = (size_t)WPB * (maxdeg + 3 * (size_t)capc) * sizeof(uint32_t);
   if (P->maxcand >= 65535 || (int64_t)P->maxcand * ndn >= 65535 || smem1 > 200 * 1024) return bail();
-  if (fork) PT((*fork)());  // the structured path will be taken: independent work may start on another stream now
+  if (fork) PT((*fork)(false));  // the structured path will be taken: independent work may start on another stream now
   FE_TRACE("build: fork (integration queued)");
 
   PT(dalloc(ctx, &P->d_adj_slot, nadj));
@@ -1405,17 +1407,14 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork)
   return FEGPU_OK;
 }
 
-int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_nzval) {
+int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_nzval, bool planes, int64_t vstride) {
   fegpu_ctx *ctx = dm->ctx;
   Pattern *P = dm->pat;
   fegpu_mesh *mesh = dm->mesh;
   if (!P) return fegpu_fail(ctx, FEGPU_ERR_STATE, "no pattern");
   if (P->nnz == 0) return FEGPU_OK;
-  {
-    bool taken = false;
-    FE_TRY(fe_tile_gather(dm, d_V, compact, d_nzval, &taken));
-    if (taken) return FEGPU_OK;
-  }
+  if (P->tile) return fe_tile_gather(dm, d_V, compact, planes, vstride, d_nzval);
+  if (planes) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: plane layout without a thread-per-node pattern");
   GatherParams G{mesh->nnodes, mesh->nne, dm->ndn, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, P->d_nnbr, P->d_nbrptr, P->d_cslot,
                  P->d_rank, dm->d_dof, P->d_colptr, d_V, d_nzval, P->maxnbr, P->maxdeg, P->maxcand, P->d_order, P->d_order ? P->norder : mesh->nnodes};
   const int EM = mesh->nne * dm->ndn;
@@ -1486,6 +1485,7 @@ int32_t fe_vec_gather(fegpu_dofmap *dm, const double *d_elvec, double *d_F) {
   fegpu_mesh *mesh = dm->mesh;
   if (!P) return fegpu_fail(ctx, FEGPU_ERR_STATE, "no pattern");
   CUDA_TRY(ctx, cudaMemsetAsync(d_F, 0, sizeof(double) * (size_t)std::max<int64_t>(dm->row_nall, 1), ctx->stream));
+  if (P->tile) return fe_tile_vec_gather(dm, d_elvec, d_F);
   const int64_t n = mesh->nnodes * dm->ndn;
   if (n == 0) return FEGPU_OK;
   k_vec_gather<<<grid_for(n, 256), 256, 0, ctx->stream>>>(mesh->nnodes, mesh->nne, dm->ndn, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, dm->d_dof,

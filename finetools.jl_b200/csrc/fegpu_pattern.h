@@ -30,9 +30,13 @@ struct Pattern {
   cudaStream_t alloc_stream = 0;  // stream the arrays were allocated on (the build's); they are freed on it, see fe_pattern_free
   int refs = 1;                   // owners: the dof map + every assembler result that borrows colptr / rowval
   // built by the thread-per-node kernels (fegpu_tile.cu): node window, dof map affine on it, adjacency capacity per node
+  // -- in plane (struct-of-arrays) form instead of the CSR adjacency / cslot arrays above, which stay nullptr:
   bool tile = false;
-  int64_t tile_lo = 0, tile_nw = 0;
-  int tile_md = 0;
+  int64_t tile_lo = 0, tile_nw = 0, tile_nwp = 0;  // node window [lo, lo + nw), plane stride nwp
+  int tile_md = 0;                 // adjacency capacity per node (planes)
+  int32_t *t_deg = nullptr;        // [nw] elements at window node i
+  uint32_t *t_adj = nullptr;       // [md][nwp] (slot << 5) | local index, ascending slot per node
+  void *t_cs = nullptr;            // [md][nwp] one word per (node, adjacent element): the NNE neighbour slots, a byte each (0xff = dropped)
   cudaEvent_t ready = nullptr;    // recorded when the build's last kernel is queued: the result transport may ship the pattern's
                                   // arrays while the integration and the numeric phase of the same call are still running
 };

@@ -6,27 +6,37 @@
 // node: its <= 64 candidate neighbours are sorted by a compile-time sorting network on registers (fegpu_sortnet.h, 543
 // comparators = 1086 VIMNMX), heads are found by a sequential scan of the sorted registers, and a CTA of 128 consecutive
 // nodes writes its outputs -- which are contiguous in rowval / nzval when the dof map is node-major affine -- with flat,
-// fully coalesced loops.  Three kernels per fresh assembly:
+// fully coalesced loops.
 //
+// Data layout: PLANES.  A thread-per-node kernel whose lanes each read their own record touches 32 cache lines per load
+// instruction, and the L1 data pipe retires about one line per cycle: the first version of the numeric kernel (element
+// records of 288 B, one per lane) ran at 88 % of the L1 wavefront peak and 32 % of DRAM (profiles/r02_ncu_tile_v1.txt).
+// So everything a node reads lives in struct-of-arrays form, indexed [entry][node] or [entry][element slot]:
+//   adj  uint32 [MAXDEG][nwp]   adjacent element j of window node i: (slot << 5) | local index, ascending slot
+//   cs   word   [MAXDEG][nwp]   neighbour slot of each of the NNE candidates of (node, adjacent element): one byte each
+//                               (0xff = row not owned by this rank), packed in one 64-bit (H8) / 32-bit (Q4, T3, T4) word
+//   V    double [values per element][vstride]   element matrices as written by the integration kernels (FormArgs::planes)
+// Consecutive lanes = consecutive nodes read consecutive words; with elements stored in ascending-smallest-node order
+// (fe_order_elements) the j-th adjacent elements of consecutive nodes are consecutive slots, so the V loads of a warp
+// fall into one or two lines as well.
+//
+// Three kernels per fresh assembly:
 //   k_adj_table   one pass over the connectivity: count the elements at every node (atomicAdd, whose return value is the
-//                 position) and drop (slot << 5 | local index) into a fixed-capacity row of the node.  Replaces the
-//                 count + fill pair of the general path (no second read of conn, no rank array).
-//   k_sym_tile    per node: sort the adjacency row, write it to the CSR arrays (ascending element order = the reference's
-//                 left-to-right duplicate sum), load the element rows, sort the candidate keys (node << 6 | k), count the
-//                 unique neighbours.  Per CTA: block scan + decoupled look-back over the tiles (single pass: the global
-//                 prefix of the neighbour counts IS nbrptr and, for an affine dof map, colptr).  Then cslot, the neighbour
-//                 lists and rowval go out from shared memory.  Replaces k_nbr_group + scans + k_col_counts + k_rows_sorted
-//                 and the intermediate list U (written and read once each in the general path).
+//                 position) and drop (slot << 5 | local index) into plane `position` of the node's column.
+//   k_sym_tile    per node: sort the adjacency column (ascending slot = the order of the duplicate sum), load the element
+//                 rows, sort the candidate keys (node << 6 | k), count the unique neighbours.  Per CTA: block scan +
+//                 decoupled look-back over the tiles (single pass: the global prefix of the neighbour counts IS nbrptr and,
+//                 for an affine dof map, colptr).  Then the cs planes, the neighbour lists and rowval go out.
 //   k_gather_tile numeric phase: thread per (node, column component) walks the node's adjacent elements in ascending order
 //                 and adds every value into the CTA's shared-memory image of its slice of nzval (laid out exactly as in
 //                 memory, so the write-out is a flat copy).  No atomics, fixed order => bit-reproducible
-//                 (test/test_basics.jl:3039-3045).  ~15 instead of ~170 warp instructions per node for scalar H8.
+//                 (test/test_basics.jl:3039-3045).
 //
-// Preconditions, checked on the device and read back with the build's first host round trip: every node has at most MAXDEG
-// elements, no element lists a node twice, node ids < 2^26 - 2, and the dof map is node-major affine on the node window
-// (dof[p][n] = dof[0][lo] + (n - lo) ndn + p: the default numberdofs! without fixed dofs, FieldModule.jl:328-345).  When one
-// fails the caller runs the general path of fegpu_pattern.cu instead (free-first numberings, T10 / H20 / H27, high valences).
-// The pattern that comes out is the same set of arrays either way.
+// Preconditions, checked on the device and read back with the build's ONE host round trip (the kernels are launched
+// optimistically and are safe when a precondition fails): every node has at most MAXDEG elements, no element lists a node
+// twice, node ids < 2^26 - 2, and the dof map is node-major affine on the node window (dof[p][n] = dof[0][lo] + (n - lo) ndn
+// + p: the default numberdofs! without fixed dofs, FieldModule.jl:328-345).  When one fails the caller runs the general path
+// of fegpu_pattern.cu instead (free-first numberings, T10 / H20 / H27, high valences) and the failure is remembered.
 #include <cstdlib>
 
 #include "fegpu_internal.h"
@@ -40,15 +50,25 @@ constexpr int TILE_KB = 6;   // low bits of a candidate key: k = a * nne + li < 
 constexpr uint32_t TILE_DROPPED = 0xffffffffu >> TILE_KB;  // node field of a candidate whose row this rank does not own / padding
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_VMASK = (1ull << 62) - 1ull;
 
+template <int NNE>
+struct CsWord {
+  using type = uint32_t;
+};
+template <>
+struct CsWord<8> {
+  using type = unsigned long long;
+};
+
 struct TileParams {
   const int32_t *conn;
   const int32_t *elem_list;
   int64_t nactive;
   int64_t nnodes;
-  int64_t lo, nw;  // node window [lo, lo + nw)
+  int64_t lo, nw, nwp;      // node window [lo, lo + nw); plane stride nwp >= nw
   int32_t own_lo, own_hi;   // PART == 1: owned rows are the node range [own_lo, own_hi)
   const uint8_t *rowowned;  // PART == 2: byte map
   const int32_t *dof;       // [ndn][nnodes]
+  int64_t ncols;
 };
 
 // dof[p][n] == dof[0][lo] + (n - lo) * ndn + p on the whole window?
@@ -60,8 +80,9 @@ __global__ void __launch_bounds__(256) k_dof_affine(const int32_t *__restrict__ 
   if (bad) *notaffine = 1;
 }
 
+// flags: [0] an element lists a node twice, [2] a node has more than MAXDEG elements
 template <int NNE, int MAXDEG>
-__global__ void __launch_bounds__(256) k_adj_table(const TileParams P, int32_t *__restrict__ deg, uint32_t *__restrict__ tab, int *degenerate) {
+__global__ void __launch_bounds__(256) k_adj_table(const TileParams P, int32_t *__restrict__ deg, uint32_t *__restrict__ tab, int *flags) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.nactive * NNE) return;
   const int64_t slot = i / NNE;
@@ -69,20 +90,28 @@ __global__ void __launch_bounds__(256) k_adj_table(const TileParams P, int32_t *
   const int64_t e = P.elem_list ? (int64_t)P.elem_list[slot] : slot;
   const int32_t *c = P.conn + e * NNE;
   const int n = c[lc];
-  const int pos = atomicAdd(&deg[n], 1);
-  if (pos < MAXDEG) tab[((int64_t)n - P.lo) * MAXDEG + pos] = ((uint32_t)slot << 5) | (uint32_t)lc;
+  const int pos = atomicAdd(&deg[n - P.lo], 1);
+  if (pos < MAXDEG) tab[(int64_t)pos * P.nwp + (n - P.lo)] = ((uint32_t)slot << 5) | (uint32_t)lc;
+  else flags[2] = 1;
   for (int k = 0; k < lc; k++)
-    if (c[k] == n) *degenerate = 1;
+    if (c[k] == n) flags[0] = 1;
 }
 
-// prefix arrays outside the window: `before` ahead of it, the window's last value behind it (cf. k_fill_outside)
-__global__ void k_tile_fill_outside(int64_t *__restrict__ a0, int64_t *__restrict__ a1, int64_t len, int64_t lo, int64_t hi, int64_t before) {
+// prefix arrays outside the window: `before` ahead of it, the window's last value behind it
+__global__ void k_tile_fill_outside(int64_t *__restrict__ a, int64_t len, int64_t lo, int64_t hi, int64_t before) {
   const int64_t nout = len - (hi - lo + 1);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nout) return;
   const int64_t idx = (i < lo) ? i : i + (hi - lo + 1);
-  if (a0) a0[idx] = (i < lo) ? before : a0[hi];
-  if (a1) a1[idx] = (i < lo) ? before : a1[hi];
+  a[idx] = (i < lo) ? before : a[hi];
+}
+// colptr outside the window's dof range [dlo, dlo + nw * ndn], dlo = dof[0][lo] read on the device (no host round trip)
+__global__ void k_tile_fill_colptr(int64_t *__restrict__ colptr, int64_t ncols, const int32_t *__restrict__ dof, int64_t lo, int64_t nw, int ndn) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > ncols) return;
+  const int64_t dlo = dof[lo], dhi = min(dlo + nw * ndn, ncols);
+  if (j < dlo) colptr[j] = 1;
+  else if (j > dhi) colptr[j] = colptr[dhi];
 }
 
 __device__ __forceinline__ unsigned long long ld_state(const unsigned long long *p) { return *reinterpret_cast<const volatile unsigned long long *>(p); }
@@ -105,16 +134,17 @@ __device__ __forceinline__ void load_conn_row(const int32_t *__restrict__ row, i
 // out[0] = total neighbour entries of the window, out[1] = largest neighbour count, out[2] = tile ticket
 template <int NNE, int MAXDEG, int NDN, int PART>
 __global__ void __launch_bounds__(TILE_T, 4)
-    k_sym_tile(const TileParams P, const int64_t *__restrict__ adjptr, const uint32_t *__restrict__ tab, int32_t *__restrict__ adj_slot,
-               uint8_t *__restrict__ adj_lc, int32_t *__restrict__ nnbr, int64_t *__restrict__ nbrptr, int64_t *__restrict__ colptr,
-               uint16_t *__restrict__ cslot, int64_t *__restrict__ rowval, int32_t *__restrict__ nbr_out, unsigned long long *tile_state,
+    k_sym_tile(const TileParams P, const int32_t *__restrict__ deg_in, uint32_t *__restrict__ adj_planes,
+               typename CsWord<NNE>::type *__restrict__ cs_planes, int32_t *__restrict__ nnbr, int64_t *__restrict__ nbrptr,
+               int64_t *__restrict__ colptr, int64_t *__restrict__ rowval, int32_t *__restrict__ nbr_out, unsigned long long *tile_state,
                unsigned long long *out) {
   constexpr int NKEY = NNE * MAXDEG;
-  constexpr int CSW = NKEY / 2 + 1;  // words per thread of the staged cslot row; odd => conflict-free when the lanes write the same k
-  static_assert(NKEY <= 64 && NKEY % 2 == 0 && CSW % 2 == 1, "candidate keys of a node must fit 6 bits");
+  constexpr int CSB = NKEY + 4;  // bytes per thread of the staged slot row: NKEY/4 + 1 words, odd => conflict-free when the lanes write the same k
+  static_assert(NKEY <= 64 && NKEY % 4 == 0 && (CSB / 4) % 2 == 1, "candidate keys of a node must fit 6 bits");
+  using CsT = typename CsWord<NNE>::type;
   extern __shared__ uint32_t smem_u32[];
-  uint32_t *U_sm = smem_u32;                   // [TILE_T * NKEY] unique neighbours of the tile's nodes, dense, node after node
-  uint32_t *cs_sm = smem_u32 + TILE_T * NKEY;  // [TILE_T][CSW]
+  uint32_t *U_sm = smem_u32;                                                  // [TILE_T * NKEY] unique neighbours of the tile's nodes, dense, node after node
+  uint8_t *cs_sm = reinterpret_cast<uint8_t *>(smem_u32 + TILE_T * NKEY);   // [TILE_T][CSB]
   __shared__ int s_tile;
   __shared__ long long s_base;
   __shared__ int s_wtot[TILE_T / 32];
@@ -126,30 +156,19 @@ __global__ void __launch_bounds__(TILE_T, 4)
   const int64_t i = (int64_t)tile * TILE_T + tid;  // window-relative node index
   const bool live = i < P.nw;
   const int64_t n = P.lo + i;
-  int64_t ab = 0;
-  int deg = 0;
-  if (live) {
-    ab = adjptr[n];
-    deg = min((int)(adjptr[n + 1] - ab), MAXDEG);
-  }
-  // ---- adjacency row: sort by element slot, write the CSR arrays
+  const int deg = live ? min(deg_in[i], MAXDEG) : 0;
+  // plane indices fit 32 bits (MAXDEG * nwp <= 16 * 2^26): one integer multiply-add per access, no 64-bit address registers
+  const int ii = (int)i, nwp = (int)P.nwp;
+  // ---- adjacency column: sort by element slot (the order of the duplicate sum), write it back in place
   uint32_t adj[MAXDEG];
-  {
-    const uint4 *row = reinterpret_cast<const uint4 *>(tab + i * MAXDEG);
 #pragma unroll
-    for (int v = 0; v < MAXDEG / 4; v++) {
-      uint4 x = make_uint4(~0u, ~0u, ~0u, ~0u);
-      if (4 * v < deg) x = row[v];
-      adj[4 * v + 0] = (4 * v + 0 < deg) ? x.x : ~0u;
-      adj[4 * v + 1] = (4 * v + 1 < deg) ? x.y : ~0u;
-      adj[4 * v + 2] = (4 * v + 2 < deg) ? x.z : ~0u;
-      adj[4 * v + 3] = (4 * v + 3 < deg) ? x.w : ~0u;
-    }
-  }
+  for (int j = 0; j < MAXDEG; j++) adj[j] = (j < deg) ? adj_planes[j * nwp + ii] : ~0u;
   fesort::sort<MAXDEG>(adj);
+#pragma unroll
+  for (int j = 0; j < MAXDEG; j++)
+    if (j < deg) adj_planes[j * nwp + ii] = adj[j];
   // ---- candidate keys: (neighbour node << 6) | k, k = a * NNE + li; rows of other ranks and padding carry the all-ones node.
-  // All loads first (element ids, then the connectivity rows: 2 x MAXDEG independent requests in flight per thread); the
-  // stores of the sorted adjacency come after the key sort so that nothing orders the loads behind them.
+  // All loads first (element ids, then the connectivity rows: 2 x MAXDEG independent requests in flight per thread).
   const int32_t *__restrict__ conn = P.conn;
   const int32_t *__restrict__ elem_list = P.elem_list;
   uint32_t el[MAXDEG];
@@ -175,12 +194,6 @@ __global__ void __launch_bounds__(TILE_T, 4)
     }
   }
   fesort::sort<NKEY>(keys);
-#pragma unroll
-  for (int j = 0; j < MAXDEG; j++)
-    if (j < deg) {
-      adj_slot[ab + j] = (int32_t)(adj[j] >> 5);
-      adj_lc[ab + j] = (uint8_t)(adj[j] & 31u);
-    }
   // ---- unique neighbours of this node
   int nu = 0;
   {
@@ -192,7 +205,8 @@ __global__ void __launch_bounds__(TILE_T, 4)
       prev = node;
     }
   }
-  // ---- prefix of the counts: inside the CTA, then over the tiles (decoupled look-back)
+  // ---- prefix of the counts inside the CTA; the tile's aggregate is published right away, the look-back over the earlier
+  // tiles happens after the base-independent work below, when their prefixes have had time to arrive
   int incl = nu;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -209,12 +223,46 @@ __global__ void __launch_bounds__(TILE_T, 4)
     total += t;
   }
   const int excl = woff + incl - nu;
+  if (tid == 0) st_state(tile_state + tile, (tile == 0 ? ST_PREFIX : ST_AGG) | (unsigned long long)total);
+  // ---- neighbour slot of every candidate (staged row, one byte each) and the unique list (dense, at the node's offset)
+  {
+    uint8_t *cs8 = cs_sm + tid * CSB;
+    int slot = -1;
+    uint32_t prev = TILE_DROPPED;
+#pragma unroll
+    for (int x = 0; x < NKEY; x++) {
+      const uint32_t node = keys[x] >> TILE_KB, k = keys[x] & ((1u << TILE_KB) - 1u);
+      const bool valid = node != TILE_DROPPED;
+      const bool head = valid && node != prev;
+      slot += head ? 1 : 0;
+      cs8[k] = valid ? (uint8_t)slot : (uint8_t)0xffu;
+      if (head) U_sm[excl + slot] = node;
+      prev = node;
+    }
+    // the thread's own row back from shared memory, one word per adjacent element, straight into the planes (coalesced)
+    const uint32_t *row = reinterpret_cast<const uint32_t *>(cs8);
+#pragma unroll
+    for (int j = 0; j < MAXDEG; j++) {
+      if (j < deg) {
+        CsT w;
+        if constexpr (NNE == 8) w = (unsigned long long)row[2 * j] | ((unsigned long long)row[2 * j + 1] << 32);
+        else if constexpr (NNE == 4) w = row[j];
+        else w = (uint32_t)cs8[3 * j] | ((uint32_t)cs8[3 * j + 1] << 8) | ((uint32_t)cs8[3 * j + 2] << 16) | 0xff000000u;
+        cs_planes[j * nwp + ii] = w;
+      }
+    }
+  }
+  if (live) nnbr[n] = nu;
+  {
+    int mx = nu;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if (lane == 0 && mx > 0) atomicMax(out + 1, (unsigned long long)mx);
+  }
+  // ---- decoupled look-back (warp 0): sum the aggregates of the preceding tiles down to the first published prefix
   if (warp == 0) {
     long long run = 0;
-    if (tile == 0) {
-      if (lane == 0) st_state(tile_state, ST_PREFIX | (unsigned long long)total);
-    } else {
-      if (lane == 0) st_state(tile_state + tile, ST_AGG | (unsigned long long)total);
+    if (tile > 0) {
       int look = tile - 1;
       while (true) {
         const int idx = look - lane;
@@ -235,43 +283,21 @@ __global__ void __launch_bounds__(TILE_T, 4)
     }
     if (lane == 0) s_base = run;
   }
-  // ---- neighbour slot of every candidate (staged row) and the unique list (dense, at the node's offset inside the tile)
-  {
-    uint16_t *cs16 = reinterpret_cast<uint16_t *>(cs_sm + tid * CSW);
-    int slot = -1;
-    uint32_t prev = TILE_DROPPED;
-#pragma unroll
-    for (int x = 0; x < NKEY; x++) {
-      const uint32_t node = keys[x] >> TILE_KB, k = keys[x] & ((1u << TILE_KB) - 1u);
-      const bool valid = node != TILE_DROPPED;
-      const bool head = valid && node != prev;
-      slot += head ? 1 : 0;
-      cs16[k] = valid ? (uint16_t)slot : (uint16_t)0xffffu;
-      if (head) U_sm[excl + slot] = node;
-      prev = node;
-    }
-  }
   __syncthreads();
   const long long base = s_base;
   const int64_t dof0 = P.dof[P.lo];
   if (live) {
     const long long nb = base + excl;
-    nnbr[n] = nu;
     nbrptr[n] = nb;
     const int64_t c0 = dof0 + i * NDN;
 #pragma unroll
-    for (int q = 0; q < NDN; q++) colptr[c0 + q] = 1 + (nb * NDN + (long long)q * nu) * NDN;
+    for (int q = 0; q < NDN; q++)
+      if (c0 + q <= P.ncols) colptr[c0 + q] = 1 + (nb * NDN + (long long)q * nu) * NDN;  // the guard only matters when the map is not affine
     if (i == P.nw - 1) {
       nbrptr[n + 1] = nb + nu;
-      colptr[c0 + NDN] = 1 + (nb + nu) * (long long)(NDN * NDN);
+      if (c0 + NDN <= P.ncols) colptr[c0 + NDN] = 1 + (nb + nu) * (long long)(NDN * NDN);
       out[0] = (unsigned long long)(nb + nu);
     }
-  }
-  {
-    int mx = nu;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    if (lane == 0 && mx > 0) atomicMax(out + 1, (unsigned long long)mx);
   }
   // ---- outputs of the tile: contiguous in memory
   if (nbr_out)
@@ -293,61 +319,21 @@ __global__ void __launch_bounds__(TILE_T, 4)
       }
     }
   }
-  for (int t = 0; t < 32; t++) {
-    const int deg_t = __shfl_sync(0xffffffffu, deg, t);
-    const long long ab_t = __shfl_sync(0xffffffffu, (long long)ab, t);
-    if (deg_t == 0) continue;
-    const uint32_t *src = cs_sm + (warp * 32 + t) * CSW;
-    if (NNE % 2 == 0) {
-      uint32_t *dst = reinterpret_cast<uint32_t *>(cslot) + (ab_t * NNE) / 2;
-      for (int w = lane; w < deg_t * NNE / 2; w += 32) dst[w] = src[w];
-    } else {
-      uint16_t *dst = cslot + ab_t * NNE;
-      const uint16_t *s16 = reinterpret_cast<const uint16_t *>(src);
-      for (int k = lane; k < deg_t * NNE; k += 32) dst[k] = s16[k];
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------ numeric phase
+template <int NNE>
 struct TileGatherParams {
-  int64_t lo, nw, nnodes;
-  const int64_t *adjptr;
-  const int32_t *adj_slot;
-  const uint8_t *adj_lc;
+  int64_t lo, nw, nwp, nnodes;
+  const int32_t *deg;
+  const uint32_t *adj;
+  const typename CsWord<NNE>::type *cs;
   const int32_t *nnbr;
-  const uint16_t *cslot;
   const int64_t *colptr;
   const int32_t *dof;
   const double *V;
+  int64_t vstride;  // PLANES: doubles between the planes of two consecutive value indices
   double *nzval;
-};
-
-// the NNE neighbour slots (uint16) of one (node, adjacent element), packed two per register
-template <int NNE>
-struct CsRow {
-  uint32_t w[(NNE + 1) / 2];
-  __device__ __forceinline__ void fill() {
-#pragma unroll
-    for (int k = 0; k < (NNE + 1) / 2; k++) w[k] = 0xffffffffu;
-  }
-  __device__ __forceinline__ void load(const uint16_t *__restrict__ cp) {
-    if constexpr (NNE == 8) {
-      const uint4 x = *reinterpret_cast<const uint4 *>(cp);
-      w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
-    } else if constexpr (NNE == 4) {
-      const uint2 x = *reinterpret_cast<const uint2 *>(cp);
-      w[0] = x.x; w[1] = x.y;
-    } else {
-#pragma unroll
-      for (int k = 0; k < NNE; k++) {
-        const uint32_t u = cp[k];
-        if (k & 1) w[k >> 1] = (w[k >> 1] & 0xffffu) | (u << 16);
-        else w[k >> 1] = (w[k >> 1] & 0xffff0000u) | u;
-      }
-    }
-  }
-  __device__ __forceinline__ unsigned get(int li) const { return (li & 1) ? (w[li >> 1] >> 16) : (w[li >> 1] & 0xffffu); }
 };
 
 template <int NDN>
@@ -356,12 +342,13 @@ struct GatherShape {
   static constexpr int NPB = T / NDN;              // nodes per CTA
 };
 
-template <int NNE, int MAXDEG, int NDN, bool COMPACT>
-__global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileGatherParams G) {
+template <int NNE, int MAXDEG, int NDN, bool COMPACT, bool PLANES>
+__global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileGatherParams<NNE> G) {
   extern __shared__ double acc[];  // the CTA's slice of nzval: columns of its nodes, exactly as in memory
   constexpr int T = GatherShape<NDN>::T, NPB = GatherShape<NDN>::NPB;
   constexpr int EM = NNE * NDN, ND2 = NDN * NDN;
   constexpr int64_t VPE = COMPACT ? (int64_t)(NNE * (NNE + 1) / 2) * ND2 : (int64_t)EM * EM;
+  using CsT = typename CsWord<NNE>::type;
   const int tid = threadIdx.x;
   const int ln = tid / NDN, q = tid - ln * NDN;
   const int64_t i0 = (int64_t)blockIdx.x * NPB;
@@ -374,42 +361,36 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
   const int total = (int)(cbE - cb0);
   for (int idx = tid; idx < total; idx += T) acc[idx] = 0.0;
   int deg = 0, nu = 0, off = 0;
-  int64_t ab = 0;
   if (live) {
     nu = G.nnbr[n];
-    ab = G.adjptr[n];
-    deg = min((int)(G.adjptr[n + 1] - ab), MAXDEG);
+    deg = min(G.deg[i], MAXDEG);
     off = (int)(G.colptr[dof0 + i * NDN + q] - 1 - cb0);
   }
   __syncthreads();
   if (nu > 0) {
     double *col = acc + off;
-    const int32_t *__restrict__ adj_slot = G.adj_slot;
-    const uint8_t *__restrict__ adj_lc = G.adj_lc;
-    const uint16_t *__restrict__ cslot = G.cslot;
+    const int ii = (int)i, nwp = (int)G.nwp;  // plane indices fit 32 bits
+    const uint32_t *__restrict__ adjp = G.adj;
+    const CsT *__restrict__ csp = G.cs;
     const double *__restrict__ V = G.V;
-    // metadata of every adjacent element first (3 x MAXDEG independent loads in flight), then per element: all its value
-    // loads, then the adds.  Rows of other ranks (slot 0xffff) are loaded as well and dropped at the add: no predicate
-    // between the loads.
-    int64_t vb[MAXDEG];
-    int lcs[MAXDEG];
-    CsRow<NNE> cs[MAXDEG];
+    // metadata of every adjacent element first (2 x MAXDEG independent, coalesced loads in flight), then per element: all its
+    // value loads, then the adds.  Rows of other ranks (slot 0xff) are loaded as well and dropped at the add.
+    uint32_t ad[MAXDEG];
+    CsT cs[MAXDEG];
 #pragma unroll
     for (int j = 0; j < MAXDEG; j++) {
-      vb[j] = 0;
-      lcs[j] = 0;
-      cs[j].fill();
+      ad[j] = 0;
+      cs[j] = ~(CsT)0;
       if (j < deg) {
-        vb[j] = (int64_t)adj_slot[ab + j] * VPE;
-        lcs[j] = adj_lc[ab + j];
-        cs[j].load(cslot + (ab + j) * NNE);
+        ad[j] = __ldcs(adjp + (j * nwp + ii));
+        cs[j] = __ldcs(csp + (j * nwp + ii));
       }
     }
 #pragma unroll
     for (int j = 0; j < MAXDEG; j++) {
       if (j < deg) {
-        const double *Vb = V + vb[j];
-        const int lc = lcs[j];
+        const int64_t slot = ad[j] >> 5;
+        const int lc = (int)(ad[j] & 31u);
         double v[NNE][NDN];
 #pragma unroll
         for (int li = 0; li < NNE; li++) {
@@ -417,19 +398,23 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
             // block (min, max) of the upper block triangle, entry (comp of min, comp of max) at comp_max * NDN + comp_min
             const bool tr = li > lc;
             const int blk = tr ? li * (li + 1) / 2 + lc : lc * (lc + 1) / 2 + li;
-            const double *B = Vb + ND2 * blk;
 #pragma unroll
-            for (int p = 0; p < NDN; p++) v[li][p] = tr ? B[p * NDN + q] : B[q * NDN + p];
+            for (int p = 0; p < NDN; p++) {
+              const int k = ND2 * blk + (tr ? p * NDN + q : q * NDN + p);
+              v[li][p] = PLANES ? V[(int64_t)k * G.vstride + slot] : V[slot * VPE + k];
+            }
           } else {
-            const double *B = Vb + (lc * NDN + q) * EM + li * NDN;  // emission order: column (lc, q), rows (li, p)
 #pragma unroll
-            for (int p = 0; p < NDN; p++) v[li][p] = B[p];
+            for (int p = 0; p < NDN; p++) {
+              const int k = (lc * NDN + q) * EM + li * NDN + p;  // emission order: column (lc, q), rows (li, p)
+              v[li][p] = PLANES ? V[(int64_t)k * G.vstride + slot] : V[slot * VPE + k];
+            }
           }
         }
 #pragma unroll
         for (int li = 0; li < NNE; li++) {
-          const unsigned s = cs[j].get(li);
-          if (s != 0xffffu) {
+          const unsigned s = (unsigned)((cs[j] >> (8 * li)) & 0xffu);
+          if (s != 0xffu) {
             double *dst = col + s * NDN;
 #pragma unroll
             for (int p = 0; p < NDN; p++) dst[p] += v[li][p];
@@ -439,7 +424,28 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < total; idx += T) G.nzval[cb0 + idx] = acc[idx];
+  for (int idx = tid; idx < total; idx += T) __stcs(G.nzval + cb0 + idx, acc[idx]);
+}
+
+// Vector assembly on a thread-per-node pattern (cf. k_vec_gather): thread per (window node, component)
+__global__ void k_vec_gather_tile(int64_t lo, int64_t nw, int64_t nwp, int64_t nnodes, int nne, int ndn, int maxdeg, const int32_t *__restrict__ deg,
+                                  const uint32_t *__restrict__ adj, const int32_t *__restrict__ dof, const uint8_t *__restrict__ rowowned,
+                                  const double *__restrict__ elvec, double *__restrict__ F) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nw * ndn) return;
+  const int64_t i = t / ndn;
+  const int p = (int)(t - i * ndn);
+  const int64_t n = lo + i;
+  if (rowowned && !rowowned[n]) return;
+  const int d = min(deg[i], maxdeg);
+  if (d == 0) return;
+  const int EM = nne * ndn;
+  double acc = 0.0;
+  for (int j = 0; j < d; j++) {
+    const uint32_t a = adj[(int64_t)j * nwp + i];
+    acc += elvec[(int64_t)(a >> 5) * EM + (a & 31u) * ndn + p];
+  }
+  F[dof[(int64_t)p * nnodes + n]] = acc;
 }
 
 template <typename T>
@@ -452,33 +458,39 @@ int tile_maxdeg_for(int nne) { return nne == 8 ? 8 : ((nne == 4 || nne == 3) ? 1
 
 }  // namespace
 
+bool fe_tile_candidate(const fegpu_dofmap *dm) {
+  static const bool tile_off = std::getenv("FEGPU_TILE") && std::atoi(std::getenv("FEGPU_TILE")) == 0;  // A/B knob
+  const fegpu_mesh *mesh = dm->mesh;
+  if (tile_off || tile_maxdeg_for(mesh->nne) == 0 || dm->ndn > 3) return false;
+  if (mesh->win_hi - mesh->win_lo <= 0 || mesh->nactive <= 0) return false;
+  if (dm->tile_failed_version == mesh->topo_version) return false;  // this mesh / numbering already failed the preconditions
+  if (mesh->nnodes > (int64_t)TILE_DROPPED - 1 || mesh->nactive >= ((int64_t)1 << 27)) return false;
+  return true;
+}
+
 // Thread-per-node symbolic phase.  *taken = false: the preconditions do not hold, nothing was built, the caller runs the
 // general path.  *taken = true with dm->pat == nullptr: degenerate elements (the caller takes the sort path).
-int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork, bool *taken) {
+int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork, bool *taken) {
   *taken = false;
+  if (!fe_tile_candidate(dm)) return FEGPU_OK;
   fegpu_ctx *ctx = dm->ctx;
   fegpu_mesh *mesh = dm->mesh;
   cudaStream_t st = ctx->stream;
-  static const bool tile_off = std::getenv("FEGPU_TILE") && std::atoi(std::getenv("FEGPU_TILE")) == 0;  // A/B knob
   const int nne = mesh->nne, ndn = dm->ndn;
   const int MD = tile_maxdeg_for(nne);
   const int64_t nn = mesh->nnodes;
   const int64_t lo = mesh->win_lo, hi = mesh->win_hi, nw = hi - lo;
-  if (tile_off || MD == 0 || ndn > 3 || nw <= 0 || mesh->nactive <= 0) return FEGPU_OK;
-  if (dm->tile_failed_version == mesh->topo_version) return FEGPU_OK;  // this mesh / numbering already failed the preconditions
-  if (nn > (int64_t)TILE_DROPPED - 1 || mesh->nactive >= ((int64_t)1 << 27)) return FEGPU_OK;
+  const int64_t nwp = (nw + 31) & ~(int64_t)31;
   const int64_t nadj = mesh->nactive * nne;
 
-  int32_t *d_deg = nullptr;
-  uint32_t *d_tab = nullptr;
-  int *d_flags = nullptr;  // [0] degenerate, [1] dof map not affine, [2] largest degree
+  int *d_flags = nullptr;  // [0] degenerate, [1] dof map not affine, [2] a node with more than MD elements
   unsigned long long *d_state = nullptr, *d_out = nullptr;
   Pattern *P = nullptr;
   auto cleanup = [&]() {
-    void *ptrs[] = {d_deg, d_tab, d_flags, d_state, d_out};
+    void *ptrs[] = {d_flags, d_state, d_out};
     for (void *q : ptrs)
       if (q) fe_dev_free(ctx, q, st);
-    d_deg = nullptr; d_tab = nullptr; d_flags = nullptr; d_state = nullptr; d_out = nullptr;
+    d_flags = nullptr; d_state = nullptr; d_out = nullptr;
   };
   auto drop_pattern = [&]() {
     if (P) fe_pattern_free(P);
@@ -489,20 +501,6 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork, bo
 #define PC(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); drop_pattern(); return fegpu_fail(ctx, FEGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
   FE_TRACE("tile build: enter");
   fe_mark(ctx, "sym:start");
-  PT(talloc(ctx, &d_deg, (size_t)nn));
-  PT(talloc(ctx, &d_tab, (size_t)nw * MD));
-  PT(talloc(ctx, &d_flags, 4));
-  PC(cudaMemsetAsync(d_deg + lo, 0, sizeof(int32_t) * nw, st));
-  PC(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, st));
-  TileParams TP{mesh->d_conn, mesh->d_elem_list, mesh->nactive, nn, lo, nw, (int32_t)mesh->own_lo, (int32_t)mesh->own_hi, mesh->d_rowowned, dm->d_dof};
-  k_dof_affine<<<(unsigned)std::min<int64_t>(grid_for(nw, 256), (int64_t)ctx->sm_count * 8), 256, 0, st>>>(dm->d_dof, nn, ndn, lo, nw, d_flags + 1);
-  switch (nne) {
-    case 8: k_adj_table<8, 8><<<grid_for(nadj, 256), 256, 0, st>>>(TP, d_deg, d_tab, d_flags); break;
-    case 4: k_adj_table<4, 16><<<grid_for(nadj, 256), 256, 0, st>>>(TP, d_deg, d_tab, d_flags); break;
-    default: k_adj_table<3, 16><<<grid_for(nadj, 256), 256, 0, st>>>(TP, d_deg, d_tab, d_flags); break;
-  }
-  ctx->launches += 2;
-  fe_mark(ctx, "sym:k_adj_table");
   if (dm->pat) { fe_pattern_free(dm->pat); dm->pat = nullptr; }
   P = new Pattern();
   dm->pat = P;
@@ -511,59 +509,45 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork, bo
   P->alloc_stream = st;
   P->ncols = dm->col_nall;
   P->nrows = dm->row_nall;
-  PT(talloc(ctx, &P->d_adjptr, (size_t)nn + 1));
-  PT(fe_exclusive_scan_i32_to_i64(ctx, d_deg + lo, P->d_adjptr + lo, nw, 0, true, nullptr));
-  PT(fe_max_i32_dev(ctx, d_deg + lo, nw, d_flags + 2));
-  int h_flags[4] = {0, 0, 0, 0};
-  PC(cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
-  PC(cudaStreamSynchronize(st));
-  FE_TRACE("tile build: sync A done");
-  fe_mark(ctx, "sym:scan_adj");
-  if (h_flags[0]) {  // an element lists a node twice: no structured path at all (same as the general build's bail)
-    mesh->degenerate = true;
-    cleanup();
-    drop_pattern();
-    *taken = true;
-    return FEGPU_OK;
-  }
-  if (h_flags[1] || h_flags[2] > MD) {
-    dm->tile_failed_version = mesh->topo_version;
-    cleanup();
-    drop_pattern();
-    return FEGPU_OK;  // *taken stays false: general path
-  }
-  *taken = true;
-  if (fork) PT((*fork)());
-  const int maxdeg = std::max(h_flags[2], 1);
-  P->maxdeg = maxdeg;
-  P->maxcand = maxdeg * nne;
   const int64_t ntiles = (nw + TILE_T - 1) / TILE_T;
   const size_t nb_cap = (size_t)nadj * nne;  // upper bound of the neighbour entries: every candidate unique
-  PT(talloc(ctx, &P->d_adj_slot, (size_t)nadj));
-  PT(talloc(ctx, &P->d_adj_lc, (size_t)nadj));
+  const size_t cs_bytes = (nne == 8 ? sizeof(unsigned long long) : sizeof(uint32_t)) * (size_t)MD * nwp;
+  PT(talloc(ctx, &P->t_deg, (size_t)nw));
+  PT(talloc(ctx, &P->t_adj, (size_t)MD * nwp));
+  PT(talloc(ctx, &d_flags, 4));
   PT(talloc(ctx, &P->d_nnbr, (size_t)nn));
   PT(talloc(ctx, &P->d_nbrptr, (size_t)nn + 1));
   PT(talloc(ctx, &P->d_colptr, (size_t)P->ncols + 1));
-  PT(talloc(ctx, &P->d_cslot, nb_cap));
+  PT(fe_dev_alloc(ctx, (void **)&P->t_cs, cs_bytes, st));
   // rowval is sized before its length is known (single pass): the bound is what the reference's COO would hold per column
   // node, nnz is typically 0.42 of it (H8)
   PT(talloc(ctx, &P->d_rowval, nb_cap * ndn * ndn));
   if (ndn >= 2) PT(talloc(ctx, &P->d_nbr, nb_cap));
   PT(talloc(ctx, &d_state, (size_t)ntiles));
   PT(talloc(ctx, &d_out, 4));
+  PC(cudaMemsetAsync(P->t_deg, 0, sizeof(int32_t) * nw, st));
+  PC(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, st));
   PC(cudaMemsetAsync(d_state, 0, sizeof(unsigned long long) * ntiles, st));
   PC(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long) * 4, st));
-  if (nw < nn) {  // consumers that walk every node (the general gather as an A/B partner) must see empty nodes outside the window
-    if (lo > 0) PC(cudaMemsetAsync(P->d_nnbr, 0, sizeof(int32_t) * lo, st));
-    if (hi < nn) PC(cudaMemsetAsync(P->d_nnbr + hi, 0, sizeof(int32_t) * (nn - hi), st));
+  TileParams TP{mesh->d_conn, mesh->d_elem_list, mesh->nactive, nn, lo, nw, nwp, (int32_t)mesh->own_lo, (int32_t)mesh->own_hi, mesh->d_rowowned, dm->d_dof, P->ncols};
+  k_dof_affine<<<(unsigned)std::min<int64_t>(grid_for(nw, 256), (int64_t)ctx->sm_count * 8), 256, 0, st>>>(dm->d_dof, nn, ndn, lo, nw, d_flags + 1);
+  switch (nne) {
+    case 8: k_adj_table<8, 8><<<grid_for(nadj, 256), 256, 0, st>>>(TP, P->t_deg, P->t_adj, d_flags); break;
+    case 4: k_adj_table<4, 16><<<grid_for(nadj, 256), 256, 0, st>>>(TP, P->t_deg, P->t_adj, d_flags); break;
+    default: k_adj_table<3, 16><<<grid_for(nadj, 256), 256, 0, st>>>(TP, P->t_deg, P->t_adj, d_flags); break;
   }
+  ctx->launches += 2;
+  fe_mark(ctx, "sym:k_adj_table");
+  // optimistic: the element integration may start now (plane layout); should a precondition turn out violated, the caller
+  // integrates again in the layout the general path needs
+  if (fork) PT((*fork)(true));
   const int part = !mesh->d_rowowned ? 0 : (mesh->own_contig ? 1 : 2);
-  const size_t smem = sizeof(uint32_t) * (size_t)TILE_T * (nne * MD + nne * MD / 2 + 1);
+  const size_t smem = sizeof(uint32_t) * (size_t)TILE_T * (nne * MD) + (size_t)TILE_T * (nne * MD + 4);
 #define SYM_LAUNCH(NNE_, MD_, NDN_, PART_)                                                                                          \
   do {                                                                                                                              \
     PC(cudaFuncSetAttribute(k_sym_tile<NNE_, MD_, NDN_, PART_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    k_sym_tile<NNE_, MD_, NDN_, PART_><<<(unsigned)ntiles, TILE_T, smem, st>>>(TP, P->d_adjptr, d_tab, P->d_adj_slot, P->d_adj_lc, \
-        P->d_nnbr, P->d_nbrptr, P->d_colptr, P->d_cslot, P->d_rowval, P->d_nbr, d_state, d_out);                                    \
+    k_sym_tile<NNE_, MD_, NDN_, PART_><<<(unsigned)ntiles, TILE_T, smem, st>>>(TP, P->t_deg, P->t_adj,                              \
+        reinterpret_cast<CsWord<NNE_>::type *>(P->t_cs), P->d_nnbr, P->d_nbrptr, P->d_colptr, P->d_rowval, P->d_nbr, d_state, d_out); \
   } while (0)
 #define SYM_PART(NNE_, MD_, NDN_)                        \
   do {                                                   \
@@ -588,23 +572,39 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork, bo
   ctx->launches++;
   PC(cudaGetLastError());
   fe_mark(ctx, "sym:k_sym_tile");
-  if (nw < nn) {
-    k_tile_fill_outside<<<grid_for(nn - nw, 256), 256, 0, st>>>(P->d_adjptr, P->d_nbrptr, nn + 1, lo, hi, 0);
+  if (nw < nn) {  // nbrptr stays a complete prefix array for the consumers that walk every node (result transport)
+    k_tile_fill_outside<<<grid_for(nn - nw, 256), 256, 0, st>>>(P->d_nbrptr, nn + 1, lo, hi, 0);
+    ctx->launches++;
+    if (lo > 0) PC(cudaMemsetAsync(P->d_nnbr, 0, sizeof(int32_t) * lo, st));
+    if (hi < nn) PC(cudaMemsetAsync(P->d_nnbr + hi, 0, sizeof(int32_t) * (nn - hi), st));
+  }
+  if (nw * ndn < P->ncols) {
+    k_tile_fill_colptr<<<grid_for(P->ncols + 1, 256), 256, 0, st>>>(P->d_colptr, P->ncols, dm->d_dof, lo, nw, ndn);
     ctx->launches++;
   }
-  // colptr: the window's columns are dof0 .. dof0 + nw*ndn; constants on both sides.  dof0 is read on the host below, so the
-  // fill of the outside runs after the second round trip (it is tiny)
+  // the ONE host round trip of the build: preconditions + sizes
+  int h_flags[4] = {0, 0, 0, 0};
   unsigned long long h_out[4] = {0, 0, 0, 0};
-  int32_t h_dof0 = 0;
+  PC(cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
   PC(cudaMemcpyAsync(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost, st));
-  PC(cudaMemcpyAsync(&h_dof0, dm->d_dof + lo, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   PC(cudaStreamSynchronize(st));
-  FE_TRACE("tile build: sync B done");
-  const int64_t dlo = h_dof0, dhi = dlo + nw * ndn;  // colptr[dlo .. dhi] written by the kernel
-  if (dhi - dlo < P->ncols) {
-    k_tile_fill_outside<<<grid_for(P->ncols - (dhi - dlo), 256), 256, 0, st>>>(P->d_colptr, nullptr, P->ncols + 1, dlo, dhi, 1);
-    ctx->launches++;
+  FE_TRACE("tile build: sync done");
+  if (h_flags[0]) {  // an element lists a node twice: no structured path at all (same as the general build's bail)
+    mesh->degenerate = true;
+    cleanup();
+    drop_pattern();
+    *taken = true;
+    return FEGPU_OK;
   }
+  if (h_flags[1] || h_flags[2]) {
+    dm->tile_failed_version = mesh->topo_version;
+    cleanup();
+    drop_pattern();
+    return FEGPU_OK;  // *taken stays false: general path
+  }
+  *taken = true;
+  P->maxdeg = MD;
+  P->maxcand = MD * nne;
   P->total_nbr = (int64_t)h_out[0];
   P->nnz = P->total_nbr * ndn * ndn;
   P->maxnbr = std::max((int)h_out[1], 1);
@@ -614,6 +614,7 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork, bo
   P->tile = true;
   P->tile_lo = lo;
   P->tile_nw = nw;
+  P->tile_nwp = nwp;
   P->tile_md = MD;
   if (P->d_nbr && P->total_nbr == 0) {  // fe_pattern_compressed keys on d_nbr: nothing to compress
     fe_dev_free(ctx, P->d_nbr, st);
@@ -630,32 +631,34 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t()> *fork, bo
   return FEGPU_OK;
 }
 
-// Numeric phase on a pattern built by fe_tile_build.  *taken = false: not applicable (the general gather runs).
-int32_t fe_tile_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_nzval, bool *taken) {
-  *taken = false;
+// Numeric phase on a pattern built by fe_tile_build.
+int32_t fe_tile_gather(fegpu_dofmap *dm, const double *d_V, bool compact, bool planes, int64_t vstride, double *d_nzval) {
   fegpu_ctx *ctx = dm->ctx;
   Pattern *P = dm->pat;
   fegpu_mesh *mesh = dm->mesh;
-  static const bool gather_off = std::getenv("FEGPU_TILE_GATHER") && std::atoi(std::getenv("FEGPU_TILE_GATHER")) == 0;  // A/B knob
-  if (!P || !P->tile || gather_off) return FEGPU_OK;
+  if (!P || !P->tile) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: not a thread-per-node pattern");
   const int nne = mesh->nne, ndn = dm->ndn;
-  if (tile_maxdeg_for(nne) != P->tile_md || ndn > 3) return FEGPU_OK;
   const int T = (ndn == 3) ? 96 : 128, npb = T / ndn;
   const size_t smem = sizeof(double) * (size_t)npb * P->maxnbr * ndn * ndn;
-  if (smem > 200 * 1024) return FEGPU_OK;
-  *taken = true;
+  if (smem > 200 * 1024) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: gather accumulators exceed shared memory");
   if (P->nnz == 0) return FEGPU_OK;
-  TileGatherParams G{P->tile_lo, P->tile_nw, mesh->nnodes, P->d_adjptr, P->d_adj_slot, P->d_adj_lc, P->d_nnbr, P->d_cslot, P->d_colptr, dm->d_dof, d_V, d_nzval};
   const unsigned grid = (unsigned)((P->tile_nw + npb - 1) / npb);
-#define G_LAUNCH(NNE_, MD_, NDN_, C_)                                                                                               \
+#define G_LAUNCH(NNE_, MD_, NDN_, C_, PL_)                                                                                          \
   do {                                                                                                                              \
-    if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_gather_tile<NNE_, MD_, NDN_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_gather_tile<NNE_, MD_, NDN_, C_><<<grid, GatherShape<NDN_>::T, smem, ctx->stream>>>(G);                                       \
+    TileGatherParams<NNE_> G{P->tile_lo, P->tile_nw, P->tile_nwp, mesh->nnodes, P->t_deg, P->t_adj,                                 \
+                             reinterpret_cast<const CsWord<NNE_>::type *>(P->t_cs), P->d_nnbr, P->d_colptr, dm->d_dof, d_V, vstride, d_nzval}; \
+    if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_gather_tile<NNE_, MD_, NDN_, C_, PL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_gather_tile<NNE_, MD_, NDN_, C_, PL_><<<grid, GatherShape<NDN_>::T, smem, ctx->stream>>>(G);                                  \
   } while (0)
-#define G_C(NNE_, MD_, NDN_)                        \
-  do {                                              \
-    if (compact) G_LAUNCH(NNE_, MD_, NDN_, true);   \
-    else G_LAUNCH(NNE_, MD_, NDN_, false);          \
+#define G_PL(NNE_, MD_, NDN_, C_)                      \
+  do {                                                 \
+    if (planes) G_LAUNCH(NNE_, MD_, NDN_, C_, true);   \
+    else G_LAUNCH(NNE_, MD_, NDN_, C_, false);         \
+  } while (0)
+#define G_C(NNE_, MD_, NDN_)                   \
+  do {                                         \
+    if (compact) G_PL(NNE_, MD_, NDN_, true);  \
+    else G_PL(NNE_, MD_, NDN_, false);         \
   } while (0)
 #define G_NDN(NNE_, MD_)                  \
   do {                                    \
@@ -670,7 +673,21 @@ int32_t fe_tile_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double
   }
 #undef G_NDN
 #undef G_C
+#undef G_PL
 #undef G_LAUNCH
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return FEGPU_OK;
+}
+
+int32_t fe_tile_vec_gather(fegpu_dofmap *dm, const double *d_elvec, double *d_F) {
+  fegpu_ctx *ctx = dm->ctx;
+  Pattern *P = dm->pat;
+  fegpu_mesh *mesh = dm->mesh;
+  const int64_t n = P->tile_nw * dm->ndn;
+  if (n == 0) return FEGPU_OK;
+  k_vec_gather_tile<<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->tile_lo, P->tile_nw, P->tile_nwp, mesh->nnodes, mesh->nne, dm->ndn, P->tile_md, P->t_deg,
+                                                              P->t_adj, dm->d_dof, mesh->d_rowowned, d_elvec, d_F);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return FEGPU_OK;
