@@ -52,9 +52,10 @@ def run(name, fens, fes, ndn, rule, form, coef, m=3, reps=5):
            "csc_nnz_per_s_fresh": nnz / ((med(fresh, "symbolic_ms") + med(fresh, "numeric_ms")) * 1e-3),
            "csc_nnz_per_s_cached": nnz / (med(cached, "numeric_ms") * 1e-3)}
     print(json.dumps(out), flush=True)
-    for dm in a._device_cache.values():
-        dm.destroy()
+    ctx = a.ctx
     del a
+    ctx.release_meshes()
+    ctx.release_cache()
 
 
 def main():

@@ -61,9 +61,10 @@ def main():
                           "fresh_ms": med(ov, "total_ms"), "fresh_serial_ms": med(ser, "total_ms"),
                           "integrate_ms": med(ser, "integrate_ms"), "symbolic_ms": med(ser, "symbolic_ms"),
                           "numeric_ms": med(ser, "numeric_ms"), "cached_ms": med(cached, "total_ms")}), flush=True)
-        for dm in a._device_cache.values():
-            dm.destroy()
+        ctx = a.ctx
         del a
+        ctx.release_meshes()
+        ctx.release_cache()
 
 
 if __name__ == "__main__":
