@@ -394,10 +394,13 @@ def run_gpu(args):
         nnodes_rank = W.win[1] - W.win[0]    # node window of the rank
         vals = spec["vals"]
         ndn = spec["ndn"]
-        # compulsory bytes per launch of the three device stages on THIS rank
-        b_int = nact * (32 + 8 * vals) + nnodes_rank * (24 + 0)           # int32 conn + values written + coordinates read once
-        b_gather = nact * 8 * vals + nnz_local * 8 + nact * 8 * 8 * 2 + nact * 8 * 5   # values read once + nzval + cslot (2 B/candidate) + adjacency
-        b_sym = nnz_local * 8 + (n_ + 1) * 8 + nact * 8 * 8 * 2 + nact * 8 * (4 + 5 + 4)  # rowval + colptr + cslot written; conn read, adjacency written and read
+        # compulsory bytes per launch of the three device stages on THIS rank; H8: 8 adjacency planes per node
+        # (4 B each), 8 neighbour-slot words per node (8 B each: one byte per candidate), int32 degree / neighbour count
+        per_node_planes = 8 * 4 + 8 * 8
+        b_int = nact * (32 + 8 * vals) + nnodes_rank * 24                # int32 conn + values written + coordinates read once
+        b_gather = nact * 8 * vals + nnz_local * 8 + nnodes_rank * (per_node_planes + 4 + 4 + 8 * ndn)   # values read once + nzval + planes + deg, nnbr, colptr
+        b_sym = (nnz_local * 8 + (n_ + 1) * 8 + nnodes_rank * (8 * 8 + 3 * 8 * 4 + 4 + 4 + 8) + nact * 32 * 2)  # rowval, colptr, slot words written;
+        # adjacency planes written (table), read and re-written (sorted); degree, nnbr, nbrptr; conn read by k_adj_table and k_sym_tile
         peaks = ctx.measure_peaks()
         k_int_ms, k_gather_ms = mk.get("integrate", ph["integrate_ms"]), mk.get("gather", ph["numeric_ms"])
         sym_kernels = {k[4:]: v for k, v in mk.items() if k.startswith("sym:")}

@@ -94,7 +94,8 @@ __global__ void k_expand_compact(const double *__restrict__ Vc, double *__restri
   const int k = (int)(i - eo * EM2), c = k / EM, r = k - c * EM;
   const int li = r / ndn, p = r - li * ndn, lc = c / ndn, q = c - lc * ndn, nd2 = ndn * ndn;
   const int off = (li <= lc) ? nd2 * (lc * (lc + 1) / 2 + li) + q * ndn + p : nd2 * (li * (li + 1) / 2 + lc) + p * ndn + q;
-  Vf[i] = vstride > 0 ? Vc[(int64_t)off * vstride + e] : Vc[e * CS + off];
+  const int blk = off / nd2, ent = off - blk * nd2;  // planes: (blk * vstride + slot) * nd2 + entry
+  Vf[i] = vstride > 0 ? Vc[((int64_t)blk * vstride + e) * nd2 + ent] : Vc[e * CS + off];
 }
 
 // smallest and largest node id used by the active elements: win[0] = max(~node) (so that a zero-initialised slot means "no node"),
@@ -179,12 +180,19 @@ struct DeviceGuard {
 }  // namespace
 
 // full element matrices permuted: out[r] = in[perm[r]]
+// (nne, ndn only matter for the plane form: position k = c * EM + r of the full matrix lives in plane b * nne + a, entry j * ndn + i)
 __global__ void k_permute_records(const double *__restrict__ in, double *__restrict__ out, int64_t nelem, int64_t rec, const int32_t *__restrict__ perm,
-                                  int64_t vstride) {
+                                  int64_t vstride, int nne, int ndn) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nelem * rec) return;
   const int64_t eo = i / rec, k = i - eo * rec;
-  out[i] = vstride > 0 ? in[k * vstride + perm[eo]] : in[(int64_t)perm[eo] * rec + k];
+  if (vstride > 0) {
+    const int EM = nne * ndn, c = (int)(k / EM), r = (int)(k - (int64_t)c * EM);
+    const int b = c / ndn, j = c - b * ndn, a = r / ndn, ii = r - a * ndn;
+    out[i] = in[((int64_t)(b * nne + a) * vstride + perm[eo]) * (ndn * ndn) + j * ndn + ii];
+  } else {
+    out[i] = in[(int64_t)perm[eo] * rec + k];
+  }
 }
 
 int32_t fe_expand_compact(fegpu_ctx *ctx, const double *d_Vc, double *d_Vfull, int64_t nelem, int nne, int ndn, const int32_t *d_perm, int64_t vstride) {
@@ -515,6 +523,7 @@ int32_t fegpu_partition_set(fegpu_mesh *m, const int32_t *node_owner, int32_t my
   cudaFree(m->d_elem_list);
   cudaFree(m->d_rowowned);
   m->d_elem_list = nullptr;
+  m->elem_base = 0;
   m->d_rowowned = nullptr;
   m->partitioned = false;
   m->nactive = m->nelem;
@@ -567,9 +576,21 @@ int32_t fegpu_partition_set(fegpu_mesh *m, const int32_t *node_owner, int32_t my
     ctx->launches++;
   }
   PT(cudaMemcpyAsync(h_win, d_win, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+  int32_t h_ends[2] = {0, -1};
+  if (nact > 0) {
+    PT(cudaMemcpyAsync(&h_ends[0], m->d_elem_list, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PT(cudaMemcpyAsync(&h_ends[1], m->d_elem_list + (nact - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
   PT(cudaStreamSynchronize(st));
 #undef PT
   cleanup();
+  if (nact > 0 && (int64_t)h_ends[1] - h_ends[0] + 1 == nact) {
+    // the active elements are one contiguous range of the internal order (slabs of a mesh with node locality): slot s is element
+    // elem_base + s, no list and no indirection in the kernels
+    cudaFree(m->d_elem_list);
+    m->d_elem_list = nullptr;
+    m->elem_base = h_ends[0];
+  }
   m->nactive = nact;
   m->partitioned = true;
   if (h_win[1] > 0) {
@@ -1028,7 +1049,7 @@ static int32_t run_lumped(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &fa
     return fegpu_fail(ctx, FEGPU_ERR_CUDA, "out of device memory");
   }
   if (nv) {
-    k_emit_rows<<<grid_for(nv, 256), 256, 0, st>>>(mesh->d_conn, mesh->d_elem_list, mesh->nactive, mesh->nne, fa.ndn, mesh->nnodes, dm->d_dof, dI);
+    k_emit_rows<<<grid_for(nv, 256), 256, 0, st>>>(mesh->conn_act(), mesh->d_elem_list, mesh->nactive, mesh->nne, fa.ndn, mesh->nnodes, dm->d_dof, dI);
     k_lump<<<grid_for(mesh->nactive * 32, 256), 256, 0, st>>>(as->d_V, mesh->nactive, EM, nullptr, nullptr, nullptr, as->lump == 2 ? 1 : 0, dD);
     ctx->launches += 2;
   }
@@ -1132,7 +1153,7 @@ int32_t fegpu_linform_dot(fegpu_mesh *mesh, fegpu_dofmap *dm, const double *forc
     if (mesh->partitioned) return fegpu_fail(ctx, FEGPU_ERR_ARG, "row-block partitioning needs an injective dof map and non-degenerate elements");
     int64_t *dI = nullptr;
     CUDA_TRY(ctx, cudaMalloc((void **)&dI, sizeof(int64_t) * std::max<int64_t>(nv, 1)));
-    if (nv) k_emit_rows<<<grid_for(nv, 256), 256, 0, st>>>(mesh->d_conn, mesh->d_elem_list, mesh->nactive, mesh->nne, dm->ndn, mesh->nnodes, dm->d_dof, dI);
+    if (nv) k_emit_rows<<<grid_for(nv, 256), 256, 0, st>>>(mesh->conn_act(), mesh->d_elem_list, mesh->nactive, mesh->nne, dm->ndn, mesh->nnodes, dm->d_dof, dI);
     const int32_t s = vector_from_pairs(as, nv, dI, as->d_V, dm->row_nall);
     cudaStreamSynchronize(st);
     cudaFree(dI);
@@ -1444,7 +1465,8 @@ int32_t fegpu_coo_copy(fegpu_asm *as, fegpu_mesh *mesh, fegpu_dofmap *dm, int64_
     if (as->V_compact) {  // the fast path stored the compact symmetric layout: expand to full matrices on the way
       s = fe_expand_compact(ctx, as->d_V, dfull, mesh->nactive, mesh->nne, dm->ndn, d_perm, as->V_planes ? as->V_stride : 0);
     } else {
-      k_permute_records<<<grid_for(n, 256), 256, 0, st>>>(as->d_V, dfull, mesh->nactive, (int64_t)EM * EM, d_perm, as->V_planes ? as->V_stride : 0);
+      k_permute_records<<<grid_for(n, 256), 256, 0, st>>>(as->d_V, dfull, mesh->nactive, (int64_t)EM * EM, d_perm, as->V_planes ? as->V_stride : 0,
+                                                          mesh->nne, dm->ndn);
       ctx->launches++;
     }
     if (s == FEGPU_OK && cudaMemcpyAsync(V, dfull, sizeof(double) * n, cudaMemcpyDeviceToHost, st) != cudaSuccess) s = FEGPU_ERR_CUDA;

@@ -105,7 +105,7 @@ template <int NNE, int MDIM, int SDIM>
 int32_t launch_dot(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
   fegpu_ctx *ctx = mesh->ctx;
   if (mesh->nactive == 0) return FEGPU_OK;
-  DotParams P{mesh->d_conn, mesh->d_xyz, mesh->nnodes, mesh->d_elem_list, mesh->nactive, mesh->d_tab, mesh->d_w, mesh->npts, d_V,
+  DotParams P{mesh->conn_act(), mesh->d_xyz, mesh->nnodes, mesh->d_elem_list, mesh->nactive, mesh->d_tab, mesh->d_w, mesh->npts, d_V,
               fa.compact ? 1 : 0, fa.planes ? fa.vstride : 0, fa.coef[0], fa.m, fa.otherdim};
   const size_t smem = sizeof(double) * ((size_t)mesh->npts * NNE * (1 + MDIM) + mesh->npts);
   auto kern = k_dot_scalar<NNE, MDIM, SDIM>;

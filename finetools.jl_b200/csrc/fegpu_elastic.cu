@@ -242,7 +242,7 @@ int32_t launch_tiled(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
   constexpr int GRP = NNE * 3 + 10 + 2 * NNE * 3 + 2 * NNE * 19;
   if (mesh->nactive == 0) return FEGPU_OK;
   ElParams P;
-  P.conn = mesh->d_conn; P.xyz = mesh->d_xyz; P.nnodes = mesh->nnodes; P.elem_list = mesh->d_elem_list; P.nactive = mesh->nactive;
+  P.conn = mesh->conn_act(); P.xyz = mesh->d_xyz; P.nnodes = mesh->nnodes; P.elem_list = mesh->d_elem_list; P.nactive = mesh->nactive;
   P.dN = mesh->d_tab + (size_t)mesh->npts * NNE;  // the table holds N [npts][NNE] first
   P.w = mesh->d_w; P.npts = mesh->npts; P.V = d_V; P.compact = fa.compact ? 1 : 0;
   for (int i = 0; i < 36; i++) P.C[i] = fa.coef[i];

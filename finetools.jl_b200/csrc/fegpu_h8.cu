@@ -289,10 +289,15 @@ __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, cons
     const int64_t sbase = slot0 + half * 16;
     const int64_t nvalid = min((int64_t)16, P.nactive - sbase);
     if (nvalid > 0 && P.vstride > 0) {
-      // planes: 16 consecutive slots of one value index per half-warp (128-byte runs); the staged matrices have an odd stride
-      for (int i = threadIdx.x; i < 16 * MSIZE; i += 128) {
-        const int k = i >> 4, el = i & 15;
-        if (el < nvalid) P.V[(int64_t)k * P.vstride + sbase + el] = sm[(size_t)el * MSTRIDE + k];
+      // planes: the 9 entries of a 3x3 block of 16 consecutive slots are one contiguous run of 144 doubles
+      constexpr int NBLK = MSIZE / 9;
+      for (int i = threadIdx.x; i < NBLK * 144; i += 128) {
+        const int blk = i / 144, rem = i - blk * 144, el = rem / 9, e = rem - el * 9;
+        if (el < nvalid) {
+          // full layout: the staged matrix is in emission order k = (b*3 + j) * 24 + a*3 + i; plane b*8 + a, entry j*3 + i
+          const int k = COMPACT ? blk * 9 + e : ((blk >> 3) * 3 + e / 3) * 24 + (blk & 7) * 3 + (e % 3);
+          P.V[((int64_t)blk * P.vstride + sbase + el) * 9 + e] = sm[(size_t)el * MSTRIDE + k];
+        }
       }
     } else if (nvalid > 0) {
       const int nval = (int)(nvalid * MSIZE);  // contiguous slots are contiguous in V
@@ -366,7 +371,7 @@ int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool 
   const bool elast = (fa.form == FORM_ELASTIC);
   if (!diff && !elast) return FEGPU_OK;
   if (mesh->nactive == 0) { *handled = true; return FEGPU_OK; }
-  H8Params P{mesh->d_conn, mesh->d_xyz, mesh->nnodes, mesh->d_elem_list, mesh->nactive, d_V, fa.planes ? fa.vstride : 0, {0}, {0}, {0}};
+  H8Params P{mesh->conn_act(), mesh->d_xyz, mesh->nnodes, mesh->d_elem_list, mesh->nactive, d_V, fa.planes ? fa.vstride : 0, {0}, {0}, {0}};
   // dN part of the host table: [npts][3][8] starting after N [npts][8]
   std::memcpy(P.dN, mesh->h_tab.data() + 8 * 8, sizeof(double) * 8 * 24);
   std::memcpy(P.w, mesh->h_w.data(), sizeof(double) * 8);

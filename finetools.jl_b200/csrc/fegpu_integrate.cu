@@ -360,28 +360,35 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
     } else if (live && SYM && P.compact) {
       // compact upper-block layout (fegpu_internal.h): block (a <= b) at NDN^2 * (b(b+1)/2 + a), column-major inside;
       // element-major records, or planes (value index x vstride + slot) for the thread-per-node numeric kernel
-      constexpr int64_t REC = (int64_t)(NNE * (NNE + 1) / 2 * NDN * NDN);
-      double *Ve = P.vstride > 0 ? P.V + slot : P.V + slot * REC;
-      const int64_t es = P.vstride > 0 ? P.vstride : 1;
+      constexpr int ND2 = NDN * NDN;
+      constexpr int64_t REC = (int64_t)(NNE * (NNE + 1) / 2 * ND2);
 #pragma unroll
       for (int k = 0; k < EPT; k++) {
         if (t + k * TPE < NENT) {
           const int r = er[k], c = ec[k];
           const int a = r / NDN, i = r % NDN, b = c / NDN, j = c % NDN;
-          const int o = NDN * NDN * (b * (b + 1) / 2 + a);
-          Ve[(o + j * NDN + i) * es] = acc[k];
-          if (a == b && i != j) Ve[(o + i * NDN + j) * es] = acc[k];
+          const int blk = b * (b + 1) / 2 + a;
+          double *Vb = P.vstride > 0 ? P.V + ((int64_t)blk * P.vstride + slot) * ND2 : P.V + slot * REC + ND2 * blk;
+          Vb[j * NDN + i] = acc[k];
+          if (a == b && i != j) Vb[i * NDN + j] = acc[k];
         }
       }
     } else if (live) {
-      double *Ve = P.vstride > 0 ? P.V + slot : P.V + slot * (int64_t)(EM * EM);
-      const int64_t es = P.vstride > 0 ? P.vstride : 1;
+      // full matrix, emission order; planes: block (column node b, row node a) = plane b * NNE + a, entry j * NDN + i
+      constexpr int ND2 = NDN * NDN;
+      double *Ve = P.V + slot * (int64_t)(EM * EM);
 #pragma unroll
       for (int k = 0; k < EPT; k++) {
         if (t + k * TPE < NENT) {
           const int r = er[k], c = ec[k];
-          Ve[(c * EM + r) * es] = acc[k];
-          if (SYM && r != c) Ve[(r * EM + c) * es] = acc[k];
+          if (P.vstride > 0) {
+            const int a = r / NDN, i = r % NDN, b = c / NDN, j = c % NDN;
+            P.V[((int64_t)(b * NNE + a) * P.vstride + slot) * ND2 + j * NDN + i] = acc[k];
+            if (SYM && r != c) P.V[((int64_t)(a * NNE + b) * P.vstride + slot) * ND2 + i * NDN + j] = acc[k];
+          } else {
+            Ve[c * EM + r] = acc[k];
+            if (SYM && r != c) Ve[r * EM + c] = acc[k];
+          }
         }
       }
     }
@@ -395,7 +402,7 @@ int32_t launch_generic(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
   constexpr int GPB = (TPE <= 32) ? 128 / TPE : 1;
   constexpr int NAUX = (FORM == FORM_ELASTIC) ? 6 * EM : (FORM == FORM_DIFF_GEN ? MDIM * NNE : (FORM == FORM_CONVECTION ? NNE * SDIM : 1));
   IntegParams P;
-  P.conn = mesh->d_conn; P.xyz = mesh->d_xyz; P.nnodes = mesh->nnodes; P.elem_list = mesh->d_elem_list;
+  P.conn = mesh->conn_act(); P.xyz = mesh->d_xyz; P.nnodes = mesh->nnodes; P.elem_list = mesh->d_elem_list;
   P.nactive = mesh->nactive; P.tab = mesh->d_tab; P.w = mesh->d_w; P.npts = mesh->npts; P.V = d_V;
   P.compact = (fa.compact && fe_form_symmetric(FORM)) ? 1 : 0;
   P.vstride = (fa.planes && FORM != FORM_LINDOT && FORM != FORM_MASSLIKE) ? fa.vstride : 0;

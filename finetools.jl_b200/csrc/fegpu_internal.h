@@ -63,7 +63,9 @@ struct fegpu_mesh {
   // partition (multi-GPU row blocks)
   bool partitioned = false;
   int64_t nactive = 0;              // == nelem when not partitioned
-  int32_t *d_elem_list = nullptr;   // active element ids ascending (nullptr = identity)
+  int32_t *d_elem_list = nullptr;   // active (internal) element ids ascending; nullptr = the contiguous range elem_base .. elem_base + nactive
+  int64_t elem_base = 0;            // (slab partitions of a mesh in internal order activate a contiguous range: no indirection then)
+  const int32_t *conn_act() const { return d_conn + elem_base * nne; }  // connectivity row of active slot 0 when d_elem_list is null
   uint8_t *d_rowowned = nullptr;    // per node, nullptr = all owned
   bool own_contig = false;          // the owned nodes are exactly the range [own_lo, own_hi) (slab / reordered partitions)
   int64_t own_lo = 0, own_hi = 0;

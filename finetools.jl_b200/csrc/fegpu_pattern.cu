@@ -1108,7 +1108,7 @@ int32_t fe_pattern_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *f
   P->nrows = dm->row_nall;
   const int64_t nn = mesh->nnodes;
   const int nne = mesh->nne, ndn = dm->ndn;
-  SymParams S{mesh->d_conn, mesh->d_elem_list, mesh->nactive, nne, nn, mesh->d_rowowned, dm->d_dof, ndn, nullptr, nn, nullptr};
+  SymParams S{mesh->conn_act(), mesh->d_elem_list, mesh->nactive, nne, nn, mesh->d_rowowned, dm->d_dof, ndn, nullptr, nn, nullptr};
   const int64_t nadj = mesh->nactive * nne;
 
   uint16_t *d_arank = nullptr;

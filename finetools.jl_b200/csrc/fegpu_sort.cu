@@ -186,7 +186,7 @@ int32_t fe_emit_ij(fegpu_dofmap *dm, int64_t *d_I, int64_t *d_J, const int32_t *
   const int EM = mesh->nne * dm->ndn;
   const int64_t n = mesh->nactive * EM * EM;
   if (n == 0) return FEGPU_OK;
-  k_emit_ij<<<grid_for(n, 256), 256, 0, dm->ctx->stream>>>(mesh->d_conn, mesh->d_elem_list, mesh->nactive, mesh->nne, dm->ndn, mesh->nnodes,
+  k_emit_ij<<<grid_for(n, 256), 256, 0, dm->ctx->stream>>>(mesh->conn_act(), mesh->d_elem_list, mesh->nactive, mesh->nne, dm->ndn, mesh->nnodes,
                                                           dm->d_dof, d_I, d_J, d_perm);
   dm->ctx->launches++;
   CUDA_TRY(dm->ctx, cudaGetLastError());
@@ -321,11 +321,11 @@ __global__ void k_permute_conn(const int32_t *__restrict__ conn_in, const uint32
   conn_out[t] = conn_in[(int64_t)e * nne + k];
   if (k == 0) orig[i] = (int32_t)e;
 }
-__global__ void k_orig_keys(const int32_t *__restrict__ orig, const int32_t *__restrict__ elem_list, int64_t nactive,
+__global__ void k_orig_keys(const int32_t *__restrict__ orig, const int32_t *__restrict__ elem_list, int64_t elem_base, int64_t nactive,
                             unsigned long long *__restrict__ keys, uint32_t *__restrict__ ids) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nactive) return;
-  const int64_t e = elem_list ? (int64_t)elem_list[s] : s;
+  const int64_t e = elem_list ? (int64_t)elem_list[s] : s + elem_base;
   keys[s] = (unsigned long long)(unsigned)(orig ? orig[e] : (int32_t)e);
   ids[s] = (uint32_t)s;
 }
@@ -405,7 +405,7 @@ int32_t fe_emission_order(fegpu_mesh *mesh, int32_t *d_perm) {
   if (n == 0) return FEGPU_OK;
   SortScratch S(ctx);
   FE_TRY(S.alloc(n));
-  k_orig_keys<<<grid_for(n, 256), 256, 0, st>>>(mesh->d_orig, mesh->d_elem_list, n, S.kA, S.iA);
+  k_orig_keys<<<grid_for(n, 256), 256, 0, st>>>(mesh->d_orig, mesh->d_elem_list, mesh->elem_base, n, S.kA, S.iA);
   ctx->launches++;
   std::vector<int> shifts;
   for (int sh = 0; sh < bits_for(mesh->nelem); sh += 8) shifts.push_back(sh);

@@ -15,7 +15,8 @@
 //   adj  uint32 [MAXDEG][nwp]   adjacent element j of window node i: (slot << 5) | local index, ascending slot
 //   cs   word   [MAXDEG][nwp]   neighbour slot of each of the NNE candidates of (node, adjacent element): one byte each
 //                               (0xff = row not owned by this rank), packed in one 64-bit (H8) / 32-bit (Q4, T3, T4) word
-//   V    double [values per element][vstride]   element matrices as written by the integration kernels (FormArgs::planes)
+//   V    double [blocks per element][vstride][ndn^2]   element matrices as written by the integration kernels (FormArgs::planes):
+//                               the ndn x ndn block of a node pair is one short run, the same block of the next slot follows it
 // Consecutive lanes = consecutive nodes read consecutive words; with elements stored in ascending-smallest-node order
 // (fe_order_elements) the j-th adjacent elements of consecutive nodes are consecutive slots, so the V loads of a warp
 // fall into one or two lines as well.
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(TILE_T, 4)
 #pragma unroll
   for (int j = 0; j < MAXDEG; j++) {
     el[j] = adj[j] >> 5;
-    if (PART != 0 && j < deg) el[j] = (uint32_t)__ldg(elem_list + el[j]);  // partitioned meshes keep a list of active elements
+    if (elem_list && j < deg) el[j] = (uint32_t)__ldg(elem_list + el[j]);  // a partition whose active elements are not one contiguous range
   }
   uint32_t keys[NKEY];
 #pragma unroll
@@ -336,21 +337,31 @@ struct TileGatherParams {
   double *nzval;
 };
 
+// One thread per (node, column component q, row component p): NDN^2 threads per node.  The shared-memory image of a node's
+// columns (nu * NDN^2 doubles) is what bounds the nodes per SM, so splitting a node over NDN^2 threads multiplies the warps in
+// flight (and the loads in flight) for the same footprint: elasticity went from 9 to 27 warps per SM.
 template <int NDN>
 struct GatherShape {
-  static constexpr int T = (NDN == 3) ? 96 : 128;  // threads per CTA: a multiple of NDN and of 32
-  static constexpr int NPB = T / NDN;              // nodes per CTA
+  static constexpr int ND2 = NDN * NDN;
+  static constexpr int NPB = (NDN == 1) ? 128 : 32;  // nodes per CTA
+  static constexpr int T = NPB * ND2;                 // 128, 128, 288 threads
 };
 
+// Position of value (block blk, entry e) of the element in slot `slot`:
+//   element-major records     slot * VPE + ND2 * blk + e
+//   planes (FormArgs::planes) (blk * vstride + slot) * ND2 + e     -- the ND2 entries of a block stay together, consecutive slots
+//                                                                     follow each other: the NDN^2 lanes of a node read one
+//                                                                     contiguous run, consecutive nodes the next one
 template <int NNE, int MAXDEG, int NDN, bool COMPACT, bool PLANES>
 __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileGatherParams<NNE> G) {
   extern __shared__ double acc[];  // the CTA's slice of nzval: columns of its nodes, exactly as in memory
-  constexpr int T = GatherShape<NDN>::T, NPB = GatherShape<NDN>::NPB;
-  constexpr int EM = NNE * NDN, ND2 = NDN * NDN;
+  constexpr int T = GatherShape<NDN>::T, NPB = GatherShape<NDN>::NPB, ND2 = NDN * NDN;
+  constexpr int EM = NNE * NDN;
   constexpr int64_t VPE = COMPACT ? (int64_t)(NNE * (NNE + 1) / 2) * ND2 : (int64_t)EM * EM;
   using CsT = typename CsWord<NNE>::type;
   const int tid = threadIdx.x;
-  const int ln = tid / NDN, q = tid - ln * NDN;
+  const int ln = tid / ND2, qp = tid - ln * ND2;
+  const int q = qp / NDN, p = qp - q * NDN;
   const int64_t i0 = (int64_t)blockIdx.x * NPB;
   const int64_t i = i0 + ln;
   const bool live = i < G.nw;
@@ -368,7 +379,7 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
   }
   __syncthreads();
   if (nu > 0) {
-    double *col = acc + off;
+    double *col = acc + off + p;
     const int ii = (int)i, nwp = (int)G.nwp;  // plane indices fit 32 bits
     const uint32_t *__restrict__ adjp = G.adj;
     const CsT *__restrict__ csp = G.cs;
@@ -391,34 +402,27 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
       if (j < deg) {
         const int64_t slot = ad[j] >> 5;
         const int lc = (int)(ad[j] & 31u);
-        double v[NNE][NDN];
+        double v[NNE];
 #pragma unroll
         for (int li = 0; li < NNE; li++) {
+          int blk, e;
           if (COMPACT) {
             // block (min, max) of the upper block triangle, entry (comp of min, comp of max) at comp_max * NDN + comp_min
             const bool tr = li > lc;
-            const int blk = tr ? li * (li + 1) / 2 + lc : lc * (lc + 1) / 2 + li;
-#pragma unroll
-            for (int p = 0; p < NDN; p++) {
-              const int k = ND2 * blk + (tr ? p * NDN + q : q * NDN + p);
-              v[li][p] = PLANES ? V[(int64_t)k * G.vstride + slot] : V[slot * VPE + k];
-            }
+            blk = tr ? li * (li + 1) / 2 + lc : lc * (lc + 1) / 2 + li;
+            e = tr ? p * NDN + q : q * NDN + p;
           } else {
-#pragma unroll
-            for (int p = 0; p < NDN; p++) {
-              const int k = (lc * NDN + q) * EM + li * NDN + p;  // emission order: column (lc, q), rows (li, p)
-              v[li][p] = PLANES ? V[(int64_t)k * G.vstride + slot] : V[slot * VPE + k];
-            }
+            blk = lc * NNE + li;  // full matrix in emission order: column (lc, q), row (li, p)
+            e = q * NDN + p;
           }
+          if (PLANES) v[li] = V[((int64_t)blk * G.vstride + slot) * ND2 + e];
+          else if (COMPACT) v[li] = V[slot * VPE + ND2 * blk + e];
+          else v[li] = V[slot * VPE + (lc * NDN + q) * EM + li * NDN + p];
         }
 #pragma unroll
         for (int li = 0; li < NNE; li++) {
           const unsigned s = (unsigned)((cs[j] >> (8 * li)) & 0xffu);
-          if (s != 0xffu) {
-            double *dst = col + s * NDN;
-#pragma unroll
-            for (int p = 0; p < NDN; p++) dst[p] += v[li][p];
-          }
+          if (s != 0xffu) col[s * NDN] += v[li];
         }
       }
     }
@@ -529,7 +533,7 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
   PC(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, st));
   PC(cudaMemsetAsync(d_state, 0, sizeof(unsigned long long) * ntiles, st));
   PC(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long) * 4, st));
-  TileParams TP{mesh->d_conn, mesh->d_elem_list, mesh->nactive, nn, lo, nw, nwp, (int32_t)mesh->own_lo, (int32_t)mesh->own_hi, mesh->d_rowowned, dm->d_dof, P->ncols};
+  TileParams TP{mesh->conn_act(), mesh->d_elem_list, mesh->nactive, nn, lo, nw, nwp, (int32_t)mesh->own_lo, (int32_t)mesh->own_hi, mesh->d_rowowned, dm->d_dof, P->ncols};
   k_dof_affine<<<(unsigned)std::min<int64_t>(grid_for(nw, 256), (int64_t)ctx->sm_count * 8), 256, 0, st>>>(dm->d_dof, nn, ndn, lo, nw, d_flags + 1);
   switch (nne) {
     case 8: k_adj_table<8, 8><<<grid_for(nadj, 256), 256, 0, st>>>(TP, P->t_deg, P->t_adj, d_flags); break;
@@ -638,7 +642,7 @@ int32_t fe_tile_gather(fegpu_dofmap *dm, const double *d_V, bool compact, bool p
   fegpu_mesh *mesh = dm->mesh;
   if (!P || !P->tile) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: not a thread-per-node pattern");
   const int nne = mesh->nne, ndn = dm->ndn;
-  const int T = (ndn == 3) ? 96 : 128, npb = T / ndn;
+  const int npb = (ndn == 1) ? 128 : 32;
   const size_t smem = sizeof(double) * (size_t)npb * P->maxnbr * ndn * ndn;
   if (smem > 200 * 1024) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: gather accumulators exceed shared memory");
   if (P->nnz == 0) return FEGPU_OK;
