@@ -10,6 +10,7 @@
 //                   The 24x24 matrix is staged through shared memory and written with coalesced 128-bit stores in the
 //                   reference's emission order.
 // Only GaussRule(3,2) (8 points) takes these paths; other rules use the generic kernel.
+#include <cstdlib>
 #include <cstring>
 
 #include "fegpu_internal.h"
@@ -311,8 +312,10 @@ __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, cons
   }
 }
 
-template <bool COMPACT>
-__global__ void __launch_bounds__(128, 2) k_h8_elastic(const __grid_constant__ H8Params P) {
+// MINB: CTAs per SM the register allocation aims at (2: 244 registers, no spills; 3: 168 registers with ~380 B of spills --
+// FEGPU_ELASTIC_CTAS=3 selects it for A/B measurements)
+template <bool COMPACT, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_h8_elastic(const __grid_constant__ H8Params P) {
   const double *c_dN = P.dN, *c_w = P.w;
   extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, t = threadIdx.x >> 5;  // lane = element in block, t = column pair
@@ -387,11 +390,16 @@ int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool 
     }
   } else {
     // the attribute is per device (a process may hold contexts on several): set it on every launch, like every other kernel here
-    if (fa.compact) CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EL_SMEM_COMPACT));
-    else CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EL_SMEM_FULL));
+    static const bool three = std::getenv("FEGPU_ELASTIC_CTAS") && std::atoi(std::getenv("FEGPU_ELASTIC_CTAS")) == 3;
     unsigned grid = grid_for(mesh->nactive, EL_EPB);
-    if (fa.compact) k_h8_elastic<true><<<grid, 128, EL_SMEM_COMPACT, ctx->stream>>>(P);
-    else k_h8_elastic<false><<<grid, 128, EL_SMEM_FULL, ctx->stream>>>(P);
+#define EL_LAUNCH(C_, M_, SM_)                                                                                             \
+  do {                                                                                                                     \
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic<C_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_));           \
+    k_h8_elastic<C_, M_><<<grid, 128, SM_, ctx->stream>>>(P);                                                              \
+  } while (0)
+    if (fa.compact) { if (three) EL_LAUNCH(true, 3, EL_SMEM_COMPACT); else EL_LAUNCH(true, 2, EL_SMEM_COMPACT); }
+    else { if (three) EL_LAUNCH(false, 3, EL_SMEM_FULL); else EL_LAUNCH(false, 2, EL_SMEM_FULL); }
+#undef EL_LAUNCH
   }
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
