@@ -289,18 +289,7 @@ __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, cons
     block_bar();
     const int64_t sbase = slot0 + half * 16;
     const int64_t nvalid = min((int64_t)16, P.nactive - sbase);
-    if (nvalid > 0 && P.vstride > 0) {
-      // planes: the 9 entries of a 3x3 block of 16 consecutive slots are one contiguous run of 144 doubles
-      constexpr int NBLK = MSIZE / 9;
-      for (int i = threadIdx.x; i < NBLK * 144; i += 128) {
-        const int blk = i / 144, rem = i - blk * 144, el = rem / 9, e = rem - el * 9;
-        if (el < nvalid) {
-          // full layout: the staged matrix is in emission order k = (b*3 + j) * 24 + a*3 + i; plane b*8 + a, entry j*3 + i
-          const int k = COMPACT ? blk * 9 + e : ((blk >> 3) * 3 + e / 3) * 24 + (blk & 7) * 3 + (e % 3);
-          P.V[((int64_t)blk * P.vstride + sbase + el) * 9 + e] = sm[(size_t)el * MSTRIDE + k];
-        }
-      }
-    } else if (nvalid > 0) {
+    if (nvalid > 0) {
       const int nval = (int)(nvalid * MSIZE);  // contiguous slots are contiguous in V
       double *dst = P.V + sbase * MSIZE;
       for (int i = threadIdx.x; i < nval; i += 128) {

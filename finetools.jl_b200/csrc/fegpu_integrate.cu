@@ -477,7 +477,10 @@ bool fe_integrate_supports_compact(const fegpu_mesh *mesh, const FormArgs &fa) {
 // elasticity keeps element-major records) and the Kronecker path of bilform_dot with more than 3 dofs per node.
 bool fe_integrate_supports_planes(const fegpu_mesh *mesh, const FormArgs &fa) {
   if (fa.form == FORM_LINDOT || fa.form == FORM_MASSLIKE) return false;
-  if (fa.form == FORM_DOT && fa.ndn > 3) return false;
+  // Scalar fields only.  For vector fields the NDN^2 lanes of a node read one contiguous ndn x ndn block of an element-major
+  // record anyway, and writing planes cost the elasticity kernel more than it gave the gather (k_h8_elastic 2.56 -> 2.69 ms with
+  // value planes, 3.47 ms with block planes; gather unchanged: profiles/r02_bench_n1_planes_variants.txt).
+  if (fa.ndn != 1) return false;
   const bool rotated = fa.use_rm && (fa.form == FORM_DIFF_GEN || fa.form == FORM_ELASTIC);
   if (fa.form == FORM_ELASTIC && mesh->sdim == 3 && mesh->mdim == 3 && !rotated && !(mesh->etype == FEGPU_H8 && mesh->npts == 8)) {
     static const bool tiled_off = std::getenv("FEGPU_ELASTIC_TILED") && std::atoi(std::getenv("FEGPU_ELASTIC_TILED")) == 0;

@@ -348,17 +348,22 @@ struct GatherShape {
 };
 
 // Position of value (block blk, entry e) of the element in slot `slot`:
-//   element-major records     slot * VPE + ND2 * blk + e
-//   planes (FormArgs::planes) (blk * vstride + slot) * ND2 + e     -- the ND2 entries of a block stay together, consecutive slots
-//                                                                     follow each other: the NDN^2 lanes of a node read one
-//                                                                     contiguous run, consecutive nodes the next one
+//   element-major records     slot * VPE + ND2 * blk + e          (vector fields: the NDN^2 lanes of a node read one 72-byte run)
+//   planes (FormArgs::planes) (blk * vstride + slot) * ND2 + e     (scalar fields: consecutive nodes read consecutive words)
+//
+// Accumulator image in shared memory.  Scalar fields: exactly the CTA's slice of nzval, so the write-out is a flat copy.
+// Vector fields: per node, component-plane major -- entry (q, p, s) at (q * NDN + p) * nu + s -- because in output order
+// (q * nu * NDN + s * NDN + p) the NDN^2 lanes of a node collide on the banks (column stride nu * NDN = 81 = 1 mod 16 for an
+// interior H8 node: 60 % of the shared-memory wavefronts of the first version were conflicts); with nu odd the plane-major
+// image is conflict free, and the write-out maps it back to output order.
 template <int NNE, int MAXDEG, int NDN, bool COMPACT, bool PLANES>
 __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileGatherParams<NNE> G) {
-  extern __shared__ double acc[];  // the CTA's slice of nzval: columns of its nodes, exactly as in memory
+  extern __shared__ double acc[];
   constexpr int T = GatherShape<NDN>::T, NPB = GatherShape<NDN>::NPB, ND2 = NDN * NDN;
   constexpr int EM = NNE * NDN;
   constexpr int64_t VPE = COMPACT ? (int64_t)(NNE * (NNE + 1) / 2) * ND2 : (int64_t)EM * EM;
   using CsT = typename CsWord<NNE>::type;
+  __shared__ int s_nu[NPB + 1];  // vector fields: neighbour counts of the CTA's nodes (their image offsets follow from colptr)
   const int tid = threadIdx.x;
   const int ln = tid / ND2, qp = tid - ln * ND2;
   const int q = qp / NDN, p = qp - q * NDN;
@@ -371,21 +376,24 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
   const int64_t cb0 = G.colptr[dof0 + i0 * NDN] - 1, cbE = G.colptr[dof0 + iend * NDN] - 1;
   const int total = (int)(cbE - cb0);
   for (int idx = tid; idx < total; idx += T) acc[idx] = 0.0;
-  int deg = 0, nu = 0, off = 0;
+  int deg = 0, nu = 0, nbase = 0;
   if (live) {
     nu = G.nnbr[n];
     deg = min(G.deg[i], MAXDEG);
-    off = (int)(G.colptr[dof0 + i * NDN + q] - 1 - cb0);
+    nbase = (int)(G.colptr[dof0 + i * NDN] - 1 - cb0);  // first entry of the node's columns inside the CTA's slice
   }
+  if (NDN > 1 && qp == 0) s_nu[ln] = nu;
   __syncthreads();
   if (nu > 0) {
-    double *col = acc + off + p;
+    // scalar: col[s]; vector: plane (q, p) of the node's image, entry s
+    double *col = acc + nbase + (NDN == 1 ? 0 : qp * nu);
     const int ii = (int)i, nwp = (int)G.nwp;  // plane indices fit 32 bits
     const uint32_t *__restrict__ adjp = G.adj;
     const CsT *__restrict__ csp = G.cs;
     const double *__restrict__ V = G.V;
-    // metadata of every adjacent element first (2 x MAXDEG independent, coalesced loads in flight), then per element: all its
-    // value loads, then the adds.  Rows of other ranks (slot 0xff) are loaded as well and dropped at the add.
+    // metadata of every adjacent element first (2 x MAXDEG independent, coalesced loads in flight), then the values of element
+    // j + 1 are requested before the adds of element j (software pipeline: the loads overlap the shared-memory adds).
+    // Rows of other ranks (slot 0xff) are loaded as well and dropped at the add.
     uint32_t ad[MAXDEG];
     CsT cs[MAXDEG];
 #pragma unroll
@@ -397,38 +405,63 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
         cs[j] = __ldcs(csp + (j * nwp + ii));
       }
     }
+    auto load_vals = [&](int j, double (&v)[NNE]) {
+      const int64_t slot = ad[j] >> 5;
+      const int lc = (int)(ad[j] & 31u);
 #pragma unroll
-    for (int j = 0; j < MAXDEG; j++) {
-      if (j < deg) {
-        const int64_t slot = ad[j] >> 5;
-        const int lc = (int)(ad[j] & 31u);
-        double v[NNE];
-#pragma unroll
-        for (int li = 0; li < NNE; li++) {
-          int blk, e;
-          if (COMPACT) {
-            // block (min, max) of the upper block triangle, entry (comp of min, comp of max) at comp_max * NDN + comp_min
-            const bool tr = li > lc;
-            blk = tr ? li * (li + 1) / 2 + lc : lc * (lc + 1) / 2 + li;
-            e = tr ? p * NDN + q : q * NDN + p;
-          } else {
-            blk = lc * NNE + li;  // full matrix in emission order: column (lc, q), row (li, p)
-            e = q * NDN + p;
-          }
-          if (PLANES) v[li] = V[((int64_t)blk * G.vstride + slot) * ND2 + e];
-          else if (COMPACT) v[li] = V[slot * VPE + ND2 * blk + e];
-          else v[li] = V[slot * VPE + (lc * NDN + q) * EM + li * NDN + p];
+      for (int li = 0; li < NNE; li++) {
+        int blk, e;
+        if (COMPACT) {
+          // block (min, max) of the upper block triangle, entry (comp of min, comp of max) at comp_max * NDN + comp_min
+          const bool tr = li > lc;
+          blk = tr ? li * (li + 1) / 2 + lc : lc * (lc + 1) / 2 + li;
+          e = tr ? p * NDN + q : q * NDN + p;
+        } else {
+          blk = lc * NNE + li;  // full matrix in emission order: column (lc, q), row (li, p)
+          e = q * NDN + p;
         }
-#pragma unroll
-        for (int li = 0; li < NNE; li++) {
-          const unsigned s = (unsigned)((cs[j] >> (8 * li)) & 0xffu);
-          if (s != 0xffu) col[s * NDN] += v[li];
-        }
+        if (PLANES) v[li] = V[((int64_t)blk * G.vstride + slot) * ND2 + e];
+        else if (COMPACT) v[li] = V[slot * VPE + ND2 * blk + e];
+        else v[li] = V[slot * VPE + (lc * NDN + q) * EM + li * NDN + p];
       }
+    };
+    auto add_vals = [&](int j, const double (&v)[NNE]) {
+#pragma unroll
+      for (int li = 0; li < NNE; li++) {
+        const unsigned s = (unsigned)((cs[j] >> (8 * li)) & 0xffu);
+        if (s != 0xffu) col[s] += v[li];
+      }
+    };
+    double va[NNE], vb[NNE];
+    load_vals(0, va);  // deg >= 1 here (nu > 0)
+#pragma unroll
+    for (int j = 0; j < MAXDEG; j += 2) {
+      if (j + 1 < deg) load_vals(j + 1, vb);
+      if (j < deg) add_vals(j, va);
+      if (j + 2 < deg && j + 2 < MAXDEG) load_vals(j + 2, va);
+      if (j + 1 < deg) add_vals(j + 1, vb);
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < total; idx += T) __stcs(G.nzval + cb0 + idx, acc[idx]);
+  if (NDN == 1) {
+    for (int idx = tid; idx < total; idx += T) __stcs(G.nzval + cb0 + idx, acc[idx]);
+  } else {
+    // a warp per node: output position idx = q * nu * NDN + s * NDN + p of the node's segment <- image entry (q * NDN + p) * nu + s
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nloc = (int)(iend - i0);
+    int run = 0;  // image offset of node t = sum of nu * ND2 over the nodes before it
+    for (int t = 0; t < nloc; t++) {
+      const int nu_t = s_nu[t];
+      if (t % (T / 32) == warp && nu_t > 0) {
+        const int per_col = nu_t * NDN, len = per_col * NDN;
+        for (int idx = lane; idx < len; idx += 32) {
+          const int qq = idx / per_col, r = idx - qq * per_col, s = r / NDN, pp = r - s * NDN;
+          __stcs(G.nzval + cb0 + run + idx, acc[run + (qq * NDN + pp) * nu_t + s]);
+        }
+      }
+      run += nu_t * ND2;
+    }
+  }
 }
 
 // Vector assembly on a thread-per-node pattern (cf. k_vec_gather): thread per (window node, component)
@@ -576,11 +609,11 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
   ctx->launches++;
   PC(cudaGetLastError());
   fe_mark(ctx, "sym:k_sym_tile");
-  if (nw < nn) {  // nbrptr stays a complete prefix array for the consumers that walk every node (result transport)
+  if (nw < nn && P->d_nbr) {
+    // nbrptr stays a complete prefix array for the one consumer that walks every node: the result transport of vector fields
+    // (neighbour lists instead of rowval on the link).  Scalar fields never read it (or nnbr) outside the window.
     k_tile_fill_outside<<<grid_for(nn - nw, 256), 256, 0, st>>>(P->d_nbrptr, nn + 1, lo, hi, 0);
     ctx->launches++;
-    if (lo > 0) PC(cudaMemsetAsync(P->d_nnbr, 0, sizeof(int32_t) * lo, st));
-    if (hi < nn) PC(cudaMemsetAsync(P->d_nnbr + hi, 0, sizeof(int32_t) * (nn - hi), st));
   }
   if (nw * ndn < P->ncols) {
     k_tile_fill_colptr<<<grid_for(P->ncols + 1, 256), 256, 0, st>>>(P->d_colptr, P->ncols, dm->d_dof, lo, nw, ndn);
