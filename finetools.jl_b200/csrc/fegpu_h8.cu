@@ -164,6 +164,9 @@ constexpr int EL_EPB = 32;                 // elements per block
 constexpr int EL_GSTRIDE = 25;             // doubles per (element, point): 24 gradients + Jw
 // shared: G [8 pts][25][32 elems] doubles = 51200 B; staging for 16 elements aliases G
 constexpr int EL_SMEM_FULL = 16 * 577 * 8;          // staging is the larger user
+// compact layout: all 32 element matrices are staged at once (32 * 325 * 8 = 83 200 B, two CTAs per SM still fit): one staging
+// pass with every lane active instead of two passes with half of them (FEGPU_ELASTIC_STAGE=2 keeps the two-pass version, 51 200 B)
+constexpr int EL_SMEM_COMPACT1 = 32 * 325 * 8;
 constexpr int EL_SMEM_COMPACT = 8 * EL_GSTRIDE * EL_EPB * 8;  // G is (16 * 325 * 8 = 41600 B of staging fits inside)
 
 __device__ __forceinline__ void db_col(const double *g, double Jw, double DB[18], const double *c_coef) {
@@ -210,8 +213,10 @@ __device__ __forceinline__ void load3(double *d, const double *g, int node) {
   d[2] = g[(node * 3 + 2) * EL_EPB];
 }
 
-template <bool COMPACT>
+// NPASS: staging passes (2: 16 elements at a time, 1: all 32 at once -- needs 32 * MSTRIDE doubles of shared memory)
+template <bool COMPACT, int NPASS>
 __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, const int t, const int64_t slot0, const H8Params &P) {
+  constexpr int EPP = 32 / NPASS;  // elements per staging pass
   constexpr int MSTRIDE = COMPACT ? EL_MSTRIDE_COMPACT : EL_MSTRIDE_FULL;
   constexpr int MSIZE = COMPACT ? 324 : 576;
   const int B1 = t, B2 = 7 - t, NB2 = 8 - t;
@@ -252,9 +257,9 @@ __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, cons
   block_bar();  // everyone is done reading G: the staging buffer may overwrite it
 
   // ---- stage + write: two halves of 16 elements
-  for (int half = 0; half < 2; half++) {
-    if ((lane >> 4) == half) {
-      double *M = sm + (size_t)(lane & 15) * MSTRIDE;
+  for (int half = 0; half < NPASS; half++) {
+    if (NPASS == 1 || (lane >> 4) == half) {
+      double *M = sm + (size_t)(lane & (EPP - 1)) * MSTRIDE;
 #pragma unroll
       for (int s = 0; s < 9; s++) {
         const int a = (s < NB2) ? s : s - NB2;
@@ -287,8 +292,8 @@ __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, cons
       }
     }
     block_bar();
-    const int64_t sbase = slot0 + half * 16;
-    const int64_t nvalid = min((int64_t)16, P.nactive - sbase);
+    const int64_t sbase = slot0 + half * EPP;
+    const int64_t nvalid = min((int64_t)EPP, P.nactive - sbase);
     if (nvalid > 0) {
       const int nval = (int)(nvalid * MSIZE);  // contiguous slots are contiguous in V
       double *dst = P.V + sbase * MSIZE;
@@ -303,7 +308,7 @@ __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, cons
 
 // MINB: CTAs per SM the register allocation aims at (2: 244 registers, no spills; 3: 168 registers with ~380 B of spills --
 // FEGPU_ELASTIC_CTAS=3 selects it for A/B measurements)
-template <bool COMPACT, int MINB>
+template <bool COMPACT, int MINB, int NPASS>
 __global__ void __launch_bounds__(128, MINB) k_h8_elastic(const __grid_constant__ H8Params P) {
   const double *c_dN = P.dN, *c_w = P.w;
   extern __shared__ double sm[];
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(128, MINB) k_h8_elastic(const __grid_constant_
     }
   }
   __syncthreads();
-  elastic_phase_b<COMPACT>(sm, lane, t, slot0, P);
+  elastic_phase_b<COMPACT, NPASS>(sm, lane, t, slot0, P);
 }
 
 }  // namespace
@@ -381,13 +386,20 @@ int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool 
     // the attribute is per device (a process may hold contexts on several): set it on every launch, like every other kernel here
     static const bool three = std::getenv("FEGPU_ELASTIC_CTAS") && std::atoi(std::getenv("FEGPU_ELASTIC_CTAS")) == 3;
     unsigned grid = grid_for(mesh->nactive, EL_EPB);
-#define EL_LAUNCH(C_, M_, SM_)                                                                                             \
+    static const bool two_pass = std::getenv("FEGPU_ELASTIC_STAGE") && std::atoi(std::getenv("FEGPU_ELASTIC_STAGE")) == 2;
+#define EL_LAUNCH(C_, M_, NP_, SM_)                                                                                        \
   do {                                                                                                                     \
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic<C_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_));           \
-    k_h8_elastic<C_, M_><<<grid, 128, SM_, ctx->stream>>>(P);                                                              \
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic<C_, M_, NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_));      \
+    k_h8_elastic<C_, M_, NP_><<<grid, 128, SM_, ctx->stream>>>(P);                                                         \
   } while (0)
-    if (fa.compact) { if (three) EL_LAUNCH(true, 3, EL_SMEM_COMPACT); else EL_LAUNCH(true, 2, EL_SMEM_COMPACT); }
-    else { if (three) EL_LAUNCH(false, 3, EL_SMEM_FULL); else EL_LAUNCH(false, 2, EL_SMEM_FULL); }
+    if (fa.compact) {
+      if (three) EL_LAUNCH(true, 3, 2, EL_SMEM_COMPACT);
+      else if (two_pass) EL_LAUNCH(true, 2, 2, EL_SMEM_COMPACT);
+      else EL_LAUNCH(true, 2, 1, EL_SMEM_COMPACT1);
+    } else {
+      if (three) EL_LAUNCH(false, 3, 2, EL_SMEM_FULL);
+      else EL_LAUNCH(false, 2, 2, EL_SMEM_FULL);
+    }
 #undef EL_LAUNCH
   }
   ctx->launches++;
