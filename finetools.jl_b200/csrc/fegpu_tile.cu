@@ -337,25 +337,21 @@ struct TileGatherParams {
   double *nzval;
 };
 
-// One thread per (node, column component q, row component p): NDN^2 threads per node.  The shared-memory image of a node's
-// columns (nu * NDN^2 doubles) is what bounds the nodes per SM, so splitting a node over NDN^2 threads multiplies the warps in
-// flight (and the loads in flight) for the same footprint: elasticity went from 9 to 27 warps per SM.
+// One thread per (node, column component q).  Measured alternatives for vector fields (config 2, profiles/r02_gather_c2_variants.txt):
+// a thread per (node, q, p) triples the warps in flight but also the per-candidate bookkeeping -- 2.4 G warp instructions, 61 %
+// issue-active, 3.3 ms -- against 3.1 ms for this mapping, whose three adds per candidate share one slot lookup and one address.
 template <int NDN>
 struct GatherShape {
-  static constexpr int ND2 = NDN * NDN;
-  static constexpr int NPB = (NDN == 1) ? 128 : 32;  // nodes per CTA
-  static constexpr int T = NPB * ND2;                 // 128, 128, 288 threads
+  static constexpr int T = (NDN == 3) ? 96 : 128;  // threads per CTA: a multiple of NDN and of 32
+  static constexpr int NPB = T / NDN;              // nodes per CTA
 };
 
 // Position of value (block blk, entry e) of the element in slot `slot`:
-//   element-major records     slot * VPE + ND2 * blk + e          (vector fields: the NDN^2 lanes of a node read one 72-byte run)
+//   element-major records     slot * VPE + ND2 * blk + e          (vector fields: the NDN lanes of a node read one 72-byte block)
 //   planes (FormArgs::planes) (blk * vstride + slot) * ND2 + e     (scalar fields: consecutive nodes read consecutive words)
-//
-// Accumulator image in shared memory.  Scalar fields: exactly the CTA's slice of nzval, so the write-out is a flat copy.
-// Vector fields: per node, component-plane major -- entry (q, p, s) at (q * NDN + p) * nu + s -- because in output order
-// (q * nu * NDN + s * NDN + p) the NDN^2 lanes of a node collide on the banks (column stride nu * NDN = 81 = 1 mod 16 for an
-// interior H8 node: 60 % of the shared-memory wavefronts of the first version were conflicts); with nu odd the plane-major
-// image is conflict free, and the write-out maps it back to output order.
+// The accumulator image in shared memory is exactly the CTA's slice of nzval (column after column, rows in order), so the
+// write-out is a flat copy; lanes = (node, q) pairs hit distinct banks for a given (slot, p) because the column stride nu * NDN
+// is odd for the 27-neighbour interior stencil.
 template <int NNE, int MAXDEG, int NDN, bool COMPACT, bool PLANES>
 __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileGatherParams<NNE> G) {
   extern __shared__ double acc[];
@@ -363,10 +359,8 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
   constexpr int EM = NNE * NDN;
   constexpr int64_t VPE = COMPACT ? (int64_t)(NNE * (NNE + 1) / 2) * ND2 : (int64_t)EM * EM;
   using CsT = typename CsWord<NNE>::type;
-  __shared__ int s_nu[NPB + 1];  // vector fields: neighbour counts of the CTA's nodes (their image offsets follow from colptr)
   const int tid = threadIdx.x;
-  const int ln = tid / ND2, qp = tid - ln * ND2;
-  const int q = qp / NDN, p = qp - q * NDN;
+  const int ln = tid / NDN, q = tid - ln * NDN;
   const int64_t i0 = (int64_t)blockIdx.x * NPB;
   const int64_t i = i0 + ln;
   const bool live = i < G.nw;
@@ -376,17 +370,15 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
   const int64_t cb0 = G.colptr[dof0 + i0 * NDN] - 1, cbE = G.colptr[dof0 + iend * NDN] - 1;
   const int total = (int)(cbE - cb0);
   for (int idx = tid; idx < total; idx += T) acc[idx] = 0.0;
-  int deg = 0, nu = 0, nbase = 0;
+  int deg = 0, nu = 0, off = 0;
   if (live) {
     nu = G.nnbr[n];
     deg = min(G.deg[i], MAXDEG);
-    nbase = (int)(G.colptr[dof0 + i * NDN] - 1 - cb0);  // first entry of the node's columns inside the CTA's slice
+    off = (int)(G.colptr[dof0 + i * NDN + q] - 1 - cb0);
   }
-  if (NDN > 1 && qp == 0) s_nu[ln] = nu;
   __syncthreads();
   if (nu > 0) {
-    // scalar: col[s]; vector: plane (q, p) of the node's image, entry s
-    double *col = acc + nbase + (NDN == 1 ? 0 : qp * nu);
+    double *col = acc + off;
     const int ii = (int)i, nwp = (int)G.nwp;  // plane indices fit 32 bits
     const uint32_t *__restrict__ adjp = G.adj;
     const CsT *__restrict__ csp = G.cs;
@@ -405,34 +397,39 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
         cs[j] = __ldcs(csp + (j * nwp + ii));
       }
     }
-    auto load_vals = [&](int j, double (&v)[NNE]) {
+    auto load_vals = [&](int j, double (&v)[NNE][NDN]) {
       const int64_t slot = ad[j] >> 5;
       const int lc = (int)(ad[j] & 31u);
 #pragma unroll
       for (int li = 0; li < NNE; li++) {
-        int blk, e;
         if (COMPACT) {
           // block (min, max) of the upper block triangle, entry (comp of min, comp of max) at comp_max * NDN + comp_min
           const bool tr = li > lc;
-          blk = tr ? li * (li + 1) / 2 + lc : lc * (lc + 1) / 2 + li;
-          e = tr ? p * NDN + q : q * NDN + p;
+          const int blk = tr ? li * (li + 1) / 2 + lc : lc * (lc + 1) / 2 + li;
+          const double *B = PLANES ? V + ((int64_t)blk * G.vstride + slot) * ND2 : V + slot * VPE + ND2 * blk;
+          const int e0 = tr ? q : q * NDN, es = tr ? NDN : 1;  // row component p: transposed block -> stride NDN
+#pragma unroll
+          for (int p = 0; p < NDN; p++) v[li][p] = B[e0 + p * es];
         } else {
-          blk = lc * NNE + li;  // full matrix in emission order: column (lc, q), row (li, p)
-          e = q * NDN + p;
+          // full matrix in emission order: column (lc, q), rows (li, p); planes: block lc * NNE + li, entry q * NDN + p
+          const double *B = PLANES ? V + ((int64_t)(lc * NNE + li) * G.vstride + slot) * ND2 + q * NDN : V + slot * VPE + (lc * NDN + q) * EM + li * NDN;
+#pragma unroll
+          for (int p = 0; p < NDN; p++) v[li][p] = B[p];
         }
-        if (PLANES) v[li] = V[((int64_t)blk * G.vstride + slot) * ND2 + e];
-        else if (COMPACT) v[li] = V[slot * VPE + ND2 * blk + e];
-        else v[li] = V[slot * VPE + (lc * NDN + q) * EM + li * NDN + p];
       }
     };
-    auto add_vals = [&](int j, const double (&v)[NNE]) {
+    auto add_vals = [&](int j, const double (&v)[NNE][NDN]) {
 #pragma unroll
       for (int li = 0; li < NNE; li++) {
         const unsigned s = (unsigned)((cs[j] >> (8 * li)) & 0xffu);
-        if (s != 0xffu) col[s] += v[li];
+        if (s != 0xffu) {
+          double *dst = col + s * NDN;
+#pragma unroll
+          for (int p = 0; p < NDN; p++) dst[p] += v[li][p];
+        }
       }
     };
-    double va[NNE], vb[NNE];
+    double va[NNE][NDN], vb[NNE][NDN];
     load_vals(0, va);  // deg >= 1 here (nu > 0)
 #pragma unroll
     for (int j = 0; j < MAXDEG; j += 2) {
@@ -443,25 +440,7 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
     }
   }
   __syncthreads();
-  if (NDN == 1) {
-    for (int idx = tid; idx < total; idx += T) __stcs(G.nzval + cb0 + idx, acc[idx]);
-  } else {
-    // a warp per node: output position idx = q * nu * NDN + s * NDN + p of the node's segment <- image entry (q * NDN + p) * nu + s
-    const int lane = tid & 31, warp = tid >> 5;
-    const int nloc = (int)(iend - i0);
-    int run = 0;  // image offset of node t = sum of nu * ND2 over the nodes before it
-    for (int t = 0; t < nloc; t++) {
-      const int nu_t = s_nu[t];
-      if (t % (T / 32) == warp && nu_t > 0) {
-        const int per_col = nu_t * NDN, len = per_col * NDN;
-        for (int idx = lane; idx < len; idx += 32) {
-          const int qq = idx / per_col, r = idx - qq * per_col, s = r / NDN, pp = r - s * NDN;
-          __stcs(G.nzval + cb0 + run + idx, acc[run + (qq * NDN + pp) * nu_t + s]);
-        }
-      }
-      run += nu_t * ND2;
-    }
-  }
+  for (int idx = tid; idx < total; idx += T) __stcs(G.nzval + cb0 + idx, acc[idx]);
 }
 
 // Vector assembly on a thread-per-node pattern (cf. k_vec_gather): thread per (window node, component)
@@ -675,7 +654,7 @@ int32_t fe_tile_gather(fegpu_dofmap *dm, const double *d_V, bool compact, bool p
   fegpu_mesh *mesh = dm->mesh;
   if (!P || !P->tile) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: not a thread-per-node pattern");
   const int nne = mesh->nne, ndn = dm->ndn;
-  const int npb = (ndn == 1) ? 128 : 32;
+  const int npb = ((ndn == 3) ? 96 : 128) / ndn;
   const size_t smem = sizeof(double) * (size_t)npb * P->maxnbr * ndn * ndn;
   if (smem > 200 * 1024) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: gather accumulators exceed shared memory");
   if (P->nnz == 0) return FEGPU_OK;
