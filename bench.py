@@ -442,11 +442,74 @@ def run_gpu(args):
         W.release()
         return res
 
+    def measure_c5(steps):
+        """BASELINE configs[4] (mixed surface / volume run, as it states it for 8 GPUs): H20 96^3 bilform_lin_elastic with GaussRule(3,3)
+        (the warp-per-element register-tiled kernel) plus the boundary mass bilform_dot on the Q4 / T3 skins of the 96^3 blocks,
+        every FESet split into `world` node-owned row blocks.  Device-resident fresh and cached steps, max over ranks."""
+        out = {}
+        nb = 96
+        cases = []
+        fens, fes = fe.H20block(1.0, 1.0, 1.0, nb, nb, nb)
+        cases.append(("H20 96^3 lin_elastic GaussRule(3,3)", fens, fes, 3, fe.GaussRule(3, 3), "elastic", isotropic_C(), 3))
+        vf, vol = fe.H8block(1.0, 1.0, 1.0, nb, nb, nb)
+        cases.append(("Q4 skin of H8 96^3, bilform_dot m=2, GaussRule(2,2)", vf, fe.meshboundary(vol), 1, fe.GaussRule(2, 2), "dot", np.array([[1.0]]), 2))
+        vf, vol = fe.T4block(1.0, 1.0, 1.0, nb, nb, nb)
+        cases.append(("T3 skin of T4 96^3, bilform_dot m=2, TriRule(3)", vf, fe.meshboundary(vol), 1, fe.TriRule(3), "dot", np.array([[1.0]]), 2))
+        for name, fens, fes, ndn, rule, form, coef, m in cases:
+            u = fe.NodalField(np.zeros((fens.count(), ndn)))
+            fe.numberdofs(u)
+            femm = fe.FEMMBase(fe.IntegDomain(fes, rule))
+            geom = fe.NodalField(fens.xyz)
+            owner = fe.slab_owner(fens.count(), world) if world > 1 else None
+            a = fe.SysmatAssemblerSparseGPU(0.0, ctx=ctx)
+            a.setnomatrixresult(True)
+            cache = fe.DataCache(coef)
+            if form == "elastic":
+                call = lambda: fe.bilform_lin_elastic(femm, a, geom, u, fe.DeforModelRed3D, cache, raw=True, node_owner=owner, my_rank=rank)
+            else:
+                call = lambda: fe.bilform_dot(femm, a, geom, u, cache, m=m, raw=True, node_owner=owner, my_rank=rank)
+            call()
+            dmesh = ctx.device_mesh(fes)
+            dof = dmesh.dofmap(u)
+            from finetools_jl_b200 import _lib as L
+            cf = np.asfortranarray(coef)
+
+            def dev(fresh):
+                if fresh:
+                    L.check(L.lib().fegpu_pattern_invalidate(dof), ctx.handle)
+                if form == "elastic":
+                    L.check(L.lib().fegpu_bilform_lin_elastic(dmesh.handle, dof, L.fptr(cf), a.handle), ctx.handle)
+                else:
+                    L.check(L.lib().fegpu_bilform_dot(dmesh.handle, dof, L.fptr(cf), int(m), 1.0, a.handle), ctx.handle)
+
+            ctx.set_async(True)
+            for _ in range(3):
+                dev(True)
+            ms_f = timed(lambda: dev(True), steps) / steps
+            dev(False)
+            ms_c = timed(lambda: dev(False), steps) / steps
+            ctx.set_async(False)
+            ctx.set_overlap(False)
+            dev(True)
+            ctx.synchronize()
+            ph = a.timings()
+            ctx.set_overlap(True)
+            nnz = allsum_int(a.sizes()[2])
+            out[name] = {"elements": fes.count(), "nnz": nnz, "fresh_ms": ms_f, "cached_ms": ms_c, "fresh_elements_per_s": fes.count() / (ms_f * 1e-3),
+                         "cached_elements_per_s": fes.count() / (ms_c * 1e-3), "phases_ms_rank0": ph}
+            a = None
+            ctx.release_meshes()
+            ctx.release_cache()
+        return out
+
     sampler = ClockSampler(local_rank)
     r4 = measure("c4", args.steps, args.warmup, sampler)
     r2 = None
     if not args.no_secondary:
         r2 = measure("c2", max(3, min(args.steps, 10)), 3)
+    r5 = None
+    if args.config5 or (world == 8 and not args.no_secondary):
+        r5 = measure_c5(max(3, min(args.steps, 5)))
 
     if rank != 0:
         if dist is not None:
@@ -508,6 +571,8 @@ def run_gpu(args):
     if r2 is not None:
         line["config2"] = {k: r2[k] for k in ("workload", "value", "ms_per_step", "phases_ms", "marks_ms", "cached", "e2e", "kernels", "launches",
                                               "nnz_per_s_csc_construction")}
+    if r5 is not None:
+        line["config5"] = {"workload": "BASELINE configs[4]: H20 96^3 volume stiffness + Q4 / T3 surface mass, %d node-owned row blocks" % world, "parts": r5}
     if cpu is None:
         del line["cpu_baseline"]
     _emit(line)
@@ -524,7 +589,8 @@ def main():
     ap.add_argument("--ref-threads", type=int, default=0, help="reference arm: threads for the element loop (0 = all cores)")
     ap.add_argument("--ref-edge", type=int, default=80, help="reference arm: block edge of the bounded sample")
     ap.add_argument("--cpu-edge", type=int, default=128, help="cpu_baseline leg: block edge of the bounded serial sample")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the config-2 block")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-2 block (and config 5 at 8 GPUs)")
+    ap.add_argument("--config5", action="store_true", help="add the config-5 block (mixed surface / volume run) at any N; it is on by default at 8 GPUs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
