@@ -460,7 +460,11 @@ def run_gpu(args):
             fe.numberdofs(u)
             femm = fe.FEMMBase(fe.IntegDomain(fes, rule))
             geom = fe.NodalField(fens.xyz)
-            owner = fe.slab_owner(fens.count(), world) if world > 1 else None
+            # H20 / skin node numbers have no slab structure (mid-edge nodes are numbered after all corner nodes): partition the
+            # nodes geometrically, as the reference does (pointpartitioning: recursive inertial bisection, MeshModificationModule.jl:1029)
+            owner = None
+            if world > 1:
+                owner = (fe.pointpartitioning(fens.xyz, world) - 1).astype(np.int32) if (world & (world - 1)) == 0 else fe.slab_owner(fens.count(), world)
             a = fe.SysmatAssemblerSparseGPU(0.0, ctx=ctx)
             a.setnomatrixresult(True)
             cache = fe.DataCache(coef)

@@ -46,7 +46,8 @@
 
 namespace {
 
-constexpr int TILE_T = 128;  // nodes (= threads) per tile of k_sym_tile
+// nodes (= threads) per tile of k_sym_tile: a template parameter TT.  64 (8 CTAs per SM) halves the warps that wait at each of the
+// CTA's three barriers and during the look-back compared with 128 (4 CTAs per SM); FEGPU_TILE_T selects (A/B knob)
 constexpr int TILE_KB = 6;   // low bits of a candidate key: k = a * nne + li < 64
 constexpr uint32_t TILE_DROPPED = 0xffffffffu >> TILE_KB;  // node field of a candidate whose row this rank does not own / padding
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_VMASK = (1ull << 62) - 1ull;
@@ -133,8 +134,8 @@ __device__ __forceinline__ void load_conn_row(const int32_t *__restrict__ row, i
 }
 
 // out[0] = total neighbour entries of the window, out[1] = largest neighbour count, out[2] = tile ticket
-template <int NNE, int MAXDEG, int NDN, int PART>
-__global__ void __launch_bounds__(TILE_T, 4)
+template <int NNE, int MAXDEG, int NDN, int PART, int TILE_T>
+__global__ void __launch_bounds__(TILE_T, 512 / TILE_T)
     k_sym_tile(const TileParams P, const int32_t *__restrict__ deg_in, uint32_t *__restrict__ adj_planes,
                typename CsWord<NNE>::type *__restrict__ cs_planes, int32_t *__restrict__ nnbr, int64_t *__restrict__ nbrptr,
                int64_t *__restrict__ colptr, int64_t *__restrict__ rowval, int32_t *__restrict__ nbr_out, unsigned long long *tile_state,
@@ -525,7 +526,8 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
   P->alloc_stream = st;
   P->ncols = dm->col_nall;
   P->nrows = dm->row_nall;
-  const int64_t ntiles = (nw + TILE_T - 1) / TILE_T;
+  static const int tile_t = (std::getenv("FEGPU_TILE_T") && std::atoi(std::getenv("FEGPU_TILE_T")) == 128) ? 128 : 64;
+  const int64_t ntiles = (nw + tile_t - 1) / tile_t;
   const size_t nb_cap = (size_t)nadj * nne;  // upper bound of the neighbour entries: every candidate unique
   const size_t cs_bytes = (nne == 8 ? sizeof(unsigned long long) : sizeof(uint32_t)) * (size_t)MD * nwp;
   PT(talloc(ctx, &P->t_deg, (size_t)nw));
@@ -558,12 +560,17 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
   // integrates again in the layout the general path needs
   if (fork) PT((*fork)(true));
   const int part = !mesh->d_rowowned ? 0 : (mesh->own_contig ? 1 : 2);
-  const size_t smem = sizeof(uint32_t) * (size_t)TILE_T * (nne * MD) + (size_t)TILE_T * (nne * MD + 4);
-#define SYM_LAUNCH(NNE_, MD_, NDN_, PART_)                                                                                          \
+  const size_t smem = sizeof(uint32_t) * (size_t)tile_t * (nne * MD) + (size_t)tile_t * (nne * MD + 4);
+#define SYM_LAUNCH_T(NNE_, MD_, NDN_, PART_, TT_)                                                                                   \
   do {                                                                                                                              \
-    PC(cudaFuncSetAttribute(k_sym_tile<NNE_, MD_, NDN_, PART_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    k_sym_tile<NNE_, MD_, NDN_, PART_><<<(unsigned)ntiles, TILE_T, smem, st>>>(TP, P->t_deg, P->t_adj,                              \
+    PC(cudaFuncSetAttribute(k_sym_tile<NNE_, MD_, NDN_, PART_, TT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    k_sym_tile<NNE_, MD_, NDN_, PART_, TT_><<<(unsigned)ntiles, TT_, smem, st>>>(TP, P->t_deg, P->t_adj,                            \
         reinterpret_cast<CsWord<NNE_>::type *>(P->t_cs), P->d_nnbr, P->d_nbrptr, P->d_colptr, P->d_rowval, P->d_nbr, d_state, d_out); \
+  } while (0)
+#define SYM_LAUNCH(NNE_, MD_, NDN_, PART_)                        \
+  do {                                                            \
+    if (tile_t == 128) SYM_LAUNCH_T(NNE_, MD_, NDN_, PART_, 128); \
+    else SYM_LAUNCH_T(NNE_, MD_, NDN_, PART_, 64);                \
   } while (0)
 #define SYM_PART(NNE_, MD_, NDN_)                        \
   do {                                                   \
@@ -585,6 +592,7 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
 #undef SYM_NDN
 #undef SYM_PART
 #undef SYM_LAUNCH
+#undef SYM_LAUNCH_T
   ctx->launches++;
   PC(cudaGetLastError());
   fe_mark(ctx, "sym:k_sym_tile");
