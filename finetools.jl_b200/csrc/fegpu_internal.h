@@ -71,6 +71,7 @@ struct fegpu_mesh {
   int64_t own_lo = 0, own_hi = 0;
   int64_t win_lo = 0, win_hi = 0;   // node window [lo, hi) that contains every node of an active element ([0, nnodes) when not partitioned)
   uint64_t topo_version = 1;        // bumped when the active set / ownership changes
+  uint64_t adj_collide_version = 0; // topo_version for which the atomic-free adjacency placement lost an entry (fegpu_tile.cu)
   bool degenerate = false;          // some element lists a node twice -> generic sort path
   double bbox_lo[3] = {0, 0, 0}, bbox_hi[3] = {0, 0, 0};  // of the coordinates at upload (node visiting order of the gather)
 };

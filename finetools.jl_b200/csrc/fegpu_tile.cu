@@ -46,8 +46,8 @@
 
 namespace {
 
-// nodes (= threads) per tile of k_sym_tile: a template parameter TT.  64 (8 CTAs per SM) halves the warps that wait at each of the
-// CTA's three barriers and during the look-back compared with 128 (4 CTAs per SM); FEGPU_TILE_T selects (A/B knob)
+// nodes (= threads) per tile of k_sym_tile: a template parameter.  128 (4 CTAs per SM) is the measured default; 64 (8 CTAs per SM,
+// half the warps waiting at each barrier and during the look-back) was slower: 3.34 vs 3.11 ms on config 4 (FEGPU_TILE_T=64, A/B knob)
 constexpr int TILE_KB = 6;   // low bits of a candidate key: k = a * nne + li < 64
 constexpr uint32_t TILE_DROPPED = 0xffffffffu >> TILE_KB;  // node field of a candidate whose row this rank does not own / padding
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_VMASK = (1ull << 62) - 1ull;
@@ -99,6 +99,26 @@ __global__ void __launch_bounds__(256) k_adj_table(const TileParams P, int32_t *
     if (c[k] == n) flags[0] = 1;
 }
 
+// The same table WITHOUT atomics, optimistically: position = the node's local index in the element.  Around a node of a mesh
+// with regular topology (block / swept / mapped meshes) every element sees the node at a different local index, so the plain
+// stores never collide; on any other mesh two elements may claim one position and the later store wins.  k_sym_tile counts the
+// entries it finds, the host compares the total with nactive * nne after the build's round trip: a lost entry shows there, the
+// mesh is remembered as colliding and the build is redone with k_adj_table.  The planes are pre-filled with the EMPTY marker.
+template <int NNE, int MAXDEG>
+__global__ void __launch_bounds__(256) k_adj_place(const TileParams P, uint32_t *__restrict__ tab, int *flags) {
+  static_assert(NNE <= MAXDEG, "one plane per local index");
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.nactive * NNE) return;
+  const int64_t slot = i / NNE;
+  const int lc = (int)(i - slot * NNE);
+  const int64_t e = P.elem_list ? (int64_t)P.elem_list[slot] : slot;
+  const int32_t *c = P.conn + e * NNE;
+  const int n = c[lc];
+  tab[(int64_t)lc * P.nwp + (n - P.lo)] = ((uint32_t)slot << 5) | (uint32_t)lc;
+  for (int k = 0; k < lc; k++)
+    if (c[k] == n) flags[0] = 1;
+}
+
 // prefix arrays outside the window: `before` ahead of it, the window's last value behind it
 __global__ void k_tile_fill_outside(int64_t *__restrict__ a, int64_t len, int64_t lo, int64_t hi, int64_t before) {
   const int64_t nout = len - (hi - lo + 1);
@@ -133,10 +153,11 @@ __device__ __forceinline__ void load_conn_row(const int32_t *__restrict__ row, i
   }
 }
 
-// out[0] = total neighbour entries of the window, out[1] = largest neighbour count, out[2] = tile ticket
+// out[0] = total neighbour entries of the window, out[1] = largest neighbour count, out[2] = tile ticket, out[3] = adjacency
+// entries found (= nactive * nne unless the optimistic placement lost one)
 template <int NNE, int MAXDEG, int NDN, int PART, int TILE_T>
 __global__ void __launch_bounds__(TILE_T, 512 / TILE_T)
-    k_sym_tile(const TileParams P, const int32_t *__restrict__ deg_in, uint32_t *__restrict__ adj_planes,
+    k_sym_tile(const TileParams P, int32_t *__restrict__ deg_out, uint32_t *__restrict__ adj_planes,
                typename CsWord<NNE>::type *__restrict__ cs_planes, int32_t *__restrict__ nnbr, int64_t *__restrict__ nbrptr,
                int64_t *__restrict__ colptr, int64_t *__restrict__ rowval, int32_t *__restrict__ nbr_out, unsigned long long *tile_state,
                unsigned long long *out) {
@@ -158,14 +179,18 @@ __global__ void __launch_bounds__(TILE_T, 512 / TILE_T)
   const int64_t i = (int64_t)tile * TILE_T + tid;  // window-relative node index
   const bool live = i < P.nw;
   const int64_t n = P.lo + i;
-  const int deg = live ? min(deg_in[i], MAXDEG) : 0;
   // plane indices fit 32 bits (MAXDEG * nwp <= 16 * 2^26): one integer multiply-add per access, no 64-bit address registers
   const int ii = (int)i, nwp = (int)P.nwp;
-  // ---- adjacency column: sort by element slot (the order of the duplicate sum), write it back in place
+  // ---- adjacency column (EMPTY = all ones where no element sits): sort by element slot (the order of the duplicate sum; EMPTY
+  // entries go last), count, write it back in place
   uint32_t adj[MAXDEG];
 #pragma unroll
-  for (int j = 0; j < MAXDEG; j++) adj[j] = (j < deg) ? adj_planes[j * nwp + ii] : ~0u;
+  for (int j = 0; j < MAXDEG; j++) adj[j] = live ? adj_planes[j * nwp + ii] : ~0u;
   fesort::sort<MAXDEG>(adj);
+  int deg = 0;
+#pragma unroll
+  for (int j = 0; j < MAXDEG; j++) deg += (adj[j] != ~0u) ? 1 : 0;
+  if (live) deg_out[i] = deg;
 #pragma unroll
   for (int j = 0; j < MAXDEG; j++)
     if (j < deg) adj_planes[j * nwp + ii] = adj[j];
@@ -256,10 +281,14 @@ __global__ void __launch_bounds__(TILE_T, 512 / TILE_T)
   }
   if (live) nnbr[n] = nu;
   {
-    int mx = nu;
+    int mx = nu, dsum = deg;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    for (int d = 16; d > 0; d >>= 1) {
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, d);
+    }
     if (lane == 0 && mx > 0) atomicMax(out + 1, (unsigned long long)mx);
+    if (lane == 0 && dsum > 0) atomicAdd(out + 3, (unsigned long long)dsum);
   }
   // ---- decoupled look-back (warp 0): sum the aggregates of the preceding tiles down to the first published prefix
   if (warp == 0) {
@@ -526,7 +555,7 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
   P->alloc_stream = st;
   P->ncols = dm->col_nall;
   P->nrows = dm->row_nall;
-  static const int tile_t = (std::getenv("FEGPU_TILE_T") && std::atoi(std::getenv("FEGPU_TILE_T")) == 128) ? 128 : 64;
+  static const int tile_t = (std::getenv("FEGPU_TILE_T") && std::atoi(std::getenv("FEGPU_TILE_T")) == 64) ? 64 : 128;
   const int64_t ntiles = (nw + tile_t - 1) / tile_t;
   const size_t nb_cap = (size_t)nadj * nne;  // upper bound of the neighbour entries: every candidate unique
   const size_t cs_bytes = (nne == 8 ? sizeof(unsigned long long) : sizeof(uint32_t)) * (size_t)MD * nwp;
@@ -543,19 +572,31 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
   if (ndn >= 2) PT(talloc(ctx, &P->d_nbr, nb_cap));
   PT(talloc(ctx, &d_state, (size_t)ntiles));
   PT(talloc(ctx, &d_out, 4));
-  PC(cudaMemsetAsync(P->t_deg, 0, sizeof(int32_t) * nw, st));
+  // adjacency table: without atomics when the mesh has not shown local-index collisions (see k_adj_place); the planes start EMPTY
+  static const bool place_off = std::getenv("FEGPU_ADJ_PLACE") && std::atoi(std::getenv("FEGPU_ADJ_PLACE")) == 0;  // A/B knob
+  // (triangles: six elements around an interior node and three local indices -- they always collide, so they start with the atomics)
+  const bool optimistic = !place_off && nne >= 4 && nne <= MD && mesh->adj_collide_version != mesh->topo_version;
+  PC(cudaMemsetAsync(P->t_adj, 0xff, sizeof(uint32_t) * (size_t)MD * nwp, st));
+  if (!optimistic) PC(cudaMemsetAsync(P->t_deg, 0, sizeof(int32_t) * nw, st));
   PC(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, st));
   PC(cudaMemsetAsync(d_state, 0, sizeof(unsigned long long) * ntiles, st));
   PC(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long) * 4, st));
   TileParams TP{mesh->conn_act(), mesh->d_elem_list, mesh->nactive, nn, lo, nw, nwp, (int32_t)mesh->own_lo, (int32_t)mesh->own_hi, mesh->d_rowowned, dm->d_dof, P->ncols};
   k_dof_affine<<<(unsigned)std::min<int64_t>(grid_for(nw, 256), (int64_t)ctx->sm_count * 8), 256, 0, st>>>(dm->d_dof, nn, ndn, lo, nw, d_flags + 1);
-  switch (nne) {
-    case 8: k_adj_table<8, 8><<<grid_for(nadj, 256), 256, 0, st>>>(TP, P->t_deg, P->t_adj, d_flags); break;
-    case 4: k_adj_table<4, 16><<<grid_for(nadj, 256), 256, 0, st>>>(TP, P->t_deg, P->t_adj, d_flags); break;
-    default: k_adj_table<3, 16><<<grid_for(nadj, 256), 256, 0, st>>>(TP, P->t_deg, P->t_adj, d_flags); break;
+  if (optimistic) {
+    switch (nne) {
+      case 8: k_adj_place<8, 8><<<grid_for(nadj, 256), 256, 0, st>>>(TP, P->t_adj, d_flags); break;
+      default: k_adj_place<4, 16><<<grid_for(nadj, 256), 256, 0, st>>>(TP, P->t_adj, d_flags); break;
+    }
+  } else {
+    switch (nne) {
+      case 8: k_adj_table<8, 8><<<grid_for(nadj, 256), 256, 0, st>>>(TP, P->t_deg, P->t_adj, d_flags); break;
+      case 4: k_adj_table<4, 16><<<grid_for(nadj, 256), 256, 0, st>>>(TP, P->t_deg, P->t_adj, d_flags); break;
+      default: k_adj_table<3, 16><<<grid_for(nadj, 256), 256, 0, st>>>(TP, P->t_deg, P->t_adj, d_flags); break;
+    }
   }
   ctx->launches += 2;
-  fe_mark(ctx, "sym:k_adj_table");
+  fe_mark(ctx, optimistic ? "sym:k_adj_place" : "sym:k_adj_table");
   // optimistic: the element integration may start now (plane layout); should a precondition turn out violated, the caller
   // integrates again in the layout the general path needs
   if (fork) PT((*fork)(true));
@@ -619,6 +660,14 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
     drop_pattern();
     *taken = true;
     return FEGPU_OK;
+  }
+  if (optimistic && !h_flags[1] && (int64_t)h_out[3] != nadj) {
+    // two elements saw a node at the same local index: an adjacency entry was overwritten.  Remember it for this mesh and
+    // build again with the atomic table (the integration that is already queued is not repeated: same layout).
+    mesh->adj_collide_version = mesh->topo_version;
+    cleanup();
+    drop_pattern();
+    return fe_tile_build(dm, fork, taken);
   }
   if (h_flags[1] || h_flags[2]) {
     dm->tile_failed_version = mesh->topo_version;

@@ -180,6 +180,41 @@ def test_dot_more_than_three_dofs(fe, orc, gpu_ctx, et, ndn):
     assert_parity(ref, got)
 
 
+def test_adjacency_placement_collisions_are_caught(fe, orc, gpu_ctx):
+    """The adjacency table is first filled without atomics, an element's entry going to the plane of the node's LOCAL index; that is
+    collision free only when the elements around a node see it at different local indices.  Rotating the connectivity of random
+    elements about their axis (a valid H8 renumbering: same geometry, positive Jacobian) makes neighbours claim the same plane: the
+    build must notice (entry count) and redo the table with atomics.  Fresh, cached, and as a rank of a partition."""
+    rng = np.random.default_rng(11)
+    fens, fes = fe.H8block(1.0, 2.0, 3.0, 9, 8, 7)
+    _distort(fens, 0.04)
+    conn = fes.conn.copy()
+    rot = np.array([1, 2, 3, 0, 5, 6, 7, 4])
+    for e in rng.choice(conn.shape[0], size=conn.shape[0] // 3, replace=False):
+        for _ in range(int(rng.integers(1, 4))):
+            conn[e] = conn[e][rot]
+    fes2 = type(fes)(np.ascontiguousarray(conn))
+    rule = fe.GaussRule(3, 2)
+    for ndn, form, coef in ((1, "diffusion", KAPPA3), (3, "elastic", isotropic_C())):
+        u = make_field(fe, fens, ndn)
+        ref, (I, J, V) = oracle_csc(orc, form, "H8", fes2, fens, u, rule, coef)
+        got, a = gpu_csc(fe, form, fes2, fens, u, rule, coef)
+        assert _path(fe, gpu_ctx, fes2, u) == 2
+        assert_parity(ref, got)
+        a.invalidate_patterns()
+        got, _ = gpu_csc(fe, form, fes2, fens, u, rule, coef, assembler=a)   # the collision is remembered: straight to the atomics
+        assert_parity(ref, got)
+        owner = fe.slab_owner(fens.count(), 2)
+        n = u.nalldofs()
+        owned = np.zeros(n + 1, bool)
+        owned[u.dofnums[owner == 1].reshape(-1)] = True
+        blk = orc.sparse(I[owned[I]], J[owned[I]], V[owned[I]], n, n)
+        g, _ = gpu_csc(fe, form, fes2, fens, u, rule, coef, assembler=a, node_owner=owner, my_rank=1)
+        np.testing.assert_array_equal(g[0], blk[0])
+        np.testing.assert_array_equal(g[1], blk[1])
+        assert np.abs(g[2] - blk[2]).max() <= 1e-12 * np.abs(ref[2]).max()
+
+
 def test_general_path_still_taken_when_preconditions_fail(fe, orc, gpu_ctx):
     """Free-first / fixed-last numbering (not affine) and a permuted dof map fall back to the group kernels -- same arrays."""
     fens, fes = fe.H8block(1.0, 2.0, 3.0, 6, 5, 7)
