@@ -22,8 +22,9 @@
 // fall into one or two lines as well.
 //
 // Three kernels per fresh assembly:
-//   k_adj_table   one pass over the connectivity: count the elements at every node (atomicAdd, whose return value is the
-//                 position) and drop (slot << 5 | local index) into plane `position` of the node's column.
+//   k_adj_place   one pass over the connectivity: drop (slot << 5 | local index) into plane `local index` of the node's column,
+//                 no atomics (optimistic: verified by the entry count, see the kernel).  k_adj_table is the version with an
+//                 atomicAdd per (element, node) whose return value is the position; triangles and colliding meshes use it.
 //   k_sym_tile    per node: sort the adjacency column (ascending slot = the order of the duplicate sum), load the element
 //                 rows, sort the candidate keys (node << 6 | k), count the unique neighbours.  Per CTA: block scan +
 //                 decoupled look-back over the tiles (single pass: the global prefix of the neighbour counts IS nbrptr and,
