@@ -779,7 +779,12 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
       cudaStream_t sym = ov ? ctx->stream2 : st;
       // called from inside the build (which runs on `sym`) as soon as it knows which structured path it takes; a second call
       // with another layout (the thread-per-node attempt failed its preconditions) integrates again
-      std::function<int32_t(bool)> fork = [&](bool tile) -> int32_t { return integrate(can_compact, tile && can_planes); };
+      std::function<int32_t(bool)> fork = [&](bool tile) -> int32_t {
+        fa2.cosched = tile;
+        const int32_t r = integrate(can_compact, tile && can_planes);
+        fa2.cosched = false;
+        return r;
+      };
       if (ov) {  // the symbolic phase starts after everything queued on the caller's stream so far
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
         CUDA_TRY(ctx, cudaStreamWaitEvent(sym, ctx->ev_fork, 0));

@@ -199,6 +199,8 @@ __device__ __forceinline__ void block_acc(double *k9, const double *ga, const do
 // distinct 8-byte bank pairs: conflict-free staging stores.
 constexpr int EL_MSTRIDE_FULL = 577;      // 576 values, emission order
 constexpr int EL_MSTRIDE_COMPACT = 325;   // 36 upper 3x3 blocks: block (a <= b) at 9*(b(b+1)/2 + a), column-major inside
+constexpr int EL_MSTRIDE_BULK = 326;      // the same, 16-byte aligned records for the bulk copy engine
+constexpr int EL_SMEM_BULK = 32 * EL_MSTRIDE_BULK * 8;
 
 // Phase B + staging for the warp owning column nodes B1 = t and B2 = 7 - t.  All warps run the SAME code (t is a
 // warp-uniform runtime value): slots 0..4 always belong to column B2, slot 8 always to B1, slots 5..7 to B2 iff
@@ -213,11 +215,25 @@ __device__ __forceinline__ void load3(double *d, const double *g, int node) {
   d[2] = g[(node * 3 + 2) * EL_EPB];
 }
 
+// Bulk asynchronous copy shared -> global (the TMA engine's non-tensor form, SASS UBLKCP): the staged element matrices leave
+// the SM without a load / store loop of the CTA's own warps, which go on with the next tile meanwhile.
+__device__ __forceinline__ void bulk_store(double *dst, const double *src_shared, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src_shared)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // NPASS: staging passes (2: 16 elements at a time, 1: all 32 at once -- needs 32 * MSTRIDE doubles of shared memory)
-template <bool COMPACT, int NPASS>
+// BULK (compact, one pass): the staged matrices are handed to the copy engine, one 2592-byte bulk store per element (stride 326
+// doubles: 16-byte aligned sources; the even stride costs a 2-way bank conflict on the staging stores); the caller waits for the
+// engine to have READ the staging area before it overwrites it
+template <bool COMPACT, int NPASS, bool BULK = false>
 __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, const int t, const int64_t slot0, const H8Params &P) {
+  static_assert(!BULK || (COMPACT && NPASS == 1), "bulk stores: compact layout, single staging pass");
   constexpr int EPP = 32 / NPASS;  // elements per staging pass
-  constexpr int MSTRIDE = COMPACT ? EL_MSTRIDE_COMPACT : EL_MSTRIDE_FULL;
+  constexpr int MSTRIDE = BULK ? EL_MSTRIDE_BULK : (COMPACT ? EL_MSTRIDE_COMPACT : EL_MSTRIDE_FULL);
   constexpr int MSIZE = COMPACT ? 324 : 576;
   const int B1 = t, B2 = 7 - t, NB2 = 8 - t;
   double K[9][9];
@@ -291,6 +307,12 @@ __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, cons
         }
       }
     }
+    if (BULK) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the staging stores become visible to the copy engine
+      block_bar();
+      if (t == 0 && slot0 + lane < P.nactive) bulk_store(P.V + (slot0 + lane) * MSIZE, sm + (size_t)lane * MSTRIDE, MSIZE * 8);
+      return;
+    }
     block_bar();
     const int64_t sbase = slot0 + half * EPP;
     const int64_t nvalid = min((int64_t)EPP, P.nactive - sbase);
@@ -358,6 +380,59 @@ __global__ void __launch_bounds__(128, MINB) k_h8_elastic(const __grid_constant_
   elastic_phase_b<COMPACT, NPASS>(sm, lane, t, slot0, P);
 }
 
+// Persistent version with bulk stores: a CTA walks tiles of 32 elements; the copy engine drains tile i's staged matrices while the
+// warps fetch the coordinates of tile i+1 (the staging area aliases G, so G is written only after the engine has read it).
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_h8_elastic_bulk(const __grid_constant__ H8Params P, const int64_t ntiles) {
+  const double *c_dN = P.dN, *c_w = P.w;
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x & 31, t = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t slot0 = tile * EL_EPB;
+    const int64_t slot_raw = slot0 + lane;
+    const int64_t slot = slot_raw < P.nactive ? slot_raw : P.nactive - 1;
+    const int64_t e = P.elem_list ? P.elem_list[slot] : slot;
+    int nd[8];
+    const int4 *c4 = reinterpret_cast<const int4 *>(P.conn + e * 8);
+    int4 a = __ldg(c4), b = __ldg(c4 + 1);
+    nd[0] = a.x; nd[1] = a.y; nd[2] = a.z; nd[3] = a.w; nd[4] = b.x; nd[5] = b.y; nd[6] = b.z; nd[7] = b.w;
+    double X[8][3];
+#pragma unroll
+    for (int n = 0; n < 8; n++)
+#pragma unroll
+      for (int s = 0; s < 3; s++) X[n][s] = __ldg(P.xyz + (int64_t)s * P.nnodes + nd[n]);
+    if (t == 0) bulk_wait_read();  // warp 0 issued the previous tile's stores
+    __syncthreads();
+#pragma unroll 1
+    for (int jj = 0; jj < 2; jj++) {
+      const int j = 2 * t + jj;
+      const double *dN = c_dN + j * 24;
+      double J[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) J[i] = 0.0;
+#pragma unroll
+      for (int n = 0; n < 8; n++)
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+#pragma unroll
+          for (int s = 0; s < 3; s++) J[s + 3 * d] += X[n][s] * dN[d * 8 + n];
+      double inv[9], det;
+      inv3(J, inv, det);
+      double *g = sm + (size_t)j * EL_GSTRIDE * EL_EPB + lane;
+#pragma unroll
+      for (int n = 0; n < 8; n++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          g[(n * 3 + c) * EL_EPB] = dN[n] * inv[0 + 3 * c] + dN[8 + n] * inv[1 + 3 * c] + dN[16 + n] * inv[2 + 3 * c];
+      g[24 * EL_EPB] = det * c_w[j];
+    }
+    __syncthreads();
+    elastic_phase_b<true, 1, true>(sm, lane, t, slot0, P);
+  }
+  if (t == 0) bulk_wait_all();  // shared memory must outlive the engine's reads
+}
+
 }  // namespace
 
 int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool *handled) {
@@ -375,13 +450,23 @@ int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool 
   std::memcpy(P.coef, fa.coef, sizeof(double) * 36);
   if (diff) {
     unsigned grid = grid_for(mesh->nactive, 128);
+    // co-residency with the symbolic kernels of a fresh assembly (other stream): an unused dynamic shared-memory request of more than
+    // half an SM keeps this kernel at one CTA per SM, which leaves registers for two CTAs of k_sym_tile (FEGPU_DIFF_PAD_KB, A/B knob)
+    static const int pad_kb = std::getenv("FEGPU_DIFF_PAD_KB") ? std::atoi(std::getenv("FEGPU_DIFF_PAD_KB")) : 0;
+    const size_t pad = fa.cosched ? (size_t)pad_kb * 1024 : 0;
+#define DIFF_LAUNCH(G_, C_)                                                                                                          \
+  do {                                                                                                                               \
+    if (pad) CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_diffusion<G_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));     \
+    k_h8_diffusion<G_, C_><<<grid, 128, pad, ctx->stream>>>(P);                                                                      \
+  } while (0)
     if (fa.form == FORM_DIFF_GEN) {
-      if (fa.compact) k_h8_diffusion<true, true><<<grid, 128, 0, ctx->stream>>>(P);
-      else k_h8_diffusion<true, false><<<grid, 128, 0, ctx->stream>>>(P);
+      if (fa.compact) DIFF_LAUNCH(true, true);
+      else DIFF_LAUNCH(true, false);
     } else {
-      if (fa.compact) k_h8_diffusion<false, true><<<grid, 128, 0, ctx->stream>>>(P);
-      else k_h8_diffusion<false, false><<<grid, 128, 0, ctx->stream>>>(P);
+      if (fa.compact) DIFF_LAUNCH(false, true);
+      else DIFF_LAUNCH(false, false);
     }
+#undef DIFF_LAUNCH
   } else {
     // the attribute is per device (a process may hold contexts on several): set it on every launch, like every other kernel here
     static const bool three = std::getenv("FEGPU_ELASTIC_CTAS") && std::atoi(std::getenv("FEGPU_ELASTIC_CTAS")) == 3;
@@ -392,7 +477,13 @@ int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool 
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic<C_, M_, NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_));      \
     k_h8_elastic<C_, M_, NP_><<<grid, 128, SM_, ctx->stream>>>(P);                                                         \
   } while (0)
-    if (fa.compact) {
+    static const bool bulk_off = std::getenv("FEGPU_ELASTIC_BULK") && std::atoi(std::getenv("FEGPU_ELASTIC_BULK")) == 0;
+    if (fa.compact && !bulk_off && !three && !two_pass) {
+      const int64_t ntiles = (mesh->nactive + EL_EPB - 1) / EL_EPB;
+      const unsigned pgrid = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 2);
+      CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic_bulk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, EL_SMEM_BULK));
+      k_h8_elastic_bulk<2><<<pgrid, 128, EL_SMEM_BULK, ctx->stream>>>(P, ntiles);
+    } else if (fa.compact) {
       if (three) EL_LAUNCH(true, 3, 2, EL_SMEM_COMPACT);
       else if (two_pass) EL_LAUNCH(true, 2, 2, EL_SMEM_COMPACT);
       else EL_LAUNCH(true, 2, 1, EL_SMEM_COMPACT1);
