@@ -94,8 +94,7 @@ __global__ void k_expand_compact(const double *__restrict__ Vc, double *__restri
   const int k = (int)(i - eo * EM2), c = k / EM, r = k - c * EM;
   const int li = r / ndn, p = r - li * ndn, lc = c / ndn, q = c - lc * ndn, nd2 = ndn * ndn;
   const int off = (li <= lc) ? nd2 * (lc * (lc + 1) / 2 + li) + q * ndn + p : nd2 * (li * (li + 1) / 2 + lc) + p * ndn + q;
-  const int blk = off / nd2, ent = off - blk * nd2;  // planes: (blk * vstride + slot) * nd2 + entry
-  Vf[i] = vstride > 0 ? Vc[((int64_t)blk * vstride + e) * nd2 + ent] : Vc[e * CS + off];
+  Vf[i] = vstride > 0 ? Vc[(int64_t)off * vstride + e] : Vc[e * CS + off];  // value planes: position off of slot e at off * vstride + e
 }
 
 // smallest and largest node id used by the active elements: win[0] = max(~node) (so that a zero-initialised slot means "no node"),
@@ -180,7 +179,7 @@ struct DeviceGuard {
 }  // namespace
 
 // full element matrices permuted: out[r] = in[perm[r]]
-// (nne, ndn only matter for the plane form: position k = c * EM + r of the full matrix lives in plane b * nne + a, entry j * ndn + i)
+// (nne, ndn only matter for the plane form: position k = c * EM + r of the full matrix lives in value plane (b * nne + a) * ndn^2 + j * ndn + i)
 __global__ void k_permute_records(const double *__restrict__ in, double *__restrict__ out, int64_t nelem, int64_t rec, const int32_t *__restrict__ perm,
                                   int64_t vstride, int nne, int ndn) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,7 +188,7 @@ __global__ void k_permute_records(const double *__restrict__ in, double *__restr
   if (vstride > 0) {
     const int EM = nne * ndn, c = (int)(k / EM), r = (int)(k - (int64_t)c * EM);
     const int b = c / ndn, j = c - b * ndn, a = r / ndn, ii = r - a * ndn;
-    out[i] = in[((int64_t)(b * nne + a) * vstride + perm[eo]) * (ndn * ndn) + j * ndn + ii];
+    out[i] = in[((int64_t)(b * nne + a) * (ndn * ndn) + j * ndn + ii) * vstride + perm[eo]];
   } else {
     out[i] = in[(int64_t)perm[eo] * rec + k];
   }
@@ -779,12 +778,7 @@ static int32_t run_bilform(fegpu_mesh *mesh, fegpu_dofmap *dm, const FormArgs &f
       cudaStream_t sym = ov ? ctx->stream2 : st;
       // called from inside the build (which runs on `sym`) as soon as it knows which structured path it takes; a second call
       // with another layout (the thread-per-node attempt failed its preconditions) integrates again
-      std::function<int32_t(bool)> fork = [&](bool tile) -> int32_t {
-        fa2.cosched = tile;
-        const int32_t r = integrate(can_compact, tile && can_planes);
-        fa2.cosched = false;
-        return r;
-      };
+      std::function<int32_t(bool)> fork = [&](bool tile) -> int32_t { return integrate(can_compact, tile && can_planes); };
       if (ov) {  // the symbolic phase starts after everything queued on the caller's stream so far
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
         CUDA_TRY(ctx, cudaStreamWaitEvent(sym, ctx->ev_fork, 0));

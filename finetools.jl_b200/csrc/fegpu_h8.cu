@@ -316,7 +316,11 @@ __device__ __forceinline__ void elastic_phase_b(double *sm, const int lane, cons
     block_bar();
     const int64_t sbase = slot0 + half * EPP;
     const int64_t nvalid = min((int64_t)EPP, P.nactive - sbase);
-    if (nvalid > 0) {
+    if (P.vstride > 0) {
+      // value planes: warp t writes planes t, t + 4, ...; lane = element (256-byte coalesced stores, conflict-free reads: odd stride)
+      if (lane < nvalid)
+        for (int k = t; k < MSIZE; k += 4) P.V[(int64_t)k * P.vstride + sbase + lane] = sm[(size_t)lane * MSTRIDE + k];
+    } else if (nvalid > 0) {
       const int nval = (int)(nvalid * MSIZE);  // contiguous slots are contiguous in V
       double *dst = P.V + sbase * MSIZE;
       for (int i = threadIdx.x; i < nval; i += 128) {
@@ -450,23 +454,15 @@ int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool 
   std::memcpy(P.coef, fa.coef, sizeof(double) * 36);
   if (diff) {
     unsigned grid = grid_for(mesh->nactive, 128);
-    // co-residency with the symbolic kernels of a fresh assembly (other stream): an unused dynamic shared-memory request of more than
-    // half an SM keeps this kernel at one CTA per SM, which leaves registers for two CTAs of k_sym_tile (FEGPU_DIFF_PAD_KB, A/B knob)
-    static const int pad_kb = std::getenv("FEGPU_DIFF_PAD_KB") ? std::atoi(std::getenv("FEGPU_DIFF_PAD_KB")) : 0;
-    const size_t pad = fa.cosched ? (size_t)pad_kb * 1024 : 0;
-#define DIFF_LAUNCH(G_, C_)                                                                                                          \
-  do {                                                                                                                               \
-    if (pad) CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_diffusion<G_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));     \
-    k_h8_diffusion<G_, C_><<<grid, 128, pad, ctx->stream>>>(P);                                                                      \
-  } while (0)
+    // (Co-residency with k_sym_tile was measured: holding this kernel at one CTA per SM so that two CTAs of the symbolic kernel fit
+    // beside it made the fresh step slower, 11.2 against 9.2 ms on config 4 -- the two kernels compete for issue slots.)
     if (fa.form == FORM_DIFF_GEN) {
-      if (fa.compact) DIFF_LAUNCH(true, true);
-      else DIFF_LAUNCH(true, false);
+      if (fa.compact) k_h8_diffusion<true, true><<<grid, 128, 0, ctx->stream>>>(P);
+      else k_h8_diffusion<true, false><<<grid, 128, 0, ctx->stream>>>(P);
     } else {
-      if (fa.compact) DIFF_LAUNCH(false, true);
-      else DIFF_LAUNCH(false, false);
+      if (fa.compact) k_h8_diffusion<false, true><<<grid, 128, 0, ctx->stream>>>(P);
+      else k_h8_diffusion<false, false><<<grid, 128, 0, ctx->stream>>>(P);
     }
-#undef DIFF_LAUNCH
   } else {
     // the attribute is per device (a process may hold contexts on several): set it on every launch, like every other kernel here
     static const bool three = std::getenv("FEGPU_ELASTIC_CTAS") && std::atoi(std::getenv("FEGPU_ELASTIC_CTAS")) == 3;
@@ -477,8 +473,10 @@ int32_t fe_integrate_h8(fegpu_mesh *mesh, const FormArgs &fa, double *d_V, bool 
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic<C_, M_, NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_));      \
     k_h8_elastic<C_, M_, NP_><<<grid, 128, SM_, ctx->stream>>>(P);                                                         \
   } while (0)
-    static const bool bulk_off = std::getenv("FEGPU_ELASTIC_BULK") && std::atoi(std::getenv("FEGPU_ELASTIC_BULK")) == 0;
-    if (fa.compact && !bulk_off && !three && !two_pass) {
+    // persistent CTAs + copy-engine stores (element-major records only): measured 2.62 ms against 2.53 ms for the plain kernel on
+    // config 2 (profiles/r02_ncu_final_c2.txt: the copy-out loop was not what keeps the FP64 pipe at 55 %) -- A/B knob, off
+    static const bool bulk_on = std::getenv("FEGPU_ELASTIC_BULK") && std::atoi(std::getenv("FEGPU_ELASTIC_BULK")) == 1;
+    if (fa.compact && bulk_on && !fa.planes && !three && !two_pass) {
       const int64_t ntiles = (mesh->nactive + EL_EPB - 1) / EL_EPB;
       const unsigned pgrid = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 2);
       CUDA_TRY(ctx, cudaFuncSetAttribute(k_h8_elastic_bulk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, EL_SMEM_BULK));

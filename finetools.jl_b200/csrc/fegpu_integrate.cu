@@ -368,9 +368,15 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
           const int r = er[k], c = ec[k];
           const int a = r / NDN, i = r % NDN, b = c / NDN, j = c % NDN;
           const int blk = b * (b + 1) / 2 + a;
-          double *Vb = P.vstride > 0 ? P.V + ((int64_t)blk * P.vstride + slot) * ND2 : P.V + slot * REC + ND2 * blk;
-          Vb[j * NDN + i] = acc[k];
-          if (a == b && i != j) Vb[i * NDN + j] = acc[k];
+          if (P.vstride > 0) {  // value planes: entry e of block blk of slot s at ((blk * ND2 + e) * vstride + s)
+            double *Vb = P.V + (int64_t)blk * ND2 * P.vstride + slot;
+            Vb[(int64_t)(j * NDN + i) * P.vstride] = acc[k];
+            if (a == b && i != j) Vb[(int64_t)(i * NDN + j) * P.vstride] = acc[k];
+          } else {
+            double *Vb = P.V + slot * REC + ND2 * blk;
+            Vb[j * NDN + i] = acc[k];
+            if (a == b && i != j) Vb[i * NDN + j] = acc[k];
+          }
         }
       }
     } else if (live) {
@@ -383,8 +389,8 @@ __global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE) k_integrate(const Integ
           const int r = er[k], c = ec[k];
           if (P.vstride > 0) {
             const int a = r / NDN, i = r % NDN, b = c / NDN, j = c % NDN;
-            P.V[((int64_t)(b * NNE + a) * P.vstride + slot) * ND2 + j * NDN + i] = acc[k];
-            if (SYM && r != c) P.V[((int64_t)(a * NNE + b) * P.vstride + slot) * ND2 + i * NDN + j] = acc[k];
+            P.V[((int64_t)(b * NNE + a) * ND2 + j * NDN + i) * P.vstride + slot] = acc[k];
+            if (SYM && r != c) P.V[((int64_t)(a * NNE + b) * ND2 + i * NDN + j) * P.vstride + slot] = acc[k];
           } else {
             Ve[c * EM + r] = acc[k];
             if (SYM && r != c) Ve[r * EM + c] = acc[k];
@@ -477,11 +483,13 @@ bool fe_integrate_supports_compact(const fegpu_mesh *mesh, const FormArgs &fa) {
 // elasticity keeps element-major records) and the Kronecker path of bilform_dot with more than 3 dofs per node.
 bool fe_integrate_supports_planes(const fegpu_mesh *mesh, const FormArgs &fa) {
   if (fa.form == FORM_LINDOT || fa.form == FORM_MASSLIKE) return false;
-  // Scalar fields only.  For vector fields the NDN^2 lanes of a node read one contiguous ndn x ndn block of an element-major
-  // record anyway, and writing planes cost the elasticity kernel more than it gave the gather (k_h8_elastic 2.56 -> 2.69 ms with
-  // value planes, 3.47 ms with block planes; gather unchanged: profiles/r02_bench_n1_planes_variants.txt).
-  if (fa.ndn != 1) return false;
+  // Scalar fields, and elasticity on H8 with the 8-point rule (k_h8_elastic writes value planes from its staging buffer with
+  // coalesced 256-byte stores).  The other vector-field kernels keep element-major records: the NDN lanes of a node read one
+  // contiguous block of the record, and strided plane stores from registers cost more than they gave
+  // (profiles/r02_bench_n1_planes_variants.txt).
   const bool rotated = fa.use_rm && (fa.form == FORM_DIFF_GEN || fa.form == FORM_ELASTIC);
+  static const bool vec_planes_off = std::getenv("FEGPU_VEC_PLANES") && std::atoi(std::getenv("FEGPU_VEC_PLANES")) == 0;  // A/B knob
+  if (fa.ndn != 1) return !vec_planes_off && fa.form == FORM_ELASTIC && fa.ndn == 3 && mesh->etype == FEGPU_H8 && mesh->npts == 8 && mesh->sdim == 3 && !rotated;
   if (fa.form == FORM_ELASTIC && mesh->sdim == 3 && mesh->mdim == 3 && !rotated && !(mesh->etype == FEGPU_H8 && mesh->npts == 8)) {
     static const bool tiled_off = std::getenv("FEGPU_ELASTIC_TILED") && std::atoi(std::getenv("FEGPU_ELASTIC_TILED")) == 0;
     if (!tiled_off) return false;  // k_elastic_tiled

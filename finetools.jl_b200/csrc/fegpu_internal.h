@@ -201,7 +201,6 @@ struct FormArgs {
   // (k = the position inside the compact / full element record).  Only the kernels of fe_integrate_supports_planes.
   bool planes = false;
   int64_t vstride = 0;
-  bool cosched = false;  // launched beside the symbolic kernels of a fresh assembly (see fe_integrate_h8)
 };
 // Compact layout of a symmetric element matrix (nne nodes x ndn dofs): the upper block triangle, block (a <= b) of
 // ndn x ndn values (column-major: row comp i, col comp j at j*ndn + i) at ndn*ndn*(b(b+1)/2 + a); diagonal blocks are stored

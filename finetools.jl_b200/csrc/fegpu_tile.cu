@@ -15,8 +15,8 @@
 //   adj  uint32 [MAXDEG][nwp]   adjacent element j of window node i: (slot << 5) | local index, ascending slot
 //   cs   word   [MAXDEG][nwp]   neighbour slot of each of the NNE candidates of (node, adjacent element): one byte each
 //                               (0xff = row not owned by this rank), packed in one 64-bit (H8) / 32-bit (Q4, T3, T4) word
-//   V    double [blocks per element][vstride][ndn^2]   element matrices as written by the integration kernels (FormArgs::planes):
-//                               the ndn x ndn block of a node pair is one short run, the same block of the next slot follows it
+//   V    double [values per element][vstride]   element matrices as written by the integration kernels (FormArgs::planes): one plane
+//                               per position of the (compact) element record
 // Consecutive lanes = consecutive nodes read consecutive words; with elements stored in ascending-smallest-node order
 // (fe_order_elements) the j-th adjacent elements of consecutive nodes are consecutive slots, so the V loads of a warp
 // fall into one or two lines as well.
@@ -50,7 +50,7 @@ namespace {
 // nodes (= threads) per tile of k_sym_tile: a template parameter.  128 (4 CTAs per SM) is the measured default; 64 (8 CTAs per SM,
 // half the warps waiting at each barrier and during the look-back) was slower: 3.34 vs 3.11 ms on config 4 (FEGPU_TILE_T=64, A/B knob)
 constexpr int TILE_KB = 6;   // low bits of a candidate key: k = a * nne + li < 64
-constexpr uint32_t TILE_DROPPED = 0xffffffffu >> TILE_KB;  // node field of a candidate whose row this rank does not own / padding
+constexpr uint32_t TILE_DROPPED = 0xffffffffu >> TILE_KB;  // largest node field of a key; the field holds node id + 1 (0 = dropped candidate / padding)
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_VMASK = (1ull << 62) - 1ull;
 
 template <int NNE>
@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(TILE_T, 512 / TILE_T)
   const int64_t n = P.lo + i;
   // plane indices fit 32 bits (MAXDEG * nwp <= 16 * 2^26): one integer multiply-add per access, no 64-bit address registers
   const int ii = (int)i, nwp = (int)P.nwp;
+  const int64_t dof0 = P.dof[P.lo];  // requested here, needed after the look-back
   // ---- adjacency column (EMPTY = all ones where no element sits): sort by element slot (the order of the duplicate sum; EMPTY
   // entries go last), count, write it back in place
   uint32_t adj[MAXDEG];
@@ -195,7 +196,8 @@ __global__ void __launch_bounds__(TILE_T, 512 / TILE_T)
 #pragma unroll
   for (int j = 0; j < MAXDEG; j++)
     if (j < deg) adj_planes[j * nwp + ii] = adj[j];
-  // ---- candidate keys: (neighbour node << 6) | k, k = a * NNE + li; rows of other ranks and padding carry the all-ones node.
+  // ---- candidate keys: ((neighbour node + 1) << 6) | k, k = a * NNE + li; rows of other ranks and padding carry node field 0, so
+  // they sort FIRST and are never a head: no validity test per key in the two scans below.
   // All loads first (element ids, then the connectivity rows: 2 x MAXDEG independent requests in flight per thread).
   const int32_t *__restrict__ conn = P.conn;
   const int32_t *__restrict__ elem_list = P.elem_list;
@@ -214,23 +216,22 @@ __global__ void __launch_bounds__(TILE_T, 512 / TILE_T)
     if (j < deg) load_conn_row<NNE>(conn + (int64_t)el[j] * NNE, m);
 #pragma unroll
     for (int li = 0; li < NNE; li++) {
-      uint32_t node = (uint32_t)m[li];
-      if (PART == 1 && (m[li] < P.own_lo || m[li] >= P.own_hi)) node = TILE_DROPPED;
-      if (PART == 2 && j < deg && !P.rowowned[m[li]]) node = TILE_DROPPED;
-      if (j >= deg) node = TILE_DROPPED;
-      keys[j * NNE + li] = (node << TILE_KB) | (uint32_t)(j * NNE + li);
+      int mm = m[li];  // -1 where j >= deg
+      if (PART == 1 && (mm < P.own_lo || mm >= P.own_hi)) mm = -1;
+      if (PART == 2 && j < deg && !P.rowowned[mm]) mm = -1;
+      keys[j * NNE + li] = ((uint32_t)(mm + 1) << TILE_KB) | (uint32_t)(j * NNE + li);
     }
   }
   fesort::sort<NKEY>(keys);
   // ---- unique neighbours of this node
+  constexpr uint32_t KMASK = (1u << TILE_KB) - 1u;
   int nu = 0;
   {
-    uint32_t prev = TILE_DROPPED;
+    uint32_t prev = 0;  // node field 0: a dropped candidate
 #pragma unroll
     for (int x = 0; x < NKEY; x++) {
-      const uint32_t node = keys[x] >> TILE_KB;
-      nu += (node != TILE_DROPPED && node != prev) ? 1 : 0;
-      prev = node;
+      nu += ((keys[x] ^ prev) > KMASK) ? 1 : 0;  // the node field differs from the previous key's
+      prev = keys[x];
     }
   }
   // ---- prefix of the counts inside the CTA; the tile's aggregate is published right away, the look-back over the earlier
@@ -255,17 +256,15 @@ __global__ void __launch_bounds__(TILE_T, 512 / TILE_T)
   // ---- neighbour slot of every candidate (staged row, one byte each) and the unique list (dense, at the node's offset)
   {
     uint8_t *cs8 = cs_sm + tid * CSB;
-    int slot = -1;
-    uint32_t prev = TILE_DROPPED;
+    int slot = -1;  // dropped candidates come first and keep -1 = 0xff
+    uint32_t prev = 0;
 #pragma unroll
     for (int x = 0; x < NKEY; x++) {
-      const uint32_t node = keys[x] >> TILE_KB, k = keys[x] & ((1u << TILE_KB) - 1u);
-      const bool valid = node != TILE_DROPPED;
-      const bool head = valid && node != prev;
+      const bool head = (keys[x] ^ prev) > KMASK;
       slot += head ? 1 : 0;
-      cs8[k] = valid ? (uint8_t)slot : (uint8_t)0xffu;
-      if (head) U_sm[excl + slot] = node;
-      prev = node;
+      cs8[keys[x] & KMASK] = (uint8_t)slot;
+      if (head) U_sm[excl + slot] = keys[x] >> TILE_KB;  // node + 1
+      prev = keys[x];
     }
     // the thread's own row back from shared memory, one word per adjacent element, straight into the planes (coalesced)
     const uint32_t *row = reinterpret_cast<const uint32_t *>(cs8);
@@ -317,7 +316,6 @@ __global__ void __launch_bounds__(TILE_T, 512 / TILE_T)
   }
   __syncthreads();
   const long long base = s_base;
-  const int64_t dof0 = P.dof[P.lo];
   if (live) {
     const long long nb = base + excl;
     nbrptr[n] = nb;
@@ -333,9 +331,10 @@ __global__ void __launch_bounds__(TILE_T, 512 / TILE_T)
   }
   // ---- outputs of the tile: contiguous in memory
   if (nbr_out)
-    for (int idx = tid; idx < total; idx += TILE_T) nbr_out[base + idx] = (int32_t)U_sm[idx];
+    for (int idx = tid; idx < total; idx += TILE_T) nbr_out[base + idx] = (int32_t)U_sm[idx] - 1;
   if (NDN == 1) {
-    for (int idx = tid; idx < total; idx += TILE_T) rowval[base + idx] = dof0 + ((int64_t)U_sm[idx] - P.lo) + 1;
+    const int64_t shift = dof0 - P.lo;  // U holds node + 1 and rowval is 1-based
+    for (int idx = tid; idx < total; idx += TILE_T) rowval[base + idx] = shift + (int64_t)U_sm[idx];
   } else {
     for (int t = 0; t < 32; t++) {
       const int nu_t = __shfl_sync(0xffffffffu, nu, t);
@@ -345,7 +344,7 @@ __global__ void __launch_bounds__(TILE_T, 512 / TILE_T)
       const int per_col = nu_t * NDN;
       for (int r = lane; r < per_col; r += 32) {
         const int s = r / NDN, p = r - s * NDN;
-        const int64_t rd = dof0 + ((int64_t)U_sm[ex_t + s] - P.lo) * NDN + p + 1;
+        const int64_t rd = dof0 + ((int64_t)U_sm[ex_t + s] - 1 - P.lo) * NDN + p + 1;
 #pragma unroll
         for (int q = 0; q < NDN; q++) rowval[rb + (long long)q * per_col + r] = rd;
       }
@@ -379,7 +378,7 @@ struct GatherShape {
 
 // Position of value (block blk, entry e) of the element in slot `slot`:
 //   element-major records     slot * VPE + ND2 * blk + e          (vector fields: the NDN lanes of a node read one 72-byte block)
-//   planes (FormArgs::planes) (blk * vstride + slot) * ND2 + e     (scalar fields: consecutive nodes read consecutive words)
+//   planes (FormArgs::planes) (blk * ND2 + e) * vstride + slot     (value planes: consecutive nodes read consecutive words)
 // The accumulator image in shared memory is exactly the CTA's slice of nzval (column after column, rows in order), so the
 // write-out is a flat copy; lanes = (node, q) pairs hit distinct banks for a given (slot, p) because the column stride nu * NDN
 // is odd for the 27-neighbour interior stencil.
@@ -391,7 +390,10 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
   constexpr int64_t VPE = COMPACT ? (int64_t)(NNE * (NNE + 1) / 2) * ND2 : (int64_t)EM * EM;
   using CsT = typename CsWord<NNE>::type;
   const int tid = threadIdx.x;
-  const int ln = tid / NDN, q = tid - ln * NDN;
+  // element-major records: the NDN threads of a node are neighbours (they read one contiguous block); planes: component-major, the
+  // threads of a warp are consecutive nodes with the same q, so every load is one contiguous run of a value plane
+  const int q = PLANES ? tid / NPB : tid % NDN;
+  const int ln = PLANES ? tid - q * NPB : tid / NDN;
   const int64_t i0 = (int64_t)blockIdx.x * NPB;
   const int64_t i = i0 + ln;
   const bool live = i < G.nw;
@@ -437,15 +439,15 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
           // block (min, max) of the upper block triangle, entry (comp of min, comp of max) at comp_max * NDN + comp_min
           const bool tr = li > lc;
           const int blk = tr ? li * (li + 1) / 2 + lc : lc * (lc + 1) / 2 + li;
-          const double *B = PLANES ? V + ((int64_t)blk * G.vstride + slot) * ND2 : V + slot * VPE + ND2 * blk;
+          const double *B = PLANES ? V + (int64_t)blk * ND2 * G.vstride + slot : V + slot * VPE + ND2 * blk;
           const int e0 = tr ? q : q * NDN, es = tr ? NDN : 1;  // row component p: transposed block -> stride NDN
 #pragma unroll
-          for (int p = 0; p < NDN; p++) v[li][p] = B[e0 + p * es];
+          for (int p = 0; p < NDN; p++) v[li][p] = PLANES ? B[(int64_t)(e0 + p * es) * G.vstride] : B[e0 + p * es];
         } else {
           // full matrix in emission order: column (lc, q), rows (li, p); planes: block lc * NNE + li, entry q * NDN + p
-          const double *B = PLANES ? V + ((int64_t)(lc * NNE + li) * G.vstride + slot) * ND2 + q * NDN : V + slot * VPE + (lc * NDN + q) * EM + li * NDN;
+          const double *B = PLANES ? V + ((int64_t)(lc * NNE + li) * ND2 + q * NDN) * G.vstride + slot : V + slot * VPE + (lc * NDN + q) * EM + li * NDN;
 #pragma unroll
-          for (int p = 0; p < NDN; p++) v[li][p] = B[p];
+          for (int p = 0; p < NDN; p++) v[li][p] = PLANES ? B[(int64_t)p * G.vstride] : B[p];
         }
       }
     };
