@@ -365,6 +365,7 @@ struct TileGatherParams {
   const double *V;
   int64_t vstride;  // PLANES: doubles between the planes of two consecutive value indices
   double *nzval;
+  int acc_doubles;  // size of the accumulator image in shared memory; T * NDN dummy cells follow it
 };
 
 // One thread per (node, column component q).  Measured alternatives for vector fields (config 2, profiles/r02_gather_c2_variants.txt):
@@ -376,18 +377,39 @@ struct GatherShape {
   static constexpr int NPB = T / NDN;              // nodes per CTA
 };
 
+// Value load of the numeric kernel: volatile with a memory clobber, so the compiler keeps the batch of loads of one element together
+// and ahead of the shared-memory adds of the previous element (left to itself it sinks every load next to its use: one or two
+// loads in flight per thread).
+__device__ __forceinline__ double ld_value(const double *p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // Position of value (block blk, entry e) of the element in slot `slot`:
 //   element-major records     slot * VPE + ND2 * blk + e          (vector fields: the NDN lanes of a node read one 72-byte block)
 //   planes (FormArgs::planes) (blk * ND2 + e) * vstride + slot     (value planes: consecutive nodes read consecutive words)
 // The accumulator image in shared memory is exactly the CTA's slice of nzval (column after column, rows in order), so the
 // write-out is a flat copy; lanes = (node, q) pairs hit distinct banks for a given (slot, p) because the column stride nu * NDN
 // is odd for the 27-neighbour interior stencil.
-template <int NNE, int MAXDEG, int NDN, bool COMPACT, bool PLANES>
+// MODE (how the value loads of element j + 1 overlap the shared-memory adds of element j; measured in profiles/r02_gather_modes.txt):
+//   0  loads of j + 1 issued, then the adds of j.  ptxas gives every load of this branchy body ONE scoreboard (profiles/
+//      r02_scoreboards.txt), so the first add of j also waits for the loads of j + 1 that were just issued: nothing overlaps
+//   1  straight-line body (no branch: missing elements re-read element 0, rows of other ranks go to a dummy cell) with warp-level
+//      fences between the load batches and the add batches
+//   2  branchy body, but the first add of j (which waits for the scoreboard) comes BEFORE the loads of j + 1 are issued, the other
+//      adds after: the shared scoreboard only ever covers one batch when it is waited for
+//   3  mode 2 + L2 prefetches two elements ahead (prefetch.global.L2: no register, no scoreboard)
+//   4  straight-line body without fences (ptxas interleaves single loads with the adds, rotating over four scoreboards)
+//   5  mode 0 + L2 prefetches;   6  mode 4 + L2 prefetches
+template <int NNE, int MAXDEG, int NDN, bool COMPACT, bool PLANES, int MODE>
 __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileGatherParams<NNE> G) {
   extern __shared__ double acc[];
   constexpr int T = GatherShape<NDN>::T, NPB = GatherShape<NDN>::NPB, ND2 = NDN * NDN;
   constexpr int EM = NNE * NDN;
   constexpr int64_t VPE = COMPACT ? (int64_t)(NNE * (NNE + 1) / 2) * ND2 : (int64_t)EM * EM;
+  constexpr bool STRAIGHT = (MODE == 1 || MODE == 4 || MODE == 6);
+  constexpr bool PREFETCH = (MODE == 3 || MODE == 5 || MODE == 6);
   using CsT = typename CsWord<NNE>::type;
   const int tid = threadIdx.x;
   // element-major records: the NDN threads of a node are neighbours (they read one contiguous block); planes: component-major, the
@@ -410,52 +432,70 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
     off = (int)(G.colptr[dof0 + i * NDN + q] - 1 - cb0);
   }
   __syncthreads();
+  const unsigned wmask = __ballot_sync(0xffffffffu, nu > 0);
   if (nu > 0) {
     double *col = acc + off;
     const int ii = (int)i, nwp = (int)G.nwp;  // plane indices fit 32 bits
     const uint32_t *__restrict__ adjp = G.adj;
     const CsT *__restrict__ csp = G.cs;
     const double *__restrict__ V = G.V;
-    // metadata of every adjacent element first (2 x MAXDEG independent, coalesced loads in flight), then the values of element
-    // j + 1 are requested before the adds of element j (software pipeline: the loads overlap the shared-memory adds).
-    // Rows of other ranks (slot 0xff) are loaded as well and dropped at the add.
+    // metadata of every adjacent element first (2 x MAXDEG independent, coalesced loads in flight).  Rows of other ranks (slot 0xff)
+    // are loaded as well and dropped at the add.
+    double *dummy = acc + G.acc_doubles + tid * NDN;
     uint32_t ad[MAXDEG];
     CsT cs[MAXDEG];
 #pragma unroll
     for (int j = 0; j < MAXDEG; j++) {
-      ad[j] = 0;
-      cs[j] = ~(CsT)0;
-      if (j < deg) {
-        ad[j] = __ldcs(adjp + (j * nwp + ii));
-        cs[j] = __ldcs(csp + (j * nwp + ii));
-      }
-    }
-    auto load_vals = [&](int j, double (&v)[NNE][NDN]) {
-      const int64_t slot = ad[j] >> 5;
-      const int lc = (int)(ad[j] & 31u);
-#pragma unroll
-      for (int li = 0; li < NNE; li++) {
-        if (COMPACT) {
-          // block (min, max) of the upper block triangle, entry (comp of min, comp of max) at comp_max * NDN + comp_min
-          const bool tr = li > lc;
-          const int blk = tr ? li * (li + 1) / 2 + lc : lc * (lc + 1) / 2 + li;
-          const double *B = PLANES ? V + (int64_t)blk * ND2 * G.vstride + slot : V + slot * VPE + ND2 * blk;
-          const int e0 = tr ? q : q * NDN, es = tr ? NDN : 1;  // row component p: transposed block -> stride NDN
-#pragma unroll
-          for (int p = 0; p < NDN; p++) v[li][p] = PLANES ? B[(int64_t)(e0 + p * es) * G.vstride] : B[e0 + p * es];
-        } else {
-          // full matrix in emission order: column (lc, q), rows (li, p); planes: block lc * NNE + li, entry q * NDN + p
-          const double *B = PLANES ? V + ((int64_t)(lc * NNE + li) * ND2 + q * NDN) * G.vstride + slot : V + slot * VPE + (lc * NDN + q) * EM + li * NDN;
-#pragma unroll
-          for (int p = 0; p < NDN; p++) v[li][p] = PLANES ? B[(int64_t)p * G.vstride] : B[p];
+      if (STRAIGHT) {
+        const int jj = j < deg ? j : 0;
+        ad[j] = __ldcs(adjp + (jj * nwp + ii));
+        cs[j] = __ldcs(csp + (jj * nwp + ii));
+        if (j >= deg) cs[j] = ~(CsT)0;
+      } else {
+        ad[j] = 0;
+        cs[j] = ~(CsT)0;
+        if (j < deg) {
+          ad[j] = __ldcs(adjp + (j * nwp + ii));
+          cs[j] = __ldcs(csp + (j * nwp + ii));
         }
       }
+    }
+    // address of value (row node li, row component p) of the element in adjacency position j
+    auto value_ptr = [&](int j, int li, int p) -> const double * {
+      const int64_t slot = ad[j] >> 5;
+      const int lc = (int)(ad[j] & 31u);
+      if (COMPACT) {
+        // block (min, max) of the upper block triangle, entry (comp of min, comp of max) at comp_max * NDN + comp_min
+        const bool tr = li > lc;
+        const int blk = tr ? li * (li + 1) / 2 + lc : lc * (lc + 1) / 2 + li;
+        const int e = tr ? q + p * NDN : q * NDN + p;  // transposed block: the row component strides by NDN
+        return PLANES ? V + ((int64_t)blk * ND2 + e) * G.vstride + slot : V + slot * VPE + ND2 * blk + e;
+      }
+      // full matrix in emission order: column (lc, q), rows (li, p); planes: value index (lc * NNE + li) * ND2 + q * NDN + p
+      return PLANES ? V + ((int64_t)(lc * NNE + li) * ND2 + q * NDN + p) * G.vstride + slot : V + slot * VPE + (lc * NDN + q) * EM + li * NDN + p;
     };
-    auto add_vals = [&](int j, const double (&v)[NNE][NDN]) {
+    auto load_vals = [&](int j, double (&v)[NNE][NDN]) {
+#pragma unroll
+      for (int li = 0; li < NNE; li++)
+#pragma unroll
+        for (int p = 0; p < NDN; p++) v[li][p] = (MODE == 1) ? ld_value(value_ptr(j, li, p)) : *value_ptr(j, li, p);  // plain ld.global: the .nc path measured 0.7 ms slower
+    };
+    auto prefetch_vals = [&](int j) {
+#pragma unroll
+      for (int li = 0; li < NNE; li++)
+#pragma unroll
+        for (int p = 0; p < NDN; p++) asm volatile("prefetch.global.L2 [%0];" ::"l"(value_ptr(j, li, p)));
+    };
+    auto add_vals = [&](int j, const double (&v)[NNE][NDN], int li0, int li1) {
 #pragma unroll
       for (int li = 0; li < NNE; li++) {
+        if (li < li0 || li >= li1) continue;
         const unsigned s = (unsigned)((cs[j] >> (8 * li)) & 0xffu);
-        if (s != 0xffu) {
+        if (STRAIGHT) {
+          double *dst = (s != 0xffu) ? col + s * NDN : dummy;
+#pragma unroll
+          for (int p = 0; p < NDN; p++) dst[p] += v[li][p];
+        } else if (s != 0xffu) {
           double *dst = col + s * NDN;
 #pragma unroll
           for (int p = 0; p < NDN; p++) dst[p] += v[li][p];
@@ -464,12 +504,43 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
     };
     double va[NNE][NDN], vb[NNE][NDN];
     load_vals(0, va);  // deg >= 1 here (nu > 0)
+    if (PREFETCH && (STRAIGHT || 1 < deg)) prefetch_vals(1);
+    if (PREFETCH && (STRAIGHT || 2 < deg)) prefetch_vals(2);
 #pragma unroll
     for (int j = 0; j < MAXDEG; j += 2) {
-      if (j + 1 < deg) load_vals(j + 1, vb);
-      if (j < deg) add_vals(j, va);
-      if (j + 2 < deg && j + 2 < MAXDEG) load_vals(j + 2, va);
-      if (j + 1 < deg) add_vals(j + 1, vb);
+      if (MODE == 1) {
+        load_vals(j + 1, vb);
+        __syncwarp(wmask);
+        add_vals(j, va, 0, NNE);
+        __syncwarp(wmask);
+        if (j + 2 < MAXDEG) load_vals(j + 2, va);
+        __syncwarp(wmask);
+        add_vals(j + 1, vb, 0, NNE);
+        __syncwarp(wmask);
+      } else if (STRAIGHT) {
+        if (PREFETCH && j + 3 < MAXDEG) prefetch_vals(j + 3);
+        load_vals(j + 1, vb);
+        add_vals(j, va, 0, NNE);
+        if (PREFETCH && j + 4 < MAXDEG) prefetch_vals(j + 4);
+        if (j + 2 < MAXDEG) load_vals(j + 2, va);
+        add_vals(j + 1, vb, 0, NNE);
+      } else if (MODE == 2 || MODE == 3) {
+        if (j < deg) add_vals(j, va, 0, 1);  // waits for the values of j; nothing else is in flight
+        if (j + 1 < deg) load_vals(j + 1, vb);
+        if (PREFETCH && j + 3 < deg && j + 3 < MAXDEG) prefetch_vals(j + 3);
+        if (j < deg) add_vals(j, va, 1, NNE);
+        if (j + 1 < deg) add_vals(j + 1, vb, 0, 1);
+        if (j + 2 < deg && j + 2 < MAXDEG) load_vals(j + 2, va);
+        if (PREFETCH && j + 4 < deg && j + 4 < MAXDEG) prefetch_vals(j + 4);
+        if (j + 1 < deg) add_vals(j + 1, vb, 1, NNE);
+      } else {
+        if (PREFETCH && j + 3 < deg && j + 3 < MAXDEG) prefetch_vals(j + 3);
+        if (j + 1 < deg) load_vals(j + 1, vb);
+        if (j < deg) add_vals(j, va, 0, NNE);
+        if (PREFETCH && j + 4 < deg && j + 4 < MAXDEG) prefetch_vals(j + 4);
+        if (j + 2 < deg && j + 2 < MAXDEG) load_vals(j + 2, va);
+        if (j + 1 < deg) add_vals(j + 1, vb, 0, NNE);
+      }
     }
   }
   __syncthreads();
@@ -715,16 +786,42 @@ int32_t fe_tile_gather(fegpu_dofmap *dm, const double *d_V, bool compact, bool p
   if (!P || !P->tile) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: not a thread-per-node pattern");
   const int nne = mesh->nne, ndn = dm->ndn;
   const int npb = ((ndn == 3) ? 96 : 128) / ndn;
-  const size_t smem = sizeof(double) * (size_t)npb * P->maxnbr * ndn * ndn;
+  const int acc_doubles = (int)((size_t)npb * P->maxnbr * ndn * ndn);
+  const size_t smem = sizeof(double) * ((size_t)acc_doubles + (size_t)npb * ndn * ndn);  // + one dummy cell of ndn doubles per thread
   if (smem > 200 * 1024) return fegpu_fail(ctx, FEGPU_ERR_STATE, "internal: gather accumulators exceed shared memory");
   if (P->nnz == 0) return FEGPU_OK;
   const unsigned grid = (unsigned)((P->tile_nw + npb - 1) / npb);
-#define G_LAUNCH(NNE_, MD_, NDN_, C_, PL_)                                                                                          \
+  // shared-memory carve-out in percent of the SM's 228 KB (-1: the driver's choice).  What is not shared memory is L1, and the L1
+  // holds the lines of the loads in flight: fewer resident CTAs with a larger L1 can move more bytes (profiles/r02_gather_modes.txt)
+  // Measured (call R): 85 % (194 KB shared + 62 KB L1) is the best point for both field kinds; at 100 % (which the driver picks when
+  // it maximises resident CTAs) the scalar gather takes 2.8 instead of 1.9 ms, the elasticity gather 3.5 instead of 2.5 ms.
+  static const int carveout_env = std::getenv("FEGPU_GATHER_CARVEOUT") ? std::atoi(std::getenv("FEGPU_GATHER_CARVEOUT")) : 85;
+  const int carveout = (smem + 1024 > (size_t)carveout_env * 228 * 1024 / 100) ? -1 : carveout_env;  // one CTA must still fit
+  static const int gmode_env = std::getenv("FEGPU_GATHER_MODE") ? std::atoi(std::getenv("FEGPU_GATHER_MODE")) : 1;  // A/B knob
+  const int gmode = (nne == 8 && gmode_env >= 0 && gmode_env <= 6) ? gmode_env : 0;  // the variants exist for H8 only
+#define G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, M_)                                                                                    \
   do {                                                                                                                              \
     TileGatherParams<NNE_> G{P->tile_lo, P->tile_nw, P->tile_nwp, mesh->nnodes, P->t_deg, P->t_adj,                                 \
-                             reinterpret_cast<const CsWord<NNE_>::type *>(P->t_cs), P->d_nnbr, P->d_colptr, dm->d_dof, d_V, vstride, d_nzval}; \
-    if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_gather_tile<NNE_, MD_, NDN_, C_, PL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_gather_tile<NNE_, MD_, NDN_, C_, PL_><<<grid, GatherShape<NDN_>::T, smem, ctx->stream>>>(G);                                  \
+                             reinterpret_cast<const CsWord<NNE_>::type *>(P->t_cs), P->d_nnbr, P->d_colptr, dm->d_dof, d_V, vstride, d_nzval, acc_doubles}; \
+    if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_gather_tile<NNE_, MD_, NDN_, C_, PL_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    if (carveout >= 0) CUDA_TRY(ctx, cudaFuncSetAttribute(k_gather_tile<NNE_, MD_, NDN_, C_, PL_, M_>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout)); \
+    k_gather_tile<NNE_, MD_, NDN_, C_, PL_, M_><<<grid, GatherShape<NDN_>::T, smem, ctx->stream>>>(G);                              \
+  } while (0)
+#define G_LAUNCH(NNE_, MD_, NDN_, C_, PL_)                         \
+  do {                                                             \
+    if constexpr (NNE_ == 8) {                                     \
+      switch (gmode) {                                             \
+        case 1: G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, 1); break;    \
+        case 2: G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, 2); break;    \
+        case 3: G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, 3); break;    \
+        case 4: G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, 4); break;    \
+        case 5: G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, 5); break;    \
+        case 6: G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, 6); break;    \
+        default: G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, 0); break;   \
+      }                                                            \
+    } else {                                                       \
+      G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, 0);                     \
+    }                                                              \
   } while (0)
 #define G_PL(NNE_, MD_, NDN_, C_)                      \
   do {                                                 \
@@ -751,6 +848,7 @@ int32_t fe_tile_gather(fegpu_dofmap *dm, const double *d_V, bool compact, bool p
 #undef G_C
 #undef G_PL
 #undef G_LAUNCH
+#undef G_LAUNCH_M
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return FEGPU_OK;
