@@ -62,7 +62,27 @@ __device__ __forceinline__ void block_acc(double *k9, const double *ga, const do
   }
 }
 
-template <int NNE>
+// cubic-symmetry D (fe_elastic_cubic, fegpu_internal.h): accumulate the outer products P = sum Jw g_a g_b' only ...
+__device__ __forceinline__ void outer_acc(double *p9, const double *ga, const double *hb) {
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) p9[i + 3 * j] = fma(ga[i], hb[j], p9[i + 3 * j]);
+}
+// ... and form the block from P at the end: K_ij = lam P_ij + mu P_ji (i != j), K_ii = D00 P_ii + mu (tr P - P_ii); c = {D00, lam, mu}
+__device__ __forceinline__ void iso_block(double *k9, const double *c) {
+  const double tr = k9[0] + k9[4] + k9[8];
+  double out[9];
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      out[i + 3 * j] = (i == j) ? fma(c[0], k9[i + 3 * i], c[2] * (tr - k9[i + 3 * i])) : fma(c[1], k9[i + 3 * j], c[2] * k9[j + 3 * i]);
+#pragma unroll
+  for (int i = 0; i < 9; i++) k9[i] = out[i];
+}
+
+template <int NNE, bool ISO>
 __global__ void __launch_bounds__(Tiles<NNE>::BLOCK) k_elastic_tiled(const ElParams P) {
   constexpr int NT = Tiles<NNE>::NT;
   constexpr bool WARP = NT <= 32;                       // groups live inside a warp
@@ -164,6 +184,10 @@ __global__ void __launch_bounds__(Tiles<NNE>::BLOCK) k_elastic_tiled(const ElPar
           for (int c = 0; c < 3; c++) gq[c] = dN[a] * inv[0 + 3 * c] + dN[NNE + a] * inv[1 + 3 * c] + dN[2 * NNE + a] * inv[2 + 3 * c];
           G[a * 3 + 0] = gq[0]; G[a * 3 + 1] = gq[1]; G[a * 3 + 2] = gq[2];
           double *Ta = T + a * TSTR;
+          if (ISO) {
+            Ta[0] = Jw * gq[0]; Ta[1] = Jw * gq[1]; Ta[2] = Jw * gq[2];
+            continue;
+          }
           // column comp x of B_a: rows 0 (g0), 3 (g1), 4 (g2); comp y: rows 1 (g1), 3 (g0), 5 (g2); comp z: rows 2 (g2), 4 (g0), 5 (g1)
 #pragma unroll
           for (int mx = 0; mx < 6; mx++) {
@@ -184,11 +208,19 @@ __global__ void __launch_bounds__(Tiles<NNE>::BLOCK) k_elastic_tiled(const ElPar
 #pragma unroll
         for (int bb = 0; bb < TC; bb++) {
           const int b = min(TC * tJ + bb, NNE - 1);
-          double Tb[18];
+          if (ISO) {
+            double hb[3];
 #pragma unroll
-          for (int i = 0; i < 18; i++) Tb[i] = T[b * TSTR + i];
+            for (int i = 0; i < 3; i++) hb[i] = T[b * TSTR + i];
 #pragma unroll
-          for (int k = 0; k < TR; k++) block_acc(K[k][bb], ga[k], Tb);
+            for (int k = 0; k < TR; k++) outer_acc(K[k][bb], ga[k], hb);
+          } else {
+            double Tb[18];
+#pragma unroll
+            for (int i = 0; i < 18; i++) Tb[i] = T[b * TSTR + i];
+#pragma unroll
+            for (int k = 0; k < TR; k++) block_acc(K[k][bb], ga[k], Tb);
+          }
         }
       }
     }
@@ -201,6 +233,7 @@ __global__ void __launch_bounds__(Tiles<NNE>::BLOCK) k_elastic_tiled(const ElPar
           const int a = TR * tI + k, b = TC * tJ + bb;
           if (a < NNE && b < NNE && a <= b) {
             const bool diag = a == b;
+            if (ISO) iso_block(K[k][bb], P.C);
             if (P.compact) {
               double *Vb = P.V + slot * (int64_t)(NNE * (NNE + 1) / 2 * 9) + 9 * (b * (b + 1) / 2 + a);
 #pragma unroll
@@ -246,13 +279,17 @@ int32_t launch_tiled(fegpu_mesh *mesh, const FormArgs &fa, double *d_V) {
   P.dN = mesh->d_tab + (size_t)mesh->npts * NNE;  // the table holds N [npts][NNE] first
   P.w = mesh->d_w; P.npts = mesh->npts; P.V = d_V; P.compact = fa.compact ? 1 : 0;
   for (int i = 0; i < 36; i++) P.C[i] = fa.coef[i];
+  double cub[3];
+  const bool iso = fe_elastic_cubic(fa.coef, cub);
+  if (iso)
+    for (int i = 0; i < 3; i++) P.C[i] = cub[i];
   int n = 0;
   for (int J = 0; J < (NNE + TC - 1) / TC; J++)
     for (int I = 0; I < (NNE + TR - 1) / TR; I++)
       if (TR * I <= TC * J + TC - 1) { P.tab.I[n] = (uint8_t)I; P.tab.J[n] = (uint8_t)J; n++; }
   P.tab.nt = n;
   const size_t smem = sizeof(double) * ((size_t)mesh->npts * 3 * NNE + mesh->npts + (size_t)GPB * GRP);
-  auto kern = k_elastic_tiled<NNE>;
+  auto kern = iso ? k_elastic_tiled<NNE, true> : k_elastic_tiled<NNE, false>;
   if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t want = (mesh->nactive + GPB - 1) / GPB;
   const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)ctx->sm_count * 16);

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <functional>
 #include <string>
 #include <vector>
@@ -202,6 +203,24 @@ struct FormArgs {
   bool planes = false;
   int64_t vstride = 0;
 };
+// Does the 6 x 6 material matrix (column-major, strain order xx,yy,zz,xy,xz,yz) have the cubic-symmetry form
+//   [D00 on the normal diagonal, lam off it] (+) mu I_3, every other entry exactly zero
+// (isotropic materials: MatDeforElastIso builds exactly this)?  Then out = {D00, lam, mu} and the elasticity kernels may use their
+// outer-product formulation (fegpu_h8.cu: outer_acc / iso_block).  FEGPU_ELASTIC_ISO=0 switches the shortcut off (A/B knob).
+static inline bool fe_elastic_cubic(const double *D, double out[3]) {
+  static const bool off = std::getenv("FEGPU_ELASTIC_ISO") && std::atoi(std::getenv("FEGPU_ELASTIC_ISO")) == 0;
+  if (off) return false;
+  const double d00 = D[0], lam = D[1], mu = D[3 + 6 * 3];
+  for (int j = 0; j < 6; j++)
+    for (int i = 0; i < 6; i++) {
+      const double v = D[i + 6 * j];
+      const double want = (i == j) ? (i < 3 ? d00 : mu) : ((i < 3 && j < 3) ? lam : 0.0);
+      if (!(v == want)) return false;
+    }
+  out[0] = d00; out[1] = lam; out[2] = mu;
+  return true;
+}
+
 // Compact layout of a symmetric element matrix (nne nodes x ndn dofs): the upper block triangle, block (a <= b) of
 // ndn x ndn values (column-major: row comp i, col comp j at j*ndn + i) at ndn*ndn*(b(b+1)/2 + a); diagonal blocks are stored
 // in full (mirrored).  This is what the symmetric forms write on the mesh-structured path: (1 + 1/nne)/2 of the bytes.

@@ -68,6 +68,28 @@ def test_elastic_parity(fe, orc, gpu_ctx, et):
 
 
 @pytest.mark.parametrize("et", ["H8", "H20", "H27", "T4", "T10"])
+@pytest.mark.parametrize("material", ["isotropic", "cubic"])
+def test_elastic_parity_cubic_symmetry_shortcut(fe, orc, gpu_ctx, et, material):
+    """A material matrix of the cubic-symmetry form (isotropic: what MatDeforElastIso produces; cubic: D00 - lam != 2 mu) takes the
+    outer-product formulation of the elasticity kernels (fe_elastic_cubic, csrc/fegpu_internal.h): same matrix as the reference's
+    B' D B loop to rounding, pattern bit-exact, K - K' == 0 exactly (test/test_forms.jl:441-442)."""
+    fens, fes = _mesh(fe, et, 2)
+    _distort(fens)
+    u = make_field(fe, fens, 3)
+    rule = _rule(fe, et)
+    C = isotropic_C(E=3.1, nu=0.27)
+    if material == "cubic":
+        C[np.arange(3), np.arange(3)] *= 1.3
+        C[3:, 3:] *= 0.7
+    ref, _ = oracle_csc(orc, "elastic", et, fes, fens, u, rule, C)
+    got, _ = gpu_csc(fe, "elastic", fes, fens, u, rule, C)
+    assert_parity(ref, got)
+    import scipy.sparse as sp
+    K = sp.csc_matrix((got[2], got[1] - 1, got[0] - 1), shape=(u.nalldofs(), u.nalldofs()))
+    assert abs(K - K.T).max() == 0.0
+
+
+@pytest.mark.parametrize("et", ["H8", "H20", "H27", "T4", "T10"])
 @pytest.mark.parametrize("ndn", [1, 3])
 def test_dot_parity(fe, orc, gpu_ctx, et, ndn):
     fens, fes = _mesh(fe, et, 2)
