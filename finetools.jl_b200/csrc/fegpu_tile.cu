@@ -675,6 +675,8 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
   // integrates again in the layout the general path needs
   if (fork) PT((*fork)(true));
   const int part = !mesh->d_rowowned ? 0 : (mesh->own_contig ? 1 : 2);
+  // (Co-residency with the integration kernel was measured twice, profiles/r02_coresidency.txt: capping this kernel at 2 or 3 CTAs per
+  // SM so that a CTA of k_h8_diffusion fits beside them makes the fresh step slower, 10.1 / 9.3 against 8.9 ms.)
   const size_t smem = sizeof(uint32_t) * (size_t)tile_t * (nne * MD) + (size_t)tile_t * (nne * MD + 4);
 #define SYM_LAUNCH_T(NNE_, MD_, NDN_, PART_, TT_)                                                                                   \
   do {                                                                                                                              \
