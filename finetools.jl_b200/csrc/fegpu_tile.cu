@@ -47,8 +47,8 @@
 
 namespace {
 
-// nodes (= threads) per tile of k_sym_tile: a template parameter.  128 (4 CTAs per SM) is the measured default; 64 (8 CTAs per SM,
-// half the warps waiting at each barrier and during the look-back) was slower: 3.34 vs 3.11 ms on config 4 (FEGPU_TILE_T=64, A/B knob)
+// nodes (= threads) per tile of k_sym_tile: a template parameter.  Measured on config 4: 64 nodes (8 CTAs per SM) 3.34 ms, 128 nodes
+// 3.11 ms (later 2.85), 256 nodes (2 CTAs per SM) 2.78 ms -- the default for H8 (FEGPU_TILE_T = 64 / 128: A/B knob)
 constexpr int TILE_KB = 6;   // low bits of a candidate key: k = a * nne + li < 64
 constexpr uint32_t TILE_DROPPED = 0xffffffffu >> TILE_KB;  // largest node field of a key; the field holds node id + 1 (0 = dropped candidate / padding)
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_VMASK = (1ull << 62) - 1ull;
@@ -83,6 +83,20 @@ __global__ void __launch_bounds__(256) k_dof_affine(const int32_t *__restrict__ 
   if (bad) *notaffine = 1;
 }
 
+template <int NNE>
+__device__ __forceinline__ void load_conn_row(const int32_t *__restrict__ row, int (&m)[NNE]) {
+  if constexpr (NNE == 8) {
+    const int4 a = __ldg(reinterpret_cast<const int4 *>(row)), b = __ldg(reinterpret_cast<const int4 *>(row) + 1);
+    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+  } else if constexpr (NNE == 4) {
+    const int4 a = __ldg(reinterpret_cast<const int4 *>(row));
+    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < NNE; k++) m[k] = __ldg(row + k);
+  }
+}
+
 // flags: [0] an element lists a node twice, [2] a node has more than MAXDEG elements
 template <int NNE, int MAXDEG>
 __global__ void __launch_bounds__(256) k_adj_table(const TileParams P, int32_t *__restrict__ deg, uint32_t *__restrict__ tab, int *flags) {
@@ -105,19 +119,26 @@ __global__ void __launch_bounds__(256) k_adj_table(const TileParams P, int32_t *
 // stores never collide; on any other mesh two elements may claim one position and the later store wins.  k_sym_tile counts the
 // entries it finds, the host compares the total with nactive * nne after the build's round trip: a lost entry shows there, the
 // mesh is remembered as colliding and the build is redone with k_adj_table.  The planes are pre-filled with the EMPTY marker.
+// One thread per ELEMENT (the first version had one per (element, node): 134 instructions per entry, issue-bound at 0.68 ms on the
+// 256^3 block): the row is loaded once, the duplicate test is NNE (NNE - 1) / 2 register compares, and the lanes of a warp --
+// consecutive slots, i.e. mostly consecutive nodes -- write runs of one plane.
 template <int NNE, int MAXDEG>
 __global__ void __launch_bounds__(256) k_adj_place(const TileParams P, uint32_t *__restrict__ tab, int *flags) {
   static_assert(NNE <= MAXDEG, "one plane per local index");
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.nactive * NNE) return;
-  const int64_t slot = i / NNE;
-  const int lc = (int)(i - slot * NNE);
+  const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= P.nactive) return;
   const int64_t e = P.elem_list ? (int64_t)P.elem_list[slot] : slot;
-  const int32_t *c = P.conn + e * NNE;
-  const int n = c[lc];
-  tab[(int64_t)lc * P.nwp + (n - P.lo)] = ((uint32_t)slot << 5) | (uint32_t)lc;
-  for (int k = 0; k < lc; k++)
-    if (c[k] == n) flags[0] = 1;
+  int m[NNE];
+  load_conn_row<NNE>(P.conn + e * NNE, m);
+  bool dup = false;
+#pragma unroll
+  for (int a = 1; a < NNE; a++)
+#pragma unroll
+    for (int b = 0; b < a; b++) dup = dup || (m[a] == m[b]);
+  if (dup) flags[0] = 1;
+  const int nwp = (int)P.nwp, lo = (int)P.lo;  // plane indices fit 32 bits (MAXDEG * nwp <= 2^30)
+#pragma unroll
+  for (int lc = 0; lc < NNE; lc++) tab[lc * nwp + (m[lc] - lo)] = ((uint32_t)slot << 5) | (uint32_t)lc;
 }
 
 // prefix arrays outside the window: `before` ahead of it, the window's last value behind it
@@ -140,19 +161,6 @@ __global__ void k_tile_fill_colptr(int64_t *__restrict__ colptr, int64_t ncols, 
 __device__ __forceinline__ unsigned long long ld_state(const unsigned long long *p) { return *reinterpret_cast<const volatile unsigned long long *>(p); }
 __device__ __forceinline__ void st_state(unsigned long long *p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long *>(p) = v; }
 
-template <int NNE>
-__device__ __forceinline__ void load_conn_row(const int32_t *__restrict__ row, int (&m)[NNE]) {
-  if constexpr (NNE == 8) {
-    const int4 a = __ldg(reinterpret_cast<const int4 *>(row)), b = __ldg(reinterpret_cast<const int4 *>(row) + 1);
-    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
-  } else if constexpr (NNE == 4) {
-    const int4 a = __ldg(reinterpret_cast<const int4 *>(row));
-    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
-  } else {
-#pragma unroll
-    for (int k = 0; k < NNE; k++) m[k] = __ldg(row + k);
-  }
-}
 
 // out[0] = total neighbour entries of the window, out[1] = largest neighbour count, out[2] = tile ticket, out[3] = adjacency
 // entries found (= nactive * nne unless the optimistic placement lost one)
@@ -629,7 +637,10 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
   P->alloc_stream = st;
   P->ncols = dm->col_nall;
   P->nrows = dm->row_nall;
-  static const int tile_t = (std::getenv("FEGPU_TILE_T") && std::atoi(std::getenv("FEGPU_TILE_T")) == 64) ? 64 : 128;
+  // H8: 256 nodes per tile (two CTAs of eight warps per SM: the warps of a CTA run in step, so each scheduler's instruction cache
+  // sees two code positions instead of four; 2.78 against 2.85 ms on config 4); the 16-plane kernels keep 128.  FEGPU_TILE_T = A/B knob
+  static const int tile_env = std::getenv("FEGPU_TILE_T") ? std::atoi(std::getenv("FEGPU_TILE_T")) : 0;
+  const int tile_t = (tile_env == 64 || tile_env == 128) ? tile_env : (nne == 8 ? 256 : 128);
   const int64_t ntiles = (nw + tile_t - 1) / tile_t;
   const size_t nb_cap = (size_t)nadj * nne;  // upper bound of the neighbour entries: every candidate unique
   const size_t cs_bytes = (nne == 8 ? sizeof(unsigned long long) : sizeof(uint32_t)) * (size_t)MD * nwp;
@@ -659,8 +670,8 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
   k_dof_affine<<<(unsigned)std::min<int64_t>(grid_for(nw, 256), (int64_t)ctx->sm_count * 8), 256, 0, st>>>(dm->d_dof, nn, ndn, lo, nw, d_flags + 1);
   if (optimistic) {
     switch (nne) {
-      case 8: k_adj_place<8, 8><<<grid_for(nadj, 256), 256, 0, st>>>(TP, P->t_adj, d_flags); break;
-      default: k_adj_place<4, 16><<<grid_for(nadj, 256), 256, 0, st>>>(TP, P->t_adj, d_flags); break;
+      case 8: k_adj_place<8, 8><<<grid_for(mesh->nactive, 256), 256, 0, st>>>(TP, P->t_adj, d_flags); break;
+      default: k_adj_place<4, 16><<<grid_for(mesh->nactive, 256), 256, 0, st>>>(TP, P->t_adj, d_flags); break;
     }
   } else {
     switch (nne) {
@@ -687,6 +698,7 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
 #define SYM_LAUNCH(NNE_, MD_, NDN_, PART_)                        \
   do {                                                            \
     if (tile_t == 128) SYM_LAUNCH_T(NNE_, MD_, NDN_, PART_, 128); \
+    else if (NNE_ == 8 && tile_t == 256) SYM_LAUNCH_T(NNE_, MD_, NDN_, PART_, (NNE_ == 8 ? 256 : 128)); \
     else SYM_LAUNCH_T(NNE_, MD_, NDN_, PART_, 64);                \
   } while (0)
 #define SYM_PART(NNE_, MD_, NDN_)                        \
