@@ -7,7 +7,7 @@ connectivity tables :994-1004 (H8), :1366-1369 (T4).
 
 The basis functions here are written from the element definitions (signed-corner tables for the hexahedra,
 1-D Lagrange factors for H27) rather than as expression lists; they agree with the reference's expressions to
-rounding (checked against the oracle's literal transcription in tests/test_oracle_basis.py).
+rounding (checked against the oracle's literal transcription in tests/test_oracle_pins.py::test_host_basis_matches_oracle_transcription).
 """
 import numpy as np
 

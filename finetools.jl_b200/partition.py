@@ -23,8 +23,9 @@ def pointpartitioning(xyz, npartitions=2):
     xyz = np.asarray(xyz, dtype=np.float64)
     if npartitions < 2:
         raise ValueError("Number of partitions must be >= 2")
-    if xyz.shape[1] != 3:
-        raise ValueError("Not implemented for 1D / 2D")
+    sdim = xyz.shape[1]
+    if sdim not in (2, 3):
+        raise ValueError("Not implemented for 1D")  # the reference only warns (MeshModificationModule.jl:1037)
     nlevels = int(round(np.ceil(np.log(npartitions) / np.log(2))))
     part = np.ones(xyz.shape[0], dtype=np.int64)
     for level in range(nlevels):
@@ -35,11 +36,15 @@ def pointpartitioning(xyz, npartitions=2):
                 continue
             X = xyz[idx]
             r = X - X.sum(axis=0) / idx.size
-            x, y, z = r[:, 0], r[:, 1], r[:, 2]
-            M = np.zeros((3, 3))
-            M[0, 0] = (y * y + z * z).sum(); M[1, 1] = (x * x + z * z).sum(); M[2, 2] = (y * y + x * x).sum()
-            M[0, 1] = -(x * y).sum(); M[0, 2] = -(x * z).sum(); M[1, 2] = -(y * z).sum()
-            M[1, 0] = M[0, 1]
+            if sdim == 3:
+                x, y, z = r[:, 0], r[:, 1], r[:, 2]
+                M = np.zeros((3, 3))
+                M[0, 0] = (y * y + z * z).sum(); M[1, 1] = (x * x + z * z).sum(); M[2, 2] = (y * y + x * x).sum()
+                M[0, 1] = -(x * y).sum(); M[0, 2] = -(x * z).sum(); M[1, 2] = -(y * z).sum()
+                M[1, 0] = M[0, 1]
+            else:  # planar point sets (_nodepartitioning2, MeshModificationModule.jl:886-951): the full symmetric 2 x 2 matrix
+                x, y = r[:, 0], r[:, 1]
+                M = np.array([[(y * y).sum(), -(x * y).sum()], [-(x * y).sum(), (x * x).sum()]])
             vals, vecs = np.linalg.eig(M)
             v = np.real(vecs[:, np.argsort(np.real(vals))[0]])
             d = r @ v

@@ -120,6 +120,15 @@ def test_pointpartitioning_labels(fe):
         assert p.shape == (fens.count(),)
     own = fe.slab_owner(fens.count(), 4)
     assert (np.diff(own) >= 0).all() and own[0] == 0 and own[-1] == 3
+    # planar point sets (_nodepartitioning2, MeshModificationModule.jl:886-951): a 4 x 1 strip is cut across its long direction
+    f2, _ = fe.Q4block(4.0, 1.0, 16, 4)
+    p2 = fe.pointpartitioning(f2.xyz, 4)
+    assert sorted(np.unique(p2)) == [1, 2, 3, 4]
+    for lab in (1, 2, 3, 4):
+        xs = f2.xyz[p2 == lab, 0]
+        assert xs.max() - xs.min() <= 1.0 + 1e-12          # every part is one quarter of the strip
+    with pytest.raises(ValueError):
+        fe.pointpartitioning(np.zeros((5, 1)), 2)
 
 
 def test_golden_fixtures_against_oracle(orc, fe):
