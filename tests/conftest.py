@@ -13,6 +13,27 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _cuda_device_present():
+    """Is there a CUDA device at all?  Asked of the driver library directly (no torch import, no dependence on our own extension:
+    a missing libfinegpu.so on a GPU box must still FAIL the GPU tests, not skip them)."""
+    import ctypes
+    try:
+        cuda = ctypes.CDLL("libcuda.so.1")
+    except OSError:
+        return False
+    n = ctypes.c_int(0)
+    return cuda.cuInit(0) == 0 and cuda.cuDeviceGetCount(ctypes.byref(n)) == 0 and n.value > 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest tests` on a machine without a GPU skips the GPU tests instead of stopping at the first one."""
+    gpu_items = [it for it in items if it.get_closest_marker("gpu")]
+    if gpu_items and not _cuda_device_present():
+        skip = pytest.mark.skip(reason="no CUDA device in this machine")
+        for it in gpu_items:
+            it.add_marker(skip)
+
+
 def isotropic_C(E=1.0, nu=0.3):
     """6x6 isotropic stiffness in the reference's strain order xx,yy,zz,xy,xz,yz (DeforModelRedModule.jl:463-468)."""
     lam = E * nu / ((1 + nu) * (1 - 2 * nu))
