@@ -360,236 +360,6 @@ __global__ void __launch_bounds__(TILE_T, 512 / TILE_T)
   }
 }
 
-// ------------------------------------------------------------------------------------------------ two threads per node
-// The same construction with a PAIR of neighbouring lanes per node (FEGPU_SYM_PAIR, measured in profiles/r02_sym_pair.txt): each
-// lane takes half of the node's elements, sorts its 32 candidate keys in registers (191 comparators), the pair merges the two runs
-// with one exchange (lane h = 0 keeps min(a[i], b[31 - i]), lane 1 the max: two bitonic sequences, everything in lane 0 below
-// everything in lane 1) and five in-register half-cleaner stages.  Half the registers per thread (twice the resident warps) for 7 %
-// more comparator instructions per node; everything after the sort works on the lane's own 32 keys, lane 1's slots offset by lane
-// 0's head count.  NODES = nodes per CTA (2 * NODES threads).
-template <int NNE, int MAXDEG, int NDN, int PART, int NODES, int MINB = 1024 / (2 * NODES)>
-__global__ void __launch_bounds__(2 * NODES, MINB)
-    k_sym_pair(const TileParams P, int32_t *__restrict__ deg_out, uint32_t *__restrict__ adj_planes,
-               typename CsWord<NNE>::type *__restrict__ cs_planes, int32_t *__restrict__ nnbr, int64_t *__restrict__ nbrptr,
-               int64_t *__restrict__ colptr, int64_t *__restrict__ rowval, int32_t *__restrict__ nbr_out, unsigned long long *tile_state,
-               unsigned long long *out) {
-  constexpr int NKEY = NNE * MAXDEG;      // candidate keys of a node (k < 64)
-  constexpr int HD = MAXDEG / 2;          // elements per lane
-  constexpr int NKH = 32;                 // keys per lane (NNE * HD <= 32; the rest is padding that sorts first)
-  constexpr int CSB = 64 + 4;             // staged slot row: 64 bytes (padding keys own the k values from NKEY up) + 4 => odd word stride
-  constexpr int NPAD = NKH - NNE * HD;    // padding keys per lane (T3: 8)
-  constexpr int T = 2 * NODES;
-  static_assert(NNE * HD <= NKH && NKEY + 2 * NPAD <= 64 && NKEY % 4 == 0 && MAXDEG % 2 == 0, "pair layout");
-  using CsT = typename CsWord<NNE>::type;
-  constexpr uint32_t KMASK = (1u << TILE_KB) - 1u;
-  extern __shared__ uint32_t smem_u32[];
-  uint32_t *U_sm = smem_u32;                                                // [NODES * NKEY]
-  uint8_t *cs_sm = reinterpret_cast<uint8_t *>(smem_u32 + NODES * NKEY);  // [NODES][CSB]
-  __shared__ int s_tile;
-  __shared__ long long s_base;
-  __shared__ int s_wtot[T / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int h = tid & 1, ln = tid >> 1;  // half, node of the tile
-  if (tid == 0) s_tile = atomicAdd(reinterpret_cast<int *>(out + 2), 1);
-  __syncthreads();
-  const int tile = s_tile;
-  const int64_t i = (int64_t)tile * NODES + ln;
-  const bool live = i < P.nw;
-  const int64_t n = P.lo + i;
-  const int ii = (int)i, nwp = (int)P.nwp;
-  const int64_t dof0 = P.dof[P.lo];
-  // ---- adjacency column: both lanes sort all of it (cheap), each writes back and works on its half
-  uint32_t adj[MAXDEG];
-#pragma unroll
-  for (int j = 0; j < MAXDEG; j++) adj[j] = live ? adj_planes[j * nwp + ii] : ~0u;
-  fesort::sort<MAXDEG>(adj);
-  int deg = 0;
-#pragma unroll
-  for (int j = 0; j < MAXDEG; j++) deg += (adj[j] != ~0u) ? 1 : 0;
-  if (live && h == 0) deg_out[i] = deg;
-  uint32_t mine[HD];  // the lane's elements: sorted positions h * HD .. h * HD + HD - 1
-#pragma unroll
-  for (int jj = 0; jj < HD; jj++) mine[jj] = h ? adj[HD + jj] : adj[jj];
-#pragma unroll
-  for (int jj = 0; jj < HD; jj++)
-    if (h * HD + jj < deg) adj_planes[(h * HD + jj) * nwp + ii] = mine[jj];
-  const int32_t *__restrict__ conn = P.conn;
-  const int32_t *__restrict__ elem_list = P.elem_list;
-  uint32_t keys[NKH];
-#pragma unroll
-  for (int x = 0; x < NKH; x++) keys[x] = (uint32_t)(NKEY + h * NPAD + (x >= NNE * HD ? x - NNE * HD : 0));  // padding: node field 0 (never a head), a k of its own
-#pragma unroll
-  for (int jj = 0; jj < HD; jj++) {
-    const int j = h * HD + jj;
-    uint32_t el = mine[jj] >> 5;
-    if (elem_list && j < deg) el = (uint32_t)__ldg(elem_list + el);
-    int m[NNE];
-#pragma unroll
-    for (int li = 0; li < NNE; li++) m[li] = -1;
-    if (j < deg) load_conn_row<NNE>(conn + (int64_t)el * NNE, m);
-#pragma unroll
-    for (int li = 0; li < NNE; li++) {
-      int mm = m[li];
-      if (PART == 1 && (mm < P.own_lo || mm >= P.own_hi)) mm = -1;
-      if (PART == 2 && j < deg && !P.rowowned[mm]) mm = -1;
-      keys[jj * NNE + li] = ((uint32_t)(mm + 1) << TILE_KB) | (uint32_t)(j * NNE + li);
-    }
-  }
-  fesort::sort<NKH>(keys);
-  // ---- merge the pair's runs: one exchange, then the lane's bitonic sequence is sorted by half-cleaners
-#pragma unroll
-  for (int x = 0; x < NKH / 2; x++) {
-    // lane 0 needs b[31 - x] for position x and b[x] for position 31 - x; lane 1 symmetrically: both send v[31 - x] and v[x]
-    const uint32_t o_hi = __shfl_xor_sync(0xffffffffu, keys[NKH - 1 - x], 1);
-    const uint32_t o_lo = __shfl_xor_sync(0xffffffffu, keys[x], 1);
-    keys[x] = h ? max(keys[x], o_hi) : min(keys[x], o_hi);
-    keys[NKH - 1 - x] = h ? max(keys[NKH - 1 - x], o_lo) : min(keys[NKH - 1 - x], o_lo);
-  }
-#pragma unroll
-  for (int st = NKH / 2; st >= 1; st >>= 1)
-#pragma unroll
-    for (int x = 0; x < NKH; x++)
-      if ((x & st) == 0) {
-        const uint32_t lo_ = min(keys[x], keys[x + st]), hi_ = max(keys[x], keys[x + st]);
-        keys[x] = lo_;
-        keys[x + st] = hi_;
-      }
-  // ---- heads of the lane's run; lane 1 continues from lane 0's last key
-  const uint32_t last0 = __shfl_sync(0xffffffffu, keys[NKH - 1], lane & ~1);
-  const uint32_t prev0 = h ? last0 : 0u;
-  int nuh = 0;
-  {
-    uint32_t prev = prev0;
-#pragma unroll
-    for (int x = 0; x < NKH; x++) {
-      nuh += ((keys[x] ^ prev) > KMASK) ? 1 : 0;
-      prev = keys[x];
-    }
-  }
-  const int nu_other = __shfl_xor_sync(0xffffffffu, nuh, 1);
-  const int nu = nuh + nu_other;
-  const int sbase = h ? nu_other : 0;  // lane 1's slots come after lane 0's
-  // ---- prefix of the counts inside the CTA (lane 0 of every pair carries the node's count)
-  int incl = h ? 0 : nu;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += t;
-  }
-  if (lane == 31) s_wtot[warp] = incl;
-  __syncthreads();
-  int woff = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < T / 32; w++) {
-    const int t = s_wtot[w];
-    if (w < warp) woff += t;
-    total += t;
-  }
-  // exclusive prefix of the node: lane 0 holds incl including its own count, lane 1 the same value (it added 0)
-  const int excl = woff + incl - nu;
-  if (tid == 0) st_state(tile_state + tile, (tile == 0 ? ST_PREFIX : ST_AGG) | (unsigned long long)total);
-  // ---- neighbour slots of the lane's candidates and the unique list
-  {
-    uint8_t *cs8 = cs_sm + ln * CSB;
-    int slot = sbase - 1;
-    uint32_t prev = prev0;
-#pragma unroll
-    for (int x = 0; x < NKH; x++) {
-      const bool head = (keys[x] ^ prev) > KMASK;
-      slot += head ? 1 : 0;
-      cs8[keys[x] & KMASK] = (uint8_t)slot;  // dropped candidates sort first and keep -1 = 0xff (in lane 1 only if lane 0 has no head at all)
-      if (head) U_sm[excl + slot] = keys[x] >> TILE_KB;  // node + 1
-      prev = keys[x];
-    }
-  }
-  __syncwarp();  // the row of a node is written by both lanes of its pair and read back by both
-  {
-    const uint8_t *cs8 = cs_sm + ln * CSB;
-    const uint32_t *row = reinterpret_cast<const uint32_t *>(cs8);
-#pragma unroll
-    for (int jj = 0; jj < HD; jj++) {
-      const int j = h * HD + jj;
-      if (j < deg) {
-        CsT w;
-        if constexpr (NNE == 8) w = (unsigned long long)row[2 * j] | ((unsigned long long)row[2 * j + 1] << 32);
-        else if constexpr (NNE == 4) w = row[j];
-        else w = (uint32_t)cs8[3 * j] | ((uint32_t)cs8[3 * j + 1] << 8) | ((uint32_t)cs8[3 * j + 2] << 16) | 0xff000000u;
-        cs_planes[j * nwp + ii] = w;
-      }
-    }
-  }
-  if (live && h == 0) nnbr[n] = nu;
-  {
-    int mx = nu, dsum = h ? 0 : deg;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-      dsum += __shfl_xor_sync(0xffffffffu, dsum, d);
-    }
-    if (lane == 0 && mx > 0) atomicMax(out + 1, (unsigned long long)mx);
-    if (lane == 0 && dsum > 0) atomicAdd(out + 3, (unsigned long long)dsum);
-  }
-  if (warp == 0) {
-    long long run = 0;
-    if (tile > 0) {
-      int look = tile - 1;
-      while (true) {
-        const int idx = look - lane;
-        unsigned long long st;
-        do {
-          st = (idx >= 0) ? ld_state(tile_state + idx) : ST_PREFIX;
-        } while (__any_sync(0xffffffffu, (st >> 62) == 0ull));
-        const unsigned pm = __ballot_sync(0xffffffffu, (st >> 62) == 2ull);
-        const int first = pm ? (__ffs(pm) - 1) : 32;
-        long long v = (lane <= first) ? (long long)(st & ST_VMASK) : 0ll;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        run += v;
-        if (pm) break;
-        look -= 32;
-      }
-      if (lane == 0) st_state(tile_state + tile, ST_PREFIX | (unsigned long long)(run + total));
-    }
-    if (lane == 0) s_base = run;
-  }
-  __syncthreads();
-  const long long base = s_base;
-  if (live && h == 0) {
-    const long long nb = base + excl;
-    nbrptr[n] = nb;
-    const int64_t c0 = dof0 + i * NDN;
-#pragma unroll
-    for (int q = 0; q < NDN; q++)
-      if (c0 + q <= P.ncols) colptr[c0 + q] = 1 + (nb * NDN + (long long)q * nu) * NDN;
-    if (i == P.nw - 1) {
-      nbrptr[n + 1] = nb + nu;
-      if (c0 + NDN <= P.ncols) colptr[c0 + NDN] = 1 + (nb + nu) * (long long)(NDN * NDN);
-      out[0] = (unsigned long long)(nb + nu);
-    }
-  }
-  if (nbr_out)
-    for (int idx = tid; idx < total; idx += T) nbr_out[base + idx] = (int32_t)U_sm[idx] - 1;
-  if (NDN == 1) {
-    const int64_t shift = dof0 - P.lo;
-    for (int idx = tid; idx < total; idx += T) rowval[base + idx] = shift + (int64_t)U_sm[idx];
-  } else {
-    // a warp holds 16 nodes (lane pairs): walk them, all 32 lanes write one node's rows
-    for (int t = 0; t < 32; t += 2) {
-      const int nu_t = __shfl_sync(0xffffffffu, nu, t);
-      const int ex_t = __shfl_sync(0xffffffffu, excl, t);
-      if (nu_t == 0) continue;
-      const long long rb = (base + ex_t) * (long long)(NDN * NDN);
-      const int per_col = nu_t * NDN;
-      for (int r = lane; r < per_col; r += 32) {
-        const int s = r / NDN, p = r - s * NDN;
-        const int64_t rd = dof0 + ((int64_t)U_sm[ex_t + s] - 1 - P.lo) * NDN + p + 1;
-#pragma unroll
-        for (int q = 0; q < NDN; q++) rowval[rb + (long long)q * per_col + r] = rd;
-      }
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ numeric phase
 template <int NNE>
 struct TileGatherParams {
@@ -871,10 +641,8 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
   // sees two code positions instead of four; 2.78 against 2.85 ms on config 4); the 16-plane kernels keep 128.  FEGPU_TILE_T = A/B knob
   static const int tile_env = std::getenv("FEGPU_TILE_T") ? std::atoi(std::getenv("FEGPU_TILE_T")) : 0;
   // two lanes per node (k_sym_pair): FEGPU_SYM_PAIR, A/B knob
-  static const int pair_mode = std::getenv("FEGPU_SYM_PAIR") ? std::atoi(std::getenv("FEGPU_SYM_PAIR")) : 0;  // 1: 128 nodes x 4 CTAs, 2: x 3 CTAs (85 registers), 3: 256 nodes x 2 CTAs
-  const bool pair = pair_mode >= 1 && pair_mode <= 3;
-  const bool pair256 = pair_mode == 3 && nne == 8 && !mesh->d_rowowned;
-  const int tile_t = pair ? (pair256 ? 256 : 128) : ((tile_env == 64 || tile_env == 128) ? tile_env : (nne == 8 ? 256 : 128));
+  // (Two lanes per node -- half the registers, twice the warps -- was built and measured: a tie at best, profiles/r02_sym_pair.txt.)
+  const int tile_t = (tile_env == 64 || tile_env == 128) ? tile_env : (nne == 8 ? 256 : 128);
   const int64_t ntiles = (nw + tile_t - 1) / tile_t;
   const size_t nb_cap = (size_t)nadj * nne;  // upper bound of the neighbour entries: every candidate unique
   const size_t cs_bytes = (nne == 8 ? sizeof(unsigned long long) : sizeof(uint32_t)) * (size_t)MD * nwp;
@@ -922,33 +690,16 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
   const int part = !mesh->d_rowowned ? 0 : (mesh->own_contig ? 1 : 2);
   // (Co-residency with the integration kernel was measured twice, profiles/r02_coresidency.txt: capping this kernel at 2 or 3 CTAs per
   // SM so that a CTA of k_h8_diffusion fits beside them makes the fresh step slower, 10.1 / 9.3 against 8.9 ms.)
-  const size_t smem = sizeof(uint32_t) * (size_t)tile_t * (nne * MD) + (size_t)tile_t * (pair ? 68 : (nne * MD + 4));
+  const size_t smem = sizeof(uint32_t) * (size_t)tile_t * (nne * MD) + (size_t)tile_t * (nne * MD + 4);
 #define SYM_LAUNCH_T(NNE_, MD_, NDN_, PART_, TT_)                                                                                   \
   do {                                                                                                                              \
     PC(cudaFuncSetAttribute(k_sym_tile<NNE_, MD_, NDN_, PART_, TT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     k_sym_tile<NNE_, MD_, NDN_, PART_, TT_><<<(unsigned)ntiles, TT_, smem, st>>>(TP, P->t_deg, P->t_adj,                            \
         reinterpret_cast<CsWord<NNE_>::type *>(P->t_cs), P->d_nnbr, P->d_nbrptr, P->d_colptr, P->d_rowval, P->d_nbr, d_state, d_out); \
   } while (0)
-#define SYM_LAUNCH_PAIR_V(NNE_, MD_, NDN_, PART_, NODES_, MINB_)                                                                     \
-  do {                                                                                                                              \
-    PC(cudaFuncSetAttribute(k_sym_pair<NNE_, MD_, NDN_, PART_, NODES_, MINB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_sym_pair<NNE_, MD_, NDN_, PART_, NODES_, MINB_><<<(unsigned)ntiles, 2 * NODES_, smem, st>>>(TP, P->t_deg, P->t_adj,           \
-        reinterpret_cast<CsWord<NNE_>::type *>(P->t_cs), P->d_nnbr, P->d_nbrptr, P->d_colptr, P->d_rowval, P->d_nbr, d_state, d_out); \
-  } while (0)
-#define SYM_LAUNCH_PAIR(NNE_, MD_, NDN_, PART_)                                                    \
-  do {                                                                                             \
-    if constexpr (NNE_ == 8 && PART_ == 0) {                                                       \
-      if (pair_mode == 2) SYM_LAUNCH_PAIR_V(NNE_, MD_, NDN_, PART_, 128, 3);                       \
-      else if (pair_mode == 3) SYM_LAUNCH_PAIR_V(NNE_, MD_, NDN_, PART_, 256, 2);                  \
-      else SYM_LAUNCH_PAIR_V(NNE_, MD_, NDN_, PART_, 128, 4);                                      \
-    } else {                                                                                       \
-      SYM_LAUNCH_PAIR_V(NNE_, MD_, NDN_, PART_, 128, 4);                                           \
-    }                                                                                              \
-  } while (0)
 #define SYM_LAUNCH(NNE_, MD_, NDN_, PART_)                        \
   do {                                                            \
-    if (pair) SYM_LAUNCH_PAIR(NNE_, MD_, NDN_, PART_);            \
-    else if (tile_t == 128) SYM_LAUNCH_T(NNE_, MD_, NDN_, PART_, 128); \
+    if (tile_t == 128) SYM_LAUNCH_T(NNE_, MD_, NDN_, PART_, 128); \
     else if (NNE_ == 8 && tile_t == 256) SYM_LAUNCH_T(NNE_, MD_, NDN_, PART_, (NNE_ == 8 ? 256 : 128)); \
     else SYM_LAUNCH_T(NNE_, MD_, NDN_, PART_, 64);                \
   } while (0)
@@ -973,8 +724,6 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
 #undef SYM_PART
 #undef SYM_LAUNCH
 #undef SYM_LAUNCH_T
-#undef SYM_LAUNCH_PAIR
-#undef SYM_LAUNCH_PAIR_V
   ctx->launches++;
   PC(cudaGetLastError());
   fe_mark(ctx, "sym:k_sym_tile");
