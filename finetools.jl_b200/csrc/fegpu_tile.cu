@@ -640,7 +640,6 @@ int32_t fe_tile_build(fegpu_dofmap *dm, const std::function<int32_t(bool)> *fork
   // H8: 256 nodes per tile (two CTAs of eight warps per SM: the warps of a CTA run in step, so each scheduler's instruction cache
   // sees two code positions instead of four; 2.78 against 2.85 ms on config 4); the 16-plane kernels keep 128.  FEGPU_TILE_T = A/B knob
   static const int tile_env = std::getenv("FEGPU_TILE_T") ? std::atoi(std::getenv("FEGPU_TILE_T")) : 0;
-  // two lanes per node (k_sym_pair): FEGPU_SYM_PAIR, A/B knob
   // (Two lanes per node -- half the registers, twice the warps -- was built and measured: a tie at best, profiles/r02_sym_pair.txt.)
   const int tile_t = (tile_env == 64 || tile_env == 128) ? tile_env : (nne == 8 ? 256 : 128);
   const int64_t ntiles = (nw + tile_t - 1) / tile_t;
