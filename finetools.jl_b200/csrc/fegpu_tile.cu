@@ -22,7 +22,7 @@
 // fall into one or two lines as well.
 //
 // Three kernels per fresh assembly:
-//   k_adj_place   one pass over the connectivity: drop (slot << 5 | local index) into plane `local index` of the node's column,
+//   k_adj_place   one thread per element: drop (slot << 5 | local index) into plane `local index` of each of its nodes' columns,
 //                 no atomics (optimistic: verified by the entry count, see the kernel).  k_adj_table is the version with an
 //                 atomicAdd per (element, node) whose return value is the position; triangles and colliding meshes use it.
 //   k_sym_tile    per node: sort the adjacency column (ascending slot = the order of the duplicate sum), load the element
@@ -32,7 +32,8 @@
 //   k_gather_tile numeric phase: thread per (node, column component) walks the node's adjacent elements in ascending order
 //                 and adds every value into the CTA's shared-memory image of its slice of nzval (laid out exactly as in
 //                 memory, so the write-out is a flat copy).  No atomics, fixed order => bit-reproducible
-//                 (test/test_basics.jl:3039-3045).
+//                 (test/test_basics.jl:3039-3045).  The loads of the next element are in flight during the adds of this one;
+//                 what it took to make that true (scoreboards, L1 carve-out) is in the kernel's comment.
 //
 // Preconditions, checked on the device and read back with the build's ONE host round trip (the kernels are launched
 // optimistically and are safe when a precondition fails): every node has at most MAXDEG elements, no element lists a node
