@@ -370,6 +370,12 @@ def run_gpu(args):
             link = (n_ + 1) * 8 + (nnz_local // nd2) * 4 + (nn + 1) * 8 + nn * spec["ndn"] * 4 + nnz_local * 8
             link_note = ("rowval is rebuilt on the host from the device's neighbour lists (int32 per node pair) + dof map by the library's "
                          "host threads while nzval is in flight")
+        elif xfer1.get("stenciled_results", 0) - xfer0.get("stenciled_results", 0) >= e2e_steps:
+            # rowval did not cross the link: colptr + one column-stencil id per column (uint32) + a dictionary of row-offset lists
+            # (a few KB) + nzval did; the host threads rebuilt rowval (fe_col_stencils / expand_stencils)
+            link = (n_ + 1) * 8 + n_ * 4 + nnz_local * 8
+            link_note = ("rowval is rebuilt on the host from one column-stencil id per column + a dictionary of row-offset lists, built and "
+                         "verified on the device, while nzval is in flight")
         else:
             link = d2h - 4 * nnz_local
             link_note = "rowval crosses the link as int32 and is widened by host threads"

@@ -65,6 +65,7 @@ SIGNATURES = {
     "fegpu_makematrix_view": (C.c_int32, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32]),
     "fegpu_transfer_stats": (C.c_int32, [VP, c_i64p, c_i64p]),
     "fegpu_transfer_compressed": (C.c_int32, [VP, c_i64p]),
+    "fegpu_transfer_stenciled": (C.c_int32, [VP, c_i64p]),
     "fegpu_makematrix_copy_values": (C.c_int32, [VP, VP]),
     "fegpu_makematrix_device": (C.c_int32, [VP, C.POINTER(VP), C.POINTER(VP), C.POINTER(VP)]),
     "fegpu_coo_copy": (C.c_int32, [VP, VP, VP, VP, VP, VP]),

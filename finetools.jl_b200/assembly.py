@@ -103,7 +103,9 @@ class GPUContext:
         check(_lib.lib().fegpu_transfer_stats(self.handle, C.byref(a), C.byref(b)), self.handle)
         c = C.c_int64(0)
         check(_lib.lib().fegpu_transfer_compressed(self.handle, C.byref(c)), self.handle)
-        return {"staged_chunks": a.value, "bypassed_chunks": b.value, "compressed_results": c.value}
+        d = C.c_int64(0)
+        check(_lib.lib().fegpu_transfer_stenciled(self.handle, C.byref(d)), self.handle)
+        return {"staged_chunks": a.value, "bypassed_chunks": b.value, "compressed_results": c.value, "stenciled_results": d.value}
 
     def measure_peaks(self):
         a, b = C.c_double(0), C.c_double(0)

@@ -205,6 +205,24 @@ void expand_rows(const int32_t *nbr, const int64_t *nbrptr, const int32_t *dof, 
   _mm_sfence();
 }
 
+// Row indices of columns [c_lo, c_hi) from the column-stencil codec (fe_col_stencils, fegpu_csc_ops.cu): the rows of column c are
+// c + 1 + offsets of the dictionary entry its id names.  A decoder of what the device produced and verified column by column.
+void expand_stencils(const uint32_t *ids, const int32_t *lut, const int32_t *dict, int stride, const int64_t *colptr, int64_t *rowval, int64_t c_lo,
+                     int64_t c_hi, bool avx2) {
+  int64_t rows[128];
+  RowSink sink(avx2);
+  for (int64_t c = c_lo; c < c_hi; c++) {
+    const int32_t *d = dict + (size_t)lut[ids[c]] * stride;
+    const int len = d[1];
+    if (len == 0) continue;
+    const int64_t c1 = c + 1;
+    for (int k = 0; k < len; k++) rows[k] = c1 + d[2 + k];
+    sink.put(rowval + (colptr[c] - 1), rows, (size_t)len);
+  }
+  sink.flush();
+  _mm_sfence();
+}
+
 }  // namespace
 
 struct Transfer {
@@ -221,6 +239,8 @@ struct Transfer {
   bool compress = true;                    // FEGPU_XFER_COMPRESS=0: never send neighbour lists instead of row indices
   int64_t staged = 0, bypassed = 0;        // chunk counters (diagnostics)
   int64_t compressed = 0;                  // results whose row indices were rebuilt from neighbour lists
+  bool stencil = true;                     // FEGPU_XFER_STENCIL=0: never send column-stencil ids instead of row indices
+  int64_t stenciled = 0;                   // results whose row indices were rebuilt from column stencils
   void *h_meta = nullptr;                  // pinned: neighbour lists, their offsets, the dof map, colptr
   size_t meta_cap = 0;
   cudaEvent_t meta_done = nullptr;
@@ -274,6 +294,7 @@ static int32_t transfer_get(fegpu_ctx *ctx, Transfer **out) {
   if (const char *e = std::getenv("FEGPU_XFER_CHUNK_MB")) t->chunk_bytes = std::min(XF_CHUNK_MAX, (size_t)std::max(1, std::atoi(e)) << 20);
   if (const char *e = std::getenv("FEGPU_XFER_NARROW")) t->narrow = std::atoi(e) != 0;
   if (const char *e = std::getenv("FEGPU_XFER_COMPRESS")) t->compress = std::atoi(e) != 0;
+  if (const char *e = std::getenv("FEGPU_XFER_STENCIL")) t->stencil = std::atoi(e) != 0;
   *out = t;
   return FEGPU_OK;
 }
@@ -360,20 +381,76 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
     h_nbr = reinterpret_cast<const int32_t *>(hm + b_col + b_ptr + b_dof);
     T->compressed++;
   }
+  // Scalar fields and every other result whose row indices would cross as int32: one id per column + a dictionary of row-offset
+  // lists (column stencils) instead -- config 4: 68 MB + a few KB instead of 1.82 GB.  The device builds and verifies the codec on
+  // the copy stream (one round trip); a matrix without a small dictionary keeps the int32 path.
+  const uint32_t *h_ids = nullptr;
+  const int32_t *h_dict = nullptr;
+  std::vector<int32_t> st_lut;
+  int st_stride = 0, st_nd = 0;
+  bool stencil = false;
+  if (!compressed && rowval && nnz >= ((int64_t)1 << 20) && T->stencil && !as->view.active) {
+    cudaEvent_t pr = as->pat_src ? fe_pattern_ready_event(as->pat_src) : nullptr;
+    if (pr) CUDA_TRY(ctx, cudaStreamWaitEvent(cs, pr, 0));
+    else FE_TRY(join());
+    uint32_t *d_ids = nullptr;
+    int32_t *d_dict = nullptr;
+    int nd = 0, maxlen = 0, cap = 0;
+    FE_TRY(fe_col_stencils(ctx, as->ncols, as->r_colptr(), as->r_rowval(), cs, &d_ids, &d_dict, &nd, &maxlen, &cap, &stencil));
+    if (stencil) {
+      st_stride = 2 + maxlen;
+      st_nd = nd;
+      const size_t b_col = ((size_t)(as->ncols + 1) * 8 + 63) & ~(size_t)63, b_ids = ((size_t)as->ncols * 4 + 63) & ~(size_t)63;
+      const size_t b_dict = ((size_t)nd * st_stride * 4 + 63) & ~(size_t)63;
+      const size_t need = b_col + b_ids + b_dict;
+      if (T->meta_cap < need) {
+        if (T->h_meta) cudaFreeHost(T->h_meta);
+        T->h_meta = nullptr; T->meta_cap = 0;
+        CUDA_TRY(ctx, cudaHostAlloc(&T->h_meta, need, cudaHostAllocDefault));
+        T->meta_cap = need;
+      }
+      char *hm = static_cast<char *>(T->h_meta);
+      CUDA_TRY(ctx, cudaMemcpyAsync(hm + b_col + b_ids, d_dict, (size_t)nd * st_stride * 4, cudaMemcpyDeviceToHost, cs));
+      CUDA_TRY(ctx, cudaMemcpyAsync(hm, as->r_colptr(), (size_t)(as->ncols + 1) * 8, cudaMemcpyDeviceToHost, cs));
+      CUDA_TRY(ctx, cudaMemcpyAsync(hm + b_col, d_ids, (size_t)as->ncols * 4, cudaMemcpyDeviceToHost, cs));
+      CUDA_TRY(ctx, cudaEventRecord(T->meta_done, cs));
+      fe_dev_free(ctx, d_ids, cs);
+      fe_dev_free(ctx, d_dict, cs);
+      h_colptr = reinterpret_cast<const int64_t *>(hm);
+      h_ids = reinterpret_cast<const uint32_t *>(hm + b_col);
+      h_dict = reinterpret_cast<const int32_t *>(hm + b_col + b_ids);
+      st_lut.assign((size_t)cap, 0);
+      c_nnodes = as->ncols;  // the slices below run over columns
+      c_total = nnz;
+      T->stenciled++;
+    }
+  }
+  const bool rebuilt = compressed || stencil;  // rowval is produced by the host threads, not shipped
   FE_TRY(join());
-  // node range [lo, hi) of slice k of K, balanced by neighbour-list length
+  // node (or column) range [lo, hi) of slice k of K, balanced by the number of row indices
   auto node_slice = [&](int64_t k, int64_t K, int64_t *lo, int64_t *hi) {
     auto cut = [&](int64_t j) -> int64_t {
       if (j <= 0) return 0;
       if (j >= K) return c_nnodes;
       const int64_t target = (int64_t)((__int128)c_total * j / K);
+      if (stencil) return std::upper_bound(h_colptr, h_colptr + c_nnodes + 1, target + 1) - h_colptr - 1;
       return std::upper_bound(h_nbrptr, h_nbrptr + c_nnodes + 1, target) - h_nbrptr - 1;
     };
     *lo = cut(k); *hi = cut(k + 1);
   };
+  auto expand_slice = [&](int64_t lo, int64_t hi) {
+    if (stencil) expand_stencils(h_ids, st_lut.data(), h_dict, st_stride, h_colptr, rowval, lo, hi, T->simd >= 1);
+    else expand_rows(h_nbr, h_nbrptr, h_dof, c_ndn, c_nnodes, h_colptr, rowval, lo, hi, T->simd >= 1);
+  };
+  auto meta_arrived = [&]() -> int32_t {  // the host may read the metadata from here on
+    CUDA_TRY(ctx, cudaEventSynchronize(T->meta_done));
+    if (stencil)
+      for (int k = 0; k < st_nd; k++) st_lut[(size_t)h_dict[(size_t)k * st_stride]] = k;  // slot number -> dictionary entry
+    return FEGPU_OK;
+  };
   int64_t exp_done = 0, exp_total = 0;  // node slices of the expansion handed to the threads so far / in all
 
-  if (rowval && nnz && !compressed) {
+  if (rowval && nnz && !rebuilt) {
     if (!T->narrow && is_pinned(rowval)) {
       direct_rv = as->r_rowval();
     } else {
@@ -394,7 +471,7 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
     jobs[k].per_chunk = (int64_t)(T->chunk_bytes / jobs[k].item_dev);
     total_chunks += (jobs[k].n + jobs[k].per_chunk - 1) / jobs[k].per_chunk;
   }
-  if (colptr && !compressed) CUDA_TRY(ctx, cudaMemcpyAsync(colptr, as->r_colptr(), sizeof(int64_t) * (as->r_ncols() + 1), cudaMemcpyDeviceToHost, cs));
+  if (colptr && !rebuilt) CUDA_TRY(ctx, cudaMemcpyAsync(colptr, as->r_colptr(), sizeof(int64_t) * (as->r_ncols() + 1), cudaMemcpyDeviceToHost, cs));
   if (direct_rv) CUDA_TRY(ctx, cudaMemcpyAsync(rowval, direct_rv, sizeof(int64_t) * nnz, cudaMemcpyDeviceToHost, cs));
 
   // page-locked nzval goes by plain DMA, sliced in between the staged chunks so the link never idles while the threads work
@@ -409,16 +486,16 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
   };
 
   std::function<void(int, int)> expand_all;
-  if (compressed) {
+  if (rebuilt) {
     exp_total = std::max<int64_t>(total_chunks, 1);
     if (total_chunks == 0) {
       // nothing is staged (nzval page-locked or not requested): the link carries nzval by plain DMA while the threads expand
       while (direct_nz && nz_issued < nnz) FE_TRY(issue_direct_nz());
-      CUDA_TRY(ctx, cudaEventSynchronize(T->meta_done));
+      FE_TRY(meta_arrived());
       expand_all = [&](int tid, int nth) {
         int64_t lo, hi;
         node_slice(tid, nth, &lo, &hi);
-        expand_rows(h_nbr, h_nbrptr, h_dof, c_ndn, c_nnodes, h_colptr, rowval, lo, hi, T->simd >= 1);
+        expand_slice(lo, hi);
         if (colptr) {  // the caller's colptr: each thread copies its share
           const int64_t n = as->ncols + 1, per = (n + nth - 1) / nth, a = std::min(n, per * tid), b = std::min(n, a + per);
           if (b > a) std::memcpy(colptr + a, h_colptr + a, (size_t)(b - a) * 8);
@@ -427,7 +504,7 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
       T->pool->run(expand_all);
       exp_done = exp_total;
     } else {
-      CUDA_TRY(ctx, cudaEventSynchronize(T->meta_done));
+      FE_TRY(meta_arrived());
       if (colptr) std::memcpy(colptr, h_colptr, (size_t)(as->ncols + 1) * 8);
     }
   }
@@ -482,13 +559,13 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
     const StagedJob &j = jobs[p.job];
     const void *src = T->h_stage[p.buf];
     const int simd = T->simd;
-    const int64_t exp_k = (compressed && exp_done < exp_total) ? exp_done++ : -1;
+    const int64_t exp_k = (rebuilt && exp_done < exp_total) ? exp_done++ : -1;
     const int wth = T->widen_threads;
     std::function<void(int, int)> fn = [&, src, p, simd, exp_k, wth](int tid, int nth) {
       if (exp_k >= 0) {  // this chunk's share of the row-index expansion
         int64_t lo, hi;
         node_slice(exp_k * nth + tid, exp_total * nth, &lo, &hi);
-        expand_rows(h_nbr, h_nbrptr, h_dof, c_ndn, c_nnodes, h_colptr, rowval, lo, hi, T->simd >= 1);
+        expand_slice(lo, hi);
       }
       // slices are multiples of 16 items so the vector loops stay aligned
       if (tid >= wth) return;
@@ -525,5 +602,11 @@ extern "C" int32_t fegpu_transfer_stats(fegpu_ctx *ctx, int64_t *staged, int64_t
 extern "C" int32_t fegpu_transfer_compressed(fegpu_ctx *ctx, int64_t *results) {
   if (!ctx || !results) return FEGPU_ERR_ARG;
   *results = ctx->xfer ? ctx->xfer->compressed : 0;
+  return FEGPU_OK;
+}
+
+extern "C" int32_t fegpu_transfer_stenciled(fegpu_ctx *ctx, int64_t *results) {
+  if (!ctx || !results) return FEGPU_ERR_ARG;
+  *results = ctx->xfer ? ctx->xfer->stenciled : 0;
   return FEGPU_OK;
 }

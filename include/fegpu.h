@@ -203,6 +203,12 @@ int32_t fegpu_transfer_stats(fegpu_ctx *ctx, int64_t *staged_chunks, int64_t *by
  * do, and the host threads decode them into `rowval` while nzval is in flight (FEGPU_XFER_COMPRESS=0 turns it off).
  * fegpu_transfer_compressed: number of results delivered that way so far. */
 int32_t fegpu_transfer_compressed(fegpu_ctx *ctx, int64_t *results);
+/* Every other result of at least 2^20 non-zeros (scalar fields, numberings that are not node-major): the row indices of column j
+ * are j + a list of offsets, and meshes repeat a few such lists, so one id per column (4 B) + a dictionary of offset lists cross
+ * the link instead of 4 B per non-zero, and the host threads rebuild `rowval` (the codec is built and verified column by column
+ * on the device; a matrix with more than 4096 distinct column shapes keeps the int32 transport; FEGPU_XFER_STENCIL=0 turns it
+ * off).  fegpu_transfer_stenciled: number of results delivered that way so far.  Nothing of the reference: a transport codec. */
+int32_t fegpu_transfer_stenciled(fegpu_ctx *ctx, int64_t *results);
 /* nzval only (re-assembly on a cached pattern: colptr/rowval did not change) */
 int32_t fegpu_makematrix_copy_values(fegpu_asm *as, double *nzval);
 /* device pointers of the current result (valid until the next assembly on this assembler) */

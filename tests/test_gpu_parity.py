@@ -705,6 +705,72 @@ def test_result_transport_large(fe, orc, gpu_ctx, pinned):
 
 
 @pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("variant", ["block", "partition", "skin", "random"])
+def test_result_transport_column_stencils(fe, orc, gpu_ctx, pinned, variant):
+    """Scalar fields (and everything else that would ship int32 row indices): one id per column + a dictionary of row-offset lists
+    cross the link and the host threads rebuild rowval (fe_col_stencils, csrc/fegpu_csc_ops.cu; decoder in fegpu_transfer.cu).  The
+    arrays that arrive must be the oracle's bit for bit.  'random': a matrix without a small dictionary (generic assemble! protocol,
+    random dofs) must fall back to the int32 transport and still arrive intact."""
+    rng = np.random.default_rng(11)
+    kw = {}
+    if variant == "random":
+        n, ne, em = 60000, 20000, 8
+        a = fe.SysmatAssemblerSparseGPU(0.0)
+        fe.startassembly(a, em, em, ne, n, n)
+        dofs = rng.integers(1, n + 1, size=(ne, em))
+        mats = rng.standard_normal((ne, em, em))
+        for e in range(ne):
+            fe.assemble(a, mats[e], dofs[e], dofs[e])
+        I = np.repeat(dofs[:, None, :], em, axis=1)   # entry (e, c, r): row dof = dofs[e, r], column-major emission
+        J = np.repeat(dofs[:, :, None], em, axis=2)   #                   column dof = dofs[e, c]
+        V = np.transpose(mats, (0, 2, 1))
+        ref = orc.sparse(I.reshape(-1).astype(np.int64), J.reshape(-1).astype(np.int64), np.ascontiguousarray(V).reshape(-1), n, n)
+        nnz = ref[2].size
+        assert nnz >= (1 << 20)
+        before = gpu_ctx.transfer_stats()["stenciled_results"]
+        got = fe.makematrix(a, raw=True)
+        assert_parity(ref, got, tol=1e-15)
+        assert gpu_ctx.transfer_stats()["stenciled_results"] == before
+        return
+    if variant == "skin":
+        fens, vol = fe.H8block(1.0, 2.0, 3.0, 300, 300, 3)
+        fes = fe.meshboundary(vol)
+        rule, form, coef, et, kw2 = fe.GaussRule(2, 2), "dot", np.array([[1.3]]), "Q4", dict(m=2)
+        okw = dict(m=2, otherdim=1.0)
+    else:
+        fens, fes = fe.H8block(1.0, 2.0, 3.0, 36, 36, 36)
+        _distort(fens)
+        rule, form, coef, et, kw2, okw = fe.GaussRule(3, 2), "diffusion", KAPPA3, "H8", {}, {}
+    u = make_field(fe, fens, 1)
+    ref, _ = oracle_csc(orc, form, et, fes, fens, u, rule, coef, **okw)
+    n = u.nalldofs()
+    if variant == "partition":
+        owner = fe.slab_owner(fens.count(), 3)
+        kw = dict(node_owner=owner, my_rank=1)
+        keep = np.zeros(n, bool)
+        keep[(u.dofnums[owner == 1] - 1).reshape(-1)] = True
+        mask = keep[ref[1] - 1]
+        col_of = np.repeat(np.arange(n), np.diff(ref[0]))
+        cnt = np.bincount(col_of[mask], minlength=n)
+        ref = (np.concatenate(([1], 1 + np.cumsum(cnt))).astype(np.int64), ref[1][mask], ref[2][mask])
+    nnz = ref[2].size
+    big = nnz >= (1 << 20)
+    before = gpu_ctx.transfer_stats()["stenciled_results"]
+    if pinned:
+        import torch
+        out = (torch.empty(n + 1, dtype=torch.int64, pin_memory=True).numpy(), torch.empty(nnz + 3, dtype=torch.int64, pin_memory=True).numpy()[3:],
+               torch.empty(nnz, dtype=torch.float64, pin_memory=True).numpy())
+    else:
+        out = (np.empty(n + 1, np.int64), np.empty(nnz + 1, np.int64)[1:], np.empty(nnz + 1, np.float64)[1:])
+    for o in out:
+        o[...] = -7
+    got, a = gpu_csc(fe, form, fes, fens, u, rule, coef, out=out, **kw2, **kw)
+    assert_parity(ref, got)
+    assert gpu_ctx.transfer_stats()["stenciled_results"] - before == (1 if big else 0)
+    assert variant == "partition" or big
+
+
+@pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("variant", ["natural", "ebc", "partition", "dot2"])
 def test_result_transport_compressed_rows(fe, orc, gpu_ctx, pinned, variant):
     """Vector fields: rowval is rebuilt on the host from the device's neighbour lists + dof map (fegpu_transfer.cu) instead
