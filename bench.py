@@ -373,7 +373,8 @@ def run_gpu(args):
         elif xfer1.get("stenciled_results", 0) - xfer0.get("stenciled_results", 0) >= e2e_steps:
             # rowval did not cross the link: colptr + one column-stencil id per column (uint32) + a dictionary of row-offset lists
             # (a few KB) + nzval did; the host threads rebuilt rowval (fe_col_stencils / expand_stencils)
-            link = (n_ + 1) * 8 + n_ * 4 + nnz_local * 8
+            ncw = min(n_, (W.win[1] - W.win[0]) * spec["ndn"])   # the rank's non-empty column window: only its colptr / ids are shipped
+            link = (ncw + 1) * 8 + ncw * 4 + nnz_local * 8
             link_note = ("rowval is rebuilt on the host from one column-stencil id per column + a dictionary of row-offset lists, built and "
                          "verified on the device, while nzval is in flight")
         else:

@@ -188,12 +188,23 @@ __global__ void __launch_bounds__(256) k_stencil_dict(int cap, const unsigned lo
   for (int64_t k = 0; k < len; k++) d[2 + k] = (int32_t)(rowval[b + k] - 1 - r);
 }
 
+// first and last non-empty column (colptr is monotone: two binary searches by one thread); range = {ncols, -1} for an empty matrix
+__global__ void k_col_range(int64_t ncols, const int64_t *__restrict__ colptr, int *range) {
+  const int64_t last = colptr[ncols];  // nnz + 1
+  int64_t lo = 0, hi = ncols;          // first c with colptr[c + 1] > 1
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (colptr[mid + 1] > 1) hi = mid; else lo = mid + 1; }
+  range[0] = (int)lo;
+  lo = -1; hi = ncols - 1;             // last c with colptr[c] < last
+  while (lo < hi) { const int64_t mid = (lo + hi + 1) >> 1; if (colptr[mid] < last) lo = mid; else hi = mid - 1; }
+  range[1] = (int)lo;
+}
+
 }  // namespace
 
 // ids[ncols] (uint32 slot numbers) and the dictionary for the CSC (colptr, rowval) on `stream`.  *ok = false: no small dictionary
 // (the caller ships int32 row indices).  The caller frees *d_ids and *d_dict with fe_dev_free when *ok.  One host round trip.
 int32_t fe_col_stencils(fegpu_ctx *ctx, int64_t ncols, const int64_t *d_colptr, const int64_t *d_rowval, cudaStream_t stream, uint32_t **d_ids,
-                        int32_t **d_dict, int *ndict, int *maxlen_out, int *cap_out, bool *ok) {
+                        int32_t **d_dict, int *ndict, int *maxlen_out, int *cap_out, int64_t *col_first, int64_t *col_last, bool *ok) {
   constexpr int CAP = 1 << 15, DMAX = 4096, MAXLEN = 126;
   *ok = false;
   *d_ids = nullptr;
@@ -201,7 +212,7 @@ int32_t fe_col_stencils(fegpu_ctx *ctx, int64_t ncols, const int64_t *d_colptr, 
   if (ncols <= 0 || ncols >= ((int64_t)1 << 31)) return FEGPU_OK;
   unsigned long long *keys = nullptr;
   int32_t *rep = nullptr;
-  int *flags = nullptr;  // [0..2] flags, [3] dictionary size
+  int *flags = nullptr;  // [0..2] flags, [3] dictionary size, [4..5] first / last non-empty column
   auto drop = [&]() {
     if (keys) fe_dev_free(ctx, keys, stream);
     if (rep) fe_dev_free(ctx, rep, stream);
@@ -212,25 +223,26 @@ int32_t fe_col_stencils(fegpu_ctx *ctx, int64_t ncols, const int64_t *d_colptr, 
 #define ST_CUDA(x) do { if ((x) != cudaSuccess) return fail(fegpu_fail(ctx, FEGPU_ERR_CUDA, "column-stencil codec: CUDA call failed")); } while (0)
   ST_TRY(fe_dev_alloc(ctx, (void **)&keys, sizeof(unsigned long long) * CAP, stream));
   ST_TRY(fe_dev_alloc(ctx, (void **)&rep, sizeof(int32_t) * CAP, stream));
-  ST_TRY(fe_dev_alloc(ctx, (void **)&flags, sizeof(int) * 4, stream));
+  ST_TRY(fe_dev_alloc(ctx, (void **)&flags, sizeof(int) * 6, stream));
   ST_TRY(fe_dev_alloc(ctx, (void **)d_ids, sizeof(uint32_t) * (size_t)ncols, stream));
   ST_TRY(fe_dev_alloc(ctx, (void **)d_dict, sizeof(int32_t) * (size_t)DMAX * (2 + MAXLEN), stream));
   ST_CUDA(cudaMemsetAsync(keys, 0xff, sizeof(unsigned long long) * CAP, stream));
   ST_CUDA(cudaMemsetAsync(rep, 0x7f, sizeof(int32_t) * CAP, stream));
-  ST_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 4, stream));
+  ST_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 6, stream));
   const unsigned grid = grid_for(ncols * ST_LANES, 256);
   k_stencil_insert<<<grid, 256, 0, stream>>>(ncols, d_colptr, d_rowval, MAXLEN, CAP - 1, keys, rep, *d_ids, flags);
   k_stencil_verify<<<grid, 256, 0, stream>>>(ncols, d_colptr, d_rowval, rep, *d_ids, flags);
   k_stencil_dict<<<grid_for(CAP, 256), 256, 0, stream>>>(CAP, keys, rep, d_colptr, d_rowval, MAXLEN, DMAX, *d_dict, flags + 3);
-  ctx->launches += 3;
-  int h[4] = {0, 0, 0, 0};
+  k_col_range<<<1, 1, 0, stream>>>(ncols, d_colptr, flags + 4);
+  ctx->launches += 4;
+  int h[6] = {0, 0, 0, 0, 0, 0};
   ST_CUDA(cudaMemcpyAsync(h, flags, sizeof(h), cudaMemcpyDeviceToHost, stream));
   ST_CUDA(cudaStreamSynchronize(stream));
   ST_CUDA(cudaGetLastError());
 #undef ST_TRY
 #undef ST_CUDA
   drop();
-  if (h[0] || h[1] || h[2] || h[3] > DMAX || h[3] <= 0) {
+  if (h[0] || h[1] || h[2] || h[3] > DMAX || h[3] <= 0 || h[5] < h[4]) {
     fe_dev_free(ctx, *d_ids, stream);
     fe_dev_free(ctx, *d_dict, stream);
     *d_ids = nullptr;
@@ -238,6 +250,8 @@ int32_t fe_col_stencils(fegpu_ctx *ctx, int64_t ncols, const int64_t *d_colptr, 
     return FEGPU_OK;
   }
   *ndict = h[3];
+  *col_first = h[4];
+  *col_last = h[5];
   *maxlen_out = MAXLEN;
   *cap_out = CAP;
   *ok = true;

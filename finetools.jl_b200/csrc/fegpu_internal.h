@@ -258,7 +258,7 @@ const int64_t *fe_pattern_rowval(const Pattern *p);
 // compressed row structure for the transport (false when the pattern keeps none): per-node ascending neighbour lists + dof map
 // column-stencil codec of the result transport (fegpu_csc_ops.cu): one id per column + a dictionary of row-offset lists
 int32_t fe_col_stencils(fegpu_ctx *ctx, int64_t ncols, const int64_t *d_colptr, const int64_t *d_rowval, cudaStream_t stream, uint32_t **d_ids,
-                        int32_t **d_dict, int *ndict, int *maxlen, int *cap, bool *ok);
+                        int32_t **d_dict, int *ndict, int *maxlen, int *cap, int64_t *col_first, int64_t *col_last, bool *ok);
 bool fe_pattern_compressed(const Pattern *p, const int32_t **nbr, const int64_t **nbrptr, int64_t *total_nbr, const int32_t **dof, int *ndn,
                            int64_t *nnodes);
 bool fe_pattern_usable(const fegpu_dofmap *dm);  // mesh-structured fast path applicable?

@@ -207,15 +207,16 @@ void expand_rows(const int32_t *nbr, const int64_t *nbrptr, const int32_t *dof, 
 
 // Row indices of columns [c_lo, c_hi) from the column-stencil codec (fe_col_stencils, fegpu_csc_ops.cu): the rows of column c are
 // c + 1 + offsets of the dictionary entry its id names.  A decoder of what the device produced and verified column by column.
+// ids and colptr are the slices of the matrix's non-empty column window, which starts at column c0 (0-based).
 void expand_stencils(const uint32_t *ids, const int32_t *lut, const int32_t *dict, int stride, const int64_t *colptr, int64_t *rowval, int64_t c_lo,
-                     int64_t c_hi, bool avx2) {
+                     int64_t c_hi, int64_t c0, bool avx2) {
   int64_t rows[128];
   RowSink sink(avx2);
   for (int64_t c = c_lo; c < c_hi; c++) {
     const int32_t *d = dict + (size_t)lut[ids[c]] * stride;
     const int len = d[1];
     if (len == 0) continue;
-    const int64_t c1 = c + 1;
+    const int64_t c1 = c0 + c + 1;
     for (int k = 0; k < len; k++) rows[k] = c1 + d[2 + k];
     sink.put(rowval + (colptr[c] - 1), rows, (size_t)len);
   }
@@ -388,6 +389,7 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
   const int32_t *h_dict = nullptr;
   std::vector<int32_t> st_lut;
   int st_stride = 0, st_nd = 0;
+  int64_t st_c0 = 0, st_nc = 0;  // the matrix's non-empty column window [st_c0, st_c0 + st_nc): only its colptr and ids cross the link
   bool stencil = false;
   if (!compressed && rowval && nnz >= ((int64_t)1 << 20) && T->stencil && !as->view.active) {
     cudaEvent_t pr = as->pat_src ? fe_pattern_ready_event(as->pat_src) : nullptr;
@@ -396,11 +398,14 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
     uint32_t *d_ids = nullptr;
     int32_t *d_dict = nullptr;
     int nd = 0, maxlen = 0, cap = 0;
-    FE_TRY(fe_col_stencils(ctx, as->ncols, as->r_colptr(), as->r_rowval(), cs, &d_ids, &d_dict, &nd, &maxlen, &cap, &stencil));
+    int64_t cfirst = 0, clast = -1;
+    FE_TRY(fe_col_stencils(ctx, as->ncols, as->r_colptr(), as->r_rowval(), cs, &d_ids, &d_dict, &nd, &maxlen, &cap, &cfirst, &clast, &stencil));
     if (stencil) {
       st_stride = 2 + maxlen;
       st_nd = nd;
-      const size_t b_col = ((size_t)(as->ncols + 1) * 8 + 63) & ~(size_t)63, b_ids = ((size_t)as->ncols * 4 + 63) & ~(size_t)63;
+      st_c0 = cfirst;
+      st_nc = clast - cfirst + 1;
+      const size_t b_col = ((size_t)(st_nc + 1) * 8 + 63) & ~(size_t)63, b_ids = ((size_t)st_nc * 4 + 63) & ~(size_t)63;
       const size_t b_dict = ((size_t)nd * st_stride * 4 + 63) & ~(size_t)63;
       const size_t need = b_col + b_ids + b_dict;
       if (T->meta_cap < need) {
@@ -411,8 +416,8 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
       }
       char *hm = static_cast<char *>(T->h_meta);
       CUDA_TRY(ctx, cudaMemcpyAsync(hm + b_col + b_ids, d_dict, (size_t)nd * st_stride * 4, cudaMemcpyDeviceToHost, cs));
-      CUDA_TRY(ctx, cudaMemcpyAsync(hm, as->r_colptr(), (size_t)(as->ncols + 1) * 8, cudaMemcpyDeviceToHost, cs));
-      CUDA_TRY(ctx, cudaMemcpyAsync(hm + b_col, d_ids, (size_t)as->ncols * 4, cudaMemcpyDeviceToHost, cs));
+      CUDA_TRY(ctx, cudaMemcpyAsync(hm, as->r_colptr() + st_c0, (size_t)(st_nc + 1) * 8, cudaMemcpyDeviceToHost, cs));
+      CUDA_TRY(ctx, cudaMemcpyAsync(hm + b_col, d_ids + st_c0, (size_t)st_nc * 4, cudaMemcpyDeviceToHost, cs));
       CUDA_TRY(ctx, cudaEventRecord(T->meta_done, cs));
       fe_dev_free(ctx, d_ids, cs);
       fe_dev_free(ctx, d_dict, cs);
@@ -420,7 +425,7 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
       h_ids = reinterpret_cast<const uint32_t *>(hm + b_col);
       h_dict = reinterpret_cast<const int32_t *>(hm + b_col + b_ids);
       st_lut.assign((size_t)cap, 0);
-      c_nnodes = as->ncols;  // the slices below run over columns
+      c_nnodes = st_nc;  // the slices below run over the columns of the window
       c_total = nnz;
       T->stenciled++;
     }
@@ -439,8 +444,19 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
     *lo = cut(k); *hi = cut(k + 1);
   };
   auto expand_slice = [&](int64_t lo, int64_t hi) {
-    if (stencil) expand_stencils(h_ids, st_lut.data(), h_dict, st_stride, h_colptr, rowval, lo, hi, T->simd >= 1);
+    if (stencil) expand_stencils(h_ids, st_lut.data(), h_dict, st_stride, h_colptr, rowval, lo, hi, st_c0, T->simd >= 1);
     else expand_rows(h_nbr, h_nbrptr, h_dof, c_ndn, c_nnodes, h_colptr, rowval, lo, hi, T->simd >= 1);
+  };
+  // share `tid` of `nth` of the caller's colptr.  Column stencils: only the window's colptr crossed the link; ahead of it every
+  // column starts at 1, behind it at nnz + 1
+  auto fill_colptr = [&](int tid, int nth) {
+    const int64_t n = as->ncols + 1, per = (n + nth - 1) / nth, a = std::min(n, per * tid), b = std::min(n, a + per);
+    if (b <= a) return;
+    if (!stencil) { std::memcpy(colptr + a, h_colptr + a, (size_t)(b - a) * 8); return; }
+    for (int64_t c = a; c < std::min(b, st_c0); c++) colptr[c] = 1;
+    const int64_t wa = std::max(a, st_c0), wb = std::min(b, st_c0 + st_nc + 1);
+    if (wb > wa) std::memcpy(colptr + wa, h_colptr + (wa - st_c0), (size_t)(wb - wa) * 8);
+    for (int64_t c = std::max(a, st_c0 + st_nc + 1); c < b; c++) colptr[c] = nnz + 1;
   };
   auto meta_arrived = [&]() -> int32_t {  // the host may read the metadata from here on
     CUDA_TRY(ctx, cudaEventSynchronize(T->meta_done));
@@ -496,16 +512,13 @@ int32_t fe_copy_result(fegpu_asm *as, int64_t *colptr, int64_t *rowval, double *
         int64_t lo, hi;
         node_slice(tid, nth, &lo, &hi);
         expand_slice(lo, hi);
-        if (colptr) {  // the caller's colptr: each thread copies its share
-          const int64_t n = as->ncols + 1, per = (n + nth - 1) / nth, a = std::min(n, per * tid), b = std::min(n, a + per);
-          if (b > a) std::memcpy(colptr + a, h_colptr + a, (size_t)(b - a) * 8);
-        }
+        if (colptr) fill_colptr(tid, nth);  // the caller's colptr: each thread writes its share
       };
       T->pool->run(expand_all);
       exp_done = exp_total;
     } else {
       FE_TRY(meta_arrived());
-      if (colptr) std::memcpy(colptr, h_colptr, (size_t)(as->ncols + 1) * 8);
+      if (colptr) fill_colptr(0, 1);
     }
   }
 

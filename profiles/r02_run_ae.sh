@@ -1,0 +1,7 @@
+#!/bin/bash
+# round 2, GPU call AE (8 GPUs): A/B of the column-stencil transport at N = 8 on one box (e2e is host-bound there)
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+for st in 0 1 0 1; do
+  FEGPU_XFER_STENCIL=$st timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2956$st bench.py --gpus 8 --steps 10 --warmup 3 --no-secondary >> gpurun_out/ae_bench_n8_stencil$st.jsonl 2>> gpurun_out/ae_bench_n8_stencil$st.err; echo "stencil $st rc=$?"
+done
