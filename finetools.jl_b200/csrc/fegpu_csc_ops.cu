@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(256) k_stencil_insert(int64_t ncols, const int
 #pragma unroll
   for (int d = 1; d < ST_LANES; d <<= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
   if (!live || gl != 0) return;
+  if (*reinterpret_cast<volatile int *>(flags + 1)) { ids[c] = 0; return; }  // the table is already known to be too crowded: no dictionary
   if (len > maxlen) { flags[0] = 1; ids[c] = 0; return; }
   h = st_mix(h + (unsigned long long)len * 0x2545f4914f6cdd1dull);
   if (h == ST_EMPTY) h = 0;
