@@ -1435,6 +1435,7 @@ int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_n
   const int64_t per_block = (int64_t)GWPB * npw;
   // persistent launch: exactly the CTAs that are resident at once (occupancy x SMs), so there is no partial last wave
   static const int waves_env = std::getenv("FEGPU_GATHER_WAVES") ? std::atoi(std::getenv("FEGPU_GATHER_WAVES")) : 0;
+  static const int gen_carveout = std::getenv("FEGPU_GATHER_GEN_CARVEOUT") ? std::atoi(std::getenv("FEGPU_GATHER_GEN_CARVEOUT")) : 85;  // measured: H20 96^3 gather 12.7 -> 10.9 ms at 85 % (and at 70 %), T10 unchanged; -1 = the driver's choice
   const int64_t need_blocks = std::max<int64_t>(1, (G.npos + per_block - 1) / per_block);
   unsigned grid = 1;
 #define LG5(L, N, C, B, R)                                                                                                          \
@@ -1442,6 +1443,11 @@ int32_t fe_gather(fegpu_dofmap *dm, const double *d_V, bool compact, double *d_n
     if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k_gather<L, N, C, B, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     int occ = 0;                                                                                                                    \
     CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gather<L, N, C, B, R>, GWPB * 32, smem));                   \
+    if (gen_carveout > 0 && smem + 1024 <= (size_t)gen_carveout * 228 * 1024 / 100) {                                               \
+      /* leave L1 for the lines in flight (see fe_tile_gather): fewer resident CTAs, sized from the carve-out */                    \
+      CUDA_TRY(ctx, cudaFuncSetAttribute(k_gather<L, N, C, B, R>, cudaFuncAttributePreferredSharedMemoryCarveout, gen_carveout));   \
+      occ = std::min<int>(occ, (int)(((size_t)gen_carveout * 228 * 1024 / 100) / (smem + 1024)));                                   \
+    }                                                                                                                               \
     grid = (unsigned)std::min<int64_t>(need_blocks, (int64_t)ctx->sm_count * std::max(occ, 1) * (waves_env > 0 ? waves_env : 1)); \
     k_gather<L, N, C, B, R><<<grid, GWPB * 32, smem, ctx->stream>>>(G);                                                             \
   } while (0)
