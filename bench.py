@@ -523,9 +523,28 @@ def run_gpu(args):
             ctx.synchronize()
             ph = a.timings()
             ctx.set_overlap(True)
-            nnz = allsum_int(a.sizes()[2])
+            nnz_rank = a.sizes()[2]
+            nnz = allsum_int(nnz_rank)
             out[name] = {"elements": fes.count(), "nnz": nnz, "fresh_ms": ms_f, "cached_ms": ms_c, "fresh_elements_per_s": fes.count() / (ms_f * 1e-3),
                          "cached_elements_per_s": fes.count() / (ms_c * 1e-3), "phases_ms_rank0": ph}
+            if form == "elastic":
+                # rank 0's kernels against their rooflines: the gather reads the compact element records (nne (nne + 1) / 2 blocks of
+                # 9 doubles) once and writes nzval; k_elastic_tiled executes (H20, 27 points) 27 x (385 geometry + 30 tiles x 72 DFMA) FMA
+                # + 210 x 32 for the blocks with the outer-product formulation of an isotropic C, 27 x (1465 + 30 x 216) FMA for a general
+                # one; the reference's own loop count is 812 430 flop per element
+                nact0 = dmesh.window()[2]
+                nne = fes.conn.shape[1]
+                b_g = nact0 * (nne * (nne + 1) // 2) * 9 * 8 + nnz_rank * 8
+                iso_path = os.environ.get("FEGPU_ELASTIC_ISO", "1") != "0"
+                fl = (27 * (385 + 30 * 72) * 2 + 210 * 32) if iso_path else 27 * (1465 + 30 * 216) * 2
+                pk = ctx.measure_peaks()
+                out[name]["rank0_kernels"] = {
+                    "k_gather": {"ms": ph["numeric_ms"], "algorithmic_bytes": b_g, "algorithmic_GBps": b_g / (ph["numeric_ms"] * 1e-3) / 1e9,
+                                 "frac_hbm": b_g / (ph["numeric_ms"] * 1e-3) / 1e9 / hbm_peak},
+                    "k_elastic_tiled": {"ms": ph["integrate_ms"], "path": "outer products (cubic-symmetry D)" if iso_path else "general D",
+                                        "executed_TFLOPs": fl * nact0 / (ph["integrate_ms"] * 1e-3) / 1e12,
+                                        "frac_fp64_executed": fl * nact0 / (ph["integrate_ms"] * 1e-3) / 1e12 / pk["dfma_tflops"],
+                                        "reference_count_TFLOPs": 812430 * nact0 / (ph["integrate_ms"] * 1e-3) / 1e12}}
             a = None
             ctx.release_meshes()
             ctx.release_cache()
