@@ -275,3 +275,46 @@ def test_bench_gpu_arm_refuses_to_run_without_a_device():
     assert out.returncode != 0
     assert "no CPU fallback" in (out.stderr + out.stdout)
     assert not [ln for ln in out.stdout.splitlines() if ln.strip().startswith("{")]
+
+
+def test_gather_loads_are_spread_over_scoreboards():
+    """Static guard for the finding of profiles/r02_scoreboards.txt: in the default instantiations of k_gather_tile (H8, scalar and
+    3-dof, value planes, MODE 1) ptxas must not put (nearly) all global loads on one scoreboard -- if it does, the first add of an
+    element waits for the loads of the next one and the software pipeline overlaps nothing.  Read from the SASS control codes of the
+    in-tree object (cuobjdump; skipped when the object or the tool is missing)."""
+    import shutil
+    import subprocess
+    from collections import Counter
+    obj = os.path.join(ROOT, "finetools.jl_b200", "csrc", "fegpu_tile.o")
+    if not os.path.exists(obj) or not shutil.which("cuobjdump"):
+        pytest.skip("needs the built object and cuobjdump")
+    txt = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    funcs, cur = {}, None
+    for line in txt.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = []
+        elif cur:
+            funcs[cur].append(line)
+    checked = 0
+    for name, lines in funcs.items():
+        if not re.search(r"k_gather_tileILi8ELi8ELi[13]ELb1ELb1ELi1E", name):
+            continue
+        wb = Counter()
+        i = 0
+        while i + 1 < len(lines):
+            m = re.match(r"\s+/\*[0-9a-f]{4,5}\*/\s+(.*?);\s+/\* (0x[0-9a-f]+) \*/", lines[i])
+            m2 = re.match(r"\s+/\* (0x[0-9a-f]+) \*/", lines[i + 1])
+            if m and m2:
+                if re.match(r"(@!?U?P[0-9T]+ )?LDG", m.group(1).strip()):
+                    wb[((int(m2.group(1), 16) >> 41) >> 5) & 7] += 1   # write-barrier index of the control code
+                i += 2
+            else:
+                i += 1
+        total = sum(wb.values())
+        assert total >= 60, (name, wb)
+        # the pathological build had 207 of 214 loads (97 %) on one scoreboard; the measured-best one has at most 62 %
+        assert max(wb.values()) <= 0.75 * total and len(wb) >= 3, "loads crowd one scoreboard: %r" % (wb,)
+        checked += 1
+    assert checked == 2
