@@ -403,22 +403,20 @@ __device__ __forceinline__ double ld_value(const double *p) {
 // is odd for the 27-neighbour interior stencil.
 // MODE (how the value loads of element j + 1 overlap the shared-memory adds of element j; measured in profiles/r02_gather_modes.txt):
 //   0  loads of j + 1 issued, then the adds of j.  ptxas gives every load of this branchy body ONE scoreboard (profiles/
-//      r02_scoreboards.txt), so the first add of j also waits for the loads of j + 1 that were just issued: nothing overlaps
+//      r02_scoreboards.txt), so the first add of j also waits for the loads of j + 1 that were just issued: nothing overlaps.
+//      The 16-plane kernels (Q4, T3, T4: few of the 16 planes are occupied) keep this form.
 //   1  straight-line body (no branch: missing elements re-read element 0, rows of other ranks go to a dummy cell) with warp-level
-//      fences between the load batches and the add batches
-//   2  branchy body, but the first add of j (which waits for the scoreboard) comes BEFORE the loads of j + 1 are issued, the other
-//      adds after: the shared scoreboard only ever covers one batch when it is waited for
-//   3  mode 2 + L2 prefetches two elements ahead (prefetch.global.L2: no register, no scoreboard)
+//      fences between the load batches and the add batches -- the default for H8
 //   4  straight-line body without fences (ptxas interleaves single loads with the adds, rotating over four scoreboards)
-//   5  mode 0 + L2 prefetches;   6  mode 4 + L2 prefetches
+// (Modes 2, 3, 5, 6 of the measurements -- first add before the next loads, L2 prefetches two elements ahead -- were removed after
+// they lost; the code is in the history of this file.)
 template <int NNE, int MAXDEG, int NDN, bool COMPACT, bool PLANES, int MODE>
 __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileGatherParams<NNE> G) {
   extern __shared__ double acc[];
   constexpr int T = GatherShape<NDN>::T, NPB = GatherShape<NDN>::NPB, ND2 = NDN * NDN;
   constexpr int EM = NNE * NDN;
   constexpr int64_t VPE = COMPACT ? (int64_t)(NNE * (NNE + 1) / 2) * ND2 : (int64_t)EM * EM;
-  constexpr bool STRAIGHT = (MODE == 1 || MODE == 4 || MODE == 6);
-  constexpr bool PREFETCH = (MODE == 3 || MODE == 5 || MODE == 6);
+  constexpr bool STRAIGHT = (MODE == 1 || MODE == 4);
   using CsT = typename CsWord<NNE>::type;
   const int tid = threadIdx.x;
   // element-major records: the NDN threads of a node are neighbours (they read one contiguous block); planes: component-major, the
@@ -489,12 +487,6 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
 #pragma unroll
         for (int p = 0; p < NDN; p++) v[li][p] = (MODE == 1) ? ld_value(value_ptr(j, li, p)) : *value_ptr(j, li, p);  // plain ld.global: the .nc path measured 0.7 ms slower
     };
-    auto prefetch_vals = [&](int j) {
-#pragma unroll
-      for (int li = 0; li < NNE; li++)
-#pragma unroll
-        for (int p = 0; p < NDN; p++) asm volatile("prefetch.global.L2 [%0];" ::"l"(value_ptr(j, li, p)));
-    };
     auto add_vals = [&](int j, const double (&v)[NNE][NDN], int li0, int li1) {
 #pragma unroll
       for (int li = 0; li < NNE; li++) {
@@ -513,8 +505,6 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
     };
     double va[NNE][NDN], vb[NNE][NDN];
     load_vals(0, va);  // deg >= 1 here (nu > 0)
-    if (PREFETCH && (STRAIGHT || 1 < deg)) prefetch_vals(1);
-    if (PREFETCH && (STRAIGHT || 2 < deg)) prefetch_vals(2);
 #pragma unroll
     for (int j = 0; j < MAXDEG; j += 2) {
       if (MODE == 1) {
@@ -527,26 +517,13 @@ __global__ void __launch_bounds__(GatherShape<NDN>::T) k_gather_tile(const TileG
         add_vals(j + 1, vb, 0, NNE);
         __syncwarp(wmask);
       } else if (STRAIGHT) {
-        if (PREFETCH && j + 3 < MAXDEG) prefetch_vals(j + 3);
         load_vals(j + 1, vb);
         add_vals(j, va, 0, NNE);
-        if (PREFETCH && j + 4 < MAXDEG) prefetch_vals(j + 4);
         if (j + 2 < MAXDEG) load_vals(j + 2, va);
         add_vals(j + 1, vb, 0, NNE);
-      } else if (MODE == 2 || MODE == 3) {
-        if (j < deg) add_vals(j, va, 0, 1);  // waits for the values of j; nothing else is in flight
-        if (j + 1 < deg) load_vals(j + 1, vb);
-        if (PREFETCH && j + 3 < deg && j + 3 < MAXDEG) prefetch_vals(j + 3);
-        if (j < deg) add_vals(j, va, 1, NNE);
-        if (j + 1 < deg) add_vals(j + 1, vb, 0, 1);
-        if (j + 2 < deg && j + 2 < MAXDEG) load_vals(j + 2, va);
-        if (PREFETCH && j + 4 < deg && j + 4 < MAXDEG) prefetch_vals(j + 4);
-        if (j + 1 < deg) add_vals(j + 1, vb, 1, NNE);
       } else {
-        if (PREFETCH && j + 3 < deg && j + 3 < MAXDEG) prefetch_vals(j + 3);
         if (j + 1 < deg) load_vals(j + 1, vb);
         if (j < deg) add_vals(j, va, 0, NNE);
-        if (PREFETCH && j + 4 < deg && j + 4 < MAXDEG) prefetch_vals(j + 4);
         if (j + 2 < deg && j + 2 < MAXDEG) load_vals(j + 2, va);
         if (j + 1 < deg) add_vals(j + 1, vb, 0, NNE);
       }
@@ -814,7 +791,7 @@ int32_t fe_tile_gather(fegpu_dofmap *dm, const double *d_V, bool compact, bool p
   static const int carveout_env = std::getenv("FEGPU_GATHER_CARVEOUT") ? std::atoi(std::getenv("FEGPU_GATHER_CARVEOUT")) : 85;
   const int carveout = (smem + 1024 > (size_t)carveout_env * 228 * 1024 / 100) ? -1 : carveout_env;  // one CTA must still fit
   static const int gmode_env = std::getenv("FEGPU_GATHER_MODE") ? std::atoi(std::getenv("FEGPU_GATHER_MODE")) : 1;  // A/B knob
-  const int gmode = (nne == 8 && gmode_env >= 0 && gmode_env <= 6) ? gmode_env : 0;  // the variants exist for H8 only
+  const int gmode = (nne == 8 && (gmode_env == 0 || gmode_env == 1 || gmode_env == 4)) ? gmode_env : 0;  // the variants exist for H8 only
 #define G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, M_)                                                                                    \
   do {                                                                                                                              \
     TileGatherParams<NNE_> G{P->tile_lo, P->tile_nw, P->tile_nwp, mesh->nnodes, P->t_deg, P->t_adj,                                 \
@@ -828,11 +805,7 @@ int32_t fe_tile_gather(fegpu_dofmap *dm, const double *d_V, bool compact, bool p
     if constexpr (NNE_ == 8) {                                     \
       switch (gmode) {                                             \
         case 1: G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, 1); break;    \
-        case 2: G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, 2); break;    \
-        case 3: G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, 3); break;    \
         case 4: G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, 4); break;    \
-        case 5: G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, 5); break;    \
-        case 6: G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, 6); break;    \
         default: G_LAUNCH_M(NNE_, MD_, NDN_, C_, PL_, 0); break;   \
       }                                                            \
     } else {                                                       \
