@@ -450,3 +450,43 @@ def test_assembler_rectangular_blocks_golden_matrix(orc):
     assert np.abs(G - A).max() < 1.0e-5
     # the three entries hit by both blocks are sums in assembly order: (1,4), (5,4), (7,4)
     assert A[0, 3] == 0.0420141 + 0.00919633 and A[4, 3] == 0.224996 + 0.958909 and A[6, 3] == 0.780298 + 0.77646
+
+
+def test_cubic_symmetry_identity_of_the_elasticity_kernels(orc, fe):
+    """The GPU elasticity kernels integrate a material matrix of the cubic-symmetry form (isotropic: MatDeforElastIso) through
+    B_a(:,i)' D B_b(:,j) = lam g_a,i g_b,j + mu g_a,j g_b,i (i != j),  D00 g_a,i g_b,i + mu sum_{k != i} g_a,k g_b,k (i == j)
+    (csrc/fegpu_h8.cu: outer_acc / iso_block).  Checked here on the CPU against the oracle's literal B' D B loop
+    (FEMMBaseModule.jl:1774-1813, DeforModelRedModule.jl:463-468) for one distorted H8 element, isotropic and cubic D."""
+    rng = np.random.default_rng(3)
+    fens, fes = fe.H8block(1.0, 1.3, 0.7, 1, 1, 1)
+    xyz = fens.xyz + 0.08 * rng.standard_normal(fens.xyz.shape)
+    rule = fe.GaussRule(3, 2)
+    u = fe.NodalField(np.zeros((8, 3)))
+    fe.numberdofs(u)
+    for cubic in (False, True):
+        lam, mu, d00 = 0.9, 0.55, 0.9 + 2 * 0.55
+        if cubic:
+            d00, mu = 2.7, 0.31
+        D = np.zeros((6, 6))
+        D[:3, :3] = lam
+        D[np.arange(3), np.arange(3)] = d00
+        D[3:, 3:] = mu * np.eye(3)
+        I, J, V = orc.bilform_lin_elastic_coo("H8", fes.conn, xyz, u.dofnums, 24, rule.param_coords, rule.weights, D)
+        K_ref = np.zeros((24, 24))
+        np.add.at(K_ref, (I - 1, J - 1), V)
+        K = np.zeros((24, 24))
+        conn = fes.conn[0] - 1
+        for pc, w in zip(rule.param_coords, rule.weights):
+            dNpar = np.asarray(orc.bfundpar("H8", pc)).reshape(8, 3)
+            Jm = xyz[conn].T @ dNpar                      # J[s, d] = sum_a x[a, s] dN[a, d]
+            g = dNpar @ np.linalg.inv(Jm)                 # gradN! (FESetModule.jl:507-544)
+            Jw = np.linalg.det(Jm) * w
+            for a in range(8):
+                for b in range(8):
+                    P = Jw * np.outer(g[a], g[b])         # P[i, j] = Jw g_a,i g_b,j
+                    blk = lam * P + mu * P.T
+                    tr = np.trace(P)
+                    for i in range(3):
+                        blk[i, i] = d00 * P[i, i] + mu * (tr - P[i, i])
+                    K[np.ix_(u.dofnums[conn[a]] - 1, u.dofnums[conn[b]] - 1)] += blk
+        assert np.abs(K - K_ref).max() <= 1e-13 * np.abs(K_ref).max()
