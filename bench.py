@@ -580,7 +580,10 @@ def run_gpu(args):
         roofline = {"bound": "hbm", "achieved": dom["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["frac"],
                     "traffic": tr, "algorithmic_bytes_per_launch": dom["algorithmic_bytes"]}
     else:  # the FP64 integration kernel: both terms of the north star's roofline
-        roofline = {"bound": "fp64", "achieved": dom["executed_TFLOPs"], "peak": dom["dfma_peak_TFLOPs_measured_here"], "unit": "TFLOP/s",
+        roofline = {"bound": "fp64", "peak_source": "DFMA micro-benchmark (fegpu_measure_peaks: k_dfma_peak, dependent-free FMA chains on every SM) run "
+                                                    "on this GPU in this process: MEASURED_PEAKS.json carries HBM and bf16 tensor peaks only, and this "
+                                                    "kernel is FP64 CUDA-core work (8-36 wide contractions: no tensor-core shape)",
+                    "achieved": dom["executed_TFLOPs"], "peak": dom["dfma_peak_TFLOPs_measured_here"], "unit": "TFLOP/s",
                     "frac": dom["frac_fp64_executed"], "traffic": tr, "hbm_GBps": dom["algorithmic_GBps"]}
     roofline.update({"kernel": dom_name, "peak_kind": r4["peaks"]["hbm_kind"], "traffic_source": traffic.get("source") if tr else None,
                      "kernels": r4["kernels"], "copy_gbs_measured_here": r4["peaks"]["copy_gbs_measured_here"],
